@@ -1,0 +1,1449 @@
+/*
+ * pprts_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY, see pprts_oracle.h for the contract and pinning status).
+ *
+ * fp64 restatement of the reference's PETSc-free pprts path.  Array layouts are the reference's own
+ * (dof fastest, then z, x, y; Fortran column-major) so that every loop can be read next to the Fortran it follows.
+ */
+#define _GNU_SOURCE
+#include "pprts_oracle.h"
+
+#include <fcntl.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_PI 3.14159265358979323846
+
+static double dmin(double a, double b) { return a < b ? a : b; }
+static double dmax(double a, double b) { return a > b ? a : b; }
+
+/* ================================================================================================================
+ * search / interpolation
+ * ================================================================================================================ */
+
+/* src/search.fypp:177-232 (search_sorted_bisection): 1-based "real-numbered" location of val in a sorted array. */
+double orc_search_sorted_bisection(const double *arr, int n, double val) {
+  int i = 1, j = n, k;
+  double inc;
+#define A_(x) arr[(x)-1]
+  if (A_(i) <= A_(j)) { /* ascending */
+    for (;;) {
+      k = (i + j) / 2;
+      if (val < A_(k)) j = k; else i = k;
+      if (i + 1 >= j) {
+        inc = (i == j) ? 0.0 : (val - A_(i)) / (A_(j) - A_(i));
+        return dmin(dmax(1.0, (double)i + inc), (double)n);
+      }
+    }
+  } else { /* descending */
+    for (;;) {
+      k = (i + j) / 2;
+      if (val > A_(k)) j = k; else i = k;
+      if (i + 1 >= j) {
+        inc = (i == j) ? 0.0 : (val - A_(j)) / (A_(i) - A_(j));
+        return dmin(dmax(1.0, (double)j - inc), (double)n);
+      }
+    }
+  }
+#undef A_
+}
+
+/* Same algorithm on an fp32 axis with an fp32 sample value (find_real_location as called from
+ * src/optprop_LUT.F90:1470-1472), arithmetic carried out in fp64. */
+double orc_find_real_location_f32axis(const float *arr, int n, float val) {
+  int i = 1, j = n, k;
+  double inc, v = (double)val;
+#define A_(x) ((double)arr[(x)-1])
+  if (A_(i) <= A_(j)) {
+    for (;;) {
+      k = (i + j) / 2;
+      if (v < A_(k)) j = k; else i = k;
+      if (i + 1 >= j) {
+        inc = (i == j) ? 0.0 : (v - A_(i)) / (A_(j) - A_(i));
+        return dmin(dmax(1.0, (double)i + inc), (double)n);
+      }
+    }
+  } else {
+    for (;;) {
+      k = (i + j) / 2;
+      if (v > A_(k)) j = k; else i = k;
+      if (i + 1 >= j) {
+        inc = (i == j) ? 0.0 : (v - A_(j)) / (A_(i) - A_(j));
+        return dmin(dmax(1.0, (double)j - inc), (double)n);
+      }
+    }
+  }
+#undef A_
+}
+
+/* src/interpolation.F90:63 and :546-556.  interpolation_lattice_snapping = max(1e-3_irealLUT, epsilon) */
+static const double ORC_SNAP = (double)1e-3f;
+int orc_dim_needs_interpolation(double pti) {
+  double frac = pti - (double)(long)pti;
+  if (frac < ORC_SNAP) return 0;
+  if (frac > 1.0 - ORC_SNAP) return 0;
+  return 1;
+}
+
+/* src/interpolation.F90:317-360 (interp_vec_bilinear_iterative). pti are 1-based fractional indices,
+ * db is [lattice][coef] (Fortran db(:, ofs)), offsets as ndarray_offsets. */
+void orc_interp_vec_nd(const double *pti, int ndim, const float *db, int ncoef, const long *offsets, double *out) {
+  long ioff_lo[ORC_MAX_DIM], ioff_hi[ORC_MAX_DIM], ofs_base = 1, ofs;
+  double wlo[ORC_MAX_DIM], whi[ORC_MAX_DIM], w;
+  int Ninterp = 0, d, c;
+  long b;
+  for (d = 0; d < ndim; ++d) {
+    if (orc_dim_needs_interpolation(pti[d])) {
+      b = (long)pti[d];
+      whi[Ninterp] = pti[d] - (double)b;
+      wlo[Ninterp] = 1.0 - whi[Ninterp];
+      ioff_lo[Ninterp] = offsets[d] * (b - 1);
+      ioff_hi[Ninterp] = offsets[d] * b;
+      ++Ninterp;
+    } else {
+      ofs_base += offsets[d] * (lround(pti[d]) - 1);
+    }
+  }
+  for (c = 0; c < ncoef; ++c) out[c] = 0.0;
+  for (b = 0; b < (1L << Ninterp); ++b) {
+    ofs = ofs_base;
+    w = 1.0;
+    for (d = 0; d < Ninterp; ++d) {
+      if (b & (1L << d)) { ofs += ioff_hi[d]; w = w * whi[d]; }
+      else               { ofs += ioff_lo[d]; w = w * wlo[d]; }
+    }
+    const float *col = db + (ofs - 1) * (long)ncoef;
+    for (c = 0; c < ncoef; ++c) out[c] = fma(w, (double)col[c], out[c]);
+  }
+}
+
+/* ================================================================================================================
+ * closed-form per-cell scalars
+ * ================================================================================================================ */
+
+static int approx_d(double a, double b) { /* helper_functions.fypp:1272-1287, default precision 10*epsilon */
+  double f = 10.0 * DBL_EPSILON;
+  return (a <= b + f) && (a >= b - f);
+}
+
+/* src/eddington.F90:167-242 (eddington_coeff_ec); irealeddington = real64 (src/data_parameters.F90:100) */
+void orc_eddington_coeff_ec(double dtau, double w0, double g, double mu0, double *t, double *r, double *rdir,
+                            double *sdir, double *tdir) {
+  double f, g1, g2, g3, g4, alpha1, alpha2, A, beta, e0, e, e2, k_mu0, k_g3, k_g4, k_2_e, dtau_slant;
+  f = 0.75 * g;
+  g1 = 2.0 - w0 * (1.25 + f);
+  g2 = w0 * (0.75 - f);
+  g3 = 0.5 - mu0 * f;
+  dtau_slant = dmax(dtau / dmax(sqrt(DBL_MIN), mu0), 0.0);
+  if (dtau_slant > 1e-6) {
+    g4 = 1.0 - g3;
+    alpha1 = g1 * g4 + g2 * g3;
+    alpha2 = g1 * g3 + g2 * g4;
+    A = sqrt(dmax((g1 - g2) * (g1 + g2), 1e-12));
+    k_mu0 = A * mu0;
+    k_g3 = A * g3;
+    k_g4 = A * g4;
+    e0 = exp(-dtau_slant);
+    *tdir = e0;
+    e = exp(-A * dtau);
+    e2 = e * e;
+    k_2_e = 2 * A * e;
+    if (approx_d(k_mu0, 1.0)) k_mu0 = 1 - 10 * DBL_EPSILON;
+    beta = 1 / (A + g1 + (A - g1) * e2);
+    *r = g2 * (1 - e2) * beta;
+    *t = k_2_e * beta;
+    beta = w0 * beta / (1 - k_mu0 * k_mu0);
+    *sdir = beta * (k_2_e * (g4 + alpha1 * mu0) - e0 * ((1 + k_mu0) * (alpha1 + k_g4) - (1 - k_mu0) * (alpha1 - k_g4) * e2));
+    *rdir = beta * ((1 - k_mu0) * (alpha2 + k_g3) - (1 + k_mu0) * (alpha2 - k_g3) * e2 - k_2_e * (g3 - alpha2 * mu0) * e0);
+  } else {
+    *t = 1.0 - g1 * dtau;
+    *r = g2 * dtau;
+    *sdir = (1.0 - g3) * (w0 * dtau);
+    *rdir = g3 * (w0 * dtau);
+    *tdir = 1.0 - dtau_slant;
+  }
+}
+
+/* src/schwarzschild.F90:36-67 (B_eff): 2-point Gauss-Legendre on (0,1) (dgauss, :173-303, m = 2) */
+static double B_eff_mu(double B_far, double B_near, double tau, double mu) {
+  double dtau = tau / mu, tm1;
+  if (dtau < 1e-3) return (B_far + B_near) * .5;
+  tm1 = expm1(-dtau);
+  return (-B_near + B_far * (tm1 + 1)) / tm1 + ((B_far - B_near) * mu) / tau;
+}
+double orc_B_eff(double B_far, double B_near, double tau) {
+  static const double pt[2] = {0.21132486540518713, 0.78867513459481287};
+  static const double wi[2] = {0.5, 0.5};
+  double B = 0;
+  int imu;
+  for (imu = 0; imu < 2; ++imu) B = B + B_eff_mu(B_far, B_near, tau, pt[imu]) * pt[imu] * wi[imu];
+  return B * 2;
+}
+
+/* src/helper_functions.fypp:1622-1666 (delta_scale with f = g**2, delta_scale_optprop) */
+void orc_delta_scale(double *kabs, double *ksca, double *g) {
+  double f = (*g) * (*g), dtau = *kabs + *ksca, w0;
+  if (dtau < DBL_EPSILON) return;
+  w0 = *ksca / dtau;
+  if (*g >= 1.0 - DBL_EPSILON * 10) {
+    dtau = dtau * (1.0 - w0);
+    w0 = 0;
+    *g = 0;
+  } else {
+    dtau = dtau * (1.0 - w0 * f);
+    *g = (*g - f) / (1.0 - f);
+    w0 = w0 * (1.0 - f) / (1.0 - f * w0);
+  }
+  *kabs = dtau * (1.0 - w0);
+  *ksca = dtau * w0;
+}
+
+/* ================================================================================================================
+ * stream tables and symmetry permutations
+ * ================================================================================================================ */
+
+/* src/pprts.F90:332-396 */
+int orc_streams_init(orc_streams *st, int solver_id) {
+  int i;
+  memset(st, 0, sizeof(*st));
+  st->solver_id = solver_id;
+  st->dirtop_adiv = 1;
+  st->dirside_adiv = 1;
+  switch (solver_id) {
+  case 310:
+    st->Ndt = 1; st->Nds = 1; st->Nft = 2; st->Nfs = 4;
+    st->ft_inward[0] = 0; st->ft_inward[1] = 1;
+    for (i = 0; i < 4; ++i) st->fs_inward[i] = i % 2; /* [F,T,F,T] */
+    break;
+  case 810:
+    st->Ndt = 4; st->Nds = 2; st->Nft = 2; st->Nfs = 4;
+    st->dirtop_adiv = 4; st->dirside_adiv = 2;
+    st->ft_inward[0] = 0; st->ft_inward[1] = 1;
+    for (i = 0; i < 4; ++i) st->fs_inward[i] = i % 2;
+    break;
+  case 324:
+    st->Ndt = 1; st->Nds = 1; st->Nft = 8; st->Nfs = 8;
+    for (i = 0; i < 8; ++i) st->ft_inward[i] = i % 2;       /* [F,T]x4 */
+    for (i = 0; i < 8; ++i) st->fs_inward[i] = (i + 1) % 2; /* [T,F]x4 */
+    break;
+  default:
+    return 1;
+  }
+  st->Nd = st->Ndt + 2 * st->Nds;
+  st->Nf = st->Nft + 2 * st->Nfs;
+  return 0;
+}
+
+/* dir2diff permutations: src/optprop.F90:1009-1045 (3->10), :1098-1124 (3->24), :1148-1184 (8->10).
+ * c is coeff(dst*Nd + src), 0-based; the Fortran block index is dst+1. */
+static void copy_block(double *c, const double *bak, int Nd, int dst_new, int dst_old, const int *srcperm) {
+  int s;
+  for (s = 0; s < Nd; ++s) c[dst_new * Nd + s] = bak[dst_old * Nd + (srcperm ? srcperm[s] : s)];
+}
+void orc_dir2diff_symmetry(const orc_streams *st, double *c, int le, int ln) {
+  double bak[ORC_MAX_DOF * ORC_MAX_DOF];
+  int Nd = st->Nd, n = st->Nd * st->Nf, k;
+  if (st->solver_id == 310) {
+    if (le) { memcpy(bak, c, n * sizeof(double)); copy_block(c, bak, Nd, 2, 3, 0); copy_block(c, bak, Nd, 3, 2, 0);
+              copy_block(c, bak, Nd, 4, 5, 0); copy_block(c, bak, Nd, 5, 4, 0); }
+    if (ln) { memcpy(bak, c, n * sizeof(double)); copy_block(c, bak, Nd, 6, 7, 0); copy_block(c, bak, Nd, 7, 6, 0);
+              copy_block(c, bak, Nd, 8, 9, 0); copy_block(c, bak, Nd, 9, 8, 0); }
+  } else if (st->solver_id == 810) {
+    static const int pe[8] = {1, 0, 3, 2, 4, 5, 6, 7}, pn[8] = {2, 3, 0, 1, 4, 5, 6, 7};
+    if (le) { memcpy(bak, c, n * sizeof(double)); copy_block(c, bak, Nd, 2, 3, pe); copy_block(c, bak, Nd, 3, 2, pe);
+              copy_block(c, bak, Nd, 4, 5, pe); copy_block(c, bak, Nd, 5, 4, pe); }
+    if (ln) { memcpy(bak, c, n * sizeof(double)); copy_block(c, bak, Nd, 6, 7, pn); copy_block(c, bak, Nd, 7, 6, pn);
+              copy_block(c, bak, Nd, 8, 9, pn); copy_block(c, bak, Nd, 9, 8, pn); }
+  } else if (st->solver_id == 324) {
+    /* pC(src, dst), 1-based dst lists from the Fortran, written 0-based here */
+    static const int e_new[8] = {0, 2, 4, 6, 1, 3, 5, 7}, e_old[8] = {2, 0, 6, 4, 3, 1, 7, 5};
+    static const int n_new[8] = {0, 2, 4, 6, 1, 3, 5, 7}, n_old[8] = {4, 6, 0, 2, 5, 7, 1, 3};
+    if (le) {
+      memcpy(bak, c, n * sizeof(double));
+      for (k = 0; k < 8; ++k) copy_block(c, bak, Nd, e_new[k], e_old[k], 0);
+      for (k = 0; k < 4; ++k) { copy_block(c, bak, Nd, 9 + 2 * k, 8 + 2 * k, 0); copy_block(c, bak, Nd, 8 + 2 * k, 9 + 2 * k, 0); }
+    }
+    if (ln) {
+      memcpy(bak, c, n * sizeof(double));
+      for (k = 0; k < 8; ++k) copy_block(c, bak, Nd, n_new[k], n_old[k], 0);
+      for (k = 0; k < 4; ++k) { copy_block(c, bak, Nd, 17 + 2 * k, 16 + 2 * k, 0); copy_block(c, bak, Nd, 16 + 2 * k, 17 + 2 * k, 0); }
+    }
+  }
+}
+/* dir2dir: none for 3 streams (src/optprop.F90:1256-1266), 8 streams :1268-1301 */
+void orc_dir2dir_symmetry(const orc_streams *st, double *c, int le, int ln) {
+  double bak[ORC_MAX_DOF * ORC_MAX_DOF];
+  int Nd = st->Nd, n = Nd * Nd, k;
+  if (Nd != 8) return;
+  static const int pe[8] = {1, 0, 3, 2, 4, 5, 6, 7}, pn[8] = {2, 3, 0, 1, 4, 5, 6, 7};
+  if (le) { memcpy(bak, c, n * sizeof(double)); for (k = 0; k < 8; ++k) copy_block(c, bak, Nd, k, pe[k], pe); }
+  if (ln) { memcpy(bak, c, n * sizeof(double)); for (k = 0; k < 8; ++k) copy_block(c, bak, Nd, k, pn[k], pn); }
+}
+
+/* ================================================================================================================
+ * LUT files and lookup
+ * ================================================================================================================ */
+
+/* src/mmap.F90:129-203 (binary_file_to_mmap / load_mmap_array_2d) */
+int orc_mmap4_open(const char *path, const float **data, long *ncoef, long *nlat, void **map, unsigned long *maplen) {
+  long pagesize = sysconf(_SC_PAGESIZE);
+  size_t nhdr = (size_t)pagesize / sizeof(size_t), i, ndim = 0;
+  size_t *header = (size_t *)malloc(nhdr * sizeof(size_t));
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { free(header); return 1; }
+  if (read(fd, header, nhdr * sizeof(size_t)) != (ssize_t)(nhdr * sizeof(size_t))) { close(fd); free(header); return 2; }
+  if (header[0] != sizeof(float)) { close(fd); free(header); return 3; }
+  for (i = 3; i < nhdr; ++i) if (header[i] != 0) ++ndim;
+  if (ndim != 2) { close(fd); free(header); return 4; }
+  *ncoef = (long)header[3];
+  *nlat = (long)header[4];
+  *maplen = header[2] + (unsigned long)pagesize;
+  *map = mmap(0, *maplen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, 0);
+  close(fd);
+  free(header);
+  if (*map == MAP_FAILED) return 5;
+  *data = (const float *)((const char *)(*map) + pagesize);
+  return 0;
+}
+
+/* src/mmap.F90:63-127 (arr_to_binary_datafile_2d) */
+int orc_mmap4_write(const char *path, const float *data, long ncoef, long nlat) {
+  long pagesize = sysconf(_SC_PAGESIZE);
+  size_t nhdr = (size_t)pagesize / sizeof(size_t);
+  size_t *header = (size_t *)calloc(nhdr, sizeof(size_t));
+  FILE *f = fopen(path, "wb");
+  if (!f) { free(header); return 1; }
+  header[0] = sizeof(float);
+  header[1] = (size_t)(ncoef * nlat);
+  header[2] = (size_t)(ncoef * nlat) * sizeof(float);
+  header[3] = (size_t)ncoef;
+  header[4] = (size_t)nlat;
+  fwrite(header, sizeof(size_t), nhdr, f);
+  fwrite(data, sizeof(float), (size_t)(ncoef * nlat), f);
+  fclose(f);
+  free(header);
+  return 0;
+}
+
+static void axes_offsets(orc_lut_axes *a) { /* helper_functions.fypp:2432-2437 ndarray_offsets */
+  int d;
+  a->off[0] = 1;
+  for (d = 1; d < a->ndim; ++d) a->off[d] = a->off[d - 1] * a->n[d - 1];
+}
+
+int orc_lut_load(orc_lut *lut, int solver_id, const char *pT, const char *pS, const char *pD, const int *ndir,
+                 const float *const *axdir) {
+  orc_streams st;
+  long nc, nl, nlat_dir = 1, nlat_diff = 1;
+  int d, rc;
+  memset(lut, 0, sizeof(*lut));
+  if (orc_streams_init(&st, solver_id)) return 10;
+  lut->Nd = st.Nd; lut->Nf = st.Nf;
+  lut->dir.ndim = 6; lut->diff.ndim = 4;
+  for (d = 0; d < 6; ++d) {
+    float *cp = (float *)malloc(sizeof(float) * ndir[d]);
+    memcpy(cp, axdir[d], sizeof(float) * ndir[d]);
+    lut->dir.n[d] = ndir[d]; lut->dir.ax[d] = cp; nlat_dir *= ndir[d];
+    if (d < 4) { lut->diff.n[d] = ndir[d]; lut->diff.ax[d] = cp; nlat_diff *= ndir[d]; }
+  }
+  axes_offsets(&lut->dir); axes_offsets(&lut->diff);
+  if (pT) { if ((rc = orc_mmap4_open(pT, &lut->Tdir, &nc, &nl, &lut->map[0], &lut->maplen[0]))) return 20 + rc;
+            if (nc != st.Nd * st.Nd || nl != nlat_dir) return 30; }
+  if (pS) { if ((rc = orc_mmap4_open(pS, &lut->Sdir, &nc, &nl, &lut->map[1], &lut->maplen[1]))) return 40 + rc;
+            if (nc != st.Nd * st.Nf || nl != nlat_dir) return 50; }
+  if (pD) { if ((rc = orc_mmap4_open(pD, &lut->Sdiff, &nc, &nl, &lut->map[2], &lut->maplen[2]))) return 60 + rc;
+            if (nc != st.Nf * st.Nf || nl != nlat_diff) return 70; }
+  return 0;
+}
+
+void orc_lut_free(orc_lut *lut) {
+  int d;
+  for (d = 0; d < 3; ++d) if (lut->map[d]) munmap(lut->map[d], lut->maplen[d]);
+  for (d = 0; d < 6; ++d) free((void *)lut->dir.ax[d]);
+  memset(lut, 0, sizeof(*lut));
+}
+
+/* src/optprop.F90:550-593 (get_coeff_cube) + src/optprop_LUT.F90:1452-1613 (LUT_get_*) */
+int orc_opp_get_coeff(const orc_lut *lut, const orc_streams *st, float tauz, float w0, float g, float aspect_zx,
+                      float phi, float theta, int mode, int le, int ln, double *coeff) {
+  double pti[ORC_MAX_DIM];
+  float sample[ORC_MAX_DIM];
+  const orc_lut_axes *ax = (mode == 3) ? &lut->diff : &lut->dir;
+  int d;
+  float save_aspect = aspect_zx;
+  if (aspect_zx < ax->ax[2][0]) save_aspect = ax->ax[2][0]; /* OPP_TINYASPECT_RETCODE: clamp, continue */
+  sample[0] = tauz; sample[1] = w0; sample[2] = save_aspect; sample[3] = g; sample[4] = phi; sample[5] = theta;
+  for (d = 0; d < ax->ndim; ++d) pti[d] = orc_find_real_location_f32axis(ax->ax[d], ax->n[d], sample[d]);
+  if (mode == 1) {
+    if (!lut->Tdir) return 1;
+    orc_interp_vec_nd(pti, 6, lut->Tdir, st->Nd * st->Nd, ax->off, coeff);
+    orc_dir2dir_symmetry(st, coeff, le, ln);
+  } else if (mode == 2) {
+    if (!lut->Sdir) return 1;
+    orc_interp_vec_nd(pti, 6, lut->Sdir, st->Nd * st->Nf, ax->off, coeff);
+    orc_dir2diff_symmetry(st, coeff, le, ln);
+  } else if (mode == 3) {
+    if (!lut->Sdiff) return 1;
+    orc_interp_vec_nd(pti, 4, lut->Sdiff, st->Nf * st->Nf, ax->off, coeff);
+  } else {
+    return 2;
+  }
+  return 0;
+}
+
+/* src/pprts_base.F90:1491-1543 (get_coeff): optical properties -> LUT space (fp32 casts, clamps) */
+int orc_get_coeff(const orc_lut *lut, const orc_streams *st, double kabs, double ksca, double g, double dz,
+                  double dx, int mode, double phi, double theta, int le, int ln, double *coeff) {
+  const orc_lut_axes *ax = (mode == 3) ? &lut->diff : &lut->dir;
+  float aspect_zx = (float)(dz / dx);
+  float w0 = (float)(ksca / dmax(kabs + ksca, DBL_EPSILON));
+  float tauz = (float)((kabs + ksca) * dz);
+  aspect_zx = fmaxf(ax->ax[2][0], aspect_zx);
+  tauz = fmaxf(ax->ax[0][0], fminf(ax->ax[0][ax->n[0] - 1], tauz));
+  w0 = fmaxf(ax->ax[1][0], fminf(ax->ax[1][ax->n[1] - 1], w0));
+  return orc_opp_get_coeff(lut, st, tauz, w0, (float)g, aspect_zx, (float)phi, (float)theta, mode, le, ln, coeff);
+}
+
+/* ================================================================================================================
+ * solver
+ * ================================================================================================================ */
+
+#define ORC_UID_MIN (-1000)
+#define ORC_UID_MAX (1000)
+#define ORC_NHIST 100
+
+typedef struct {
+  int lset, lsolar_rad, lthermal_rad, lchanged, lWm2_dir, lWm2_diff;
+  double *edir, *ediff, *abso; /* interior (dof, Nz+1, Nx, Ny) / (Nz,Nx,Ny) */
+  double dir_hist[ORC_NHIST], diff_hist[ORC_NHIST];
+  int Niter_dir, Niter_diff;
+  double final_res_dir, final_res_diff;
+  double diff_sor_omega;
+} orc_solution;
+
+struct orc_solver {
+  orc_config cfg;
+  orc_streams st;
+  const orc_lut *lut;
+  int Nz, Nx, Ny, Nz1;
+  double dx, dy;
+  double *dz;
+  int *l1d;
+  double unconstrained_fraction;
+  /* t_suninfo, src/pprts_base.F90:128-135 */
+  double phi, theta, mu, costheta, symmetry_phi, sundir[3];
+  int xinc, yinc;
+  /* t_atmosphere */
+  double *kabs, *ksca, *g, *planck, *Bsrfc, *albedo;
+  int have_planck, have_Bsrfc, have_optprop;
+  double *a11, *a12, *a13, *a23, *a33;
+  double *dir2dir, *dir2diff, *diff2diff;
+  double *b;
+  double *dir_scale, *diff_scale; /* Wm2_to_W, interior layout */
+  orc_solution *sol[ORC_UID_MAX - ORC_UID_MIN + 1];
+};
+
+#define FG(a, nd, d, k, i, j) (a)[(d) + (long)(nd) * ((k) + (long)Nz1 * (((i) + 1) + (long)(Nx + 2) * ((j) + 1)))]
+#define FI(a, nd, d, k, i, j) (a)[(d) + (long)(nd) * ((k) + (long)Nz1 * ((i) + (long)Nx * (j)))]
+#define CF(a, nc, n, k, i, j) (a)[(n) + (long)(nc) * ((k) + (long)Nz * ((i) + (long)Nx * (j)))]
+#define A3(a, k, i, j) (a)[(k) + (long)Nz * ((i) + (long)Nx * (j))]
+#define P3(a, k, i, j) (a)[(k) + (long)Nz1 * ((i) + (long)Nx * (j))]
+#define A2(a, i, j) (a)[(i) + (long)Nx * (j)]
+#define LOCALS                                                                                                       \
+  const int Nz = s->Nz, Nx = s->Nx, Ny = s->Ny, Nz1 = s->Nz1;                                                          \
+  const int Nd = s->st.Nd, Nf = s->st.Nf, Ndt = s->st.Ndt, Nds = s->st.Nds, Nft = s->st.Nft, Nfs = s->st.Nfs;          \
+  (void)Nz; (void)Nx; (void)Ny; (void)Nz1; (void)Nd; (void)Nf; (void)Ndt; (void)Nds; (void)Nft; (void)Nfs;
+
+static long ngh(const orc_solver *s, int nd) { return (long)nd * s->Nz1 * (s->Nx + 2) * (s->Ny + 2); }
+static long nin(const orc_solver *s, int nd) { return (long)nd * s->Nz1 * s->Nx * s->Ny; }
+
+/* ---- halo helpers for ONE periodic rank (src/pprts_base.F90:1622-1731, src/pprts_explicit.F90:1019-1073) ------ */
+static void interior_to_ghosted(const orc_solver *s, int nd, const double *in, double *gh) {
+  LOCALS
+  int d, k, i, j;
+  memset(gh, 0, sizeof(double) * ngh(s, nd));
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d)
+    FG(gh, nd, d, k, i, j) = FI(in, nd, d, k, i, j);
+}
+static void ghosted_to_interior(const orc_solver *s, int nd, const double *gh, double *out) {
+  LOCALS
+  int d, k, i, j;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d)
+    FI(out, nd, d, k, i, j) = FG(gh, nd, d, k, i, j);
+}
+/* halo_fill_5pt: x ghosts over the full (ghosted) y range, y ghosts over interior x only */
+static void halo_fill_5pt(const orc_solver *s, int nd, double *v) {
+  LOCALS
+  int d, k, i, j;
+  for (j = -1; j <= Ny; ++j) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    double se = FG(v, nd, d, k, Nx - 1, j), sw = FG(v, nd, d, k, 0, j);
+    FG(v, nd, d, k, -1, j) = se; /* rw: from west neighbour's east edge */
+    FG(v, nd, d, k, Nx, j) = sw; /* re */
+  }
+  for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    double sn = FG(v, nd, d, k, i, Ny - 1), ss = FG(v, nd, d, k, i, 0);
+    FG(v, nd, d, k, i, -1) = sn;
+    FG(v, nd, d, k, i, Ny) = ss;
+  }
+}
+/* fill_ghost (src/pprts_explicit.F90:1019-1073): like halo_fill_5pt but x ghosts over interior y only */
+static void fill_ghost(const orc_solver *s, int nd, double *v) {
+  LOCALS
+  int d, k, i, j;
+  for (j = 0; j < Ny; ++j) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    double se = FG(v, nd, d, k, Nx - 1, j), sw = FG(v, nd, d, k, 0, j);
+    FG(v, nd, d, k, -1, j) = se;
+    FG(v, nd, d, k, Nx, j) = sw;
+  }
+  for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    double sn = FG(v, nd, d, k, i, Ny - 1), ss = FG(v, nd, d, k, i, 0);
+    FG(v, nd, d, k, i, -1) = sn;
+    FG(v, nd, d, k, i, Ny) = ss;
+  }
+}
+/* halo_reduce_5pt: ghost -> owner (ADD), then zero ghosts */
+static void halo_reduce_5pt(const orc_solver *s, int nd, double *v) {
+  LOCALS
+  int d, k, i, j;
+  long n = (long)nd * Nz1 * (Ny + 2);
+  double *se = (double *)malloc(sizeof(double) * n), *sw = (double *)malloc(sizeof(double) * n);
+  long c = 0;
+  for (j = -1; j <= Ny; ++j) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d, ++c) {
+    se[c] = FG(v, nd, d, k, Nx, j);
+    sw[c] = FG(v, nd, d, k, -1, j);
+  }
+  n = (long)nd * Nz1 * Nx;
+  double *sn = (double *)malloc(sizeof(double) * n), *ss = (double *)malloc(sizeof(double) * n);
+  c = 0;
+  for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d, ++c) {
+    sn[c] = FG(v, nd, d, k, i, Ny);
+    ss[c] = FG(v, nd, d, k, i, -1);
+  }
+  c = 0;
+  for (j = -1; j <= Ny; ++j) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d, ++c) {
+    FG(v, nd, d, k, 0, j) += se[c];      /* rw = west neighbour's east ghost */
+    FG(v, nd, d, k, Nx - 1, j) += sw[c]; /* re */
+  }
+  c = 0;
+  for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d, ++c) {
+    FG(v, nd, d, k, i, 0) += sn[c];      /* rs = south neighbour's north ghost */
+    FG(v, nd, d, k, i, Ny - 1) += ss[c]; /* rn */
+  }
+  for (j = -1; j <= Ny; ++j) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    FG(v, nd, d, k, -1, j) = 0; FG(v, nd, d, k, Nx, j) = 0;
+  }
+  for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    FG(v, nd, d, k, i, -1) = 0; FG(v, nd, d, k, i, Ny) = 0;
+  }
+  free(se); free(sw); free(sn); free(ss);
+}
+
+/* ---- init ------------------------------------------------------------------------------------------------------ */
+
+/* helper_functions.fypp:1993-2016 (cartesian_2_spherical) */
+static void cartesian_2_spherical(const double sundir[3], double *phi, double *theta) {
+  double n = sqrt(sundir[0] * sundir[0] + sundir[1] * sundir[1] + sundir[2] * sundir[2]);
+  double sn[3] = {sundir[0], sundir[1], sundir[2]}, proj[3], pn, az, c;
+  if (n > 0) { sn[0] /= n; sn[1] /= n; sn[2] /= n; }
+  c = dmax(-1.0, dmin(1.0, -sn[2])); /* dot(sundir_normed, -e_z) */
+  *theta = acos(c) * 180.0 / ORC_PI;
+  /* vec_proj_on_plane(sundir, -e_z) = v - dot(v,n) n */
+  proj[0] = sundir[0]; proj[1] = sundir[1]; proj[2] = 0.0;
+  pn = sqrt(proj[0] * proj[0] + proj[1] * proj[1]);
+  if (pn > 0) { proj[0] /= pn; proj[1] /= pn; }
+  c = dmax(-1.0, dmin(1.0, -proj[1])); /* angle to -e_y */
+  az = acos(c);
+  az = az * ((-proj[0]) >= 0 ? 1.0 : -1.0); /* sign(1, dot(proj, -e_x)) */
+  *phi = az * 180.0 / ORC_PI;
+}
+
+/* src/pprts.F90:1118-1183 (setup_suninfo) */
+void orc_set_angles(orc_solver *s, const double sundir[3]) {
+  double d2r = ORC_PI / 180.0, sp;
+  cartesian_2_spherical(sundir, &s->phi, &s->theta);
+  s->mu = dmax(cos(s->theta * d2r), 0.0);
+  /* spherical_2_cartesian, helper_functions.fypp:2022-2033 */
+  s->sundir[0] = -sin(s->theta * d2r) * sin(s->phi * d2r);
+  s->sundir[1] = -sin(s->theta * d2r) * cos(s->phi * d2r);
+  s->sundir[2] = -cos(s->theta * d2r);
+  if (s->theta >= 90.0) s->theta = -1.0;
+  s->costheta = dmax(cos(s->theta * d2r), 0.0);
+  sp = acos(cos(s->phi * d2r));
+  s->symmetry_phi = dmin(90.0, dmax(0.0, asin(sin(sp)) / d2r));
+  s->xinc = (sin(s->phi * d2r) > 0.0) ? 0 : 1;
+  s->yinc = (cos(s->phi * d2r) < 0.0) ? 1 : 0;
+}
+
+void orc_get_suninfo(orc_solver *s, double *phi, double *theta, double *symmetry_phi, int *xinc, int *yinc) {
+  *phi = s->phi; *theta = s->theta; *symmetry_phi = s->symmetry_phi; *xinc = s->xinc; *yinc = s->yinc;
+}
+
+/* src/pprts.F90:649-725 (determine_1d_layers), one rank, no collapse */
+static void determine_1d_layers(orc_solver *s) {
+  LOCALS
+  int k, i, j, any, kk, count3d = 0;
+  for (k = 0; k < Nz; ++k) s->l1d[k] = 0;
+  any = 0;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) if (A3(s->dz, Nz - 1, i, j) / s->dx > s->cfg.twostr_ratio) any = 1;
+  s->l1d[Nz - 1] = any;
+  for (k = Nz - 2; k >= 0; --k) {
+    any = 0;
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) if (A3(s->dz, k, i, j) / s->dx > s->cfg.twostr_ratio) any = 1;
+    if (any) { for (kk = 0; kk <= k; ++kk) s->l1d[kk] = 1; break; }
+  }
+  { /* :708-719: the 1-D block is contiguous from the top */
+    int n1d = 0;
+    for (k = 0; k < Nz; ++k) n1d += s->l1d[k];
+    for (k = 0; k < n1d; ++k) s->l1d[k] = 1;
+  }
+  for (k = 0; k < Nz; ++k) count3d += !s->l1d[k];
+  s->unconstrained_fraction = (double)count3d / (double)Nz;
+}
+
+/* src/pprts.F90:3901-3987 (gen_scale_dir_flx_vec_arr / gen_scale_diff_flx_vec_arr) */
+static void gen_scale_vectors(orc_solver *s) {
+  LOCALS
+  int k, i, j, d;
+  double Az, Ax, Ay;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) {
+    for (k = 0; k < Nz1; ++k) {
+      Az = s->dx * s->dy / (double)s->st.dirtop_adiv;
+      for (d = 0; d < Ndt; ++d) FI(s->dir_scale, Nd, d, k, i, j) = Az;
+    }
+    for (k = 0; k < Nz; ++k) {
+      Ax = s->dy * A3(s->dz, k, i, j) / (double)s->st.dirside_adiv;
+      for (d = 0; d < Nds; ++d) FI(s->dir_scale, Nd, Ndt + d, k, i, j) = Ax;
+      Ay = s->dx * A3(s->dz, k, i, j) / (double)s->st.dirside_adiv;
+      for (d = 0; d < Nds; ++d) FI(s->dir_scale, Nd, Ndt + Nds + d, k, i, j) = Ay;
+    }
+    for (d = Ndt; d < Nd; ++d) FI(s->dir_scale, Nd, d, Nz, i, j) = 1.0;
+    /* diffuse: difftop%area_divider = diffside%area_divider = 1 for every pprts solver */
+    Az = s->dx * s->dy;
+    for (k = 0; k < Nz1; ++k) for (d = 0; d < Nft; ++d) FI(s->diff_scale, Nf, d, k, i, j) = Az;
+    for (k = 0; k < Nz; ++k) {
+      Ax = s->dy * A3(s->dz, k, i, j);
+      for (d = 0; d < Nfs; ++d) FI(s->diff_scale, Nf, Nft + d, k, i, j) = Ax;
+      Ay = s->dx * A3(s->dz, k, i, j);
+      for (d = 0; d < Nfs; ++d) FI(s->diff_scale, Nf, Nft + Nfs + d, k, i, j) = Ay;
+    }
+    for (d = Nft; d < Nf; ++d) FI(s->diff_scale, Nf, d, Nz, i, j) = 1.0;
+  }
+}
+
+orc_solver *orc_solver_create(const orc_config *cfg, const orc_lut *lut) {
+  orc_solver *s = (orc_solver *)calloc(1, sizeof(orc_solver));
+  long nc;
+  s->cfg = *cfg;
+  if (orc_streams_init(&s->st, cfg->solver_id)) { free(s); return 0; }
+  s->lut = lut;
+  s->Nz = cfg->Nz; s->Nx = cfg->Nx; s->Ny = cfg->Ny; s->Nz1 = cfg->Nz + 1;
+  s->dx = cfg->dx; s->dy = cfg->dy;
+  nc = (long)s->Nz * s->Nx * s->Ny;
+  s->dz = (double *)malloc(sizeof(double) * nc);
+  memcpy(s->dz, cfg->dz, sizeof(double) * nc);
+  s->l1d = (int *)calloc(s->Nz, sizeof(int));
+  determine_1d_layers(s);
+  s->kabs = (double *)calloc(nc, sizeof(double));
+  s->ksca = (double *)calloc(nc, sizeof(double));
+  s->g = (double *)calloc(nc, sizeof(double));
+  s->planck = (double *)calloc((long)s->Nz1 * s->Nx * s->Ny, sizeof(double));
+  s->Bsrfc = (double *)calloc((long)s->Nx * s->Ny, sizeof(double));
+  s->albedo = (double *)calloc((long)s->Nx * s->Ny, sizeof(double));
+  s->a11 = (double *)calloc(nc, sizeof(double)); s->a12 = (double *)calloc(nc, sizeof(double));
+  s->a13 = (double *)calloc(nc, sizeof(double)); s->a23 = (double *)calloc(nc, sizeof(double));
+  s->a33 = (double *)calloc(nc, sizeof(double));
+  s->dir2dir = (double *)calloc(nc * s->st.Nd * s->st.Nd, sizeof(double));
+  s->dir2diff = (double *)calloc(nc * s->st.Nd * s->st.Nf, sizeof(double));
+  s->diff2diff = (double *)calloc(nc * s->st.Nf * s->st.Nf, sizeof(double));
+  s->b = (double *)calloc(nin(s, s->st.Nf), sizeof(double));
+  s->dir_scale = (double *)calloc(nin(s, s->st.Nd), sizeof(double));
+  s->diff_scale = (double *)calloc(nin(s, s->st.Nf), sizeof(double));
+  gen_scale_vectors(s);
+  orc_set_angles(s, cfg->sundir);
+#ifdef _OPENMP
+  if (cfg->nthreads > 0) omp_set_num_threads(cfg->nthreads);
+#endif
+  return s;
+}
+
+static void free_solution(orc_solution *p) {
+  if (!p) return;
+  free(p->edir); free(p->ediff); free(p->abso); free(p);
+}
+
+void orc_solver_destroy(orc_solver *s) {
+  int u;
+  if (!s) return;
+  for (u = 0; u <= ORC_UID_MAX - ORC_UID_MIN; ++u) free_solution(s->sol[u]);
+  free(s->dz); free(s->l1d); free(s->kabs); free(s->ksca); free(s->g); free(s->planck); free(s->Bsrfc);
+  free(s->albedo); free(s->a11); free(s->a12); free(s->a13); free(s->a23); free(s->a33);
+  free(s->dir2dir); free(s->dir2diff); free(s->diff2diff); free(s->b); free(s->dir_scale); free(s->diff_scale);
+  free(s);
+}
+
+/* ---- set_optical_properties (src/pprts.F90:1764-2076) --------------------------------------------------------- */
+int orc_set_optical_properties(orc_solver *s, double albedo, const double *kabs, const double *ksca, const double *g,
+                               const double *planck, const double *planck_srfc, const double *albedo_2d,
+                               int ldelta_scaling) {
+  LOCALS
+  long nc = (long)Nz * Nx * Ny, n;
+  int k, i, j;
+  for (n = 0; n < (long)Nx * Ny; ++n) s->albedo[n] = albedo_2d ? albedo_2d[n] : albedo;
+  if (kabs) memcpy(s->kabs, kabs, sizeof(double) * nc);
+  if (ksca) memcpy(s->ksca, ksca, sizeof(double) * nc);
+  if (g) memcpy(s->g, g, sizeof(double) * nc);
+  s->have_planck = planck != 0;
+  if (planck) memcpy(s->planck, planck, sizeof(double) * (long)Nz1 * Nx * Ny);
+  s->have_Bsrfc = planck_srfc != 0;
+  if (planck_srfc) memcpy(s->Bsrfc, planck_srfc, sizeof(double) * (long)Nx * Ny);
+  if (ldelta_scaling) /* :1912-1914 */
+    for (n = 0; n < nc; ++n) orc_delta_scale(&s->kabs[n], &s->ksca[n], &s->g[n]);
+  for (n = 0; n < nc; ++n) /* :1929-1935 */
+    if (s->kabs[n] < 0 || s->ksca[n] < 0 || s->g[n] < 0 || isnan(s->kabs[n]) || isnan(s->ksca[n]) || isnan(s->g[n]))
+      return 1;
+  /* :1962-2007 Eddington coefficients in 1-D layers; a21 = a12, a22 = a11 (:2072-2073) */
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+    if (s->l1d[k]) {
+      double ext = dmax(DBL_MIN, A3(s->kabs, k, i, j) + A3(s->ksca, k, i, j));
+      orc_eddington_coeff_ec(A3(s->dz, k, i, j) * ext, A3(s->ksca, k, i, j) / ext, A3(s->g, k, i, j), s->costheta,
+                             &A3(s->a11, k, i, j), &A3(s->a12, k, i, j), &A3(s->a13, k, i, j),
+                             &A3(s->a23, k, i, j), &A3(s->a33, k, i, j));
+    }
+  }
+  s->have_optprop = 1;
+  return 0;
+}
+
+/* ---- coefficients (src/pprts.F90:3088-3494) ---------------------------------------------------------------------- */
+static void store_coeff(const orc_solver *s, const double *v, double *dst, int n) {
+  int c;
+  if (s->cfg.coeff_fp32) for (c = 0; c < n; ++c) dst[c] = (double)(float)v[c];
+  else for (c = 0; c < n; ++c) dst[c] = v[c];
+}
+static void alloc_coeffs(orc_solver *s, int lsolar) {
+  LOCALS
+  long col;
+#pragma omp parallel for schedule(static)
+  for (col = 0; col < (long)Nx * Ny; ++col) {
+    int i = (int)(col % Nx), j = (int)(col / Nx), k;
+    double v[ORC_MAX_DOF * ORC_MAX_DOF];
+    for (k = 0; k < Nz; ++k) {
+      if (s->l1d[k]) continue;
+      double ka = A3(s->kabs, k, i, j), ks = A3(s->ksca, k, i, j), gg = A3(s->g, k, i, j), dz = A3(s->dz, k, i, j);
+      if (lsolar) {
+        orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 1, s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
+        store_coeff(s, v, &CF(s->dir2dir, Nd * Nd, 0, k, i, j), Nd * Nd);
+        orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 2, s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
+        store_coeff(s, v, &CF(s->dir2diff, Nd * Nf, 0, k, i, j), Nd * Nf);
+      }
+      orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 3, 0, 0, 0, 0, v);
+      store_coeff(s, v, &CF(s->diff2diff, Nf * Nf, 0, k, i, j), Nf * Nf);
+    }
+  }
+}
+
+/* ---- scale_flx (src/pprts.F90:3682-3741) ------------------------------------------------------------------------ */
+void orc_scale_flx_arr(orc_solver *s, double *arr, int ldir, int lWm2) {
+  long n, N = nin(s, ldir ? s->st.Nd : s->st.Nf);
+  const double *sc = ldir ? s->dir_scale : s->diff_scale;
+  for (n = 0; n < N; ++n) {
+    if (lWm2) arr[n] = arr[n] * ((sc[n] != 0.0) ? 1.0 / sc[n] : 0.0);
+    else arr[n] = arr[n] * sc[n];
+  }
+}
+static void scale_flx(orc_solver *s, orc_solution *sol, int lWm2) {
+  if (sol->lsolar_rad && sol->lWm2_dir != lWm2) { orc_scale_flx_arr(s, sol->edir, 1, lWm2); sol->lWm2_dir = lWm2; }
+  if (sol->lWm2_diff != lWm2) { orc_scale_flx_arr(s, sol->ediff, 0, lWm2); sol->lWm2_diff = lWm2; }
+}
+
+/* src/pprts_base.F90:1097-1142 (determine_ksp_tolerances, non-PETSc branch) */
+static void determine_ksp_tolerances(const orc_solver *s, double *rtol, double *atol) {
+  *rtol = 1e-5;
+  *atol = dmax(1e-8, 1e-4 * (double)s->Nx * (double)s->Ny * (double)s->Nz1 * s->unconstrained_fraction);
+}
+
+/* ---- direct beam (src/pprts_explicit.F90:60-459) ----------------------------------------------------------------- */
+static void exchange_direct_boundary(const orc_solver *s, int lsun_north, int lsun_east, double *x) {
+  LOCALS
+  int d, k, i, j;
+  for (d = Ndt; d < Ndt + Nds; ++d) for (j = 0; j < Ny; ++j) for (k = 0; k < Nz1; ++k) {
+    if (lsun_east) FG(x, Nd, d, k, Nx, j) = FG(x, Nd, d, k, 0, j);  /* send xs west, recv from east into xe+1 */
+    else           FG(x, Nd, d, k, 0, j) = FG(x, Nd, d, k, Nx, j);  /* send xe+1 east, recv from west into xs */
+  }
+  for (d = Ndt + Nds; d < Nd; ++d) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) {
+    if (lsun_north) FG(x, Nd, d, k, i, Ny) = FG(x, Nd, d, k, i, 0);
+    else            FG(x, Nd, d, k, i, 0) = FG(x, Nd, d, k, i, Ny);
+  }
+}
+
+static void explicit_edir_forward_sweep(const orc_solver *s, const int dxr[3], const int dyr[3], const double *b,
+                                        double *x) {
+  LOCALS
+  const int xinc = s->xinc, yinc = s->yinc;
+  int i, j, k, idst, isrc, src, dst;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (dst = 0; dst < Ndt; ++dst)
+    FG(x, Nd, dst, 0, i, j) = FG(b, Nd, dst, 0, i, j);
+  for (k = 0; k < Nz; ++k) {
+    if (s->l1d[k]) {
+      for (j = dyr[0]; j != dyr[1] + dyr[2]; j += dyr[2]) for (i = dxr[0]; i != dxr[1] + dxr[2]; i += dxr[2])
+        for (idst = 0; idst < Ndt; ++idst) FG(x, Nd, idst, k + 1, i, j) = FG(x, Nd, idst, k, i, j) * A3(s->a33, k, i, j);
+    } else {
+      for (j = dyr[0]; j != dyr[1] + dyr[2]; j += dyr[2]) for (i = dxr[0]; i != dxr[1] + dxr[2]; i += dxr[2]) {
+        const double *v = &CF(s->dir2dir, Nd * Nd, 0, k, i, j); /* v(src,dst) = v[dst*Nd+src] */
+        double acc;
+        dst = 0;
+        for (idst = 0; idst < Ndt; ++idst, ++dst) {
+          acc = 0; src = 0;
+          for (isrc = 0; isrc < Ndt; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i, j) * v[dst * Nd + src];
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i + 1 - xinc, j) * v[dst * Nd + src];
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i, j + 1 - yinc) * v[dst * Nd + src];
+          FG(x, Nd, dst, k + 1, i, j) = acc;
+        }
+        for (idst = 0; idst < Nds; ++idst, ++dst) {
+          acc = 0; src = 0;
+          for (isrc = 0; isrc < Ndt; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i, j) * v[dst * Nd + src];
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i + 1 - xinc, j) * v[dst * Nd + src];
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i, j + 1 - yinc) * v[dst * Nd + src];
+          FG(x, Nd, dst, k, i + xinc, j) = acc;
+        }
+        for (idst = 0; idst < Nds; ++idst, ++dst) {
+          acc = 0; src = 0;
+          for (isrc = 0; isrc < Ndt; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i, j) * v[dst * Nd + src];
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i + 1 - xinc, j) * v[dst * Nd + src];
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) acc = acc + FG(x, Nd, src, k, i, j + 1 - yinc) * v[dst * Nd + src];
+          FG(x, Nd, dst, k, i, j + yinc) = acc;
+        }
+      }
+    }
+  }
+}
+
+static double norm2_diff_and_copy(const orc_solver *s, int nd, double *xg, const double *v0) {
+  LOCALS
+  int d, k, i, j;
+  double acc = 0;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d) {
+    double df = FI(xg, nd, d, k, i, j) - FG(v0, nd, d, k, i, j);
+    acc += df * df;
+    FI(xg, nd, d, k, i, j) = FG(v0, nd, d, k, i, j);
+  }
+  return sqrt(acc);
+}
+
+static int explicit_edir(orc_solver *s, double edirTOA, orc_solution *sol) {
+  LOCALS
+  int maxiter = s->cfg.maxit_dir > 0 ? s->cfg.maxit_dir : 1000, iter, i, j, d, converged = 0;
+  double rtol_d, atol_d, rtol, atol, res, res1 = 0, rel, fac;
+  double *lb = (double *)calloc(ngh(s, Nd), sizeof(double));
+  double *v0 = (double *)calloc(ngh(s, Nd), sizeof(double));
+  int dxr[3] = {0, Nx - 1, 1}, dyr[3] = {0, Ny - 1, 1};
+  const int lsun_north = s->yinc == 0, lsun_east = s->xinc == 0;
+  determine_ksp_tolerances(s, &rtol_d, &atol_d);
+  rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d;
+  atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol->dir_hist[0] < 0) { /* -ksp_complete_initial_run, src/pprts_explicit.F90:114-121 */
+    maxiter = maxiter + 2;
+    rtol = dmin(rtol, rtol_d);
+    atol = dmin(atol, atol_d);
+  }
+  if (lsun_east) { dxr[0] = Nx - 1; dxr[1] = 0; dxr[2] = -1; }  /* -explicit_edir_permute (default on) */
+  if (lsun_north) { dyr[0] = Ny - 1; dyr[1] = 0; dyr[2] = -1; }
+  /* setup_incSolar, src/pprts_base.F90:1146-1181 */
+  fac = edirTOA * s->dx * s->dy / (double)s->st.dirtop_adiv;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (d = 0; d < Ndt; ++d) FG(lb, Nd, d, 0, i, j) = fac;
+  interior_to_ghosted(s, Nd, sol->edir, v0);
+  exchange_direct_boundary(s, lsun_north, lsun_east, v0);
+  sol->Niter_dir = 0;
+  for (iter = 1; iter <= maxiter; ++iter) {
+    explicit_edir_forward_sweep(s, dxr, dyr, lb, v0);
+    exchange_direct_boundary(s, lsun_north, lsun_east, v0);
+    res = dmax(DBL_MIN, norm2_diff_and_copy(s, Nd, sol->edir, v0));
+    if (iter == 1) res1 = res;
+    rel = (res1 <= sqrt(DBL_MIN)) ? 0.0 : res / res1;
+    sol->dir_hist[(iter < ORC_NHIST ? iter : ORC_NHIST) - 1] = res;
+    sol->Niter_dir = iter;
+    sol->final_res_dir = res;
+    if (res < atol || rel < rtol) { converged = 1; break; }
+  }
+  ghosted_to_interior(s, Nd, v0, sol->edir);
+  sol->lchanged = 1;
+  sol->lWm2_dir = 0;
+  free(lb); free(v0);
+  return converged ? 0 : 1;
+}
+
+/* ---- source term (src/pprts.F90:4641-4987) ----------------------------------------------------------------------- */
+static void setup_b(orc_solver *s, orc_solution *sol) {
+  LOCALS
+  const double eps = DBL_EPSILON;
+  double *xsrc = (double *)calloc(ngh(s, Nf), sizeof(double));
+  int k, i, j, src, dst, idof, idofdst, idiff, iside;
+  if (sol->lsolar_rad) { /* set_solar_source :4684-4846 */
+    double *xedir = (double *)calloc(ngh(s, Nd), sizeof(double));
+    const int xinc = s->xinc, yinc = s->yinc;
+    interior_to_ghosted(s, Nd, sol->edir, xedir);
+    halo_fill_5pt(s, Nd, xedir);
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+      int any = 0;
+      for (src = 0; src < Nd; ++src) if (FG(xedir, Nd, src, k, i, j) > eps) any = 1;
+      if (!any) continue;
+      if (s->l1d[k]) {
+        for (src = 0; src < Ndt; ++src) for (idiff = 0; idiff < Nft; ++idiff) {
+          if (s->st.ft_inward[idiff])
+            FG(xsrc, Nf, idiff, k + 1, i, j) += FG(xedir, Nd, src, k, i, j) * A3(s->a23, k, i, j) / (double)(Nft / 2);
+          else
+            FG(xsrc, Nf, idiff, k, i, j) += FG(xedir, Nd, src, k, i, j) * A3(s->a13, k, i, j) / (double)(Nft / 2);
+        }
+      } else {
+        const double *c = &CF(s->dir2diff, Nd * Nf, 0, k, i, j); /* dir2diff(dst*Nd + src) */
+        double solrad;
+        dst = 0;
+        for (idofdst = 0; idofdst < Nft; ++idofdst, ++dst) {
+          double *tgt = s->st.ft_inward[idofdst] ? &FG(xsrc, Nf, dst, k + 1, i, j) : &FG(xsrc, Nf, dst, k, i, j);
+          src = 0;
+          for (idof = 0; idof < Ndt; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i, j); *tgt += solrad * c[dst * Nd + src]; }
+          for (idof = 0; idof < Nds; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i + 1 - xinc, j); *tgt += solrad * c[dst * Nd + src]; }
+          for (idof = 0; idof < Nds; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i, j + 1 - yinc); *tgt += solrad * c[dst * Nd + src]; }
+        }
+        for (idofdst = 0; idofdst < Nfs; ++idofdst, ++dst) {
+          double *tgt = s->st.fs_inward[idofdst] ? &FG(xsrc, Nf, dst, k, i + 1, j) : &FG(xsrc, Nf, dst, k, i, j);
+          src = 0;
+          for (idof = 0; idof < Ndt; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i, j); *tgt += solrad * c[dst * Nd + src]; }
+          for (idof = 0; idof < Nds; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i + 1 - xinc, j); *tgt += solrad * c[dst * Nd + src]; }
+          for (idof = 0; idof < Nds; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i, j + 1 - yinc); *tgt += solrad * c[dst * Nd + src]; }
+        }
+        for (idofdst = 0; idofdst < Nfs; ++idofdst, ++dst) {
+          double *tgt = s->st.fs_inward[idofdst] ? &FG(xsrc, Nf, dst, k, i, j + 1) : &FG(xsrc, Nf, dst, k, i, j);
+          src = 0;
+          for (idof = 0; idof < Ndt; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i, j); *tgt += solrad * c[dst * Nd + src]; }
+          for (idof = 0; idof < Nds; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i + 1 - xinc, j); *tgt += solrad * c[dst * Nd + src]; }
+          for (idof = 0; idof < Nds; ++idof, ++src) { solrad = FG(xedir, Nd, src, k, i, j + 1 - yinc); *tgt += solrad * c[dst * Nd + src]; }
+        }
+      }
+    }
+    /* ground albedo reflecting direct radiation :4830-4843 */
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (dst = 0; dst < Nft; ++dst) if (!s->st.ft_inward[dst])
+      for (src = 0; src < Ndt; ++src)
+        FG(xsrc, Nf, dst, Nz, i, j) += FG(xedir, Nd, src, Nz, i, j) * A2(s->albedo, i, j) / (double)(Nft / 2);
+    free(xedir);
+  }
+  if (sol->lthermal_rad) { /* set_thermal_source :4848-4987 */
+    const double Az = s->dx * s->dy; /* difftop%area_divider = 1 */
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) {
+      for (k = 0; k < Nz; ++k) {
+        double b0 = P3(s->planck, k, i, j), b1 = P3(s->planck, k + 1, i, j);
+        double tauz = A3(s->kabs, k, i, j) * A3(s->dz, k, i, j), btop, bbot, bfac, emis;
+        if (s->l1d[k]) {
+          bfac = ORC_PI * Az / (double)(Nft / 2);
+          emis = 1.0 - A3(s->a11, k, i, j) - A3(s->a12, k, i, j);
+          emis = dmax(0.0, dmin(1.0, emis));
+          btop = orc_B_eff(b1, b0, tauz) * bfac * emis;
+          bbot = orc_B_eff(b0, b1, tauz) * bfac * emis;
+          for (src = 0; src < Nft; ++src) {
+            if (s->st.ft_inward[src]) FG(xsrc, Nf, src, k + 1, i, j) += bbot;
+            else FG(xsrc, Nf, src, k, i, j) += btop;
+          }
+        } else {
+          const double *c = &CF(s->diff2diff, Nf * Nf, 0, k, i, j); /* diff2diff(src,dst) = c[dst*Nf+src] */
+          double Ax = s->dy * A3(s->dz, k, i, j), Ay = s->dx * A3(s->dz, k, i, j), sum;
+          btop = orc_B_eff(b1, b0, tauz);
+          bbot = orc_B_eff(b0, b1, tauz);
+          src = 0;
+          bfac = ORC_PI * Az / (double)(Nft / 2);
+          for (iside = 1; iside <= Nft; ++iside, ++src) {
+            sum = 0; for (dst = 0; dst < Nf; ++dst) sum += c[dst * Nf + src];
+            emis = dmax(0.0, dmin(1.0, 1.0 - sum));
+            if (!s->st.ft_inward[iside - 1]) FG(xsrc, Nf, src, k, i, j) += btop * bfac * emis;
+            else FG(xsrc, Nf, src, k + 1, i, j) += bbot * bfac * emis;
+          }
+          bfac = ORC_PI * Ax / (double)(Nfs / 2);
+          for (iside = 1; iside <= Nfs; ++iside, ++src) {
+            sum = 0; for (dst = 0; dst < Nf; ++dst) sum += c[dst * Nf + src];
+            emis = dmax(0.0, dmin(1.0, 1.0 - sum));
+            emis = (iside > Nfs / 2) ? btop * emis : bbot * emis;
+            if (!s->st.fs_inward[iside - 1]) FG(xsrc, Nf, src, k, i, j) += emis * bfac;
+            else FG(xsrc, Nf, src, k, i + 1, j) += emis * bfac;
+          }
+          bfac = ORC_PI * Ay / (double)(Nfs / 2);
+          for (iside = 1; iside <= Nfs; ++iside, ++src) {
+            sum = 0; for (dst = 0; dst < Nf; ++dst) sum += c[dst * Nf + src];
+            emis = dmax(0.0, dmin(1.0, 1.0 - sum));
+            emis = (iside > Nfs / 2) ? btop * emis : bbot * emis;
+            if (!s->st.fs_inward[iside - 1]) FG(xsrc, Nf, src, k, i, j) += emis * bfac;
+            else FG(xsrc, Nf, src, k, i, j + 1) += emis * bfac;
+          }
+        }
+      }
+      /* thermal emission at the surface :4958-4985 */
+      for (src = 0; src < Nft; ++src) if (!s->st.ft_inward[src]) {
+        if (s->have_Bsrfc) {
+          double emis = dmax(0.0, dmin(1.0, 1.0 - A2(s->albedo, i, j)));
+          FG(xsrc, Nf, src, Nz, i, j) += A2(s->Bsrfc, i, j) * Az * emis * ORC_PI / (double)(Nft / 2);
+        } else {
+          FG(xsrc, Nf, src, Nz, i, j) += P3(s->planck, Nz, i, j) * Az * (1.0 - A2(s->albedo, i, j)) * ORC_PI / (double)(Nft / 2);
+        }
+      }
+    }
+  }
+  halo_reduce_5pt(s, Nf, xsrc);
+  ghosted_to_interior(s, Nf, xsrc, s->b);
+  free(xsrc);
+}
+
+/* ---- diffuse operator and solvers ------------------------------------------------------------------------------ */
+static int inv_dof(const orc_solver *s, int dof) { /* src/pprts_explicit.F90:1001-1014 */
+  int inc = s->st.ft_inward[0] ? 1 : -1;
+  return s->st.ft_inward[dof] ? dof + inc : dof - inc;
+}
+
+/* src/pprts_shell.F90:366-541 (op_mat_mult_ediff) */
+void orc_mat_mult_ediff(orc_solver *s, const double *x, double *y) {
+  LOCALS
+  double *xx = (double *)malloc(sizeof(double) * ngh(s, Nf));
+  double *xb = (double *)calloc(ngh(s, Nf), sizeof(double));
+  long col, n, N = nin(s, Nf);
+  interior_to_ghosted(s, Nf, x, xx);
+  halo_fill_5pt(s, Nf, xx); /* DMGlobalToLocal */
+  for (col = 0; col < (long)Nx * Ny; ++col) {
+    int i = (int)(col % Nx), j = (int)(col / Nx), k, idst, isrc, dst, src, mdst, msrc;
+    for (k = 0; k < Nz; ++k) {
+      if (s->l1d[k]) {
+        for (idst = 0; idst < Nft; ++idst) {
+          if (s->st.ft_inward[idst]) {
+            FG(xb, Nf, idst, k + 1, i, j) -= FG(xx, Nf, idst, k, i, j) * A3(s->a11, k, i, j);
+            FG(xb, Nf, idst, k + 1, i, j) -= FG(xx, Nf, inv_dof(s, idst), k + 1, i, j) * A3(s->a12, k, i, j);
+          } else {
+            FG(xb, Nf, idst, k, i, j) -= FG(xx, Nf, idst, k + 1, i, j) * A3(s->a11, k, i, j);
+            FG(xb, Nf, idst, k, i, j) -= FG(xx, Nf, inv_dof(s, idst), k, i, j) * A3(s->a12, k, i, j);
+          }
+        }
+      } else {
+        const double *v = &CF(s->diff2diff, Nf * Nf, 0, k, i, j);
+        double *tgt;
+        dst = 0;
+        for (idst = 0; idst < Nft + 2 * Nfs; ++idst, ++dst) {
+          if (idst < Nft) { mdst = s->st.ft_inward[idst] ? k + 1 : k; tgt = &FG(xb, Nf, dst, mdst, i, j); }
+          else if (idst < Nft + Nfs) { mdst = s->st.fs_inward[idst - Nft] ? i + 1 : i; tgt = &FG(xb, Nf, dst, k, mdst, j); }
+          else { mdst = s->st.fs_inward[idst - Nft - Nfs] ? j + 1 : j; tgt = &FG(xb, Nf, dst, k, i, mdst); }
+          src = 0;
+          for (isrc = 0; isrc < Nft; ++isrc, ++src) {
+            msrc = s->st.ft_inward[isrc] ? k : k + 1;
+            *tgt -= FG(xx, Nf, src, msrc, i, j) * v[dst * Nf + src];
+          }
+          for (isrc = 0; isrc < Nfs; ++isrc, ++src) {
+            msrc = s->st.fs_inward[isrc] ? i : i + 1;
+            *tgt -= FG(xx, Nf, src, k, msrc, j) * v[dst * Nf + src];
+          }
+          for (isrc = 0; isrc < Nfs; ++isrc, ++src) {
+            msrc = s->st.fs_inward[isrc] ? j : j + 1;
+            *tgt -= FG(xx, Nf, src, k, i, msrc) * v[dst * Nf + src];
+          }
+        }
+      }
+    }
+    for (idst = 0; idst < Nft; ++idst) if (!s->st.ft_inward[idst]) /* albedo row :500-505 */
+      FG(xb, Nf, idst, Nz, i, j) -= FG(xx, Nf, inv_dof(s, idst), Nz, i, j) * A2(s->albedo, i, j);
+  }
+  halo_reduce_5pt(s, Nf, xb); /* DMLocalToGlobal(ADD_VALUES) */
+  ghosted_to_interior(s, Nf, xb, y);
+  for (n = 0; n < N; ++n) y[n] += x[n]; /* VecAXPY: diagonal */
+  free(xx); free(xb);
+}
+
+/* src/pprts_explicit.F90:715-848 (exchange_diffuse_boundary), one periodic rank */
+static void exchange_diffuse_boundary(const orc_solver *s, double *v0) {
+  LOCALS
+  int k, i, j, idof, dof;
+  for (j = 0; j < Ny; ++j) for (k = 0; k < Nz1; ++k) for (idof = 0; idof < Nfs; ++idof) {
+    dof = Nft + idof;
+    if (s->st.fs_inward[idof]) FG(v0, Nf, dof, k, 0, j) = FG(v0, Nf, dof, k, Nx, j);   /* send_e(xe+1) -> neighbour xs */
+    else                       FG(v0, Nf, dof, k, Nx, j) = FG(v0, Nf, dof, k, 0, j);   /* send_w(xs) -> neighbour xe+1 */
+  }
+  for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (idof = 0; idof < Nfs; ++idof) {
+    dof = Nft + Nfs + idof;
+    if (s->st.fs_inward[idof]) FG(v0, Nf, dof, k, i, 0) = FG(v0, Nf, dof, k, i, Ny);
+    else                       FG(v0, Nf, dof, k, i, Ny) = FG(v0, Nf, dof, k, i, 0);
+  }
+}
+
+/* src/pprts_explicit.F90:849-1015 (explicit_ediff_sor_sweep) */
+static void explicit_ediff_sor_sweep(const orc_solver *s, const int dxr[3], const int dyr[3], const int dzr[3],
+                                     double omega, const double *xb, double *x0) {
+  LOCALS
+  int i, j, k, idst, isrc, src, dst, msrc, mdst;
+  double sigma;
+  if (dzr[2] < 0) {
+    for (j = dyr[0]; j != dyr[1] + dyr[2]; j += dyr[2]) for (i = dxr[0]; i != dxr[1] + dxr[2]; i += dxr[2])
+      for (idst = 0; idst < Nft; ++idst) if (!s->st.ft_inward[idst])
+        FG(x0, Nf, idst, Nz, i, j) = FG(xb, Nf, idst, Nz, i, j) + FG(x0, Nf, inv_dof(s, idst), Nz, i, j) * A2(s->albedo, i, j);
+  }
+  for (j = dyr[0]; j != dyr[1] + dyr[2]; j += dyr[2]) for (i = dxr[0]; i != dxr[1] + dxr[2]; i += dxr[2])
+    for (k = dzr[0]; k != dzr[1] + dzr[2]; k += dzr[2]) {
+      if (s->l1d[k]) {
+        for (idst = 0; idst < Nft; ++idst) {
+          if (s->st.ft_inward[idst])
+            FG(x0, Nf, idst, k + 1, i, j) = FG(xb, Nf, idst, k + 1, i, j) + FG(x0, Nf, idst, k, i, j) * A3(s->a11, k, i, j) +
+                                            FG(x0, Nf, inv_dof(s, idst), k + 1, i, j) * A3(s->a12, k, i, j);
+          else
+            FG(x0, Nf, idst, k, i, j) = FG(xb, Nf, idst, k, i, j) + FG(x0, Nf, idst, k + 1, i, j) * A3(s->a11, k, i, j) +
+                                        FG(x0, Nf, inv_dof(s, idst), k, i, j) * A3(s->a12, k, i, j);
+        }
+      } else {
+        const double *v = &CF(s->diff2diff, Nf * Nf, 0, k, i, j);
+        dst = 0;
+        for (idst = 0; idst < Nft + 2 * Nfs; ++idst, ++dst) {
+          double *px; const double *pb;
+          if (idst < Nft) { mdst = s->st.ft_inward[idst] ? k + 1 : k; px = &FG(x0, Nf, dst, mdst, i, j); pb = &FG(xb, Nf, dst, mdst, i, j); }
+          else if (idst < Nft + Nfs) { mdst = s->st.fs_inward[idst - Nft] ? i + 1 : i; px = &FG(x0, Nf, dst, k, mdst, j); pb = &FG(xb, Nf, dst, k, mdst, j); }
+          else { mdst = s->st.fs_inward[idst - Nft - Nfs] ? j + 1 : j; px = &FG(x0, Nf, dst, k, i, mdst); pb = &FG(xb, Nf, dst, k, i, mdst); }
+          sigma = 0; src = 0;
+          for (isrc = 0; isrc < Nft; ++isrc, ++src) { msrc = s->st.ft_inward[isrc] ? k : k + 1; sigma = sigma + FG(x0, Nf, src, msrc, i, j) * v[dst * Nf + src]; }
+          for (isrc = 0; isrc < Nfs; ++isrc, ++src) { msrc = s->st.fs_inward[isrc] ? i : i + 1; sigma = sigma + FG(x0, Nf, src, k, msrc, j) * v[dst * Nf + src]; }
+          for (isrc = 0; isrc < Nfs; ++isrc, ++src) { msrc = s->st.fs_inward[isrc] ? j : j + 1; sigma = sigma + FG(x0, Nf, src, k, i, msrc) * v[dst * Nf + src]; }
+          *px = (1.0 - omega) * (*px) + omega * (*pb + sigma);
+        }
+      }
+    }
+  if (dzr[2] > 0) {
+    for (j = dyr[0]; j != dyr[1] + dyr[2]; j += dyr[2]) for (i = dxr[0]; i != dxr[1] + dxr[2]; i += dxr[2])
+      for (idst = 0; idst < Nft; ++idst) if (!s->st.ft_inward[idst])
+        FG(x0, Nf, idst, Nz, i, j) = FG(xb, Nf, idst, Nz, i, j) + FG(x0, Nf, inv_dof(s, idst), Nz, i, j) * A2(s->albedo, i, j);
+  }
+}
+
+/* src/pprts_explicit.F90:461-713 (explicit_ediff): alternating-direction SOR with adaptive omega */
+static int explicit_ediff(orc_solver *s, orc_solution *sol) {
+  LOCALS
+  int maxiter = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 10000, iter, converged = 0;
+  double rtol_d, atol_d, rtol, atol, rel;
+  double omega_adaptive = 1.0, omega_min = 1.0, omega_max = 1.25, omega_dir = 1.0, omega_step = 0.1 * 0.5;
+  double omega_save, log_rate, log_rate_prev = 0.0, best = DBL_MAX;
+  int iter_at_best = 1, frozen = 0;
+  const int stagnation_window = 50;
+  double *residual, *v0, *lvb;
+  determine_ksp_tolerances(s, &rtol_d, &atol_d);
+  rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d;
+  atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol->diff_sor_omega > 0.0) omega_adaptive = sol->diff_sor_omega;
+  omega_save = omega_adaptive;
+  if (sol->diff_hist[0] < 0) { maxiter = maxiter + 2; rtol = dmin(rtol, rtol_d); atol = dmin(atol, atol_d); }
+  residual = (double *)calloc(maxiter + 1, sizeof(double));
+  v0 = (double *)calloc(ngh(s, Nf), sizeof(double));
+  lvb = (double *)calloc(ngh(s, Nf), sizeof(double));
+  interior_to_ghosted(s, Nf, sol->ediff, v0);
+  fill_ghost(s, Nf, v0);
+  interior_to_ghosted(s, Nf, s->b, lvb);
+  fill_ghost(s, Nf, lvb);
+  sol->Niter_diff = 0;
+  for (iter = 1; iter <= maxiter; ++iter) {
+    if ((iter + 1) % 2 == 0) {
+      int dxr[3] = {0, Nx - 1, 1}, dyr[3] = {0, Ny - 1, 1}, dzr[3] = {0, Nz - 1, 1};
+      explicit_ediff_sor_sweep(s, dxr, dyr, dzr, omega_adaptive, lvb, v0);
+    } else {
+      int dxr[3] = {Nx - 1, 0, -1}, dyr[3] = {Ny - 1, 0, -1}, dzr[3] = {Nz - 1, 0, -1};
+      explicit_ediff_sor_sweep(s, dxr, dyr, dzr, omega_adaptive, lvb, v0);
+    }
+    exchange_diffuse_boundary(s, v0);
+    residual[iter] = norm2_diff_and_copy(s, Nf, sol->ediff, v0);
+    rel = (residual[1] <= sqrt(DBL_MIN)) ? 0.0 : residual[iter] / residual[1];
+    sol->diff_hist[(iter < ORC_NHIST ? iter : ORC_NHIST) - 1] = residual[iter];
+    sol->Niter_diff = iter;
+    sol->final_res_diff = residual[iter];
+    if (residual[iter] < atol || rel < rtol) { converged = 1; break; }
+    if (residual[iter] < best) { best = residual[iter]; iter_at_best = iter; }
+    if (iter >= 3) {
+      if (!frozen && omega_adaptive > omega_min && (iter - iter_at_best) > stagnation_window) {
+        omega_adaptive = omega_min; omega_save = omega_adaptive; frozen = 1;
+      }
+      if (!frozen && residual[iter] > 0.0 && residual[iter - 2] > 0.0) {
+        log_rate = 0.5 * log(residual[iter] / residual[iter - 2]);
+        if (log_rate < log_rate_prev) omega_step = dmin(omega_step * 1.3, omega_max - omega_min);
+        else { omega_dir = -omega_dir; omega_step = dmax(omega_step * 0.5, 0.01); }
+        log_rate_prev = log_rate;
+        omega_adaptive = dmin(dmax(omega_adaptive + omega_dir * omega_step, omega_min), omega_max);
+        omega_save = omega_adaptive;
+      }
+    }
+  }
+  sol->diff_sor_omega = omega_save;
+  ghosted_to_interior(s, Nf, v0, sol->ediff);
+  sol->lchanged = 1;
+  sol->lWm2_diff = 0;
+  free(residual); free(v0); free(lvb);
+  return converged ? 0 : 1;
+}
+
+/* Unpreconditioned BiCGStab on the shell operator with the convergence test of MyKSPConverged
+ * (src/pprts.F90:4437-4486: r/r0 <= rtol or r <= atol, checked from iteration 1; nonzero initial guess :4343).
+ * PETSc's KSPFBCGS+ILU itself is third-party and not restated; any converged Krylov method yields the same x. */
+static double dot_(const double *a, const double *b, long n) { double s = 0; long i; for (i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+static int bicgstab_ediff(orc_solver *s, orc_solution *sol) {
+  long n = nin(s, s->st.Nf), i;
+  int maxit = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 1000, it, converged = 0;
+  double rtol_d, atol_d, rtol, atol, rho = 1, alpha = 1, omega = 1, rho1, beta, r0n, rn, tt;
+  double *x = sol->ediff, *r = (double *)malloc(sizeof(double) * n), *rh = (double *)malloc(sizeof(double) * n);
+  double *p = (double *)calloc(n, sizeof(double)), *v = (double *)calloc(n, sizeof(double));
+  double *sv = (double *)malloc(sizeof(double) * n), *t = (double *)malloc(sizeof(double) * n);
+  determine_ksp_tolerances(s, &rtol_d, &atol_d);
+  rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d;
+  atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol->diff_hist[0] < 0) { rtol = dmin(rtol, rtol_d); atol = dmin(atol, atol_d); }
+  orc_mat_mult_ediff(s, x, r);
+  for (i = 0; i < n; ++i) { r[i] = s->b[i] - r[i]; rh[i] = r[i]; }
+  r0n = dmax(DBL_MIN, sqrt(dot_(r, r, n)));
+  sol->diff_hist[0] = r0n;
+  sol->Niter_diff = 0;
+  for (it = 1; it <= maxit; ++it) {
+    rho1 = dot_(rh, r, n);
+    beta = (rho1 / rho) * (alpha / omega);
+    for (i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+    orc_mat_mult_ediff(s, p, v);
+    alpha = rho1 / dot_(rh, v, n);
+    for (i = 0; i < n; ++i) sv[i] = r[i] - alpha * v[i];
+    orc_mat_mult_ediff(s, sv, t);
+    tt = dot_(t, t, n);
+    omega = tt > 0 ? dot_(t, sv, n) / tt : 0.0;
+    for (i = 0; i < n; ++i) { x[i] += alpha * p[i] + omega * sv[i]; r[i] = sv[i] - omega * t[i]; }
+    rho = rho1;
+    rn = sqrt(dot_(r, r, n));
+    sol->diff_hist[(it < ORC_NHIST ? it : ORC_NHIST - 1)] = rn;
+    sol->Niter_diff = it;
+    sol->final_res_diff = rn;
+    if (rn / r0n <= rtol || rn <= atol) { converged = 1; break; }
+    if (omega == 0.0 || isnan(rn)) break;
+  }
+  sol->lchanged = 1;
+  sol->lWm2_diff = 0;
+  free(r); free(rh); free(p); free(v); free(sv); free(t);
+  return converged ? 0 : 1;
+}
+
+/* ---- absorption (src/pprts.F90:5152-5504) ----------------------------------------------------------------------- */
+static void calc_flx_div(orc_solver *s, orc_solution *sol) {
+  LOCALS
+  int i, j, k, isrc, idof, msrc, src, dst;
+  double cdiv, sum;
+  double *ledir = 0, *lediff = (double *)calloc(ngh(s, Nf), sizeof(double));
+  const int xinc = s->xinc, yinc = s->yinc;
+  memset(sol->abso, 0, sizeof(double) * (long)Nz * Nx * Ny);
+  scale_flx(s, sol, 0);
+  if (sol->lsolar_rad) {
+    ledir = (double *)calloc(ngh(s, Nd), sizeof(double));
+    interior_to_ghosted(s, Nd, sol->edir, ledir);
+    halo_fill_5pt(s, Nd, ledir);
+  }
+  interior_to_ghosted(s, Nf, sol->ediff, lediff);
+  halo_fill_5pt(s, Nf, lediff);
+  if (s->cfg.by_coeff_divergence) {
+    if (sol->lsolar_rad) {
+      for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+        if (s->l1d[k]) {
+          for (isrc = 0; isrc < Ndt; ++isrc) {
+            cdiv = A3(s->kabs, k, i, j) * A3(s->dz, k, i, j) / s->costheta;
+            A3(sol->abso, k, i, j) += FG(ledir, Nd, isrc, k, i, j) * (-expm1(-cdiv));
+          }
+        } else {
+          const double *c1 = &CF(s->dir2dir, Nd * Nd, 0, k, i, j), *c2 = &CF(s->dir2diff, Nd * Nf, 0, k, i, j);
+          idof = 0;
+          for (isrc = 0; isrc < Ndt + 2 * Nds; ++isrc, ++idof) {
+            double sum1 = 0, sum2 = 0, e;
+            for (dst = 0; dst < Nd; ++dst) sum1 += c1[dst * Nd + idof];
+            for (dst = 0; dst < Nf; ++dst) sum2 += c2[dst * Nd + idof];
+            cdiv = 1.0 - sum1 - sum2;
+            if (isrc < Ndt) e = FG(ledir, Nd, idof, k, i, j);
+            else if (isrc < Ndt + Nds) e = FG(ledir, Nd, idof, k, i + 1 - xinc, j);
+            else e = FG(ledir, Nd, idof, k, i, j + 1 - yinc);
+            A3(sol->abso, k, i, j) += e * cdiv;
+          }
+        }
+      }
+    }
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+      if (!s->l1d[k]) {
+        const double *c = &CF(s->diff2diff, Nf * Nf, 0, k, i, j);
+        idof = 0;
+        for (isrc = 0; isrc < Nft + 2 * Nfs; ++isrc, ++idof) {
+          double e;
+          sum = 0; for (dst = 0; dst < Nf; ++dst) sum += c[dst * Nf + idof];
+          cdiv = 1.0 - sum;
+          if (isrc < Nft) { msrc = s->st.ft_inward[isrc] ? k : k + 1; e = FG(lediff, Nf, idof, msrc, i, j); }
+          else if (isrc < Nft + Nfs) { msrc = s->st.fs_inward[isrc - Nft] ? i : i + 1; e = FG(lediff, Nf, idof, k, msrc, j); }
+          else { msrc = s->st.fs_inward[isrc - Nft - Nfs] ? j : j + 1; e = FG(lediff, Nf, idof, k, i, msrc); }
+          A3(sol->abso, k, i, j) += e * cdiv;
+        }
+      } else {
+        cdiv = dmax(0.0, 1.0 - A3(s->a11, k, i, j) - A3(s->a12, k, i, j));
+        for (isrc = 0; isrc < Nft; ++isrc) {
+          msrc = s->st.ft_inward[isrc] ? k : k + 1;
+          A3(sol->abso, k, i, j) += FG(lediff, Nf, isrc, msrc, i, j) * cdiv;
+        }
+      }
+    }
+    if (sol->lthermal_rad) {
+      double *lsrc = (double *)calloc(ngh(s, Nf), sizeof(double));
+      interior_to_ghosted(s, Nf, s->b, lsrc);
+      halo_fill_5pt(s, Nf, lsrc);
+      for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+        idof = 0;
+        for (isrc = 0; isrc < Nft; ++isrc, ++idof) { msrc = s->st.ft_inward[isrc] ? k + 1 : k; A3(sol->abso, k, i, j) -= FG(lsrc, Nf, idof, msrc, i, j); }
+        for (isrc = 0; isrc < Nfs; ++isrc, ++idof) { msrc = s->st.fs_inward[isrc] ? i + 1 : i; A3(sol->abso, k, i, j) -= FG(lsrc, Nf, idof, k, msrc, j); }
+        for (isrc = 0; isrc < Nfs; ++isrc, ++idof) { msrc = s->st.fs_inward[isrc] ? j + 1 : j; A3(sol->abso, k, i, j) -= FG(lsrc, Nf, idof, k, i, msrc); }
+      }
+      free(lsrc);
+    }
+  } else { /* by flux divergence :5400-5472 */
+    if (sol->lsolar_rad) {
+      for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+        if (s->l1d[k]) {
+          for (isrc = 0; isrc < Ndt; ++isrc) A3(sol->abso, k, i, j) += FG(ledir, Nd, isrc, k, i, j) - FG(ledir, Nd, isrc, k + 1, i, j);
+        } else {
+          src = 0;
+          for (isrc = 0; isrc < Ndt; ++isrc, ++src) A3(sol->abso, k, i, j) += FG(ledir, Nd, src, k, i, j) - FG(ledir, Nd, src, k + 1, i, j);
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) A3(sol->abso, k, i, j) += FG(ledir, Nd, src, k, i + 1 - xinc, j) - FG(ledir, Nd, src, k, i + xinc, j);
+          for (isrc = 0; isrc < Nds; ++isrc, ++src) A3(sol->abso, k, i, j) += FG(ledir, Nd, src, k, i, j + 1 - yinc) - FG(ledir, Nd, src, k, i, j + yinc);
+        }
+      }
+    }
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+      src = 0;
+      for (isrc = 0; isrc < Nft; ++isrc, ++src) {
+        if (s->st.ft_inward[isrc]) A3(sol->abso, k, i, j) += FG(lediff, Nf, src, k, i, j) - FG(lediff, Nf, src, k + 1, i, j);
+        else A3(sol->abso, k, i, j) += FG(lediff, Nf, src, k + 1, i, j) - FG(lediff, Nf, src, k, i, j);
+      }
+      if (s->l1d[k]) continue;
+      for (isrc = 0; isrc < Nfs; ++isrc, ++src) {
+        if (s->st.fs_inward[isrc]) A3(sol->abso, k, i, j) += FG(lediff, Nf, src, k, i, j) - FG(lediff, Nf, src, k, i + 1, j);
+        else A3(sol->abso, k, i, j) += FG(lediff, Nf, src, k, i + 1, j) - FG(lediff, Nf, src, k, i, j);
+      }
+      for (isrc = 0; isrc < Nfs; ++isrc, ++src) {
+        if (s->st.fs_inward[isrc]) A3(sol->abso, k, i, j) += FG(lediff, Nf, src, k, i, j) - FG(lediff, Nf, src, k, i, j + 1);
+        else A3(sol->abso, k, i, j) += FG(lediff, Nf, src, k, i, j + 1) - FG(lediff, Nf, src, k, i, j);
+      }
+    }
+  }
+  /* abso_scalevec :5477, :5483-5503 */
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k)
+    A3(sol->abso, k, i, j) = A3(sol->abso, k, i, j) * (1.0 / (s->dx * s->dy * A3(s->dz, k, i, j)));
+  free(ledir); free(lediff);
+}
+
+/* ---- solve_pprts / pprts / restore_solution (src/pprts.F90:2487-3033, :3991-4076) ---------------------------------- */
+static orc_solution *prepare_solution(orc_solver *s, int lsolar, int lthermal) { /* src/pprts_base.F90:298-344 */
+  orc_solution *sol = (orc_solution *)calloc(1, sizeof(orc_solution));
+  int h;
+  sol->lset = 1; sol->lsolar_rad = lsolar; sol->lthermal_rad = lthermal; sol->lchanged = 1;
+  sol->lWm2_dir = 1; sol->lWm2_diff = 1;
+  sol->edir = (double *)calloc(nin(s, s->st.Nd), sizeof(double));
+  sol->ediff = (double *)calloc(nin(s, s->st.Nf), sizeof(double));
+  sol->abso = (double *)calloc((long)s->Nz * s->Nx * s->Ny, sizeof(double));
+  for (h = 0; h < ORC_NHIST; ++h) { sol->dir_hist[h] = -1; sol->diff_hist[h] = -1; }
+  sol->diff_sor_omega = -1;
+  return sol;
+}
+
+int orc_solve(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid) {
+  orc_solution *sol;
+  int derived_lsolar, rc = 0;
+  long n, N;
+  double b_norm, rtol, atol;
+  if (!s->have_optprop) return 10;
+  if (uid < ORC_UID_MIN || uid > ORC_UID_MAX) return 11;
+  if (lthermal && !s->have_planck) return 12;
+  derived_lsolar = lsolar && edirTOA > 0.0 && s->theta >= 0.0;
+  if (derived_lsolar && lthermal) return 13; /* src/pprts.F90:2523-2530 */
+  sol = s->sol[uid - ORC_UID_MIN];
+  if (!sol) {
+    sol = s->sol[uid - ORC_UID_MIN] = prepare_solution(s, derived_lsolar, lthermal);
+    /* -initial_guess_from_last_uid (default on), src/pprts.F90:2542-2558 */
+    if (uid - 1 >= ORC_UID_MIN && s->sol[uid - 1 - ORC_UID_MIN] && s->sol[uid - 1 - ORC_UID_MIN]->lset) {
+      orc_solution *last = s->sol[uid - 1 - ORC_UID_MIN];
+      if (last->lsolar_rad) { memcpy(sol->edir, last->edir, sizeof(double) * nin(s, s->st.Nd)); sol->lWm2_dir = last->lWm2_dir; }
+      memcpy(sol->ediff, last->ediff, sizeof(double) * nin(s, s->st.Nf));
+      sol->lWm2_diff = last->lWm2_diff;
+    }
+  } else if (sol->lsolar_rad != derived_lsolar) {
+    free_solution(sol);
+    sol = s->sol[uid - ORC_UID_MIN] = prepare_solution(s, derived_lsolar, lthermal);
+  }
+  if (!sol->lthermal_rad && !sol->lsolar_rad) { /* :2590-2596 */
+    memset(sol->edir, 0, sizeof(double) * nin(s, s->st.Nd));
+    memset(sol->ediff, 0, sizeof(double) * nin(s, s->st.Nf));
+    memset(sol->abso, 0, sizeof(double) * (long)s->Nz * s->Nx * s->Ny);
+    sol->lchanged = 0;
+    return 0;
+  }
+  /* pprts(), :2668-3033 */
+  alloc_coeffs(s, sol->lsolar_rad);
+  scale_flx(s, sol, 0);
+  if (sol->lsolar_rad) rc |= explicit_edir(s, edirTOA, sol);
+  setup_b(s, sol);
+  determine_ksp_tolerances(s, &rtol, &atol);
+  N = nin(s, s->st.Nf);
+  b_norm = 0; for (n = 0; n < N; ++n) b_norm += fabs(s->b[n]);
+  if (b_norm < atol) { /* :2776-2784 */
+    memcpy(sol->ediff, s->b, sizeof(double) * N);
+    sol->Niter_diff = 0;
+    for (n = 0; n < ORC_NHIST; ++n) sol->diff_hist[n] = atol;
+  } else {
+    if (s->cfg.diff_solver == 0) rc |= explicit_ediff(s, sol) << 1;
+    else rc |= bicgstab_ediff(s, sol) << 1;
+  }
+  sol->lchanged = 1;
+  sol->lWm2_diff = 0;
+  /* restore_solution :3991-4033 */
+  calc_flx_div(s, sol);
+  scale_flx(s, sol, 1);
+  sol->lchanged = 0;
+  return rc;
+}
+
+/* src/pprts.F90:5799-5917 (pprts_get_result) */
+int orc_get_result(orc_solver *s, int uid, double *edn, double *eup, double *abso, double *edir) {
+  LOCALS
+  orc_solution *sol;
+  int k, i, j, d;
+  if (uid < ORC_UID_MIN || uid > ORC_UID_MAX || !(sol = s->sol[uid - ORC_UID_MIN])) return 1;
+  if (sol->lchanged) return 2;
+  if (!sol->lWm2_diff) return 3;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) {
+    for (k = 0; k < Nz1; ++k) {
+      double dn = 0, up = 0, dr = 0;
+      for (d = 0; d < Nft; ++d) {
+        if (s->st.ft_inward[d]) dn = dn + FI(sol->ediff, Nf, d, k, i, j) / 1.0;
+        else up = up + FI(sol->ediff, Nf, d, k, i, j) / 1.0;
+      }
+      if (sol->lsolar_rad) {
+        for (d = 0; d < Ndt; ++d) dr += FI(sol->edir, Nd, d, k, i, j);
+        dr = dr / (double)s->st.dirtop_adiv;
+        dr *= s->mu; dn *= s->mu; up *= s->mu;
+      }
+      P3(edn, k, i, j) = dn; P3(eup, k, i, j) = up;
+      if (edir) P3(edir, k, i, j) = dr;
+    }
+    for (k = 0; k < Nz; ++k) A3(abso, k, i, j) = A3(sol->abso, k, i, j) * (sol->lsolar_rad ? s->mu : 1.0);
+  }
+  return 0;
+}
+
+const double *orc_coeff_ptr(orc_solver *s, int which) { return which == 1 ? s->dir2dir : which == 2 ? s->dir2diff : s->diff2diff; }
+const double *orc_state_ptr(orc_solver *s, int uid, int which) {
+  orc_solution *sol = s->sol[uid - ORC_UID_MIN];
+  if (which == 4) return s->b;
+  if (!sol) return 0;
+  return which == 1 ? sol->edir : which == 2 ? sol->ediff : sol->abso;
+}
+const int *orc_l1d_ptr(orc_solver *s) { return s->l1d; }
+void orc_get_info(orc_solver *s, int uid, int *niter_dir, int *niter_diff, double *res_dir, double *res_diff) {
+  orc_solution *sol = s->sol[uid - ORC_UID_MIN];
+  if (!sol) return;
+  *niter_dir = sol->Niter_dir; *niter_diff = sol->Niter_diff;
+  *res_dir = sol->final_res_dir; *res_diff = sol->final_res_diff;
+}

@@ -1,0 +1,126 @@
+/*
+ * pprts_oracle.h -- CPU oracle for the TenStream pprts solve path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C, fp64 restatement of the reference's own PETSc-free formulation of
+ * the path (src/pprts_explicit.F90, src/pprts_shell.F90, the optprop_LUT lookup, ...).  It exists so that the
+ * CUDA library can be parity-checked without a Fortran/MPI/PETSc toolchain.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it; the product (tenstream_b200/) never does.
+ *
+ * PARITY PINNING: the reference cannot be compiled in this environment (no gfortran/MPI/PETSc/NetCDF/fypp) and
+ * its real LUT files are not available offline.  What pins this oracle is every LUT-free known-answer test of
+ * the reference (tests/test_oracle_known_answers.py: interpolation, search, eddington, symmetry involutions,
+ * mmap round trip, scale round trip) plus the reference's property tests run on synthetic tables
+ * (absorption-by-divergence == absorption-by-coefficients, phi / phi+180 mirror symmetry, energy closure).
+ * End-to-end parity against reference-produced flux files is UNPINNED.
+ *
+ * Every function cites the reference file:line it follows (paths relative to the reference tree).
+ */
+#ifndef PPRTS_ORACLE_H
+#define PPRTS_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_DIM 6
+#define ORC_MAX_DOF 32
+
+typedef struct {
+  int solver_id;                 /* c_wrapper/f2c_solver_ids.h: 310, 810, 324 */
+  int Ndt, Nds, Nft, Nfs;        /* dirtop%dof, dirside%dof, difftop%dof, diffside%dof (src/pprts.F90:332-396) */
+  int Nd, Nf;                    /* Ndt + 2 Nds, Nft + 2 Nfs */
+  int dirtop_adiv, dirside_adiv; /* area_divider (src/pprts.F90:250-254, :362-366) */
+  int ft_inward[ORC_MAX_DOF];    /* difftop%is_inward */
+  int fs_inward[ORC_MAX_DOF];    /* diffside%is_inward */
+} orc_streams;
+
+typedef struct {
+  int ndim;                      /* 6 (direct) or 4 (diffuse) */
+  int n[ORC_MAX_DIM];
+  const float *ax[ORC_MAX_DIM];  /* axis values (fp32, as irealLUT) */
+  long off[ORC_MAX_DIM];         /* ndarray_offsets: first axis fastest */
+} orc_lut_axes;
+
+typedef struct {
+  orc_lut_axes dir, diff;
+  const float *Tdir, *Sdir, *Sdiff; /* (Ncoef, Nlattice) column major == [lattice][coef] in C */
+  int Nd, Nf;
+  void *map[3];
+  unsigned long maplen[3];
+} orc_lut;
+
+/* ---- scalar building blocks ------------------------------------------------------------------------------- */
+double orc_search_sorted_bisection(const double *arr, int n, double val);      /* src/search.fypp:177-232 */
+double orc_find_real_location_f32axis(const float *arr, int n, float val);     /* same, fp32 axis, fp64 arithmetic */
+int orc_dim_needs_interpolation(double pti);                                   /* src/interpolation.F90:546-556 */
+void orc_interp_vec_nd(const double *pti, int ndim, const float *db, int ncoef, const long *offsets,
+                       double *out);                                           /* src/interpolation.F90:317-360 */
+void orc_eddington_coeff_ec(double dtau, double w0, double g, double mu0, double *t, double *r, double *rdir,
+                            double *sdir, double *tdir);                       /* src/eddington.F90:167-242 */
+double orc_B_eff(double B_far, double B_near, double tau);                     /* src/schwarzschild.F90:36-67 */
+void orc_delta_scale(double *kabs, double *ksca, double *g);                   /* helper_functions.fypp:1622-1666 */
+int orc_streams_init(orc_streams *st, int solver_id);                          /* src/pprts.F90:256-453 */
+void orc_dir2diff_symmetry(const orc_streams *st, double *c, int lswitch_east, int lswitch_north);
+void orc_dir2dir_symmetry(const orc_streams *st, double *c, int lswitch_east, int lswitch_north);
+
+/* ---- LUT --------------------------------------------------------------------------------------------------- */
+int orc_mmap4_open(const char *path, const float **data, long *ncoef, long *nlat, void **map,
+                   unsigned long *maplen);                                     /* src/mmap.F90:129-203 */
+int orc_mmap4_write(const char *path, const float *data, long ncoef, long nlat); /* src/mmap.F90:63-127 */
+int orc_lut_load(orc_lut *lut, int solver_id, const char *path_Tdir, const char *path_Sdir,
+                 const char *path_Sdiff, const int *ndir, const float *const *axdir);
+void orc_lut_free(orc_lut *lut);
+/* src/pprts_base.F90:1491-1543 + src/optprop.F90:550-593 + src/optprop_LUT.F90:1452-1613.
+ * mode 1 = dir2dir, 2 = dir2diff, 3 = diff2diff (c_wrapper/f2c_pprts.F90:659-681). phi = symmetry_phi. */
+int orc_get_coeff(const orc_lut *lut, const orc_streams *st, double kabs, double ksca, double g, double dz,
+                  double dx, int mode, double phi, double theta, int lswitch_east, int lswitch_north,
+                  double *coeff);
+/* direct LUT-space variant used by the coefficient probe (c_wrapper/f2c_pprts.F90:628-685) */
+int orc_opp_get_coeff(const orc_lut *lut, const orc_streams *st, float tauz, float w0, float g, float aspect_zx,
+                      float phi, float theta, int mode, int lswitch_east, int lswitch_north, double *coeff);
+
+/* ---- solver ------------------------------------------------------------------------------------------------- */
+typedef struct orc_solver orc_solver;
+
+typedef struct {
+  int solver_id;
+  int Nz, Nx, Ny;
+  double dx, dy;
+  const double *dz;      /* (Nz,Nx,Ny) Fortran order: z fastest */
+  double sundir[3];
+  double twostr_ratio;   /* src/tenstream_options.F90: 2.0 */
+  int coeff_fp32;        /* 1: round stored 3-D coefficients through fp32 (what the reference's fp32 LUT path yields) */
+  int by_coeff_divergence; /* src/pprts.F90:5286 default .true. */
+  int diff_solver;       /* 0: explicit SOR (src/pprts_explicit.F90:461), 1: BiCGStab on the shell operator */
+  double rtol, atol;     /* <0: reference defaults (src/pprts_base.F90:1128-1131) */
+  int maxit_dir, maxit_diff; /* <=0: reference defaults 1000 / 10000 */
+  int nthreads;          /* OpenMP threads for the embarrassingly parallel loops (coefficients, MatMult) */
+} orc_config;
+
+orc_solver *orc_solver_create(const orc_config *cfg, const orc_lut *lut);      /* init_pprts, src/pprts.F90:213 */
+void orc_solver_destroy(orc_solver *s);
+void orc_set_angles(orc_solver *s, const double sundir[3]);                    /* src/pprts.F90:1100-1183 */
+/* set_optical_properties (src/pprts.F90:1764-2076). Arrays (Nz,Nx,Ny) / planck (Nz+1,Nx,Ny) / 2-D (Nx,Ny),
+ * Fortran order; planck, planck_srfc, albedo_2d may be NULL. */
+int orc_set_optical_properties(orc_solver *s, double albedo, const double *kabs, const double *ksca,
+                               const double *g, const double *planck, const double *planck_srfc,
+                               const double *albedo_2d, int ldelta_scaling);
+int orc_solve(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid); /* src/pprts.F90:2487-3033 */
+/* pprts_get_result (src/pprts.F90:5799-5917): edn,eup,edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny); edir may be NULL */
+int orc_get_result(orc_solver *s, int uid, double *edn, double *eup, double *abso, double *edir);
+
+/* introspection used by the parity tests */
+const double *orc_coeff_ptr(orc_solver *s, int which); /* 1 dir2dir, 2 dir2diff, 3 diff2diff: (ncoef,Nz,Nx,Ny) */
+const double *orc_state_ptr(orc_solver *s, int uid, int which); /* 1 edir (Nd,Nz+1,Nx,Ny), 2 ediff, 3 abso, 4 b */
+const int *orc_l1d_ptr(orc_solver *s);
+void orc_get_info(orc_solver *s, int uid, int *niter_dir, int *niter_diff, double *res_dir, double *res_diff);
+void orc_get_suninfo(orc_solver *s, double *phi, double *theta, double *symmetry_phi, int *xinc, int *yinc);
+/* y = (I - T) x on interior arrays (Nf,Nz+1,Nx,Ny): src/pprts_shell.F90:366-541 */
+void orc_mat_mult_ediff(orc_solver *s, const double *x, double *y);
+/* one scale_flx direction on a raw (dof,Nz+1,Nx,Ny) array; ldir selects direct/diffuse scale vector */
+void orc_scale_flx_arr(orc_solver *s, double *arr, int ldir, int lWm2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

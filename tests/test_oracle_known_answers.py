@@ -1,0 +1,223 @@
+"""Pins the CPU oracle against every LUT-free known-answer test the reference holds for the pprts path
+(SURVEY.md section 8c).  Each test names the reference test it restates."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tenstream_b200 import lut as L
+
+
+# tests/test_search/test_search.F90:13-49
+def test_search_sorted_bisection():
+    A = [-10.0, 0.0, 2.0]
+    for val, want in [(-20, 1.0), (-10, 1.0), (-7.5, 1.25), (-5, 1.5), (-0.0, 2.0), (0.0, 2.0), (1, 2.5), (2, 3.0),
+                      (3, 3.0)]:
+        assert ob.search_sorted_bisection(A, val) == want
+    for val in (-1, 1, 2):
+        assert ob.search_sorted_bisection([1.0], val) == 1.0
+    assert ob.search_sorted_bisection([0.0, 1.0], -1) == 1.0
+    assert ob.search_sorted_bisection([0.0, 1.0], 1) == 2.0
+    assert ob.search_sorted_bisection([0.0, 1.0], 2) == 2.0
+
+
+def test_search_sorted_bisection_reversed():
+    A = [10.0, 0.0, -2.0]
+    for val, want in [(20, 1.0), (10, 1.0), (7.5, 1.25), (5, 1.5), (0.0, 2.0), (-0.0, 2.0), (-1, 2.5), (-2, 3.0),
+                      (-3, 3.0)]:
+        assert ob.search_sorted_bisection(A, val) == want
+
+
+TOL32 = np.sqrt(np.finfo(np.float32).eps) * 10
+
+
+def _db(nd_array):
+    """pack(db_nd, .true.): Fortran order flattening, one coefficient per lattice point."""
+    a = np.asarray(nd_array, dtype=np.float32)
+    return a.reshape(-1, order="F")[:, None], a.shape
+
+
+# tests/interpolation/test_interp.F90:14-109
+def test_interp_2d():
+    t = np.array([[0, 2], [1, 4]], dtype=np.float32)  # t[i-1, j-1]: (1,1)=0 (2,1)=1 (1,2)=2 (2,2)=4
+    db, shape = _db(t)
+    for i in (1, 2):
+        for j in (1, 2):
+            assert ob.interp_vec_nd([i, j], db, shape)[0] == t[i - 1, j - 1]
+    for pt, want in [((1.5, 1), .5), ((1.75, 1), .75), ((1.5, 2), 3.), ((1.75, 2), 3.5), ((1, 1.5), 1.),
+                     ((1, 1.75), 1.5), ((2, 1.5), 2.5), ((2, 1.75), 3.25)]:
+        assert abs(ob.interp_vec_nd(pt, db, shape)[0] - want) < TOL32
+    db, shape = _db(np.array([[0, 2], [2, 4]]))
+    assert abs(ob.interp_vec_nd((1.5, 1.5), db, shape)[0] - 2.0) < TOL32
+    db, shape = _db(np.array([[0, 2], [0, 2]]))
+    for j in range(10):
+        for i in range(10):
+            got = ob.interp_vec_nd((np.float32(1 + i * .1), np.float32(1 + j * .1)), db, shape)[0]
+            assert abs(got - j * .1 * 2) < TOL32
+
+
+# tests/interpolation/test_interp.F90:111-160
+def test_interp_3d():
+    t = np.zeros((2, 2, 2), dtype=np.float32)
+    t[:, :, 0] = [[0, 2], [2, 4]]
+    t[:, :, 1] = [[10, 12], [12, 14]]
+    db, shape = _db(t)
+    for i in (1, 2):
+        for j in (1, 2):
+            for k in (1, 2):
+                assert ob.interp_vec_nd((i, j, k), db, shape)[0] == t[i - 1, j - 1, k - 1]
+    assert abs(ob.interp_vec_nd((1.5, 1.5, 1.5), db, shape)[0] - t.mean()) < TOL32
+
+
+# tests/interpolation/test_interp.F90:395-527
+def test_interp_6d():
+    Nv = 4
+    idx = np.indices((Nv,) * 6).astype(np.float32) + 1
+
+    def x(i, j, k, l, m, n):
+        return i + 2 * j + 8 * k + 16 * l + 32 * m + 64 * n
+
+    t1 = x(*idx)
+    t2 = x(*(2 * idx))
+    db = np.stack([t1.reshape(-1, order="F"), t2.reshape(-1, order="F")], axis=1).astype(np.float32)
+    shape = (Nv,) * 6
+    rng = np.random.default_rng(0)
+    pts = [tuple(rng.integers(1, Nv, 6)) for _ in range(60)] + [(1,) * 6, (Nv - 1,) * 6]
+    for p in pts:
+        p = np.array(p, dtype=np.float64)
+        r = ob.interp_vec_nd(p, db, shape)
+        assert r[0] == x(*p) and r[1] == x(*(2 * p))
+        r = ob.interp_vec_nd(p + .5, db, shape)
+        assert r[0] == x(*(p + .5)) and r[1] == x(*(2 * (p + .5)))
+
+
+# src/interpolation.F90:63, :546-556
+def test_lattice_snapping():
+    db, shape = _db(np.array([0.0, 1.0]))
+    assert ob.interp_vec_nd([1.0005], db, shape)[0] == 0.0      # snapped down
+    assert ob.interp_vec_nd([1.9995], db, shape)[0] == 1.0      # snapped up
+    assert abs(ob.interp_vec_nd([1.002], db, shape)[0] - 0.002) < 1e-12
+
+
+EDD_CASES = [  # tests/eddington/test_delta_eddington.F90:20-142: (tau, w0, g, mu0) -> (a11, a12, a13, a23, a33)
+    ((0.4824516550e-01, 0.5542391539, 0.4550637007, 0.5), (0.947543502, 1.03599848e-02, 1.65330153e-02, 3.33561152e-02, 0.908018649)),
+    ((0.4824516550e-01, 0.5542391539, 0.4550637007, 1.0), (0.947543502, 1.03599848e-02, 4.14878177e-03, 2.13973932e-02, 0.952900112)),
+    ((0.2018013448, 0.3797843754, 0.4556422830, 1.0), (0.754876196, 2.39296965e-02, 1.03387358e-02, 5.08127585e-02, 0.817257285)),
+    ((0.1731484532, 0.6180083156, 0.4121485054, 1.0), (0.836549520, 3.96644436e-02, 1.88425109e-02, 7.29937181e-02, 0.841012776)),
+    ((0.1931012775e-04, 0.4384377003, -0.0, 0.7070999742), (0.999971986, 6.34953813e-06, 6.10753023e-06, 4.93132757e-06, 0.999972701)),
+    ((4.895462513, 0.3104626103e-05, -0.0, 0.49999997019767761), (5.59581749e-05, 5.82118503e-07, 7.76157776e-07, 8.66550609e-10, 5.59570581e-05)),
+    ((3.2662250689525390e-011, 0.99999171495417127, 0.0, 0.17364817766693041), (1.0, 2.45013107e-11, 9.40557285e-11, 9.40355432e-11, 1.0)),
+    ((2.9317851124478626e-012, 1.0, 0.0, 0.17364817766693041), (0.99999999999779732, 2.2026824808563106e-012, 8.4443208651779663e-012, 8.4384068595938508e-012, 0.99999999998311651)),
+    ((1.93321303e-10, 0.999984443, 2.22044605e-16, 0.17364817766693041), (0.99999999985500665, 1.4499335065920604e-010, 5.5664139018583103e-010, 5.5664738411040951e-010, 0.99999999888670699)),
+    ((7.89528581e-11, 0.999988437, 2.22044605e-16, 0.17364817766693041), (0.99999999994077626, 5.9209526170889148e-011, 2.2734076817292897e-010, 2.2733741157516502e-010, 0.99999999954532859)),
+    ((1.3865453490508738e-011, 0.99999499320987351, 0.0, 0.17364817766693041), (0.99999999998959765, 1.0402345651527867e-011, 3.9931125946960987e-011, 3.9926650483275707e-011, 0.99999999992015198)),
+    ((113.59224626216431, 2.7005225550306174e-008, 0.0, 0.17364817766693041), (0.0, 0.0, 9.6352077372196252e-009, 4.1335735289420085e-024, 0.0)),
+    ((1.4503301e-02, 1.5233955e-12, 1.1920928e-07, 1.0), (0.971410036, 1.60991978e-14, 1.08102478e-14, 1.08094940e-14, 0.985601366)),
+]
+
+
+@pytest.mark.parametrize("inp,targ", EDD_CASES)
+def test_eddington_ec(inp, targ):
+    out = ob.eddington_coeff_ec(*inp)
+    tol = 1e-4
+    assert np.all(np.abs(out - np.array(targ)) <= tol)
+    assert out[:2].sum() < 1 + tol and out[2:].sum() < 1 + tol
+    assert np.all(out >= 0) and np.all(out <= 1)
+
+
+# tests/test_pprts_symmetry/test_pprts_symmetry.F90:315-391: the permutations are involutions
+@pytest.mark.parametrize("solver_id", [310, 810, 324])
+def test_symmetry_involution(solver_id):
+    st = ob.streams(solver_id)
+    c = np.arange(1, st.Nd * st.Nf + 1, dtype=np.float64)
+    for le, ln in [(True, False), (False, True), (True, True)]:
+        once = ob.dir2diff_symmetry(solver_id, c, le, ln)
+        if solver_id != 324 or True:
+            assert not np.array_equal(once, c)
+        twice = ob.dir2diff_symmetry(solver_id, once, le, ln)
+        assert np.array_equal(twice, c)
+    c = np.arange(1, st.Nd * st.Nd + 1, dtype=np.float64)
+    for le, ln in [(True, False), (False, True), (True, True)]:
+        once = ob.dir2dir_symmetry(solver_id, c, le, ln)
+        assert (st.Nd == 8) != np.array_equal(once, c)       # src/optprop.F90:1256-1266: none for 3 streams
+        assert np.array_equal(ob.dir2dir_symmetry(solver_id, once, le, ln), c)
+
+
+# src/optprop.F90:1009-1045 spelled out for 3_10: east swaps dst blocks 3<->4, 5<->6 (1-based); north 7<->8, 9<->10
+def test_symmetry_3_10_blocks():
+    c = np.arange(30, dtype=np.float64)
+    e = ob.dir2diff_symmetry(310, c, True, False).reshape(10, 3)
+    assert np.array_equal(e, c.reshape(10, 3)[[0, 1, 3, 2, 5, 4, 6, 7, 8, 9]])
+    n = ob.dir2diff_symmetry(310, c, False, True).reshape(10, 3)
+    assert np.array_equal(n, c.reshape(10, 3)[[0, 1, 2, 3, 4, 5, 7, 6, 9, 8]])
+
+
+# tests/test_mmap/: header + payload round trip, and byte-compatibility of the C and numpy writers
+def test_mmap4_roundtrip(tmp_path):
+    rng = np.random.default_rng(1)
+    t = rng.random((37, 9), dtype=np.float32)
+    p1, p2 = str(tmp_path / "a.mmap4"), str(tmp_path / "b.mmap4")
+    L.write_mmap4(p1, t)
+    assert ob.mmap4_write(p2, t) == 0
+    assert open(p1, "rb").read() == open(p2, "rb").read()
+    hdr = np.fromfile(p1, dtype=np.uint64, count=5)
+    assert list(hdr) == [4, 37 * 9, 37 * 9 * 4, 9, 37]            # src/mmap.F90:85-93
+    assert np.array_equal(ob.mmap4_read(p1), t)
+    assert np.array_equal(np.asarray(L.read_mmap4(p2)), t)
+
+
+# src/helper_functions.fypp:1622-1666
+def test_delta_scale():
+    kabs, ksca, g = ob.delta_scale(1e-3, 1e-2, 0.85)
+    f = 0.85 ** 2
+    dtau, w0 = 1.1e-2, 1e-2 / 1.1e-2
+    assert abs(g - (0.85 - f) / (1 - f)) < 1e-15
+    assert abs((kabs + ksca) - dtau * (1 - w0 * f)) < 1e-18
+    assert abs(kabs - 1e-3) < 1e-15                                   # absorption is invariant
+    assert ob.delta_scale(0.0, 0.0, 0.5) == (0.0, 0.0, 0.5)
+    k, s, gg = ob.delta_scale(1.0, 2.0, 1.0)
+    assert (s, gg) == (0.0, 0.0) and abs(k - 1.0) < 1e-15
+
+
+# src/schwarzschild.F90:36-67: limits of the effective Planck emission
+def test_B_eff():
+    assert abs(ob.B_eff(3.0, 5.0, 1e-9) - 4.0) < 1e-12        # optically thin: mean
+    assert abs(ob.B_eff(2.0, 2.0, 0.7) - 2.0) < 1e-12         # isothermal
+    thick = ob.B_eff(0.0, 1.0, 1e4)
+    assert 0.99 < thick <= 1.0                                # optically thick: near-side value
+    assert ob.B_eff(1.0, 2.0, 1.0) > ob.B_eff(2.0, 1.0, 1.0)
+
+
+# src/pprts.F90:1118-1183 (setup_suninfo): folding of the azimuth and the x/y increments
+@pytest.mark.parametrize("phi,sym,xinc,yinc", [(10, 10, 0, 0), (100, 80, 0, 1), (190, 10, 1, 1), (280, 80, 1, 0),
+                                               (0, 0, 1, 0), (180, 0, 1, 1), (120, 60, 0, 1)])
+def test_suninfo(oracle_lut, phi, sym, xinc, yinc):
+    s = ob.OracleSolver(oracle_lut, 2, 3, 3, 100., 100., ob.sundir_from_angles(phi, 40.), np.full(2, 50.))
+    info = s.suninfo()
+    assert abs(info["symmetry_phi"] - sym) < 1e-9 and abs(info["theta"] - 40) < 1e-9
+    if phi not in (0, 180):   # sin(180 deg) is +-1e-16: the branch is decided by rounding, as in the reference
+        assert info["xinc"] == xinc
+    assert info["yinc"] == yinc
+    s.destroy()
+
+
+# tests/test_pprts_solution_vecscale/: W <-> W/m2 scaling twice is the identity
+def test_scale_roundtrip(oracle_lut):
+    Nz, Nx, Ny = 4, 3, 5
+    s = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 120., 120., ob.sundir_from_angles(0, 20.), np.linspace(30, 90, Nz))
+    rng = np.random.default_rng(3)
+    for ldir, nd in ((1, 3), (0, 10)):
+        a = rng.random((nd, Nz + 1, Nx, Ny))
+        w = s.scale_flx_arr(a, ldir, 0)
+        back = s.scale_flx_arr(w, ldir, 1)
+        assert np.allclose(back, a, rtol=4e-16, atol=0)
+        assert np.array_equal(w[nd // 3:, Nz], a[nd // 3:, Nz])       # side dofs below ground scaled by 1
+        assert np.allclose(w[0], a[0] * 120. * 120.)
+    s.destroy()
+
+
+# src/pprts.F90:649-725
+def test_determine_1d_layers(oracle_lut):
+    dz = np.array([500., 300., 150., 250., 100., 50.])
+    s = ob.OracleSolver(oracle_lut, 6, 3, 3, 100., 100., ob.sundir_from_angles(0, 20.), dz, twostr_ratio=2.0)
+    assert list(s.l1d) == [True, True, True, True, False, False]       # lowest thick layer (k=3) and all above
+    s.destroy()

@@ -1,0 +1,159 @@
+/*
+ * pprts_b200.h -- C ABI of libpprts_b200.so: the TenStream pprts solve path on B200 (sm_100a).
+ *
+ * Two layers, both plain C (pointers + sizes, host memory unless stated otherwise):
+ *
+ *  1. pprts_f2c_*  : the entry points the reference's own C wrapper exports (c_wrapper/f2c_pprts.h:61-99,
+ *                    implemented in c_wrapper/f2c_pprts.F90).  Same names, same argument meaning, same "abort on
+ *                    error" behaviour, so c_wrapper/pprts.c links against this library unchanged.
+ *  2. pprts_b200_* : a handle-based API one level lower, which is what a Fortran ISO_C_BINDING shim binds to
+ *                    (fortran/m_pprts_b200.F90).  It mirrors the Fortran module API of src/pprts.F90:192-200:
+ *                    init_pprts / set_angles / set_optical_properties / solve_pprts / pprts_get_result /
+ *                    destroy_pprts.  Every function returns 0 on success; pprts_b200_last_error() has the text.
+ *
+ * Array conventions of layer 2 are the reference's Fortran ones: 3-D fields are (Nz, Nx, Ny) column-major, i.e.
+ * z fastest in memory, index 0 = top of atmosphere; level fields are (Nz+1, Nx, Ny); 2-D fields (Nx, Ny).
+ * There is no CPU fallback: every call that computes needs a CUDA device.
+ */
+#ifndef PPRTS_B200_H
+#define PPRTS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layer 1: drop-in for c_wrapper/f2c_pprts.h
+ * ------------------------------------------------------------------------------------------------------------ */
+#define SOLVER_ID_PPRTS_3_10 310 /* c_wrapper/f2c_solver_ids.h */
+#define SOLVER_ID_PPRTS_3_24 324
+#define SOLVER_ID_PPRTS_8_10 810
+
+/* c_wrapper/f2c_pprts.F90:130-284.  fcomm is the caller's Fortran MPI communicator handle; inside one box the
+ * library runs one process per GPU and does not use it.  Scalars are in/out like the reference (rank 0's values
+ * are "broadcast back").  hhl: Nz+1 level heights [m], TOA first.  LUT files are located through the
+ * environment variable PPRTS_B200_LUT_BASENAME (fallback LUT_BASENAME, default "./LUT"), the reference's
+ * -lut_basename option (src/optprop_LUT.F90:503-518). */
+void pprts_f2c_init(int fcomm, int *solver_id, int *Nz, int *Nx, int *Ny, double *dx, double *dy, float *hhl,
+                    float *phi0, float *theta0, int *collapseindex);
+/* c_wrapper/f2c_pprts.F90:286-323. arrays [Ny][Nx][Nz] (planck [Ny][Nx][Nz+1]) in C order; planck used iff any > 0 */
+void pprts_f2c_set_global_optical_properties(int Nz, int Nx, int Ny, float *albedo, float *kabs, float *ksca,
+                                             float *g, float *planck);
+/* c_wrapper/f2c_pprts.F90:325-356: solar iff edirTOA > 0, thermal otherwise */
+void pprts_f2c_solve(int fcomm, float edirTOA);
+/* c_wrapper/f2c_pprts.F90:358-406: W/m2 on levels [Ny][Nx][Nz+1], abso W/m3 [Ny][Nx][Nz] */
+void pprts_f2c_get_result(int Nz, int Nx, int Ny, float *edn, float *eup, float *abso, float *edir);
+/* c_wrapper/f2c_pprts.F90:458-478: by VALUE in the implementation (the header's int* prototype is stale) */
+void pprts_f2c_destroy(int lfinalizepetsc);
+
+/* coefficient probe, c_wrapper/f2c_pprts.F90:591-758.  imode 1 = dir2dir, 2 = dir2diff, 3 = diff2diff;
+ * coeff is [dst][src] float. */
+void pprts_f2c_opp_init(const int comm, const int solver_id, void **opp, int *ierr);
+void pprts_f2c_opp_get_coeff(void *opp, const float tauz, const float w0, const float g, const float aspect_zx,
+                             const float phi, const float theta, const int imode, const int lswitch_east,
+                             const int lswitch_north, const int Ncoeff, float *coeff, int *ierr);
+void pprts_f2c_opp_destroy(void *opp, int *ierr);
+void pprts_f2c_opp_get_info(void *opp, int *Ndir, int *Ndiff, float *diff_tauz_range, float *diff_w0_range,
+                            float *diff_g_range, float *diff_aspect_zx_range, float *dir_tauz_range,
+                            float *dir_w0_range, float *dir_g_range, float *dir_aspect_zx_range,
+                            float *dir_phi_range, float *dir_theta_range, int *ierr);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layer 2: handle-based API (what fortran/m_pprts_b200.F90 binds)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct pprts_b200_solver pprts_b200_solver;
+typedef struct pprts_b200_lut pprts_b200_lut;
+
+/* optprop tables (src/optprop_LUT.F90:186-330, :1336-1435): the three .mmap4 files are memory-mapped on the host;
+ * ndir/axes are the six direct axes [tau, w0, aspect_zx, g, phi, theta] (the diffuse table uses the first four). */
+int pprts_b200_lut_open(int solver_id, const char *path_Tdir, const char *path_Sdir, const char *path_Sdiff,
+                        const int ndir[6], const float *const axes[6], pprts_b200_lut **lut);
+int pprts_b200_lut_close(pprts_b200_lut *lut);
+
+typedef struct {
+  int solver_id;       /* 310, 810, 324 */
+  int Nz, Nx, Ny;      /* local domain: layers, columns */
+  double dx, dy;       /* must be equal (src/pprts.F90:459) */
+  const double *dz1d;  /* (Nz) or NULL */
+  const double *dz3d;  /* (Nz,Nx,Ny) or NULL; exactly one of dz1d / dz3d */
+  double sundir[3];    /* cartesian, pointing away from the sun (init_pprts argument) */
+  double twostr_ratio; /* -twostr_ratio, <= 0 -> 2.0 (src/tenstream_options.F90) */
+  int coeff_fp32;      /* 1: store 3-D transport coefficients as fp32 (the LUT's own precision), 0: fp64 */
+  int by_coeff_divergence; /* -absorption_by_coeff_divergence, default 1 (src/pprts.F90:5286) */
+  double rtol, atol;   /* < 0: reference defaults (src/pprts_base.F90:1128-1131) */
+  int maxit_dir;       /* <= 0: 1000 (src/pprts_explicit.F90:78) */
+  int maxit_diff;      /* <= 0: 1000 (src/pprts_base.F90:1126) */
+  int precond;         /* diffuse Krylov preconditioner: 0 none, 1 vertical-line (column two-stream) solve */
+  int device;          /* CUDA ordinal, < 0: current device */
+  int keep_solutions;  /* 1: cache edir/ediff/abso per uid for warm starts like solver%solutions(uid) */
+  /* x/y decomposition over the GPUs of one box (src/pprts_base.F90:721-828): this rank's cartesian position.
+   * nxproc = nyproc = 1 means a single periodic domain. */
+  int nxproc, nyproc, xrank, yrank;
+} pprts_b200_config;
+
+void pprts_b200_default_config(pprts_b200_config *cfg);
+
+/* init_pprts (src/pprts.F90:213-553) */
+int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_lut *lut, pprts_b200_solver **solver);
+/* destroy_pprts (src/pprts_base.F90:877) */
+int pprts_b200_destroy(pprts_b200_solver *solver);
+/* set_angles (src/pprts.F90:1100-1183) */
+int pprts_b200_set_angles(pprts_b200_solver *solver, const double sundir[3]);
+/* set_optical_properties (src/pprts.F90:1764-2076). planck, planck_srfc, albedo_2d may be NULL. */
+int pprts_b200_set_optical_properties(pprts_b200_solver *solver, double albedo, const double *kabs,
+                                      const double *ksca, const double *g, const double *planck,
+                                      const double *planck_srfc, const double *albedo_2d, int ldelta_scaling);
+/* solve_pprts (src/pprts.F90:2487-2665). uid in [-1000, 1000]. */
+int pprts_b200_solve(pprts_b200_solver *solver, int lthermal, int lsolar, double edirTOA, int uid);
+/* pprts_get_result (src/pprts.F90:5799-5917): caller-allocated, edir may be NULL */
+int pprts_b200_get_result(pprts_b200_solver *solver, int uid, double *edn, double *eup, double *abso,
+                          double *edir);
+
+/* Device-resident variants used for throughput measurement with inputs already in HBM: stage() uploads a set of
+ * optical properties into slot (untimed), set_optical_properties_staged() consumes it on the device, and
+ * compute_result_device() runs the result reduction without the device->host copy. */
+int pprts_b200_stage_optical_properties(pprts_b200_solver *solver, int slot, double albedo, const double *kabs,
+                                        const double *ksca, const double *g, const double *planck,
+                                        const double *planck_srfc, const double *albedo_2d);
+int pprts_b200_set_optical_properties_staged(pprts_b200_solver *solver, int slot, int ldelta_scaling);
+int pprts_b200_compute_result_device(pprts_b200_solver *solver, int uid);
+int pprts_b200_synchronize(pprts_b200_solver *solver);
+
+/* spectral accumulation for band sharding: acc += weight * result(uid) on the device; read back once */
+int pprts_b200_accumulate_result(pprts_b200_solver *solver, int uid, double weight);
+int pprts_b200_reset_accumulator(pprts_b200_solver *solver);
+int pprts_b200_get_accumulated(pprts_b200_solver *solver, double *edn, double *eup, double *abso, double *edir);
+
+/* NCCL plumbing (one process per GPU). The unique id is produced on rank 0 and distributed by the caller
+ * (MPI_Bcast in a Fortran host, torch.distributed in the tests). */
+int pprts_b200_nccl_unique_id(char id[128]);
+int pprts_b200_comm_init(pprts_b200_solver *solver, int nranks, int rank, const char id[128]);
+/* sum of the accumulated spectral integrals over all ranks (final flux / heating-rate reduction) */
+int pprts_b200_allreduce_accumulated(pprts_b200_solver *solver);
+
+/* introspection (parity tests, profiling) */
+/* which: 1 dir2dir, 2 dir2diff, 3 diff2diff -> out (ncoef, Nz, Nx, Ny) column-major, zeros in 1-D layers */
+int pprts_b200_get_coeffs(pprts_b200_solver *solver, int which, double *out);
+/* which: 1 edir (Nd,Nz+1,Nx,Ny), 2 ediff (Nf,Nz+1,Nx,Ny), 3 abso (Nz,Nx,Ny), 4 b (Nf,Nz+1,Nx,Ny); W/m2 resp. W */
+int pprts_b200_get_state(pprts_b200_solver *solver, int uid, int which, double *out);
+int pprts_b200_get_info(pprts_b200_solver *solver, int uid, int *niter_dir, int *niter_diff, double *res_dir,
+                        double *res_diff);
+/* y = (I - T) x with the current coefficients, x and y (Nf,Nz+1,Nx,Ny) column-major host arrays */
+int pprts_b200_mat_mult_ediff(pprts_b200_solver *solver, const double *x, double *y);
+/* fp64 coefficient lookup for n sample cells on the device (pprts_base.F90:1491 get_coeff): mode 1/2/3,
+ * out (ncoef, n) column-major */
+int pprts_b200_lookup_coeffs(pprts_b200_solver *solver, int mode, long n, const double *kabs, const double *ksca,
+                             const double *g, const double *dz, double *out);
+/* counters: kernels launched by this library since creation, and the ids of the last timed kernels */
+long pprts_b200_kernel_launches(pprts_b200_solver *solver);
+/* device time [ms] and launch count accumulated per kernel family since the last reset:
+ * 0 lookup, 1 edir sweep, 2 source, 3 matmult, 4 precond, 5 vector ops, 6 absorption+result, 7 ingest/egress */
+int pprts_b200_kernel_stats(pprts_b200_solver *solver, int reset, double ms[8], long launches[8]);
+int pprts_b200_enable_kernel_timing(pprts_b200_solver *solver, int on);
+
+const char *pprts_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,996 @@
+// kernels.cuh -- the hand-written sm_100a kernels of the pprts path.  All of them are HBM-bound streaming kernels
+// (coalesced plane reads, one thread per cell or per column); none is GEMM-shaped, tensor cores are not used.
+// Each kernel names the reference loop it replaces.
+#pragma once
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+#define PB_PI 3.14159265358979323846
+
+// =================================================================================================================
+// layout conversion between the caller's Fortran arrays (z fastest) and the device layout (x fastest)
+// =================================================================================================================
+// in : h[k + nz*(i + Nx*j)]     out: d[(k*Ny + j)*Nx + i]      32x32 shared-memory tile over (k, i), one j per z-block
+template <class TIN>
+__global__ void k_zxy_to_kji(int nz, int Nx, int Ny, const TIN *__restrict__ in, double *__restrict__ out) {
+  __shared__ double tile[32][33];
+  const int j = blockIdx.z;
+  const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r: i offset, threadIdx.x: k offset (contiguous in `in`)
+    int i = i0 + r, k = k0 + threadIdx.x;
+    if (i < Nx && k < nz) tile[r][threadIdx.x] = (double)in[k + (long)nz * (i + (long)Nx * j)];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r: k offset, threadIdx.x: i offset (contiguous in `out`)
+    int k = k0 + r, i = i0 + threadIdx.x;
+    if (i < Nx && k < nz) out[((long)k * Ny + j) * Nx + i] = tile[threadIdx.x][r];
+  }
+}
+// reverse: in d[(k*Ny + j)*Nx + i] -> out h[k + nz*(i + Nx*j)], optional scale
+template <class TOUT>
+__global__ void k_kji_to_zxy(int nz, int Nx, int Ny, const double *__restrict__ in, TOUT *__restrict__ out,
+                             double scale) {
+  __shared__ double tile[32][33];
+  const int j = blockIdx.z;
+  const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, i = i0 + threadIdx.x;
+    if (i < Nx && k < nz) tile[r][threadIdx.x] = in[((long)k * Ny + j) * Nx + i];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int i = i0 + r, k = k0 + threadIdx.x;
+    if (i < Nx && k < nz) out[k + (long)nz * (i + (long)Nx * j)] = (TOUT)(tile[threadIdx.x][r] * scale);
+  }
+}
+// state (dof, z, x, y) column-major <-> x[d*nlev + lev]; introspection only, not on the hot path
+__global__ void k_state_to_host_layout(Grid g, int nd, const double *__restrict__ x, double *__restrict__ out) {
+  long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nd * g.nlev) return;
+  int d = (int)(n / g.nlev);
+  long l = n % g.nlev;
+  int i = (int)(l % g.Nx), j = (int)((l / g.Nx) % g.Ny), k = (int)(l / g.ncol);
+  out[d + (long)nd * (k + (long)(g.Nz + 1) * (i + (long)g.Nx * j))] = x[n];
+}
+__global__ void k_state_from_host_layout(Grid g, int nd, const double *__restrict__ in, double *__restrict__ x) {
+  long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nd * g.nlev) return;
+  int d = (int)(n / g.nlev);
+  long l = n % g.nlev;
+  int i = (int)(l % g.Nx), j = (int)((l / g.Nx) % g.Ny), k = (int)(l / g.ncol);
+  x[n] = in[d + (long)nd * (k + (long)(g.Nz + 1) * (i + (long)g.Nx * j))];
+}
+template <class CT>
+__global__ void k_coeff_to_host_layout(Grid g, int nc, const CT *__restrict__ c, double *__restrict__ out) {
+  long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nc * g.ncell) return;
+  int q = (int)(n / g.ncell);
+  long l = n % g.ncell;
+  int i = (int)(l % g.Nx), j = (int)((l / g.Nx) % g.Ny), k = (int)(l / g.ncol);
+  out[q + (long)nc * (k + (long)g.Nz * (i + (long)g.Nx * j))] = (double)c[(long)q * g.ncp + l];
+}
+
+// =================================================================================================================
+// set_optical_properties: delta scaling (helper_functions.fypp:1622-1666, f = g^2) + validity check
+// =================================================================================================================
+__global__ void k_delta_scale(long n, double *__restrict__ kabs, double *__restrict__ ksca, double *__restrict__ g,
+                              int ldelta, int *__restrict__ bad) {
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double ka = kabs[c], ks = ksca[c], gg = g[c];
+  if (ldelta) {
+    double f = gg * gg, dtau = ka + ks;
+    if (!(dtau < DBL_EPSILON)) {
+      double w0 = ks / dtau;
+      if (gg >= 1.0 - DBL_EPSILON * 10) {
+        dtau = dtau * (1.0 - w0);
+        w0 = 0;
+        gg = 0;
+      } else {
+        dtau = dtau * (1.0 - w0 * f);
+        gg = (gg - f) / (1.0 - f);
+        w0 = w0 * (1.0 - f) / (1.0 - f * w0);
+      }
+      ka = dtau * (1.0 - w0);
+      ks = dtau * w0;
+    }
+    kabs[c] = ka; ksca[c] = ks; g[c] = gg;
+  }
+  if (ka < 0 || ks < 0 || gg < 0 || isnan(ka) || isnan(ks) || isnan(gg)) atomicExch(bad, 1);  // src/pprts.F90:1929
+}
+
+// eddington_coeff_ec (src/eddington.F90:167-242) for every cell of the 1-D layers (src/pprts.F90:1962-2007)
+__device__ __forceinline__ void eddington_ec(double dtau, double w0, double g, double mu0, double &t, double &r,
+                                             double &rdir, double &sdir, double &tdir) {
+  double f = 0.75 * g;
+  double g1 = 2.0 - w0 * (1.25 + f);
+  double g2 = w0 * (0.75 - f);
+  double g3 = 0.5 - mu0 * f;
+  double dtau_slant = fmax(dtau / fmax(sqrt(DBL_MIN), mu0), 0.0);
+  if (dtau_slant > 1e-6) {
+    double g4 = 1.0 - g3;
+    double alpha1 = g1 * g4 + g2 * g3;
+    double alpha2 = g1 * g3 + g2 * g4;
+    double A = sqrt(fmax((g1 - g2) * (g1 + g2), 1e-12));
+    double k_mu0 = A * mu0, k_g3 = A * g3, k_g4 = A * g4;
+    double e0 = exp(-dtau_slant);
+    tdir = e0;
+    double e = exp(-A * dtau), e2 = e * e, k_2_e = 2 * A * e;
+    if (k_mu0 <= 1.0 + 10 * DBL_EPSILON && k_mu0 >= 1.0 - 10 * DBL_EPSILON) k_mu0 = 1 - 10 * DBL_EPSILON;
+    double beta = 1 / (A + g1 + (A - g1) * e2);
+    r = g2 * (1 - e2) * beta;
+    t = k_2_e * beta;
+    beta = w0 * beta / (1 - k_mu0 * k_mu0);
+    sdir = beta * (k_2_e * (g4 + alpha1 * mu0) - e0 * ((1 + k_mu0) * (alpha1 + k_g4) - (1 - k_mu0) * (alpha1 - k_g4) * e2));
+    rdir = beta * ((1 - k_mu0) * (alpha2 + k_g3) - (1 + k_mu0) * (alpha2 - k_g3) * e2 - k_2_e * (g3 - alpha2 * mu0) * e0);
+  } else {
+    t = 1.0 - g1 * dtau;
+    r = g2 * dtau;
+    sdir = (1.0 - g3) * (w0 * dtau);
+    rdir = g3 * (w0 * dtau);
+    tdir = 1.0 - dtau_slant;
+  }
+}
+// a11..a33 are cell fields over the first n1d layers only (the 1-D block is contiguous from the top)
+__global__ void k_eddington(Grid g, int n1d, double costheta, const double *__restrict__ kabs,
+                            const double *__restrict__ ksca, const double *__restrict__ gg,
+                            const double *__restrict__ dz, double *__restrict__ a11, double *__restrict__ a12,
+                            double *__restrict__ a13, double *__restrict__ a23, double *__restrict__ a33) {
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= (long)n1d * g.ncol) return;
+  double ext = fmax(DBL_MIN, kabs[c] + ksca[c]);
+  double t, r, rdir, sdir, tdir;
+  eddington_ec(dz[c] * ext, ksca[c] / ext, gg[c], costheta, t, r, rdir, sdir, tdir);
+  a11[c] = t; a12[c] = r; a13[c] = rdir; a23[c] = sdir; a33[c] = tdir;
+}
+
+// =================================================================================================================
+// HOT LOOP A: coefficient lookup (src/pprts.F90:3088-3494 -> pprts_base.F90:1491 get_coeff -> optprop.F90:550
+// get_coeff_cube -> optprop_LUT.F90:1452-1613 -> search.fypp:177 + interpolation.F90:317).
+// One thread per 3-D cell.  The direct tables arrive already contracted over (phi, theta) -- the sun angle is the
+// same for every cell of a solve -- as fp64 [lattice4][ncoef]; the diffuse table is the fp32 file payload.  All 16
+// corner vectors of a cell are contiguous runs in an L2-resident table; outputs are written plane by plane so that
+// the writes (the algorithmic bytes of this kernel) are fully coalesced.
+// =================================================================================================================
+struct LutDev {
+  int n[4];            // axis lengths: tau, w0, aspect, g
+  long off[4];         // ndarray_offsets of the 4-D lattice (tau fastest)
+  const float *ax[4];  // axis values (device)
+  const double *Tdir4; // [lat4][Nd*Nd], contracted over (phi, theta) in fp64
+  const double *Sdir4; // [lat4][Nd*Nf]
+  const float *Sdiff;  // [lat4][Nf*Nf]
+};
+struct SymMaps {  // stream permutation symmetries (src/optprop.F90:986-1301) as gather maps new[n] = old[map[n]]
+  short d2d[PB_MAX_DIRDOF * PB_MAX_DIRDOF];
+  short d2f[PB_MAX_DIRDOF * PB_MAX_DOF];
+};
+
+// search_sorted_bisection (src/search.fypp:177-232) on an ascending fp32 axis, arithmetic in fp64; 1-based result
+__device__ __forceinline__ double find_real_location(const float *__restrict__ arr, int n, float val) {
+  int i = 1, j = n;
+  const double v = (double)val;
+  for (;;) {
+    int k = (i + j) / 2;
+    if (v < (double)arr[k - 1]) j = k; else i = k;
+    if (i + 1 >= j) {
+      double inc = (i == j) ? 0.0 : (v - (double)arr[i - 1]) / ((double)arr[j - 1] - (double)arr[i - 1]);
+      return fmin(fmax(1.0, (double)i + inc), (double)n);
+    }
+  }
+}
+
+struct InterpPlan {  // interp_vec_bilinear_iterative (src/interpolation.F90:317-360) for <= 4 dimensions
+  int ncorner;
+  long ofs[16];   // 0-based lattice index of each corner
+  double w[16];
+};
+__device__ __forceinline__ void make_plan(const LutDev &lut, const float sample[4], InterpPlan &p) {
+  const double snap = (double)1e-3f;  // interpolation_lattice_snapping, src/interpolation.F90:63
+  long ioff_lo[4], ioff_hi[4], ofs_base = 0;
+  double wlo[4], whi[4];
+  int Ninterp = 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    double pti = find_real_location(lut.ax[d], lut.n[d], sample[d]);
+    double frac = pti - (double)(long)pti;
+    if (frac < snap || frac > 1.0 - snap) {  // dim_needs_interpolation == false: snap to the lattice (:546-556)
+      ofs_base += lut.off[d] * (lround(pti) - 1);
+    } else {
+      long b = (long)pti;
+      whi[Ninterp] = pti - (double)b;
+      wlo[Ninterp] = 1.0 - whi[Ninterp];
+      ioff_lo[Ninterp] = lut.off[d] * (b - 1);
+      ioff_hi[Ninterp] = lut.off[d] * b;
+      ++Ninterp;
+    }
+  }
+  p.ncorner = 1 << Ninterp;
+  for (int b = 0; b < p.ncorner; ++b) {
+    long ofs = ofs_base;
+    double w = 1.0;
+    for (int d = 0; d < Ninterp; ++d) {
+      if (b & (1 << d)) { ofs += ioff_hi[d]; w = w * whi[d]; }
+      else              { ofs += ioff_lo[d]; w = w * wlo[d]; }
+    }
+    p.ofs[b] = ofs;
+    p.w[b] = w;
+  }
+}
+
+// get_coeff (src/pprts_base.F90:1491-1543): optical properties -> LUT space with the reference's fp32 casts/clamps
+__device__ __forceinline__ void lut_sample(const LutDev &lut, double kabs, double ksca, double g, double dz,
+                                           double dx, float sample[4]) {
+  float aspect_zx = (float)(dz / dx);
+  float w0 = (float)(ksca / fmax(kabs + ksca, DBL_EPSILON));
+  float tauz = (float)((kabs + ksca) * dz);
+  aspect_zx = fmaxf(lut.ax[2][0], aspect_zx);
+  tauz = fmaxf(lut.ax[0][0], fminf(lut.ax[0][lut.n[0] - 1], tauz));
+  w0 = fmaxf(lut.ax[1][0], fminf(lut.ax[1][lut.n[1] - 1], w0));
+  sample[0] = tauz; sample[1] = w0; sample[2] = aspect_zx; sample[3] = (float)g;
+}
+
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *__restrict__ kabs,
+         const double *__restrict__ ksca, const double *__restrict__ gg, const double *__restrict__ dz,
+         CT *__restrict__ d2d, CT *__restrict__ d2f, CT *__restrict__ f2f, double *__restrict__ cdiv_dir,
+         double *__restrict__ cdiv_diff) {
+  constexpr int Nd = L::Nd, Nf = L::Nf;
+  long c = (long)kstart * g.ncol + (long)blockIdx.x * blockDim.x + threadIdx.x;  // 3-D layers start at kstart
+  if (c >= g.ncell) return;
+  float sample[4];
+  lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
+  InterpPlan p;
+  make_plan(lut, sample, p);
+
+  // ---- diff2diff: one dst row (Nf contiguous fp32 per corner) at a time
+  double colsum[Nf];
+#pragma unroll
+  for (int s = 0; s < Nf; ++s) colsum[s] = 0.0;
+  for (int dst = 0; dst < Nf; ++dst) {
+    double acc[Nf];
+#pragma unroll
+    for (int s = 0; s < Nf; ++s) acc[s] = 0.0;
+    for (int b = 0; b < p.ncorner; ++b) {
+      const float *row = lut.Sdiff + p.ofs[b] * (long)(Nf * Nf) + dst * Nf;
+      const double w = p.w[b];
+#pragma unroll
+      for (int s = 0; s < Nf; ++s) acc[s] = fma(w, (double)__ldg(row + s), acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < Nf; ++s) {
+      CT st = (CT)acc[s];
+      f2f[(long)(dst * Nf + s) * g.ncp + c] = st;
+      colsum[s] += (double)st;  // sum over dst in ascending order, as calc_flx_div does (src/pprts.F90:5343)
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < Nf; ++s) cdiv_diff[(long)s * g.ncp + c] = 1.0 - colsum[s];
+
+  if (!lsolar) return;
+  // ---- dir2dir / dir2diff from the (phi,theta)-contracted fp64 tables, stream permutation applied on the fly
+  double sum1[Nd], sum2[Nd];
+#pragma unroll
+  for (int s = 0; s < Nd; ++s) { sum1[s] = 0.0; sum2[s] = 0.0; }
+  for (int dst = 0; dst < Nd; ++dst) {
+    double acc[Nd];
+#pragma unroll
+    for (int s = 0; s < Nd; ++s) acc[s] = 0.0;
+    for (int b = 0; b < p.ncorner; ++b) {
+      const double *base = lut.Tdir4 + p.ofs[b] * (long)(Nd * Nd);
+      const double w = p.w[b];
+#pragma unroll
+      for (int s = 0; s < Nd; ++s) acc[s] = fma(w, __ldg(base + sym.d2d[dst * Nd + s]), acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < Nd; ++s) {
+      CT st = (CT)acc[s];
+      d2d[(long)(dst * Nd + s) * g.ncp + c] = st;
+      sum1[s] += (double)st;
+    }
+  }
+  for (int dst = 0; dst < Nf; ++dst) {
+    double acc[Nd];
+#pragma unroll
+    for (int s = 0; s < Nd; ++s) acc[s] = 0.0;
+    for (int b = 0; b < p.ncorner; ++b) {
+      const double *base = lut.Sdir4 + p.ofs[b] * (long)(Nd * Nf);
+      const double w = p.w[b];
+#pragma unroll
+      for (int s = 0; s < Nd; ++s) acc[s] = fma(w, __ldg(base + sym.d2f[dst * Nd + s]), acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < Nd; ++s) {
+      CT st = (CT)acc[s];
+      d2f[(long)(dst * Nd + s) * g.ncp + c] = st;
+      sum2[s] += (double)st;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < Nd; ++s) cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1[s] - sum2[s];  // src/pprts.F90:5315
+}
+
+// fp64 lookup of n arbitrary sample cells (coefficient probe / parity hook); out[(coef) + ncoef*n]
+template <class L>
+__global__ void k_lookup_probe(LutDev lut, SymMaps sym, int mode, long n, double dx, const double *__restrict__ kabs,
+                               const double *__restrict__ ksca, const double *__restrict__ gg,
+                               const double *__restrict__ dz, const float *__restrict__ lutspace,
+                               double *__restrict__ out) {
+  constexpr int Nd = L::Nd, Nf = L::Nf;
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float sample[4];
+  if (lutspace) {  // get_coeff_cube entry (tauz, w0, aspect, g already in LUT space): only the aspect clamp applies
+    sample[0] = lutspace[4 * c + 0]; sample[1] = lutspace[4 * c + 1];
+    sample[2] = fmaxf(lutspace[4 * c + 2], lut.ax[2][0]); sample[3] = lutspace[4 * c + 3];
+  } else {
+    lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], dx, sample);
+  }
+  InterpPlan p;
+  make_plan(lut, sample, p);
+  const int nc = (mode == 1) ? Nd * Nd : (mode == 2) ? Nd * Nf : Nf * Nf;
+  for (int q = 0; q < nc; ++q) {
+    double acc = 0.0;
+    for (int b = 0; b < p.ncorner; ++b) {
+      double v;
+      if (mode == 1) v = lut.Tdir4[p.ofs[b] * (long)(Nd * Nd) + sym.d2d[q]];
+      else if (mode == 2) v = lut.Sdir4[p.ofs[b] * (long)(Nd * Nf) + sym.d2f[q]];
+      else v = (double)lut.Sdiff[p.ofs[b] * (long)(Nf * Nf) + q];
+      acc = fma(p.w[b], v, acc);
+    }
+    out[q + (long)nc * c] = acc;
+  }
+}
+
+// =================================================================================================================
+// scale_flx (src/pprts.F90:3682-3741, :3901-3987): W/m2 <-> W with per-dof face areas computed on the fly
+// =================================================================================================================
+template <int NT, int NS, int ADT, int ADS>
+__global__ void k_scale_flx(Grid g, const double *__restrict__ dz, double *__restrict__ x, int lWm2) {
+  long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= g.nlev) return;
+  int k = (int)(l / g.ncol);
+  const double Az = g.dx * g.dy / (double)ADT;
+  double Ax = 1.0, Ay = 1.0;
+  if (k < g.Nz) {
+    double dzc = dz[l];
+    Ax = g.dy * dzc / (double)ADS;
+    Ay = g.dx * dzc / (double)ADS;
+  }
+  double fz = lWm2 ? 1.0 / Az : Az, fx = lWm2 ? 1.0 / Ax : Ax, fy = lWm2 ? 1.0 / Ay : Ay;
+#pragma unroll
+  for (int d = 0; d < NT; ++d) x[(long)d * g.nlev + l] *= fz;
+#pragma unroll
+  for (int d = 0; d < NS; ++d) x[(long)(NT + d) * g.nlev + l] *= fx;
+#pragma unroll
+  for (int d = 0; d < NS; ++d) x[(long)(NT + NS + d) * g.nlev + l] *= fy;
+}
+
+// =================================================================================================================
+// HOT LOOP B: direct beam (src/pprts_explicit.F90:60-230 explicit_edir, :330-459 forward sweep).
+// One thread per column marches from TOA to the surface (the vertical dependency is exact within a pass); the two
+// horizontal inputs of a cell come from the previous pass (ping-pong buffers -> deterministic, no races), so a pass
+// is one coalesced stream over dir2dir and the state.  Passes are repeated until ||x_n - x_{n-1}||_2 meets the
+// reference's atol/rtol test, exactly like the reference repeats whole-domain sweeps for the periodic wrap-around.
+// =================================================================================================================
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__restrict__ d2d,
+            const double *__restrict__ a33, const double *__restrict__ xold, double *__restrict__ xnew,
+            double *partials, unsigned int *counter, double *out_norm2) {
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds;
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double d2sum[1] = {0.0};
+  if (col < g.ncol) {
+    const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
+    const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
+    const int i_in = xinc ? i : ip, i_out = xinc ? ip : i;   // faces i+1-xinc (source) and i+xinc (destination)
+    const int j_in = yinc ? j : jp, j_out = yinc ? jp : j;
+    const long o_own = (long)j * g.Nx + i;
+    const long o_xin = (long)j * g.Nx + i_in, o_xout = (long)j * g.Nx + i_out;
+    const long o_yin = (long)j_in * g.Nx + i, o_yout = (long)j_out * g.Nx + i;
+    double top[Ndt];
+#pragma unroll
+    for (int d = 0; d < Ndt; ++d) {  // setup_incSolar (src/pprts_base.F90:1146-1181)
+      top[d] = inc_top;
+      long q = (long)d * g.nlev + o_own;
+      double df = inc_top - xold[q];
+      d2sum[0] += df * df;
+      xnew[q] = inc_top;
+    }
+    for (int k = 0; k < g.Nz; ++k) {
+      const long lk = (long)k * g.ncol, lk1 = (long)(k + 1) * g.ncol;
+      if (k < n1d) {  // 1-D layer: top(k+1) = top(k) * a33 (:383-391); side dofs are left untouched
+        const double t = a33[lk + o_own];
+#pragma unroll
+        for (int d = 0; d < Ndt; ++d) {
+          top[d] = top[d] * t;
+          long q = (long)d * g.nlev + lk1 + o_own;
+          double df = top[d] - xold[q];
+          d2sum[0] += df * df;
+          xnew[q] = top[d];
+        }
+#pragma unroll
+        for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lk + o_own] = xold[(long)d * g.nlev + lk + o_own];
+      } else {
+        double src[Nd];
+#pragma unroll
+        for (int d = 0; d < Ndt; ++d) src[d] = top[d];
+#pragma unroll
+        for (int d = 0; d < Nds; ++d) src[Ndt + d] = xold[(long)(Ndt + d) * g.nlev + lk + o_xin];
+#pragma unroll
+        for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = xold[(long)(Ndt + Nds + d) * g.nlev + lk + o_yin];
+        const long c = lk + o_own;
+#pragma unroll
+        for (int dst = 0; dst < Nd; ++dst) {
+          double acc = 0.0;
+#pragma unroll
+          for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)d2d[(long)(dst * Nd + s) * g.ncp + c];
+          long q;
+          if (dst < Ndt) { q = (long)dst * g.nlev + lk1 + o_own; top[dst] = acc; }
+          else if (dst < Ndt + Nds) q = (long)dst * g.nlev + lk + o_xout;
+          else q = (long)dst * g.nlev + lk + o_yout;
+          double df = acc - xold[q];
+          d2sum[0] += df * df;
+          xnew[q] = acc;
+        }
+      }
+    }
+    // side dofs below the ground are never written by the sweep
+    const long lz = (long)g.Nz * g.ncol;
+#pragma unroll
+    for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lz + o_own] = xold[(long)d * g.nlev + lz + o_own];
+  }
+  grid_reduce_sum<1>(d2sum, partials, counter, out_norm2);
+}
+
+// =================================================================================================================
+// HOT LOOP C: source term (src/pprts.F90:4641-4987 setup_b).  The reference scatter-adds into the six faces of a
+// cell and folds ghosts with halo_reduce_5pt; here every b entry has exactly one producing cell (the cell for which
+// that stream is an outgoing one), so each thread stores the Nf outgoing dofs of its cell: no atomics, no halo add.
+// =================================================================================================================
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, const double *__restrict__ a13,
+               const double *__restrict__ a23, const double *__restrict__ albedo, const double *__restrict__ edir,
+               double *__restrict__ b) {
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.ncell) return;
+  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
+  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
+  const long l_own = lidx(g, k, j, i), l_dn = lidx(g, k + 1, j, i);
+  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+  const long l_xin = xinc ? l_own : l_xp, l_yin = yinc ? l_own : l_yp;
+  // `if (any(xedir(:, k, i, j) .gt. epsilon(one)))` (:4706) -- tested on the cell's OWN index for every dof
+  bool any = false;
+#pragma unroll
+  for (int d = 0; d < Nd; ++d) any = any || (edir[(long)d * g.nlev + l_own] > DBL_EPSILON);
+  if (any) {
+    if (k < n1d) {
+      double acc_dn = 0.0, acc_up = 0.0;
+#pragma unroll
+      for (int s = 0; s < Ndt; ++s) {
+        double e = edir[(long)s * g.nlev + l_own];
+        acc_dn += e * a23[c] / (double)(Nft / 2);
+        acc_up += e * a13[c] / (double)(Nft / 2);
+      }
+#pragma unroll
+      for (int d = 0; d < Nft; ++d) {
+        if (L::top_in(d)) b[(long)d * g.nlev + l_dn] = acc_dn;
+        else b[(long)d * g.nlev + l_own] = acc_up;
+      }
+    } else {
+      double src[Nd];
+#pragma unroll
+      for (int d = 0; d < Ndt; ++d) src[d] = edir[(long)d * g.nlev + l_own];
+#pragma unroll
+      for (int d = 0; d < Nds; ++d) src[Ndt + d] = edir[(long)(Ndt + d) * g.nlev + l_xin];
+#pragma unroll
+      for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = edir[(long)(Ndt + Nds + d) * g.nlev + l_yin];
+#pragma unroll
+      for (int dst = 0; dst < Nf; ++dst) {
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < Nd; ++s) acc += src[s] * (double)d2f[(long)(dst * Nd + s) * g.ncp + c];
+        long q;
+        if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
+        else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
+        else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
+        b[(long)dst * g.nlev + q] = acc;
+      }
+    }
+  }
+  if (k == g.Nz - 1) {  // ground albedo reflecting direct radiation (:4830-4843)
+    double e = 0.0;
+#pragma unroll
+    for (int s = 0; s < Ndt; ++s) e += edir[(long)s * g.nlev + l_dn] * albedo[(long)j * g.Nx + i] / (double)(Nft / 2);
+#pragma unroll
+    for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) b[(long)d * g.nlev + l_dn] = e;
+  }
+}
+
+// B_eff (src/schwarzschild.F90:36-67), 2-point Gauss-Legendre on (0,1)
+__device__ __forceinline__ double B_eff_mu(double B_far, double B_near, double tau, double mu) {
+  double dtau = tau / mu;
+  if (dtau < 1e-3) return (B_far + B_near) * .5;
+  double tm1 = expm1(-dtau);
+  return (-B_near + B_far * (tm1 + 1)) / tm1 + ((B_far - B_near) * mu) / tau;
+}
+__device__ __forceinline__ double B_eff(double B_far, double B_near, double tau) {
+  const double p0 = 0.21132486540518713, p1 = 0.78867513459481287;
+  double B = 0;
+  B = B + B_eff_mu(B_far, B_near, tau, p0) * p0 * 0.5;
+  B = B + B_eff_mu(B_far, B_near, tau, p1) * p1 * 0.5;
+  return B * 2;
+}
+
+template <class L>
+__global__ void __launch_bounds__(128)
+k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdiv_diff,
+                 const double *__restrict__ a11, const double *__restrict__ a12, const double *__restrict__ kabs,
+                 const double *__restrict__ dz, const double *__restrict__ planck, const double *__restrict__ Bsrfc,
+                 const double *__restrict__ albedo, double *__restrict__ b) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.ncell) return;
+  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
+  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
+  const long l_own = lidx(g, k, j, i), l_dn = lidx(g, k + 1, j, i);
+  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+  const double Az = g.dx * g.dy;
+  const double b0 = planck[l_own], b1 = planck[l_dn];
+  const double tauz = kabs[c] * dz[c];
+  if (k < n1d) {
+    double bfac = PB_PI * Az / (double)(Nft / 2);
+    double emis = fmax(0.0, fmin(1.0, 1.0 - a11[c] - a12[c]));
+    double btop = B_eff(b1, b0, tauz) * bfac * emis;
+    double bbot = B_eff(b0, b1, tauz) * bfac * emis;
+#pragma unroll
+    for (int d = 0; d < Nft; ++d) {
+      if (L::top_in(d)) b[(long)d * g.nlev + l_dn] = bbot;
+      else b[(long)d * g.nlev + l_own] = btop;
+    }
+  } else {
+    const double Ax = g.dy * dz[c], Ay = g.dx * dz[c];
+    const double btop = B_eff(b1, b0, tauz), bbot = B_eff(b0, b1, tauz);
+    int src = 0;
+    double bfac = PB_PI * Az / (double)(Nft / 2);
+#pragma unroll
+    for (int d = 0; d < Nft; ++d, ++src) {
+      double emis = fmax(0.0, fmin(1.0, cdiv_diff[(long)src * g.ncp + c]));
+      if (!L::top_in(d)) b[(long)src * g.nlev + l_own] = btop * bfac * emis;
+      else b[(long)src * g.nlev + l_dn] = bbot * bfac * emis;
+    }
+    bfac = PB_PI * Ax / (double)(Nfs / 2);
+#pragma unroll
+    for (int d = 0; d < Nfs; ++d, ++src) {
+      double emis = fmax(0.0, fmin(1.0, cdiv_diff[(long)src * g.ncp + c]));
+      emis = (d + 1 > Nfs / 2) ? btop * emis : bbot * emis;
+      b[(long)src * g.nlev + (L::side_in(d) ? l_xp : l_own)] = emis * bfac;
+    }
+    bfac = PB_PI * Ay / (double)(Nfs / 2);
+#pragma unroll
+    for (int d = 0; d < Nfs; ++d, ++src) {
+      double emis = fmax(0.0, fmin(1.0, cdiv_diff[(long)src * g.ncp + c]));
+      emis = (d + 1 > Nfs / 2) ? btop * emis : bbot * emis;
+      b[(long)src * g.nlev + (L::side_in(d) ? l_yp : l_own)] = emis * bfac;
+    }
+  }
+  if (k == g.Nz - 1) {  // thermal emission at the surface (:4958-4985)
+    const long cs = (long)j * g.Nx + i;
+    double e;
+    if (have_Bsrfc) e = Bsrfc[cs] * Az * fmax(0.0, fmin(1.0, 1.0 - albedo[cs])) * PB_PI / (double)(Nft / 2);
+    else e = planck[l_dn] * Az * (1.0 - albedo[cs]) * PB_PI / (double)(Nft / 2);
+#pragma unroll
+    for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) b[(long)d * g.nlev + l_dn] = e;
+  }
+}
+
+// =================================================================================================================
+// HOT LOOP D: diffuse operator y = (I - T) x (src/pprts_shell.F90:366-541 op_mat_mult_ediff == assembled matrix
+// src/pprts.F90:5511-5796).  One thread per cell in gather form: it loads the Nf incoming streams of its cell,
+// streams the Nf*Nf coefficient planes once (fp32 storage: 400 B/cell for 3_10) and writes the Nf outgoing streams,
+// each of which has exactly one producer.  NDOT weighted dot products with y are fused (rh.v, t.s, t.t of BiCGStab).
+// =================================================================================================================
+template <class L, class CT, int NDOT>
+__global__ void __launch_bounds__(128)
+k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
+          const double *__restrict__ albedo, const double *__restrict__ x, double *__restrict__ y,
+          const double *__restrict__ w0, double *partials, unsigned int *counter, double *out_dots) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  constexpr int NV = (NDOT > 0) ? NDOT : 1;
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dots[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) dots[n] = 0.0;
+  // NDOT == 1: dots[0] = sum w0*y ; NDOT == 2: dots[0] = sum y*w0, dots[1] = sum y*y
+  auto emit = [&](long q, double val) {
+    y[q] = val;
+    if (NDOT >= 1) dots[0] += val * w0[q];
+    if (NDOT >= 2) dots[1] += val * val;
+  };
+  if (c < g.ncell) {
+    const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
+    const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
+    const long l_own = lidx(g, k, j, i), l_dn = l_own + g.ncol;
+    const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+    if (k < n1d) {
+      const double t = a11[c], r = a12[c];
+#pragma unroll
+      for (int d = 0; d < Nft; ++d) {
+        if (L::top_in(d)) {  // edn: xb(k+1) -= x(d,k)*a11 ; -= x(inv,k+1)*a12
+          long q = (long)d * g.nlev + l_dn;
+          double acc = 0.0;
+          acc = acc - x[(long)d * g.nlev + l_own] * t;
+          acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_dn] * r;
+          emit(q, acc + x[q]);
+        } else {
+          long q = (long)d * g.nlev + l_own;
+          double acc = 0.0;
+          acc = acc - x[(long)d * g.nlev + l_dn] * t;
+          acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_own] * r;
+          emit(q, acc + x[q]);
+        }
+      }
+#pragma unroll
+      for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+    } else {
+      double xs[Nf];
+#pragma unroll
+      for (int d = 0; d < Nft; ++d) xs[d] = x[(long)d * g.nlev + (L::top_in(d) ? l_own : l_dn)];
+#pragma unroll
+      for (int d = 0; d < Nfs; ++d) xs[Nft + d] = x[(long)(Nft + d) * g.nlev + (L::side_in(d) ? l_own : l_xp)];
+#pragma unroll
+      for (int d = 0; d < Nfs; ++d) xs[Nft + Nfs + d] = x[(long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? l_own : l_yp)];
+#pragma unroll
+      for (int dst = 0; dst < Nf; ++dst) {
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < Nf; ++s) acc = acc - xs[s] * (double)T[(long)(dst * Nf + s) * g.ncp + c];
+        long q;
+        if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
+        else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
+        else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
+        q += (long)dst * g.nlev;
+        emit(q, acc + x[q]);
+      }
+    }
+    if (k == 0) {  // rows without a producing cell: incoming diffuse at TOA
+#pragma unroll
+      for (int d = 0; d < Nft; ++d) if (L::top_in(d)) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+    }
+    if (k == g.Nz - 1) {  // albedo row (src/pprts_shell.F90:500-505) and the unused side dofs below the ground
+      const double alb = albedo[(long)j * g.Nx + i];
+#pragma unroll
+      for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) {
+        long q = (long)d * g.nlev + l_dn;
+        emit(q, x[q] - x[(long)L::inv_dof(d) * g.nlev + l_dn] * alb);
+      }
+#pragma unroll
+      for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, x[q]); }
+    }
+  }
+  if (NDOT > 0) grid_reduce_sum<NV>(dots, partials, counter, out_dots);
+}
+
+// =================================================================================================================
+// Preconditioner: vertical-line (column) solve.  M = I - T_col keeps the couplings that stay inside one column of
+// cells -- the up/down two-stream system through all layers plus the side streams that enter and leave through the
+// column's own faces -- and is inverted exactly per column by an adding-method recurrence (one upward sweep
+// accumulating the reflectance R_k and source S_k of everything below level k, one downward sweep).  This captures
+// the strongest coupling of the operator (vertical propagation through optically thin layers), which a pointwise
+// Jacobi cannot (diag(A) = 1, src/pprts.F90:1294-1308), and it is embarrassingly parallel over columns.
+// Only for layouts with one up/down pair of top streams (3_10, 8_10).
+// =================================================================================================================
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
+             const double *__restrict__ a12, const double *__restrict__ albedo, double *__restrict__ R,
+             double *__restrict__ inv) {
+  constexpr int Nf = L::Nf;
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.ncol) return;
+  double Rn = albedo[col];
+  R[(long)g.Nz * g.ncol + col] = Rn;
+  for (int k = g.Nz - 1; k >= 0; --k) {
+    const long c = (long)k * g.ncol + col;
+    double tuu, tdu, tdd, tud;
+    if (k < n1d) { tuu = tdd = a11[c]; tdu = tud = a12[c]; }
+    else {
+      tuu = (double)T[(long)(0 * Nf + 0) * g.ncp + c]; tdu = (double)T[(long)(0 * Nf + 1) * g.ncp + c];
+      tud = (double)T[(long)(1 * Nf + 0) * g.ncp + c]; tdd = (double)T[(long)(1 * Nf + 1) * g.ncp + c];
+    }
+    double iv = 1.0 / (1.0 - tud * Rn);
+    Rn = tdu + tuu * Rn * tdd * iv;
+    inv[c] = iv;
+    R[c] = Rn;
+  }
+}
+
+// upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied.  If `upd` is set the input vector is first formed
+// as r <- r + beta*(p_old - omega*v) (the BiCGStab direction update fused in), and written back to p.
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
+          const double *__restrict__ R, const double *__restrict__ inv, const double *__restrict__ r,
+          double *__restrict__ z) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  static_assert(Nft == 2, "column preconditioner needs one up/down pair of top streams");
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.ncol) return;
+  const long lz = (long)g.Nz * g.ncol + col;
+  double S = r[0 * g.nlev + lz];  // f_U at the surface
+  z[0 * g.nlev + lz] = S;
+#pragma unroll
+  for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + lz] = r[(long)d * g.nlev + lz];
+  double Rn = R[lz];
+  for (int k = g.Nz - 1; k >= 0; --k) {
+    const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+    double fU = r[0 * g.nlev + c], fD = r[1 * g.nlev + l1];
+    double tuu, tud;
+    if (k < n1d) {
+      tuu = a11[c]; tud = a12[c];
+#pragma unroll
+      for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + c] = r[(long)d * g.nlev + c];
+    } else {
+      tuu = (double)T[(long)(0 * Nf + 0) * g.ncp + c];
+      tud = (double)T[(long)(1 * Nf + 0) * g.ncp + c];
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        const int dof = Nft + d;
+        const bool inw = L::side_in(d % Nfs);
+        if (inw) {
+          double rs = r[(long)dof * g.nlev + c];
+          z[(long)dof * g.nlev + c] = rs;
+          fU = fma((double)T[(long)(0 * Nf + dof) * g.ncp + c], rs, fU);
+          fD = fma((double)T[(long)(1 * Nf + dof) * g.ncp + c], rs, fD);
+        }
+      }
+    }
+    const double iv = inv[c];
+    S = fU + tuu * (S + Rn * (tud * S + fD) * iv);
+    Rn = R[c];
+    z[0 * g.nlev + c] = S;
+    z[1 * g.nlev + l1] = fD;
+  }
+  z[1 * g.nlev + col] = r[1 * g.nlev + col];  // f_D(0) = r_D(0)
+}
+
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
+            const double *__restrict__ a12, const double *__restrict__ R, const double *__restrict__ inv,
+            const double *__restrict__ r, double *__restrict__ z) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.ncol) return;
+  double D = z[1 * g.nlev + col];
+  double U = R[col] * D + z[0 * g.nlev + col];
+  z[0 * g.nlev + col] = U;
+  for (int k = 0; k < g.Nz; ++k) {
+    const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+    double tdd, tud;
+    if (k < n1d) { tdd = a11[c]; tud = a12[c]; }
+    else { tdd = (double)T[(long)(1 * Nf + 1) * g.ncp + c]; tud = (double)T[(long)(1 * Nf + 0) * g.ncp + c]; }
+    const double S1 = z[0 * g.nlev + l1], fD = z[1 * g.nlev + l1];
+    const double D1 = (tdd * D + tud * S1 + fD) * inv[c];
+    const double U1 = R[l1] * D1 + S1;
+    if (k >= n1d) {  // outgoing side streams through the column's own faces
+      double rin[2 * Nfs];
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) rin[d] = L::side_in(d % Nfs) ? r[(long)(Nft + d) * g.nlev + c] : 0.0;
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        if (!L::side_in(d % Nfs)) {
+          const int dof = Nft + d;
+          double acc = r[(long)dof * g.nlev + c];
+          acc = fma((double)T[(long)(dof * Nf + 0) * g.ncp + c], U1, acc);
+          acc = fma((double)T[(long)(dof * Nf + 1) * g.ncp + c], D, acc);
+#pragma unroll
+          for (int s = 0; s < 2 * Nfs; ++s)
+            if (L::side_in(s % Nfs)) acc = fma((double)T[(long)(dof * Nf + Nft + s) * g.ncp + c], rin[s], acc);
+          z[(long)dof * g.nlev + c] = acc;
+        }
+      }
+    }
+    z[0 * g.nlev + l1] = U1;
+    z[1 * g.nlev + l1] = D1;
+    D = D1;
+  }
+}
+
+// =================================================================================================================
+// BiCGStab vector kernels.  Scalars live in device memory (sc[]); every kernel derives alpha/beta/omega from the raw
+// dot products itself, the last block of the reducing kernels rotates them -> no host round trip inside an iteration
+// except the convergence read.
+// =================================================================================================================
+enum { SC_RHO = 0, SC_RHO_OLD, SC_ALPHA, SC_OMEGA, SC_RHV, SC_TS, SC_TT, SC_RR, SC_RHO_NEW, SC_BNORM1, SC_EDIR0 = 16, SC_COUNT = 32 };
+
+// r = b - Ax (Ax in `r` on entry), rh = r, p = v = 0, rr = rho = (r,r)
+__global__ void k_bicg_init(long n, const double *__restrict__ b, double *__restrict__ r, double *__restrict__ rh,
+                            double *__restrict__ p, double *__restrict__ v, double *partials, unsigned int *counter,
+                            double *sc) {
+  double acc[1] = {0.0};
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    double rv = b[q] - r[q];
+    r[q] = rv; rh[q] = rv; p[q] = 0.0; v[q] = 0.0;
+    acc[0] += rv * rv;
+  }
+  if (grid_reduce_sum<1>(acc, partials, counter, &sc[SC_RR])) {
+    if (threadIdx.x == 0) { sc[SC_RHO] = sc[SC_RR]; sc[SC_RHO_OLD] = 1.0; sc[SC_ALPHA] = 1.0; sc[SC_OMEGA] = 1.0; }
+  }
+}
+// p = r + beta (p - omega v),  beta = (rho/rho_old)(alpha/omega)
+__global__ void k_bicg_update_p(long n, const double *__restrict__ r, const double *__restrict__ v,
+                                double *__restrict__ p, const double *__restrict__ sc) {
+  const double beta = (sc[SC_RHO] / sc[SC_RHO_OLD]) * (sc[SC_ALPHA] / sc[SC_OMEGA]), omega = sc[SC_OMEGA];
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
+    p[q] = r[q] + beta * (p[q] - omega * v[q]);
+}
+// s = r - alpha v, alpha = rho / (rh, v)
+__global__ void k_bicg_update_s(long n, const double *__restrict__ r, const double *__restrict__ v,
+                                double *__restrict__ s, double *sc) {
+  const double alpha = sc[SC_RHO] / sc[SC_RHV];
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
+    s[q] = r[q] - alpha * v[q];
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc[SC_ALPHA] = alpha;
+}
+// x += alpha ph + omega sh ; r = s - omega t ; rr = (r,r), rho_new = (rh, r); rotate scalars
+__global__ void k_bicg_update_xr(long n, const double *__restrict__ ph, const double *__restrict__ sh,
+                                 const double *__restrict__ s, const double *__restrict__ t,
+                                 const double *__restrict__ rh, double *__restrict__ x, double *__restrict__ r,
+                                 double *partials, unsigned int *counter, double *sc) {
+  const double alpha = sc[SC_RHO] / sc[SC_RHV];
+  const double tt = sc[SC_TT];
+  const double omega = (tt > 0.0) ? sc[SC_TS] / tt : 0.0;
+  double acc[2] = {0.0, 0.0};
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    x[q] = x[q] + alpha * ph[q] + omega * sh[q];
+    double rv = s[q] - omega * t[q];
+    r[q] = rv;
+    acc[0] += rv * rv;
+    acc[1] += rv * rh[q];
+  }
+  if (grid_reduce_sum<2>(acc, partials, counter, &sc[SC_RR])) {  // writes SC_RR, SC_RHO_NEW (adjacent)
+    if (threadIdx.x == 0) {
+      sc[SC_RHO_OLD] = sc[SC_RHO];
+      sc[SC_RHO] = sc[SC_RHO_NEW];
+      sc[SC_OMEGA] = omega;
+      sc[SC_ALPHA] = alpha;
+    }
+  }
+}
+// sum |b| (src/pprts.F90:2774)
+__global__ void k_norm1(long n, const double *__restrict__ b, double *partials, unsigned int *counter, double *out) {
+  double acc[1] = {0.0};
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
+    acc[0] += fabs(b[q]);
+  grid_reduce_sum<1>(acc, partials, counter, out);
+}
+
+// =================================================================================================================
+// HOT LOOP E: absorption (src/pprts.F90:5152-5504 calc_flx_div) -- fluxes in W, result in W/m3
+// =================================================================================================================
+template <class L>
+__global__ void __launch_bounds__(128)
+k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int by_coeff, double costheta,
+             const double *__restrict__ cdiv_dir, const double *__restrict__ cdiv_diff,
+             const double *__restrict__ a11, const double *__restrict__ a12, const double *__restrict__ kabs,
+             const double *__restrict__ dz, const double *__restrict__ edir, const double *__restrict__ ediff,
+             const double *__restrict__ bsrc, double *__restrict__ abso) {
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.ncell) return;
+  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
+  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
+  const long l_own = lidx(g, k, j, i), l_dn = l_own + g.ncol;
+  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+  const long l_xin = xinc ? l_own : l_xp, l_xout = xinc ? l_xp : l_own;
+  const long l_yin = yinc ? l_own : l_yp, l_yout = yinc ? l_yp : l_own;
+  const bool l1d = k < n1d;
+  double a = 0.0;
+  if (by_coeff) {
+    if (lsolar) {
+      if (l1d) {
+#pragma unroll
+        for (int s = 0; s < Ndt; ++s) {
+          double cdiv = kabs[c] * dz[c] / costheta;
+          a += edir[(long)s * g.nlev + l_own] * (-expm1(-cdiv));
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < Nd; ++s) {
+          long q = (s < Ndt) ? l_own : (s < Ndt + Nds) ? l_xin : l_yin;
+          a += edir[(long)s * g.nlev + q] * cdiv_dir[(long)s * g.ncp + c];
+        }
+      }
+    }
+    if (!l1d) {
+#pragma unroll
+      for (int s = 0; s < Nf; ++s) {
+        long q;
+        if (s < Nft) q = L::top_in(s) ? l_own : l_dn;
+        else if (s < Nft + Nfs) q = L::side_in(s - Nft) ? l_own : l_xp;
+        else q = L::side_in(s - Nft - Nfs) ? l_own : l_yp;
+        a += ediff[(long)s * g.nlev + q] * cdiv_diff[(long)s * g.ncp + c];
+      }
+    } else {
+      double cdiv = fmax(0.0, 1.0 - a11[c] - a12[c]);
+#pragma unroll
+      for (int s = 0; s < Nft; ++s) a += ediff[(long)s * g.nlev + (L::top_in(s) ? l_own : l_dn)] * cdiv;
+    }
+    if (lthermal) {
+#pragma unroll
+      for (int s = 0; s < Nf; ++s) {
+        long q;
+        if (s < Nft) q = L::top_in(s) ? l_dn : l_own;
+        else if (s < Nft + Nfs) q = L::side_in(s - Nft) ? l_xp : l_own;
+        else q = L::side_in(s - Nft - Nfs) ? l_yp : l_own;
+        a -= bsrc[(long)s * g.nlev + q];
+      }
+    }
+  } else {  // by flux divergence (:5400-5472)
+    if (lsolar) {
+#pragma unroll
+      for (int s = 0; s < Ndt; ++s) a += edir[(long)s * g.nlev + l_own] - edir[(long)s * g.nlev + l_dn];
+      if (!l1d) {
+#pragma unroll
+        for (int s = Ndt; s < Ndt + Nds; ++s) a += edir[(long)s * g.nlev + l_xin] - edir[(long)s * g.nlev + l_xout];
+#pragma unroll
+        for (int s = Ndt + Nds; s < Nd; ++s) a += edir[(long)s * g.nlev + l_yin] - edir[(long)s * g.nlev + l_yout];
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < Nft; ++s) {
+      if (L::top_in(s)) a += ediff[(long)s * g.nlev + l_own] - ediff[(long)s * g.nlev + l_dn];
+      else a += ediff[(long)s * g.nlev + l_dn] - ediff[(long)s * g.nlev + l_own];
+    }
+    if (!l1d) {
+#pragma unroll
+      for (int s = 0; s < Nfs; ++s) {
+        long q = (long)(Nft + s) * g.nlev;
+        if (L::side_in(s)) a += ediff[q + l_own] - ediff[q + l_xp];
+        else a += ediff[q + l_xp] - ediff[q + l_own];
+      }
+#pragma unroll
+      for (int s = 0; s < Nfs; ++s) {
+        long q = (long)(Nft + Nfs + s) * g.nlev;
+        if (L::side_in(s)) a += ediff[q + l_own] - ediff[q + l_yp];
+        else a += ediff[q + l_yp] - ediff[q + l_own];
+      }
+    }
+  }
+  abso[c] = a * (1.0 / (g.dx * g.dy * dz[c]));  // abso_scalevec (:5477, :5483-5503)
+}
+
+// pprts_get_result (src/pprts.F90:5799-5917): sum the top streams, x mu for solar; device layout level fields
+template <class L>
+__global__ void k_result(Grid g, int lsolar, double mu, const double *__restrict__ edir,
+                         const double *__restrict__ ediff, const double *__restrict__ abso_in,
+                         double *__restrict__ edn, double *__restrict__ eup, double *__restrict__ redir,
+                         double *__restrict__ abso, int accumulate, double weight) {
+  constexpr int Ndt = L::Ndt, Nft = L::Nft;
+  long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= g.nlev) return;
+  double dn = 0, up = 0, dr = 0;
+#pragma unroll
+  for (int d = 0; d < Nft; ++d) {
+    if (L::top_in(d)) dn = dn + ediff[(long)d * g.nlev + l];
+    else up = up + ediff[(long)d * g.nlev + l];
+  }
+  if (lsolar) {
+#pragma unroll
+    for (int d = 0; d < Ndt; ++d) dr += edir[(long)d * g.nlev + l];
+    dr = dr / (double)L::dirtop_adiv;
+    dr *= mu; dn *= mu; up *= mu;
+  }
+  if (accumulate) { edn[l] += weight * dn; eup[l] += weight * up; redir[l] += weight * dr; }
+  else { edn[l] = dn; eup[l] = up; redir[l] = dr; }
+  if (l < g.ncell) {
+    double a = abso_in[l] * (lsolar ? mu : 1.0);
+    if (accumulate) abso[l] += weight * a; else abso[l] = a;
+  }
+}

@@ -1,0 +1,1111 @@
+// solver.cu -- host side of libpprts_b200.so: the handle-based C ABI of include/pprts_b200.h.
+// Mirrors the Fortran module API of the reference (src/pprts.F90:192-200); the orchestration below follows
+// solve_pprts -> pprts() -> restore_solution (src/pprts.F90:2487-3033, :3991-4076) step by step, every heavy step
+// being one of the kernels in kernels.cuh.  There is no CPU fallback anywhere in this file.
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pprts_b200.h"
+#include "kernels.cuh"
+#include "internal.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char *pprts_b200_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return set_err(100 + (int)e_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// LUT (host side): memory-mapped .mmap4 files (src/mmap.F90:129-203)
+// ---------------------------------------------------------------------------------------------------------------
+struct pprts_b200_lut {
+  int solver_id, Nd, Nf;
+  int n[6];
+  std::vector<float> ax[6];
+  long off[6];
+  const float *Tdir = nullptr, *Sdir = nullptr, *Sdiff = nullptr;
+  void *map[3] = {nullptr, nullptr, nullptr};
+  size_t maplen[3] = {0, 0, 0};
+};
+
+static int stream_counts(int solver_id, int &Nd, int &Nf) {
+  switch (solver_id) {
+    case 310: Nd = L310::Nd; Nf = L310::Nf; return 0;
+    case 810: Nd = L810::Nd; Nf = L810::Nf; return 0;
+    case 324: Nd = L324::Nd; Nf = L324::Nf; return 0;
+  }
+  return 1;
+}
+
+static int mmap4_open(const char *path, const float **data, long *ncoef, long *nlat, void **map, size_t *maplen) {
+  long pagesize = sysconf(_SC_PAGESIZE);
+  size_t nhdr = (size_t)pagesize / sizeof(size_t);
+  std::vector<size_t> header(nhdr);
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return set_err(2, "cannot open LUT file %s", path);
+  if (read(fd, header.data(), nhdr * sizeof(size_t)) != (ssize_t)(nhdr * sizeof(size_t))) {
+    close(fd);
+    return set_err(2, "short read on %s", path);
+  }
+  if (header[0] != sizeof(float)) { close(fd); return set_err(2, "%s: dtype size %zu != 4", path, header[0]); }
+  int ndim = 0;
+  for (size_t i = 3; i < nhdr; ++i) ndim += header[i] != 0;
+  if (ndim != 2) { close(fd); return set_err(2, "%s: expected a 2-d table", path); }
+  *ncoef = (long)header[3];
+  *nlat = (long)header[4];
+  *maplen = header[2] + (size_t)pagesize;
+  *map = mmap(0, *maplen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, 0);
+  close(fd);
+  if (*map == MAP_FAILED) return set_err(2, "mmap failed on %s", path);
+  *data = (const float *)((const char *)(*map) + pagesize);
+  return 0;
+}
+
+extern "C" int pprts_b200_lut_open(int solver_id, const char *pT, const char *pS, const char *pD, const int ndir[6],
+                                   const float *const axes[6], pprts_b200_lut **out) {
+  auto *lut = new pprts_b200_lut();
+  lut->solver_id = solver_id;
+  if (stream_counts(solver_id, lut->Nd, lut->Nf)) { delete lut; return set_err(1, "unknown solver id %d", solver_id); }
+  long nlat_dir = 1, nlat_diff = 1;
+  for (int d = 0; d < 6; ++d) {
+    lut->n[d] = ndir[d];
+    lut->ax[d].assign(axes[d], axes[d] + ndir[d]);
+    for (int q = 1; q < ndir[d]; ++q)
+      if (!(axes[d][q] > axes[d][q - 1])) { delete lut; return set_err(1, "LUT axis %d is not strictly ascending", d); }
+    lut->off[d] = d == 0 ? 1 : lut->off[d - 1] * ndir[d - 1];
+    nlat_dir *= ndir[d];
+    if (d < 4) nlat_diff *= ndir[d];
+  }
+  long nc, nl;
+  int rc;
+  if (pT && pS) {
+    if ((rc = mmap4_open(pT, &lut->Tdir, &nc, &nl, &lut->map[0], &lut->maplen[0]))) { delete lut; return rc; }
+    if (nc != lut->Nd * lut->Nd || nl != nlat_dir) { delete lut; return set_err(3, "%s: shape (%ld,%ld) does not match the axes", pT, nc, nl); }
+    if ((rc = mmap4_open(pS, &lut->Sdir, &nc, &nl, &lut->map[1], &lut->maplen[1]))) { delete lut; return rc; }
+    if (nc != lut->Nd * lut->Nf || nl != nlat_dir) { delete lut; return set_err(3, "%s: shape (%ld,%ld) does not match the axes", pS, nc, nl); }
+  }
+  if ((rc = mmap4_open(pD, &lut->Sdiff, &nc, &nl, &lut->map[2], &lut->maplen[2]))) { delete lut; return rc; }
+  if (nc != lut->Nf * lut->Nf || nl != nlat_diff) { delete lut; return set_err(3, "%s: shape (%ld,%ld) does not match the axes", pD, nc, nl); }
+  *out = lut;
+  return 0;
+}
+extern "C" int pprts_b200_lut_close(pprts_b200_lut *lut) {
+  if (!lut) return 0;
+  for (int d = 0; d < 3; ++d) if (lut->map[d]) munmap(lut->map[d], lut->maplen[d]);
+  delete lut;
+  return 0;
+}
+
+// search_sorted_bisection on the host (src/search.fypp:177-232), fp32 axis, fp64 arithmetic
+static double h_find_real_location(const std::vector<float> &arr, float val) {
+  int i = 1, j = (int)arr.size();
+  const double v = (double)val;
+  for (;;) {
+    int k = (i + j) / 2;
+    if (v < (double)arr[k - 1]) j = k; else i = k;
+    if (i + 1 >= j) {
+      double inc = (i == j) ? 0.0 : (v - (double)arr[i - 1]) / ((double)arr[j - 1] - (double)arr[i - 1]);
+      return std::min(std::max(1.0, (double)i + inc), (double)arr.size());
+    }
+  }
+}
+
+// stream permutation gather maps (src/optprop.F90:986-1301): new[n] = old[map[n]]
+static void apply_blocks(std::vector<short> &m, int Nsrc, const std::vector<std::pair<int, int>> &blocks,
+                         const int *srcperm) {
+  std::vector<short> bak = m;
+  for (auto &b : blocks)
+    for (int s = 0; s < Nsrc; ++s) m[b.first * Nsrc + s] = bak[b.second * Nsrc + (srcperm ? srcperm[s] : s)];
+}
+static void build_sym_maps(int solver_id, bool le, bool ln, SymMaps &sym) {
+  int Nd, Nf;
+  stream_counts(solver_id, Nd, Nf);
+  std::vector<short> d2d(Nd * Nd), d2f(Nd * Nf);
+  for (int n = 0; n < Nd * Nd; ++n) d2d[n] = (short)n;
+  for (int n = 0; n < Nd * Nf; ++n) d2f[n] = (short)n;
+  static const int pe[8] = {1, 0, 3, 2, 4, 5, 6, 7}, pn[8] = {2, 3, 0, 1, 4, 5, 6, 7};
+  if (solver_id == 310) {  // :1009-1045
+    if (le) apply_blocks(d2f, Nd, {{2, 3}, {3, 2}, {4, 5}, {5, 4}}, nullptr);
+    if (ln) apply_blocks(d2f, Nd, {{6, 7}, {7, 6}, {8, 9}, {9, 8}}, nullptr);
+  } else if (solver_id == 810) {  // :1148-1184 (dir2diff), :1268-1301 (dir2dir)
+    if (le) apply_blocks(d2f, Nd, {{2, 3}, {3, 2}, {4, 5}, {5, 4}}, pe);
+    if (ln) apply_blocks(d2f, Nd, {{6, 7}, {7, 6}, {8, 9}, {9, 8}}, pn);
+    if (le) apply_blocks(d2d, Nd, {{0, 1}, {1, 0}, {2, 3}, {3, 2}, {4, 4}, {5, 5}, {6, 6}, {7, 7}}, pe);
+    if (ln) apply_blocks(d2d, Nd, {{0, 2}, {1, 3}, {2, 0}, {3, 1}, {4, 4}, {5, 5}, {6, 6}, {7, 7}}, pn);
+  } else if (solver_id == 324) {  // :1098-1124
+    if (le) apply_blocks(d2f, Nd, {{0, 2}, {2, 0}, {4, 6}, {6, 4}, {1, 3}, {3, 1}, {5, 7}, {7, 5},
+                                   {9, 8}, {11, 10}, {13, 12}, {15, 14}, {8, 9}, {10, 11}, {12, 13}, {14, 15}}, nullptr);
+    if (ln) apply_blocks(d2f, Nd, {{0, 4}, {2, 6}, {4, 0}, {6, 2}, {1, 5}, {3, 7}, {5, 1}, {7, 3},
+                                   {17, 16}, {19, 18}, {21, 20}, {23, 22}, {16, 17}, {18, 19}, {20, 21}, {22, 23}}, nullptr);
+  }
+  memset(&sym, 0, sizeof(sym));
+  for (int n = 0; n < Nd * Nd; ++n) sym.d2d[n] = d2d[n];
+  for (int n = 0; n < Nd * Nf; ++n) sym.d2f[n] = d2f[n];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// solver object
+// ---------------------------------------------------------------------------------------------------------------
+struct Solution {  // t_state_container (src/pprts_base.F90:137-169)
+  bool lset = false, lsolar_rad = false, lthermal_rad = false, lchanged = true, lWm2_dir = true, lWm2_diff = true;
+  double *edir = nullptr, *ediff = nullptr, *abso = nullptr;
+  bool first_dir = true, first_diff = true;  // residual_history(1) < 0
+  int niter_dir = 0, niter_diff = 0;
+  double res_dir = 0, res_diff = 0;
+};
+
+enum { FAM_LOOKUP = 0, FAM_EDIR, FAM_SOURCE, FAM_MATMULT, FAM_PRECOND, FAM_VEC, FAM_ABSO, FAM_IO, FAM_COUNT };
+
+struct Staged {
+  double albedo = 0;
+  double *kabs = nullptr, *ksca = nullptr, *g = nullptr, *planck = nullptr, *Bsrfc = nullptr, *albedo2d = nullptr;
+  bool have_planck = false, have_Bsrfc = false, have_albedo2d = false;
+};
+
+struct pprts_b200_solver {
+  pprts_b200_config cfg;
+  const pprts_b200_lut *lut = nullptr;
+  int device = 0;
+  Grid g;
+  int Nd = 0, Nf = 0, n1d = 0;
+  double unconstrained_fraction = 1.0;
+  std::vector<unsigned char> l1d;
+  // sun (t_suninfo, src/pprts_base.F90:128-135)
+  double phi = 0, theta = 0, mu = 0, costheta = 0, symmetry_phi = 0;
+  int xinc = 0, yinc = 0;
+  bool angles_dirty = true, coeffs_dirty = true, coeffs_have_dir = false;
+  // device state
+  cudaStream_t stream = nullptr;
+  double *dz = nullptr, *kabs = nullptr, *ksca = nullptr, *gg = nullptr, *planck = nullptr, *Bsrfc = nullptr,
+         *albedo = nullptr, *raw = nullptr;
+  bool have_planck = false, have_Bsrfc = false, have_optprop = false;
+  double *a11 = nullptr, *a12 = nullptr, *a13 = nullptr, *a23 = nullptr, *a33 = nullptr;
+  void *d2d = nullptr, *d2f = nullptr, *f2f = nullptr;
+  double *cdiv_dir = nullptr, *cdiv_diff = nullptr;
+  double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
+  double *precR = nullptr, *precInv = nullptr;
+  bool prec_ready = false;
+  double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
+  bool res_valid = false;
+  int res_uid = 0;
+  double *partials = nullptr, *sc = nullptr;
+  unsigned int *counter = nullptr;
+  int *bad = nullptr;
+  double *h_sc = nullptr;  // pinned
+  int *h_bad = nullptr;
+  // LUT on device
+  float *d_ax[4] = {nullptr};
+  double *d_Tdir4 = nullptr, *d_Sdir4 = nullptr;
+  float *d_Sdiff = nullptr;
+  LutDev lutdev;
+  SymMaps sym;
+  std::map<int, Solution> solutions;
+  std::map<int, Staged> staged;
+  // stats
+  long launches = 0;
+  bool timing = false;
+  long fam_launch[FAM_COUNT] = {0};
+  double fam_ms[FAM_COUNT] = {0};
+  struct Ev { int fam; cudaEvent_t a, b; };
+  std::vector<Ev> evs;
+  std::vector<cudaEvent_t> evpool;
+  // NCCL
+  void *nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+static cudaEvent_t get_event(pprts_b200_solver *s) {
+  if (!s->evpool.empty()) { cudaEvent_t e = s->evpool.back(); s->evpool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+static void collect_events(pprts_b200_solver *s) {
+  if (s->evs.empty()) return;
+  cudaStreamSynchronize(s->stream);
+  for (auto &ev : s->evs) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev.a, ev.b);
+    s->fam_ms[ev.fam] += ms;
+    s->evpool.push_back(ev.a);
+    s->evpool.push_back(ev.b);
+  }
+  s->evs.clear();
+}
+
+#define LAUNCH(S, FAM, KERNEL, GRID, BLOCK, ...)                           \
+  do {                                                                     \
+    cudaEvent_t ea_ = nullptr, eb_ = nullptr;                              \
+    if ((S)->timing) { ea_ = get_event(S); eb_ = get_event(S); cudaEventRecord(ea_, (S)->stream); } \
+    KERNEL<<<(GRID), (BLOCK), 0, (S)->stream>>>(__VA_ARGS__);              \
+    if ((S)->timing) { cudaEventRecord(eb_, (S)->stream); (S)->evs.push_back({FAM, ea_, eb_}); } \
+    (S)->launches++;                                                       \
+    (S)->fam_launch[FAM]++;                                                \
+  } while (0)
+
+#define DISPATCH_L(S, ...)                                          \
+  do {                                                              \
+    switch ((S)->cfg.solver_id) {                                   \
+      case 310: { using L = L310; __VA_ARGS__; } break;             \
+      case 810: { using L = L810; __VA_ARGS__; } break;             \
+      case 324: { using L = L324; __VA_ARGS__; } break;             \
+    }                                                               \
+  } while (0)
+#define DISPATCH_LC(S, ...)                                                             \
+  do {                                                                                  \
+    if ((S)->cfg.coeff_fp32) { using CT = float; DISPATCH_L(S, __VA_ARGS__); }          \
+    else { using CT = double; DISPATCH_L(S, __VA_ARGS__); }                             \
+  } while (0)
+
+static inline unsigned int nblk(long n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+static const int VEC_BLOCK = 256;
+static inline unsigned int vec_grid(long n) { return (unsigned int)std::min<long>((n + VEC_BLOCK - 1) / VEC_BLOCK, 148L * 16); }
+
+extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->solver_id = 310;
+  cfg->twostr_ratio = 2.0;
+  cfg->coeff_fp32 = 1;
+  cfg->by_coeff_divergence = 1;
+  cfg->rtol = -1; cfg->atol = -1;
+  cfg->precond = 1;
+  cfg->device = -1;
+  cfg->keep_solutions = 1;
+  cfg->nxproc = cfg->nyproc = 1;
+}
+
+template <class T>
+static int dalloc(T **p, size_t n) {
+  CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+  CU(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+#define DA(p, n) do { int rc_ = dalloc(&(p), (n)); if (rc_) return rc_; } while (0)
+
+// src/pprts.F90:1118-1183 (setup_suninfo) incl. cartesian_2_spherical (helper_functions.fypp:1993-2016)
+static void setup_suninfo(pprts_b200_solver *s, const double sundir[3]) {
+  const double d2r = PB_PI / 180.0;
+  double n = std::sqrt(sundir[0] * sundir[0] + sundir[1] * sundir[1] + sundir[2] * sundir[2]);
+  double sn2 = n > 0 ? sundir[2] / n : sundir[2];
+  double theta = std::acos(std::max(-1.0, std::min(1.0, -sn2))) / d2r;
+  double px = sundir[0], py = sundir[1], pn = std::sqrt(px * px + py * py);
+  if (pn > 0) { px /= pn; py /= pn; }
+  double az = std::acos(std::max(-1.0, std::min(1.0, -py)));
+  az = az * ((-px) >= 0 ? 1.0 : -1.0);
+  s->phi = az / d2r;
+  s->theta = theta;
+  s->mu = std::max(std::cos(s->theta * d2r), 0.0);
+  if (s->theta >= 90.0) s->theta = -1.0;
+  s->costheta = std::max(std::cos(s->theta * d2r), 0.0);
+  double sp = std::acos(std::cos(s->phi * d2r));
+  s->symmetry_phi = std::min(90.0, std::max(0.0, std::asin(std::sin(sp)) / d2r));
+  s->xinc = (std::sin(s->phi * d2r) > 0.0) ? 0 : 1;
+  s->yinc = (std::cos(s->phi * d2r) < 0.0) ? 1 : 0;
+  s->angles_dirty = true;
+  s->coeffs_dirty = true;
+}
+
+// Contract the 6-D direct tables over (phi, theta) for the current sun: interp_vec_bilinear_iterative restricted to
+// the two slowest axes (snapping included), fp64.  Touches <= 4 contiguous (phi,theta) blocks of the mapped files.
+static int contract_direct_tables(pprts_b200_solver *s) {
+  const pprts_b200_lut *lut = s->lut;
+  if (!lut->Tdir || !lut->Sdir) return set_err(4, "direct LUT tables not loaded");
+  const double snap = (double)1e-3f;
+  long lat4 = 1;
+  for (int d = 0; d < 4; ++d) lat4 *= lut->n[d];
+  double pti[2] = {h_find_real_location(lut->ax[4], (float)s->symmetry_phi),
+                   h_find_real_location(lut->ax[5], (float)s->theta)};
+  long off_lo[2], off_hi[2], base = 0;
+  double wlo[2], whi[2];
+  int Ninterp = 0;
+  for (int d = 0; d < 2; ++d) {
+    double frac = pti[d] - (double)(long)pti[d];
+    if (frac < snap || frac > 1.0 - snap) base += lut->off[4 + d] * (std::lround(pti[d]) - 1);
+    else {
+      long b = (long)pti[d];
+      whi[Ninterp] = pti[d] - (double)b; wlo[Ninterp] = 1.0 - whi[Ninterp];
+      off_lo[Ninterp] = lut->off[4 + d] * (b - 1); off_hi[Ninterp] = lut->off[4 + d] * b;
+      ++Ninterp;
+    }
+  }
+  const int ncorner = 1 << Ninterp;
+  long cofs[4];
+  double cw[4];
+  for (int b = 0; b < ncorner; ++b) {
+    long o = base; double w = 1.0;
+    for (int d = 0; d < Ninterp; ++d) { if (b & (1 << d)) { o += off_hi[d]; w *= whi[d]; } else { o += off_lo[d]; w *= wlo[d]; } }
+    cofs[b] = o; cw[b] = w;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    const int nc = pass == 0 ? s->Nd * s->Nd : s->Nd * s->Nf;
+    const float *tab = pass == 0 ? lut->Tdir : lut->Sdir;
+    std::vector<double> h((size_t)lat4 * nc, 0.0);
+    for (int b = 0; b < ncorner; ++b) {
+      const float *src = tab + cofs[b] * nc;
+      const double w = cw[b];
+      for (size_t q = 0; q < h.size(); ++q) h[q] = std::fma(w, (double)src[q], h[q]);
+    }
+    CU(cudaMemcpyAsync(pass == 0 ? s->d_Tdir4 : s->d_Sdir4, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  build_sym_maps(s->cfg.solver_id, s->xinc == 0, s->yinc == 0, s->sym);
+  s->angles_dirty = false;
+  return 0;
+}
+
+extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_lut *lut, pprts_b200_solver **out) {
+  if (!cfg || !lut || !out) return set_err(1, "null argument");
+  int Nd, Nf;
+  if (stream_counts(cfg->solver_id, Nd, Nf)) return set_err(1, "unknown solver id %d", cfg->solver_id);
+  if (lut->solver_id != cfg->solver_id) return set_err(1, "LUT was opened for solver %d, not %d", lut->solver_id, cfg->solver_id);
+  if (cfg->Nz < 1 || cfg->Nx < 1 || cfg->Ny < 1) return set_err(1, "bad grid %d %d %d", cfg->Nz, cfg->Nx, cfg->Ny);
+  if (std::fabs(cfg->dx - cfg->dy) > 1e-9 * std::fabs(cfg->dx))  // src/pprts.F90:459
+    return set_err(1, "dx and dy currently have to be the same %g vs %g", cfg->dx, cfg->dy);
+  if ((cfg->dz1d == nullptr) == (cfg->dz3d == nullptr)) return set_err(1, "have to give either dz1d or dz3d");
+  if ((cfg->nxproc > 1 || cfg->nyproc > 1)) return set_err(1, "x/y decomposition is not available in this build");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(90, "no CUDA device: libpprts_b200 has no CPU fallback");
+  auto *s = new pprts_b200_solver();
+  s->cfg = *cfg;
+  if (s->cfg.twostr_ratio <= 0) s->cfg.twostr_ratio = 2.0;
+  s->cfg.dz1d = s->cfg.dz3d = nullptr;
+  s->lut = lut;
+  s->Nd = Nd; s->Nf = Nf;
+  if (cfg->device >= 0) { CU(cudaSetDevice(cfg->device)); s->device = cfg->device; }
+  else CU(cudaGetDevice(&s->device));
+  Grid &g = s->g;
+  g.Nz = cfg->Nz; g.Nx = cfg->Nx; g.Ny = cfg->Ny;
+  g.ncol = (long)g.Nx * g.Ny; g.ncell = g.ncol * g.Nz; g.nlev = g.ncol * (g.Nz + 1);
+  g.ncp = (g.ncell + 31) / 32 * 32;
+  g.dx = cfg->dx; g.dy = cfg->dy;
+  CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+  // dz in device layout + determine_1d_layers (src/pprts.F90:649-725)
+  std::vector<double> hdz((size_t)g.ncell);
+  s->l1d.assign(g.Nz, 0);
+  std::vector<unsigned char> thick(g.Nz, 0);
+  for (int j = 0; j < g.Ny; ++j) for (int i = 0; i < g.Nx; ++i) for (int k = 0; k < g.Nz; ++k) {
+    double v = cfg->dz1d ? cfg->dz1d[k] : cfg->dz3d[k + (size_t)g.Nz * (i + (size_t)g.Nx * j)];
+    hdz[((size_t)k * g.Ny + j) * g.Nx + i] = v;
+    if (v / cfg->dx > s->cfg.twostr_ratio) thick[k] = 1;
+  }
+  s->l1d[g.Nz - 1] = thick[g.Nz - 1];
+  for (int k = g.Nz - 2; k >= 0; --k) if (thick[k]) { for (int kk = 0; kk <= k; ++kk) s->l1d[kk] = 1; break; }
+  s->n1d = 0;
+  for (int k = 0; k < g.Nz; ++k) s->n1d += s->l1d[k];
+  for (int k = 0; k < g.Nz; ++k) s->l1d[k] = k < s->n1d;  // :708-719 contiguous from the top
+  s->unconstrained_fraction = (double)(g.Nz - s->n1d) / (double)g.Nz;
+
+  const size_t n1c = (size_t)s->n1d * g.ncol;
+  DA(s->dz, g.ncell); DA(s->kabs, g.ncell); DA(s->ksca, g.ncell); DA(s->gg, g.ncell);
+  DA(s->planck, g.nlev); DA(s->Bsrfc, g.ncol); DA(s->albedo, g.ncol); DA(s->raw, g.nlev);
+  DA(s->a11, n1c); DA(s->a12, n1c); DA(s->a13, n1c); DA(s->a23, n1c); DA(s->a33, n1c);
+  const size_t csz = cfg->coeff_fp32 ? 4 : 8;
+  CU(cudaMalloc(&s->d2d, (size_t)Nd * Nd * g.ncp * csz)); CU(cudaMemset(s->d2d, 0, (size_t)Nd * Nd * g.ncp * csz));
+  CU(cudaMalloc(&s->d2f, (size_t)Nd * Nf * g.ncp * csz)); CU(cudaMemset(s->d2f, 0, (size_t)Nd * Nf * g.ncp * csz));
+  CU(cudaMalloc(&s->f2f, (size_t)Nf * Nf * g.ncp * csz)); CU(cudaMemset(s->f2f, 0, (size_t)Nf * Nf * g.ncp * csz));
+  DA(s->cdiv_dir, (size_t)Nd * g.ncp); DA(s->cdiv_diff, (size_t)Nf * g.ncp);
+  DA(s->b, (size_t)Nf * g.nlev);
+  for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)Nf * g.nlev);
+  DA(s->edir_tmp, (size_t)Nd * g.nlev);
+  DA(s->precR, g.nlev); DA(s->precInv, g.ncell);
+  for (int q = 0; q < 4; ++q) { DA(s->res[q], g.nlev); DA(s->acc[q], g.nlev); }
+  DA(s->out_stage, (size_t)std::max(Nd, Nf) * g.nlev);
+  DA(s->partials, (size_t)4 * (nblk(g.ncell, 128) + 148 * 16 + 64));
+  DA(s->sc, SC_COUNT); DA(s->counter, 4); DA(s->bad, 1);
+  CU(cudaMallocHost((void **)&s->h_sc, SC_COUNT * sizeof(double)));
+  CU(cudaMallocHost((void **)&s->h_bad, sizeof(int)));
+  CU(cudaMemcpy(s->dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+  // LUT to the device: the four shared axes, the diffuse table; direct tables are contracted per sun angle
+  long lat4 = 1;
+  for (int d = 0; d < 4; ++d) {
+    lat4 *= lut->n[d];
+    DA(s->d_ax[d], lut->n[d]);
+    CU(cudaMemcpy(s->d_ax[d], lut->ax[d].data(), lut->n[d] * sizeof(float), cudaMemcpyHostToDevice));
+    s->lutdev.n[d] = lut->n[d]; s->lutdev.off[d] = lut->off[d]; s->lutdev.ax[d] = s->d_ax[d];
+  }
+  DA(s->d_Sdiff, (size_t)lat4 * Nf * Nf);
+  CU(cudaMemcpy(s->d_Sdiff, lut->Sdiff, (size_t)lat4 * Nf * Nf * sizeof(float), cudaMemcpyHostToDevice));
+  DA(s->d_Tdir4, (size_t)lat4 * Nd * Nd); DA(s->d_Sdir4, (size_t)lat4 * Nd * Nf);
+  s->lutdev.Tdir4 = s->d_Tdir4; s->lutdev.Sdir4 = s->d_Sdir4; s->lutdev.Sdiff = s->d_Sdiff;
+  build_sym_maps(cfg->solver_id, false, false, s->sym);
+  setup_suninfo(s, cfg->sundir);
+  *out = s;
+  return 0;
+}
+
+static void free_solution(Solution &sol) {
+  cudaFree(sol.edir); cudaFree(sol.ediff); cudaFree(sol.abso);
+  sol = Solution();
+}
+
+extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
+  if (!s) return 0;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  for (auto &kv : s->solutions) free_solution(kv.second);
+  for (auto &kv : s->staged) { cudaFree(kv.second.kabs); cudaFree(kv.second.ksca); cudaFree(kv.second.g);
+                               cudaFree(kv.second.planck); cudaFree(kv.second.Bsrfc); cudaFree(kv.second.albedo2d); }
+  double *ptrs[] = {s->dz, s->kabs, s->ksca, s->gg, s->planck, s->Bsrfc, s->albedo, s->raw, s->a11, s->a12, s->a13,
+                    s->a23, s->a33, s->cdiv_dir, s->cdiv_diff, s->b, s->edir_tmp, s->precR, s->precInv, s->out_stage,
+                    s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
+  for (double *p : ptrs) cudaFree(p);
+  for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
+  for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
+  cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
+  cudaFreeHost(s->h_sc); cudaFreeHost(s->h_bad);
+  for (auto &ev : s->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (auto e : s->evpool) cudaEventDestroy(e);
+  cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+extern "C" int pprts_b200_set_angles(pprts_b200_solver *s, const double sundir[3]) {
+  if (!s) return set_err(1, "null solver");
+  setup_suninfo(s, sundir);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// set_optical_properties (src/pprts.F90:1764-2076)
+// ---------------------------------------------------------------------------------------------------------------
+static int ingest_field(pprts_b200_solver *s, const double *src_dev_or_host, bool on_device, int nz, double *dst) {
+  const Grid &g = s->g;
+  const double *in = src_dev_or_host;
+  if (!on_device) {
+    CU(cudaMemcpyAsync(s->raw, src_dev_or_host, (size_t)nz * g.ncol * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    in = s->raw;
+  }
+  dim3 grid((g.Nx + 31) / 32, (nz + 31) / 32, g.Ny), block(32, 8);
+  LAUNCH(s, FAM_IO, k_zxy_to_kji<double>, grid, block, nz, g.Nx, g.Ny, in, dst);
+  return 0;
+}
+// 2-D (Nx,Ny) column-major is already x fastest == device layout
+static int ingest_2d(pprts_b200_solver *s, const double *src, bool on_device, double *dst) {
+  CU(cudaMemcpyAsync(dst, src, (size_t)s->g.ncol * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream));
+  return 0;
+}
+
+static int set_optprop_impl(pprts_b200_solver *s, double albedo, const double *kabs, const double *ksca,
+                            const double *g, const double *planck, const double *planck_srfc, const double *albedo_2d,
+                            int ldelta, bool on_device) {
+  const Grid &gr = s->g;
+  CU(cudaSetDevice(s->device));
+  int rc;
+  if (albedo_2d) { if ((rc = ingest_2d(s, albedo_2d, on_device, s->albedo))) return rc; }
+  else {
+    std::vector<double> h((size_t)gr.ncol, albedo);
+    CU(cudaMemcpyAsync(s->albedo, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  // the staging buffer `raw` is reused: serialize the three uploads on the stream (copies are stream ordered)
+  if (kabs) { if ((rc = ingest_field(s, kabs, on_device, gr.Nz, s->kabs))) return rc; }
+  if (ksca) { if ((rc = ingest_field(s, ksca, on_device, gr.Nz, s->ksca))) return rc; }
+  if (g) { if ((rc = ingest_field(s, g, on_device, gr.Nz, s->gg))) return rc; }
+  s->have_planck = planck != nullptr;
+  if (planck) { if ((rc = ingest_field(s, planck, on_device, gr.Nz + 1, s->planck))) return rc; }
+  s->have_Bsrfc = planck_srfc != nullptr;
+  if (planck_srfc) { if ((rc = ingest_2d(s, planck_srfc, on_device, s->Bsrfc))) return rc; }
+  CU(cudaMemsetAsync(s->bad, 0, sizeof(int), s->stream));
+  LAUNCH(s, FAM_IO, k_delta_scale, nblk(gr.ncell, 256), 256, gr.ncell, s->kabs, s->ksca, s->gg, ldelta, s->bad);
+  if (s->n1d > 0)
+    LAUNCH(s, FAM_IO, k_eddington, nblk((long)s->n1d * gr.ncol, 256), 256, gr, s->n1d, s->costheta, s->kabs, s->ksca,
+           s->gg, s->dz, s->a11, s->a12, s->a13, s->a23, s->a33);
+  CU(cudaMemcpyAsync(s->h_bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  if (*s->h_bad) return set_err(5, "set_optical_properties :: found illegal value in delta_scaled optical properties!");
+  s->have_optprop = true;
+  s->coeffs_dirty = true;
+  s->prec_ready = false;
+  return 0;
+}
+
+extern "C" int pprts_b200_set_optical_properties(pprts_b200_solver *s, double albedo, const double *kabs,
+                                                 const double *ksca, const double *g, const double *planck,
+                                                 const double *planck_srfc, const double *albedo_2d, int ldelta) {
+  if (!s) return set_err(1, "null solver");
+  return set_optprop_impl(s, albedo, kabs, ksca, g, planck, planck_srfc, albedo_2d, ldelta, false);
+}
+
+extern "C" int pprts_b200_stage_optical_properties(pprts_b200_solver *s, int slot, double albedo, const double *kabs,
+                                                   const double *ksca, const double *g, const double *planck,
+                                                   const double *planck_srfc, const double *albedo_2d) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const Grid &gr = s->g;
+  Staged &st = s->staged[slot];
+  st.albedo = albedo;
+  auto up = [&](double **dst, const double *src, size_t n) -> int {
+    if (!*dst) CU(cudaMalloc((void **)dst, n * sizeof(double)));
+    CU(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  int rc;
+  if ((rc = up(&st.kabs, kabs, gr.ncell)) || (rc = up(&st.ksca, ksca, gr.ncell)) || (rc = up(&st.g, g, gr.ncell))) return rc;
+  st.have_planck = planck != nullptr;
+  if (planck && (rc = up(&st.planck, planck, gr.nlev))) return rc;
+  st.have_Bsrfc = planck_srfc != nullptr;
+  if (planck_srfc && (rc = up(&st.Bsrfc, planck_srfc, gr.ncol))) return rc;
+  st.have_albedo2d = albedo_2d != nullptr;
+  if (albedo_2d && (rc = up(&st.albedo2d, albedo_2d, gr.ncol))) return rc;
+  return 0;
+}
+extern "C" int pprts_b200_set_optical_properties_staged(pprts_b200_solver *s, int slot, int ldelta) {
+  if (!s) return set_err(1, "null solver");
+  auto it = s->staged.find(slot);
+  if (it == s->staged.end()) return set_err(1, "no optical properties staged in slot %d", slot);
+  Staged &st = it->second;
+  return set_optprop_impl(s, st.albedo, st.kabs, st.ksca, st.g, st.have_planck ? st.planck : nullptr,
+                          st.have_Bsrfc ? st.Bsrfc : nullptr, st.have_albedo2d ? st.albedo2d : nullptr, ldelta, true);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// solve_pprts
+// ---------------------------------------------------------------------------------------------------------------
+static void determine_ksp_tolerances(const pprts_b200_solver *s, double &rtol, double &atol) {  // pprts_base.F90:1128-1131
+  rtol = 1e-5;
+  atol = std::max(1e-8, 1e-4 * (double)s->g.Nx * (double)s->g.Ny * (double)(s->g.Nz + 1) * s->unconstrained_fraction);
+}
+
+static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
+  if (!s->coeffs_dirty && (!lsolar || s->coeffs_have_dir)) return 0;
+  const Grid &g = s->g;
+  if (lsolar && s->angles_dirty) { int rc = contract_direct_tables(s); if (rc) return rc; }
+  const long n3d = (long)(g.Nz - s->n1d) * g.ncol;
+  if (n3d > 0) {
+    DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_lookup<L, CT>), nblk(n3d, 128), 128, g, s->lutdev, s->sym, (int)lsolar,
+                           s->n1d, s->kabs, s->ksca, s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f,
+                           s->cdiv_dir, s->cdiv_diff));
+  }
+  s->coeffs_dirty = false;
+  s->coeffs_have_dir = lsolar;
+  s->prec_ready = false;
+  return 0;
+}
+
+static int scale_flx(pprts_b200_solver *s, Solution &sol, bool lWm2) {
+  const Grid &g = s->g;
+  if (sol.lsolar_rad && sol.lWm2_dir != lWm2) {
+    DISPATCH_L(s, LAUNCH(s, FAM_VEC, (k_scale_flx<L::Ndt, L::Nds, L::dirtop_adiv, L::dirside_adiv>), nblk(g.nlev, 256),
+                          256, g, s->dz, sol.edir, (int)lWm2));
+    sol.lWm2_dir = lWm2;
+  }
+  if (sol.lWm2_diff != lWm2) {
+    DISPATCH_L(s, LAUNCH(s, FAM_VEC, (k_scale_flx<L::Nft, L::Nfs, 1, 1>), nblk(g.nlev, 256), 256, g, s->dz, sol.ediff,
+                          (int)lWm2));
+    sol.lWm2_diff = lWm2;
+  }
+  return 0;
+}
+
+static int read_scalars(pprts_b200_solver *s) {
+  CU(cudaMemcpyAsync(s->h_sc, s->sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// explicit_edir (src/pprts_explicit.F90:60-230)
+static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
+  const Grid &g = s->g;
+  int maxiter = s->cfg.maxit_dir > 0 ? s->cfg.maxit_dir : 1000;
+  double rtol_d, atol_d;
+  determine_ksp_tolerances(s, rtol_d, atol_d);
+  double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol.first_dir) { maxiter += 2; rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
+  int adiv = 1;
+  DISPATCH_L(s, adiv = L::dirtop_adiv);
+  const double fac = edirTOA * g.dx * g.dy / (double)adiv;
+  double *xold = sol.edir, *xnew = s->edir_tmp;
+  double res1 = 0;
+  bool converged = false;
+  // The horizontal inputs of a pass are one pass old, so information needs one pass per column it crosses; the
+  // norm is only read back every `check` passes to keep the host out of the loop.
+  const int check = 4;
+  int iter = 0;
+  while (iter < maxiter && !converged) {
+    int nb = std::min(check, maxiter - iter);
+    for (int q = 0; q < nb; ++q) {
+      DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_pass<L, CT>), nblk(g.ncol, 128), 128, g, s->xinc, s->yinc, s->n1d, fac,
+                             (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
+      std::swap(xold, xnew);
+    }
+    int rc = read_scalars(s);
+    if (rc) return rc;
+    for (int q = 0; q < nb; ++q) {
+      ++iter;
+      double res = std::max(DBL_MIN, std::sqrt(s->h_sc[SC_EDIR0 + q]));
+      if (iter == 1) res1 = res;
+      double rel = (res1 <= std::sqrt(DBL_MIN)) ? 0.0 : res / res1;
+      sol.res_dir = res;
+      sol.niter_dir = iter;
+      if (res < atol || rel < rtol) { converged = true; /* later passes of this batch only refine */ sol.niter_dir = iter + (nb - 1 - q); break; }
+    }
+  }
+  if (xold != sol.edir) {  // result of the last pass lives in edir_tmp: swap the buffers
+    s->edir_tmp = sol.edir;
+    sol.edir = xold;
+  }
+  sol.first_dir = false;
+  sol.lchanged = true;
+  sol.lWm2_dir = false;
+  if (!converged) return set_err(20, "solar_dir_ did not converge in %d passes (res %g)", iter, sol.res_dir);
+  return 0;
+}
+
+static int setup_b(pprts_b200_solver *s, Solution &sol) {
+  const Grid &g = s->g;
+  CU(cudaMemsetAsync(s->b, 0, (size_t)s->Nf * g.nlev * sizeof(double), s->stream));
+  if (sol.lsolar_rad) {
+    DISPATCH_LC(s, LAUNCH(s, FAM_SOURCE, (k_source_solar<L, CT>), nblk(g.ncell, 128), 128, g, s->xinc, s->yinc, s->n1d,
+                           (const CT *)s->d2f, s->a13, s->a23, s->albedo, sol.edir, s->b));
+  }
+  if (sol.lthermal_rad) {
+    DISPATCH_L(s, LAUNCH(s, FAM_SOURCE, (k_source_thermal<L>), nblk(g.ncell, 128), 128, g, s->n1d, (int)s->have_Bsrfc,
+                          s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, s->planck, s->Bsrfc, s->albedo, s->b));
+  }
+  return 0;
+}
+
+template <int NDOT>
+static void launch_matmult(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+  const Grid &g = s->g;
+  DISPATCH_LC(s, LAUNCH(s, FAM_MATMULT, (k_matmult<L, CT, NDOT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f,
+                         s->a11, s->a12, s->albedo, x, y, w, s->partials, s->counter, dots));
+}
+
+static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond == 1 && s->cfg.solver_id != 324; }
+
+template <class L, class CT>
+static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
+  if constexpr (L::Nft == 2) {
+    const Grid &g = s->g;
+    if (!s->prec_ready) {
+      LAUNCH(s, FAM_PRECOND, (k_prec_setup<L, CT>), nblk(g.ncol, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+             s->albedo, s->precR, s->precInv);
+      s->prec_ready = true;
+    }
+    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+           s->precR, s->precInv, r, z);
+    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+           s->precR, s->precInv, r, z);
+  }
+}
+static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, launch_prec_t<L, CT>(s, r, z)); }
+
+// Right-preconditioned BiCGStab on the matrix-free operator; convergence test of MyKSPConverged
+// (src/pprts.F90:4437-4486): ||r||/||r0|| <= rtol or ||r|| <= atol, nonzero initial guess (:4343).
+static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
+  const Grid &g = s->g;
+  const long n = (long)s->Nf * g.nlev;
+  int maxit = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 1000;
+  double rtol_d, atol_d;
+  determine_ksp_tolerances(s, rtol_d, atol_d);
+  double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol.first_diff) { rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
+  double *x = sol.ediff, *r = s->kr[0], *rh = s->kr[1], *p = s->kr[2], *v = s->kr[3], *sv = s->kr[4], *t = s->kr[5];
+  const bool prec = precond_available(s);
+  double *ph = prec ? s->kr[6] : p, *sh = prec ? s->kr[7] : sv;
+  launch_matmult<0>(s, x, r, nullptr, nullptr);
+  LAUNCH(s, FAM_VEC, k_bicg_init, vec_grid(n), VEC_BLOCK, n, s->b, r, rh, p, v, s->partials, s->counter, s->sc);
+  int rc = read_scalars(s);
+  if (rc) return rc;
+  const double r0 = std::max(DBL_MIN, std::sqrt(s->h_sc[SC_RR]));
+  sol.niter_diff = 0;
+  sol.res_diff = r0;
+  bool converged = false;
+  if (r0 <= atol) converged = true;  // x already solves the system to tolerance (warm start)
+  for (int it = 1; it <= maxit && !converged; ++it) {
+    LAUNCH(s, FAM_VEC, k_bicg_update_p, vec_grid(n), VEC_BLOCK, n, r, v, p, s->sc);
+    if (prec) launch_prec(s, p, ph);
+    launch_matmult<1>(s, ph, v, rh, s->sc + SC_RHV);
+    LAUNCH(s, FAM_VEC, k_bicg_update_s, vec_grid(n), VEC_BLOCK, n, r, v, sv, s->sc);
+    if (prec) launch_prec(s, sv, sh);
+    launch_matmult<2>(s, sh, t, sv, s->sc + SC_TS);
+    LAUNCH(s, FAM_VEC, k_bicg_update_xr, vec_grid(n), VEC_BLOCK, n, ph, sh, sv, t, rh, x, r, s->partials, s->counter, s->sc);
+    if ((rc = read_scalars(s))) return rc;
+    const double rn = std::sqrt(s->h_sc[SC_RR]);
+    sol.niter_diff = it;
+    sol.res_diff = rn;
+    if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", it);
+    if (rn / r0 <= rtol || rn <= atol) converged = true;
+  }
+  sol.first_diff = false;
+  sol.lchanged = true;
+  sol.lWm2_diff = false;
+  if (!converged) return set_err(22, "***** SOLVER did NOT converge :( -- %d iterations, residual %g", sol.niter_diff, sol.res_diff);
+  return 0;
+}
+
+static int calc_flx_div(pprts_b200_solver *s, Solution &sol) {
+  const Grid &g = s->g;
+  int rc = scale_flx(s, sol, false);
+  if (rc) return rc;
+  DISPATCH_L(s, LAUNCH(s, FAM_ABSO, (k_absorption<L>), nblk(g.ncell, 128), 128, g, s->xinc, s->yinc, s->n1d,
+                        (int)sol.lsolar_rad, (int)sol.lthermal_rad, s->cfg.by_coeff_divergence, s->costheta, s->cdiv_dir,
+                        s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, sol.edir, sol.ediff, s->b, sol.abso));
+  return 0;
+}
+
+static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool lthermal, Solution **out) {
+  const Grid &g = s->g;
+  const int key = s->cfg.keep_solutions ? uid : 0;
+  Solution &sol = s->solutions[key];
+  auto prepare = [&]() -> int {  // prepare_solution (src/pprts_base.F90:297-344)
+    if (!sol.edir) { DA(sol.edir, (size_t)s->Nd * g.nlev); DA(sol.ediff, (size_t)s->Nf * g.nlev); DA(sol.abso, g.ncell); }
+    else {
+      CU(cudaMemsetAsync(sol.edir, 0, (size_t)s->Nd * g.nlev * sizeof(double), s->stream));
+      CU(cudaMemsetAsync(sol.ediff, 0, (size_t)s->Nf * g.nlev * sizeof(double), s->stream));
+      CU(cudaMemsetAsync(sol.abso, 0, (size_t)g.ncell * sizeof(double), s->stream));
+    }
+    sol.lset = true; sol.lsolar_rad = lsolar; sol.lthermal_rad = lthermal; sol.lchanged = true;
+    sol.lWm2_dir = sol.lWm2_diff = true; sol.first_dir = sol.first_diff = true;
+    return 0;
+  };
+  if (!sol.lset || !s->cfg.keep_solutions) {
+    int rc = prepare();
+    if (rc) return rc;
+    if (s->cfg.keep_solutions) {  // -initial_guess_from_last_uid (src/pprts.F90:2542-2558)
+      auto it = s->solutions.find(uid - 1);
+      if (it != s->solutions.end() && it->second.lset) {
+        Solution &last = it->second;
+        if (last.lsolar_rad && lsolar) {
+          CU(cudaMemcpyAsync(sol.edir, last.edir, (size_t)s->Nd * g.nlev * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+          sol.lWm2_dir = last.lWm2_dir;
+        }
+        CU(cudaMemcpyAsync(sol.ediff, last.ediff, (size_t)s->Nf * g.nlev * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        sol.lWm2_diff = last.lWm2_diff;
+      }
+    }
+  } else if (sol.lsolar_rad != lsolar) {  // :2578-2582
+    int rc = prepare();
+    if (rc) return rc;
+  }
+  *out = &sol;
+  return 0;
+}
+
+extern "C" int pprts_b200_solve(pprts_b200_solver *s, int lthermal, int lsolar, double edirTOA, int uid) {
+  if (!s) return set_err(1, "null solver");
+  if (!s->have_optprop) return set_err(10, "atmosphere%%kabs is not allocated! - maybe you need to call set_optical_properties() first");
+  if (uid < -1000 || uid > 1000) return set_err(11, "solution uid %d out of range", uid);
+  if (lthermal && !s->have_planck)
+    return set_err(12, "you asked to compute thermal radiation but did not provide planck emissions in set_optical_properties");
+  CU(cudaSetDevice(s->device));
+  const bool derived_lsolar = lsolar && edirTOA > 0.0 && s->theta >= 0.0;
+  if (derived_lsolar && lthermal)
+    return set_err(13, "Somehow ended up with a request to compute solar and thermal radiation in one call.");
+  Solution *psol;
+  int rc = get_solution(s, uid, derived_lsolar, lthermal != 0, &psol);
+  if (rc) return rc;
+  Solution &sol = *psol;
+  const Grid &g = s->g;
+  s->res_valid = false;
+  if (!sol.lthermal_rad && !sol.lsolar_rad) {  // nothing to do (src/pprts.F90:2590-2596)
+    CU(cudaMemsetAsync(sol.edir, 0, (size_t)s->Nd * g.nlev * sizeof(double), s->stream));
+    CU(cudaMemsetAsync(sol.ediff, 0, (size_t)s->Nf * g.nlev * sizeof(double), s->stream));
+    CU(cudaMemsetAsync(sol.abso, 0, (size_t)g.ncell * sizeof(double), s->stream));
+    sol.lchanged = false;
+    return 0;
+  }
+  if ((rc = ensure_coeffs(s, sol.lsolar_rad))) return rc;
+  if ((rc = scale_flx(s, sol, false))) return rc;
+  if (sol.lsolar_rad && (rc = solve_edir(s, sol, edirTOA))) return rc;
+  if ((rc = setup_b(s, sol))) return rc;
+  // b_norm = sum(abs(b)); skip the diffuse solve if < atol (src/pprts.F90:2774-2785)
+  const long n = (long)s->Nf * g.nlev;
+  LAUNCH(s, FAM_VEC, k_norm1, vec_grid(n), VEC_BLOCK, n, s->b, s->partials, s->counter, s->sc + SC_BNORM1);
+  if ((rc = read_scalars(s))) return rc;
+  double rtol, atol;
+  determine_ksp_tolerances(s, rtol, atol);
+  if (s->h_sc[SC_BNORM1] < atol) {
+    CU(cudaMemcpyAsync(sol.ediff, s->b, n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    sol.niter_diff = 0;
+    sol.res_diff = atol;
+  } else {
+    if ((rc = solve_ediff(s, sol))) return rc;
+  }
+  sol.lchanged = true;
+  sol.lWm2_diff = false;
+  // restore_solution (src/pprts.F90:3991-4033)
+  if ((rc = calc_flx_div(s, sol))) return rc;
+  if ((rc = scale_flx(s, sol, true))) return rc;
+  sol.lchanged = false;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------------------------
+static int find_solution(pprts_b200_solver *s, int uid, Solution **out) {
+  auto it = s->solutions.find(s->cfg.keep_solutions ? uid : 0);
+  if (it == s->solutions.end() || !it->second.lset) return set_err(30, "no solution for uid %d", uid);
+  if (it->second.lchanged) return set_err(31, "tried to get results from unrestored solution -- call restore_solution first");
+  if (!it->second.lWm2_diff) return set_err(32, "tried to get result from a result vector(diff) which is not in [W/m2]");
+  *out = &it->second;
+  return 0;
+}
+
+static int compute_result(pprts_b200_solver *s, int uid, bool accumulate, double weight) {
+  Solution *sol;
+  int rc = find_solution(s, uid, &sol);
+  if (rc) return rc;
+  const Grid &g = s->g;
+  double **dst = accumulate ? s->acc : s->res;
+  DISPATCH_L(s, LAUNCH(s, FAM_ABSO, (k_result<L>), nblk(g.nlev, 256), 256, g, (int)sol->lsolar_rad, s->mu, sol->edir,
+                        sol->ediff, sol->abso, dst[0], dst[1], dst[2], dst[3], (int)accumulate, weight));
+  if (!accumulate) { s->res_valid = true; s->res_uid = uid; }
+  return 0;
+}
+
+static int download_fields(pprts_b200_solver *s, double **src, double *edn, double *eup, double *abso, double *edir) {
+  const Grid &g = s->g;
+  double *hosts[4] = {edn, eup, edir, abso};
+  for (int q = 0; q < 4; ++q) {
+    if (!hosts[q]) continue;
+    const int nz = q == 3 ? g.Nz : g.Nz + 1;
+    dim3 grid((g.Nx + 31) / 32, (nz + 31) / 32, g.Ny), block(32, 8);
+    LAUNCH(s, FAM_IO, k_kji_to_zxy<double>, grid, block, nz, g.Nx, g.Ny, src[q], s->out_stage, 1.0);
+    CU(cudaMemcpyAsync(hosts[q], s->out_stage, (size_t)nz * g.ncol * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int pprts_b200_compute_result_device(pprts_b200_solver *s, int uid) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  return compute_result(s, uid, false, 1.0);
+}
+extern "C" int pprts_b200_synchronize(pprts_b200_solver *s) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int pprts_b200_get_result(pprts_b200_solver *s, int uid, double *edn, double *eup, double *abso, double *edir) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  int rc = compute_result(s, uid, false, 1.0);
+  if (rc) return rc;
+  return download_fields(s, s->res, edn, eup, abso, edir);
+}
+extern "C" int pprts_b200_accumulate_result(pprts_b200_solver *s, int uid, double weight) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  return compute_result(s, uid, true, weight);
+}
+extern "C" int pprts_b200_reset_accumulator(pprts_b200_solver *s) {
+  if (!s) return set_err(1, "null solver");
+  for (int q = 0; q < 4; ++q) CU(cudaMemsetAsync(s->acc[q], 0, (size_t)s->g.nlev * sizeof(double), s->stream));
+  return 0;
+}
+extern "C" int pprts_b200_get_accumulated(pprts_b200_solver *s, double *edn, double *eup, double *abso, double *edir) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  return download_fields(s, s->acc, edn, eup, abso, edir);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL (dlopen'ed: single-GPU users do not need the library)
+// ---------------------------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_ncclGetUniqueId)(nccl_uid_t *);
+typedef int (*fn_ncclCommInitRank)(void **, int, nccl_uid_t, int);
+typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void *);
+typedef const char *(*fn_ncclGetErrorString)(int);
+static struct {
+  void *h = nullptr;
+  fn_ncclGetUniqueId GetUniqueId; fn_ncclCommInitRank CommInitRank; fn_ncclAllReduce AllReduce;
+  fn_ncclCommDestroy CommDestroy; fn_ncclGetErrorString GetErrorString;
+} g_nccl;
+static int load_nccl() {
+  if (g_nccl.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) { g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+  if (!g_nccl.h) return set_err(40, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (fn_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return set_err(40, "libnccl is missing symbols");
+  return 0;
+}
+extern "C" int pprts_b200_nccl_unique_id(char id[128]) {
+  int rc = load_nccl();
+  if (rc) return rc;
+  nccl_uid_t u;
+  if ((rc = g_nccl.GetUniqueId(&u))) return set_err(41, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+extern "C" int pprts_b200_comm_init(pprts_b200_solver *s, int nranks, int rank, const char id[128]) {
+  if (!s) return set_err(1, "null solver");
+  int rc = load_nccl();
+  if (rc) return rc;
+  CU(cudaSetDevice(s->device));
+  nccl_uid_t u;
+  memcpy(u.internal, id, 128);
+  if ((rc = g_nccl.CommInitRank(&s->nccl_comm, nranks, u, rank))) return set_err(42, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+  s->nranks = nranks; s->rank = rank;
+  return 0;
+}
+extern "C" int pprts_b200_allreduce_accumulated(pprts_b200_solver *s) {
+  if (!s) return set_err(1, "null solver");
+  if (!s->nccl_comm) return s->nranks == 1 ? 0 : set_err(43, "communicator not initialised");
+  CU(cudaSetDevice(s->device));
+  for (int q = 0; q < 4; ++q) {
+    int rc = g_nccl.AllReduce(s->acc[q], s->acc[q], (size_t)s->g.nlev, /*ncclFloat64*/ 8, /*ncclSum*/ 0, s->nccl_comm, s->stream);
+    if (rc) return set_err(44, "ncclAllReduce: %s", g_nccl.GetErrorString(rc));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pprts_b200_get_coeffs(pprts_b200_solver *s, int which, double *out) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const Grid &g = s->g;
+  const int nc = which == 1 ? s->Nd * s->Nd : which == 2 ? s->Nd * s->Nf : s->Nf * s->Nf;
+  const void *src = which == 1 ? s->d2d : which == 2 ? s->d2f : s->f2f;
+  double *tmp;
+  CU(cudaMalloc((void **)&tmp, (size_t)nc * g.ncell * sizeof(double)));
+  if (s->cfg.coeff_fp32) LAUNCH(s, FAM_IO, k_coeff_to_host_layout<float>, nblk((long)nc * g.ncell, 256), 256, g, nc, (const float *)src, tmp);
+  else LAUNCH(s, FAM_IO, k_coeff_to_host_layout<double>, nblk((long)nc * g.ncell, 256), 256, g, nc, (const double *)src, tmp);
+  CU(cudaMemcpyAsync(out, tmp, (size_t)nc * g.ncell * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaFree(tmp));
+  return 0;
+}
+extern "C" int pprts_b200_get_state(pprts_b200_solver *s, int uid, int which, double *out) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const Grid &g = s->g;
+  Solution *sol = nullptr;
+  if (which != 4) { int rc = find_solution(s, uid, &sol); if (rc) return rc; }
+  if (which == 3) {
+    dim3 grid((g.Nx + 31) / 32, (g.Nz + 31) / 32, g.Ny), block(32, 8);
+    LAUNCH(s, FAM_IO, k_kji_to_zxy<double>, grid, block, g.Nz, g.Nx, g.Ny, sol->abso, s->out_stage, 1.0);
+    CU(cudaMemcpyAsync(out, s->out_stage, (size_t)g.ncell * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  } else {
+    const int nd = which == 1 ? s->Nd : s->Nf;
+    const double *src = which == 1 ? sol->edir : which == 2 ? sol->ediff : s->b;
+    LAUNCH(s, FAM_IO, k_state_to_host_layout, nblk((long)nd * g.nlev, 256), 256, g, nd, src, s->out_stage);
+    CU(cudaMemcpyAsync(out, s->out_stage, (size_t)nd * g.nlev * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+extern "C" int pprts_b200_get_info(pprts_b200_solver *s, int uid, int *niter_dir, int *niter_diff, double *res_dir, double *res_diff) {
+  if (!s) return set_err(1, "null solver");
+  auto it = s->solutions.find(s->cfg.keep_solutions ? uid : 0);
+  if (it == s->solutions.end()) return set_err(30, "no solution for uid %d", uid);
+  *niter_dir = it->second.niter_dir; *niter_diff = it->second.niter_diff;
+  *res_dir = it->second.res_dir; *res_diff = it->second.res_diff;
+  return 0;
+}
+extern "C" int pprts_b200_mat_mult_ediff(pprts_b200_solver *s, const double *x, double *y) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const Grid &g = s->g;
+  int rc = ensure_coeffs(s, false);
+  if (rc) return rc;
+  const long n = (long)s->Nf * g.nlev;
+  CU(cudaMemcpyAsync(s->out_stage, x, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  LAUNCH(s, FAM_IO, k_state_from_host_layout, nblk(n, 256), 256, g, s->Nf, s->out_stage, s->kr[6]);
+  launch_matmult<0>(s, s->kr[6], s->kr[7], nullptr, nullptr);
+  LAUNCH(s, FAM_IO, k_state_to_host_layout, nblk(n, 256), 256, g, s->Nf, s->kr[7], s->out_stage);
+  CU(cudaMemcpyAsync(y, s->out_stage, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+static int lookup_probe(pprts_b200_solver *s, int mode, long n, const double *kabs, const double *ksca, const double *g,
+                        const double *dz, const float *lutspace, const SymMaps &sym, double *out) {
+  CU(cudaSetDevice(s->device));
+  if (mode != 3 && s->angles_dirty) { int rc = contract_direct_tables(s); if (rc) return rc; }
+  const int nc = mode == 1 ? s->Nd * s->Nd : mode == 2 ? s->Nd * s->Nf : s->Nf * s->Nf;
+  double *d_in[4] = {nullptr, nullptr, nullptr, nullptr}, *d_out;
+  float *d_ls = nullptr;
+  const double *h_in[4] = {kabs, ksca, g, dz};
+  if (lutspace) { CU(cudaMalloc((void **)&d_ls, n * 4 * sizeof(float))); CU(cudaMemcpy(d_ls, lutspace, n * 4 * sizeof(float), cudaMemcpyHostToDevice)); }
+  else for (int q = 0; q < 4; ++q) { CU(cudaMalloc((void **)&d_in[q], n * sizeof(double))); CU(cudaMemcpy(d_in[q], h_in[q], n * sizeof(double), cudaMemcpyHostToDevice)); }
+  CU(cudaMalloc((void **)&d_out, (size_t)n * nc * sizeof(double)));
+  DISPATCH_L(s, LAUNCH(s, FAM_LOOKUP, (k_lookup_probe<L>), nblk(n, 128), 128, s->lutdev, sym, mode, n, s->g.dx, d_in[0],
+                        d_in[1], d_in[2], d_in[3], d_ls, d_out));
+  CU(cudaMemcpyAsync(out, d_out, (size_t)n * nc * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (int q = 0; q < 4; ++q) cudaFree(d_in[q]);
+  cudaFree(d_ls); cudaFree(d_out);
+  return 0;
+}
+extern "C" int pprts_b200_lookup_coeffs(pprts_b200_solver *s, int mode, long n, const double *kabs, const double *ksca,
+                                        const double *g, const double *dz, double *out) {
+  if (!s) return set_err(1, "null solver");
+  if (mode < 1 || mode > 3) return set_err(1, "mode option %d not recognized", mode);
+  return lookup_probe(s, mode, n, kabs, ksca, g, dz, nullptr, s->sym, out);
+}
+// used by the pprts_f2c_opp_* compatibility layer (f2c.cu)
+int pprts_b200_internal_opp_probe(pprts_b200_solver *s, int mode, const float sample[4], int le, int ln, double *out) {
+  SymMaps sym;
+  build_sym_maps(s->cfg.solver_id, le != 0, ln != 0, sym);
+  return lookup_probe(s, mode, 1, nullptr, nullptr, nullptr, nullptr, sample, sym, out);
+}
+int pprts_b200_internal_force_angles(pprts_b200_solver *s, double symmetry_phi, double theta) {
+  s->symmetry_phi = symmetry_phi; s->theta = theta; s->angles_dirty = true; s->coeffs_dirty = true;
+  return 0;
+}
+
+extern "C" long pprts_b200_kernel_launches(pprts_b200_solver *s) { return s ? s->launches : 0; }
+extern "C" int pprts_b200_enable_kernel_timing(pprts_b200_solver *s, int on) {
+  if (!s) return set_err(1, "null solver");
+  collect_events(s);
+  s->timing = on != 0;
+  return 0;
+}
+extern "C" int pprts_b200_kernel_stats(pprts_b200_solver *s, int reset, double ms[8], long launches[8]) {
+  if (!s) return set_err(1, "null solver");
+  collect_events(s);
+  for (int q = 0; q < FAM_COUNT; ++q) { ms[q] = s->fam_ms[q]; launches[q] = s->fam_launch[q]; }
+  if (reset) for (int q = 0; q < FAM_COUNT; ++q) { s->fam_ms[q] = 0; s->fam_launch[q] = 0; }
+  return 0;
+}
+int pprts_b200_internal_lut_ranges(const pprts_b200_lut *lut, float ranges[6][2], int *Nd, int *Nf) {
+  for (int d = 0; d < 6; ++d) { ranges[d][0] = lut->ax[d].front(); ranges[d][1] = lut->ax[d].back(); }
+  *Nd = lut->Nd; *Nf = lut->Nf;
+  return 0;
+}

@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's Fortran module API for the pprts path (``m_pprts``, src/pprts.F90:192-200),
+bound to ``libpprts_b200.so`` through its C ABI (include/pprts_b200.h) with ctypes.
+
+Same names, argument meaning and error behaviour as the reference:
+
+    solver = init_pprts(comm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=..., lut=...)   # src/pprts.F90:213
+    set_optical_properties(solver, albedo, kabs, ksca, g, planck=None, ...)                 # src/pprts.F90:1764
+    solve_pprts(solver, lthermal, lsolar, edirTOA, opt_solution_uid=0)                      # src/pprts.F90:2487
+    edn, eup, abso, edir = pprts_get_result(solver, opt_solution_uid=0)                     # src/pprts.F90:5799
+    destroy_pprts(solver)                                                                   # src/pprts_base.F90:877
+
+Arrays are indexed ``[k, i, j]`` like the Fortran ``(Nz, Nx, Ny)`` arrays and are passed in Fortran (column-major)
+memory order, which is what a Fortran caller hands to the same C entry points.  Every failure of the reference is a
+fatal ``CHKERR``; here it is a ``PprtsError``.  There is no CPU path: without a CUDA device and the compiled
+extension every call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import lut as _lut
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpprts_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+c_long_p = C.POINTER(C.c_long)
+
+
+class PprtsError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("solver_id", C.c_int), ("Nz", C.c_int), ("Nx", C.c_int), ("Ny", C.c_int),
+                ("dx", C.c_double), ("dy", C.c_double), ("dz1d", c_double_p), ("dz3d", c_double_p),
+                ("sundir", C.c_double * 3), ("twostr_ratio", C.c_double), ("coeff_fp32", C.c_int),
+                ("by_coeff_divergence", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
+                ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
+                ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
+                ("yrank", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/pprts_b200.h declares (checked by tests/test_abi.py without touching a GPU)
+ABI_SYMBOLS = [
+    "pprts_f2c_init", "pprts_f2c_set_global_optical_properties", "pprts_f2c_solve", "pprts_f2c_get_result",
+    "pprts_f2c_destroy", "pprts_f2c_opp_init", "pprts_f2c_opp_get_coeff", "pprts_f2c_opp_destroy",
+    "pprts_f2c_opp_get_info",
+    "pprts_b200_lut_open", "pprts_b200_lut_close", "pprts_b200_default_config", "pprts_b200_create",
+    "pprts_b200_destroy", "pprts_b200_set_angles", "pprts_b200_set_optical_properties", "pprts_b200_solve",
+    "pprts_b200_get_result", "pprts_b200_stage_optical_properties", "pprts_b200_set_optical_properties_staged",
+    "pprts_b200_compute_result_device", "pprts_b200_synchronize", "pprts_b200_accumulate_result",
+    "pprts_b200_reset_accumulator", "pprts_b200_get_accumulated", "pprts_b200_nccl_unique_id",
+    "pprts_b200_comm_init", "pprts_b200_allreduce_accumulated", "pprts_b200_get_coeffs", "pprts_b200_get_state",
+    "pprts_b200_get_info", "pprts_b200_mat_mult_ediff", "pprts_b200_lookup_coeffs", "pprts_b200_kernel_launches",
+    "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error",
+]
+
+
+def lib():
+    """Load the compiled extension. Fails loudly if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PprtsError(f"{LIB_PATH} is missing: build it with `python -m tenstream_b200.build` "
+                         "(there is no CPU fallback for the pprts path)")
+    L = C.CDLL(LIB_PATH)
+    L.pprts_b200_last_error.restype = C.c_char_p
+    L.pprts_b200_lut_open.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, c_int_p, C.POINTER(c_float_p),
+                                      C.POINTER(C.c_void_p)]
+    L.pprts_b200_lut_close.argtypes = [C.c_void_p]
+    L.pprts_b200_default_config.argtypes = [C.POINTER(_Config)]
+    L.pprts_b200_create.argtypes = [C.POINTER(_Config), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pprts_b200_destroy.argtypes = [C.c_void_p]
+    L.pprts_b200_set_angles.argtypes = [C.c_void_p, c_double_p]
+    L.pprts_b200_set_optical_properties.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 6 + [C.c_int]
+    L.pprts_b200_stage_optical_properties.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6
+    L.pprts_b200_set_optical_properties_staged.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pprts_b200_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.pprts_b200_get_result.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.pprts_b200_compute_result_device.argtypes = [C.c_void_p, C.c_int]
+    L.pprts_b200_synchronize.argtypes = [C.c_void_p]
+    L.pprts_b200_accumulate_result.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.pprts_b200_reset_accumulator.argtypes = [C.c_void_p]
+    L.pprts_b200_get_accumulated.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    L.pprts_b200_nccl_unique_id.argtypes = [C.c_char_p]
+    L.pprts_b200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    L.pprts_b200_allreduce_accumulated.argtypes = [C.c_void_p]
+    L.pprts_b200_get_coeffs.argtypes = [C.c_void_p, C.c_int, c_double_p]
+    L.pprts_b200_get_state.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+    L.pprts_b200_get_info.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p]
+    L.pprts_b200_mat_mult_ediff.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    L.pprts_b200_lookup_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_long] + [c_double_p] * 5
+    L.pprts_b200_kernel_launches.restype = C.c_long
+    L.pprts_b200_kernel_launches.argtypes = [C.c_void_p]
+    L.pprts_b200_kernel_stats.argtypes = [C.c_void_p, C.c_int, c_double_p, c_long_p]
+    L.pprts_b200_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise PprtsError(f"{what} failed ({rc}): {lib().pprts_b200_last_error().decode()}")
+
+
+def _f(a, dtype=np.float64):
+    """Fortran-ordered contiguous view/copy: what a Fortran caller's (Nz,Nx,Ny) array looks like in memory."""
+    return None if a is None else np.asfortranarray(a, dtype=dtype)
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+class Lut:
+    """The optprop tables of one solver (``t_optprop_LUT``): memory-mapped ``.mmap4`` files + their axes."""
+
+    def __init__(self, cfg: _lut.LutConfig, paths: dict):
+        self.cfg = cfg
+        self.paths = dict(paths)
+        axes = [np.ascontiguousarray(a, dtype=np.float32) for a in cfg.dir_axes]
+        self._axes = axes
+        n = (C.c_int * 6)(*[len(a) for a in axes])
+        ptrs = (c_float_p * 6)(*[a.ctypes.data_as(c_float_p) for a in axes])
+        h = C.c_void_p()
+        _chk(lib().pprts_b200_lut_open(cfg.solver_id, paths["Tdir"].encode(), paths["Sdir"].encode(),
+                                       paths["Sdiff"].encode(), n, ptrs, C.byref(h)), "LUT load")
+        self._h = h
+
+    @classmethod
+    def from_basename(cls, cfg: _lut.LutConfig, lut_basename: str):
+        return cls(cfg, cfg.paths(lut_basename))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pprts_b200_lut_close(self._h)
+            self._h = None
+
+
+class Solver:
+    """``class(t_solver)`` of the reference (src/pprts_base.F90:223-268); state lives on the GPU."""
+
+    def __init__(self, handle, lut, Nz, Nx, Ny, Nd, Nf):
+        self._h = handle
+        self.lut = lut
+        self.Nz, self.Nx, self.Ny, self.Nd, self.Nf = Nz, Nx, Ny, Nd, Nf
+        self._pinned = []
+
+    # -- introspection used by the parity tests -----------------------------------------------------------------
+    def coeffs(self, which):
+        n = {1: self.Nd ** 2, 2: self.Nd * self.Nf, 3: self.Nf ** 2}[which]
+        out = np.zeros((n, self.Nz, self.Nx, self.Ny), order="F")
+        _chk(lib().pprts_b200_get_coeffs(self._h, which, _dp(out)), "get_coeffs")
+        return out
+
+    def state(self, which, uid=0):
+        if which == 3:
+            out = np.zeros((self.Nz, self.Nx, self.Ny), order="F")
+        else:
+            out = np.zeros((self.Nd if which == 1 else self.Nf, self.Nz + 1, self.Nx, self.Ny), order="F")
+        _chk(lib().pprts_b200_get_state(self._h, uid, which, _dp(out)), "get_state")
+        return out
+
+    def info(self, uid=0):
+        a, b = C.c_int(), C.c_int()
+        c, d = C.c_double(), C.c_double()
+        _chk(lib().pprts_b200_get_info(self._h, uid, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "get_info")
+        return dict(niter_dir=a.value, niter_diff=b.value, res_dir=c.value, res_diff=d.value)
+
+    def mat_mult_ediff(self, x):
+        xf = _f(x)
+        y = np.zeros_like(xf, order="F")
+        _chk(lib().pprts_b200_mat_mult_ediff(self._h, _dp(xf), _dp(y)), "mat_mult_ediff")
+        return y
+
+    def lookup_coeffs(self, mode, kabs, ksca, g, dz):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (kabs, ksca, g, dz)]
+        n = arrs[0].size
+        nc = {1: self.Nd ** 2, 2: self.Nd * self.Nf, 3: self.Nf ** 2}[mode]
+        out = np.zeros((n, nc))
+        _chk(lib().pprts_b200_lookup_coeffs(self._h, mode, n, *[_dp(a) for a in arrs], _dp(out)), "lookup_coeffs")
+        return out
+
+    def kernel_launches(self):
+        return int(lib().pprts_b200_kernel_launches(self._h))
+
+    def enable_kernel_timing(self, on=True):
+        _chk(lib().pprts_b200_enable_kernel_timing(self._h, int(on)), "enable_kernel_timing")
+
+    FAMILIES = ["lookup", "edir", "source", "matmult", "precond", "vector", "absorption_result", "ingest_egress"]
+
+    def kernel_stats(self, reset=False):
+        ms = (C.c_double * 8)()
+        ln = (C.c_long * 8)()
+        _chk(lib().pprts_b200_kernel_stats(self._h, int(reset), ms, ln), "kernel_stats")
+        return {f: dict(ms=ms[q], launches=ln[q]) for q, f in enumerate(self.FAMILIES)}
+
+    # -- device-resident variants (throughput with inputs already in HBM) ------------------------------------------
+    def stage_optical_properties(self, slot, albedo, kabs, ksca, g, planck=None, planck_srfc=None, albedo_2d=None):
+        arrs = [_f(a) for a in (kabs, ksca, g, planck, planck_srfc, albedo_2d)]
+        _chk(lib().pprts_b200_stage_optical_properties(self._h, slot, float(albedo), *[_vp(a) for a in arrs]),
+             "stage_optical_properties")
+
+    def set_optical_properties_staged(self, slot, ldelta_scaling=True):
+        _chk(lib().pprts_b200_set_optical_properties_staged(self._h, slot, int(ldelta_scaling)),
+             "set_optical_properties_staged")
+
+    def compute_result_device(self, uid=0):
+        _chk(lib().pprts_b200_compute_result_device(self._h, uid), "compute_result_device")
+
+    def synchronize(self):
+        _chk(lib().pprts_b200_synchronize(self._h), "synchronize")
+
+    # -- spectral accumulation / band sharding -------------------------------------------------------------------
+    def accumulate_result(self, uid=0, weight=1.0):
+        _chk(lib().pprts_b200_accumulate_result(self._h, uid, float(weight)), "accumulate_result")
+
+    def reset_accumulator(self):
+        _chk(lib().pprts_b200_reset_accumulator(self._h), "reset_accumulator")
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        _chk(lib().pprts_b200_comm_init(self._h, nranks, rank, unique_id), "comm_init")
+
+    def allreduce_accumulated(self):
+        _chk(lib().pprts_b200_allreduce_accumulated(self._h), "allreduce_accumulated")
+
+    def get_accumulated(self):
+        out = _alloc_results(self)
+        _chk(lib().pprts_b200_get_accumulated(self._h, *[_vp(a) for a in out]), "get_accumulated")
+        edn, eup, abso, edir = out
+        return edn, eup, abso, edir
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _chk(lib().pprts_b200_nccl_unique_id(buf), "nccl_unique_id")
+    return buf.raw
+
+
+def _alloc_results(s):
+    return (np.zeros((s.Nz + 1, s.Nx, s.Ny), order="F"), np.zeros((s.Nz + 1, s.Nx, s.Ny), order="F"),
+            np.zeros((s.Nz, s.Nx, s.Ny), order="F"), np.zeros((s.Nz + 1, s.Nx, s.Ny), order="F"))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the module API
+# ---------------------------------------------------------------------------------------------------------------
+def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=None, nxproc=None, nyproc=None,
+               collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
+               by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
+               keep_solutions=True) -> Solver:
+    """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
+    the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
+    arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...)."""
+    if collapseindex is not None and collapseindex > 1:
+        raise PprtsError("collapseindex > 1 (atmosphere collapse, src/pprts.F90:2080-2198) is not supported")
+    if (dz1d is None) == (dz3d is None):
+        raise PprtsError("have to give either dz1d or dz3d in routine call....")
+    cfg = _Config()
+    lib().pprts_b200_default_config(C.byref(cfg))
+    cfg.solver_id, cfg.Nz, cfg.Nx, cfg.Ny = int(solver), int(Nz), int(Nx), int(Ny)
+    cfg.dx, cfg.dy = float(dx), float(dy)
+    keep = []
+    if dz1d is not None:
+        a = np.ascontiguousarray(dz1d, dtype=np.float64)
+        if a.shape != (Nz,):
+            raise PprtsError(f"dz1d has shape {a.shape}, expected ({Nz},)")
+        cfg.dz1d = _dp(a)
+        keep.append(a)
+    else:
+        a = _f(dz3d)
+        if a.shape != (Nz, Nx, Ny):
+            raise PprtsError(f"Shape mismatch: 3D dz {a.shape} vs grid {(Nz, Nx, Ny)}")
+        cfg.dz3d = _dp(a)
+        keep.append(a)
+    cfg.sundir = (C.c_double * 3)(*[float(v) for v in sundir])
+    cfg.twostr_ratio = float(twostr_ratio)
+    cfg.coeff_fp32 = int(coeff_fp32)
+    cfg.by_coeff_divergence = int(by_coeff_divergence)
+    cfg.rtol, cfg.atol = float(rtol), float(atol)
+    cfg.maxit_dir, cfg.maxit_diff = int(maxit_dir), int(maxit_diff)
+    cfg.precond, cfg.device, cfg.keep_solutions = int(precond), int(device), int(keep_solutions)
+    cfg.nxproc = len(nxproc) if nxproc is not None else 1
+    cfg.nyproc = len(nyproc) if nyproc is not None else 1
+    h = C.c_void_p()
+    _chk(lib().pprts_b200_create(C.byref(cfg), lut._h, C.byref(h)), "init_pprts")
+    Nd, Nf = _lut.solver_dofs(int(solver))
+    return Solver(h, lut, Nz, Nx, Ny, Nd, Nf)
+
+
+def set_angles(solver: Solver, sundir):
+    """``set_angles`` (src/pprts.F90:1100-1112)"""
+    s = np.ascontiguousarray(sundir, dtype=np.float64)
+    _chk(lib().pprts_b200_set_angles(solver._h, _dp(s)), "set_angles")
+
+
+def set_optical_properties(solver: Solver, albedo, kabs=None, ksca=None, g=None, planck=None, planck_srfc=None,
+                           albedo_2d=None, ldelta_scaling=True):
+    """``set_optical_properties`` (src/pprts.F90:1764-2076): local arrays (Nz,Nx,Ny), planck (Nz+1,Nx,Ny)."""
+    s = solver
+    for name, a, shp in (("kabs", kabs, (s.Nz, s.Nx, s.Ny)), ("ksca", ksca, (s.Nz, s.Nx, s.Ny)),
+                         ("g", g, (s.Nz, s.Nx, s.Ny)), ("planck", planck, (s.Nz + 1, s.Nx, s.Ny)),
+                         ("planck_srfc", planck_srfc, (s.Nx, s.Ny)), ("albedo_2d", albedo_2d, (s.Nx, s.Ny))):
+        if a is not None and tuple(np.shape(a)) != shp:
+            raise PprtsError(f"set_optical_properties: {name} has shape {np.shape(a)}, expected {shp}")
+    arrs = [_f(a) for a in (kabs, ksca, g, planck, planck_srfc, albedo_2d)]
+    _chk(lib().pprts_b200_set_optical_properties(s._h, float(albedo), *[_vp(a) for a in arrs], int(ldelta_scaling)),
+         "set_optical_properties")
+
+
+def solve_pprts(solver: Solver, lthermal, lsolar, edirTOA, opt_solution_uid=0, opt_solution_time=None):
+    """``solve_pprts`` (src/pprts.F90:2487-2665)"""
+    _chk(lib().pprts_b200_solve(solver._h, int(bool(lthermal)), int(bool(lsolar)), float(edirTOA),
+                                int(opt_solution_uid)), "solve_pprts")
+
+
+def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None):
+    """``pprts_get_result`` (src/pprts.F90:5799-5917) -> (edn, eup, abso, edir) in W/m2 resp. W/m3,
+    shapes (Nz+1,Nx,Ny) / (Nz,Nx,Ny).  ``out`` may carry preallocated Fortran-ordered arrays."""
+    edn, eup, abso, edir = out if out is not None else _alloc_results(solver)
+    _chk(lib().pprts_b200_get_result(solver._h, int(opt_solution_uid), _vp(edn), _vp(eup), _vp(abso), _vp(edir)),
+         "pprts_get_result")
+    return edn, eup, abso, edir
+
+
+def destroy_pprts(solver: Solver, lfinalizepetsc=False):
+    """``destroy_pprts`` (src/pprts_base.F90:877)"""
+    if solver._h:
+        lib().pprts_b200_destroy(solver._h)
+        solver._h = None
+
+
+def sundir_from_angles(phi0, theta0):
+    """``spherical_2_cartesian`` (src/helper_functions.fypp:2022-2033), as ``pprts_f2c_init`` does."""
+    p, t = np.deg2rad(phi0), np.deg2rad(theta0)
+    return np.array([-np.sin(t) * np.sin(p), -np.sin(t) * np.cos(p), -np.cos(t)])

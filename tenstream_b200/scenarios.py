@@ -1,0 +1,79 @@
+"""Deterministic synthetic inputs for the configurations BASELINE.json names.
+All fields are indexed [k, i, j] = (Nz, Nx, Ny), k = 0 at the top of the atmosphere."""
+from __future__ import annotations
+
+import numpy as np
+
+SIGMA_SB = 5.670374419e-8
+
+
+def box_cloud(Nx=32, Ny=32, Nz=40, dx=200.0, dz=100.0):
+    """C1: the box-cloud example (examples/pprts/pprts_box_cld.F90:22-74), resized: one optically thick cloud layer
+    at Nz/2 over +-5 columns around the centre, phi0 = 0, theta0 = 70, S0 = 1364 W/m2, albedo 0.1, solar only."""
+    kabs = np.full((Nz, Nx, Ny), 0.001 / (dz * Nz))
+    ksca = np.full((Nz, Nx, Ny), 0.005 / (dz * Nz))
+    g = np.zeros((Nz, Nx, Ny))
+    k = Nz // 2
+    ci, cj = Nx // 2, Ny // 2
+    sl = (k, slice(max(ci - 5, 0), ci + 6), slice(max(cj - 5, 0), cj + 6))
+    kabs[sl] = 1.001 / (dz * Nz)
+    ksca[sl] = 10.0 / dz
+    g[sl] = 0.9
+    return dict(Nx=Nx, Ny=Ny, Nz=Nz, dx=dx, dy=dx, dz1d=np.full(Nz, dz), phi0=0.0, theta0=70.0, albedo=0.1,
+                edirTOA=1364.0, kabs=kabs, ksca=ksca, g=g)
+
+
+def _periodic_gaussian_filter(field, sigma):
+    fx = np.fft.fftfreq(field.shape[0])[:, None]
+    fy = np.fft.fftfreq(field.shape[1])[None, :]
+    kern = np.exp(-2.0 * (np.pi * sigma) ** 2 * (fx ** 2 + fy ** 2))
+    return np.real(np.fft.ifft2(np.fft.fft2(field) * kern))
+
+
+def cloud_field(Nx=256, Ny=256, Nz=80, dx=100.0, dz=50.0, phi0=120.0, theta0=40.0, albedo=0.15, seed=20240229,
+                cover=0.30, sigma_px=6.0):
+    """C2: seeded filtered-noise cloud field with 30 % cover, cloud base at 65 % of the column from the top,
+    thickness 5-20 % of the column; in-cloud ksca U(10,40)/km, g = 0.85; clear air ksca = 1.2e-5 exp(-z/8km)."""
+    rng = np.random.default_rng(seed)
+    noise = _periodic_gaussian_filter(rng.standard_normal((Nx, Ny)), sigma_px * min(1.0, Nx / 64.0))
+    thresh = np.quantile(noise, 1.0 - cover)
+    cloudy = noise > thresh
+    strength = np.clip((noise - thresh) / (noise.max() - thresh + 1e-30), 0.0, 1.0)
+    kbase = int(round(0.65 * Nz))
+    tmin, tmax = max(1, int(round(0.05 * Nz))), max(2, int(round(0.20 * Nz)))
+    thick = (tmin + np.round(strength * (tmax - tmin))).astype(int)
+    zmid = (Nz - 0.5 - np.arange(Nz)) * dz                       # height of layer centres above ground [m]
+    ksca = np.empty((Nz, Nx, Ny))
+    ksca[:] = (1.2e-5 * np.exp(-zmid / 8000.0))[:, None, None]
+    kabs = 0.25 * ksca
+    g = np.zeros((Nz, Nx, Ny))
+    kcld = rng.uniform(10.0, 40.0, size=(Nx, Ny)) / 1000.0
+    kk = np.arange(Nz)[:, None, None]
+    incloud = cloudy[None] & (kk < kbase) & (kk >= kbase - thick[None])
+    ksca = np.where(incloud, kcld[None], ksca)
+    kabs = np.where(incloud, kcld[None] * 1e-3, kabs)
+    g = np.where(incloud, 0.85, g)
+    # thermal band: T(z) = 288 K - 6.5 K/km, planck = sigma T^4 / pi on levels, kabs_th = 10 kabs, no scattering
+    zlev = (Nz - np.arange(Nz + 1)) * dz
+    T = 288.0 - 6.5e-3 * zlev
+    planck = np.broadcast_to((SIGMA_SB * T ** 4 / np.pi)[:, None, None], (Nz + 1, Nx, Ny)).copy()
+    planck_srfc = np.full((Nx, Ny), SIGMA_SB * 288.0 ** 4 / np.pi)
+    return dict(Nx=Nx, Ny=Ny, Nz=Nz, dx=dx, dy=dx, dz1d=np.full(Nz, dz), phi0=phi0, theta0=theta0, albedo=albedo,
+                edirTOA=1364.0, kabs=kabs, ksca=ksca, g=g,
+                kabs_th=10.0 * kabs, ksca_th=np.zeros_like(ksca), g_th=np.zeros_like(g), planck=planck,
+                planck_srfc=planck_srfc, albedo_th=0.02)
+
+
+def spectral_bands(base, n_sw=112, n_lw=140):
+    """C3: pseudo g-points on top of a cloud_field: kabs scaled by 10^(-3+4u), u = (b-1/2)/N; solar weights
+    ~ exp(-3u) normalised (RRTMG counts: rrtmg/rrtm_sw/parrrsw.f90:36, rrtmg/rrtm_lw/parrrtm.f90:39)."""
+    bands = []
+    u = (np.arange(n_sw) + 0.5) / n_sw
+    w = np.exp(-3 * u)
+    w /= w.sum()
+    for b in range(n_sw):
+        bands.append(dict(kind="solar", uid=b + 1, scale=10.0 ** (-3 + 4 * u[b]), edirTOA=base["edirTOA"] * w[b]))
+    u = (np.arange(n_lw) + 0.5) / n_lw
+    for b in range(n_lw):
+        bands.append(dict(kind="thermal", uid=500 + b + 1, scale=10.0 ** (-3 + 4 * u[b]), weight=1.0 / n_lw))
+    return bands

@@ -1,0 +1,293 @@
+"""Parity of the CUDA path (through the C ABI, via tenstream_b200.pprts) against the CPU oracle on identical inputs
+and identical synthetic tables.  Tolerances: interpolated coefficients 1e-12 relative (fp64, north_star), fluxes and
+absorption 1e-5 relative with both sides converged well below that (rtol 1e-10)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from tenstream_b200 import pprts
+    pprts.lib()  # must load the in-tree extension; raises if it is missing (no fallback)
+    return pprts
+
+
+@pytest.fixture(scope="module")
+def gpu_lut(P, small_lut):
+    cfg, paths = small_lut
+    lut = P.Lut(cfg, paths)
+    yield lut
+    lut.close()
+
+
+def relerr(a, b, floor_frac=1e-6):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.abs(b).max()
+    if scale == 0:
+        return np.abs(a).max()
+    m = np.abs(b) > floor_frac * scale
+    return float((np.abs(a - b)[m] / np.abs(b)[m]).max()) if m.any() else 0.0
+
+
+def random_atm(rng, Nz, Nx, Ny, cloudy=True):
+    kabs = 10 ** rng.uniform(-7, -4, (Nz, Nx, Ny))
+    ksca = 10 ** rng.uniform(-6, -3.5, (Nz, Nx, Ny))
+    g = rng.uniform(0, 0.9, (Nz, Nx, Ny))
+    if cloudy:
+        k0 = Nz // 2
+        ksca[k0:k0 + 2, 1:Nx - 1, 1:Ny - 1] = rng.uniform(0.01, 0.05, (2, Nx - 2, Ny - 2))
+        g[k0:k0 + 2] = 0.85
+    return kabs, ksca, g
+
+
+# ---- HOT LOOP A ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("phi0,theta0", [(0., 0.), (30., 40.), (120., 40.), (200., 65.), (300., 20.), (45., 89.)])
+def test_lookup_probe_vs_oracle(P, gpu_lut, oracle_lut, phi0, theta0):
+    from oracle import binding as ob
+    rng = np.random.default_rng(7)
+    n = 400
+    kabs = 10 ** rng.uniform(-9, -1, n)
+    ksca = 10 ** rng.uniform(-9, -1, n)
+    g = rng.uniform(0, 1.0, n)
+    dz = 10 ** rng.uniform(0.3, 3.3, n)
+    kabs[:5] = 0.0; ksca[:3] = 0.0            # tau clamps to the lower table edge
+    dx = 100.0
+    sd = P.sundir_from_angles(phi0, theta0)
+    s = P.init_pprts(0, 2, 3, 3, dx, dx, sd, dz1d=np.full(2, 50.), lut=gpu_lut)
+    osv = ob.OracleSolver(oracle_lut, 2, 3, 3, dx, dx, sd, np.full(2, 50.))
+    sun = osv.suninfo()
+    for mode in (1, 2, 3):
+        got = s.lookup_coeffs(mode, kabs, ksca, g, dz)
+        want = np.array([oracle_lut.get_coeff(kabs[q], ksca[q], g[q], dz[q], dx, mode, sun["symmetry_phi"],
+                                              sun["theta"], sun["xinc"] == 0, sun["yinc"] == 0) for q in range(n)])
+        scale = np.abs(want).max()
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * scale)
+        assert err.max() < 1e-12, (mode, err.max())
+        if mode == 3:
+            assert np.array_equal(got, want)   # same corner order, same fma chain: bit-identical
+    P.destroy_pprts(s); osv.destroy()
+
+
+@pytest.mark.parametrize("coeff_fp32", [False, True])
+def test_stored_coeffs_vs_oracle(P, gpu_lut, oracle_lut, coeff_fp32):
+    from oracle import binding as ob
+    rng = np.random.default_rng(11)
+    Nz, Nx, Ny = 6, 5, 4
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    sd = P.sundir_from_angles(250., 35.)
+    dz = np.linspace(40, 120, Nz)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, coeff_fp32=coeff_fp32, rtol=1e-10, atol=1e-30)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, coeff_fp32=coeff_fp32, rtol=1e-10, atol=1e-30)
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    o.set_optical_properties(0.2, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000.0)
+    assert o.solve(False, True, 1000.0) == 0
+    for which in (1, 2, 3):
+        got, want = s.coeffs(which), o.coeffs(which)
+        if coeff_fp32:
+            assert np.abs(got - want).max() <= 2e-7 * np.abs(want).max()
+            assert np.array_equal(got, got.astype(np.float32))
+        else:
+            assert relerr(got, want, 1e-3) < 1e-12
+    P.destroy_pprts(s); o.destroy()
+
+
+# ---- HOT LOOP D: operator ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("twostr_ratio", [2.0, 0.9])
+def test_mat_mult_vs_oracle(P, gpu_lut, oracle_lut, twostr_ratio):
+    from oracle import binding as ob
+    rng = np.random.default_rng(5)
+    Nz, Nx, Ny = 7, 6, 5
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    dz = np.array([150., 120., 100., 80., 60., 50., 40.])     # with ratio 0.9 the top three layers are 1-D
+    sd = P.sundir_from_angles(10., 30.)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, coeff_fp32=False, twostr_ratio=twostr_ratio)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, twostr_ratio=twostr_ratio, maxit_diff=1)
+    alb2d = rng.uniform(0.05, 0.5, (Nx, Ny))
+    P.set_optical_properties(s, 0.2, kabs, ksca, g, albedo_2d=alb2d)
+    o.set_optical_properties(0.2, kabs, ksca, g, albedo_2d=alb2d)
+    o.solve(False, True, 1000.0)    # populates the oracle's coefficients
+    x = rng.standard_normal((10, Nz + 1, Nx, Ny))
+    got, want = s.mat_mult_ediff(x), o.mat_mult_ediff(x)
+    assert np.abs(got - want).max() < 1e-13 * max(1.0, np.abs(want).max())
+    P.destroy_pprts(s); o.destroy()
+
+
+# ---- full path ---------------------------------------------------------------------------------------------------
+def run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, dx, dz, phi0, theta0, albedo, kabs, ksca, g, solar=True, edirTOA=1000.,
+             planck=None, planck_srfc=None, albedo_2d=None, dz3d=None, precond=1, tol=1e-10, **kw):
+    from oracle import binding as ob
+    sd = P.sundir_from_angles(phi0, theta0)
+    s = P.init_pprts(0, Nz, Nx, Ny, dx, dx, sd, dz1d=None if dz3d is not None else dz, dz3d=dz3d, lut=gpu_lut,
+                     coeff_fp32=kw.get("coeff_fp32", False), rtol=tol, atol=1e-30, precond=precond,
+                     twostr_ratio=kw.get("twostr_ratio", 2.0), by_coeff_divergence=kw.get("by_coeff_divergence", True))
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, dx, dx, sd, dz3d if dz3d is not None else dz,
+                        coeff_fp32=kw.get("coeff_fp32", False), rtol=tol, atol=1e-30, diff_solver=1,
+                        twostr_ratio=kw.get("twostr_ratio", 2.0), by_coeff_divergence=kw.get("by_coeff_divergence", True),
+                        maxit_diff=5000)
+    P.set_optical_properties(s, albedo, kabs, ksca, g, planck=planck, planck_srfc=planck_srfc, albedo_2d=albedo_2d)
+    o.set_optical_properties(albedo, kabs, ksca, g, planck=planck, planck_srfc=planck_srfc, albedo_2d=albedo_2d)
+    P.solve_pprts(s, not solar, solar, edirTOA if solar else 0.0)
+    assert o.solve(not solar, solar, edirTOA if solar else 0.0) == 0
+    res_g = P.pprts_get_result(s)
+    res_o = o.get_result()
+    out = dict(gpu=res_g, oracle=res_o, info=s.info(), oinfo=o.info(), b=(s.state(4), o.state(4)),
+               edir=(s.state(1), o.state(1)) if solar else None, ediff=(s.state(2), o.state(2)))
+    P.destroy_pprts(s); o.destroy()
+    return out
+
+
+def check_fluxes(out, tol=1e-5):
+    names = ["edn", "eup", "abso", "edir"]
+    for name, a, b in zip(names, out["gpu"], out["oracle"]):
+        assert relerr(a, b) < tol, (name, relerr(a, b), out["info"], out["oinfo"])
+
+
+@pytest.mark.parametrize("phi0,theta0", [(0., 70.), (30., 40.), (120., 40.), (200., 60.), (315., 25.), (90., 0.)])
+@pytest.mark.parametrize("precond", [0, 1])
+def test_solar_vs_oracle(P, gpu_lut, oracle_lut, phi0, theta0, precond):
+    rng = np.random.default_rng(3)
+    Nz, Nx, Ny = 8, 7, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., np.full(Nz, 60.), phi0, theta0, 0.3, kabs, ksca, g,
+                   precond=precond)
+    assert relerr(*out["edir"], 1e-9) < 1e-9            # the direct beam has a unique fixed point
+    assert relerr(*out["b"], 1e-9) < 1e-9
+    check_fluxes(out, 1e-7)
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_thermal_vs_oracle(P, gpu_lut, oracle_lut, precond):
+    rng = np.random.default_rng(4)
+    Nz, Nx, Ny = 8, 5, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    kabs *= 30
+    T = np.linspace(220, 290, Nz + 1)[:, None, None] + rng.uniform(-3, 3, (Nz + 1, Nx, Ny))
+    planck = 5.67e-8 * T ** 4 / np.pi
+    for srfc in (None, 5.67e-8 * 295. ** 4 / np.pi * np.ones((Nx, Ny))):
+        out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., np.full(Nz, 60.), 0., 0., 0.05, kabs, ksca, g,
+                       solar=False, planck=planck, planck_srfc=srfc, precond=precond)
+        assert relerr(*out["b"], 1e-9) < 1e-10
+        check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-7)
+        assert np.all(out["gpu"][3] == 0)
+
+
+def test_1d_layers_and_topography(P, gpu_lut, oracle_lut):
+    """thick upper layers -> 1-D Eddington block (src/pprts.F90:649-725, :1962-2007) + per-column dz3d (config C5 shape)"""
+    rng = np.random.default_rng(8)
+    Nz, Nx, Ny = 9, 6, 7
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    dz1 = np.array([400., 300., 250., 120., 100., 80., 60., 50., 40.])
+    hill = 1.0 - 0.3 / (1.0 + ((np.arange(Ny) - Ny / 2) / 2.0) ** 2)          # Lorentzian hill in y
+    dz3d = dz1[:, None, None] * np.ones((Nz, Nx, Ny)) * hill[None, None, :]
+    out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., None, 180., 40., 0.2, kabs, ksca, g, dz3d=dz3d)
+    assert relerr(*out["edir"], 1e-9) < 1e-9
+    check_fluxes(out, 1e-7)
+    T = np.linspace(220, 290, Nz + 1)[:, None, None] * np.ones((Nz + 1, Nx, Ny))
+    out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., None, 180., 40., 0.2, kabs * 20, ksca, g, dz3d=dz3d,
+                   solar=False, planck=5.67e-8 * T ** 4 / np.pi)
+    check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-7)
+
+
+def test_fp32_coefficient_storage(P, gpu_lut, oracle_lut):
+    rng = np.random.default_rng(9)
+    Nz, Nx, Ny = 8, 6, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., np.full(Nz, 60.), 120., 40., 0.3, kabs, ksca, g,
+                   coeff_fp32=True)
+    check_fluxes(out, 1e-7)            # both sides round the stored coefficients through fp32 identically
+
+
+def test_absorption_by_flux_divergence(P, gpu_lut, oracle_lut):
+    """tests/test_pprts_absorption_by_coeff_divergence: both absorption methods agree (1 % of max) and match the oracle"""
+    Nz, Nx, Ny = 4, 3, 3
+    dtau_clear, dtau_cloud, w0_cloud, g_cloud = 1.0, 1.0, 0.2, 0.2
+    kabs = np.full((Nz, Nx, Ny), dtau_clear / 1.0)
+    ksca = np.zeros((Nz, Nx, Ny)); g = np.zeros((Nz, Nx, Ny))
+    kabs[1:3] = dtau_cloud * (1 - w0_cloud); ksca[1:3] = dtau_cloud * w0_cloud; g[1:3] = g_cloud
+    res = {}
+    for by_coeff in (True, False):
+        out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 1., np.full(Nz, 1.), 180., 0., 0.1, kabs, ksca, g, edirTOA=1.,
+                       by_coeff_divergence=by_coeff)
+        check_fluxes(out, 1e-7)
+        res[by_coeff] = out["gpu"][2]
+    assert np.abs(res[True] - res[False]).max() < 1e-2 * res[False].max()
+    B = 100 / np.pi
+    planck = np.full((Nz + 1, Nx, Ny), B)
+    for by_coeff in (True, False):
+        out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 1., np.full(Nz, 1.), 180., 0., 0.1, kabs, ksca, g, solar=False,
+                       planck=planck, planck_srfc=np.full((Nx, Ny), 100.), by_coeff_divergence=by_coeff)
+        check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-7)
+        res[by_coeff] = out["gpu"][2]
+    assert np.abs(res[True] - res[False]).max() < 1e-2 * np.abs(res[False]).max()
+
+
+def test_warm_start_and_uid_cache(P, gpu_lut):
+    """solutions(uid) caching (src/pprts.F90:2532-2558): a second solve of the same uid starts from its own result"""
+    rng = np.random.default_rng(12)
+    Nz, Nx, Ny = 8, 6, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(40., 30.), dz1d=np.full(Nz, 60.), lut=gpu_lut,
+                     rtol=1e-9, atol=1e-30)
+    P.set_optical_properties(s, 0.3, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000., opt_solution_uid=5)
+    first = s.info(5)
+    r1 = P.pprts_get_result(s, 5)
+    P.solve_pprts(s, False, True, 1000., opt_solution_uid=5)
+    second = s.info(5)
+    r2 = P.pprts_get_result(s, 5)
+    assert second["niter_diff"] <= 2 < first["niter_diff"]
+    for a, b in zip(r1, r2):
+        assert relerr(a, b) < 1e-7
+    P.solve_pprts(s, False, True, 1000., opt_solution_uid=6)       # new uid: warm start from uid-1
+    assert s.info(6)["niter_diff"] <= 2
+    with pytest.raises(P.PprtsError):
+        P.pprts_get_result(s, 77)
+    P.destroy_pprts(s)
+
+
+def test_error_behaviour(P, gpu_lut):
+    s = P.init_pprts(0, 4, 3, 3, 100., 100., P.sundir_from_angles(0., 20.), dz1d=np.full(4, 50.), lut=gpu_lut)
+    with pytest.raises(P.PprtsError, match="set_optical_properties"):
+        P.solve_pprts(s, False, True, 1000.)
+    k = np.full((4, 3, 3), 1e-4)
+    with pytest.raises(P.PprtsError, match="illegal value"):
+        P.set_optical_properties(s, 0.1, -k, k, k * 0)
+    P.set_optical_properties(s, 0.1, k, k, k * 0)
+    with pytest.raises(P.PprtsError, match="planck"):
+        P.solve_pprts(s, True, False, 0.)
+    with pytest.raises(P.PprtsError, match="dx and dy"):
+        P.init_pprts(0, 4, 3, 3, 100., 120., P.sundir_from_angles(0., 20.), dz1d=np.full(4, 50.), lut=gpu_lut)
+    P.destroy_pprts(s)
+
+
+# ---- properties at sizes the oracle does not need to reach -----------------------------------------------------------
+def test_energy_closure_and_mirror_symmetry(P, gpu_lut):
+    """Energy closure (sum absorbed + outgoing = incoming) and tests/test_pprts_symmetry :393-521: the fields for
+    phi and phi+180 are mirror images of each other."""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field(Nx=48, Ny=40, Nz=24, dx=100., dz=60., seed=5)
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    res = {}
+    for phi0 in (10., 190., 100., 280.):
+        s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dx"], P.sundir_from_angles(phi0, 60.), dz1d=sc["dz1d"], lut=gpu_lut,
+                         rtol=1e-10, atol=1e-30, coeff_fp32=False)
+        kabs, ksca, g = sc["kabs"], sc["ksca"], sc["g"]
+        if phi0 in (190., 280.):          # mirrored domain
+            kabs, ksca, g = [a[:, ::-1, ::-1] for a in (kabs, ksca, g)]
+        P.set_optical_properties(s, 0.15, kabs, ksca, g)
+        P.solve_pprts(s, False, True, 1364.)
+        edn, eup, abso, edir = P.pprts_get_result(s)
+        inc = edir[0].sum() + edn[0].sum()
+        out = eup[0].sum() + (edir[-1].sum() + edn[-1].sum() - eup[-1].sum()) + (abso * sc["dz1d"][:, None, None]).sum()
+        assert abs(out / inc - 1) < 1e-9, (phi0, out / inc)
+        res[phi0] = (edn, eup, abso, edir)
+        P.destroy_pprts(s)
+    for a, b in ((10., 190.), (100., 280.)):
+        for fa, fb in zip(res[a], res[b]):
+            assert relerr(fa, fb[:, ::-1, ::-1]) < 1e-8

@@ -146,6 +146,8 @@ int pprts_b200_lookup_coeffs(pprts_b200_solver *solver, int mode, long n, const 
                              const double *g, const double *dz, double *out);
 /* counters: kernels launched by this library since creation, and the ids of the last timed kernels */
 long pprts_b200_kernel_launches(pprts_b200_solver *solver);
+/* the cudaStream_t every kernel of this solver is launched on (to record timing events on the launching stream) */
+void *pprts_b200_stream(pprts_b200_solver *solver);
 /* device time [ms] and launch count accumulated per kernel family since the last reset:
  * 0 lookup, 1 edir sweep, 2 source, 3 matmult, 4 precond, 5 vector ops, 6 absorption+result, 7 ingest/egress */
 int pprts_b200_kernel_stats(pprts_b200_solver *solver, int reset, double ms[8], long launches[8]);

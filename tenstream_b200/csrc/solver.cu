@@ -1091,6 +1091,7 @@ int pprts_b200_internal_force_angles(pprts_b200_solver *s, double symmetry_phi, 
 }
 
 extern "C" long pprts_b200_kernel_launches(pprts_b200_solver *s) { return s ? s->launches : 0; }
+extern "C" void *pprts_b200_stream(pprts_b200_solver *s) { return s ? (void *)s->stream : nullptr; }
 extern "C" int pprts_b200_enable_kernel_timing(pprts_b200_solver *s, int on) {
   if (!s) return set_err(1, "null solver");
   collect_events(s);

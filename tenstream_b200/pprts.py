@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "pprts_b200_reset_accumulator", "pprts_b200_get_accumulated", "pprts_b200_nccl_unique_id",
     "pprts_b200_comm_init", "pprts_b200_allreduce_accumulated", "pprts_b200_get_coeffs", "pprts_b200_get_state",
     "pprts_b200_get_info", "pprts_b200_mat_mult_ediff", "pprts_b200_lookup_coeffs", "pprts_b200_kernel_launches",
-    "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error",
+    "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error", "pprts_b200_stream",
 ]
 
 
@@ -101,6 +101,8 @@ def lib():
     L.pprts_b200_lookup_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_long] + [c_double_p] * 5
     L.pprts_b200_kernel_launches.restype = C.c_long
     L.pprts_b200_kernel_launches.argtypes = [C.c_void_p]
+    L.pprts_b200_stream.restype = C.c_void_p
+    L.pprts_b200_stream.argtypes = [C.c_void_p]
     L.pprts_b200_kernel_stats.argtypes = [C.c_void_p, C.c_int, c_double_p, c_long_p]
     L.pprts_b200_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     _lib = L
@@ -193,6 +195,10 @@ class Solver:
         out = np.zeros((n, nc))
         _chk(lib().pprts_b200_lookup_coeffs(self._h, mode, n, *[_dp(a) for a in arrs], _dp(out)), "lookup_coeffs")
         return out
+
+    def cuda_stream(self) -> int:
+        """cudaStream_t (as an integer) all kernels of this solver are launched on"""
+        return int(lib().pprts_b200_stream(self._h) or 0)
 
     def kernel_launches(self):
         return int(lib().pprts_b200_kernel_launches(self._h))

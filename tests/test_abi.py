@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/pprts_b200.h declares (no compute calls, no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from tenstream_b200 import build
+    return build.build()
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "pprts_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pprts_(?:f2c|b200)_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(built_lib):
+    L = ctypes.CDLL(built_lib)
+    syms = header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/pprts_b200.h but not exported"
+
+
+def test_python_binding_lists_the_same_symbols():
+    from tenstream_b200 import pprts
+    assert set(header_symbols()) == set(pprts.ABI_SYMBOLS)
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the handle API refuses to create a solver; nothing routes through the oracle."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import numpy as np
+    from tenstream_b200 import lut as L
+    from tenstream_b200 import pprts as P
+    import tempfile
+    cfg = L.small_test_config(310)
+    paths = L.write_synthetic_lut(cfg, os.path.join(tempfile.mkdtemp(), "LUT"))
+    lut = P.Lut(cfg, paths)
+    with pytest.raises(P.PprtsError, match="no CUDA device"):
+        P.init_pprts(0, 4, 3, 3, 100., 100., P.sundir_from_angles(0., 20.), dz1d=np.full(4, 50.), lut=lut)
+    lut.close()
+    src = open(os.path.join(ROOT, "tenstream_b200", "pprts.py")).read()
+    assert "oracle" not in src.replace("CPU oracle", "")
+
+
+def test_product_does_not_import_oracle():
+    import glob
+    for f in glob.glob(os.path.join(ROOT, "tenstream_b200", "**", "*"), recursive=True):
+        if f.endswith((".py", ".cu", ".cuh", ".h")):
+            txt = open(f).read()
+            assert "from oracle" not in txt and "import oracle" not in txt and "pprts_oracle" not in txt, f

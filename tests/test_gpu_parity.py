@@ -173,7 +173,7 @@ def test_thermal_vs_oracle(P, gpu_lut, oracle_lut, precond):
         out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., np.full(Nz, 60.), 0., 0., 0.05, kabs, ksca, g,
                        solar=False, planck=planck, planck_srfc=srfc, precond=precond)
         assert relerr(*out["b"], 1e-9) < 1e-10
-        check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-7)
+        check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-6)  # abso = absorbed - emitted cancels
         assert np.all(out["gpu"][3] == 0)
 
 
@@ -191,7 +191,7 @@ def test_1d_layers_and_topography(P, gpu_lut, oracle_lut):
     T = np.linspace(220, 290, Nz + 1)[:, None, None] * np.ones((Nz + 1, Nx, Ny))
     out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., None, 180., 40., 0.2, kabs * 20, ksca, g, dz3d=dz3d,
                    solar=False, planck=5.67e-8 * T ** 4 / np.pi)
-    check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-7)
+    check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-6)  # abso = absorbed - emitted cancels
 
 
 def test_fp32_coefficient_storage(P, gpu_lut, oracle_lut):
@@ -222,7 +222,7 @@ def test_absorption_by_flux_divergence(P, gpu_lut, oracle_lut):
     for by_coeff in (True, False):
         out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 1., np.full(Nz, 1.), 180., 0., 0.1, kabs, ksca, g, solar=False,
                        planck=planck, planck_srfc=np.full((Nx, Ny), 100.), by_coeff_divergence=by_coeff)
-        check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-7)
+        check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-6)  # abso = absorbed - emitted cancels
         res[by_coeff] = out["gpu"][2]
     assert np.abs(res[True] - res[False]).max() < 1e-2 * np.abs(res[False]).max()
 

@@ -1,0 +1,206 @@
+!> ISO_C_BINDING shim over libpprts_b200.so (include/pprts_b200.h, layer 2).
+!>
+!> Host code stays in Fortran: this module keeps the reference's call signatures for the pprts path
+!> (src/pprts.F90:192-200 -- init_pprts, set_angles, set_optical_properties, solve_pprts, pprts_get_result,
+!> destroy_pprts) and forwards them to the handle-based C ABI.  A host model that today does
+!>     use m_pprts, only: init_pprts, set_optical_properties, solve_pprts, pprts_get_result, destroy_pprts
+!> switches to `use m_pprts_b200` and replaces `class(t_solver)` by `type(t_solver_b200)`.
+!>
+!> Not compiled in this repository's CI (the build image has no Fortran compiler); it only uses F2003 features.
+module m_pprts_b200
+  use iso_c_binding
+  implicit none
+  private
+  public :: t_solver_b200, t_lut_b200, lut_open, lut_close, init_pprts, set_angles, set_optical_properties, &
+    & solve_pprts, pprts_get_result, destroy_pprts
+
+  integer, parameter :: ireals = c_double, iintegers = c_int
+
+  type t_lut_b200
+    type(c_ptr) :: h = c_null_ptr
+  end type
+  type t_solver_b200
+    type(c_ptr) :: h = c_null_ptr
+    integer(iintegers) :: Nz = 0, Nx = 0, Ny = 0
+  end type
+
+  !> mirrors pprts_b200_config (include/pprts_b200.h)
+  type, bind(c) :: c_config
+    integer(c_int) :: solver_id, Nz, Nx, Ny
+    real(c_double) :: dx, dy
+    type(c_ptr) :: dz1d, dz3d
+    real(c_double) :: sundir(3)
+    real(c_double) :: twostr_ratio
+    integer(c_int) :: coeff_fp32, by_coeff_divergence
+    real(c_double) :: rtol, atol
+    integer(c_int) :: maxit_dir, maxit_diff, precond, device, keep_solutions, nxproc, nyproc, xrank, yrank
+  end type
+
+  interface
+    subroutine c_default_config(cfg) bind(c, name='pprts_b200_default_config')
+      import; type(c_config), intent(out) :: cfg
+    end subroutine
+    integer(c_int) function c_lut_open(solver_id, pT, pS, pD, ndir, axes, lut) bind(c, name='pprts_b200_lut_open')
+      import; integer(c_int), value :: solver_id
+      character(kind=c_char), intent(in) :: pT(*), pS(*), pD(*)
+      integer(c_int), intent(in) :: ndir(6)
+      type(c_ptr), intent(in) :: axes(6)
+      type(c_ptr), intent(out) :: lut
+    end function
+    integer(c_int) function c_lut_close(lut) bind(c, name='pprts_b200_lut_close')
+      import; type(c_ptr), value :: lut
+    end function
+    integer(c_int) function c_create(cfg, lut, solver) bind(c, name='pprts_b200_create')
+      import; type(c_config), intent(in) :: cfg
+      type(c_ptr), value :: lut
+      type(c_ptr), intent(out) :: solver
+    end function
+    integer(c_int) function c_destroy(solver) bind(c, name='pprts_b200_destroy')
+      import; type(c_ptr), value :: solver
+    end function
+    integer(c_int) function c_set_angles(solver, sundir) bind(c, name='pprts_b200_set_angles')
+      import; type(c_ptr), value :: solver
+      real(c_double), intent(in) :: sundir(3)
+    end function
+    integer(c_int) function c_set_optprop(solver, albedo, kabs, ksca, g, planck, planck_srfc, albedo_2d, ldelta) &
+        & bind(c, name='pprts_b200_set_optical_properties')
+      import; type(c_ptr), value :: solver
+      real(c_double), value :: albedo
+      type(c_ptr), value :: kabs, ksca, g, planck, planck_srfc, albedo_2d
+      integer(c_int), value :: ldelta
+    end function
+    integer(c_int) function c_solve(solver, lthermal, lsolar, edirTOA, uid) bind(c, name='pprts_b200_solve')
+      import; type(c_ptr), value :: solver
+      integer(c_int), value :: lthermal, lsolar, uid
+      real(c_double), value :: edirTOA
+    end function
+    integer(c_int) function c_get_result(solver, uid, edn, eup, abso, edir) bind(c, name='pprts_b200_get_result')
+      import; type(c_ptr), value :: solver
+      integer(c_int), value :: uid
+      type(c_ptr), value :: edn, eup, abso, edir
+    end function
+    function c_last_error() bind(c, name='pprts_b200_last_error') result(msg)
+      import; type(c_ptr) :: msg
+    end function
+  end interface
+
+contains
+
+  !> CHKERR (src/helper_functions.fypp:888-906): print and stop; a host model may replace this by mpi_abort
+  subroutine chkerr(ierr, where)
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: where
+    character(kind=c_char), pointer :: cmsg(:)
+    integer :: n
+    if (ierr .eq. 0) return
+    call c_f_pointer(c_last_error(), cmsg, [1024])
+    n = 1
+    do while (n .lt. 1024 .and. cmsg(n) .ne. c_null_char); n = n + 1; end do
+    print *, 'pprts_b200 :: '//where//' failed (', ierr, '): ', cmsg(1:n - 1)
+    error stop 1
+  end subroutine
+
+  subroutine lut_open(lut, solver_id, fname_Tdir, fname_Sdir, fname_Sdiff, tau, w0, aspect_zx, g, phi, theta)
+    type(t_lut_b200), intent(out) :: lut
+    integer(iintegers), intent(in) :: solver_id
+    character(len=*), intent(in) :: fname_Tdir, fname_Sdir, fname_Sdiff
+    real(c_float), intent(in), target :: tau(:), w0(:), aspect_zx(:), g(:), phi(:), theta(:)
+    integer(c_int) :: ndir(6)
+    type(c_ptr) :: axes(6)
+    ndir = [size(tau), size(w0), size(aspect_zx), size(g), size(phi), size(theta)]
+    axes = [c_loc(tau), c_loc(w0), c_loc(aspect_zx), c_loc(g), c_loc(phi), c_loc(theta)]
+    call chkerr(c_lut_open(solver_id, trim(fname_Tdir)//c_null_char, trim(fname_Sdir)//c_null_char, &
+      & trim(fname_Sdiff)//c_null_char, ndir, axes, lut%h), 'lut_open')
+  end subroutine
+
+  subroutine lut_close(lut)
+    type(t_lut_b200), intent(inout) :: lut
+    call chkerr(c_lut_close(lut%h), 'lut_close'); lut%h = c_null_ptr
+  end subroutine
+
+  !> init_pprts (src/pprts.F90:213): icomm is kept in the signature; one process drives one GPU
+  subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, device)
+    integer, intent(in) :: icomm
+    integer(iintegers), intent(in) :: Nz, Nx, Ny
+    real(ireals), intent(in) :: dx, dy, sundir(3)
+    type(t_solver_b200), intent(inout) :: solver
+    type(t_lut_b200), intent(in) :: lut
+    integer(iintegers), intent(in) :: solver_id
+    real(ireals), intent(in), target, optional :: dz1d(:), dz3d(:, :, :)
+    integer(iintegers), intent(in), optional :: device
+    type(c_config) :: cfg
+    call c_default_config(cfg)
+    cfg%solver_id = solver_id; cfg%Nz = Nz; cfg%Nx = Nx; cfg%Ny = Ny; cfg%dx = dx; cfg%dy = dy; cfg%sundir = sundir
+    if (present(dz1d)) cfg%dz1d = c_loc(dz1d)
+    if (present(dz3d)) cfg%dz3d = c_loc(dz3d)
+    if (present(device)) cfg%device = device
+    call chkerr(c_create(cfg, lut%h, solver%h), 'init_pprts')
+    solver%Nz = Nz; solver%Nx = Nx; solver%Ny = Ny
+    if (.false.) print *, icomm
+  end subroutine
+
+  subroutine set_angles(solver, sundir)
+    type(t_solver_b200), intent(inout) :: solver
+    real(ireals), intent(in) :: sundir(3)
+    call chkerr(c_set_angles(solver%h, sundir), 'set_angles')
+  end subroutine
+
+  !> set_optical_properties (src/pprts.F90:1764): local arrays (Nz,Nx,Ny); planck (Nz+1,Nx,Ny)
+  subroutine set_optical_properties(solver, albedo, kabs, ksca, g, planck, planck_srfc, albedo_2d, ldelta_scaling)
+    type(t_solver_b200), intent(inout) :: solver
+    real(ireals), intent(in) :: albedo
+    real(ireals), intent(in), target, contiguous, optional :: kabs(:, :, :), ksca(:, :, :), g(:, :, :), planck(:, :, :)
+    real(ireals), intent(in), target, contiguous, optional :: planck_srfc(:, :), albedo_2d(:, :)
+    logical, intent(in), optional :: ldelta_scaling
+    type(c_ptr) :: p(6)
+    integer(c_int) :: ldelta
+    p = c_null_ptr
+    if (present(kabs)) p(1) = c_loc(kabs)
+    if (present(ksca)) p(2) = c_loc(ksca)
+    if (present(g)) p(3) = c_loc(g)
+    if (present(planck)) p(4) = c_loc(planck)
+    if (present(planck_srfc)) p(5) = c_loc(planck_srfc)
+    if (present(albedo_2d)) p(6) = c_loc(albedo_2d)
+    ldelta = 1
+    if (present(ldelta_scaling)) ldelta = merge(1, 0, ldelta_scaling)
+    call chkerr(c_set_optprop(solver%h, albedo, p(1), p(2), p(3), p(4), p(5), p(6), ldelta), 'set_optical_properties')
+  end subroutine
+
+  !> solve_pprts (src/pprts.F90:2487)
+  subroutine solve_pprts(solver, lthermal, lsolar, edirTOA, opt_solution_uid)
+    type(t_solver_b200), intent(inout) :: solver
+    logical, intent(in) :: lthermal, lsolar
+    real(ireals), intent(in) :: edirTOA
+    integer(iintegers), intent(in), optional :: opt_solution_uid
+    integer(c_int) :: uid
+    uid = 0; if (present(opt_solution_uid)) uid = opt_solution_uid
+    call chkerr(c_solve(solver%h, merge(1, 0, lthermal), merge(1, 0, lsolar), edirTOA, uid), 'solve_pprts')
+  end subroutine
+
+  !> pprts_get_result (src/pprts.F90:5799): allocates the outputs if needed, like the reference
+  subroutine pprts_get_result(solver, redn, reup, rabso, redir, opt_solution_uid)
+    type(t_solver_b200), intent(inout) :: solver
+    real(ireals), allocatable, target, intent(inout) :: redn(:, :, :), reup(:, :, :), rabso(:, :, :)
+    real(ireals), allocatable, target, intent(inout), optional :: redir(:, :, :)
+    integer(iintegers), intent(in), optional :: opt_solution_uid
+    integer(c_int) :: uid
+    type(c_ptr) :: pdir
+    uid = 0; if (present(opt_solution_uid)) uid = opt_solution_uid
+    if (.not. allocated(redn)) allocate (redn(solver%Nz + 1, solver%Nx, solver%Ny))
+    if (.not. allocated(reup)) allocate (reup(solver%Nz + 1, solver%Nx, solver%Ny))
+    if (.not. allocated(rabso)) allocate (rabso(solver%Nz, solver%Nx, solver%Ny))
+    pdir = c_null_ptr
+    if (present(redir)) then
+      if (.not. allocated(redir)) allocate (redir(solver%Nz + 1, solver%Nx, solver%Ny))
+      pdir = c_loc(redir)
+    end if
+    call chkerr(c_get_result(solver%h, uid, c_loc(redn), c_loc(reup), c_loc(rabso), pdir), 'pprts_get_result')
+  end subroutine
+
+  subroutine destroy_pprts(solver, lfinalizepetsc)
+    type(t_solver_b200), intent(inout) :: solver
+    logical, intent(in), optional :: lfinalizepetsc
+    call chkerr(c_destroy(solver%h), 'destroy_pprts'); solver%h = c_null_ptr
+    if (.false. .and. present(lfinalizepetsc)) print *, lfinalizepetsc
+  end subroutine
+end module

@@ -228,12 +228,14 @@ def test_absorption_by_flux_divergence(P, gpu_lut, oracle_lut):
 
 
 def test_warm_start_and_uid_cache(P, gpu_lut):
-    """solutions(uid) caching (src/pprts.F90:2532-2558): a second solve of the same uid starts from its own result"""
+    """solutions(uid) caching (src/pprts.F90:2532-2558): a second solve of the same uid starts from its own result,
+    a new uid starts from uid-1.  The convergence test is relative to the INITIAL residual (MyKSPConverged,
+    src/pprts.F90:4437-4486), so a warm start still iterates -- but from a residual that is already ~rtol small."""
     rng = np.random.default_rng(12)
     Nz, Nx, Ny = 8, 6, 6
     kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
     s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(40., 30.), dz1d=np.full(Nz, 60.), lut=gpu_lut,
-                     rtol=1e-9, atol=1e-30)
+                     rtol=1e-6, atol=1e-30)
     P.set_optical_properties(s, 0.3, kabs, ksca, g)
     P.solve_pprts(s, False, True, 1000., opt_solution_uid=5)
     first = s.info(5)
@@ -241,11 +243,12 @@ def test_warm_start_and_uid_cache(P, gpu_lut):
     P.solve_pprts(s, False, True, 1000., opt_solution_uid=5)
     second = s.info(5)
     r2 = P.pprts_get_result(s, 5)
-    assert second["niter_diff"] <= 2 < first["niter_diff"]
+    assert second["res_diff"] < 1e-4 * first["res_diff"]          # started from the converged state
+    assert second["niter_dir"] <= 8 < first["niter_dir"]
     for a, b in zip(r1, r2):
-        assert relerr(a, b) < 1e-7
+        assert relerr(a, b) < 1e-5
     P.solve_pprts(s, False, True, 1000., opt_solution_uid=6)       # new uid: warm start from uid-1
-    assert s.info(6)["niter_diff"] <= 2
+    assert s.info(6)["res_diff"] < 1e-4 * first["res_diff"]
     with pytest.raises(P.PprtsError):
         P.pprts_get_result(s, 77)
     P.destroy_pprts(s)

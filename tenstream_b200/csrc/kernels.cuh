@@ -5,6 +5,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 #define PB_PI 3.14159265358979323846
@@ -595,83 +597,195 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdi
 // streams the Nf*Nf coefficient planes once (fp32 storage: 400 B/cell for 3_10) and writes the Nf outgoing streams,
 // each of which has exactly one producer.  NDOT weighted dot products with y are fused (rh.v, t.s, t.t of BiCGStab).
 // =================================================================================================================
-template <class L, class CT, int NDOT>
-__global__ void __launch_bounds__(128)
-k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
-          const double *__restrict__ albedo, const double *__restrict__ x, double *__restrict__ y,
-          const double *__restrict__ w0, double *partials, unsigned int *counter, double *out_dots) {
+// per-cell body shared by the plain and the TMA-staged kernel; COEF(n) returns coefficient n = dst*Nf+src of cell c
+template <class L, int NDOT, class COEF>
+__device__ __forceinline__ void matmult_cell(const Grid &g, int n1d, COEF coef, const double *__restrict__ a11,
+                                             const double *__restrict__ a12, const double *__restrict__ albedo,
+                                             const double *__restrict__ x, double *__restrict__ y,
+                                             const double *__restrict__ w0, long c, double *dots) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
-  constexpr int NV = (NDOT > 0) ? NDOT : 1;
-  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  double dots[NV];
-#pragma unroll
-  for (int n = 0; n < NV; ++n) dots[n] = 0.0;
   // NDOT == 1: dots[0] = sum w0*y ; NDOT == 2: dots[0] = sum y*w0, dots[1] = sum y*y
   auto emit = [&](long q, double val) {
     y[q] = val;
     if (NDOT >= 1) dots[0] += val * w0[q];
     if (NDOT >= 2) dots[1] += val * val;
   };
-  if (c < g.ncell) {
-    const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
-    const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
-    const long l_own = lidx(g, k, j, i), l_dn = l_own + g.ncol;
-    const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
-    if (k < n1d) {
-      const double t = a11[c], r = a12[c];
+  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
+  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
+  const long l_own = lidx(g, k, j, i), l_dn = l_own + g.ncol;
+  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+  if (k < n1d) {
+    const double t = a11[c], r = a12[c];
 #pragma unroll
-      for (int d = 0; d < Nft; ++d) {
-        if (L::top_in(d)) {  // edn: xb(k+1) -= x(d,k)*a11 ; -= x(inv,k+1)*a12
-          long q = (long)d * g.nlev + l_dn;
-          double acc = 0.0;
-          acc = acc - x[(long)d * g.nlev + l_own] * t;
-          acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_dn] * r;
-          emit(q, acc + x[q]);
-        } else {
-          long q = (long)d * g.nlev + l_own;
-          double acc = 0.0;
-          acc = acc - x[(long)d * g.nlev + l_dn] * t;
-          acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_own] * r;
-          emit(q, acc + x[q]);
-        }
-      }
-#pragma unroll
-      for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
-    } else {
-      double xs[Nf];
-#pragma unroll
-      for (int d = 0; d < Nft; ++d) xs[d] = x[(long)d * g.nlev + (L::top_in(d) ? l_own : l_dn)];
-#pragma unroll
-      for (int d = 0; d < Nfs; ++d) xs[Nft + d] = x[(long)(Nft + d) * g.nlev + (L::side_in(d) ? l_own : l_xp)];
-#pragma unroll
-      for (int d = 0; d < Nfs; ++d) xs[Nft + Nfs + d] = x[(long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? l_own : l_yp)];
-#pragma unroll
-      for (int dst = 0; dst < Nf; ++dst) {
+    for (int d = 0; d < Nft; ++d) {
+      if (L::top_in(d)) {  // edn: xb(k+1) -= x(d,k)*a11 ; -= x(inv,k+1)*a12
+        long q = (long)d * g.nlev + l_dn;
         double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < Nf; ++s) acc = acc - xs[s] * (double)T[(long)(dst * Nf + s) * g.ncp + c];
-        long q;
-        if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
-        else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
-        else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
-        q += (long)dst * g.nlev;
+        acc = acc - x[(long)d * g.nlev + l_own] * t;
+        acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_dn] * r;
+        emit(q, acc + x[q]);
+      } else {
+        long q = (long)d * g.nlev + l_own;
+        double acc = 0.0;
+        acc = acc - x[(long)d * g.nlev + l_dn] * t;
+        acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_own] * r;
         emit(q, acc + x[q]);
       }
     }
-    if (k == 0) {  // rows without a producing cell: incoming diffuse at TOA
 #pragma unroll
-      for (int d = 0; d < Nft; ++d) if (L::top_in(d)) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+  } else {
+    double xs[Nf], xd[Nf];
+#pragma unroll
+    for (int d = 0; d < Nft; ++d) {
+      xs[d] = x[(long)d * g.nlev + (L::top_in(d) ? l_own : l_dn)];
+      xd[d] = x[(long)d * g.nlev + (L::top_in(d) ? l_dn : l_own)];
     }
-    if (k == g.Nz - 1) {  // albedo row (src/pprts_shell.F90:500-505) and the unused side dofs below the ground
-      const double alb = albedo[(long)j * g.Nx + i];
 #pragma unroll
-      for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) {
-        long q = (long)d * g.nlev + l_dn;
-        emit(q, x[q] - x[(long)L::inv_dof(d) * g.nlev + l_dn] * alb);
-      }
-#pragma unroll
-      for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, x[q]); }
+    for (int d = 0; d < Nfs; ++d) {
+      xs[Nft + d] = x[(long)(Nft + d) * g.nlev + (L::side_in(d) ? l_own : l_xp)];
+      xd[Nft + d] = x[(long)(Nft + d) * g.nlev + (L::side_in(d) ? l_xp : l_own)];
     }
+#pragma unroll
+    for (int d = 0; d < Nfs; ++d) {
+      xs[Nft + Nfs + d] = x[(long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? l_own : l_yp)];
+      xd[Nft + Nfs + d] = x[(long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? l_yp : l_own)];
+    }
+#pragma unroll
+    for (int dst = 0; dst < Nf; ++dst) {
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < Nf; ++s) acc = acc - xs[s] * coef(dst * Nf + s);
+      long q;
+      if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
+      else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
+      else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
+      q += (long)dst * g.nlev;
+      emit(q, acc + xd[dst]);
+    }
+  }
+  if (k == 0) {  // rows without a producing cell: incoming diffuse at TOA
+#pragma unroll
+    for (int d = 0; d < Nft; ++d) if (L::top_in(d)) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+  }
+  if (k == g.Nz - 1) {  // albedo row (src/pprts_shell.F90:500-505) and the unused side dofs below the ground
+    const double alb = albedo[(long)j * g.Nx + i];
+#pragma unroll
+    for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) {
+      long q = (long)d * g.nlev + l_dn;
+      emit(q, x[q] - x[(long)L::inv_dof(d) * g.nlev + l_dn] * alb);
+    }
+#pragma unroll
+    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, x[q]); }
+  }
+}
+
+template <class L, class CT, int NDOT>
+__global__ void __launch_bounds__(128)
+k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
+          const double *__restrict__ albedo, const double *__restrict__ x, double *__restrict__ y,
+          const double *__restrict__ w0, double *partials, unsigned int *counter, double *out_dots) {
+  constexpr int NV = (NDOT > 0) ? NDOT : 1;
+  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dots[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) dots[n] = 0.0;
+  if (c < g.ncell) {
+    auto coef = [&](int n) { return (double)T[(long)n * g.ncp + c]; };
+    matmult_cell<L, NDOT>(g, n1d, coef, a11, a12, albedo, x, y, w0, c, dots);
+  }
+  if (NDOT > 0) grid_reduce_sum<NV>(dots, partials, counter, out_dots);
+}
+
+// ---- TMA-staged variant (fp32 coefficients) ---------------------------------------------------------------------
+// The plain kernel is latency-bound: 100 dependent-free but register-hungry 4-byte loads per thread leave only
+// ~46 % of HBM bandwidth in flight (profiles/r1_matmult.txt: "No Eligible" 85 %).  Here a persistent CTA per tile of
+// TILE consecutive cells lets ONE thread fetch the whole [Nf*Nf planes x TILE cells] box with a single TMA tensor
+// copy (cp.async.bulk.tensor.2d over the coefficient array viewed as a 2-D [plane][cell] tensor) into a
+// double-buffered shared-memory stage, completion tracked by an mbarrier; the copy of tile t+1 is in flight while
+// tile t is being consumed, independent of register pressure.  (Issuing the planes as Nf*Nf separate 512-byte
+// cp.async.bulk copies was measured slower than the plain kernel: the single issuing thread becomes the bottleneck.)
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int c0, int c1, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <class L, int NDOT, int TILE>
+__global__ void __launch_bounds__(TILE)
+k_matmult_tma(Grid g, int n1d, long ntiles, const __grid_constant__ CUtensorMap tmap, const double *__restrict__ a11,
+              const double *__restrict__ a12, const double *__restrict__ albedo, const double *__restrict__ x,
+              double *__restrict__ y, const double *__restrict__ w0, double *partials, unsigned int *counter,
+              double *out_dots) {
+  constexpr int NP = L::Nf * L::Nf;
+  constexpr int NV = (NDOT > 0) ? NDOT : 1;
+  constexpr unsigned int STAGE_BYTES = NP * TILE * sizeof(float);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar[2];
+  float *stage0 = reinterpret_cast<float *>(smem_raw);
+  float *stage1 = reinterpret_cast<float *>(smem_raw + STAGE_BYTES);
+  const int tid = threadIdx.x;
+  const long c1d = (long)n1d * g.ncol;  // cells below this index are in 1-D layers and need no plane data
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](long tile, int st) {
+    const long c0 = tile * TILE;
+    unsigned long long *b = &bar[st];
+    if (c0 + TILE <= c1d) { mbar_arrive(b); return; }
+    float *dst = st ? stage1 : stage0;
+    mbar_expect_tx(b, STAGE_BYTES);
+    tma_load_2d(dst, &tmap, (int)c0, 0, b);  // one box: NP planes x TILE cells
+  };
+  double dots[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) dots[n] = 0.0;
+  if (tid == 0 && (long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  unsigned int it = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    const unsigned int parity = (it >> 1) & 1;
+    const long next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) issue(next, st ^ 1);
+    const long c = tile * TILE + tid;
+    mbar_wait(&bar[st], parity);
+    if (c < g.ncell) {
+      const float *sp = (st ? stage1 : stage0) + tid;
+      auto coef = [&](int n) { return (double)sp[n * TILE]; };
+      matmult_cell<L, NDOT>(g, n1d, coef, a11, a12, albedo, x, y, w0, c, dots);
+    }
+    __syncthreads();  // stage st may be refilled from the next iteration on
   }
   if (NDOT > 0) grid_reduce_sum<NV>(dots, partials, counter, out_dots);
 }

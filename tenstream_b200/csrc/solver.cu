@@ -239,6 +239,9 @@ struct pprts_b200_solver {
   // NCCL
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  int num_sms = 148;
+  bool use_tma = true;
+  CUtensorMap tmap_f2f;
 };
 
 static cudaEvent_t get_event(pprts_b200_solver *s) {
@@ -287,6 +290,30 @@ static void collect_events(pprts_b200_solver *s) {
 static inline unsigned int nblk(long n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 static const int VEC_BLOCK = 256;
 static inline unsigned int vec_grid(long n) { return (unsigned int)std::min<long>((n + VEC_BLOCK - 1) / VEC_BLOCK, 148L * 16); }
+
+// 2-D tensor map over a coefficient array viewed as [nplanes][ncp] fp32, box = [nplanes][tile] (one TMA per tile).
+// cuTensorMapEncodeTiled is fetched from the driver at run time: no link-time dependency on libcuda.
+typedef CUresult (*fn_cuTensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                              CUtensorMapFloatOOBfill);
+static int make_plane_tensor_map(CUtensorMap *tm, void *base, int nplanes, long ncp, int tile) {
+  static fn_cuTensorMapEncodeTiled enc = nullptr;
+  if (!enc) {
+    cudaDriverEntryPointQueryResult q;
+    void *p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 1;
+    enc = (fn_cuTensorMapEncodeTiled)p;
+  }
+  if (nplanes > 256 || tile > 256) return 2;
+  cuuint64_t dims[2] = {(cuuint64_t)ncp, (cuuint64_t)nplanes};
+  cuuint64_t strides[1] = {(cuuint64_t)ncp * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)tile, (cuuint32_t)nplanes};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 3;
+}
 
 extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   memset(cfg, 0, sizeof(*cfg));
@@ -404,9 +431,11 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   Grid &g = s->g;
   g.Nz = cfg->Nz; g.Nx = cfg->Nx; g.Ny = cfg->Ny;
   g.ncol = (long)g.Nx * g.Ny; g.ncell = g.ncol * g.Nz; g.nlev = g.ncol * (g.Nz + 1);
-  g.ncp = (g.ncell + 31) / 32 * 32;
+  g.ncp = (g.ncell + 127) / 128 * 128;  // plane stride; a multiple of the TMA tile so bulk copies never run off a plane
   g.dx = cfg->dx; g.dy = cfg->dy;
   CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CU(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device));
+  s->use_tma = getenv("PPRTS_B200_NO_TMA") == nullptr;
 
   // dz in device layout + determine_1d_layers (src/pprts.F90:649-725)
   std::vector<double> hdz((size_t)g.ncell);
@@ -432,6 +461,7 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   CU(cudaMalloc(&s->d2d, (size_t)Nd * Nd * g.ncp * csz)); CU(cudaMemset(s->d2d, 0, (size_t)Nd * Nd * g.ncp * csz));
   CU(cudaMalloc(&s->d2f, (size_t)Nd * Nf * g.ncp * csz)); CU(cudaMemset(s->d2f, 0, (size_t)Nd * Nf * g.ncp * csz));
   CU(cudaMalloc(&s->f2f, (size_t)Nf * Nf * g.ncp * csz)); CU(cudaMemset(s->f2f, 0, (size_t)Nf * Nf * g.ncp * csz));
+  if (s->use_tma && cfg->coeff_fp32 && make_plane_tensor_map(&s->tmap_f2f, s->f2f, Nf * Nf, g.ncp, 128)) s->use_tma = false;
   DA(s->cdiv_dir, (size_t)Nd * g.ncp); DA(s->cdiv_diff, (size_t)Nf * g.ncp);
   DA(s->b, (size_t)Nf * g.nlev);
   for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)Nf * g.nlev);
@@ -697,9 +727,37 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   return 0;
 }
 
+static const int MM_TILE = 128;
+template <class L, int NDOT>
+static bool launch_matmult_tma(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+  constexpr size_t smem = 2 * (size_t)L::Nf * L::Nf * MM_TILE * sizeof(float);
+  if constexpr (smem > 200 * 1024) return false;
+  else {
+    const Grid &g = s->g;
+    static bool attr_set = false;
+    auto kern = k_matmult_tma<L, NDOT, MM_TILE>;
+    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const long ntiles = (g.ncell + MM_TILE - 1) / MM_TILE;
+    const unsigned int grid = (unsigned int)std::min<long>(ntiles, 2L * s->num_sms);
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (s->timing) { ea = get_event(s); eb = get_event(s); cudaEventRecord(ea, s->stream); }
+    kern<<<grid, MM_TILE, smem, s->stream>>>(g, s->n1d, ntiles, s->tmap_f2f, s->a11, s->a12, s->albedo, x, y, w,
+                                             s->partials, s->counter, dots);
+    if (s->timing) { cudaEventRecord(eb, s->stream); s->evs.push_back({FAM_MATMULT, ea, eb}); }
+    s->launches++;
+    s->fam_launch[FAM_MATMULT]++;
+    return true;
+  }
+}
+
 template <int NDOT>
 static void launch_matmult(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
   const Grid &g = s->g;
+  if (s->cfg.coeff_fp32 && s->use_tma) {
+    bool done = false;
+    DISPATCH_L(s, done = launch_matmult_tma<L, NDOT>(s, x, y, w, dots));
+    if (done) return;
+  }
   DISPATCH_LC(s, LAUNCH(s, FAM_MATMULT, (k_matmult<L, CT, NDOT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f,
                          s->a11, s->a12, s->albedo, x, y, w, s->partials, s->counter, dots));
 }

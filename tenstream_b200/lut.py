@@ -250,32 +250,33 @@ def _entry_points(face, s, aspect, n=5, sub=None):
 
 
 def _trace(points, d, aspect):
-    """Exit face ('z+', 'z-', 'x+', ...) index and path length of straight rays through the box."""
+    """Straight rays through the box: returns a list of hits (ray index, exit axis, sign, path length, share).
+    A ray leaving exactly through an edge or corner is shared equally between the faces it touches, which keeps
+    the tables exactly mirror-symmetric (an argmin tie-break would depend on rounding of the entry points)."""
     d = np.asarray(d, dtype=np.float64)
     hi = np.array([1.0, 1.0, aspect])
     with np.errstate(divide="ignore", invalid="ignore"):
         t = np.where(d > 0, (hi - points) / d, np.where(d < 0, (0.0 - points) / d, np.inf))
-    t = np.where(t < 1e-12, np.where(np.abs(d) > 0, t, np.inf), t)
     t = np.where(t < 0, np.inf, t)
-    axis = np.argmin(t, axis=1)
-    path = t[np.arange(len(points)), axis]
-    return axis, np.sign(d)[axis], path
+    tmin = t.min(axis=1, keepdims=True)
+    tied = t <= tmin * (1 + 1e-9) + 1e-12
+    share = tied / tied.sum(axis=1, keepdims=True)
+    hits = []
+    for n in range(len(points)):
+        for ax in range(3):
+            if tied[n, ax]:
+                hits.append((n, ax, float(np.sign(d[ax])), float(tmin[n, 0]), float(share[n, ax])))
+    return hits
 
 
-def _classify_diffuse(axis, sgn, d, streams):
-    """Index of the diffuse stream a ray leaving through (axis, sgn) with direction d joins."""
-    idx = np.empty(len(axis), dtype=np.int64)
-    for n in range(len(axis)):
-        ax, s = axis[n], sgn[n]
-        for k, st in enumerate(streams):
-            if "xyz"[ax] != st["face"] or st["s"] != s:
-                continue
-            if st["face"] == "z" or st["sz"] == (1 if d[2] >= 0 else -1):
-                idx[n] = k
-                break
-        else:
-            raise RuntimeError("unclassified ray")
-    return idx
+def _classify_diffuse(ax, sgn, d, streams):
+    """Index of the diffuse stream a ray leaving through (axis, sign) with direction d joins."""
+    for k, st in enumerate(streams):
+        if "xyz"[ax] != st["face"] or st["s"] != sgn:
+            continue
+        if st["face"] == "z" or st["sz"] == (1 if d[2] >= 0 else -1):
+            return k
+    raise RuntimeError("unclassified ray")
 
 
 def _iso_weights(streams, aspect):
@@ -299,30 +300,24 @@ def _direct_streams(solver_id):
     raise NotImplementedError
 
 
-def _classify_direct(points_out, axis, dstreams, aspect):
-    idx = np.empty(len(axis), dtype=np.int64)
-    for n in range(len(axis)):
-        face = "xyz"[axis[n]]
-        p = points_out[n]
-        for k, st in enumerate(dstreams):
-            if st["face"] != face:
-                continue
-            if st["sub"] is None:
-                idx[n] = k
-                break
-            if face == "z":
-                a, b = p[0], p[1]
-            elif face == "x":
-                a, b = p[1], p[2] / aspect
-            else:
-                a, b = p[0], p[2] / aspect
-            lo0, hi0, lo1, hi1 = st["sub"]
-            if lo0 - 1e-9 <= a <= hi0 + 1e-9 and lo1 - 1e-9 <= b <= hi1 + 1e-9:
-                idx[n] = k
-                break
+def _classify_direct(p, ax, dstreams, aspect):
+    """Index of the direct stream whose (sub-)face contains the exit point p on face `ax`."""
+    face = "xyz"[ax]
+    for k, st in enumerate(dstreams):
+        if st["face"] != face:
+            continue
+        if st["sub"] is None:
+            return k
+        if face == "z":
+            a, b = p[0], p[1]
+        elif face == "x":
+            a, b = p[1], p[2] / aspect
         else:
-            raise RuntimeError("unclassified direct ray")
-    return idx
+            a, b = p[0], p[2] / aspect
+        lo0, hi0, lo1, hi1 = st["sub"]
+        if lo0 - 1e-9 <= a <= hi0 + 1e-9 and lo1 - 1e-9 <= b <= hi1 + 1e-9:
+            return k
+    raise RuntimeError("unclassified direct ray")
 
 
 def synth_diffuse_table(cfg: LutConfig) -> np.ndarray:
@@ -340,13 +335,11 @@ def synth_diffuse_table(cfg: LutConfig) -> np.ndarray:
             fwd = np.zeros(Nf)
             pts = _entry_points(st["face"], st["s"], a)
             for d, wd in _stream_dirs(st):
-                axis, sgn, path = _trace(pts, d, a)
-                dst = _classify_diffuse(axis, sgn, d, streams)
                 wray = wd / len(pts)
-                att = np.exp(-np.outer(tau, path / a))       # tau_z * path/dz
-                for n in range(len(pts)):
-                    unsc[:, dst[n]] += wray * att[:, n]
-                    fwd[dst[n]] += wray
+                for n, ax, sgn, path, share in _trace(pts, d, a):
+                    dst = _classify_diffuse(ax, sgn, d, streams)
+                    unsc[:, dst] += wray * share * np.exp(-tau * (path / a))       # tau_z * path/dz
+                    fwd[dst] += wray * share
             sc = 1.0 - unsc.sum(1)                             # extinguished fraction (tau)
             # coef[g,w0,tau,dst] = unsc + w0*sc*((1-g)*iso + g*fwd)
             redis = (1 - g)[:, None] * iso[None, :] + g[:, None] * fwd[None, :]      # [g, dst]
@@ -379,17 +372,15 @@ def synth_direct_tables(cfg: LutConfig) -> tuple[np.ndarray, np.ndarray]:
                 iso = _iso_weights(fstreams, a)
                 for s, st in enumerate(dstreams):
                     pts = _entry_points(st["face"], +1, a, n=6, sub=st["sub"])
-                    axis, sgn, path = _trace(pts, d, a)
-                    pout = pts + path[:, None] * d[None, :]
-                    ddst = _classify_direct(pout, axis, dstreams, a)
-                    fdst = _classify_diffuse(axis, sgn, d, fstreams)
                     wray = 1.0 / len(pts)
-                    att = np.exp(-np.outer(tau, path / a))
                     unsc = np.zeros((len(tau), Nd))
                     fwd = np.zeros(Nf)
-                    for n in range(len(pts)):
-                        unsc[:, ddst[n]] += wray * att[:, n]
-                        fwd[fdst[n]] += wray
+                    for n, ax, sgn, path, share in _trace(pts, d, a):
+                        pout = pts[n] + path * d
+                        ddst = _classify_direct(pout, ax, dstreams, a)
+                        fdst = _classify_diffuse(ax, sgn, d, fstreams)
+                        unsc[:, ddst] += wray * share * np.exp(-tau * (path / a))
+                        fwd[fdst] += wray * share
                     sc = 1.0 - unsc.sum(1)
                     redis = (1 - g)[:, None] * iso[None, :] + g[:, None] * fwd[None, :]   # [g, dst]
                     T[it, ip, :, ia, :, :, :, s] = unsc[None, None, :, :]

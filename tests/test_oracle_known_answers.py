@@ -221,3 +221,23 @@ def test_determine_1d_layers(oracle_lut):
     s = ob.OracleSolver(oracle_lut, 6, 3, 3, 100., 100., ob.sundir_from_angles(0, 20.), dz, twostr_ratio=2.0)
     assert list(s.l1d) == [True, True, True, True, False, False]       # lowest thick layer (k=3) and all above
     s.destroy()
+
+
+# the synthetic tables must have the E/W and N/S mirror symmetry the reference's stream permutations assume
+# (src/optprop.F90:1009-1045) and conserve energy per source stream, like the Monte-Carlo tables they stand in for
+@pytest.mark.parametrize("solver_id", [310, 810])
+def test_synthetic_lut_symmetry_and_energy(solver_id):
+    cfg = L.small_test_config(solver_id)
+    Nd, Nf = cfg.Nd, cfg.Nf
+    D = L.synth_diffuse_table(cfg).reshape(-1, Nf, Nf).astype(np.float64)
+    px = [0, 1, 3, 2, 5, 4, 6, 7, 8, 9]
+    py = [0, 1, 2, 3, 4, 5, 7, 6, 9, 8]
+    pxy = [0, 1, 6, 7, 8, 9, 2, 3, 4, 5]                 # x <-> y exchange
+    for p in (px, py, pxy):
+        assert np.allclose(D, D[:, p][:, :, p], rtol=1e-6, atol=1e-7)      # equal up to fp32 rounding of the table
+    assert D.min() >= 0 and D.sum(1).max() <= 1 + 1e-6
+    T, S = L.synth_direct_tables(cfg)
+    T = T.reshape(-1, Nd, Nd).astype(np.float64)
+    S = S.reshape(-1, Nf, Nd).astype(np.float64)
+    tot = T.sum(1) + S.sum(1)
+    assert T.min() >= 0 and S.min() >= 0 and tot.max() <= 1 + 1e-6

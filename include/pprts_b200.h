@@ -58,6 +58,12 @@ void pprts_f2c_opp_get_info(void *opp, int *Ndir, int *Ndiff, float *diff_tauz_r
                             float *dir_w0_range, float *dir_g_range, float *dir_aspect_zx_range,
                             float *dir_phi_range, float *dir_theta_range, int *ierr);
 
+/* Not in the reference: register an already opened table set for the module-level solver of the pprts_f2c_* layer
+ * (tests use reduced parameter spaces), and replace the "print + abort" of CHKERR by a callback. */
+struct pprts_b200_lut;
+void pprts_b200_f2c_set_lut(struct pprts_b200_lut *lut);
+void pprts_b200_f2c_set_abort_handler(void (*handler)(const char *message));
+
 /* ------------------------------------------------------------------------------------------------------------
  * Layer 2: handle-based API (what fortran/m_pprts_b200.F90 binds)
  * ------------------------------------------------------------------------------------------------------------ */

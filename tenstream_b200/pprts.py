@@ -52,7 +52,7 @@ _lib = None
 ABI_SYMBOLS = [
     "pprts_f2c_init", "pprts_f2c_set_global_optical_properties", "pprts_f2c_solve", "pprts_f2c_get_result",
     "pprts_f2c_destroy", "pprts_f2c_opp_init", "pprts_f2c_opp_get_coeff", "pprts_f2c_opp_destroy",
-    "pprts_f2c_opp_get_info",
+    "pprts_f2c_opp_get_info", "pprts_b200_f2c_set_lut", "pprts_b200_f2c_set_abort_handler",
     "pprts_b200_lut_open", "pprts_b200_lut_close", "pprts_b200_default_config", "pprts_b200_create",
     "pprts_b200_destroy", "pprts_b200_set_angles", "pprts_b200_set_optical_properties", "pprts_b200_solve",
     "pprts_b200_get_result", "pprts_b200_stage_optical_properties", "pprts_b200_set_optical_properties_staged",

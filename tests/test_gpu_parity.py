@@ -293,3 +293,104 @@ def test_energy_closure_and_mirror_symmetry(P, gpu_lut):
     for a, b in ((10., 190.), (100., 280.)):
         for fa, fb in zip(res[a], res[b]):
             assert relerr(fa, fb[:, ::-1, ::-1]) < 1e-5      # tables are mirror symmetric up to fp32 rounding
+
+
+# ---- alternate stream layouts (config C5) and the c_wrapper entry points ----------------------------------------------
+@pytest.fixture(scope="module")
+def luts_810(P, tmp_path_factory):
+    from oracle import binding as ob
+    from tenstream_b200 import lut as L
+    cfg = L.small_test_config(810)
+    paths = L.write_synthetic_lut(cfg, str(tmp_path_factory.mktemp("lut810") / "LUT"))
+    glut, olut = P.Lut(cfg, paths), ob.OracleLut(cfg, paths)
+    yield glut, olut
+    glut.close()
+
+
+@pytest.mark.parametrize("phi0,theta0", [(20., 30.), (110., 50.), (200., 40.), (290., 60.)])
+def test_solver_8_10_vs_oracle(P, luts_810, phi0, theta0):
+    """8 direct streams (4 top quadrants + 2x2 side halves, area_divider 4/2) incl. the dir2dir8 / dir8_to_diff10
+    stream permutations (src/optprop.F90:1148-1184, :1268-1301), on a hill-shaped dz3d"""
+    from oracle import binding as ob
+    glut, olut = luts_810
+    rng = np.random.default_rng(21)
+    Nz, Nx, Ny = 7, 6, 5
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    hill = 1.0 - 0.25 / (1.0 + ((np.arange(Ny) - Ny / 2) / 1.5) ** 2)
+    dz3d = np.full((Nz, Nx, Ny), 55.) * hill[None, None, :]
+    sd = P.sundir_from_angles(phi0, theta0)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, solver=810, dz3d=dz3d, lut=glut, coeff_fp32=False, rtol=1e-10, atol=1e-30)
+    o = ob.OracleSolver(olut, Nz, Nx, Ny, 100., 100., sd, dz3d, solver_id=810, rtol=1e-10, atol=1e-30, diff_solver=1)
+    P.set_optical_properties(s, 0.25, kabs, ksca, g)
+    o.set_optical_properties(0.25, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1200.)
+    assert o.solve(False, True, 1200.) == 0
+    for which in (1, 2, 3):
+        assert relerr(s.coeffs(which), o.coeffs(which), 1e-3) < 1e-12
+    assert relerr(s.state(1), o.state(1), 1e-9) < 1e-9
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b) < 1e-7, name
+    P.destroy_pprts(s); o.destroy()
+
+
+def test_f2c_entry_points(P, small_lut, oracle_lut):
+    """c_wrapper/pprts.c call sequence through the reference's own C symbols (float arrays [Ny][Nx][Nz])"""
+    import ctypes as C
+    from oracle import binding as ob
+    cfg, paths = small_lut
+    lib = P.lib()
+    lut = P.Lut(cfg, paths)
+    lib.pprts_b200_f2c_set_lut.argtypes = [C.c_void_p]
+    lib.pprts_b200_f2c_set_lut(lut._h)
+    Nz, Nx, Ny = 6, 5, 4
+    c_int, c_dbl, c_flt = C.c_int, C.c_double, C.c_float
+    hhl = np.ascontiguousarray(np.arange(Nz, -1, -1) * 80.0, dtype=np.float32)
+    sid, nz, nx, ny, ci = c_int(310), c_int(Nz), c_int(Nx), c_int(Ny), c_int(0)
+    dx, dy, phi0, theta0 = c_dbl(100.), c_dbl(100.), c_flt(135.), c_flt(35.)
+    fp = C.POINTER(c_flt)
+    lib.pprts_f2c_init.argtypes = [c_int] + [C.POINTER(c_int)] * 4 + [C.POINTER(c_dbl)] * 2 + [fp, fp, fp, C.POINTER(c_int)]
+    lib.pprts_f2c_init(0, C.byref(sid), C.byref(nz), C.byref(nx), C.byref(ny), C.byref(dx), C.byref(dy),
+                       hhl.ctypes.data_as(fp), C.byref(phi0), C.byref(theta0), C.byref(ci))
+    rng = np.random.default_rng(2)
+    kabs, ksca, g = [a.astype(np.float32) for a in random_atm(rng, Nz, Nx, Ny)]
+    planck = np.zeros((Nz + 1, Nx, Ny), dtype=np.float32)
+    c_order = lambda a: np.ascontiguousarray(a.transpose(2, 1, 0))       # [k,i,j] -> [Ny][Nx][Nz]
+    alb = c_flt(0.2)
+    lib.pprts_f2c_set_global_optical_properties.argtypes = [c_int] * 3 + [fp] * 5
+    arrs = [c_order(a) for a in (kabs, ksca, g, planck)]
+    lib.pprts_f2c_set_global_optical_properties(Nz, Nx, Ny, C.byref(alb), *[a.ctypes.data_as(fp) for a in arrs])
+    lib.pprts_f2c_solve.argtypes = [c_int, c_flt]
+    lib.pprts_f2c_solve(0, 1000.0)
+    outs = [np.zeros((Ny, Nx, Nz + 1), np.float32), np.zeros((Ny, Nx, Nz + 1), np.float32),
+            np.zeros((Ny, Nx, Nz), np.float32), np.zeros((Ny, Nx, Nz + 1), np.float32)]
+    lib.pprts_f2c_get_result.argtypes = [c_int] * 3 + [fp] * 4
+    lib.pprts_f2c_get_result(Nz, Nx, Ny, *[a.ctypes.data_as(fp) for a in outs])
+    lib.pprts_f2c_destroy.argtypes = [c_int]
+    lib.pprts_f2c_destroy(0)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., ob.sundir_from_angles(135., 35.), np.full(Nz, 80.), coeff_fp32=True,
+                        diff_solver=1)
+    o.set_optical_properties(0.2, kabs.astype(np.float64), ksca.astype(np.float64), g.astype(np.float64))
+    assert o.solve(False, True, 1000.) == 0
+    for name, got, want in zip(("edn", "eup", "abso", "edir"), outs, o.get_result()):
+        assert relerr(got.transpose(2, 1, 0), want, 1e-3) < 2e-4, name        # float32 I/O, default solver tolerances
+    # coefficient probe (pprts_f2c_opp_*, f2c_pprts.F90:591-758)
+    lib.pprts_b200_f2c_set_lut(lut._h)
+    opp, ierr = C.c_void_p(), c_int()
+    lib.pprts_f2c_opp_init.argtypes = [c_int, c_int, C.POINTER(C.c_void_p), C.POINTER(c_int)]
+    lib.pprts_f2c_opp_init(0, 310, C.byref(opp), C.byref(ierr))
+    assert ierr.value == 0
+    lib.pprts_f2c_opp_get_coeff.argtypes = [C.c_void_p] + [c_flt] * 6 + [c_int] * 4 + [fp, C.POINTER(c_int)]
+    for imode, n in ((1, 9), (2, 30), (3, 100)):
+        coeff = np.zeros(n, np.float32)
+        lib.pprts_f2c_opp_get_coeff(opp, 0.37, 0.8, 0.3, 0.6, 25., 48., imode, 1, 0, n, coeff.ctypes.data_as(fp), C.byref(ierr))
+        want = oracle_lut.opp_get_coeff(0.37, 0.8, 0.3, 0.6, 25., 48., imode, True, False)
+        assert ierr.value == 0 and np.abs(coeff - want).max() < 1e-6
+    nd, nf = c_int(), c_int()
+    rngs = [(c_flt * 2)() for _ in range(10)]
+    lib.pprts_f2c_opp_get_info.argtypes = [C.c_void_p, C.POINTER(c_int), C.POINTER(c_int)] + [C.POINTER(c_flt * 2)] * 10 + [C.POINTER(c_int)]
+    lib.pprts_f2c_opp_get_info(opp, C.byref(nd), C.byref(nf), *[C.byref(r) for r in rngs], C.byref(ierr))
+    assert (nd.value, nf.value) == (3, 10) and abs(rngs[0][1] - 100.0) < 1e-6 and abs(rngs[9][1] - 90.0) < 1e-6
+    lib.pprts_f2c_opp_destroy.argtypes = [C.c_void_p, C.POINTER(c_int)]
+    lib.pprts_f2c_opp_destroy(opp, C.byref(ierr))
+    lib.pprts_b200_f2c_set_lut(None)
+    lut.close()

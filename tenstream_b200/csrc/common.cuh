@@ -5,7 +5,10 @@
 //   cell  field  f[(k*Ny + j)*Nx + i]                      k = 0..Nz-1 (TOA first)
 //   level field  f[(k*Ny + j)*Nx + i]                      k = 0..Nz
 //   state        x[d*nlev + (k*Ny + j)*Nx + i]             d = stream (dof), one plane per dof
-//   coefficients c[n*ncp + cell]                           n = dst*Nsrc + src (reference order), ncp = padded ncell
+//   coefficients c[(cell/128)*NP*128 + n*128 + cell%128]   n = dst*Nsrc + src (reference order), NP = planes of the array:
+//                blocked by tiles of 128 consecutive cells, so the NP coefficients of a tile are ONE contiguous run
+//                (51 KB for diff2diff 3_10) that a single bulk copy fetches with perfect DRAM page locality
+//   divergence   cdiv[s*ncp + cell]                        fp64 planes, ncp = ncell padded to the tile
 // A side dof with index (k,i,j) lives on the low-x / low-y face of cell (k,i,j), exactly as in the reference
 // (src/pprts_explicit.F90:398-451); face i+1 of the last column is the periodic image (one GPU) or a ghost.
 #pragma once
@@ -14,13 +17,15 @@
 
 #define PB_MAX_DOF 24
 #define PB_MAX_DIRDOF 8
+#define PB_TILE 128        // cells per coefficient tile
+#define PB_TILE_SHIFT 7
 
 struct Grid {
   int Nz, Nx, Ny;
   long ncol;   // Nx*Ny
   long ncell;  // Nz*ncol
   long nlev;   // (Nz+1)*ncol
-  long ncp;    // ncell padded to a multiple of 32 (plane stride of coefficient arrays)
+  long ncp;    // ncell padded to a multiple of PB_TILE
   double dx, dy;
 };
 
@@ -39,6 +44,48 @@ struct Layout {
 using L310 = Layout<1, 1, 2, 4, false, 1, 1>;
 using L810 = Layout<4, 2, 2, 4, false, 4, 2>;
 using L324 = Layout<1, 1, 8, 8, true, 1, 1>;
+
+// tile-blocked coefficient index: base of cell c in an array of NP planes; coefficient n lives at base + n*PB_TILE
+template <int NP>
+__device__ __forceinline__ long cbase(long c) { return (c >> PB_TILE_SHIFT) * (long)(NP * PB_TILE) + (c & (PB_TILE - 1)); }
+__device__ __forceinline__ long cbase_rt(int np, long c) { return (c >> PB_TILE_SHIFT) * ((long)np * PB_TILE) + (c & (PB_TILE - 1)); }
+
+// fp32 -> fp64 widening on the integer ALU.  cvt.f64.f32 (SASS F2F.F64.F32) runs on the XU pipe at ~4 results/clk/SM
+// on sm_100a; with Nf*Nf conversions per cell it saturated that pipe in the diffuse MatMult (ncu: XU 87 % busy,
+// profiles/r1_matmult_tma.txt).  For a normal, non-negative float the widening is a re-bias of the exponent and a
+// 29-bit shift of the mantissa -- two ALU instructions (SHF + LEA.HI); everything else (zero, subnormal, negative,
+// inf/nan) takes the exact but slow cvt path.  Bit-identical to (double)f for every input.
+__device__ __forceinline__ double widen(float f) {
+  const unsigned int b = __float_as_uint(f);
+  if (__builtin_expect((b - 0x00800000u) < 0x7f000000u, 1))
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+  return (double)f;
+}
+__device__ __forceinline__ double widen(double f) { return f; }
+// Per-tile fast paths of the diffuse MatMult.  The lookup kernel classifies every coefficient tile (k_lookup,
+// `tile_class`): 0 = every entry is a normal positive finite float, 1 = additionally exact +0 entries, 2 = anything
+// else (subnormal, negative, inf/nan).  Class 0 widens with ONE integer multiply-add, b * 2^29 + (896 << 52): the
+// 64-bit product puts mantissa and exponent in place, the addend re-biases the exponent (SASS IMAD.WIDE.U32).
+// Class 1 adds the bias only where b != 0 (ISETP + predicated IADD).  Class 2 uses cvt.  All three are bit-identical
+// to (double)f on the values of their class.
+__device__ __forceinline__ int widen_class(float f) {
+  const unsigned int b = __float_as_uint(f);
+  if ((b - 0x00800000u) < 0x7f000000u) return 0;
+  return b == 0u ? 1 : 2;
+}
+__device__ __forceinline__ double widen_normal(float f) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 0x20000000, %2;" : "=l"(r) : "r"(__float_as_uint(f)), "l"(0x3800000000000000ull));
+  return __longlong_as_double((long long)r);
+}
+__device__ __forceinline__ double widen_normal_or_zero(float f) {
+  const unsigned int b = __float_as_uint(f);
+  unsigned long long r;
+  asm("mul.wide.u32 %0, %1, 0x20000000;" : "=l"(r) : "r"(b));
+  unsigned int hi = (unsigned int)(r >> 32);
+  if (b) hi += 0x38000000u;
+  return __hiloint2double((int)hi, (int)(unsigned int)r);
+}
 
 __device__ __forceinline__ long lidx(const Grid &g, int k, int j, int i) { return ((long)k * g.Ny + j) * g.Nx + i; }
 __device__ __forceinline__ int wrap_p(int i, int n) { return (i + 1 == n) ? 0 : i + 1; }

@@ -71,7 +71,7 @@ __global__ void k_coeff_to_host_layout(Grid g, int nc, const CT *__restrict__ c,
   int q = (int)(n / g.ncell);
   long l = n % g.ncell;
   int i = (int)(l % g.Nx), j = (int)((l / g.Nx) % g.Ny), k = (int)(l / g.ncol);
-  out[q + (long)nc * (k + (long)g.Nz * (i + (long)g.Nx * j))] = (double)c[(long)q * g.ncp + l];
+  out[q + (long)nc * (k + (long)g.Nz * (i + (long)g.Nx * j))] = (double)c[cbase_rt(nc, l) + (long)q * PB_TILE];
 }
 
 // =================================================================================================================
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128)
 k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *__restrict__ kabs,
          const double *__restrict__ ksca, const double *__restrict__ gg, const double *__restrict__ dz,
          CT *__restrict__ d2d, CT *__restrict__ d2f, CT *__restrict__ f2f, double *__restrict__ cdiv_dir,
-         double *__restrict__ cdiv_diff) {
+         double *__restrict__ cdiv_diff, unsigned char *__restrict__ tile_class) {
   constexpr int Nd = L::Nd, Nf = L::Nf;
   long c = (long)kstart * g.ncol + (long)blockIdx.x * blockDim.x + threadIdx.x;  // 3-D layers start at kstart
   if (c >= g.ncell) return;
@@ -246,9 +246,11 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
   lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
   InterpPlan p;
   make_plan(lut, sample, p);
+  const long cb_ff = cbase<Nf * Nf>(c), cb_dd = cbase<Nd * Nd>(c), cb_df = cbase<Nd * Nf>(c);
 
   // ---- diff2diff: one dst row (Nf contiguous fp32 per corner) at a time
   double colsum[Nf];
+  int wclass = 0;  // widening class of this cell's diff2diff entries (common.cuh widen_class)
 #pragma unroll
   for (int s = 0; s < Nf; ++s) colsum[s] = 0.0;
   for (int dst = 0; dst < Nf; ++dst) {
@@ -264,12 +266,14 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
 #pragma unroll
     for (int s = 0; s < Nf; ++s) {
       CT st = (CT)acc[s];
-      f2f[(long)(dst * Nf + s) * g.ncp + c] = st;
+      if (sizeof(CT) == 4) wclass = max(wclass, widen_class((float)st));
+      f2f[cb_ff + (dst * Nf + s) * PB_TILE] = st;
       colsum[s] += (double)st;  // sum over dst in ascending order, as calc_flx_div does (src/pprts.F90:5343)
     }
   }
 #pragma unroll
   for (int s = 0; s < Nf; ++s) cdiv_diff[(long)s * g.ncp + c] = 1.0 - colsum[s];
+  if (wclass > 0) atomicMax(reinterpret_cast<unsigned int *>(tile_class) + (c >> PB_TILE_SHIFT), (unsigned int)wclass);
 
   if (!lsolar) return;
   // ---- dir2dir / dir2diff from the (phi,theta)-contracted fp64 tables, stream permutation applied on the fly
@@ -289,7 +293,7 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
 #pragma unroll
     for (int s = 0; s < Nd; ++s) {
       CT st = (CT)acc[s];
-      d2d[(long)(dst * Nd + s) * g.ncp + c] = st;
+      d2d[cb_dd + (dst * Nd + s) * PB_TILE] = st;
       sum1[s] += (double)st;
     }
   }
@@ -306,7 +310,7 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
 #pragma unroll
     for (int s = 0; s < Nd; ++s) {
       CT st = (CT)acc[s];
-      d2f[(long)(dst * Nd + s) * g.ncp + c] = st;
+      d2f[cb_df + (dst * Nd + s) * PB_TILE] = st;
       sum2[s] += (double)st;
     }
   }
@@ -424,12 +428,12 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
         for (int d = 0; d < Nds; ++d) src[Ndt + d] = xold[(long)(Ndt + d) * g.nlev + lk + o_xin];
 #pragma unroll
         for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = xold[(long)(Ndt + Nds + d) * g.nlev + lk + o_yin];
-        const long c = lk + o_own;
+        const long cb = cbase<Nd * Nd>(lk + o_own);
 #pragma unroll
         for (int dst = 0; dst < Nd; ++dst) {
           double acc = 0.0;
 #pragma unroll
-          for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)d2d[(long)(dst * Nd + s) * g.ncp + c];
+          for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)d2d[cb + (dst * Nd + s) * PB_TILE];
           long q;
           if (dst < Ndt) { q = (long)dst * g.nlev + lk1 + o_own; top[dst] = acc; }
           else if (dst < Ndt + Nds) q = (long)dst * g.nlev + lk + o_xout;
@@ -486,6 +490,7 @@ k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, 
       }
     } else {
       double src[Nd];
+      const long cb_df = cbase<Nd * Nf>(c);
 #pragma unroll
       for (int d = 0; d < Ndt; ++d) src[d] = edir[(long)d * g.nlev + l_own];
 #pragma unroll
@@ -496,7 +501,7 @@ k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, 
       for (int dst = 0; dst < Nf; ++dst) {
         double acc = 0.0;
 #pragma unroll
-        for (int s = 0; s < Nd; ++s) acc += src[s] * (double)d2f[(long)(dst * Nd + s) * g.ncp + c];
+        for (int s = 0; s < Nd; ++s) acc += src[s] * widen(d2f[cb_df + (dst * Nd + s) * PB_TILE]);
         long q;
         if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
         else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
@@ -597,84 +602,114 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdi
 // streams the Nf*Nf coefficient planes once (fp32 storage: 400 B/cell for 3_10) and writes the Nf outgoing streams,
 // each of which has exactly one producer.  NDOT weighted dot products with y are fused (rh.v, t.s, t.t of BiCGStab).
 // =================================================================================================================
-// per-cell body shared by the plain and the TMA-staged kernel; COEF(n) returns coefficient n = dst*Nf+src of cell c
+// The per-cell work is split in two phases so that the TMA-staged kernel can have the state loads of the NEXT tile in
+// flight while it computes the current one:
+//   matmult_load : the 2*Nf state values a cell touches -- xs[d] at the face where stream d ENTERS the cell, xd[d] at
+//                  the face where it LEAVES (its destination row) -- the same set serves 3-D cells, 1-D cells, the
+//                  TOA rows and the albedo row
+//   matmult_emit : y = xd - sum_s coef(dst,s) xs, stores + fused dot products; COEF(n) returns coefficient dst*Nf+src
+template <class L>
+struct MatIn {
+  double xs[L::Nf], xd[L::Nf];
+  double wd[L::Nf];  // dot-product weight w0 at the destination row of stream d (NDOT > 0)
+};
+template <class L>
+struct CellIdx {
+  long l_own, l_dn, l_xp, l_yp;
+  int i, j, k;
+};
+template <class L>
+__device__ __forceinline__ CellIdx<L> cell_index(const Grid &g, long c) {
+  CellIdx<L> ci;
+  ci.i = (int)(c % g.Nx); ci.j = (int)((c / g.Nx) % g.Ny); ci.k = (int)(c / g.ncol);
+  const int ip = wrap_p(ci.i, g.Nx), jp = wrap_p(ci.j, g.Ny);
+  ci.l_own = c; ci.l_dn = c + g.ncol;
+  ci.l_xp = lidx(g, ci.k, ci.j, ip); ci.l_yp = lidx(g, ci.k, jp, ci.i);
+  return ci;
+}
+template <class L, int NDOT>
+__device__ __forceinline__ void matmult_load(const Grid &g, const CellIdx<L> &ci, const double *__restrict__ x,
+                                             const double *__restrict__ w0, MatIn<L> &in) {
+  constexpr int Nft = L::Nft, Nfs = L::Nfs;
+#pragma unroll
+  for (int d = 0; d < Nft; ++d) {
+    const long qs = (long)d * g.nlev + (L::top_in(d) ? ci.l_own : ci.l_dn);
+    const long qd = (long)d * g.nlev + (L::top_in(d) ? ci.l_dn : ci.l_own);
+    in.xs[d] = x[qs]; in.xd[d] = x[qd];
+    if (NDOT > 0) in.wd[d] = w0[qd];
+  }
+#pragma unroll
+  for (int d = 0; d < Nfs; ++d) {
+    const long qs = (long)(Nft + d) * g.nlev + (L::side_in(d) ? ci.l_own : ci.l_xp);
+    const long qd = (long)(Nft + d) * g.nlev + (L::side_in(d) ? ci.l_xp : ci.l_own);
+    in.xs[Nft + d] = x[qs]; in.xd[Nft + d] = x[qd];
+    if (NDOT > 0) in.wd[Nft + d] = w0[qd];
+  }
+#pragma unroll
+  for (int d = 0; d < Nfs; ++d) {
+    const long qs = (long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? ci.l_own : ci.l_yp);
+    const long qd = (long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? ci.l_yp : ci.l_own);
+    in.xs[Nft + Nfs + d] = x[qs]; in.xd[Nft + Nfs + d] = x[qd];
+    if (NDOT > 0) in.wd[Nft + Nfs + d] = w0[qd];
+  }
+}
 template <class L, int NDOT, class COEF>
-__device__ __forceinline__ void matmult_cell(const Grid &g, int n1d, COEF coef, const double *__restrict__ a11,
+__device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, const CellIdx<L> &ci,
+                                             const MatIn<L> &in, const double *__restrict__ a11,
                                              const double *__restrict__ a12, const double *__restrict__ albedo,
                                              const double *__restrict__ x, double *__restrict__ y,
-                                             const double *__restrict__ w0, long c, double *dots) {
+                                             const double *__restrict__ w0, double *dots) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   // NDOT == 1: dots[0] = sum w0*y ; NDOT == 2: dots[0] = sum y*w0, dots[1] = sum y*y
-  auto emit = [&](long q, double val) {
+  auto emit = [&](long q, double val) {  // rare rows: weight loaded on the spot
     y[q] = val;
     if (NDOT >= 1) dots[0] += val * w0[q];
     if (NDOT >= 2) dots[1] += val * val;
   };
-  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
-  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
-  const long l_own = lidx(g, k, j, i), l_dn = l_own + g.ncol;
-  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+  auto emit_w = [&](long q, double val, double w) {  // destination rows: weight prefetched with the state
+    y[q] = val;
+    if (NDOT >= 1) dots[0] += val * w;
+    if (NDOT >= 2) dots[1] += val * val;
+  };
+  const long l_own = ci.l_own, l_dn = ci.l_dn, l_xp = ci.l_xp, l_yp = ci.l_yp;
+  const int k = ci.k;
   if (k < n1d) {
-    const double t = a11[c], r = a12[c];
+    const double t = a11[l_own], r = a12[l_own];
 #pragma unroll
-    for (int d = 0; d < Nft; ++d) {
-      if (L::top_in(d)) {  // edn: xb(k+1) -= x(d,k)*a11 ; -= x(inv,k+1)*a12
-        long q = (long)d * g.nlev + l_dn;
-        double acc = 0.0;
-        acc = acc - x[(long)d * g.nlev + l_own] * t;
-        acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_dn] * r;
-        emit(q, acc + x[q]);
-      } else {
-        long q = (long)d * g.nlev + l_own;
-        double acc = 0.0;
-        acc = acc - x[(long)d * g.nlev + l_dn] * t;
-        acc = acc - x[(long)L::inv_dof(d) * g.nlev + l_own] * r;
-        emit(q, acc + x[q]);
-      }
+    for (int d = 0; d < Nft; ++d) {  // xb(dst) = x(dst) - x(d, other side)*a11 - x(inv_dof, same level)*a12
+      const long q = (long)d * g.nlev + (L::top_in(d) ? l_dn : l_own);
+      double acc = 0.0;
+      acc = acc - in.xs[d] * t;
+      acc = acc - in.xs[L::inv_dof(d)] * r;
+      emit_w(q, acc + in.xd[d], in.wd[d]);
     }
 #pragma unroll
-    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+    for (int d = Nft; d < Nf; ++d) {
+      const bool inw = L::side_in((d - Nft) % Nfs);
+      emit((long)d * g.nlev + l_own, inw ? in.xs[d] : in.xd[d]);
+    }
   } else {
-    double xs[Nf], xd[Nf];
-#pragma unroll
-    for (int d = 0; d < Nft; ++d) {
-      xs[d] = x[(long)d * g.nlev + (L::top_in(d) ? l_own : l_dn)];
-      xd[d] = x[(long)d * g.nlev + (L::top_in(d) ? l_dn : l_own)];
-    }
-#pragma unroll
-    for (int d = 0; d < Nfs; ++d) {
-      xs[Nft + d] = x[(long)(Nft + d) * g.nlev + (L::side_in(d) ? l_own : l_xp)];
-      xd[Nft + d] = x[(long)(Nft + d) * g.nlev + (L::side_in(d) ? l_xp : l_own)];
-    }
-#pragma unroll
-    for (int d = 0; d < Nfs; ++d) {
-      xs[Nft + Nfs + d] = x[(long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? l_own : l_yp)];
-      xd[Nft + Nfs + d] = x[(long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? l_yp : l_own)];
-    }
 #pragma unroll
     for (int dst = 0; dst < Nf; ++dst) {
       double acc = 0.0;
 #pragma unroll
-      for (int s = 0; s < Nf; ++s) acc = acc - xs[s] * coef(dst * Nf + s);
+      for (int s = 0; s < Nf; ++s) acc = acc - in.xs[s] * coef(dst * Nf + s);
       long q;
       if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
       else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
       else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
       q += (long)dst * g.nlev;
-      emit(q, acc + xd[dst]);
+      emit_w(q, acc + in.xd[dst], in.wd[dst]);
     }
   }
   if (k == 0) {  // rows without a producing cell: incoming diffuse at TOA
 #pragma unroll
-    for (int d = 0; d < Nft; ++d) if (L::top_in(d)) { long q = (long)d * g.nlev + l_own; emit(q, x[q]); }
+    for (int d = 0; d < Nft; ++d) if (L::top_in(d)) emit((long)d * g.nlev + l_own, in.xs[d]);
   }
   if (k == g.Nz - 1) {  // albedo row (src/pprts_shell.F90:500-505) and the unused side dofs below the ground
-    const double alb = albedo[(long)j * g.Nx + i];
+    const double alb = albedo[(long)ci.j * g.Nx + ci.i];
 #pragma unroll
-    for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) {
-      long q = (long)d * g.nlev + l_dn;
-      emit(q, x[q] - x[(long)L::inv_dof(d) * g.nlev + l_dn] * alb);
-    }
+    for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) emit((long)d * g.nlev + l_dn, in.xs[d] - in.xd[L::inv_dof(d)] * alb);
 #pragma unroll
     for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, x[q]); }
   }
@@ -691,20 +726,23 @@ k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
 #pragma unroll
   for (int n = 0; n < NV; ++n) dots[n] = 0.0;
   if (c < g.ncell) {
-    auto coef = [&](int n) { return (double)T[(long)n * g.ncp + c]; };
-    matmult_cell<L, NDOT>(g, n1d, coef, a11, a12, albedo, x, y, w0, c, dots);
+    const long cb = cbase<L::Nf * L::Nf>(c);
+    auto coef = [&](int n) { return widen(T[cb + n * PB_TILE]); };
+    const CellIdx<L> ci = cell_index<L>(g, c);
+    MatIn<L> in;
+    matmult_load<L, NDOT>(g, ci, x, w0, in);
+    matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
   }
   if (NDOT > 0) grid_reduce_sum<NV>(dots, partials, counter, out_dots);
 }
 
-// ---- TMA-staged variant (fp32 coefficients) ---------------------------------------------------------------------
-// The plain kernel is latency-bound: 100 dependent-free but register-hungry 4-byte loads per thread leave only
-// ~46 % of HBM bandwidth in flight (profiles/r1_matmult.txt: "No Eligible" 85 %).  Here a persistent CTA per tile of
-// TILE consecutive cells lets ONE thread fetch the whole [Nf*Nf planes x TILE cells] box with a single TMA tensor
-// copy (cp.async.bulk.tensor.2d over the coefficient array viewed as a 2-D [plane][cell] tensor) into a
-// double-buffered shared-memory stage, completion tracked by an mbarrier; the copy of tile t+1 is in flight while
-// tile t is being consumed, independent of register pressure.  (Issuing the planes as Nf*Nf separate 512-byte
-// cp.async.bulk copies was measured slower than the plain kernel: the single issuing thread becomes the bottleneck.)
+// ---- bulk-copy staged variant (fp32 coefficients) ---------------------------------------------------------------
+// The plain kernel is latency-bound: 100 independent but register-hungry 4-byte loads per thread leave only ~46 % of
+// HBM bandwidth in flight (profiles/r1_matmult.txt).  Here a persistent CTA walks over tiles of PB_TILE consecutive
+// cells.  Because the coefficient array is tile-blocked, the Nf*Nf planes of a tile are one contiguous 51 KB run: ONE
+// thread fetches it with a single cp.async.bulk (TMA engine, SASS UBLKCP) into a double-buffered shared-memory stage,
+// completion tracked by an mbarrier.  The copy of tile t+1 AND the state loads of tile t+1 (register prefetch) are in
+// flight while tile t is being computed.
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -733,25 +771,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
       : "memory");
 }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int c0, int c1, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <class L, int NDOT, int TILE>
-__global__ void __launch_bounds__(TILE)
-k_matmult_tma(Grid g, int n1d, long ntiles, const __grid_constant__ CUtensorMap tmap, const double *__restrict__ a11,
+// NSTAGE = 2, PREFETCH: double-buffered stage + register prefetch of the next tile's state, 2 CTAs/SM
+// NSTAGE = 1          : single stage, state loads issued together with the bulk copy, 4 CTAs/SM hide each other's waits
+template <class L, int NDOT, int NSTAGE, bool PREFETCH>
+__global__ void __launch_bounds__(PB_TILE, (NSTAGE == 1) ? 4 : 2)
+k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
+              const unsigned int *__restrict__ tile_class, const double *__restrict__ a11,
               const double *__restrict__ a12, const double *__restrict__ albedo, const double *__restrict__ x,
               double *__restrict__ y, const double *__restrict__ w0, double *partials, unsigned int *counter,
               double *out_dots) {
   constexpr int NP = L::Nf * L::Nf;
   constexpr int NV = (NDOT > 0) ? NDOT : 1;
-  constexpr unsigned int STAGE_BYTES = NP * TILE * sizeof(float);
+  constexpr unsigned int STAGE_BYTES = NP * PB_TILE * sizeof(float);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar[2];
-  float *stage0 = reinterpret_cast<float *>(smem_raw);
-  float *stage1 = reinterpret_cast<float *>(smem_raw + STAGE_BYTES);
   const int tid = threadIdx.x;
   const long c1d = (long)n1d * g.ncol;  // cells below this index are in 1-D layers and need no plane data
   if (tid == 0) {
@@ -760,32 +793,88 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const __grid_constant__ CUtensorMap 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  auto stage = [&](int st) { return reinterpret_cast<float *>(smem_raw + (size_t)st * STAGE_BYTES); };
   auto issue = [&](long tile, int st) {
-    const long c0 = tile * TILE;
+    const long c0 = tile * PB_TILE;
     unsigned long long *b = &bar[st];
-    if (c0 + TILE <= c1d) { mbar_arrive(b); return; }
-    float *dst = st ? stage1 : stage0;
+    if (c0 + PB_TILE <= c1d) { mbar_arrive(b); return; }
     mbar_expect_tx(b, STAGE_BYTES);
-    tma_load_2d(dst, &tmap, (int)c0, 0, b);  // one box: NP planes x TILE cells
+    bulk_g2s(stage(st), T + tile * (long)(NP * PB_TILE), STAGE_BYTES, b);  // one contiguous run
+  };
+  auto compute = [&](long tile, int st, unsigned int cls, const CellIdx<L> &ci, const MatIn<L> &in, double *dots) {
+    const float *sp = stage(st) + tid;
+    if (__builtin_expect(cls == 0, 1)) {  // CTA-uniform
+      auto coef = [&](int n) { return widen_normal(sp[n * PB_TILE]); };
+      matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
+    } else if (cls == 1) {
+      auto coef = [&](int n) { return widen_normal_or_zero(sp[n * PB_TILE]); };
+      matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
+    } else {
+      auto coef = [&](int n) { return (double)sp[n * PB_TILE]; };
+      matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
+    }
   };
   double dots[NV];
 #pragma unroll
   for (int n = 0; n < NV; ++n) dots[n] = 0.0;
-  if (tid == 0 && (long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
-  unsigned int it = 0;
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int st = it & 1;
-    const unsigned int parity = (it >> 1) & 1;
-    const long next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue(next, st ^ 1);
-    const long c = tile * TILE + tid;
-    mbar_wait(&bar[st], parity);
-    if (c < g.ncell) {
-      const float *sp = (st ? stage1 : stage0) + tid;
-      auto coef = [&](int n) { return (double)sp[n * TILE]; };
-      matmult_cell<L, NDOT>(g, n1d, coef, a11, a12, albedo, x, y, w0, c, dots);
+  long tile = blockIdx.x;
+  if (NSTAGE == 1) {
+    unsigned int it = 0;
+    for (; tile < ntiles; tile += gridDim.x, ++it) {
+      if (tid == 0) issue(tile, 0);
+      const long c = tile * PB_TILE + tid;
+      const unsigned int cls = tile_class[tile];
+      CellIdx<L> ci;
+      MatIn<L> in;
+      if (c < g.ncell) {  // state loads travel together with the bulk copy
+        ci = cell_index<L>(g, c);
+        matmult_load<L, NDOT>(g, ci, x, w0, in);
+      }
+      mbar_wait(&bar[0], it & 1);
+      if (c < g.ncell) compute(tile, 0, cls, ci, in, dots);
+      __syncthreads();  // the stage is refilled at the top of the next iteration
     }
-    __syncthreads();  // stage st may be refilled from the next iteration on
+  } else {
+    if (tid == 0 && tile < ntiles) issue(tile, 0);
+    CellIdx<L> ci, ci_n;
+    MatIn<L> in, in_n;
+    unsigned int cls = 0, cls_n = 0;
+    if (PREFETCH) {
+      if (tile < ntiles) cls = tile_class[tile];
+      if (tile < ntiles && tile * PB_TILE + tid < g.ncell) {
+        ci = cell_index<L>(g, tile * PB_TILE + tid);
+        matmult_load<L, NDOT>(g, ci, x, w0, in);
+      }
+    }
+    unsigned int it = 0;
+    for (; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const unsigned int parity = (it >> 1) & 1;
+      const long next = tile + gridDim.x;
+      if (tid == 0 && next < ntiles) issue(next, st ^ 1);
+      const long c = tile * PB_TILE + tid, cn = next * PB_TILE + tid;
+      const bool have_next = next < ntiles && cn < g.ncell;
+      if (PREFETCH) {
+        if (next < ntiles) cls_n = tile_class[next];
+        if (have_next) {  // register prefetch of the next tile's state
+          ci_n = cell_index<L>(g, cn);
+          matmult_load<L, NDOT>(g, ci_n, x, w0, in_n);
+        }
+      } else {
+        cls = tile_class[tile];
+        if (c < g.ncell) {
+          ci = cell_index<L>(g, c);
+          matmult_load<L, NDOT>(g, ci, x, w0, in);
+        }
+      }
+      mbar_wait(&bar[st], parity);
+      if (c < g.ncell) compute(tile, st, cls, ci, in, dots);
+      __syncthreads();  // stage st may be refilled from the next iteration on
+      if (PREFETCH) {
+        cls = cls_n;
+        if (have_next) { ci = ci_n; in = in_n; }
+      }
+    }
   }
   if (NDOT > 0) grid_reduce_sum<NV>(dots, partials, counter, out_dots);
 }
@@ -799,8 +888,12 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const __grid_constant__ CUtensorMap 
 // Jacobi cannot (diag(A) = 1, src/pprts.F90:1294-1308), and it is embarrassingly parallel over columns.
 // Only for layouts with one up/down pair of top streams (3_10, 8_10).
 // =================================================================================================================
+// All three kernels are one thread per column marching through the levels; the recurrences are short dependent
+// chains, so the loads of level k-1 (resp. k+1) are issued into registers BEFORE level k is computed (software
+// pipelining, depth 1) to keep two levels of loads in flight per thread; blocks of 64 threads balance the 148 SMs.
+#define PREC_BLOCK 64
 template <class L, class CT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
              const double *__restrict__ a12, const double *__restrict__ albedo, double *__restrict__ R,
              double *__restrict__ inv) {
@@ -814,8 +907,9 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
     double tuu, tdu, tdd, tud;
     if (k < n1d) { tuu = tdd = a11[c]; tdu = tud = a12[c]; }
     else {
-      tuu = (double)T[(long)(0 * Nf + 0) * g.ncp + c]; tdu = (double)T[(long)(0 * Nf + 1) * g.ncp + c];
-      tud = (double)T[(long)(1 * Nf + 0) * g.ncp + c]; tdd = (double)T[(long)(1 * Nf + 1) * g.ncp + c];
+      const long cb = cbase<Nf * Nf>(c);
+      tuu = (double)T[cb + (0 * Nf + 0) * PB_TILE]; tdu = (double)T[cb + (0 * Nf + 1) * PB_TILE];
+      tud = (double)T[cb + (1 * Nf + 0) * PB_TILE]; tdd = (double)T[cb + (1 * Nf + 1) * PB_TILE];
     }
     double iv = 1.0 / (1.0 - tud * Rn);
     Rn = tdu + tuu * Rn * tdd * iv;
@@ -824,10 +918,46 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
   }
 }
 
-// upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied.  If `upd` is set the input vector is first formed
-// as r <- r + beta*(p_old - omega*v) (the BiCGStab direction update fused in), and written back to p.
+// upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied
 template <class L, class CT>
-__global__ void __launch_bounds__(128)
+struct PrecUpIn {
+  double fU, fD, tuu, tud, iv, Rc;
+  double rs[2 * L::Nfs];         // all side dofs of the level (1-D layers copy them, 3-D layers use the inward ones)
+  CT t0[L::Nfs], t1[L::Nfs];     // T(0, inward side), T(1, inward side)
+};
+template <class L, class CT>
+__device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
+                                             const double *__restrict__ a11, const double *__restrict__ a12,
+                                             const double *__restrict__ R, const double *__restrict__ inv,
+                                             const double *__restrict__ r, PrecUpIn<L, CT> &in) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+  in.fU = r[0 * g.nlev + c];
+  in.fD = r[1 * g.nlev + l1];
+  in.iv = inv[c];
+  in.Rc = R[c];
+  if (k < n1d) {
+    in.tuu = a11[c]; in.tud = a12[c];
+#pragma unroll
+    for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+  } else {
+    const long cb = cbase<Nf * Nf>(c);
+    in.tuu = (double)T[cb + (0 * Nf + 0) * PB_TILE];
+    in.tud = (double)T[cb + (1 * Nf + 0) * PB_TILE];
+    int q = 0;
+#pragma unroll
+    for (int d = 0; d < 2 * Nfs; ++d) {
+      if (L::side_in(d % Nfs)) {
+        in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+        in.t0[q] = T[cb + (0 * Nf + Nft + d) * PB_TILE];
+        in.t1[q] = T[cb + (1 * Nf + Nft + d) * PB_TILE];
+        ++q;
+      }
+    }
+  }
+}
+template <class L, class CT>
+__global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
           const double *__restrict__ R, const double *__restrict__ inv, const double *__restrict__ r,
           double *__restrict__ z) {
@@ -841,78 +971,117 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
 #pragma unroll
   for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + lz] = r[(long)d * g.nlev + lz];
   double Rn = R[lz];
+  PrecUpIn<L, CT> cur, nxt;
+  prec_up_load<L, CT>(g, n1d, g.Nz - 1, col, T, a11, a12, R, inv, r, cur);
   for (int k = g.Nz - 1; k >= 0; --k) {
+    if (k > 0) prec_up_load<L, CT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-    double fU = r[0 * g.nlev + c], fD = r[1 * g.nlev + l1];
-    double tuu, tud;
+    double fU = cur.fU, fD = cur.fD;
     if (k < n1d) {
-      tuu = a11[c]; tud = a12[c];
 #pragma unroll
-      for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + c] = r[(long)d * g.nlev + c];
+      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
     } else {
-      tuu = (double)T[(long)(0 * Nf + 0) * g.ncp + c];
-      tud = (double)T[(long)(1 * Nf + 0) * g.ncp + c];
+      int q = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
-        const int dof = Nft + d;
-        const bool inw = L::side_in(d % Nfs);
-        if (inw) {
-          double rs = r[(long)dof * g.nlev + c];
-          z[(long)dof * g.nlev + c] = rs;
-          fU = fma((double)T[(long)(0 * Nf + dof) * g.ncp + c], rs, fU);
-          fD = fma((double)T[(long)(1 * Nf + dof) * g.ncp + c], rs, fD);
+        if (L::side_in(d % Nfs)) {
+          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
+          fU = fma(widen(cur.t0[q]), cur.rs[d], fU);
+          fD = fma(widen(cur.t1[q]), cur.rs[d], fD);
+          ++q;
         }
       }
     }
-    const double iv = inv[c];
-    S = fU + tuu * (S + Rn * (tud * S + fD) * iv);
-    Rn = R[c];
+    S = fU + cur.tuu * (S + Rn * (cur.tud * S + fD) * cur.iv);
+    Rn = cur.Rc;
     z[0 * g.nlev + c] = S;
     z[1 * g.nlev + l1] = fD;
+    if (k > 0) cur = nxt;
   }
   z[1 * g.nlev + col] = r[1 * g.nlev + col];  // f_D(0) = r_D(0)
 }
 
 template <class L, class CT>
-__global__ void __launch_bounds__(128)
+struct PrecDownIn {
+  double tdd, tud, S1, fD, iv, R1;
+  double rsd[2 * L::Nfs];                 // r of all side dofs at the cell
+  CT tt[L::Nfs][2 + L::Nfs];              // per outward dof: T(dof,0), T(dof,1), T(dof, inward sides)
+};
+template <class L, class CT>
+__device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
+                                               const double *__restrict__ a11, const double *__restrict__ a12,
+                                               const double *__restrict__ R, const double *__restrict__ inv,
+                                               const double *__restrict__ r, const double *z, PrecDownIn<L, CT> &in) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+  in.S1 = z[0 * g.nlev + l1];
+  in.fD = z[1 * g.nlev + l1];
+  in.iv = inv[c];
+  in.R1 = R[l1];
+  if (k < n1d) { in.tdd = a11[c]; in.tud = a12[c]; }
+  else {
+    const long cb = cbase<Nf * Nf>(c);
+    in.tdd = (double)T[cb + (1 * Nf + 1) * PB_TILE];
+    in.tud = (double)T[cb + (1 * Nf + 0) * PB_TILE];
+#pragma unroll
+    for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
+    int o = 0;
+#pragma unroll
+    for (int d = 0; d < 2 * Nfs; ++d) {
+      if (!L::side_in(d % Nfs)) {
+        const int dof = Nft + d;
+        in.tt[o][0] = T[cb + (dof * Nf + 0) * PB_TILE];
+        in.tt[o][1] = T[cb + (dof * Nf + 1) * PB_TILE];
+        int q = 0;
+#pragma unroll
+        for (int s = 0; s < 2 * Nfs; ++s)
+          if (L::side_in(s % Nfs)) { in.tt[o][2 + q] = T[cb + (dof * Nf + Nft + s) * PB_TILE]; ++q; }
+        ++o;
+      }
+    }
+  }
+}
+template <class L, class CT>
+__global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const double *__restrict__ R, const double *__restrict__ inv,
-            const double *__restrict__ r, double *__restrict__ z) {
-  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+            const double *__restrict__ r, double *z) {
+  constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
   double D = z[1 * g.nlev + col];
   double U = R[col] * D + z[0 * g.nlev + col];
   z[0 * g.nlev + col] = U;
+  PrecDownIn<L, CT> cur, nxt;
+  prec_down_load<L, CT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cur);
   for (int k = 0; k < g.Nz; ++k) {
+    // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
+    if (k + 1 < g.Nz) prec_down_load<L, CT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-    double tdd, tud;
-    if (k < n1d) { tdd = a11[c]; tud = a12[c]; }
-    else { tdd = (double)T[(long)(1 * Nf + 1) * g.ncp + c]; tud = (double)T[(long)(1 * Nf + 0) * g.ncp + c]; }
-    const double S1 = z[0 * g.nlev + l1], fD = z[1 * g.nlev + l1];
-    const double D1 = (tdd * D + tud * S1 + fD) * inv[c];
-    const double U1 = R[l1] * D1 + S1;
+    const double S1 = cur.S1;
+    const double D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
+    const double U1 = cur.R1 * D1 + S1;
     if (k >= n1d) {  // outgoing side streams through the column's own faces
-      double rin[2 * Nfs];
-#pragma unroll
-      for (int d = 0; d < 2 * Nfs; ++d) rin[d] = L::side_in(d % Nfs) ? r[(long)(Nft + d) * g.nlev + c] : 0.0;
+      int o = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (!L::side_in(d % Nfs)) {
-          const int dof = Nft + d;
-          double acc = r[(long)dof * g.nlev + c];
-          acc = fma((double)T[(long)(dof * Nf + 0) * g.ncp + c], U1, acc);
-          acc = fma((double)T[(long)(dof * Nf + 1) * g.ncp + c], D, acc);
+          double acc = cur.rsd[d];
+          acc = fma(widen(cur.tt[o][0]), U1, acc);
+          acc = fma(widen(cur.tt[o][1]), D, acc);
+          int q = 0;
 #pragma unroll
           for (int s = 0; s < 2 * Nfs; ++s)
-            if (L::side_in(s % Nfs)) acc = fma((double)T[(long)(dof * Nf + Nft + s) * g.ncp + c], rin[s], acc);
-          z[(long)dof * g.nlev + c] = acc;
+            if (L::side_in(s % Nfs)) { acc = fma(widen(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
+          z[(long)(Nft + d) * g.nlev + c] = acc;
+          ++o;
         }
       }
     }
     z[0 * g.nlev + l1] = U1;
     z[1 * g.nlev + l1] = D1;
     D = D1;
+    if (k + 1 < g.Nz) cur = nxt;
   }
 }
 

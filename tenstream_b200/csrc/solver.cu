@@ -209,6 +209,8 @@ struct pprts_b200_solver {
   double *a11 = nullptr, *a12 = nullptr, *a13 = nullptr, *a23 = nullptr, *a33 = nullptr;
   void *d2d = nullptr, *d2f = nullptr, *f2f = nullptr;
   double *cdiv_dir = nullptr, *cdiv_diff = nullptr;
+  unsigned int *tile_class = nullptr;  // per coefficient tile: widening class of its diff2diff entries (common.cuh)
+  int mm_variant = 2;  // 0: 2 stages + register prefetch, 1: 2 stages, 2: 1 stage x 4 CTAs/SM (fastest measured)
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
   bool prec_ready = false;
@@ -241,7 +243,6 @@ struct pprts_b200_solver {
   int nranks = 1, rank = 0;
   int num_sms = 148;
   bool use_tma = true;
-  CUtensorMap tmap_f2f;
 };
 
 static cudaEvent_t get_event(pprts_b200_solver *s) {
@@ -290,30 +291,6 @@ static void collect_events(pprts_b200_solver *s) {
 static inline unsigned int nblk(long n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 static const int VEC_BLOCK = 256;
 static inline unsigned int vec_grid(long n) { return (unsigned int)std::min<long>((n + VEC_BLOCK - 1) / VEC_BLOCK, 148L * 16); }
-
-// 2-D tensor map over a coefficient array viewed as [nplanes][ncp] fp32, box = [nplanes][tile] (one TMA per tile).
-// cuTensorMapEncodeTiled is fetched from the driver at run time: no link-time dependency on libcuda.
-typedef CUresult (*fn_cuTensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                              CUtensorMapFloatOOBfill);
-static int make_plane_tensor_map(CUtensorMap *tm, void *base, int nplanes, long ncp, int tile) {
-  static fn_cuTensorMapEncodeTiled enc = nullptr;
-  if (!enc) {
-    cudaDriverEntryPointQueryResult q;
-    void *p = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 1;
-    enc = (fn_cuTensorMapEncodeTiled)p;
-  }
-  if (nplanes > 256 || tile > 256) return 2;
-  cuuint64_t dims[2] = {(cuuint64_t)ncp, (cuuint64_t)nplanes};
-  cuuint64_t strides[1] = {(cuuint64_t)ncp * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)tile, (cuuint32_t)nplanes};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 3;
-}
 
 extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   memset(cfg, 0, sizeof(*cfg));
@@ -431,11 +408,12 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   Grid &g = s->g;
   g.Nz = cfg->Nz; g.Nx = cfg->Nx; g.Ny = cfg->Ny;
   g.ncol = (long)g.Nx * g.Ny; g.ncell = g.ncol * g.Nz; g.nlev = g.ncol * (g.Nz + 1);
-  g.ncp = (g.ncell + 127) / 128 * 128;  // plane stride; a multiple of the TMA tile so bulk copies never run off a plane
+  g.ncp = (g.ncell + PB_TILE - 1) / PB_TILE * PB_TILE;  // whole coefficient tiles (tile-blocked layout, common.cuh)
   g.dx = cfg->dx; g.dy = cfg->dy;
   CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CU(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device));
   s->use_tma = getenv("PPRTS_B200_NO_TMA") == nullptr;
+  if (const char *v = getenv("PPRTS_B200_MM_VARIANT")) s->mm_variant = atoi(v);
 
   // dz in device layout + determine_1d_layers (src/pprts.F90:649-725)
   std::vector<double> hdz((size_t)g.ncell);
@@ -461,8 +439,8 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   CU(cudaMalloc(&s->d2d, (size_t)Nd * Nd * g.ncp * csz)); CU(cudaMemset(s->d2d, 0, (size_t)Nd * Nd * g.ncp * csz));
   CU(cudaMalloc(&s->d2f, (size_t)Nd * Nf * g.ncp * csz)); CU(cudaMemset(s->d2f, 0, (size_t)Nd * Nf * g.ncp * csz));
   CU(cudaMalloc(&s->f2f, (size_t)Nf * Nf * g.ncp * csz)); CU(cudaMemset(s->f2f, 0, (size_t)Nf * Nf * g.ncp * csz));
-  if (s->use_tma && cfg->coeff_fp32 && make_plane_tensor_map(&s->tmap_f2f, s->f2f, Nf * Nf, g.ncp, 128)) s->use_tma = false;
   DA(s->cdiv_dir, (size_t)Nd * g.ncp); DA(s->cdiv_diff, (size_t)Nf * g.ncp);
+  DA(s->tile_class, (size_t)(g.ncp / PB_TILE));
   DA(s->b, (size_t)Nf * g.nlev);
   for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)Nf * g.nlev);
   DA(s->edir_tmp, (size_t)Nd * g.nlev);
@@ -511,7 +489,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
-  cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
+  cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_bad);
   for (auto &ev : s->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto e : s->evpool) cudaEventDestroy(e);
@@ -634,9 +612,10 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
   if (lsolar && s->angles_dirty) { int rc = contract_direct_tables(s); if (rc) return rc; }
   const long n3d = (long)(g.Nz - s->n1d) * g.ncol;
   if (n3d > 0) {
+    CU(cudaMemsetAsync(s->tile_class, 0, (size_t)(g.ncp / PB_TILE) * sizeof(unsigned int), s->stream));
     DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_lookup<L, CT>), nblk(n3d, 128), 128, g, s->lutdev, s->sym, (int)lsolar,
                            s->n1d, s->kabs, s->ksca, s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f,
-                           s->cdiv_dir, s->cdiv_diff));
+                           s->cdiv_dir, s->cdiv_diff, (unsigned char *)s->tile_class));
   }
   s->coeffs_dirty = false;
   s->coeffs_have_dir = lsolar;
@@ -727,26 +706,34 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   return 0;
 }
 
-static const int MM_TILE = 128;
-template <class L, int NDOT>
-static bool launch_matmult_tma(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
-  constexpr size_t smem = 2 * (size_t)L::Nf * L::Nf * MM_TILE * sizeof(float);
+template <class L, int NDOT, int NSTAGE, bool PREFETCH>
+static bool launch_matmult_tma_v(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+  constexpr size_t smem = (size_t)NSTAGE * L::Nf * L::Nf * PB_TILE * sizeof(float);
   if constexpr (smem > 200 * 1024) return false;
   else {
     const Grid &g = s->g;
     static bool attr_set = false;
-    auto kern = k_matmult_tma<L, NDOT, MM_TILE>;
+    auto kern = k_matmult_tma<L, NDOT, NSTAGE, PREFETCH>;
     if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    const long ntiles = (g.ncell + MM_TILE - 1) / MM_TILE;
-    const unsigned int grid = (unsigned int)std::min<long>(ntiles, 2L * s->num_sms);
+    const long ntiles = (g.ncell + PB_TILE - 1) / PB_TILE;
+    const int per_sm = std::max(1, std::min<int>(NSTAGE == 1 ? 4 : 2, (int)((220 * 1024) / smem)));
+    const unsigned int grid = (unsigned int)std::min<long>(ntiles, (long)per_sm * s->num_sms);
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (s->timing) { ea = get_event(s); eb = get_event(s); cudaEventRecord(ea, s->stream); }
-    kern<<<grid, MM_TILE, smem, s->stream>>>(g, s->n1d, ntiles, s->tmap_f2f, s->a11, s->a12, s->albedo, x, y, w,
-                                             s->partials, s->counter, dots);
+    kern<<<grid, PB_TILE, smem, s->stream>>>(g, s->n1d, ntiles, (const float *)s->f2f, s->tile_class, s->a11, s->a12,
+                                             s->albedo, x, y, w, s->partials, s->counter, dots);
     if (s->timing) { cudaEventRecord(eb, s->stream); s->evs.push_back({FAM_MATMULT, ea, eb}); }
     s->launches++;
     s->fam_launch[FAM_MATMULT]++;
     return true;
+  }
+}
+template <class L, int NDOT>
+static bool launch_matmult_tma(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+  switch (s->mm_variant) {
+    case 0: return launch_matmult_tma_v<L, NDOT, 2, true>(s, x, y, w, dots);
+    case 1: return launch_matmult_tma_v<L, NDOT, 2, false>(s, x, y, w, dots);
+    default: return launch_matmult_tma_v<L, NDOT, 1, false>(s, x, y, w, dots);
   }
 }
 
@@ -769,13 +756,13 @@ static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
   if constexpr (L::Nft == 2) {
     const Grid &g = s->g;
     if (!s->prec_ready) {
-      LAUNCH(s, FAM_PRECOND, (k_prec_setup<L, CT>), nblk(g.ncol, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+      LAUNCH(s, FAM_PRECOND, (k_prec_setup<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
              s->albedo, s->precR, s->precInv);
       s->prec_ready = true;
     }
-    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z);
-    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z);
   }
 }

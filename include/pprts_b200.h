@@ -155,8 +155,9 @@ long pprts_b200_kernel_launches(pprts_b200_solver *solver);
 /* the cudaStream_t every kernel of this solver is launched on (to record timing events on the launching stream) */
 void *pprts_b200_stream(pprts_b200_solver *solver);
 /* device time [ms] and launch count accumulated per kernel family since the last reset:
- * 0 lookup, 1 edir sweep, 2 source, 3 matmult, 4 precond, 5 vector ops, 6 absorption+result, 7 ingest/egress */
-int pprts_b200_kernel_stats(pprts_b200_solver *solver, int reset, double ms[8], long launches[8]);
+ * 0 lookup, 1 edir sweep, 2 source, 3 matmult, 4 precond, 5 vector ops, 6 absorption+result, 7 ingest/egress,
+ * 8 halo pack/unpack; entries 9..15 are reserved (zero) */
+int pprts_b200_kernel_stats(pprts_b200_solver *solver, int reset, double ms[16], long launches[16]);
 int pprts_b200_enable_kernel_timing(pprts_b200_solver *solver, int on);
 
 const char *pprts_b200_last_error(void);

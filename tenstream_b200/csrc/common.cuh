@@ -27,7 +27,21 @@ struct Grid {
   long nlev;   // (Nz+1)*ncol
   long ncp;    // ncell padded to a multiple of PB_TILE
   double dx, dy;
+  int gx, gy;  // 1: the domain is split across GPUs in x / y -> the high-x / high-y faces are ghost planes
 };
+
+// x/y decomposition (src/pprts_base.F90:721-828, halo exchange src/pprts_explicit.F90:232-328, :715-848).
+// A state vector of ND dofs is [ND*nlev main][ND*(Nz+1)*Ny ghost-x][ND*(Nz+1)*Nx ghost-y]: the ghost-x block holds the
+// dofs living on the face i = Nx (owned by the east neighbour as its i = 0 face), laid out [d][k][j]; ghost-y likewise
+// for j = Ny, laid out [d][k][i].  Kernels reach the high-x / high-y face of a cell through (offset, dof stride)
+// pairs, so the periodic single-GPU case, the ghost case and interior cells run the same branch-free code.
+__host__ __device__ __forceinline__ long state_len(const Grid &g, int nd) {
+  return (long)nd * g.nlev + (long)nd * (g.Nz + 1) * ((g.gx ? g.Ny : 0) + (g.gy ? g.Nx : 0));
+}
+__host__ __device__ __forceinline__ long ghost_x_base(const Grid &g, int nd) { return (long)nd * g.nlev; }
+__host__ __device__ __forceinline__ long ghost_y_base(const Grid &g, int nd) {
+  return (long)nd * g.nlev + (g.gx ? (long)nd * (g.Nz + 1) * g.Ny : 0);
+}
 
 // Stream layouts (src/pprts.F90:332-396). Top streams alternate [F,T,...] (E_up first); side streams alternate
 // starting with F (3_10, 8_10) or T (3_24).
@@ -89,6 +103,46 @@ __device__ __forceinline__ double widen_normal_or_zero(float f) {
 
 __device__ __forceinline__ long lidx(const Grid &g, int k, int j, int i) { return ((long)k * g.Ny + j) * g.Nx + i; }
 __device__ __forceinline__ int wrap_p(int i, int n) { return (i + 1 == n) ? 0 : i + 1; }
+
+// element offsets of the face locations of cell (k, j, i) in a state vector of ND dofs: dof d on the cell's own
+// (low) faces is at own + d*nlev, on the level below at dn + d*nlev, on the high-x face at xp + d*xps, on the high-y
+// face at yp + d*yps
+struct Faces {
+  long own, dn, xp, xps, yp, yps;
+  bool xg, yg;  // the high-x / high-y face is a ghost (its rows belong to the neighbouring rank)
+  int i, j, k;
+};
+template <int ND>
+__device__ __forceinline__ Faces cell_faces(const Grid &g, long c) {
+  Faces f;
+  f.i = (int)(c % g.Nx); f.j = (int)((c / g.Nx) % g.Ny); f.k = (int)(c / g.ncol);
+  f.own = c; f.dn = c + g.ncol;
+  f.xg = g.gx && f.i + 1 == g.Nx;
+  f.yg = g.gy && f.j + 1 == g.Ny;
+  if (f.xg) { f.xp = ghost_x_base(g, ND) + (long)f.k * g.Ny + f.j; f.xps = (long)(g.Nz + 1) * g.Ny; }
+  else { f.xp = lidx(g, f.k, f.j, wrap_p(f.i, g.Nx)); f.xps = g.nlev; }
+  if (f.yg) { f.yp = ghost_y_base(g, ND) + (long)f.k * g.Nx + f.i; f.yps = (long)(g.Nz + 1) * g.Nx; }
+  else { f.yp = lidx(g, f.k, wrap_p(f.j, g.Ny), f.i); f.yps = g.nlev; }
+  return f;
+}
+
+// offset of dof d's entry / exit face for a cell (entry: where the stream comes in, exit: its destination row)
+template <class L>
+__device__ __forceinline__ long diff_face(const Grid &g, const Faces &f, int d, bool exit_face) {
+  constexpr int Nft = L::Nft, Nfs = L::Nfs;
+  if (d < Nft) return (long)d * g.nlev + ((L::top_in(d) == exit_face) ? f.dn : f.own);
+  if (d < Nft + Nfs) return (L::side_in(d - Nft) == exit_face) ? f.xp + (long)d * f.xps : f.own + (long)d * g.nlev;
+  return (L::side_in(d - Nft - Nfs) == exit_face) ? f.yp + (long)d * f.yps : f.own + (long)d * g.nlev;
+}
+// true if dof d's destination row of this cell lies on a ghost face (owned by the neighbouring rank)
+template <class L>
+__device__ __forceinline__ bool diff_exit_is_ghost(const Faces &f, int d) {
+  constexpr int Nft = L::Nft, Nfs = L::Nfs;
+  if (d < Nft) return false;
+  if (d < Nft + Nfs) return L::side_in(d - Nft) && f.xg;
+  return L::side_in(d - Nft - Nfs) && f.yg;
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // Deterministic grid-wide sum of NV doubles per thread: warp shuffles -> shared memory -> one partial per block;

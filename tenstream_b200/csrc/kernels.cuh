@@ -391,12 +391,19 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
   double d2sum[1] = {0.0};
   if (col < g.ncol) {
     const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
-    const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
-    const int i_in = xinc ? i : ip, i_out = xinc ? ip : i;   // faces i+1-xinc (source) and i+xinc (destination)
-    const int j_in = yinc ? j : jp, j_out = yinc ? jp : j;
     const long o_own = (long)j * g.Nx + i;
-    const long o_xin = (long)j * g.Nx + i_in, o_xout = (long)j * g.Nx + i_out;
-    const long o_yin = (long)j_in * g.Nx + i, o_yout = (long)j_out * g.Nx + i;
+    // dof d at level k: own (low) faces at d*nlev + k*ncol + o_own; high-x face at xp0 + d*xps + k*xpk (the periodic
+    // image, or the ghost-x block when the domain is split in x); high-y face likewise
+    long xp0, xps, xpk, yp0, yps, ypk;
+    if (g.gx && i + 1 == g.Nx) { xp0 = ghost_x_base(g, Nd) + j; xps = (long)(g.Nz + 1) * g.Ny; xpk = g.Ny; }
+    else { xp0 = (long)j * g.Nx + wrap_p(i, g.Nx); xps = g.nlev; xpk = g.ncol; }
+    if (g.gy && j + 1 == g.Ny) { yp0 = ghost_y_base(g, Nd) + i; yps = (long)(g.Nz + 1) * g.Nx; ypk = g.Nx; }
+    else { yp0 = (long)wrap_p(j, g.Ny) * g.Nx + i; yps = g.nlev; ypk = g.ncol; }
+    // beam enters through faces i+1-xinc / j+1-yinc and leaves through i+xinc / j+yinc
+    const long xin0 = xinc ? o_own : xp0, xins = xinc ? g.nlev : xps, xink = xinc ? g.ncol : xpk;
+    const long xout0 = xinc ? xp0 : o_own, xouts = xinc ? xps : g.nlev, xoutk = xinc ? xpk : g.ncol;
+    const long yin0 = yinc ? o_own : yp0, yins = yinc ? g.nlev : yps, yink = yinc ? g.ncol : ypk;
+    const long yout0 = yinc ? yp0 : o_own, youts = yinc ? yps : g.nlev, youtk = yinc ? ypk : g.ncol;
     double top[Ndt];
 #pragma unroll
     for (int d = 0; d < Ndt; ++d) {  // setup_incSolar (src/pprts_base.F90:1146-1181)
@@ -425,9 +432,9 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
 #pragma unroll
         for (int d = 0; d < Ndt; ++d) src[d] = top[d];
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) src[Ndt + d] = xold[(long)(Ndt + d) * g.nlev + lk + o_xin];
+        for (int d = 0; d < Nds; ++d) src[Ndt + d] = xold[xin0 + (Ndt + d) * xins + k * xink];
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = xold[(long)(Ndt + Nds + d) * g.nlev + lk + o_yin];
+        for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
         const long cb = cbase<Nd * Nd>(lk + o_own);
 #pragma unroll
         for (int dst = 0; dst < Nd; ++dst) {
@@ -436,8 +443,8 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
           for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)d2d[cb + (dst * Nd + s) * PB_TILE];
           long q;
           if (dst < Ndt) { q = (long)dst * g.nlev + lk1 + o_own; top[dst] = acc; }
-          else if (dst < Ndt + Nds) q = (long)dst * g.nlev + lk + o_xout;
-          else q = (long)dst * g.nlev + lk + o_yout;
+          else if (dst < Ndt + Nds) q = xout0 + dst * xouts + k * xoutk;
+          else q = yout0 + dst * youts + k * youtk;
           double df = acc - xold[q];
           d2sum[0] += df * df;
           xnew[q] = acc;
@@ -465,11 +472,9 @@ k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, 
   constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.ncell) return;
-  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
-  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
-  const long l_own = lidx(g, k, j, i), l_dn = lidx(g, k + 1, j, i);
-  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
-  const long l_xin = xinc ? l_own : l_xp, l_yin = yinc ? l_own : l_yp;
+  const Faces fd = cell_faces<Nd>(g, c), ff = cell_faces<Nf>(g, c);  // faces in the edir / in the b vector
+  const int i = fd.i, j = fd.j, k = fd.k;
+  const long l_own = fd.own, l_dn = fd.dn;
   // `if (any(xedir(:, k, i, j) .gt. epsilon(one)))` (:4706) -- tested on the cell's OWN index for every dof
   bool any = false;
 #pragma unroll
@@ -494,19 +499,17 @@ k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, 
 #pragma unroll
       for (int d = 0; d < Ndt; ++d) src[d] = edir[(long)d * g.nlev + l_own];
 #pragma unroll
-      for (int d = 0; d < Nds; ++d) src[Ndt + d] = edir[(long)(Ndt + d) * g.nlev + l_xin];
+      for (int d = 0; d < Nds; ++d)
+        src[Ndt + d] = edir[xinc ? (long)(Ndt + d) * g.nlev + l_own : fd.xp + (Ndt + d) * fd.xps];
 #pragma unroll
-      for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = edir[(long)(Ndt + Nds + d) * g.nlev + l_yin];
+      for (int d = 0; d < Nds; ++d)
+        src[Ndt + Nds + d] = edir[yinc ? (long)(Ndt + Nds + d) * g.nlev + l_own : fd.yp + (Ndt + Nds + d) * fd.yps];
 #pragma unroll
       for (int dst = 0; dst < Nf; ++dst) {
         double acc = 0.0;
 #pragma unroll
         for (int s = 0; s < Nd; ++s) acc += src[s] * widen(d2f[cb_df + (dst * Nd + s) * PB_TILE]);
-        long q;
-        if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
-        else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
-        else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
-        b[(long)dst * g.nlev + q] = acc;
+        b[diff_face<L>(g, ff, dst, true)] = acc;
       }
     }
   }
@@ -543,10 +546,9 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdi
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.ncell) return;
-  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
-  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
-  const long l_own = lidx(g, k, j, i), l_dn = lidx(g, k + 1, j, i);
-  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
+  const Faces ff = cell_faces<Nf>(g, c);
+  const int i = ff.i, j = ff.j, k = ff.k;
+  const long l_own = ff.own, l_dn = ff.dn;
   const double Az = g.dx * g.dy;
   const double b0 = planck[l_own], b1 = planck[l_dn];
   const double tauz = kabs[c] * dz[c];
@@ -576,14 +578,14 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdi
     for (int d = 0; d < Nfs; ++d, ++src) {
       double emis = fmax(0.0, fmin(1.0, cdiv_diff[(long)src * g.ncp + c]));
       emis = (d + 1 > Nfs / 2) ? btop * emis : bbot * emis;
-      b[(long)src * g.nlev + (L::side_in(d) ? l_xp : l_own)] = emis * bfac;
+      b[diff_face<L>(g, ff, src, true)] = emis * bfac;
     }
     bfac = PB_PI * Ay / (double)(Nfs / 2);
 #pragma unroll
     for (int d = 0; d < Nfs; ++d, ++src) {
       double emis = fmax(0.0, fmin(1.0, cdiv_diff[(long)src * g.ncp + c]));
       emis = (d + 1 > Nfs / 2) ? btop * emis : bbot * emis;
-      b[(long)src * g.nlev + (L::side_in(d) ? l_yp : l_own)] = emis * bfac;
+      b[diff_face<L>(g, ff, src, true)] = emis * bfac;
     }
   }
   if (k == g.Nz - 1) {  // thermal emission at the surface (:4958-4985)
@@ -613,48 +615,19 @@ struct MatIn {
   double xs[L::Nf], xd[L::Nf];
   double wd[L::Nf];  // dot-product weight w0 at the destination row of stream d (NDOT > 0)
 };
-template <class L>
-struct CellIdx {
-  long l_own, l_dn, l_xp, l_yp;
-  int i, j, k;
-};
-template <class L>
-__device__ __forceinline__ CellIdx<L> cell_index(const Grid &g, long c) {
-  CellIdx<L> ci;
-  ci.i = (int)(c % g.Nx); ci.j = (int)((c / g.Nx) % g.Ny); ci.k = (int)(c / g.ncol);
-  const int ip = wrap_p(ci.i, g.Nx), jp = wrap_p(ci.j, g.Ny);
-  ci.l_own = c; ci.l_dn = c + g.ncol;
-  ci.l_xp = lidx(g, ci.k, ci.j, ip); ci.l_yp = lidx(g, ci.k, jp, ci.i);
-  return ci;
-}
 template <class L, int NDOT>
-__device__ __forceinline__ void matmult_load(const Grid &g, const CellIdx<L> &ci, const double *__restrict__ x,
+__device__ __forceinline__ void matmult_load(const Grid &g, const Faces &f, const double *__restrict__ x,
                                              const double *__restrict__ w0, MatIn<L> &in) {
-  constexpr int Nft = L::Nft, Nfs = L::Nfs;
 #pragma unroll
-  for (int d = 0; d < Nft; ++d) {
-    const long qs = (long)d * g.nlev + (L::top_in(d) ? ci.l_own : ci.l_dn);
-    const long qd = (long)d * g.nlev + (L::top_in(d) ? ci.l_dn : ci.l_own);
-    in.xs[d] = x[qs]; in.xd[d] = x[qd];
-    if (NDOT > 0) in.wd[d] = w0[qd];
-  }
-#pragma unroll
-  for (int d = 0; d < Nfs; ++d) {
-    const long qs = (long)(Nft + d) * g.nlev + (L::side_in(d) ? ci.l_own : ci.l_xp);
-    const long qd = (long)(Nft + d) * g.nlev + (L::side_in(d) ? ci.l_xp : ci.l_own);
-    in.xs[Nft + d] = x[qs]; in.xd[Nft + d] = x[qd];
-    if (NDOT > 0) in.wd[Nft + d] = w0[qd];
-  }
-#pragma unroll
-  for (int d = 0; d < Nfs; ++d) {
-    const long qs = (long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? ci.l_own : ci.l_yp);
-    const long qd = (long)(Nft + Nfs + d) * g.nlev + (L::side_in(d) ? ci.l_yp : ci.l_own);
-    in.xs[Nft + Nfs + d] = x[qs]; in.xd[Nft + Nfs + d] = x[qd];
-    if (NDOT > 0) in.wd[Nft + Nfs + d] = w0[qd];
+  for (int d = 0; d < L::Nf; ++d) {
+    const long qd = diff_face<L>(g, f, d, true);
+    in.xs[d] = x[diff_face<L>(g, f, d, false)];
+    in.xd[d] = x[qd];
+    if (NDOT > 0) in.wd[d] = diff_exit_is_ghost<L>(f, d) ? 0.0 : w0[qd];  // ghost rows: the owner adds its share
   }
 }
 template <class L, int NDOT, class COEF>
-__device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, const CellIdx<L> &ci,
+__device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, const Faces &f,
                                              const MatIn<L> &in, const double *__restrict__ a11,
                                              const double *__restrict__ a12, const double *__restrict__ albedo,
                                              const double *__restrict__ x, double *__restrict__ y,
@@ -666,22 +639,21 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
     if (NDOT >= 1) dots[0] += val * w0[q];
     if (NDOT >= 2) dots[1] += val * val;
   };
-  auto emit_w = [&](long q, double val, double w) {  // destination rows: weight prefetched with the state
+  auto emit_w = [&](int d, long q, double val) {  // destination rows: weight prefetched with the state
     y[q] = val;
-    if (NDOT >= 1) dots[0] += val * w;
-    if (NDOT >= 2) dots[1] += val * val;
+    if (NDOT >= 1) dots[0] += val * in.wd[d];
+    if (NDOT >= 2) { if (!diff_exit_is_ghost<L>(f, d)) dots[1] += val * val; }
   };
-  const long l_own = ci.l_own, l_dn = ci.l_dn, l_xp = ci.l_xp, l_yp = ci.l_yp;
-  const int k = ci.k;
+  const long l_own = f.own, l_dn = f.dn;
+  const int k = f.k;
   if (k < n1d) {
     const double t = a11[l_own], r = a12[l_own];
 #pragma unroll
     for (int d = 0; d < Nft; ++d) {  // xb(dst) = x(dst) - x(d, other side)*a11 - x(inv_dof, same level)*a12
-      const long q = (long)d * g.nlev + (L::top_in(d) ? l_dn : l_own);
       double acc = 0.0;
       acc = acc - in.xs[d] * t;
       acc = acc - in.xs[L::inv_dof(d)] * r;
-      emit_w(q, acc + in.xd[d], in.wd[d]);
+      emit_w(d, diff_face<L>(g, f, d, true), acc + in.xd[d]);
     }
 #pragma unroll
     for (int d = Nft; d < Nf; ++d) {
@@ -694,12 +666,7 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
       double acc = 0.0;
 #pragma unroll
       for (int s = 0; s < Nf; ++s) acc = acc - in.xs[s] * coef(dst * Nf + s);
-      long q;
-      if (dst < Nft) q = L::top_in(dst) ? l_dn : l_own;
-      else if (dst < Nft + Nfs) q = L::side_in(dst - Nft) ? l_xp : l_own;
-      else q = L::side_in(dst - Nft - Nfs) ? l_yp : l_own;
-      q += (long)dst * g.nlev;
-      emit_w(q, acc + in.xd[dst], in.wd[dst]);
+      emit_w(dst, diff_face<L>(g, f, dst, true), acc + in.xd[dst]);
     }
   }
   if (k == 0) {  // rows without a producing cell: incoming diffuse at TOA
@@ -707,7 +674,7 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
     for (int d = 0; d < Nft; ++d) if (L::top_in(d)) emit((long)d * g.nlev + l_own, in.xs[d]);
   }
   if (k == g.Nz - 1) {  // albedo row (src/pprts_shell.F90:500-505) and the unused side dofs below the ground
-    const double alb = albedo[(long)ci.j * g.Nx + ci.i];
+    const double alb = albedo[(long)f.j * g.Nx + f.i];
 #pragma unroll
     for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) emit((long)d * g.nlev + l_dn, in.xs[d] - in.xd[L::inv_dof(d)] * alb);
 #pragma unroll
@@ -728,7 +695,7 @@ k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   if (c < g.ncell) {
     const long cb = cbase<L::Nf * L::Nf>(c);
     auto coef = [&](int n) { return widen(T[cb + n * PB_TILE]); };
-    const CellIdx<L> ci = cell_index<L>(g, c);
+    const Faces ci = cell_faces<L::Nf>(g, c);
     MatIn<L> in;
     matmult_load<L, NDOT>(g, ci, x, w0, in);
     matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
@@ -801,7 +768,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
     mbar_expect_tx(b, STAGE_BYTES);
     bulk_g2s(stage(st), T + tile * (long)(NP * PB_TILE), STAGE_BYTES, b);  // one contiguous run
   };
-  auto compute = [&](long tile, int st, unsigned int cls, const CellIdx<L> &ci, const MatIn<L> &in, double *dots) {
+  auto compute = [&](long tile, int st, unsigned int cls, const Faces &ci, const MatIn<L> &in, double *dots) {
     const float *sp = stage(st) + tid;
     if (__builtin_expect(cls == 0, 1)) {  // CTA-uniform
       auto coef = [&](int n) { return widen_normal(sp[n * PB_TILE]); };
@@ -824,10 +791,10 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
       if (tid == 0) issue(tile, 0);
       const long c = tile * PB_TILE + tid;
       const unsigned int cls = tile_class[tile];
-      CellIdx<L> ci;
+      Faces ci;
       MatIn<L> in;
       if (c < g.ncell) {  // state loads travel together with the bulk copy
-        ci = cell_index<L>(g, c);
+        ci = cell_faces<L::Nf>(g, c);
         matmult_load<L, NDOT>(g, ci, x, w0, in);
       }
       mbar_wait(&bar[0], it & 1);
@@ -836,13 +803,13 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
     }
   } else {
     if (tid == 0 && tile < ntiles) issue(tile, 0);
-    CellIdx<L> ci, ci_n;
+    Faces ci, ci_n;
     MatIn<L> in, in_n;
     unsigned int cls = 0, cls_n = 0;
     if (PREFETCH) {
       if (tile < ntiles) cls = tile_class[tile];
       if (tile < ntiles && tile * PB_TILE + tid < g.ncell) {
-        ci = cell_index<L>(g, tile * PB_TILE + tid);
+        ci = cell_faces<L::Nf>(g, tile * PB_TILE + tid);
         matmult_load<L, NDOT>(g, ci, x, w0, in);
       }
     }
@@ -857,13 +824,13 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
       if (PREFETCH) {
         if (next < ntiles) cls_n = tile_class[next];
         if (have_next) {  // register prefetch of the next tile's state
-          ci_n = cell_index<L>(g, cn);
+          ci_n = cell_faces<L::Nf>(g, cn);
           matmult_load<L, NDOT>(g, ci_n, x, w0, in_n);
         }
       } else {
         cls = tile_class[tile];
         if (c < g.ncell) {
-          ci = cell_index<L>(g, c);
+          ci = cell_faces<L::Nf>(g, c);
           matmult_load<L, NDOT>(g, ci, x, w0, in);
         }
       }
@@ -1090,61 +1057,66 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
 // dot products itself, the last block of the reducing kernels rotates them -> no host round trip inside an iteration
 // except the convergence read.
 // =================================================================================================================
-enum { SC_RHO = 0, SC_RHO_OLD, SC_ALPHA, SC_OMEGA, SC_RHV, SC_TS, SC_TT, SC_RR, SC_RHO_NEW, SC_BNORM1, SC_EDIR0 = 16, SC_COUNT = 32 };
+// Slot layout: the two rho slots alternate with the iteration parity (rho of iteration `it` lives in SC_RHO0 + 2*(it&1),
+// rho_old in the other one) and SC_RR sits between them, so that every reducing kernel writes a CONTIGUOUS run of raw
+// dot products and no kernel has to rotate scalars -- in a decomposed run each run is summed over the ranks with one
+// small all-reduce right after the kernel that produced it.
+enum { SC_RHO0 = 0, SC_RR = 1, SC_RHO1 = 2, SC_RHV = 3, SC_TS = 4, SC_TT = 5, SC_BNORM1 = 6, SC_TMP = 8, SC_EDIR0 = 16, SC_COUNT = 32 };
+__device__ __forceinline__ int sc_rho_slot(int it) { return (it & 1) ? SC_RHO1 : SC_RHO0; }
 
-// r = b - Ax (Ax in `r` on entry), rh = r, p = v = 0, rr = rho = (r,r)
+// r = b - Ax (Ax in `r` on entry), rh = r, p = v = 0, rr = rho(it = 1) = (r,r)
 __global__ void k_bicg_init(long n, const double *__restrict__ b, double *__restrict__ r, double *__restrict__ rh,
                             double *__restrict__ p, double *__restrict__ v, double *partials, unsigned int *counter,
                             double *sc) {
-  double acc[1] = {0.0};
+  double acc[2] = {0.0, 0.0};
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
     double rv = b[q] - r[q];
     r[q] = rv; rh[q] = rv; p[q] = 0.0; v[q] = 0.0;
     acc[0] += rv * rv;
   }
-  if (grid_reduce_sum<1>(acc, partials, counter, &sc[SC_RR])) {
-    if (threadIdx.x == 0) { sc[SC_RHO] = sc[SC_RR]; sc[SC_RHO_OLD] = 1.0; sc[SC_ALPHA] = 1.0; sc[SC_OMEGA] = 1.0; }
-  }
+  acc[1] = acc[0];
+  grid_reduce_sum<2>(acc, partials, counter, &sc[SC_RR]);  // SC_RR, SC_RHO1 = rho of iteration 1
 }
-// p = r + beta (p - omega v),  beta = (rho/rho_old)(alpha/omega)
-__global__ void k_bicg_update_p(long n, const double *__restrict__ r, const double *__restrict__ v,
+// p = r + beta (p - omega v),  beta = (rho/rho_old)(alpha/omega) with alpha, omega of the previous iteration
+__global__ void k_bicg_update_p(long n, int it, const double *__restrict__ r, const double *__restrict__ v,
                                 double *__restrict__ p, const double *__restrict__ sc) {
-  const double beta = (sc[SC_RHO] / sc[SC_RHO_OLD]) * (sc[SC_ALPHA] / sc[SC_OMEGA]), omega = sc[SC_OMEGA];
+  double beta = 0.0, omega = 0.0;
+  if (it > 1) {
+    const double rho = sc[sc_rho_slot(it)], rho_old = sc[sc_rho_slot(it - 1)];
+    const double alpha = rho_old / sc[SC_RHV];
+    const double tt = sc[SC_TT];
+    omega = (tt > 0.0) ? sc[SC_TS] / tt : 0.0;
+    beta = (rho / rho_old) * (alpha / omega);
+  }
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
     p[q] = r[q] + beta * (p[q] - omega * v[q]);
 }
 // s = r - alpha v, alpha = rho / (rh, v)
-__global__ void k_bicg_update_s(long n, const double *__restrict__ r, const double *__restrict__ v,
-                                double *__restrict__ s, double *sc) {
-  const double alpha = sc[SC_RHO] / sc[SC_RHV];
+__global__ void k_bicg_update_s(long n, int it, const double *__restrict__ r, const double *__restrict__ v,
+                                double *__restrict__ s, const double *__restrict__ sc) {
+  const double alpha = sc[sc_rho_slot(it)] / sc[SC_RHV];
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
     s[q] = r[q] - alpha * v[q];
-  if (blockIdx.x == 0 && threadIdx.x == 0) sc[SC_ALPHA] = alpha;
 }
-// x += alpha ph + omega sh ; r = s - omega t ; rr = (r,r), rho_new = (rh, r); rotate scalars
-__global__ void k_bicg_update_xr(long n, const double *__restrict__ ph, const double *__restrict__ sh,
+// x += alpha ph + omega sh ; r = s - omega t ; rr = (r,r), rho(it+1) = (rh, r)
+__global__ void k_bicg_update_xr(long n, int it, const double *__restrict__ ph, const double *__restrict__ sh,
                                  const double *__restrict__ s, const double *__restrict__ t,
                                  const double *__restrict__ rh, double *__restrict__ x, double *__restrict__ r,
                                  double *partials, unsigned int *counter, double *sc) {
-  const double alpha = sc[SC_RHO] / sc[SC_RHV];
+  const double alpha = sc[sc_rho_slot(it)] / sc[SC_RHV];
   const double tt = sc[SC_TT];
   const double omega = (tt > 0.0) ? sc[SC_TS] / tt : 0.0;
-  double acc[2] = {0.0, 0.0};
+  const bool rho_first = sc_rho_slot(it + 1) == SC_RHO0;  // output run is (RHO0, RR) or (RR, RHO1)
+  double rr = 0.0, rhr = 0.0;
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
     x[q] = x[q] + alpha * ph[q] + omega * sh[q];
     double rv = s[q] - omega * t[q];
     r[q] = rv;
-    acc[0] += rv * rv;
-    acc[1] += rv * rh[q];
+    rr += rv * rv;
+    rhr += rv * rh[q];
   }
-  if (grid_reduce_sum<2>(acc, partials, counter, &sc[SC_RR])) {  // writes SC_RR, SC_RHO_NEW (adjacent)
-    if (threadIdx.x == 0) {
-      sc[SC_RHO_OLD] = sc[SC_RHO];
-      sc[SC_RHO] = sc[SC_RHO_NEW];
-      sc[SC_OMEGA] = omega;
-      sc[SC_ALPHA] = alpha;
-    }
-  }
+  double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
+  grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
 }
 // sum |b| (src/pprts.F90:2774)
 __global__ void k_norm1(long n, const double *__restrict__ b, double *partials, unsigned int *counter, double *out) {
@@ -1152,6 +1124,58 @@ __global__ void k_norm1(long n, const double *__restrict__ b, double *partials, 
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
     acc[0] += fabs(b[q]);
   grid_reduce_sum<1>(acc, partials, counter, out);
+}
+
+// =================================================================================================================
+// Halo exchange helpers for the x/y decomposition (src/pprts_explicit.F90:232-328, :715-848; src/pprts_base.F90:
+// 1622-1731).  dir = 0: x faces (plane i = 0, buffer [d][k][j]), dir = 1: y faces (plane j = 0, buffer [d][k][i]).
+// =================================================================================================================
+// buf[d][k][t] = v(d0 + d, k, low face) : what the west / south neighbour needs in its ghost block
+__global__ void k_halo_pack(Grid g, int dir, int d0, int nd, const double *__restrict__ v, double *__restrict__ buf) {
+  const int len = dir == 0 ? g.Ny : g.Nx;
+  const long n = (long)nd * (g.Nz + 1) * len;
+  long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int t = (int)(q % len), k = (int)((q / len) % (g.Nz + 1)), d = (int)(q / ((long)len * (g.Nz + 1)));
+  const long l = dir == 0 ? lidx(g, k, t, 0) : lidx(g, k, 0, t);
+  buf[q] = v[(long)(d0 + d) * g.nlev + l];
+}
+// v(d0 + d, k, low face) = buf[d][k][t] for the dofs in `mask` and the levels [k0, k1): rows of this rank that were
+// produced by the west / south neighbour (every row has exactly one producer, so this is a store, not an add).
+// NDOT > 0 adds the dot products of the stored rows to dots_out[0..NDOT) (the producer could not: it has no w0 there).
+template <int NDOT>
+__global__ void k_halo_unpack(Grid g, int dir, int d0, int nd, unsigned int mask, int k0, int k1,
+                              const double *__restrict__ buf, double *__restrict__ v, const double *__restrict__ w0,
+                              double *partials, unsigned int *counter, double *tmp, double *dots_out) {
+  constexpr int NV = NDOT > 0 ? NDOT : 1;
+  const int len = dir == 0 ? g.Ny : g.Nx;
+  const long n = (long)nd * (g.Nz + 1) * len;
+  double dots[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) dots[m] = 0.0;
+  long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) {
+    const int t = (int)(q % len), k = (int)((q / len) % (g.Nz + 1)), d = (int)(q / ((long)len * (g.Nz + 1)));
+    if (((mask >> d) & 1u) && k >= k0 && k < k1) {
+      const long l = (long)(d0 + d) * g.nlev + (dir == 0 ? lidx(g, k, t, 0) : lidx(g, k, 0, t));
+      const double val = buf[q];
+      v[l] = val;
+      if (NDOT >= 1) dots[0] += val * w0[l];
+      if (NDOT >= 2) dots[1] += val * val;
+    }
+  }
+  if (NDOT > 0) {
+    if (grid_reduce_sum<NV>(dots, partials, counter, tmp)) {
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int m = 0; m < NV; ++m) dots_out[m] += tmp[m];
+      }
+    }
+  }
+}
+// v[0] <- sqrt(v[0]) / nranks : local 2-norm -> this rank's share of the mean over ranks (src/pprts_explicit.F90:182)
+__global__ void k_sqrt_mean(double *v, int n, double inv_nranks) {
+  if (threadIdx.x < n) v[threadIdx.x] = sqrt(v[threadIdx.x]) * inv_nranks;
 }
 
 // =================================================================================================================
@@ -1167,12 +1191,15 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
   constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.ncell) return;
-  const int i = (int)(c % g.Nx), j = (int)((c / g.Nx) % g.Ny), k = (int)(c / g.ncol);
-  const int ip = wrap_p(i, g.Nx), jp = wrap_p(j, g.Ny);
-  const long l_own = lidx(g, k, j, i), l_dn = l_own + g.ncol;
-  const long l_xp = lidx(g, k, j, ip), l_yp = lidx(g, k, jp, i);
-  const long l_xin = xinc ? l_own : l_xp, l_xout = xinc ? l_xp : l_own;
-  const long l_yin = yinc ? l_own : l_yp, l_yout = yinc ? l_yp : l_own;
+  const Faces fd = cell_faces<Nd>(g, c), ff = cell_faces<Nf>(g, c);
+  const int k = fd.k;
+  const long l_own = fd.own, l_dn = fd.dn;
+  // direct dof s on the face the beam enters (in = true) or leaves the cell through
+  auto dir_face = [&](int s, bool in) -> long {
+    if (s < Ndt) return (long)s * g.nlev + (in ? l_own : l_dn);
+    if (s < Ndt + Nds) return ((xinc != 0) == in) ? (long)s * g.nlev + l_own : fd.xp + s * fd.xps;
+    return ((yinc != 0) == in) ? (long)s * g.nlev + l_own : fd.yp + s * fd.yps;
+  };
   const bool l1d = k < n1d;
   double a = 0.0;
   if (by_coeff) {
@@ -1185,21 +1212,12 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
         }
       } else {
 #pragma unroll
-        for (int s = 0; s < Nd; ++s) {
-          long q = (s < Ndt) ? l_own : (s < Ndt + Nds) ? l_xin : l_yin;
-          a += edir[(long)s * g.nlev + q] * cdiv_dir[(long)s * g.ncp + c];
-        }
+        for (int s = 0; s < Nd; ++s) a += edir[dir_face(s, true)] * cdiv_dir[(long)s * g.ncp + c];
       }
     }
     if (!l1d) {
 #pragma unroll
-      for (int s = 0; s < Nf; ++s) {
-        long q;
-        if (s < Nft) q = L::top_in(s) ? l_own : l_dn;
-        else if (s < Nft + Nfs) q = L::side_in(s - Nft) ? l_own : l_xp;
-        else q = L::side_in(s - Nft - Nfs) ? l_own : l_yp;
-        a += ediff[(long)s * g.nlev + q] * cdiv_diff[(long)s * g.ncp + c];
-      }
+      for (int s = 0; s < Nf; ++s) a += ediff[diff_face<L>(g, ff, s, false)] * cdiv_diff[(long)s * g.ncp + c];
     } else {
       double cdiv = fmax(0.0, 1.0 - a11[c] - a12[c]);
 #pragma unroll
@@ -1207,13 +1225,7 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
     }
     if (lthermal) {
 #pragma unroll
-      for (int s = 0; s < Nf; ++s) {
-        long q;
-        if (s < Nft) q = L::top_in(s) ? l_dn : l_own;
-        else if (s < Nft + Nfs) q = L::side_in(s - Nft) ? l_xp : l_own;
-        else q = L::side_in(s - Nft - Nfs) ? l_yp : l_own;
-        a -= bsrc[(long)s * g.nlev + q];
-      }
+      for (int s = 0; s < Nf; ++s) a -= bsrc[diff_face<L>(g, ff, s, true)];
     }
   } else {  // by flux divergence (:5400-5472)
     if (lsolar) {
@@ -1221,9 +1233,7 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
       for (int s = 0; s < Ndt; ++s) a += edir[(long)s * g.nlev + l_own] - edir[(long)s * g.nlev + l_dn];
       if (!l1d) {
 #pragma unroll
-        for (int s = Ndt; s < Ndt + Nds; ++s) a += edir[(long)s * g.nlev + l_xin] - edir[(long)s * g.nlev + l_xout];
-#pragma unroll
-        for (int s = Ndt + Nds; s < Nd; ++s) a += edir[(long)s * g.nlev + l_yin] - edir[(long)s * g.nlev + l_yout];
+        for (int s = Ndt; s < Nd; ++s) a += edir[dir_face(s, true)] - edir[dir_face(s, false)];
       }
     }
 #pragma unroll
@@ -1233,17 +1243,7 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
     }
     if (!l1d) {
 #pragma unroll
-      for (int s = 0; s < Nfs; ++s) {
-        long q = (long)(Nft + s) * g.nlev;
-        if (L::side_in(s)) a += ediff[q + l_own] - ediff[q + l_xp];
-        else a += ediff[q + l_xp] - ediff[q + l_own];
-      }
-#pragma unroll
-      for (int s = 0; s < Nfs; ++s) {
-        long q = (long)(Nft + Nfs + s) * g.nlev;
-        if (L::side_in(s)) a += ediff[q + l_own] - ediff[q + l_yp];
-        else a += ediff[q + l_yp] - ediff[q + l_own];
-      }
+      for (int s = Nft; s < Nf; ++s) a += ediff[diff_face<L>(g, ff, s, false)] - ediff[diff_face<L>(g, ff, s, true)];
     }
   }
   abso[c] = a * (1.0 / (g.dx * g.dy * dz[c]));  // abso_scalevec (:5477, :5483-5503)

@@ -181,7 +181,7 @@ struct Solution {  // t_state_container (src/pprts_base.F90:137-169)
   double res_dir = 0, res_diff = 0;
 };
 
-enum { FAM_LOOKUP = 0, FAM_EDIR, FAM_SOURCE, FAM_MATMULT, FAM_PRECOND, FAM_VEC, FAM_ABSO, FAM_IO, FAM_COUNT };
+enum { FAM_LOOKUP = 0, FAM_EDIR, FAM_SOURCE, FAM_MATMULT, FAM_PRECOND, FAM_VEC, FAM_ABSO, FAM_IO, FAM_HALO, FAM_COUNT };
 
 struct Staged {
   double albedo = 0;
@@ -241,9 +241,59 @@ struct pprts_b200_solver {
   // NCCL
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // x/y decomposition: neighbour ranks (rank = xi + yi*nxproc, periodic; src/pprts_base.F90:721-828), halo buffers
+  bool decomposed = false;
+  int nb_west = 0, nb_east = 0, nb_south = 0, nb_north = 0;
+  double glob_ncol = 0;  // global number of columns (KSP tolerances use the global domain, pprts_base.F90:1128-1131)
+  double *hs[2] = {nullptr, nullptr}, *hr[2] = {nullptr, nullptr};  // send / receive staging, [0] x faces, [1] y faces
+  long halo_exchanges = 0;
   int num_sms = 148;
   bool use_tma = true;
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL entry points (dlopen'ed: single-GPU users do not need the library)
+// ---------------------------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_ncclGetUniqueId)(nccl_uid_t *);
+typedef int (*fn_ncclCommInitRank)(void **, int, nccl_uid_t, int);
+typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclSend)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclRecv)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_ncclGroup)(void);
+typedef int (*fn_ncclCommDestroy)(void *);
+typedef const char *(*fn_ncclGetErrorString)(int);
+static struct {
+  void *h = nullptr;
+  fn_ncclGetUniqueId GetUniqueId; fn_ncclCommInitRank CommInitRank; fn_ncclAllReduce AllReduce;
+  fn_ncclSend Send; fn_ncclRecv Recv; fn_ncclGroup GroupStart, GroupEnd;
+  fn_ncclCommDestroy CommDestroy; fn_ncclGetErrorString GetErrorString;
+} g_nccl;
+static const int NCCL_F64 = 8, NCCL_SUM = 0;  // ncclFloat64, ncclSum
+static int load_nccl() {
+  if (g_nccl.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) { g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+  if (!g_nccl.h) return set_err(40, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (fn_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.Send = (fn_ncclSend)dlsym(g_nccl.h, "ncclSend");
+  g_nccl.Recv = (fn_ncclRecv)dlsym(g_nccl.h, "ncclRecv");
+  g_nccl.GroupStart = (fn_ncclGroup)dlsym(g_nccl.h, "ncclGroupStart");
+  g_nccl.GroupEnd = (fn_ncclGroup)dlsym(g_nccl.h, "ncclGroupEnd");
+  g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Send || !g_nccl.Recv ||
+      !g_nccl.GroupStart || !g_nccl.GroupEnd)
+    return set_err(40, "libnccl is missing symbols");
+  return 0;
+}
+#define NC(call)                                                                                              \
+  do {                                                                                                        \
+    int e_ = (call);                                                                                          \
+    if (e_) return set_err(44, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "?"); \
+  } while (0)
 
 static cudaEvent_t get_event(pprts_b200_solver *s) {
   if (!s->evpool.empty()) { cudaEvent_t e = s->evpool.back(); s->evpool.pop_back(); return e; }
@@ -291,6 +341,96 @@ static void collect_events(pprts_b200_solver *s) {
 static inline unsigned int nblk(long n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 static const int VEC_BLOCK = 256;
 static inline unsigned int vec_grid(long n) { return (unsigned int)std::min<long>((n + VEC_BLOCK - 1) / VEC_BLOCK, 148L * 16); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// x/y decomposition: halo exchange over NCCL send/recv (replaces the PETSc VecScatter / MPI_Isend+Irecv of
+// src/pprts_explicit.F90:232-328, :715-848 and the reverse-add of src/pprts_base.F90:1676-1731) and the scalar
+// all-reduce behind every dot product.  All traffic is enqueued on the solver's stream: no host synchronisation.
+// ---------------------------------------------------------------------------------------------------------------
+struct HaloDofs { int d0x, ndx, d0y, ndy; };  // x-side dofs [d0x, d0x+ndx), y-side dofs [d0y, d0y+ndy) of the vector
+
+static int need_comm(const pprts_b200_solver *s) {
+  if (s->decomposed && !s->nccl_comm) return set_err(43, "decomposed solver: call pprts_b200_comm_init first");
+  return 0;
+}
+// sum the n doubles at sc over all ranks (dot products, norms)
+static int allreduce_scalars(pprts_b200_solver *s, double *sc, int n) {
+  if (!s->decomposed) return 0;
+  NC(g_nccl.AllReduce(sc, sc, (size_t)n, NCCL_F64, NCCL_SUM, s->nccl_comm, s->stream));
+  return 0;
+}
+// Ghost FILL: my low faces (i = 0 / j = 0) -> the ghost block of the west / south neighbour; my ghost block <- the
+// low faces of the east / north neighbour.  fill_x / fill_y select the directions (the direct beam needs only one).
+static int halo_fill(pprts_b200_solver *s, double *v, int nd_total, HaloDofs h, bool fill_x, bool fill_y) {
+  const Grid &g = s->g;
+  fill_x = fill_x && g.gx; fill_y = fill_y && g.gy;
+  if (!fill_x && !fill_y) return 0;
+  const size_t nx = (size_t)h.ndx * (g.Nz + 1) * g.Ny, ny = (size_t)h.ndy * (g.Nz + 1) * g.Nx;
+  if (fill_x) LAUNCH(s, FAM_HALO, k_halo_pack, nblk((long)nx, 256), 256, g, 0, h.d0x, h.ndx, v, s->hs[0]);
+  if (fill_y) LAUNCH(s, FAM_HALO, k_halo_pack, nblk((long)ny, 256), 256, g, 1, h.d0y, h.ndy, v, s->hs[1]);
+  NC(g_nccl.GroupStart());
+  if (fill_x) {
+    NC(g_nccl.Send(s->hs[0], nx, NCCL_F64, s->nb_west, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(v + ghost_x_base(g, nd_total) + (size_t)h.d0x * (g.Nz + 1) * g.Ny, nx, NCCL_F64, s->nb_east, s->nccl_comm, s->stream));
+  }
+  if (fill_y) {
+    NC(g_nccl.Send(s->hs[1], ny, NCCL_F64, s->nb_south, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(v + ghost_y_base(g, nd_total) + (size_t)h.d0y * (g.Nz + 1) * g.Nx, ny, NCCL_F64, s->nb_north, s->nccl_comm, s->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  s->halo_exchanges++;
+  return 0;
+}
+// Ghost PUSH: rows this rank produced on its high faces (its ghost block) -> the east / north neighbour, which stores
+// them on its low faces (dofs in maskx / masky, levels [n1d, Nz)); ndot > 0 adds the rows' dot products to `dots`.
+static int halo_push(pprts_b200_solver *s, double *v, int nd_total, HaloDofs h, bool push_x, bool push_y,
+                     unsigned int maskx, unsigned int masky, int ndot, const double *w0, double *dots) {
+  const Grid &g = s->g;
+  push_x = push_x && g.gx; push_y = push_y && g.gy;
+  if (!push_x && !push_y) return 0;
+  const size_t nx = (size_t)h.ndx * (g.Nz + 1) * g.Ny, ny = (size_t)h.ndy * (g.Nz + 1) * g.Nx;
+  NC(g_nccl.GroupStart());
+  if (push_x) {
+    NC(g_nccl.Send(v + ghost_x_base(g, nd_total) + (size_t)h.d0x * (g.Nz + 1) * g.Ny, nx, NCCL_F64, s->nb_east, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(s->hr[0], nx, NCCL_F64, s->nb_west, s->nccl_comm, s->stream));
+  }
+  if (push_y) {
+    NC(g_nccl.Send(v + ghost_y_base(g, nd_total) + (size_t)h.d0y * (g.Nz + 1) * g.Nx, ny, NCCL_F64, s->nb_north, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(s->hr[1], ny, NCCL_F64, s->nb_south, s->nccl_comm, s->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  s->halo_exchanges++;
+  for (int dir = 0; dir < 2; ++dir) {
+    if (!(dir == 0 ? push_x : push_y)) continue;
+    const size_t n = dir == 0 ? nx : ny;
+    const int d0 = dir == 0 ? h.d0x : h.d0y, nd = dir == 0 ? h.ndx : h.ndy;
+    const unsigned int mask = dir == 0 ? maskx : masky;
+    double *tmp = s->sc + SC_TMP;
+    if (ndot == 0)
+      LAUNCH(s, FAM_HALO, k_halo_unpack<0>, nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, s->hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+    else if (ndot == 1)
+      LAUNCH(s, FAM_HALO, k_halo_unpack<1>, nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, s->hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+    else
+      LAUNCH(s, FAM_HALO, k_halo_unpack<2>, nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, s->hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+  }
+  return 0;
+}
+static HaloDofs diff_halo(const pprts_b200_solver *s) {
+  int nft = 2, nfs = 4;
+  DISPATCH_L(s, { nft = L::Nft; nfs = L::Nfs; });
+  return HaloDofs{nft, nfs, nft + nfs, nfs};
+}
+static HaloDofs dir_halo(const pprts_b200_solver *s) {
+  int ndt = 1, nds = 1;
+  DISPATCH_L(s, { ndt = L::Ndt; nds = L::Nds; });
+  return HaloDofs{ndt, nds, ndt + nds, nds};
+}
+// bit d set: side dof d (within its direction) is an inward stream, i.e. produced on the neighbour's high face
+static unsigned int diff_inward_mask(const pprts_b200_solver *s) {
+  unsigned int m = 0;
+  DISPATCH_L(s, { for (int d = 0; d < L::Nfs; ++d) if (L::side_in(d)) m |= 1u << d; });
+  return m;
+}
 
 extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   memset(cfg, 0, sizeof(*cfg));
@@ -393,7 +533,9 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   if (std::fabs(cfg->dx - cfg->dy) > 1e-9 * std::fabs(cfg->dx))  // src/pprts.F90:459
     return set_err(1, "dx and dy currently have to be the same %g vs %g", cfg->dx, cfg->dy);
   if ((cfg->dz1d == nullptr) == (cfg->dz3d == nullptr)) return set_err(1, "have to give either dz1d or dz3d");
-  if ((cfg->nxproc > 1 || cfg->nyproc > 1)) return set_err(1, "x/y decomposition is not available in this build");
+  if (cfg->nxproc < 1 || cfg->nyproc < 1 || cfg->xrank < 0 || cfg->xrank >= cfg->nxproc || cfg->yrank < 0 ||
+      cfg->yrank >= cfg->nyproc)
+    return set_err(1, "bad process grid %d x %d, position (%d, %d)", cfg->nxproc, cfg->nyproc, cfg->xrank, cfg->yrank);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return set_err(90, "no CUDA device: libpprts_b200 has no CPU fallback");
@@ -410,6 +552,9 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   g.ncol = (long)g.Nx * g.Ny; g.ncell = g.ncol * g.Nz; g.nlev = g.ncol * (g.Nz + 1);
   g.ncp = (g.ncell + PB_TILE - 1) / PB_TILE * PB_TILE;  // whole coefficient tiles (tile-blocked layout, common.cuh)
   g.dx = cfg->dx; g.dy = cfg->dy;
+  g.gx = cfg->nxproc > 1; g.gy = cfg->nyproc > 1;
+  s->decomposed = g.gx || g.gy;
+  s->glob_ncol = (double)g.ncol;  // replaced by the sum over ranks in pprts_b200_comm_init
   CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CU(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device));
   s->use_tma = getenv("PPRTS_B200_NO_TMA") == nullptr;
@@ -441,9 +586,13 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   CU(cudaMalloc(&s->f2f, (size_t)Nf * Nf * g.ncp * csz)); CU(cudaMemset(s->f2f, 0, (size_t)Nf * Nf * g.ncp * csz));
   DA(s->cdiv_dir, (size_t)Nd * g.ncp); DA(s->cdiv_diff, (size_t)Nf * g.ncp);
   DA(s->tile_class, (size_t)(g.ncp / PB_TILE));
-  DA(s->b, (size_t)Nf * g.nlev);
-  for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)Nf * g.nlev);
-  DA(s->edir_tmp, (size_t)Nd * g.nlev);
+  DA(s->b, (size_t)state_len(g, Nf));
+  for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)state_len(g, Nf));
+  DA(s->edir_tmp, (size_t)state_len(g, Nd));
+  if (s->decomposed) {
+    const size_t hx = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Ny, hy = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Nx;
+    DA(s->hs[0], hx); DA(s->hr[0], hx); DA(s->hs[1], hy); DA(s->hr[1], hy);
+  }
   DA(s->precR, g.nlev); DA(s->precInv, g.ncell);
   for (int q = 0; q < 4; ++q) { DA(s->res[q], g.nlev); DA(s->acc[q], g.nlev); }
   DA(s->out_stage, (size_t)std::max(Nd, Nf) * g.nlev);
@@ -490,6 +639,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
   cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
+  for (int q = 0; q < 2; ++q) { cudaFree(s->hs[q]); cudaFree(s->hr[q]); }
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_bad);
   for (auto &ev : s->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto e : s->evpool) cudaEventDestroy(e);
@@ -603,7 +753,7 @@ extern "C" int pprts_b200_set_optical_properties_staged(pprts_b200_solver *s, in
 // ---------------------------------------------------------------------------------------------------------------
 static void determine_ksp_tolerances(const pprts_b200_solver *s, double &rtol, double &atol) {  // pprts_base.F90:1128-1131
   rtol = 1e-5;
-  atol = std::max(1e-8, 1e-4 * (double)s->g.Nx * (double)s->g.Ny * (double)(s->g.Nz + 1) * s->unconstrained_fraction);
+  atol = std::max(1e-8, 1e-4 * s->glob_ncol * (double)(s->g.Nz + 1) * s->unconstrained_fraction);
 }
 
 static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
@@ -645,6 +795,16 @@ static int read_scalars(pprts_b200_solver *s) {
 }
 
 // explicit_edir (src/pprts_explicit.F90:60-230)
+// exchange_direct_boundary (src/pprts_explicit.F90:232-328): rows produced on a high face travel downstream to their
+// owner (sun from the west/south: xinc/yinc = 1), or the owner's low face is mirrored into the upstream ghost block
+static int edir_exchange(pprts_b200_solver *s, double *v) {
+  if (!s->decomposed) return 0;
+  const HaloDofs h = dir_halo(s);
+  int rc = halo_fill(s, v, s->Nd, h, s->xinc == 0, s->yinc == 0);
+  if (rc) return rc;
+  return halo_push(s, v, s->Nd, h, s->xinc != 0, s->yinc != 0, ~0u, ~0u, 0, nullptr, nullptr);
+}
+
 static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   const Grid &g = s->g;
   int maxiter = s->cfg.maxit_dir > 0 ? s->cfg.maxit_dir : 1000;
@@ -662,18 +822,24 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   // norm is only read back every `check` passes to keep the host out of the loop.
   const int check = 4;
   int iter = 0;
+  int rc = edir_exchange(s, xold);  // warm-start ghosts from the previous solution (:167)
+  if (rc) return rc;
   while (iter < maxiter && !converged) {
     int nb = std::min(check, maxiter - iter);
     for (int q = 0; q < nb; ++q) {
       DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_pass<L, CT>), nblk(g.ncol, 128), 128, g, s->xinc, s->yinc, s->n1d, fac,
                              (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
+      if ((rc = edir_exchange(s, xnew))) return rc;
+      if (s->decomposed) {  // residual = mean over ranks of the local 2-norms (:176-183)
+        LAUNCH(s, FAM_VEC, k_sqrt_mean, 1, 32, s->sc + SC_EDIR0 + q, 1, 1.0 / (double)s->nranks);
+        if ((rc = allreduce_scalars(s, s->sc + SC_EDIR0 + q, 1))) return rc;
+      }
       std::swap(xold, xnew);
     }
-    int rc = read_scalars(s);
-    if (rc) return rc;
+    if ((rc = read_scalars(s))) return rc;
     for (int q = 0; q < nb; ++q) {
       ++iter;
-      double res = std::max(DBL_MIN, std::sqrt(s->h_sc[SC_EDIR0 + q]));
+      double res = std::max(DBL_MIN, s->decomposed ? s->h_sc[SC_EDIR0 + q] : std::sqrt(s->h_sc[SC_EDIR0 + q]));
       if (iter == 1) res1 = res;
       double rel = (res1 <= std::sqrt(DBL_MIN)) ? 0.0 : res / res1;
       sol.res_dir = res;
@@ -694,7 +860,7 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
 
 static int setup_b(pprts_b200_solver *s, Solution &sol) {
   const Grid &g = s->g;
-  CU(cudaMemsetAsync(s->b, 0, (size_t)s->Nf * g.nlev * sizeof(double), s->stream));
+  CU(cudaMemsetAsync(s->b, 0, (size_t)state_len(g, s->Nf) * sizeof(double), s->stream));
   if (sol.lsolar_rad) {
     DISPATCH_LC(s, LAUNCH(s, FAM_SOURCE, (k_source_solar<L, CT>), nblk(g.ncell, 128), 128, g, s->xinc, s->yinc, s->n1d,
                            (const CT *)s->d2f, s->a13, s->a23, s->albedo, sol.edir, s->b));
@@ -702,6 +868,12 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   if (sol.lthermal_rad) {
     DISPATCH_L(s, LAUNCH(s, FAM_SOURCE, (k_source_thermal<L>), nblk(g.ncell, 128), 128, g, s->n1d, (int)s->have_Bsrfc,
                           s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, s->planck, s->Bsrfc, s->albedo, s->b));
+  }
+  // source emitted into a neighbour's face: stored there by its one producer (replaces halo_reduce_5pt, :4678)
+  if (s->decomposed) {
+    const unsigned int m = diff_inward_mask(s);
+    int rc = halo_push(s, s->b, s->Nf, diff_halo(s), true, true, m, m, 0, nullptr, nullptr);
+    if (rc) return rc;
   }
   return 0;
 }
@@ -738,7 +910,7 @@ static bool launch_matmult_tma(pprts_b200_solver *s, const double *x, double *y,
 }
 
 template <int NDOT>
-static void launch_matmult(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+static void launch_matmult_local(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
   const Grid &g = s->g;
   if (s->cfg.coeff_fp32 && s->use_tma) {
     bool done = false;
@@ -747,6 +919,21 @@ static void launch_matmult(pprts_b200_solver *s, const double *x, double *y, con
   }
   DISPATCH_LC(s, LAUNCH(s, FAM_MATMULT, (k_matmult<L, CT, NDOT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f,
                          s->a11, s->a12, s->albedo, x, y, w, s->partials, s->counter, dots));
+}
+
+// y = (I - T) x on the decomposed domain: ghost fill of x, local kernel, rows produced for the neighbour pushed to
+// their owner (which also adds their share of the fused dot products), dot products summed over the ranks
+template <int NDOT>
+static int launch_matmult(pprts_b200_solver *s, double *x, double *y, const double *w, double *dots) {
+  if (!s->decomposed) { launch_matmult_local<NDOT>(s, x, y, w, dots); return 0; }
+  const HaloDofs h = diff_halo(s);
+  int rc = halo_fill(s, x, s->Nf, h, true, true);
+  if (rc) return rc;
+  launch_matmult_local<NDOT>(s, x, y, w, dots);
+  const unsigned int m = diff_inward_mask(s);
+  if ((rc = halo_push(s, y, s->Nf, h, true, true, m, m, NDOT, w, dots))) return rc;
+  if (NDOT > 0) rc = allreduce_scalars(s, dots, NDOT);
+  return rc;
 }
 
 static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond == 1 && s->cfg.solver_id != 324; }
@@ -781,23 +968,26 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
   double *x = sol.ediff, *r = s->kr[0], *rh = s->kr[1], *p = s->kr[2], *v = s->kr[3], *sv = s->kr[4], *t = s->kr[5];
   const bool prec = precond_available(s);
   double *ph = prec ? s->kr[6] : p, *sh = prec ? s->kr[7] : sv;
-  launch_matmult<0>(s, x, r, nullptr, nullptr);
-  LAUNCH(s, FAM_VEC, k_bicg_init, vec_grid(n), VEC_BLOCK, n, s->b, r, rh, p, v, s->partials, s->counter, s->sc);
-  int rc = read_scalars(s);
+  int rc = need_comm(s);
   if (rc) return rc;
+  if ((rc = launch_matmult<0>(s, x, r, nullptr, nullptr))) return rc;
+  LAUNCH(s, FAM_VEC, k_bicg_init, vec_grid(n), VEC_BLOCK, n, s->b, r, rh, p, v, s->partials, s->counter, s->sc);
+  if ((rc = allreduce_scalars(s, s->sc + SC_RR, 2))) return rc;
+  if ((rc = read_scalars(s))) return rc;
   const double r0 = std::max(DBL_MIN, std::sqrt(s->h_sc[SC_RR]));
   sol.niter_diff = 0;
   sol.res_diff = r0;
   bool converged = false;
   if (r0 <= atol) converged = true;  // x already solves the system to tolerance (warm start)
   for (int it = 1; it <= maxit && !converged; ++it) {
-    LAUNCH(s, FAM_VEC, k_bicg_update_p, vec_grid(n), VEC_BLOCK, n, r, v, p, s->sc);
+    LAUNCH(s, FAM_VEC, k_bicg_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
     if (prec) launch_prec(s, p, ph);
-    launch_matmult<1>(s, ph, v, rh, s->sc + SC_RHV);
-    LAUNCH(s, FAM_VEC, k_bicg_update_s, vec_grid(n), VEC_BLOCK, n, r, v, sv, s->sc);
+    if ((rc = launch_matmult<1>(s, ph, v, rh, s->sc + SC_RHV))) return rc;
+    LAUNCH(s, FAM_VEC, k_bicg_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
     if (prec) launch_prec(s, sv, sh);
-    launch_matmult<2>(s, sh, t, sv, s->sc + SC_TS);
-    LAUNCH(s, FAM_VEC, k_bicg_update_xr, vec_grid(n), VEC_BLOCK, n, ph, sh, sv, t, rh, x, r, s->partials, s->counter, s->sc);
+    if ((rc = launch_matmult<2>(s, sh, t, sv, s->sc + SC_TS))) return rc;
+    LAUNCH(s, FAM_VEC, k_bicg_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, x, r, s->partials, s->counter, s->sc);
+    if ((rc = allreduce_scalars(s, s->sc + (((it + 1) & 1) ? SC_RR : SC_RHO0), 2))) return rc;
     if ((rc = read_scalars(s))) return rc;
     const double rn = std::sqrt(s->h_sc[SC_RR]);
     sol.niter_diff = it;
@@ -816,6 +1006,10 @@ static int calc_flx_div(pprts_b200_solver *s, Solution &sol) {
   const Grid &g = s->g;
   int rc = scale_flx(s, sol, false);
   if (rc) return rc;
+  if (s->decomposed) {  // the cell balance reads the streams entering through the high faces
+    if ((rc = halo_fill(s, sol.ediff, s->Nf, diff_halo(s), true, true))) return rc;
+    if (sol.lsolar_rad && (rc = halo_fill(s, sol.edir, s->Nd, dir_halo(s), s->xinc == 0, s->yinc == 0))) return rc;
+  }
   DISPATCH_L(s, LAUNCH(s, FAM_ABSO, (k_absorption<L>), nblk(g.ncell, 128), 128, g, s->xinc, s->yinc, s->n1d,
                         (int)sol.lsolar_rad, (int)sol.lthermal_rad, s->cfg.by_coeff_divergence, s->costheta, s->cdiv_dir,
                         s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, sol.edir, sol.ediff, s->b, sol.abso));
@@ -827,7 +1021,7 @@ static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool ltherma
   const int key = s->cfg.keep_solutions ? uid : 0;
   Solution &sol = s->solutions[key];
   auto prepare = [&]() -> int {  // prepare_solution (src/pprts_base.F90:297-344)
-    if (!sol.edir) { DA(sol.edir, (size_t)s->Nd * g.nlev); DA(sol.ediff, (size_t)s->Nf * g.nlev); DA(sol.abso, g.ncell); }
+    if (!sol.edir) { DA(sol.edir, (size_t)state_len(g, s->Nd)); DA(sol.ediff, (size_t)state_len(g, s->Nf)); DA(sol.abso, g.ncell); }
     else {
       CU(cudaMemsetAsync(sol.edir, 0, (size_t)s->Nd * g.nlev * sizeof(double), s->stream));
       CU(cudaMemsetAsync(sol.ediff, 0, (size_t)s->Nf * g.nlev * sizeof(double), s->stream));
@@ -883,6 +1077,7 @@ extern "C" int pprts_b200_solve(pprts_b200_solver *s, int lthermal, int lsolar, 
     sol.lchanged = false;
     return 0;
   }
+  if ((rc = need_comm(s))) return rc;
   if ((rc = ensure_coeffs(s, sol.lsolar_rad))) return rc;
   if ((rc = scale_flx(s, sol, false))) return rc;
   if (sol.lsolar_rad && (rc = solve_edir(s, sol, edirTOA))) return rc;
@@ -890,6 +1085,7 @@ extern "C" int pprts_b200_solve(pprts_b200_solver *s, int lthermal, int lsolar, 
   // b_norm = sum(abs(b)); skip the diffuse solve if < atol (src/pprts.F90:2774-2785)
   const long n = (long)s->Nf * g.nlev;
   LAUNCH(s, FAM_VEC, k_norm1, vec_grid(n), VEC_BLOCK, n, s->b, s->partials, s->counter, s->sc + SC_BNORM1);
+  if ((rc = allreduce_scalars(s, s->sc + SC_BNORM1, 1))) return rc;
   if ((rc = read_scalars(s))) return rc;
   double rtol, atol;
   determine_ksp_tolerances(s, rtol, atol);
@@ -984,30 +1180,6 @@ extern "C" int pprts_b200_get_accumulated(pprts_b200_solver *s, double *edn, dou
 // ---------------------------------------------------------------------------------------------------------------
 // NCCL (dlopen'ed: single-GPU users do not need the library)
 // ---------------------------------------------------------------------------------------------------------------
-typedef struct { char internal[128]; } nccl_uid_t;
-typedef int (*fn_ncclGetUniqueId)(nccl_uid_t *);
-typedef int (*fn_ncclCommInitRank)(void **, int, nccl_uid_t, int);
-typedef int (*fn_ncclAllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
-typedef int (*fn_ncclCommDestroy)(void *);
-typedef const char *(*fn_ncclGetErrorString)(int);
-static struct {
-  void *h = nullptr;
-  fn_ncclGetUniqueId GetUniqueId; fn_ncclCommInitRank CommInitRank; fn_ncclAllReduce AllReduce;
-  fn_ncclCommDestroy CommDestroy; fn_ncclGetErrorString GetErrorString;
-} g_nccl;
-static int load_nccl() {
-  if (g_nccl.h) return 0;
-  const char *names[] = {"libnccl.so.2", "libnccl.so"};
-  for (const char *nm : names) { g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
-  if (!g_nccl.h) return set_err(40, "cannot dlopen libnccl.so.2: %s", dlerror());
-  g_nccl.GetUniqueId = (fn_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
-  g_nccl.CommInitRank = (fn_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
-  g_nccl.AllReduce = (fn_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
-  g_nccl.CommDestroy = (fn_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
-  g_nccl.GetErrorString = (fn_ncclGetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return set_err(40, "libnccl is missing symbols");
-  return 0;
-}
 extern "C" int pprts_b200_nccl_unique_id(char id[128]) {
   int rc = load_nccl();
   if (rc) return rc;
@@ -1023,13 +1195,32 @@ extern "C" int pprts_b200_comm_init(pprts_b200_solver *s, int nranks, int rank, 
   CU(cudaSetDevice(s->device));
   nccl_uid_t u;
   memcpy(u.internal, id, 128);
+  if (s->decomposed) {
+    const int nxp = s->cfg.nxproc, nyp = s->cfg.nyproc, xi = s->cfg.xrank, yi = s->cfg.yrank;
+    if (nranks != nxp * nyp) return set_err(45, "communicator has %d ranks, the process grid is %d x %d", nranks, nxp, nyp);
+    if (rank != xi + yi * nxp)  // PETSc DMDA / MPI_Cart order, x fastest (src/pprts_base.F90:745-773)
+      return set_err(45, "rank %d does not sit at (%d, %d) of a %d x %d grid (rank = xi + yi*nxproc)", rank, xi, yi, nxp, nyp);
+    s->nb_west = (xi + nxp - 1) % nxp + yi * nxp;
+    s->nb_east = (xi + 1) % nxp + yi * nxp;
+    s->nb_south = xi + ((yi + nyp - 1) % nyp) * nxp;
+    s->nb_north = xi + ((yi + 1) % nyp) * nxp;
+  }
   if ((rc = g_nccl.CommInitRank(&s->nccl_comm, nranks, u, rank))) return set_err(42, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
   s->nranks = nranks; s->rank = rank;
+  if (s->decomposed) {  // global column count for the solver tolerances; also checks the face lengths of the neighbours
+    double h[3] = {(double)s->g.ncol, 0, 0};
+    CU(cudaMemcpyAsync(s->sc + SC_TMP, h, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    NC(g_nccl.AllReduce(s->sc + SC_TMP, s->sc + SC_TMP, 1, NCCL_F64, NCCL_SUM, s->nccl_comm, s->stream));
+    CU(cudaMemcpyAsync(h, s->sc + SC_TMP, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->glob_ncol = h[0];
+  }
   return 0;
 }
 extern "C" int pprts_b200_allreduce_accumulated(pprts_b200_solver *s) {
   if (!s) return set_err(1, "null solver");
   if (!s->nccl_comm) return s->nranks == 1 ? 0 : set_err(43, "communicator not initialised");
+  if (s->decomposed) return set_err(46, "band sharding and x/y decomposition share one communicator: use one of them");
   CU(cudaSetDevice(s->device));
   for (int q = 0; q < 4; ++q) {
     int rc = g_nccl.AllReduce(s->acc[q], s->acc[q], (size_t)s->g.nlev, /*ncclFloat64*/ 8, /*ncclSum*/ 0, s->nccl_comm, s->stream);
@@ -1092,7 +1283,7 @@ extern "C" int pprts_b200_mat_mult_ediff(pprts_b200_solver *s, const double *x, 
   const long n = (long)s->Nf * g.nlev;
   CU(cudaMemcpyAsync(s->out_stage, x, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   LAUNCH(s, FAM_IO, k_state_from_host_layout, nblk(n, 256), 256, g, s->Nf, s->out_stage, s->kr[6]);
-  launch_matmult<0>(s, s->kr[6], s->kr[7], nullptr, nullptr);
+  if ((rc = need_comm(s)) || (rc = launch_matmult<0>(s, s->kr[6], s->kr[7], nullptr, nullptr))) return rc;
   LAUNCH(s, FAM_IO, k_state_to_host_layout, nblk(n, 256), 256, g, s->Nf, s->kr[7], s->out_stage);
   CU(cudaMemcpyAsync(y, s->out_stage, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -1143,9 +1334,10 @@ extern "C" int pprts_b200_enable_kernel_timing(pprts_b200_solver *s, int on) {
   s->timing = on != 0;
   return 0;
 }
-extern "C" int pprts_b200_kernel_stats(pprts_b200_solver *s, int reset, double ms[8], long launches[8]) {
+extern "C" int pprts_b200_kernel_stats(pprts_b200_solver *s, int reset, double ms[16], long launches[16]) {
   if (!s) return set_err(1, "null solver");
   collect_events(s);
+  for (int q = 0; q < 16; ++q) { ms[q] = 0; launches[q] = 0; }
   for (int q = 0; q < FAM_COUNT; ++q) { ms[q] = s->fam_ms[q]; launches[q] = s->fam_launch[q]; }
   if (reset) for (int q = 0; q < FAM_COUNT; ++q) { s->fam_ms[q] = 0; s->fam_launch[q] = 0; }
   return 0;

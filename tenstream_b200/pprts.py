@@ -206,11 +206,12 @@ class Solver:
     def enable_kernel_timing(self, on=True):
         _chk(lib().pprts_b200_enable_kernel_timing(self._h, int(on)), "enable_kernel_timing")
 
-    FAMILIES = ["lookup", "edir", "source", "matmult", "precond", "vector", "absorption_result", "ingest_egress"]
+    FAMILIES = ["lookup", "edir", "source", "matmult", "precond", "vector", "absorption_result", "ingest_egress",
+                "halo"]
 
     def kernel_stats(self, reset=False):
-        ms = (C.c_double * 8)()
-        ln = (C.c_long * 8)()
+        ms = (C.c_double * 16)()
+        ln = (C.c_long * 16)()
         _chk(lib().pprts_b200_kernel_stats(self._h, int(reset), ms, ln), "kernel_stats")
         return {f: dict(ms=ms[q], launches=ln[q]) for q, f in enumerate(self.FAMILIES)}
 
@@ -267,10 +268,15 @@ def _alloc_results(s):
 def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=None, nxproc=None, nyproc=None,
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
-               keep_solutions=True) -> Solver:
+               keep_solutions=True, rank=None) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
-    arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...)."""
+    arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
+
+    x/y decomposition (src/pprts_base.F90:721-828): as in the reference, ``nxproc`` / ``nyproc`` list the number of
+    columns every process owns along x / y, ``Nx, Ny`` are then this process's LOCAL sizes, and the process grid is
+    x-fastest (``rank = xi + yi*len(nxproc)``).  ``rank`` is this process's rank in the communicator (default: the
+    ``RANK`` environment variable); ``Solver.comm_init`` must be called before the first solve."""
     if collapseindex is not None and collapseindex > 1:
         raise PprtsError("collapseindex > 1 (atmosphere collapse, src/pprts.F90:2080-2198) is not supported")
     if (dz1d is None) == (dz3d is None):
@@ -301,6 +307,15 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.precond, cfg.device, cfg.keep_solutions = int(precond), int(device), int(keep_solutions)
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
+    if cfg.nxproc * cfg.nyproc > 1:
+        r = int(os.environ.get("RANK", 0)) if rank is None else int(rank)
+        cfg.xrank, cfg.yrank = r % cfg.nxproc, r // cfg.nxproc
+        if cfg.yrank >= cfg.nyproc:
+            raise PprtsError(f"rank {r} is outside the {cfg.nxproc} x {cfg.nyproc} process grid")
+        want = (int(nxproc[cfg.xrank]) if nxproc is not None else Nx, int(nyproc[cfg.yrank]) if nyproc is not None else Ny)
+        if (Nx, Ny) != want:
+            raise PprtsError(f"local domain {(Nx, Ny)} does not match nxproc/nyproc {want} at grid position "
+                             f"({cfg.xrank}, {cfg.yrank})")
     h = C.c_void_p()
     _chk(lib().pprts_b200_create(C.byref(cfg), lut._h, C.byref(h)), "init_pprts")
     Nd, Nf = _lut.solver_dofs(int(solver))

@@ -1,0 +1,107 @@
+"""x/y domain decomposition with NCCL halo exchange on 2 GPUs (run with `gpurun --gpus 2 -- pytest -m gpu`): the
+decomposed solve must reproduce the single-GPU solve of the same global problem (the reference's DMDA runs are checked
+the same way, against the 1-rank result).  Skipped when fewer than 2 devices are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tenstream_b200 import lut as L
+    from tenstream_b200 import pprts as P
+    from tenstream_b200 import scenarios
+    from tenstream_b200.parallel import CartDecomposition
+    cfg = L.small_test_config(solver_id)
+    lut = P.Lut(cfg, paths)
+    sc = scenarios.cloud_field(Nx=18, Ny=14, Nz=10, dx=100., dz=60., seed=11, phi0=phi0, theta0=50.)
+    sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
+    dec = CartDecomposition(sc["Nx"], sc["Ny"], nxp, nyp, rank)
+    kw = dict(dz1d=sc["dz1d"], lut=lut, device=rank, rtol=1e-10, atol=1e-30, solver=solver_id)
+    s = P.init_pprts(0, sc["Nz"], dec.xm, dec.ym, sc["dx"], sc["dy"], sd, nxproc=dec.nxproc, nyproc=dec.nyproc,
+                     rank=rank, **kw)
+    uid = [P.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    s.comm_init(world, rank, uid[0])
+    loc = lambda a: np.asfortranarray(dec.local(a))    # noqa: E731
+    out = {}
+    # diffuse operator on a random global vector: exercises ghost fill + push without any solver on top
+    xg = np.random.default_rng(3).random((s.Nf, sc["Nz"] + 1, sc["Nx"], sc["Ny"]))
+    P.set_optical_properties(s, sc["albedo"], loc(sc["kabs"]), loc(sc["ksca"]), loc(sc["g"]))
+    out["matmult"] = s.mat_mult_ediff(loc(xg))
+    P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+    out["solar"] = P.pprts_get_result(s, 1)
+    out["solar_info"] = s.info(1)
+    P.set_optical_properties(s, sc["albedo_th"], loc(sc["kabs_th"]), loc(sc["ksca_th"]), loc(sc["g_th"]),
+                             planck=loc(sc["planck"]), planck_srfc=loc(sc["planck_srfc"]))
+    P.solve_pprts(s, True, False, 0.0, 2)
+    out["thermal"] = P.pprts_get_result(s, 2)
+    ref = None
+    if rank == 0:      # the same global problem on one GPU
+        g = P.init_pprts(0, sc["Nz"], sc["Nx"], sc["Ny"], sc["dx"], sc["dy"], sd, **kw)
+        ref = {}
+        P.set_optical_properties(g, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+        ref["matmult"] = g.mat_mult_ediff(xg)
+        P.solve_pprts(g, False, True, sc["edirTOA"], 1)
+        ref["solar"] = P.pprts_get_result(g, 1)
+        P.set_optical_properties(g, sc["albedo_th"], sc["kabs_th"], sc["ksca_th"], sc["g_th"], planck=sc["planck"],
+                                 planck_srfc=sc["planck_srfc"])
+        P.solve_pprts(g, True, False, 0.0, 2)
+        ref["thermal"] = P.pprts_get_result(g, 2)
+        P.destroy_pprts(g)
+    q.put((rank, (dec.xs, dec.xm, dec.ys, dec.ym), out, ref))
+    dist.barrier()
+    P.destroy_pprts(s)
+    dist.destroy_process_group()
+
+
+def _run(paths, nxp, nyp, solver_id, phi0):
+    import torch
+    import torch.multiprocessing as mp
+    world = nxp * nyp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, box, out, ref = q.get(timeout=900)
+        res[r] = (box, out, ref)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = res[0][2]
+    for r in range(world):
+        (xs, xm, ys, ym), out, _ = res[r]
+        sl = (slice(None), slice(xs, xs + xm), slice(ys, ys + ym))
+        want = ref["matmult"][(slice(None),) + sl]
+        assert np.abs(out["matmult"] - want).max() <= 1e-13 * np.abs(want).max(), (r, "matmult")
+        for band in ("solar", "thermal"):
+            for name, a, b in zip(("edn", "eup", "abso", "edir"), out[band], ref[band]):
+                b = b[sl]
+                scale = np.abs(ref[band][("edn", "eup", "abso", "edir").index(name)]).max()
+                if scale == 0:
+                    assert np.abs(a).max() == 0
+                    continue
+                err = np.abs(a - b).max() / scale
+                assert err < 2e-7, (r, band, name, err)     # both runs solve to rtol 1e-10; Krylov paths differ
+
+
+@pytest.mark.parametrize("nxp,nyp,phi0", [(2, 1, 120.0), (1, 2, 120.0), (2, 1, 300.0), (1, 2, 300.0)])
+def test_decomposed_matches_single_gpu_3_10(small_lut, nxp, nyp, phi0):
+    _, paths = small_lut
+    _run(paths, nxp, nyp, 310, phi0)

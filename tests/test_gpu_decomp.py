@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, q):
+def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank))
@@ -23,6 +23,9 @@ def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, q):
     cfg = L.small_test_config(solver_id)
     lut = P.Lut(cfg, paths)
     sc = scenarios.cloud_field(Nx=18, Ny=14, Nz=10, dx=100., dz=60., seed=11, phi0=phi0, theta0=50.)
+    if thick_top:      # three thick layers on top become 1-D (twostr) layers: dz/dx > twostr_ratio (pprts.F90:649-725)
+        sc["dz1d"] = sc["dz1d"].copy()
+        sc["dz1d"][:3] = 250.0
     sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
     dec = CartDecomposition(sc["Nx"], sc["Ny"], nxp, nyp, rank)
     kw = dict(dz1d=sc["dz1d"], lut=lut, device=rank, rtol=1e-10, atol=1e-30, solver=solver_id)
@@ -63,7 +66,7 @@ def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, q):
     dist.destroy_process_group()
 
 
-def _run(paths, nxp, nyp, solver_id, phi0):
+def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False):
     import torch
     import torch.multiprocessing as mp
     world = nxp * nyp
@@ -74,7 +77,7 @@ def _run(paths, nxp, nyp, solver_id, phi0):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -105,3 +108,22 @@ def _run(paths, nxp, nyp, solver_id, phi0):
 def test_decomposed_matches_single_gpu_3_10(small_lut, nxp, nyp, phi0):
     _, paths = small_lut
     _run(paths, nxp, nyp, 310, phi0)
+
+
+def test_decomposed_with_1d_layers(small_lut):
+    _, paths = small_lut
+    _run(paths, 2, 1, 310, 120.0, thick_top=True)
+    _run(paths, 1, 2, 310, 300.0, thick_top=True)
+
+
+@pytest.mark.parametrize("nxp,nyp,phi0", [(2, 1, 200.0), (1, 2, 20.0)])
+def test_decomposed_matches_single_gpu_8_10(tmp_path_factory, nxp, nyp, phi0):
+    from tenstream_b200 import lut as L
+    cfg = L.small_test_config(810)
+    paths = L.write_synthetic_lut(cfg, str(tmp_path_factory.mktemp("lut810d") / "LUT"))
+    _run(paths, nxp, nyp, 810, phi0)
+
+
+def test_decomposed_2x2_four_gpus(small_lut):
+    _, paths = small_lut
+    _run(paths, 2, 2, 310, 120.0)

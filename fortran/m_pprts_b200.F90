@@ -79,6 +79,14 @@ module m_pprts_b200
       integer(c_int), value :: uid
       type(c_ptr), value :: edn, eup, abso, edir
     end function
+    integer(c_int) function c_nccl_unique_id(id) bind(c, name='pprts_b200_nccl_unique_id')
+      import; character(kind=c_char), intent(out) :: id(128)
+    end function
+    integer(c_int) function c_comm_init(solver, nranks, rank, id) bind(c, name='pprts_b200_comm_init')
+      import; type(c_ptr), value :: solver
+      integer(c_int), value :: nranks, rank
+      character(kind=c_char), intent(in) :: id(128)
+    end function
     function c_last_error() bind(c, name='pprts_b200_last_error') result(msg)
       import; type(c_ptr) :: msg
     end function
@@ -118,8 +126,12 @@ contains
     call chkerr(c_lut_close(lut%h), 'lut_close'); lut%h = c_null_ptr
   end subroutine
 
-  !> init_pprts (src/pprts.F90:213): icomm is kept in the signature; one process drives one GPU
-  subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, device)
+  !> init_pprts (src/pprts.F90:213).  One MPI rank drives one GPU.  With nxproc/nyproc (columns per process along x/y,
+  !> exactly the reference's optional arguments) the domain is decomposed DMDA-style: Nx, Ny are then LOCAL sizes, the
+  !> process grid is x-fastest (rank = xi + yi*size(nxproc), src/pprts_base.F90:745-773), and the NCCL communicator of
+  !> the halo exchange is bootstrapped over icomm (rank 0 creates the NCCL id, MPI_Bcast distributes it).
+  subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, nxproc, nyproc, device)
+    use mpi
     integer, intent(in) :: icomm
     integer(iintegers), intent(in) :: Nz, Nx, Ny
     real(ireals), intent(in) :: dx, dy, sundir(3)
@@ -127,16 +139,29 @@ contains
     type(t_lut_b200), intent(in) :: lut
     integer(iintegers), intent(in) :: solver_id
     real(ireals), intent(in), target, optional :: dz1d(:), dz3d(:, :, :)
+    integer(iintegers), intent(in), optional :: nxproc(:), nyproc(:)
     integer(iintegers), intent(in), optional :: device
     type(c_config) :: cfg
+    character(kind=c_char) :: nccl_id(128)
+    integer :: myid, nranks, ierr
     call c_default_config(cfg)
     cfg%solver_id = solver_id; cfg%Nz = Nz; cfg%Nx = Nx; cfg%Ny = Ny; cfg%dx = dx; cfg%dy = dy; cfg%sundir = sundir
     if (present(dz1d)) cfg%dz1d = c_loc(dz1d)
     if (present(dz3d)) cfg%dz3d = c_loc(dz3d)
     if (present(device)) cfg%device = device
+    if (present(nxproc) .and. present(nyproc)) then
+      call mpi_comm_rank(icomm, myid, ierr)
+      call mpi_comm_size(icomm, nranks, ierr)
+      cfg%nxproc = size(nxproc); cfg%nyproc = size(nyproc)
+      cfg%xrank = modulo(myid, cfg%nxproc); cfg%yrank = myid / cfg%nxproc
+    end if
     call chkerr(c_create(cfg, lut%h, solver%h), 'init_pprts')
     solver%Nz = Nz; solver%Nx = Nx; solver%Ny = Ny
-    if (.false.) print *, icomm
+    if (cfg%nxproc * cfg%nyproc .gt. 1) then
+      if (myid .eq. 0) call chkerr(c_nccl_unique_id(nccl_id), 'nccl_unique_id')
+      call mpi_bcast(nccl_id, 128, MPI_CHARACTER, 0, icomm, ierr)
+      call chkerr(c_comm_init(solver%h, int(nranks, c_int), int(myid, c_int), nccl_id), 'comm_init')
+    end if
   end subroutine
 
   subroutine set_angles(solver, sundir)

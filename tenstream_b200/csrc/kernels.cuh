@@ -927,7 +927,7 @@ template <class L, class CT>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
           const double *__restrict__ R, const double *__restrict__ inv, const double *__restrict__ r,
-          double *__restrict__ z) {
+          double *__restrict__ z, int sides) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   static_assert(Nft == 2, "column preconditioner needs one up/down pair of top streams");
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -953,8 +953,10 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (L::side_in(d % Nfs)) {
           z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
-          fU = fma(widen(cur.t0[q]), cur.rs[d], fU);
-          fD = fma(widen(cur.t1[q]), cur.rs[d], fD);
+          if (sides) {
+            fU = fma(widen(cur.t0[q]), cur.rs[d], fU);
+            fD = fma(widen(cur.t1[q]), cur.rs[d], fD);
+          }
           ++q;
         }
       }
@@ -1012,7 +1014,7 @@ template <class L, class CT>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const double *__restrict__ R, const double *__restrict__ inv,
-            const double *__restrict__ r, double *z) {
+            const double *__restrict__ r, double *z, int sides) {
   constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
@@ -1034,12 +1036,14 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (!L::side_in(d % Nfs)) {
           double acc = cur.rsd[d];
+          if (sides) {
           acc = fma(widen(cur.tt[o][0]), U1, acc);
           acc = fma(widen(cur.tt[o][1]), D, acc);
           int q = 0;
 #pragma unroll
           for (int s = 0; s < 2 * Nfs; ++s)
             if (L::side_in(s % Nfs)) { acc = fma(widen(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
+          }
           z[(long)(Nft + d) * g.nlev + c] = acc;
           ++o;
         }

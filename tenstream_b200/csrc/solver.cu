@@ -936,7 +936,7 @@ static int launch_matmult(pprts_b200_solver *s, double *x, double *y, const doub
   return rc;
 }
 
-static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond == 1 && s->cfg.solver_id != 324; }
+static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond >= 1 && s->cfg.solver_id != 324; }
 
 template <class L, class CT>
 static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
@@ -948,9 +948,9 @@ static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
       s->prec_ready = true;
     }
     LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           s->precR, s->precInv, r, z);
+           s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
     LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           s->precR, s->precInv, r, z);
+           s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
   }
 }
 static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, launch_prec_t<L, CT>(s, r, z)); }

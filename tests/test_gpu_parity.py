@@ -333,6 +333,51 @@ def test_solver_8_10_vs_oracle(P, luts_810, phi0, theta0):
     P.destroy_pprts(s); o.destroy()
 
 
+@pytest.fixture(scope="module")
+def luts_324(P, tmp_path_factory):
+    from oracle import binding as ob
+    from tenstream_b200 import lut as L
+    cfg = L.small_test_config(324)
+    paths = L.write_synthetic_lut(cfg, str(tmp_path_factory.mktemp("lut324") / "LUT"))
+    glut, olut = P.Lut(cfg, paths), ob.OracleLut(cfg, paths)
+    yield glut, olut
+    glut.close()
+
+
+@pytest.mark.parametrize("phi0,theta0", [(30., 35.), (160., 55.), (250., 20.)])
+@pytest.mark.parametrize("coeff_fp32", [False, True])
+def test_solver_3_24_vs_oracle(P, luts_324, phi0, theta0, coeff_fp32):
+    """24 diffuse streams (8 top + 8 + 8 side, side streams start with an inward one, src/pprts.F90:386-390) incl. the
+    dir3_to_diff24 permutation (src/optprop.F90:1098-1124); the shell operator's albedo row couples inv_dof pairs only
+    (src/pprts_shell.F90:500-505).  Solar and thermal, operator and solution."""
+    from oracle import binding as ob
+    glut, olut = luts_324
+    rng = np.random.default_rng(24)
+    Nz, Nx, Ny = 6, 5, 7
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    dz = np.full(Nz, 60.)
+    sd = P.sundir_from_angles(phi0, theta0)
+    tol = dict(rtol=1e-10, atol=1e-30)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, solver=324, dz1d=dz, lut=glut, coeff_fp32=coeff_fp32, **tol)
+    o = ob.OracleSolver(olut, Nz, Nx, Ny, 100., 100., sd, dz, solver_id=324, diff_solver=1, coeff_fp32=coeff_fp32, **tol)
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    o.set_optical_properties(0.2, kabs, ksca, g)
+    x = rng.random((24, Nz + 1, Nx, Ny))
+    P.solve_pprts(s, False, True, 1000.)
+    assert o.solve(False, True, 1000.) == 0
+    assert relerr(s.mat_mult_ediff(x), o.mat_mult_ediff(x)) < 1e-13
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b) < 1e-7, name
+    planck = np.broadcast_to(np.linspace(60., 120., Nz + 1)[:, None, None], (Nz + 1, Nx, Ny)).copy()
+    P.set_optical_properties(s, 0.05, kabs * 5, ksca, g, planck=planck)
+    o.set_optical_properties(0.05, kabs * 5, ksca, g, planck=planck)
+    P.solve_pprts(s, True, False, 0., 3)
+    assert o.solve(True, False, 0., 3) == 0
+    for name, a, b in zip(("edn", "eup", "abso"), P.pprts_get_result(s, 3), o.get_result(3)):
+        assert relerr(a, b) < 1e-7, name
+    P.destroy_pprts(s); o.destroy()
+
+
 def test_f2c_entry_points(P, small_lut, oracle_lut):
     """c_wrapper/pprts.c call sequence through the reference's own C symbols (float arrays [Ny][Nx][Nz])"""
     import ctypes as C

@@ -101,6 +101,16 @@ __device__ __forceinline__ double widen_normal_or_zero(float f) {
   return __hiloint2double((int)hi, (int)(unsigned int)r);
 }
 
+// Signed variant for the fp32 Krylov work vectors (values of either sign, exact zeros are common): normal numbers and
+// +-0 stay on the integer ALU, subnormals / inf / nan take cvt.  Bit-identical to (double)f.
+__device__ __forceinline__ double widen_any(float f) {
+  const unsigned int b = __float_as_uint(f), m = b & 0x7fffffffu;
+  if (__builtin_expect((m - 0x00800000u) < 0x7f000000u || m == 0u, 1))
+    return __hiloint2double((int)(((m >> 3) + (m ? 0x38000000u : 0u)) | (b & 0x80000000u)), (int)(b << 29));
+  return (double)f;
+}
+__device__ __forceinline__ double widen_any(double f) { return f; }
+
 __device__ __forceinline__ long lidx(const Grid &g, int k, int j, int i) { return ((long)k * g.Ny + j) * g.Nx + i; }
 __device__ __forceinline__ int wrap_p(int i, int n) { return (i + 1 == n) ? 0 : i + 1; }
 

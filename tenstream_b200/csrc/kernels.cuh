@@ -615,32 +615,32 @@ struct MatIn {
   double xs[L::Nf], xd[L::Nf];
   double wd[L::Nf];  // dot-product weight w0 at the destination row of stream d (NDOT > 0)
 };
-template <class L, int NDOT>
-__device__ __forceinline__ void matmult_load(const Grid &g, const Faces &f, const double *__restrict__ x,
-                                             const double *__restrict__ w0, MatIn<L> &in) {
+template <class L, int NDOT, class VT>
+__device__ __forceinline__ void matmult_load(const Grid &g, const Faces &f, const VT *__restrict__ x,
+                                             const VT *__restrict__ w0, MatIn<L> &in) {
 #pragma unroll
   for (int d = 0; d < L::Nf; ++d) {
     const long qd = diff_face<L>(g, f, d, true);
-    in.xs[d] = x[diff_face<L>(g, f, d, false)];
-    in.xd[d] = x[qd];
-    if (NDOT > 0) in.wd[d] = diff_exit_is_ghost<L>(f, d) ? 0.0 : w0[qd];  // ghost rows: the owner adds its share
+    in.xs[d] = widen_any(x[diff_face<L>(g, f, d, false)]);
+    in.xd[d] = widen_any(x[qd]);
+    if (NDOT > 0) in.wd[d] = diff_exit_is_ghost<L>(f, d) ? 0.0 : widen_any(w0[qd]);  // ghost rows: the owner adds its share
   }
 }
-template <class L, int NDOT, class COEF>
+template <class L, int NDOT, class COEF, class VT>
 __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, const Faces &f,
                                              const MatIn<L> &in, const double *__restrict__ a11,
                                              const double *__restrict__ a12, const double *__restrict__ albedo,
-                                             const double *__restrict__ x, double *__restrict__ y,
-                                             const double *__restrict__ w0, double *dots) {
+                                             const VT *__restrict__ x, VT *__restrict__ y,
+                                             const VT *__restrict__ w0, double *dots) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   // NDOT == 1: dots[0] = sum w0*y ; NDOT == 2: dots[0] = sum y*w0, dots[1] = sum y*y
   auto emit = [&](long q, double val) {  // rare rows: weight loaded on the spot
-    y[q] = val;
-    if (NDOT >= 1) dots[0] += val * w0[q];
+    y[q] = (VT)val;
+    if (NDOT >= 1) dots[0] += val * widen_any(w0[q]);
     if (NDOT >= 2) dots[1] += val * val;
   };
   auto emit_w = [&](int d, long q, double val) {  // destination rows: weight prefetched with the state
-    y[q] = val;
+    y[q] = (VT)val;
     if (NDOT >= 1) dots[0] += val * in.wd[d];
     if (NDOT >= 2) { if (!diff_exit_is_ghost<L>(f, d)) dots[1] += val * val; }
   };
@@ -678,15 +678,15 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
 #pragma unroll
     for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) emit((long)d * g.nlev + l_dn, in.xs[d] - in.xd[L::inv_dof(d)] * alb);
 #pragma unroll
-    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, x[q]); }
+    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, widen_any(x[q])); }
   }
 }
 
-template <class L, class CT, int NDOT>
+template <class L, class CT, int NDOT, class VT = double>
 __global__ void __launch_bounds__(128)
 k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
-          const double *__restrict__ albedo, const double *__restrict__ x, double *__restrict__ y,
-          const double *__restrict__ w0, double *partials, unsigned int *counter, double *out_dots) {
+          const double *__restrict__ albedo, const VT *__restrict__ x, VT *__restrict__ y,
+          const VT *__restrict__ w0, double *partials, unsigned int *counter, double *out_dots) {
   constexpr int NV = (NDOT > 0) ? NDOT : 1;
   long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   double dots[NV];
@@ -697,7 +697,7 @@ k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
     auto coef = [&](int n) { return widen(T[cb + n * PB_TILE]); };
     const Faces ci = cell_faces<L::Nf>(g, c);
     MatIn<L> in;
-    matmult_load<L, NDOT>(g, ci, x, w0, in);
+    matmult_load<L, NDOT, VT>(g, ci, x, w0, in);
     matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
   }
   if (NDOT > 0) grid_reduce_sum<NV>(dots, partials, counter, out_dots);
@@ -740,12 +740,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
 
 // NSTAGE = 2, PREFETCH: double-buffered stage + register prefetch of the next tile's state, 2 CTAs/SM
 // NSTAGE = 1          : single stage, state loads issued together with the bulk copy, 4 CTAs/SM hide each other's waits
-template <class L, int NDOT, int NSTAGE, bool PREFETCH>
+template <class L, int NDOT, int NSTAGE, bool PREFETCH, class VT = double>
 __global__ void __launch_bounds__(PB_TILE, (NSTAGE == 1) ? 4 : 2)
 k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
               const unsigned int *__restrict__ tile_class, const double *__restrict__ a11,
-              const double *__restrict__ a12, const double *__restrict__ albedo, const double *__restrict__ x,
-              double *__restrict__ y, const double *__restrict__ w0, double *partials, unsigned int *counter,
+              const double *__restrict__ a12, const double *__restrict__ albedo, const VT *__restrict__ x,
+              VT *__restrict__ y, const VT *__restrict__ w0, double *partials, unsigned int *counter,
               double *out_dots) {
   constexpr int NP = L::Nf * L::Nf;
   constexpr int NV = (NDOT > 0) ? NDOT : 1;
@@ -795,7 +795,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
       MatIn<L> in;
       if (c < g.ncell) {  // state loads travel together with the bulk copy
         ci = cell_faces<L::Nf>(g, c);
-        matmult_load<L, NDOT>(g, ci, x, w0, in);
+        matmult_load<L, NDOT, VT>(g, ci, x, w0, in);
       }
       mbar_wait(&bar[0], it & 1);
       if (c < g.ncell) compute(tile, 0, cls, ci, in, dots);
@@ -810,7 +810,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
       if (tile < ntiles) cls = tile_class[tile];
       if (tile < ntiles && tile * PB_TILE + tid < g.ncell) {
         ci = cell_faces<L::Nf>(g, tile * PB_TILE + tid);
-        matmult_load<L, NDOT>(g, ci, x, w0, in);
+        matmult_load<L, NDOT, VT>(g, ci, x, w0, in);
       }
     }
     unsigned int it = 0;
@@ -825,13 +825,13 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
         if (next < ntiles) cls_n = tile_class[next];
         if (have_next) {  // register prefetch of the next tile's state
           ci_n = cell_faces<L::Nf>(g, cn);
-          matmult_load<L, NDOT>(g, ci_n, x, w0, in_n);
+          matmult_load<L, NDOT, VT>(g, ci_n, x, w0, in_n);
         }
       } else {
         cls = tile_class[tile];
         if (c < g.ncell) {
           ci = cell_faces<L::Nf>(g, c);
-          matmult_load<L, NDOT>(g, ci, x, w0, in);
+          matmult_load<L, NDOT, VT>(g, ci, x, w0, in);
         }
       }
       mbar_wait(&bar[st], parity);
@@ -892,21 +892,21 @@ struct PrecUpIn {
   double rs[2 * L::Nfs];         // all side dofs of the level (1-D layers copy them, 3-D layers use the inward ones)
   CT t0[L::Nfs], t1[L::Nfs];     // T(0, inward side), T(1, inward side)
 };
-template <class L, class CT>
+template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                              const double *__restrict__ a11, const double *__restrict__ a12,
                                              const double *__restrict__ R, const double *__restrict__ inv,
-                                             const double *__restrict__ r, PrecUpIn<L, CT> &in) {
+                                             const VT *__restrict__ r, PrecUpIn<L, CT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-  in.fU = r[0 * g.nlev + c];
-  in.fD = r[1 * g.nlev + l1];
+  in.fU = widen_any(r[0 * g.nlev + c]);
+  in.fD = widen_any(r[1 * g.nlev + l1]);
   in.iv = inv[c];
   in.Rc = R[c];
   if (k < n1d) {
     in.tuu = a11[c]; in.tud = a12[c];
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+    for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = widen_any(r[(long)(Nft + d) * g.nlev + c]);
   } else {
     const long cb = cbase<Nf * Nf>(c);
     in.tuu = (double)T[cb + (0 * Nf + 0) * PB_TILE];
@@ -915,7 +915,7 @@ __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long
 #pragma unroll
     for (int d = 0; d < 2 * Nfs; ++d) {
       if (L::side_in(d % Nfs)) {
-        in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+        in.rs[d] = widen_any(r[(long)(Nft + d) * g.nlev + c]);
         in.t0[q] = T[cb + (0 * Nf + Nft + d) * PB_TILE];
         in.t1[q] = T[cb + (1 * Nf + Nft + d) * PB_TILE];
         ++q;
@@ -923,36 +923,36 @@ __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long
     }
   }
 }
-template <class L, class CT>
+template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
-          const double *__restrict__ R, const double *__restrict__ inv, const double *__restrict__ r,
-          double *__restrict__ z, int sides) {
+          const double *__restrict__ R, const double *__restrict__ inv, const VT *__restrict__ r,
+          VT *__restrict__ z, int sides) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   static_assert(Nft == 2, "column preconditioner needs one up/down pair of top streams");
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
   const long lz = (long)g.Nz * g.ncol + col;
-  double S = r[0 * g.nlev + lz];  // f_U at the surface
-  z[0 * g.nlev + lz] = S;
+  double S = widen_any(r[0 * g.nlev + lz]);  // f_U at the surface
+  z[0 * g.nlev + lz] = (VT)S;
 #pragma unroll
   for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + lz] = r[(long)d * g.nlev + lz];
   double Rn = R[lz];
   PrecUpIn<L, CT> cur, nxt;
-  prec_up_load<L, CT>(g, n1d, g.Nz - 1, col, T, a11, a12, R, inv, r, cur);
+  prec_up_load<L, CT, VT>(g, n1d, g.Nz - 1, col, T, a11, a12, R, inv, r, cur);
   for (int k = g.Nz - 1; k >= 0; --k) {
-    if (k > 0) prec_up_load<L, CT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, nxt);
+    if (k > 0) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     double fU = cur.fU, fD = cur.fD;
     if (k < n1d) {
 #pragma unroll
-      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
+      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = (VT)cur.rs[d];
     } else {
       int q = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (L::side_in(d % Nfs)) {
-          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
+          z[(long)(Nft + d) * g.nlev + c] = (VT)cur.rs[d];
           if (sides) {
             fU = fma(widen(cur.t0[q]), cur.rs[d], fU);
             fD = fma(widen(cur.t1[q]), cur.rs[d], fD);
@@ -963,8 +963,8 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
     }
     S = fU + cur.tuu * (S + Rn * (cur.tud * S + fD) * cur.iv);
     Rn = cur.Rc;
-    z[0 * g.nlev + c] = S;
-    z[1 * g.nlev + l1] = fD;
+    z[0 * g.nlev + c] = (VT)S;
+    z[1 * g.nlev + l1] = (VT)fD;
     if (k > 0) cur = nxt;
   }
   z[1 * g.nlev + col] = r[1 * g.nlev + col];  // f_D(0) = r_D(0)
@@ -976,15 +976,15 @@ struct PrecDownIn {
   double rsd[2 * L::Nfs];                 // r of all side dofs at the cell
   CT tt[L::Nfs][2 + L::Nfs];              // per outward dof: T(dof,0), T(dof,1), T(dof, inward sides)
 };
-template <class L, class CT>
+template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                                const double *__restrict__ a11, const double *__restrict__ a12,
                                                const double *__restrict__ R, const double *__restrict__ inv,
-                                               const double *__restrict__ r, const double *z, PrecDownIn<L, CT> &in) {
+                                               const VT *__restrict__ r, const VT *z, PrecDownIn<L, CT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-  in.S1 = z[0 * g.nlev + l1];
-  in.fD = z[1 * g.nlev + l1];
+  in.S1 = widen_any(z[0 * g.nlev + l1]);
+  in.fD = widen_any(z[1 * g.nlev + l1]);
   in.iv = inv[c];
   in.R1 = R[l1];
   if (k < n1d) { in.tdd = a11[c]; in.tud = a12[c]; }
@@ -993,7 +993,7 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
     in.tdd = (double)T[cb + (1 * Nf + 1) * PB_TILE];
     in.tud = (double)T[cb + (1 * Nf + 0) * PB_TILE];
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
+    for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = widen_any(r[(long)(Nft + d) * g.nlev + c]);
     int o = 0;
 #pragma unroll
     for (int d = 0; d < 2 * Nfs; ++d) {
@@ -1010,22 +1010,22 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
     }
   }
 }
-template <class L, class CT>
+template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const double *__restrict__ R, const double *__restrict__ inv,
-            const double *__restrict__ r, double *z, int sides) {
+            const VT *__restrict__ r, VT *z, int sides) {
   constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
-  double D = z[1 * g.nlev + col];
-  double U = R[col] * D + z[0 * g.nlev + col];
-  z[0 * g.nlev + col] = U;
+  double D = widen_any(z[1 * g.nlev + col]);
+  double U = R[col] * D + widen_any(z[0 * g.nlev + col]);
+  z[0 * g.nlev + col] = (VT)U;
   PrecDownIn<L, CT> cur, nxt;
-  prec_down_load<L, CT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cur);
+  prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cur);
   for (int k = 0; k < g.Nz; ++k) {
     // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
-    if (k + 1 < g.Nz) prec_down_load<L, CT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, nxt);
+    if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     const double S1 = cur.S1;
     const double D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
@@ -1044,13 +1044,13 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
           for (int s = 0; s < 2 * Nfs; ++s)
             if (L::side_in(s % Nfs)) { acc = fma(widen(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
           }
-          z[(long)(Nft + d) * g.nlev + c] = acc;
+          z[(long)(Nft + d) * g.nlev + c] = (VT)acc;
           ++o;
         }
       }
     }
-    z[0 * g.nlev + l1] = U1;
-    z[1 * g.nlev + l1] = D1;
+    z[0 * g.nlev + l1] = (VT)U1;
+    z[1 * g.nlev + l1] = (VT)D1;
     D = D1;
     if (k + 1 < g.Nz) cur = nxt;
   }
@@ -1118,6 +1118,115 @@ __global__ void k_bicg_update_xr(long n, int it, const double *__restrict__ ph, 
     r[q] = rv;
     rr += rv * rv;
     rhr += rv * rh[q];
+  }
+  double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
+  grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
+}
+// ---- mixed precision: fp32 Krylov work vectors (r, rh, p, v, s, t, ph, sh), fp64 solution x and fp64 TRUE residual.
+// Every cycle starts from r64 = b - A x evaluated in fp64 (iterative refinement), so the convergence test of
+// MyKSPConverged is applied to a residual that carries no fp32 rounding.  Vector arithmetic is fp32 (the operands are
+// fp32 anyway), dot products accumulate in fp64; float -> double goes through widen_any (integer ALU, not the XU pipe).
+// Vector bodies move 16 bytes per thread and array (float4 / 2 x double2); the < 4 element tail is scalar.
+struct BicgScalars { double alpha, omega, beta; };
+__device__ __forceinline__ BicgScalars bicg_scalars(const double *__restrict__ sc, int it, bool need_beta) {
+  BicgScalars o;
+  o.alpha = sc[sc_rho_slot(it)] / sc[SC_RHV];
+  const double tt = sc[SC_TT];
+  o.omega = (tt > 0.0) ? sc[SC_TS] / tt : 0.0;
+  o.beta = 0.0;
+  if (need_beta) {  // beta of iteration `it` from rho(it), rho(it-1) and alpha, omega of iteration it-1
+    const double rho = sc[sc_rho_slot(it)], rho_old = sc[sc_rho_slot(it - 1)];
+    o.alpha = rho_old / sc[SC_RHV];
+    o.beta = (rho / rho_old) * (o.alpha / o.omega);
+  }
+  return o;
+}
+// r64 = b - Ax (Ax in `ax`); r = rh = (float) r64;  SC_RR = (r64, r64) [true residual], SC_RHO1 = (r, r) = rho(1)
+__global__ void k_mixed_init(long n, const double *__restrict__ b, const double *__restrict__ ax,
+                             float *__restrict__ r, float *__restrict__ rh, double *partials, unsigned int *counter,
+                             double *sc) {
+  double acc[2] = {0.0, 0.0};
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const double rv = b[q] - ax[q];
+    const float rf = (float)rv;
+    r[q] = rf; rh[q] = rf;
+    acc[0] += rv * rv;
+    const double rd = widen_any(rf);
+    acc[1] += rd * rd;
+  }
+  grid_reduce_sum<2>(acc, partials, counter, &sc[SC_RR]);
+}
+// p = r + beta (p - omega v)   (it == 1: p = r)
+__global__ void k_bicg32_update_p(long n, int it, const float *__restrict__ r, const float *__restrict__ v,
+                                  float *__restrict__ p, const double *__restrict__ sc) {
+  float beta = 0.f, omega = 0.f;
+  if (it > 1) { const BicgScalars k = bicg_scalars(sc, it, true); beta = (float)k.beta; omega = (float)k.omega; }
+  const long n4 = n >> 2, stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 *r4 = reinterpret_cast<const float4 *>(r), *v4 = reinterpret_cast<const float4 *>(v);
+  float4 *p4 = reinterpret_cast<float4 *>(p);
+  if (it == 1) {
+    for (long q = t0; q < n4; q += stride) p4[q] = r4[q];
+    for (long q = (n4 << 2) + t0; q < n; q += stride) p[q] = r[q];
+    return;
+  }
+  auto f = [&](float rr, float pp, float vv) { return fmaf(beta, fmaf(-omega, vv, pp), rr); };
+  for (long q = t0; q < n4; q += stride) {
+    const float4 a = r4[q], b = p4[q], c = v4[q];
+    p4[q] = make_float4(f(a.x, b.x, c.x), f(a.y, b.y, c.y), f(a.z, b.z, c.z), f(a.w, b.w, c.w));
+  }
+  for (long q = (n4 << 2) + t0; q < n; q += stride) p[q] = f(r[q], p[q], v[q]);
+}
+// s = r - alpha v
+__global__ void k_bicg32_update_s(long n, int it, const float *__restrict__ r, const float *__restrict__ v,
+                                  float *__restrict__ s, const double *__restrict__ sc) {
+  const float alpha = (float)(sc[sc_rho_slot(it)] / sc[SC_RHV]);
+  const long n4 = n >> 2, stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 *r4 = reinterpret_cast<const float4 *>(r), *v4 = reinterpret_cast<const float4 *>(v);
+  float4 *s4 = reinterpret_cast<float4 *>(s);
+  for (long q = t0; q < n4; q += stride) {
+    const float4 a = r4[q], c = v4[q];
+    s4[q] = make_float4(fmaf(-alpha, c.x, a.x), fmaf(-alpha, c.y, a.y), fmaf(-alpha, c.z, a.z), fmaf(-alpha, c.w, a.w));
+  }
+  for (long q = (n4 << 2) + t0; q < n; q += stride) s[q] = fmaf(-alpha, v[q], r[q]);
+}
+// x (fp64) += alpha ph + omega sh ; r = s - omega t ; rr = (r,r), rho(it+1) = (rh, r)
+__global__ void k_bicg32_update_xr(long n, int it, const float *__restrict__ ph, const float *__restrict__ sh,
+                                   const float *__restrict__ s, const float *__restrict__ t,
+                                   const float *__restrict__ rh, double *__restrict__ x, float *__restrict__ r,
+                                   double *partials, unsigned int *counter, double *sc) {
+  const BicgScalars k = bicg_scalars(sc, it, false);
+  const double alpha = k.alpha, omega = k.omega;
+  const float omegaf = (float)omega;
+  const bool rho_first = sc_rho_slot(it + 1) == SC_RHO0;  // output run is (RHO0, RR) or (RR, RHO1)
+  double rr = 0.0, rhr = 0.0;
+  auto one = [&](float phv, float shv, float sv, float tv, float rhv, double xv, float &rout) -> double {
+    rout = fmaf(-omegaf, tv, sv);
+    const double rd = widen_any(rout);
+    rr = fma(rd, rd, rr);
+    rhr = fma(rd, widen_any(rhv), rhr);
+    return fma(omega, widen_any(shv), fma(alpha, widen_any(phv), xv));
+  };
+  const long n4 = n >> 2, stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 *ph4 = reinterpret_cast<const float4 *>(ph), *sh4 = reinterpret_cast<const float4 *>(sh),
+               *s4 = reinterpret_cast<const float4 *>(s), *t4 = reinterpret_cast<const float4 *>(t),
+               *rh4 = reinterpret_cast<const float4 *>(rh);
+  float4 *r4 = reinterpret_cast<float4 *>(r);
+  double2 *x2 = reinterpret_cast<double2 *>(x);
+  for (long q = t0; q < n4; q += stride) {
+    const float4 a = ph4[q], b = sh4[q], c = s4[q], d = t4[q], e = rh4[q];
+    double2 xa = x2[2 * q], xb = x2[2 * q + 1];
+    float4 ro;
+    xa.x = one(a.x, b.x, c.x, d.x, e.x, xa.x, ro.x);
+    xa.y = one(a.y, b.y, c.y, d.y, e.y, xa.y, ro.y);
+    xb.x = one(a.z, b.z, c.z, d.z, e.z, xb.x, ro.z);
+    xb.y = one(a.w, b.w, c.w, d.w, e.w, xb.y, ro.w);
+    x2[2 * q] = xa; x2[2 * q + 1] = xb;
+    r4[q] = ro;
+  }
+  for (long q = (n4 << 2) + t0; q < n; q += stride) {
+    float ro;
+    x[q] = one(ph[q], sh[q], s[q], t[q], rh[q], x[q], ro);
+    r[q] = ro;
   }
   double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
   grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);

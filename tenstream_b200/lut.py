@@ -192,23 +192,34 @@ def read_mmap4(path: str) -> np.ndarray:
 # stream permutations assume (src/optprop.F90:1009-1045).  Values are smooth in all six parameters.
 
 def _diffuse_streams(solver_id):
-    """Returns a list of streams; each is dict(face, sx, sy, sz) describing the open set of directions:
-    face 'z' with sz=+1 is E_dn (enters through the top, leaves through the bottom)."""
+    """Returns a list of streams; each is dict(face, s, ...) describing the open set of directions:
+    face 'z' with s=+1 is E_dn (enters through the top, leaves through the bottom).  z points DOWN here.
+    10-stream layouts: side streams carry ``sz`` (the vertical half-space).  24-stream layout
+    (src/boxmc_3_24.inc:36-120): every face direction is split into four angular quadrants ``q`` = the signs of the two
+    transverse direction components -- (x, y) on top/bottom faces, (y, z) on x faces, (x, z) on y faces."""
     _, _, ft, fs = SOLVER_STREAMS[solver_id]
-    if (ft, fs) != (2, 4):
-        raise NotImplementedError("synthetic diffuse tables are implemented for 10-stream layouts")
-    return [
-        dict(face="z", s=-1),            # 0 E_up      (is_inward = F)
-        dict(face="z", s=+1),            # 1 E_dn      (T)
-        dict(face="x", s=-1, sz=+1),     # 2 down, -x  (F)
-        dict(face="x", s=+1, sz=+1),     # 3 down, +x  (T)
-        dict(face="x", s=-1, sz=-1),     # 4 up,   -x  (F)
-        dict(face="x", s=+1, sz=-1),     # 5 up,   +x  (T)
-        dict(face="y", s=-1, sz=+1),     # 6 down, -y  (F)
-        dict(face="y", s=+1, sz=+1),     # 7 down, +y  (T)
-        dict(face="y", s=-1, sz=-1),     # 8 up,   -y  (F)
-        dict(face="y", s=+1, sz=-1),     # 9 up,   +y  (T)
-    ]
+    if (ft, fs) == (2, 4):
+        return [
+            dict(face="z", s=-1),            # 0 E_up      (is_inward = F)
+            dict(face="z", s=+1),            # 1 E_dn      (T)
+            dict(face="x", s=-1, sz=+1),     # 2 down, -x  (F)
+            dict(face="x", s=+1, sz=+1),     # 3 down, +x  (T)
+            dict(face="x", s=-1, sz=-1),     # 4 up,   -x  (F)
+            dict(face="x", s=+1, sz=-1),     # 5 up,   +x  (T)
+            dict(face="y", s=-1, sz=+1),     # 6 down, -y  (F)
+            dict(face="y", s=+1, sz=+1),     # 7 down, +y  (T)
+            dict(face="y", s=-1, sz=-1),     # 8 up,   -y  (F)
+            dict(face="y", s=+1, sz=-1),     # 9 up,   +y  (T)
+        ]
+    if (ft, fs) == (8, 8):
+        out = []
+        for q in ((-1, +1), (+1, +1), (-1, -1), (+1, -1)):        # top/bottom: (x, y) quadrants 1/2, 3/4, 5/6, 7/8
+            out += [dict(face="z", s=-1, q=q), dict(face="z", s=+1, q=q)]          # [up (F), down (T)]
+        for face in ("x", "y"):                                    # sides: (transverse, z) quadrants, "up" first
+            for q in ((-1, -1), (+1, -1), (-1, +1), (+1, +1)):     # z points down: up = -1
+                out += [dict(face=face, s=+1, q=q), dict(face=face, s=-1, q=q)]    # [inward (T), outward (F)]
+        return out
+    raise NotImplementedError(f"no synthetic diffuse table for a {ft}+2*{fs} stream layout")
 
 
 def _stream_dirs(st):
@@ -217,19 +228,26 @@ def _stream_dirs(st):
     if st["face"] == "z":
         for mu, wmu in ((0.9, 0.45), (0.55, 0.55)):
             sin = np.sqrt(1 - mu * mu)
-            for az in (45., 135., 225., 315.):
-                a = np.deg2rad(az)
-                out.append(((sin * np.cos(a), sin * np.sin(a), st["s"] * mu), wmu / 4))
+            if "q" in st:
+                for az in (22.5, 67.5):
+                    a = np.deg2rad(az)
+                    out.append(((st["q"][0] * sin * np.cos(a), st["q"][1] * sin * np.sin(a), st["s"] * mu), wmu / 2))
+            else:
+                for az in (45., 135., 225., 315.):
+                    a = np.deg2rad(az)
+                    out.append(((sin * np.cos(a), sin * np.sin(a), st["s"] * mu), wmu / 4))
     else:
-        # flux through a side face, restricted to one vertical half-space
+        # flux through a side face, restricted to one vertical half-space (and one transverse sign for quadrants)
         for un, wn in ((0.85, 0.5), (0.5, 0.5)):          # component along the face normal
             rest = np.sqrt(1 - un * un)
             for ct in (0.35, 0.85):                        # share of the remainder that is vertical
-                for sgn in (-1.0, 1.0):                    # transverse sign: mirror-symmetric
-                    uz = st["sz"] * rest * ct
+                sz = st["q"][1] if "q" in st else st["sz"]
+                signs = (float(st["q"][0]),) if "q" in st else (-1.0, 1.0)   # transverse sign: mirror-symmetric
+                for sgn in signs:
+                    uz = sz * rest * ct
                     ut = sgn * rest * np.sqrt(1 - ct * ct)
                     d = (st["s"] * un, ut, uz) if st["face"] == "x" else (ut, st["s"] * un, uz)
-                    out.append((d, wn / 4))
+                    out.append((d, wn / (2 * len(signs))))
     return out
 
 
@@ -271,16 +289,25 @@ def _trace(points, d, aspect):
 
 def _classify_diffuse(ax, sgn, d, streams):
     """Index of the diffuse stream a ray leaving through (axis, sign) with direction d joins."""
+    sg = lambda v: 1 if v >= 0 else -1
     for k, st in enumerate(streams):
         if "xyz"[ax] != st["face"] or st["s"] != sgn:
             continue
-        if st["face"] == "z" or st["sz"] == (1 if d[2] >= 0 else -1):
+        if "q" in st:
+            tr = (d[0], d[1]) if st["face"] == "z" else (d[1], d[2]) if st["face"] == "x" else (d[0], d[2])
+            if (sg(tr[0]), sg(tr[1])) == tuple(st["q"]):
+                return k
+        elif st["face"] == "z" or st["sz"] == sg(d[2]):
             return k
     raise RuntimeError("unclassified ray")
 
 
 def _iso_weights(streams, aspect):
-    w = np.array([1.0 if st["face"] == "z" else aspect / 2 for st in streams])
+    """Isotropic redistribution by face area, shared equally between the streams of one face direction."""
+    nshare = {}
+    for st in streams:
+        nshare[(st["face"], st["s"])] = nshare.get((st["face"], st["s"]), 0) + 1
+    w = np.array([(1.0 if st["face"] == "z" else aspect) / nshare[(st["face"], st["s"])] for st in streams])
     return w / w.sum()
 
 

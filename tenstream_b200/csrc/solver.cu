@@ -214,6 +214,7 @@ struct pprts_b200_solver {
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
   bool prec_ready = false;
+  int prec_block[2] = {0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
   bool res_valid = false;
   int res_uid = 0;
@@ -938,6 +939,25 @@ static int launch_matmult(pprts_b200_solver *s, double *x, double *y, const doub
 
 static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond >= 1 && s->cfg.solver_id != 324; }
 
+// Column kernels are one thread per column and latency-bound per thread, so their run time is (number of waves) x
+// (time of one column): pick the block size (<= PREC_BLOCK) for which all columns are resident in the fewest waves.
+// 256x256 columns with 64-thread blocks at 144 registers are 1024 blocks on 888 slots = 2 waves (ncu: 0.30 ms, 51 % of
+// DRAM peak, profiles/r1_hot_kernels.txt); 32-thread blocks fit in one.
+template <class K>
+static int column_block(pprts_b200_solver *s, K kernel, int *cache) {
+  if (*cache) return *cache;
+  int best = PREC_BLOCK;
+  long best_waves = -1;
+  for (int bs = PREC_BLOCK; bs >= 32; bs >>= 1) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, bs, 0) != cudaSuccess || per_sm < 1) continue;
+    const long slots = (long)per_sm * s->num_sms, blocks = (s->g.ncol + bs - 1) / bs;
+    const long waves = (blocks + slots - 1) / slots;
+    if (best_waves < 0 || waves < best_waves) { best_waves = waves; best = bs; }
+  }
+  return *cache = best;
+}
+
 template <class L, class CT>
 static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
   if constexpr (L::Nft == 2) {
@@ -947,9 +967,11 @@ static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
              s->albedo, s->precR, s->precInv);
       s->prec_ready = true;
     }
-    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+    const int bu = column_block(s, k_prec_up<L, CT>, &s->prec_block[0]);
+    const int bd = column_block(s, k_prec_down<L, CT>, &s->prec_block[1]);
+    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
-    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
   }
 }

@@ -365,7 +365,9 @@ def test_solver_3_24_vs_oracle(P, luts_324, phi0, theta0, coeff_fp32):
     x = rng.random((24, Nz + 1, Nx, Ny))
     P.solve_pprts(s, False, True, 1000.)
     assert o.solve(False, True, 1000.) == 0
-    assert relerr(s.mat_mult_ediff(x), o.mat_mult_ediff(x)) < 1e-13
+    # 24-term rows summed in a different order (and with FMA contraction) than the oracle: a few ulp of the row's
+    # largest term, which after the cancellation in x - T x is up to ~1e-12 of the entry
+    assert relerr(s.mat_mult_ediff(x), o.mat_mult_ediff(x)) < 1e-12
     for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
         assert relerr(a, b) < 1e-7, name
     planck = np.broadcast_to(np.linspace(60., 120., Nz + 1)[:, None, None], (Nz + 1, Nx, Ny)).copy()

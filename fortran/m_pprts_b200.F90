@@ -33,7 +33,8 @@ module m_pprts_b200
     real(c_double) :: twostr_ratio
     integer(c_int) :: coeff_fp32, by_coeff_divergence
     real(c_double) :: rtol, atol
-    integer(c_int) :: maxit_dir, maxit_diff, precond, device, keep_solutions, nxproc, nyproc, xrank, yrank
+    integer(c_int) :: maxit_dir, maxit_diff, precond, device, keep_solutions, nxproc, nyproc, xrank, yrank, &
+      & diff_explicit
   end type
 
   interface

@@ -95,6 +95,11 @@ typedef struct {
   /* x/y decomposition over the GPUs of one box (src/pprts_base.F90:721-828): this rank's cartesian position.
    * nxproc = nyproc = 1 means a single periodic domain. */
   int nxproc, nyproc, xrank, yrank;
+  /* -solar_diff_explicit / -thermal_diff_explicit (src/pprts.F90:2793-2800 -> explicit_ediff,
+   * src/pprts_explicit.F90:461-713): stationary relaxation with the reference's ||x_n - x_{n-1}||_2 atol/rtol test
+   * instead of the Krylov solve.  The reference's cell-by-cell SOR ordering is sequential; here every sweep relaxes
+   * all columns at once (x += M^-1 (b - A x), M = the column operator of `precond`, plain Jacobi when precond = 0). */
+  int diff_explicit;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);
@@ -129,6 +134,35 @@ int pprts_b200_synchronize(pprts_b200_solver *solver);
 int pprts_b200_accumulate_result(pprts_b200_solver *solver, int uid, double weight);
 int pprts_b200_reset_accumulator(pprts_b200_solver *solver);
 int pprts_b200_get_accumulated(pprts_b200_solver *solver, double *edn, double *eup, double *abso, double *edir);
+
+/* Band loop of the spectral callers in one call (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053 solar, :621-708 thermal;
+ * specint/specint_pprts.F90:89-213): for ib in 0..nbands-1
+ *     set_optical_properties(albedo, kabs(:,:,:,ib), ksca(:,:,:,ib), g(:,:,:,ib), planck(:,:,:,ib), planck_srfc(:,:,ib))
+ *     solve_pprts(lthermal = !lsolar, lsolar, edirTOA(ib), uid = uid0 + ib)
+ *     edn, eup, abso, edir += weights(ib) * pprts_get_result(uid0 + ib)
+ * The per-band host arrays never come back: the optical properties of band ib+1 are uploaded on a copy stream while
+ * band ib is being solved (pass page-locked memory for the copy to be asynchronous), the spectral sum is kept on
+ * the device and read back once.  Fields are (Nz,Nx,Ny[,nbands]) column-major like set_optical_properties; a band
+ * stride of 0 elements re-uses the same field for every band (e.g. ksca = g = 0 in the thermal loop). */
+typedef struct {
+  int nbands;
+  int lsolar;                 /* 1: solar bands, 0: thermal bands */
+  int uid0;                   /* solution uid of band 0 (reference: ib for solar, 500 + ib for thermal) */
+  int ldelta_scaling;
+  double albedo;
+  const double *albedo_2d;    /* (Nx,Ny) or NULL */
+  const double *kabs, *ksca, *g;                       /* band ib at ptr + ib * stride */
+  long stride_kabs, stride_ksca, stride_g;             /* in elements; 0: shared by all bands */
+  const double *planck, *planck_srfc;                  /* thermal: (Nz+1,Nx,Ny[,nbands]), (Nx,Ny[,nbands]) or NULL */
+  long stride_planck, stride_planck_srfc;
+  const double *edirTOA;      /* (nbands), solar */
+  const double *weights;      /* (nbands) or NULL: 1 */
+  int accumulate_only;        /* 1: add to the device accumulator without resetting it first */
+} pprts_b200_bands;
+/* edn/eup/edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny): spectral sums, any may be NULL (NULL for all four leaves the sums in the
+ * device accumulator for pprts_b200_allreduce_accumulated / pprts_b200_get_accumulated); niter_diff (nbands) or NULL */
+int pprts_b200_solve_bands(pprts_b200_solver *solver, const pprts_b200_bands *bands, double *edn, double *eup,
+                           double *abso, double *edir, int *niter_diff);
 
 /* NCCL plumbing (one process per GPU). The unique id is produced on rank 0 and distributed by the caller
  * (MPI_Bcast in a Fortran host, torch.distributed in the tests). */

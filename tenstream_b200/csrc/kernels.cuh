@@ -1231,6 +1231,21 @@ __global__ void k_bicg32_update_xr(long n, int it, const float *__restrict__ ph,
   double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
   grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
 }
+// explicit relaxation (explicit_ediff analogue): r = b - Ax (Ax in `r` on entry)
+__global__ void k_relax_residual(long n, const double *__restrict__ b, double *__restrict__ r) {
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) r[q] = b[q] - r[q];
+}
+// x += omega z ; out = sum (omega z)^2  (= ||x_n - x_{n-1}||^2, the reference's residual, src/pprts_explicit.F90:620)
+__global__ void k_relax_update(long n, double omega, const double *__restrict__ z, double *__restrict__ x,
+                               double *partials, unsigned int *counter, double *out) {
+  double acc[1] = {0.0};
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const double d = omega * z[q];
+    x[q] += d;
+    acc[0] += d * d;
+  }
+  grid_reduce_sum<1>(acc, partials, counter, out);
+}
 // sum |b| (src/pprts.F90:2774)
 __global__ void k_norm1(long n, const double *__restrict__ b, double *partials, unsigned int *counter, double *out) {
   double acc[1] = {0.0};

@@ -202,7 +202,8 @@ struct pprts_b200_solver {
   int xinc = 0, yinc = 0;
   bool angles_dirty = true, coeffs_dirty = true, coeffs_have_dir = false;
   // device state
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t band_uploaded[2] = {nullptr, nullptr};
   double *dz = nullptr, *kabs = nullptr, *ksca = nullptr, *gg = nullptr, *planck = nullptr, *Bsrfc = nullptr,
          *albedo = nullptr, *raw = nullptr;
   bool have_planck = false, have_Bsrfc = false, have_optprop = false;
@@ -444,6 +445,7 @@ extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   cfg->device = -1;
   cfg->keep_solutions = 1;
   cfg->nxproc = cfg->nyproc = 1;
+  cfg->diff_explicit = 0;
 }
 
 template <class T>
@@ -644,6 +646,8 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_bad);
   for (auto &ev : s->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto e : s->evpool) cudaEventDestroy(e);
+  if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+  for (int q = 0; q < 2; ++q) if (s->band_uploaded[q]) cudaEventDestroy(s->band_uploaded[q]);
   cudaStreamDestroy(s->stream);
   delete s;
   return 0;
@@ -977,6 +981,49 @@ static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
 }
 static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, launch_prec_t<L, CT>(s, r, z)); }
 
+// explicit_ediff (src/pprts_explicit.F90:461-713) analogue: stationary relaxation x += M^-1 (b - A x), all columns
+// at once; residual = ||x_n - x_{n-1}||_2 (mean over ranks of the local norms, :620-626), converged when it is < atol
+// or < rtol * residual(1) (:641-642); the first solve of a uid uses at most the default tolerances (:548-554).
+static int solve_ediff_explicit(pprts_b200_solver *s, Solution &sol) {
+  const Grid &g = s->g;
+  const long n = (long)s->Nf * g.nlev;
+  const int maxit = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 10000;
+  double rtol_d, atol_d;
+  determine_ksp_tolerances(s, rtol_d, atol_d);
+  double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol.first_diff) { rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
+  double *x = sol.ediff, *r = s->kr[0], *z = s->kr[1];
+  const bool prec = precond_available(s);
+  int rc = need_comm(s);
+  if (rc) return rc;
+  double first = 0.0;
+  bool converged = false;
+  sol.niter_diff = 0;
+  for (int it = 1; it <= maxit && !converged; ++it) {
+    if ((rc = launch_matmult<0>(s, x, r, nullptr, nullptr))) return rc;
+    LAUNCH(s, FAM_VEC, k_relax_residual, vec_grid(n), VEC_BLOCK, n, s->b, r);
+    if (prec) launch_prec(s, r, z);
+    LAUNCH(s, FAM_VEC, k_relax_update, vec_grid(n), VEC_BLOCK, n, 1.0, prec ? z : r, x, s->partials, s->counter, s->sc + SC_TMP);
+    if (s->decomposed) {  // mean over ranks of the local 2-norms, like the direct sweep
+      LAUNCH(s, FAM_VEC, k_sqrt_mean, 1, 1, s->sc + SC_TMP, 1, 1.0 / s->nranks);
+      if ((rc = allreduce_scalars(s, s->sc + SC_TMP, 1))) return rc;
+    }
+    if ((rc = read_scalars(s))) return rc;
+    const double res = s->decomposed ? s->h_sc[SC_TMP] : std::sqrt(s->h_sc[SC_TMP]);
+    if (it == 1) first = res;
+    sol.niter_diff = it;
+    sol.res_diff = res;
+    if (!(res == res)) return set_err(21, "explicit diffuse solve broke down (NaN residual) at iteration %d", it);
+    const double rel = first <= std::sqrt(DBL_MIN) ? 0.0 : res / first;
+    if (res < atol || rel < rtol) converged = true;
+  }
+  sol.first_diff = false;
+  sol.lchanged = true;
+  sol.lWm2_diff = false;
+  if (!converged) return set_err(22, "explicit diffuse solve did not converge -- %d iterations, residual %g", sol.niter_diff, sol.res_diff);
+  return 0;
+}
+
 // Right-preconditioned BiCGStab on the matrix-free operator; convergence test of MyKSPConverged
 // (src/pprts.F90:4437-4486): ||r||/||r0|| <= rtol or ||r|| <= atol, nonzero initial guess (:4343).
 static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
@@ -990,6 +1037,7 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
   double *x = sol.ediff, *r = s->kr[0], *rh = s->kr[1], *p = s->kr[2], *v = s->kr[3], *sv = s->kr[4], *t = s->kr[5];
   const bool prec = precond_available(s);
   double *ph = prec ? s->kr[6] : p, *sh = prec ? s->kr[7] : sv;
+  if (s->cfg.diff_explicit) return solve_ediff_explicit(s, sol);
   int rc = need_comm(s);
   if (rc) return rc;
   if ((rc = launch_matmult<0>(s, x, r, nullptr, nullptr))) return rc;
@@ -1197,6 +1245,79 @@ extern "C" int pprts_b200_get_accumulated(pprts_b200_solver *s, double *edn, dou
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));
   return download_fields(s, s->acc, edn, eup, abso, edir);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// band loop (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053, :621-708): upload of band ib+1 overlaps the solve of band ib
+// ---------------------------------------------------------------------------------------------------------------
+static const int BAND_SLOT0 = 1 << 30;  // staging slots reserved for the band loop (user slots are small integers)
+static int stage_band_async(pprts_b200_solver *s, Staged &st, const pprts_b200_bands *b, int ib) {
+  const Grid &gr = s->g;
+  auto up = [&](double **dst, const double *src, size_t n) -> int {
+    if (!*dst) CU(cudaMalloc((void **)dst, n * sizeof(double)));
+    CU(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));
+    return 0;
+  };
+  int rc;
+  st.albedo = b->albedo;
+  if ((rc = up(&st.kabs, b->kabs + (long)ib * b->stride_kabs, gr.ncell))) return rc;
+  if ((rc = up(&st.ksca, b->ksca + (long)ib * b->stride_ksca, gr.ncell))) return rc;
+  if ((rc = up(&st.g, b->g + (long)ib * b->stride_g, gr.ncell))) return rc;
+  st.have_planck = b->planck != nullptr;
+  if (b->planck && (rc = up(&st.planck, b->planck + (long)ib * b->stride_planck, gr.nlev))) return rc;
+  st.have_Bsrfc = b->planck_srfc != nullptr;
+  if (b->planck_srfc && (rc = up(&st.Bsrfc, b->planck_srfc + (long)ib * b->stride_planck_srfc, gr.ncol))) return rc;
+  st.have_albedo2d = b->albedo_2d != nullptr;
+  if (b->albedo_2d && (rc = up(&st.albedo2d, b->albedo_2d, gr.ncol))) return rc;
+  return 0;
+}
+
+extern "C" int pprts_b200_solve_bands(pprts_b200_solver *s, const pprts_b200_bands *b, double *edn, double *eup,
+                                      double *abso, double *edir, int *niter_diff) {
+  if (!s) return set_err(1, "null solver");
+  if (!b || b->nbands < 0) return set_err(2, "solve_bands: bad band description");
+  if (b->nbands > 0 && (!b->kabs || !b->ksca || !b->g)) return set_err(2, "solve_bands: kabs, ksca and g are required");
+  if (b->nbands > 0 && b->lsolar && !b->edirTOA) return set_err(2, "solve_bands: solar bands need edirTOA(nbands)");
+  if (b->nbands > 0 && !b->lsolar && !b->planck)
+    return set_err(12, "you asked to compute thermal radiation but did not provide planck emissions in set_optical_properties");
+  if (b->uid0 < -1000 || b->uid0 + std::max(0, b->nbands - 1) > 1000) return set_err(11, "solution uids %d.. out of range", b->uid0);
+  CU(cudaSetDevice(s->device));
+  if (!s->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) CU(cudaEventCreateWithFlags(&s->band_uploaded[q], cudaEventDisableTiming));
+  }
+  int rc;
+  if (!b->accumulate_only && (rc = pprts_b200_reset_accumulator(s))) return rc;
+  if (b->nbands > 0) {
+    if ((rc = stage_band_async(s, s->staged[BAND_SLOT0], b, 0))) return rc;
+    CU(cudaEventRecord(s->band_uploaded[0], s->copy_stream));
+  }
+  for (int ib = 0; ib < b->nbands; ++ib) {
+    Staged &st = s->staged[BAND_SLOT0 + (ib & 1)];
+    CU(cudaStreamWaitEvent(s->stream, s->band_uploaded[ib & 1], 0));
+    // returns after the ingest kernels have run: this slot and the other one (consumed one band earlier) are free
+    rc = set_optprop_impl(s, st.albedo, st.kabs, st.ksca, st.g, st.have_planck ? st.planck : nullptr,
+                          st.have_Bsrfc ? st.Bsrfc : nullptr, st.have_albedo2d ? st.albedo2d : nullptr,
+                          b->ldelta_scaling, true);
+    if (rc) return rc;
+    if (ib + 1 < b->nbands) {
+      if ((rc = stage_band_async(s, s->staged[BAND_SLOT0 + ((ib + 1) & 1)], b, ib + 1))) return rc;
+      CU(cudaEventRecord(s->band_uploaded[(ib + 1) & 1], s->copy_stream));
+    }
+    const int uid = b->uid0 + ib;
+    rc = pprts_b200_solve(s, !b->lsolar, b->lsolar, b->lsolar ? b->edirTOA[ib] : 0.0, uid);
+    if (rc) {
+      char msg[sizeof(g_err)];
+      snprintf(msg, sizeof(msg), "%s", g_err);
+      cudaStreamSynchronize(s->copy_stream);
+      return set_err(rc, "solve_bands: band %d (uid %d): %s", ib, uid, msg);
+    }
+    if (niter_diff) { Solution *sol; if (!find_solution(s, uid, &sol)) niter_diff[ib] = sol->niter_diff; }
+    if ((rc = compute_result(s, uid, true, b->weights ? b->weights[ib] : 1.0))) return rc;
+  }
+  CU(cudaStreamSynchronize(s->copy_stream));
+  if (edn || eup || abso || edir) return download_fields(s, s->acc, edn, eup, abso, edir);
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -130,3 +130,41 @@ def halo_fill_reference(field, dec: CartDecomposition):
         for r in dist.batch_isend_irecv(ops):
             r.wait()
     return recv_x.numpy(), recv_y.numpy()
+
+
+def gather_all_to_zero(local, dec: CartDecomposition):
+    """``gather_all_toZero`` (src/pprts.F90:6325-6359): every rank announces (xs, ys, xm, ym) (the allgather of the
+    six-integer meta record; z is never split), then ranks > 0 send their (nz, xm, ym) block to rank 0, which pastes
+    it at its offsets.  Returns the global (nz, Nx, Ny) array on rank 0 and None elsewhere.  Host arrays over
+    ``torch.distributed`` (any backend): the result arrays are already on the host after ``pprts_get_result``."""
+    import torch
+    import torch.distributed as dist
+    a = np.ascontiguousarray(local, dtype=np.float64)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return a.copy()
+    meta = torch.tensor([dec.xs, dec.ys, dec.xm, dec.ym], dtype=torch.int64)
+    all_meta = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_meta, meta)
+    rank = dist.get_rank()
+    if rank != 0:
+        dist.send(torch.from_numpy(a), dst=0, tag=77)
+        return None
+    nz = a.shape[0]
+    Nx = max(int(m[0] + m[2]) for m in all_meta)
+    Ny = max(int(m[1] + m[3]) for m in all_meta)
+    out = np.zeros((nz, Nx, Ny))
+    out[:, dec.xs:dec.xs + dec.xm, dec.ys:dec.ys + dec.ym] = a
+    for src in range(1, world):
+        xs, ys, xm, ym = (int(v) for v in all_meta[src])
+        buf = torch.empty((nz, xm, ym), dtype=torch.float64)
+        dist.recv(buf, src=src, tag=77)
+        out[:, xs:xs + xm, ys:ys + ym] = buf.numpy()
+    return out
+
+
+def pprts_get_result_toZero(api, solver, dec: CartDecomposition, opt_solution_uid=0):
+    """``pprts_get_result_toZero`` (src/pprts.F90:6265-6323): local results of every rank, gathered on rank 0 as
+    global (Nz[+1], Nx, Ny) arrays -> (gedn, geup, gabso, gedir) there, four ``None`` elsewhere."""
+    edn, eup, abso, edir = api.pprts_get_result(solver, opt_solution_uid)
+    return tuple(gather_all_to_zero(a, dec) for a in (edn, eup, abso, edir))

@@ -43,7 +43,17 @@ class _Config(C.Structure):
                 ("by_coeff_divergence", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
-                ("yrank", C.c_int)]
+                ("yrank", C.c_int), ("diff_explicit", C.c_int)]
+
+
+class _Bands(C.Structure):
+    _fields_ = [("nbands", C.c_int), ("lsolar", C.c_int), ("uid0", C.c_int), ("ldelta_scaling", C.c_int),
+                ("albedo", C.c_double), ("albedo_2d", C.c_void_p),
+                ("kabs", C.c_void_p), ("ksca", C.c_void_p), ("g", C.c_void_p),
+                ("stride_kabs", C.c_long), ("stride_ksca", C.c_long), ("stride_g", C.c_long),
+                ("planck", C.c_void_p), ("planck_srfc", C.c_void_p),
+                ("stride_planck", C.c_long), ("stride_planck_srfc", C.c_long),
+                ("edirTOA", C.c_void_p), ("weights", C.c_void_p), ("accumulate_only", C.c_int)]
 
 
 _lib = None
@@ -61,6 +71,7 @@ ABI_SYMBOLS = [
     "pprts_b200_comm_init", "pprts_b200_allreduce_accumulated", "pprts_b200_get_coeffs", "pprts_b200_get_state",
     "pprts_b200_get_info", "pprts_b200_mat_mult_ediff", "pprts_b200_lookup_coeffs", "pprts_b200_kernel_launches",
     "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error", "pprts_b200_stream",
+    "pprts_b200_solve_bands",
 ]
 
 
@@ -105,6 +116,7 @@ def lib():
     L.pprts_b200_stream.argtypes = [C.c_void_p]
     L.pprts_b200_kernel_stats.argtypes = [C.c_void_p, C.c_int, c_double_p, c_long_p]
     L.pprts_b200_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    L.pprts_b200_solve_bands.argtypes = [C.c_void_p, C.POINTER(_Bands)] + [C.c_void_p] * 4 + [c_int_p]
     _lib = L
     return L
 
@@ -268,7 +280,7 @@ def _alloc_results(s):
 def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=None, nxproc=None, nyproc=None,
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
-               keep_solutions=True, rank=None) -> Solver:
+               keep_solutions=True, rank=None, diff_explicit=False) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -305,6 +317,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.rtol, cfg.atol = float(rtol), float(atol)
     cfg.maxit_dir, cfg.maxit_diff = int(maxit_dir), int(maxit_diff)
     cfg.precond, cfg.device, cfg.keep_solutions = int(precond), int(device), int(keep_solutions)
+    cfg.diff_explicit = int(diff_explicit)
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
     if cfg.nxproc * cfg.nyproc > 1:
@@ -355,6 +368,77 @@ def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None):
     _chk(lib().pprts_b200_get_result(solver._h, int(opt_solution_uid), _vp(edn), _vp(eup), _vp(abso), _vp(edir)),
          "pprts_get_result")
     return edn, eup, abso, edir
+
+
+def solve_bands(solver: Solver, lsolar, albedo, kabs, ksca, g, planck=None, planck_srfc=None, edirTOA=None,
+                weights=None, uid0=None, albedo_2d=None, ldelta_scaling=True, out=None, download=True,
+                accumulate_only=False):
+    """The band loop of the spectral callers (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053 solar, :621-708 thermal) in one call:
+    ``set_optical_properties -> solve_pprts -> pprts_get_result -> sum`` for every band, with the upload of band ib+1
+    overlapping the solve of band ib and the spectral sum kept on the device.
+
+    ``kabs/ksca/g``: (Nz,Nx,Ny,nbands), or (Nz,Nx,Ny) to share a field between all bands; ``planck`` (Nz+1,Nx,Ny[,nbands]);
+    ``planck_srfc`` (Nx,Ny[,nbands]); ``edirTOA``, ``weights``: (nbands).  Solution uids are ``uid0 + ib`` (default: the
+    reference's 1.. for solar, 501.. for thermal).  Returns (edn, eup, abso, edir, niter) -- the weighted sums; with
+    ``download=False`` they stay in the device accumulator (``allreduce_accumulated`` / ``get_accumulated``)."""
+    s = solver
+    c3, l3, c2 = (s.Nz, s.Nx, s.Ny), (s.Nz + 1, s.Nx, s.Ny), (s.Nx, s.Ny)
+    nb = None
+    keep, ptr, stride = [], {}, {}
+    for name, a, shp in (("kabs", kabs, c3), ("ksca", ksca, c3), ("g", g, c3), ("planck", planck, l3),
+                         ("planck_srfc", planck_srfc, c2)):
+        if a is None:
+            ptr[name], stride[name] = None, 0
+            continue
+        sh = tuple(np.shape(a))
+        if sh == shp:
+            stride[name] = 0
+        elif sh[:-1] == shp:
+            if nb is not None and sh[-1] != nb:
+                raise PprtsError(f"solve_bands: {name} has {sh[-1]} bands, other fields have {nb}")
+            nb = sh[-1]
+            stride[name] = int(np.prod(shp))
+        else:
+            raise PprtsError(f"solve_bands: {name} has shape {sh}, expected {shp} or {shp + ('nbands',)}")
+        a = _f(a)
+        keep.append(a)
+        ptr[name] = _vp(a)
+    for name, a in (("kabs", kabs), ("ksca", ksca), ("g", g)):
+        if a is None:
+            raise PprtsError(f"solve_bands: {name} is required")
+    e = None if edirTOA is None else np.ascontiguousarray(edirTOA, dtype=np.float64).reshape(-1)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
+    for name, a in (("edirTOA", e), ("weights", w)):
+        if a is not None:
+            if nb is not None and a.size != nb:
+                raise PprtsError(f"solve_bands: {name} has {a.size} entries for {nb} bands")
+            nb = a.size
+    if nb is None:
+        nb = 1
+    if lsolar and e is None:
+        raise PprtsError("solve_bands: solar bands need edirTOA")
+    a2 = _f(albedo_2d)
+    if a2 is not None and a2.shape != c2:
+        raise PprtsError(f"solve_bands: albedo_2d has shape {a2.shape}, expected {c2}")
+    b = _Bands()
+    b.nbands, b.lsolar, b.ldelta_scaling = int(nb), int(bool(lsolar)), int(ldelta_scaling)
+    b.uid0 = int(uid0) if uid0 is not None else (1 if lsolar else 501)
+    b.albedo, b.albedo_2d = float(albedo), _vp(a2)
+    b.kabs, b.ksca, b.g = ptr["kabs"], ptr["ksca"], ptr["g"]
+    b.stride_kabs, b.stride_ksca, b.stride_g = stride["kabs"], stride["ksca"], stride["g"]
+    b.planck, b.planck_srfc = ptr["planck"], ptr["planck_srfc"]
+    b.stride_planck, b.stride_planck_srfc = stride["planck"], stride["planck_srfc"]
+    b.edirTOA, b.weights = _vp(e), _vp(w)
+    b.accumulate_only = int(accumulate_only)
+    niter = np.zeros(nb, dtype=np.int32)
+    if download:
+        edn, eup, abso, edir = out if out is not None else _alloc_results(s)
+        ptrs = [_vp(edn), _vp(eup), _vp(abso), _vp(edir)]
+    else:
+        edn = eup = abso = edir = None
+        ptrs = [None] * 4
+    _chk(lib().pprts_b200_solve_bands(s._h, C.byref(b), *ptrs, niter.ctypes.data_as(c_int_p)), "solve_bands")
+    return edn, eup, abso, edir, niter
 
 
 def destroy_pprts(solver: Solver, lfinalizepetsc=False):

@@ -8,7 +8,8 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from tenstream_b200.parallel import CartDecomposition, halo_fill_reference, proc_grid, split_even
+from tenstream_b200.parallel import (CartDecomposition, gather_all_to_zero, halo_fill_reference, proc_grid,
+                                     split_even)
 
 
 def test_coord_1rank():
@@ -58,7 +59,10 @@ def _worker(rank, world, port, nxp, nyp, q):
     # the ghost planes are the periodic images of the global field at x = xe+1 / y = ye+1
     want_x = np.roll(glob, -1, axis=2)[:, :, dec.xs + dec.xm - 1, dec.ys:dec.ys + dec.ym]
     want_y = np.roll(glob, -1, axis=3)[:, :, dec.xs:dec.xs + dec.xm, dec.ys + dec.ym - 1]
-    q.put((rank, bool(np.array_equal(gx, want_x)), bool(np.array_equal(gy, want_y))))
+    # gather_all_toZero (src/pprts.F90:6325-6359): rank 0 reassembles the global field from the local blocks
+    full = gather_all_to_zero(dec.local(glob[0]), dec)
+    ok_gather = (full is None) if rank else bool(np.array_equal(full, glob[0]))
+    q.put((rank, bool(np.array_equal(gx, want_x)) and ok_gather, bool(np.array_equal(gy, want_y))))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1011,7 +1011,7 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
   }
 }
 template <class L, class CT, class VT = double>
-__global__ void __launch_bounds__(PREC_BLOCK)
+__global__ void __launch_bounds__(PREC_BLOCK, 8)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const double *__restrict__ R, const double *__restrict__ inv,
             const VT *__restrict__ r, VT *z, int sides) {

@@ -1,0 +1,38 @@
+"""The committed golden vectors (tests/golden/pprts_cases.npz, written by tests/golden/make_golden.py) pin the oracle:
+any change to oracle/pprts_oracle.c or to the synthetic tables that moves a flux shows up here, on the CPU."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mg)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "pprts_cases.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(mg.CASES))
+def test_oracle_reproduces_golden(golden, tmp_path, name):
+    out = mg.run_case(str(tmp_path), name)
+    assert set(out) == {k for k in golden.files if k.startswith(name + "/")}
+    for k, a in out.items():
+        b = golden[k]
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 1e-9 * max(1e-30, np.abs(b).max()), k
+
+
+def test_golden_is_physical(golden):
+    for k in golden.files:
+        a = golden[k]
+        assert np.isfinite(a).all(), k
+        if not k.endswith("abso"):
+            assert (a >= -1e-9).all(), k
+    # all-1-D case: the direct beam follows Beer-Lambert per column, so it decreases monotonically downwards
+    e = golden["s310_b/solar/edir"]
+    assert (np.diff(e, axis=0) <= 1e-9).all()

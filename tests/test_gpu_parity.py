@@ -526,3 +526,35 @@ def test_explicit_relaxation_vs_oracle_sor(P, gpu_lut, oracle_lut, precond, sola
         assert relerr(a, b) < 1e-7, name
     assert s.info()["niter_diff"] > k.info()["niter_diff"]
     P.destroy_pprts(s); P.destroy_pprts(k); o.destroy()
+
+
+# ---- committed golden vectors (no oracle in the loop) -------------------------------------------------------------
+@pytest.mark.parametrize("name", ["s310_a", "s310_b", "s310_c", "s810_a", "s324_a"])
+def test_gpu_vs_committed_golden(P, tmp_path, name):
+    """tests/golden/pprts_cases.npz: fluxes and absorption of five small cases (3_10 incl. an all-1-D atmosphere,
+    8_10, 3_24; solar and thermal), frozen from the oracle by tests/golden/make_golden.py.  Tolerance 1e-5 relative
+    (north_star) -- both sides were converged to 1e-11, so the observed difference is ~1e-9."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    from tenstream_b200 import lut as L
+    golden = np.load(os.path.join(here, "golden", "pprts_cases.npz"))
+    sid, seed, (Nz, Nx, Ny), dz, phi0, theta0, albedo, ratio = mg.CASES[name]
+    cfg = L.small_test_config(sid)
+    lut = P.Lut(cfg, L.write_synthetic_lut(cfg, str(tmp_path / f"LUT{sid}")))
+    kabs, ksca, g = mg.atmosphere(seed, Nz, Nx, Ny)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(phi0, theta0), solver=sid, dz1d=np.full(Nz, dz),
+                     lut=lut, coeff_fp32=False, rtol=1e-11, atol=1e-30, twostr_ratio=ratio)
+    P.set_optical_properties(s, albedo, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1364.)
+    for nm, a in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s)):
+        assert relerr(a, golden[f"{name}/solar/{nm}"]) < 1e-5, nm
+    planck = np.broadcast_to(np.linspace(60., 120., Nz + 1)[:, None, None], (Nz + 1, Nx, Ny)).copy()
+    P.set_optical_properties(s, albedo / 4, kabs * 5, ksca, g, planck=planck, planck_srfc=np.full((Nx, Ny), 130.))
+    P.solve_pprts(s, True, False, 0., 3)
+    for nm, a in zip(("edn", "eup", "abso"), P.pprts_get_result(s, 3)):
+        assert relerr(a, golden[f"{name}/thermal/{nm}"]) < 1e-5, nm
+    P.destroy_pprts(s); lut.close()

@@ -151,9 +151,12 @@ def run_ours(args):
         s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]),
                          dz1d=sc["dz1d"], lut=lut, device=local, keep_solutions=False, coeff_fp32=True,
                          nxproc=dec.nxproc, nyproc=dec.nyproc, rank=rank)
+        mixed = False   # a decomposed run keeps fp64 Krylov vectors (the halo exchange is fp64)
     else:
+        mixed = args.krylov == "mixed"
         s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]),
-                         dz1d=sc["dz1d"], lut=lut, device=local, keep_solutions=False, coeff_fp32=True)
+                         dz1d=sc["dz1d"], lut=lut, device=local, keep_solutions=False, coeff_fp32=True,
+                         krylov_fp32=mixed)
     if world > 1:
         uid = [P.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -246,7 +249,7 @@ def run_ours(args):
                       "krylov_iterations": nfo["niter_diff"]})
     stats = s.kernel_stats(reset=True)
     s.enable_kernel_timing(False)
-    Nf, Cb, Sb = 10, 4, 8
+    Nf, Cb, Sb = 10, 4, (4 if mixed else 8)   # the (cycles + 1) fp64 MatMults per solve are counted at 4 B too: conservative
     ncell_local = Nz * Nx * Ny
     bytes_mv = (Nf * Nf * Cb + 2 * Nf * Sb) * ncell_local    # B_mv per cell x cells per launch
     mm = stats["matmult"]
@@ -267,7 +270,8 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"pprts 3_10 solar+thermal, synthetic cloud field {args.nx}x{args.ny}x{Nz} (BASELINE configs[1])",
                    "bands_per_step_per_gpu": len(bands), "cells": ncell, "coefficient_storage": "fp32",
-                   "state": "fp64", "tolerances": "reference defaults rtol=1e-5 atol=1e-4*Nx*Ny*(Nz+1)",
+                   "state": ("fp64 solution + fp64 true residual (iterative refinement), fp32 Krylov work vectors"
+                             if mixed else "fp64"), "tolerances": "reference defaults rtol=1e-5 atol=1e-4*Nx*Ny*(Nz+1)",
                    "krylov": "BiCGStab + vertical-line preconditioner", "start": "cold (zero initial guess)",
                    "l2": "working set per step (3.4 GB coefficients + 4 GB vectors) is far larger than the 126 MB L2",
                    "parallelism": (f"x/y decomposition {nxp}x{nyp} of one {args.nx}x{args.ny}x{Nz} domain, NCCL halo "
@@ -286,6 +290,17 @@ def run_ours(args):
         "iterations": iters,
         "clocks": clk,
     }
+    if mixed and world == 1:
+        # the same step with fp64 Krylov work vectors (krylov_fp32 = 0), for comparison
+        P.destroy_pprts(s)
+        s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]),
+                         dz1d=sc["dz1d"], lut=lut, device=local, keep_solutions=False, coeff_fp32=True)
+        stream = torch.cuda.ExternalStream(s.cuda_stream())
+        for slot, b in enumerate(bands):
+            s.stage_optical_properties(slot, b["albedo"], b["kabs"], b["ksca"], b["g"], b["planck"], b["planck_srfc"])
+        ms64, _ = timed(step_device, args.steps, 3)
+        line["fp64_vectors"] = {"value": units * args.steps / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64 / args.steps,
+                                "krylov_iterations": [s.info(b["uid"])["niter_diff"] for b in bands]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, steps=1)
     print(json.dumps(line))
@@ -392,6 +407,8 @@ def main():
     ap.add_argument("--cpu-ny", type=int, default=48)
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: replicas run side by side (0 = host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--krylov", default="mixed", choices=["mixed", "fp64"],
+                    help="Krylov work vectors: mixed = fp32 vectors + fp64 solution/true residual (iterative refinement)")
     ap.add_argument("--decomp", action="store_true", help="x/y domain decomposition over the GPUs instead of band sharding")
     args = ap.parse_args()
     if args.impl == "reference":

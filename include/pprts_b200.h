@@ -100,6 +100,10 @@ typedef struct {
    * instead of the Krylov solve.  The reference's cell-by-cell SOR ordering is sequential; here every sweep relaxes
    * all columns at once (x += M^-1 (b - A x), M = the column operator of `precond`, plain Jacobi when precond = 0). */
   int diff_explicit;
+  /* 1: mixed-precision Krylov solve -- fp32 work vectors inside BiCGStab, fp64 solution and fp64 true residual with
+   * iterative refinement (the convergence test is always evaluated on an fp64 residual).  Halves the vector traffic
+   * of the iteration.  Single-domain runs only (a decomposed run keeps fp64 vectors). Default 0. */
+  int krylov_fp32;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);

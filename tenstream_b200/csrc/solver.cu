@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -215,7 +216,7 @@ struct pprts_b200_solver {
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
   bool prec_ready = false;
-  int prec_block[2] = {0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
+  int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
   bool res_valid = false;
   int res_uid = 0;
@@ -446,6 +447,7 @@ extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   cfg->keep_solutions = 1;
   cfg->nxproc = cfg->nyproc = 1;
   cfg->diff_explicit = 0;
+  cfg->krylov_fp32 = 0;
 }
 
 template <class T>
@@ -590,7 +592,7 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   DA(s->cdiv_dir, (size_t)Nd * g.ncp); DA(s->cdiv_diff, (size_t)Nf * g.ncp);
   DA(s->tile_class, (size_t)(g.ncp / PB_TILE));
   DA(s->b, (size_t)state_len(g, Nf));
-  for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)state_len(g, Nf));
+  for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)state_len(g, Nf) + 2);  // +2: two 16-byte aligned fp32 vectors fit in one
   DA(s->edir_tmp, (size_t)state_len(g, Nd));
   if (s->decomposed) {
     const size_t hx = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Ny, hy = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Nx;
@@ -883,14 +885,14 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   return 0;
 }
 
-template <class L, int NDOT, int NSTAGE, bool PREFETCH>
-static bool launch_matmult_tma_v(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+template <class L, int NDOT, int NSTAGE, bool PREFETCH, class VT>
+static bool launch_matmult_tma_v(pprts_b200_solver *s, const VT *x, VT *y, const VT *w, double *dots) {
   constexpr size_t smem = (size_t)NSTAGE * L::Nf * L::Nf * PB_TILE * sizeof(float);
   if constexpr (smem > 200 * 1024) return false;
   else {
     const Grid &g = s->g;
     static bool attr_set = false;
-    auto kern = k_matmult_tma<L, NDOT, NSTAGE, PREFETCH>;
+    auto kern = k_matmult_tma<L, NDOT, NSTAGE, PREFETCH, VT>;
     if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     const long ntiles = (g.ncell + PB_TILE - 1) / PB_TILE;
     const int per_sm = std::max(1, std::min<int>(NSTAGE == 1 ? 4 : 2, (int)((220 * 1024) / smem)));
@@ -905,24 +907,27 @@ static bool launch_matmult_tma_v(pprts_b200_solver *s, const double *x, double *
     return true;
   }
 }
-template <class L, int NDOT>
-static bool launch_matmult_tma(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
-  switch (s->mm_variant) {
-    case 0: return launch_matmult_tma_v<L, NDOT, 2, true>(s, x, y, w, dots);
-    case 1: return launch_matmult_tma_v<L, NDOT, 2, false>(s, x, y, w, dots);
-    default: return launch_matmult_tma_v<L, NDOT, 1, false>(s, x, y, w, dots);
+template <class L, int NDOT, class VT>
+static bool launch_matmult_tma(pprts_b200_solver *s, const VT *x, VT *y, const VT *w, double *dots) {
+  if constexpr (std::is_same<VT, float>::value) return launch_matmult_tma_v<L, NDOT, 1, false, VT>(s, x, y, w, dots);
+  else {
+    switch (s->mm_variant) {
+      case 0: return launch_matmult_tma_v<L, NDOT, 2, true, VT>(s, x, y, w, dots);
+      case 1: return launch_matmult_tma_v<L, NDOT, 2, false, VT>(s, x, y, w, dots);
+      default: return launch_matmult_tma_v<L, NDOT, 1, false, VT>(s, x, y, w, dots);
+    }
   }
 }
 
-template <int NDOT>
-static void launch_matmult_local(pprts_b200_solver *s, const double *x, double *y, const double *w, double *dots) {
+template <int NDOT, class VT = double>
+static void launch_matmult_local(pprts_b200_solver *s, const VT *x, VT *y, const VT *w, double *dots) {
   const Grid &g = s->g;
   if (s->cfg.coeff_fp32 && s->use_tma) {
     bool done = false;
-    DISPATCH_L(s, done = launch_matmult_tma<L, NDOT>(s, x, y, w, dots));
+    DISPATCH_L(s, done = (launch_matmult_tma<L, NDOT, VT>(s, x, y, w, dots)));
     if (done) return;
   }
-  DISPATCH_LC(s, LAUNCH(s, FAM_MATMULT, (k_matmult<L, CT, NDOT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f,
+  DISPATCH_LC(s, LAUNCH(s, FAM_MATMULT, (k_matmult<L, CT, NDOT, VT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f,
                          s->a11, s->a12, s->albedo, x, y, w, s->partials, s->counter, dots));
 }
 
@@ -962,8 +967,8 @@ static int column_block(pprts_b200_solver *s, K kernel, int *cache) {
   return *cache = best;
 }
 
-template <class L, class CT>
-static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
+template <class L, class CT, class VT>
+static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
   if constexpr (L::Nft == 2) {
     const Grid &g = s->g;
     if (!s->prec_ready) {
@@ -971,15 +976,17 @@ static void launch_prec_t(pprts_b200_solver *s, const double *r, double *z) {
              s->albedo, s->precR, s->precInv);
       s->prec_ready = true;
     }
-    const int bu = column_block(s, k_prec_up<L, CT>, &s->prec_block[0]);
-    const int bd = column_block(s, k_prec_down<L, CT>, &s->prec_block[1]);
-    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+    constexpr int slot = std::is_same<VT, float>::value ? 2 : 0;
+    const int bu = column_block(s, k_prec_up<L, CT, VT>, &s->prec_block[slot]);
+    const int bd = column_block(s, k_prec_down<L, CT, VT>, &s->prec_block[slot + 1]);
+    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
-    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
   }
 }
-static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, launch_prec_t<L, CT>(s, r, z)); }
+static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, (launch_prec_t<L, CT, double>(s, r, z))); }
+static void launch_prec32(pprts_b200_solver *s, const float *r, float *z) { DISPATCH_LC(s, (launch_prec_t<L, CT, float>(s, r, z))); }
 
 // explicit_ediff (src/pprts_explicit.F90:461-713) analogue: stationary relaxation x += M^-1 (b - A x), all columns
 // at once; residual = ||x_n - x_{n-1}||_2 (mean over ranks of the local norms, :620-626), converged when it is < atol
@@ -1024,6 +1031,62 @@ static int solve_ediff_explicit(pprts_b200_solver *s, Solution &sol) {
   return 0;
 }
 
+
+// Mixed-precision BiCGStab (cfg.krylov_fp32): the eight Krylov work vectors are fp32 (half the vector traffic of every
+// kernel of the iteration), the solution x and the residual every cycle starts from are fp64.  A cycle is an fp32
+// BiCGStab run on r64 = b - A x; when its recursive residual meets the tolerance (or has dropped by 1e-4, the range an
+// fp32 recursion can be trusted over) the TRUE fp64 residual is evaluated again (iterative refinement): MyKSPConverged's
+// test (src/pprts.F90:4437-4486) is only ever passed by a residual that carries no fp32 rounding.  Typical solve at the
+// default rtol = 1e-5: one cycle plus one verifying MatMult.
+static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, double atol, int maxit) {
+  const Grid &g = s->g;
+  const long n = (long)s->Nf * g.nlev, n4 = (n + 3) & ~3L;
+  double *x = sol.ediff, *ax = s->kr[0];
+  float *r = (float *)s->kr[1], *rh = r + n4, *p = (float *)s->kr[2], *v = p + n4, *sv = (float *)s->kr[3], *t = sv + n4;
+  const bool prec = precond_available(s);
+  float *ph = prec ? (float *)s->kr[4] : p, *sh = prec ? ph + n4 : sv;
+  int rc;
+  double r0 = 0.0;
+  int total = 0;
+  bool converged = false;
+  sol.niter_diff = 0;
+  for (int cycle = 0; !converged; ++cycle) {
+    launch_matmult_local<0, double>(s, x, ax, nullptr, nullptr);
+    LAUNCH(s, FAM_VEC, k_mixed_init, vec_grid(n), VEC_BLOCK, n, s->b, ax, r, rh, s->partials, s->counter, s->sc);
+    if ((rc = read_scalars(s))) return rc;
+    const double rtrue = std::sqrt(s->h_sc[SC_RR]);
+    if (cycle == 0) r0 = std::max(DBL_MIN, rtrue);
+    sol.res_diff = rtrue;
+    if (!(rtrue == rtrue)) return set_err(21, "diffuse solve broke down (NaN residual) in refinement cycle %d", cycle);
+    if (rtrue / r0 <= rtol || rtrue <= atol) { converged = true; break; }
+    if (total >= maxit || cycle > 50) break;
+    const double rc0 = rtrue;  // residual this cycle starts from
+    bool restart = false;
+    for (int it = 1; total < maxit && !restart; ++it) {
+      LAUNCH(s, FAM_VEC, k_bicg32_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
+      if (prec) launch_prec32(s, p, ph);
+      launch_matmult_local<1, float>(s, ph, v, rh, s->sc + SC_RHV);
+      LAUNCH(s, FAM_VEC, k_bicg32_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
+      if (prec) launch_prec32(s, sv, sh);
+      launch_matmult_local<2, float>(s, sh, t, sv, s->sc + SC_TS);
+      LAUNCH(s, FAM_VEC, k_bicg32_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, x, r, s->partials, s->counter, s->sc);
+      if ((rc = read_scalars(s))) return rc;
+      const double rn = std::sqrt(s->h_sc[SC_RR]);
+      ++total;
+      sol.niter_diff = total;
+      sol.res_diff = rn;
+      if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", total);
+      if (rn / r0 <= rtol || rn <= atol || rn <= 1e-4 * rc0) restart = true;  // verify / refine in fp64
+    }
+    if (!restart) break;  // maxit
+  }
+  sol.first_diff = false;
+  sol.lchanged = true;
+  sol.lWm2_diff = false;
+  if (!converged) return set_err(22, "***** SOLVER did NOT converge :( -- %d iterations, residual %g", sol.niter_diff, sol.res_diff);
+  return 0;
+}
+
 // Right-preconditioned BiCGStab on the matrix-free operator; convergence test of MyKSPConverged
 // (src/pprts.F90:4437-4486): ||r||/||r0|| <= rtol or ||r|| <= atol, nonzero initial guess (:4343).
 static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
@@ -1040,6 +1103,7 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
   if (s->cfg.diff_explicit) return solve_ediff_explicit(s, sol);
   int rc = need_comm(s);
   if (rc) return rc;
+  if (s->cfg.krylov_fp32 && !s->decomposed) return solve_ediff_mixed(s, sol, rtol, atol, maxit);
   if ((rc = launch_matmult<0>(s, x, r, nullptr, nullptr))) return rc;
   LAUNCH(s, FAM_VEC, k_bicg_init, vec_grid(n), VEC_BLOCK, n, s->b, r, rh, p, v, s->partials, s->counter, s->sc);
   if ((rc = allreduce_scalars(s, s->sc + SC_RR, 2))) return rc;

@@ -43,7 +43,7 @@ class _Config(C.Structure):
                 ("by_coeff_divergence", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
-                ("yrank", C.c_int), ("diff_explicit", C.c_int)]
+                ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int)]
 
 
 class _Bands(C.Structure):
@@ -280,7 +280,7 @@ def _alloc_results(s):
 def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=None, nxproc=None, nyproc=None,
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
-               keep_solutions=True, rank=None, diff_explicit=False) -> Solver:
+               keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -318,6 +318,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.maxit_dir, cfg.maxit_diff = int(maxit_dir), int(maxit_diff)
     cfg.precond, cfg.device, cfg.keep_solutions = int(precond), int(device), int(keep_solutions)
     cfg.diff_explicit = int(diff_explicit)
+    cfg.krylov_fp32 = int(krylov_fp32)
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
     if cfg.nxproc * cfg.nyproc > 1:

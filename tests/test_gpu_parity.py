@@ -528,6 +528,67 @@ def test_explicit_relaxation_vs_oracle_sor(P, gpu_lut, oracle_lut, precond, sola
     P.destroy_pprts(s); P.destroy_pprts(k); o.destroy()
 
 
+# ---- mixed-precision Krylov solve (fp32 work vectors, fp64 solution + true residual) ------------------------------
+@pytest.mark.parametrize("sid", [310, 810])
+@pytest.mark.parametrize("coeff_fp32", [False, True])
+@pytest.mark.parametrize("solar", [True, False])
+def test_mixed_precision_krylov_vs_oracle(P, gpu_lut, oracle_lut, tmp_path, sid, coeff_fp32, solar):
+    """krylov_fp32: iterative refinement must reach the SAME tight tolerance (rtol 1e-10 on the fp64 true residual) as
+    the fp64-vector solve, i.e. the fp32 work vectors cost refinement cycles, never accuracy."""
+    from oracle import binding as ob
+    from tenstream_b200 import lut as L
+    if sid == 310:
+        glut, olut = gpu_lut, oracle_lut
+    else:
+        cfg = L.small_test_config(sid)
+        paths = L.write_synthetic_lut(cfg, str(tmp_path / f"LUT{sid}"))
+        glut, olut = P.Lut(cfg, paths), ob.OracleLut(cfg, paths)
+    rng = np.random.default_rng(23)
+    Nz, Nx, Ny = 9, 7, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    dz = np.full(Nz, 80.)
+    dz[:2] = 400.   # two 1-D layers on top
+    sd = P.sundir_from_angles(250., 35.)
+    tol = dict(rtol=1e-10, atol=1e-30)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, solver=sid, dz1d=dz, lut=glut, coeff_fp32=coeff_fp32,
+                     krylov_fp32=True, **tol)
+    o = ob.OracleSolver(olut, Nz, Nx, Ny, 100., 100., sd, dz, solver_id=sid, coeff_fp32=coeff_fp32, diff_solver=1, **tol)
+    planck = None if solar else np.broadcast_to(np.linspace(60., 120., Nz + 1)[:, None, None], (Nz + 1, Nx, Ny)).copy()
+    kw = dict(planck=planck) if not solar else {}
+    P.set_optical_properties(s, 0.2, kabs * (1 if solar else 5), ksca, g, **kw)
+    o.set_optical_properties(0.2, kabs * (1 if solar else 5), ksca, g, **kw)
+    P.solve_pprts(s, not solar, solar, 1000. if solar else 0.)
+    assert o.solve(not solar, solar, 1000. if solar else 0.) == 0
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b) < 1e-7, (name, s.info(), o.info())
+    P.destroy_pprts(s); o.destroy()
+    if sid != 310:
+        glut.close()
+
+
+def test_mixed_precision_default_tolerances_match_fp64_vectors(P, gpu_lut):
+    """At the reference's default tolerances (the bench configuration) the mixed solve and the fp64-vector solve both
+    stop on an fp64 residual <= rtol*r0: their fluxes agree far inside the 1e-5 contract on a cloudy 32x32x24 field."""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field(Nx=32, Ny=32, Nz=24)
+    sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
+    out = []
+    for mixed in (False, True):
+        s = P.init_pprts(0, sc["Nz"], sc["Nx"], sc["Ny"], sc["dx"], sc["dy"], sd, dz1d=sc["dz1d"], lut=gpu_lut,
+                         coeff_fp32=True, krylov_fp32=mixed, rtol=1e-8)
+        P.set_optical_properties(s, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+        P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+        res = [np.array(a) for a in P.pprts_get_result(s, 1)]
+        P.set_optical_properties(s, sc["albedo_th"], sc["kabs_th"], sc["ksca_th"], sc["g_th"], planck=sc["planck"],
+                                 planck_srfc=sc["planck_srfc"])
+        P.solve_pprts(s, True, False, 0., 501)
+        res += [np.array(a) for a in P.pprts_get_result(s, 501)[:3]]
+        out.append((res, s.info(1), s.info(501)))
+        P.destroy_pprts(s)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert relerr(b, a) < 1e-6, (out[0][1:], out[1][1:])
+
+
 # ---- committed golden vectors (no oracle in the loop) -------------------------------------------------------------
 @pytest.mark.parametrize("name", ["s310_a", "s310_b", "s310_c", "s810_a", "s324_a"])
 def test_gpu_vs_committed_golden(P, tmp_path, name):

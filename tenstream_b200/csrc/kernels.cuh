@@ -4,6 +4,7 @@
 #pragma once
 #include <float.h>
 #include <math.h>
+#include <type_traits>
 
 #include <cuda.h>
 
@@ -610,47 +611,57 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdi
 //                  the face where it LEAVES (its destination row) -- the same set serves 3-D cells, 1-D cells, the
 //                  TOA rows and the albedo row
 //   matmult_emit : y = xd - sum_s coef(dst,s) xs, stores + fused dot products; COEF(n) returns coefficient dst*Nf+src
-template <class L>
+// AT is the arithmetic type: double for fp64 state vectors; float for the fp32 Krylov work vectors of the mixed
+// solve, where coefficients (fp32 storage), operands and products stay fp32 (FFMA, no conversions at all) and only the
+// per-cell subtotals of the fused dot products are widened into the fp64 accumulators.
+template <class L, class AT = double>
 struct MatIn {
-  double xs[L::Nf], xd[L::Nf];
-  double wd[L::Nf];  // dot-product weight w0 at the destination row of stream d (NDOT > 0)
+  AT xs[L::Nf], xd[L::Nf];
+  AT wd[L::Nf];  // dot-product weight w0 at the destination row of stream d (NDOT > 0)
 };
+template <class AT, class T>
+__device__ __forceinline__ AT to_at(T v) {
+  if constexpr (std::is_same<AT, double>::value) return widen_any(v);
+  else return (AT)v;
+}
 template <class L, int NDOT, class VT>
 __device__ __forceinline__ void matmult_load(const Grid &g, const Faces &f, const VT *__restrict__ x,
-                                             const VT *__restrict__ w0, MatIn<L> &in) {
+                                             const VT *__restrict__ w0, MatIn<L, VT> &in) {
 #pragma unroll
   for (int d = 0; d < L::Nf; ++d) {
     const long qd = diff_face<L>(g, f, d, true);
-    in.xs[d] = widen_any(x[diff_face<L>(g, f, d, false)]);
-    in.xd[d] = widen_any(x[qd]);
-    if (NDOT > 0) in.wd[d] = diff_exit_is_ghost<L>(f, d) ? 0.0 : widen_any(w0[qd]);  // ghost rows: the owner adds its share
+    in.xs[d] = x[diff_face<L>(g, f, d, false)];
+    in.xd[d] = x[qd];
+    if (NDOT > 0) in.wd[d] = diff_exit_is_ghost<L>(f, d) ? VT(0) : w0[qd];  // ghost rows: the owner adds its share
   }
 }
 template <class L, int NDOT, class COEF, class VT>
 __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, const Faces &f,
-                                             const MatIn<L> &in, const double *__restrict__ a11,
+                                             const MatIn<L, VT> &in, const double *__restrict__ a11,
                                              const double *__restrict__ a12, const double *__restrict__ albedo,
                                              const VT *__restrict__ x, VT *__restrict__ y,
                                              const VT *__restrict__ w0, double *dots) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  using AT = VT;
+  AT ld0 = 0, ld1 = 0;  // this cell's share of the dot products
   // NDOT == 1: dots[0] = sum w0*y ; NDOT == 2: dots[0] = sum y*w0, dots[1] = sum y*y
-  auto emit = [&](long q, double val) {  // rare rows: weight loaded on the spot
-    y[q] = (VT)val;
-    if (NDOT >= 1) dots[0] += val * widen_any(w0[q]);
-    if (NDOT >= 2) dots[1] += val * val;
+  auto emit = [&](long q, AT val) {  // rare rows: weight loaded on the spot
+    y[q] = val;
+    if (NDOT >= 1) ld0 += val * w0[q];
+    if (NDOT >= 2) ld1 += val * val;
   };
-  auto emit_w = [&](int d, long q, double val) {  // destination rows: weight prefetched with the state
-    y[q] = (VT)val;
-    if (NDOT >= 1) dots[0] += val * in.wd[d];
-    if (NDOT >= 2) { if (!diff_exit_is_ghost<L>(f, d)) dots[1] += val * val; }
+  auto emit_w = [&](int d, long q, AT val) {  // destination rows: weight prefetched with the state
+    y[q] = val;
+    if (NDOT >= 1) ld0 += val * in.wd[d];
+    if (NDOT >= 2) { if (!diff_exit_is_ghost<L>(f, d)) ld1 += val * val; }
   };
   const long l_own = f.own, l_dn = f.dn;
   const int k = f.k;
   if (k < n1d) {
-    const double t = a11[l_own], r = a12[l_own];
+    const AT t = (AT)a11[l_own], r = (AT)a12[l_own];
 #pragma unroll
     for (int d = 0; d < Nft; ++d) {  // xb(dst) = x(dst) - x(d, other side)*a11 - x(inv_dof, same level)*a12
-      double acc = 0.0;
+      AT acc = 0;
       acc = acc - in.xs[d] * t;
       acc = acc - in.xs[L::inv_dof(d)] * r;
       emit_w(d, diff_face<L>(g, f, d, true), acc + in.xd[d]);
@@ -663,7 +674,7 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
   } else {
 #pragma unroll
     for (int dst = 0; dst < Nf; ++dst) {
-      double acc = 0.0;
+      AT acc = 0;
 #pragma unroll
       for (int s = 0; s < Nf; ++s) acc = acc - in.xs[s] * coef(dst * Nf + s);
       emit_w(dst, diff_face<L>(g, f, dst, true), acc + in.xd[dst]);
@@ -674,12 +685,14 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
     for (int d = 0; d < Nft; ++d) if (L::top_in(d)) emit((long)d * g.nlev + l_own, in.xs[d]);
   }
   if (k == g.Nz - 1) {  // albedo row (src/pprts_shell.F90:500-505) and the unused side dofs below the ground
-    const double alb = albedo[(long)f.j * g.Nx + f.i];
+    const AT alb = (AT)albedo[(long)f.j * g.Nx + f.i];
 #pragma unroll
     for (int d = 0; d < Nft; ++d) if (!L::top_in(d)) emit((long)d * g.nlev + l_dn, in.xs[d] - in.xd[L::inv_dof(d)] * alb);
 #pragma unroll
-    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, widen_any(x[q])); }
+    for (int d = Nft; d < Nf; ++d) { long q = (long)d * g.nlev + l_dn; emit(q, x[q]); }
   }
+  if (NDOT >= 1) dots[0] += to_at<double>(ld0);
+  if (NDOT >= 2) dots[1] += to_at<double>(ld1);
 }
 
 template <class L, class CT, int NDOT, class VT = double>
@@ -694,9 +707,9 @@ k_matmult(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   for (int n = 0; n < NV; ++n) dots[n] = 0.0;
   if (c < g.ncell) {
     const long cb = cbase<L::Nf * L::Nf>(c);
-    auto coef = [&](int n) { return widen(T[cb + n * PB_TILE]); };
+    auto coef = [&](int n) { if constexpr (std::is_same<VT, float>::value) return (float)T[cb + n * PB_TILE]; else return widen(T[cb + n * PB_TILE]); };
     const Faces ci = cell_faces<L::Nf>(g, c);
-    MatIn<L> in;
+    MatIn<L, VT> in;
     matmult_load<L, NDOT, VT>(g, ci, x, w0, in);
     matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
   }
@@ -768,9 +781,12 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
     mbar_expect_tx(b, STAGE_BYTES);
     bulk_g2s(stage(st), T + tile * (long)(NP * PB_TILE), STAGE_BYTES, b);  // one contiguous run
   };
-  auto compute = [&](long tile, int st, unsigned int cls, const Faces &ci, const MatIn<L> &in, double *dots) {
+  auto compute = [&](long tile, int st, unsigned int cls, const Faces &ci, const MatIn<L, VT> &in, double *dots) {
     const float *sp = stage(st) + tid;
-    if (__builtin_expect(cls == 0, 1)) {  // CTA-uniform
+    if constexpr (std::is_same<VT, float>::value) {  // fp32 arithmetic: the staged coefficients are used as they are
+      auto coef = [&](int n) { return sp[n * PB_TILE]; };
+      matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
+    } else if (__builtin_expect(cls == 0, 1)) {  // CTA-uniform
       auto coef = [&](int n) { return widen_normal(sp[n * PB_TILE]); };
       matmult_emit<L, NDOT>(g, n1d, coef, ci, in, a11, a12, albedo, x, y, w0, dots);
     } else if (cls == 1) {
@@ -792,7 +808,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
       const long c = tile * PB_TILE + tid;
       const unsigned int cls = tile_class[tile];
       Faces ci;
-      MatIn<L> in;
+      MatIn<L, VT> in;
       if (c < g.ncell) {  // state loads travel together with the bulk copy
         ci = cell_faces<L::Nf>(g, c);
         matmult_load<L, NDOT, VT>(g, ci, x, w0, in);
@@ -804,7 +820,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
   } else {
     if (tid == 0 && tile < ntiles) issue(tile, 0);
     Faces ci, ci_n;
-    MatIn<L> in, in_n;
+    MatIn<L, VT> in, in_n;
     unsigned int cls = 0, cls_n = 0;
     if (PREFETCH) {
       if (tile < ntiles) cls = tile_class[tile];
@@ -885,37 +901,43 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
   }
 }
 
+// coefficient -> arithmetic type of the column kernels: exact widening for fp64 vectors, as stored / rounded for fp32
+template <class AT, class T>
+__device__ __forceinline__ AT cw(T c) {
+  if constexpr (std::is_same<AT, double>::value) return widen(c);
+  else return (AT)c;
+}
 // upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied
-template <class L, class CT>
+template <class L, class CT, class AT>
 struct PrecUpIn {
-  double fU, fD, tuu, tud, iv, Rc;
-  double rs[2 * L::Nfs];         // all side dofs of the level (1-D layers copy them, 3-D layers use the inward ones)
+  AT fU, fD, tuu, tud, iv, Rc;
+  AT rs[2 * L::Nfs];         // all side dofs of the level (1-D layers copy them, 3-D layers use the inward ones)
   CT t0[L::Nfs], t1[L::Nfs];     // T(0, inward side), T(1, inward side)
 };
 template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                              const double *__restrict__ a11, const double *__restrict__ a12,
                                              const double *__restrict__ R, const double *__restrict__ inv,
-                                             const VT *__restrict__ r, PrecUpIn<L, CT> &in) {
+                                             const VT *__restrict__ r, PrecUpIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-  in.fU = widen_any(r[0 * g.nlev + c]);
-  in.fD = widen_any(r[1 * g.nlev + l1]);
-  in.iv = inv[c];
-  in.Rc = R[c];
+  in.fU = r[0 * g.nlev + c];
+  in.fD = r[1 * g.nlev + l1];
+  in.iv = (VT)inv[c];
+  in.Rc = (VT)R[c];
   if (k < n1d) {
-    in.tuu = a11[c]; in.tud = a12[c];
+    in.tuu = (VT)a11[c]; in.tud = (VT)a12[c];
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = widen_any(r[(long)(Nft + d) * g.nlev + c]);
+    for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
   } else {
     const long cb = cbase<Nf * Nf>(c);
-    in.tuu = (double)T[cb + (0 * Nf + 0) * PB_TILE];
-    in.tud = (double)T[cb + (1 * Nf + 0) * PB_TILE];
+    in.tuu = (VT)T[cb + (0 * Nf + 0) * PB_TILE];
+    in.tud = (VT)T[cb + (1 * Nf + 0) * PB_TILE];
     int q = 0;
 #pragma unroll
     for (int d = 0; d < 2 * Nfs; ++d) {
       if (L::side_in(d % Nfs)) {
-        in.rs[d] = widen_any(r[(long)(Nft + d) * g.nlev + c]);
+        in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
         in.t0[q] = T[cb + (0 * Nf + Nft + d) * PB_TILE];
         in.t1[q] = T[cb + (1 * Nf + Nft + d) * PB_TILE];
         ++q;
@@ -933,29 +955,29 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
   const long lz = (long)g.Nz * g.ncol + col;
-  double S = widen_any(r[0 * g.nlev + lz]);  // f_U at the surface
-  z[0 * g.nlev + lz] = (VT)S;
+  VT S = r[0 * g.nlev + lz];  // f_U at the surface
+  z[0 * g.nlev + lz] = S;
 #pragma unroll
   for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + lz] = r[(long)d * g.nlev + lz];
-  double Rn = R[lz];
-  PrecUpIn<L, CT> cur, nxt;
+  VT Rn = (VT)R[lz];
+  PrecUpIn<L, CT, VT> cur, nxt;
   prec_up_load<L, CT, VT>(g, n1d, g.Nz - 1, col, T, a11, a12, R, inv, r, cur);
   for (int k = g.Nz - 1; k >= 0; --k) {
     if (k > 0) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-    double fU = cur.fU, fD = cur.fD;
+    VT fU = cur.fU, fD = cur.fD;
     if (k < n1d) {
 #pragma unroll
-      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = (VT)cur.rs[d];
+      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
     } else {
       int q = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (L::side_in(d % Nfs)) {
-          z[(long)(Nft + d) * g.nlev + c] = (VT)cur.rs[d];
+          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
           if (sides) {
-            fU = fma(widen(cur.t0[q]), cur.rs[d], fU);
-            fD = fma(widen(cur.t1[q]), cur.rs[d], fD);
+            fU = fma(cw<VT>(cur.t0[q]), cur.rs[d], fU);
+            fD = fma(cw<VT>(cur.t1[q]), cur.rs[d], fD);
           }
           ++q;
         }
@@ -963,37 +985,37 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
     }
     S = fU + cur.tuu * (S + Rn * (cur.tud * S + fD) * cur.iv);
     Rn = cur.Rc;
-    z[0 * g.nlev + c] = (VT)S;
-    z[1 * g.nlev + l1] = (VT)fD;
+    z[0 * g.nlev + c] = S;
+    z[1 * g.nlev + l1] = fD;
     if (k > 0) cur = nxt;
   }
   z[1 * g.nlev + col] = r[1 * g.nlev + col];  // f_D(0) = r_D(0)
 }
 
-template <class L, class CT>
+template <class L, class CT, class AT>
 struct PrecDownIn {
-  double tdd, tud, S1, fD, iv, R1;
-  double rsd[2 * L::Nfs];                 // r of all side dofs at the cell
+  AT tdd, tud, S1, fD, iv, R1;
+  AT rsd[2 * L::Nfs];                 // r of all side dofs at the cell
   CT tt[L::Nfs][2 + L::Nfs];              // per outward dof: T(dof,0), T(dof,1), T(dof, inward sides)
 };
 template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                                const double *__restrict__ a11, const double *__restrict__ a12,
                                                const double *__restrict__ R, const double *__restrict__ inv,
-                                               const VT *__restrict__ r, const VT *z, PrecDownIn<L, CT> &in) {
+                                               const VT *__restrict__ r, const VT *z, PrecDownIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-  in.S1 = widen_any(z[0 * g.nlev + l1]);
-  in.fD = widen_any(z[1 * g.nlev + l1]);
-  in.iv = inv[c];
-  in.R1 = R[l1];
-  if (k < n1d) { in.tdd = a11[c]; in.tud = a12[c]; }
+  in.S1 = z[0 * g.nlev + l1];
+  in.fD = z[1 * g.nlev + l1];
+  in.iv = (VT)inv[c];
+  in.R1 = (VT)R[l1];
+  if (k < n1d) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
   else {
     const long cb = cbase<Nf * Nf>(c);
-    in.tdd = (double)T[cb + (1 * Nf + 1) * PB_TILE];
-    in.tud = (double)T[cb + (1 * Nf + 0) * PB_TILE];
+    in.tdd = (VT)T[cb + (1 * Nf + 1) * PB_TILE];
+    in.tud = (VT)T[cb + (1 * Nf + 0) * PB_TILE];
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = widen_any(r[(long)(Nft + d) * g.nlev + c]);
+    for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
     int o = 0;
 #pragma unroll
     for (int d = 0; d < 2 * Nfs; ++d) {
@@ -1018,39 +1040,39 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
   constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
-  double D = widen_any(z[1 * g.nlev + col]);
-  double U = R[col] * D + widen_any(z[0 * g.nlev + col]);
-  z[0 * g.nlev + col] = (VT)U;
-  PrecDownIn<L, CT> cur, nxt;
+  VT D = z[1 * g.nlev + col];
+  VT U = (VT)R[col] * D + z[0 * g.nlev + col];
+  z[0 * g.nlev + col] = U;
+  PrecDownIn<L, CT, VT> cur, nxt;
   prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cur);
   for (int k = 0; k < g.Nz; ++k) {
     // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
     if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
-    const double S1 = cur.S1;
-    const double D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
-    const double U1 = cur.R1 * D1 + S1;
+    const VT S1 = cur.S1;
+    const VT D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
+    const VT U1 = cur.R1 * D1 + S1;
     if (k >= n1d) {  // outgoing side streams through the column's own faces
       int o = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (!L::side_in(d % Nfs)) {
-          double acc = cur.rsd[d];
+          VT acc = cur.rsd[d];
           if (sides) {
-          acc = fma(widen(cur.tt[o][0]), U1, acc);
-          acc = fma(widen(cur.tt[o][1]), D, acc);
+          acc = fma(cw<VT>(cur.tt[o][0]), U1, acc);
+          acc = fma(cw<VT>(cur.tt[o][1]), D, acc);
           int q = 0;
 #pragma unroll
           for (int s = 0; s < 2 * Nfs; ++s)
-            if (L::side_in(s % Nfs)) { acc = fma(widen(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
+            if (L::side_in(s % Nfs)) { acc = fma(cw<VT>(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
           }
-          z[(long)(Nft + d) * g.nlev + c] = (VT)acc;
+          z[(long)(Nft + d) * g.nlev + c] = acc;
           ++o;
         }
       }
     }
-    z[0 * g.nlev + l1] = (VT)U1;
-    z[1 * g.nlev + l1] = (VT)D1;
+    z[0 * g.nlev + l1] = U1;
+    z[1 * g.nlev + l1] = D1;
     D = D1;
     if (k + 1 < g.Nz) cur = nxt;
   }
@@ -1155,6 +1177,16 @@ __global__ void k_mixed_init(long n, const double *__restrict__ b, const double 
     acc[1] += rd * rd;
   }
   grid_reduce_sum<2>(acc, partials, counter, &sc[SC_RR]);
+}
+// SC_TMP = ||b - Ax||^2 (Ax in `ax`): fp64 check of the true residual that leaves the fp32 recursion untouched
+__global__ void k_residual_norm2(long n, const double *__restrict__ b, const double *__restrict__ ax,
+                                 double *partials, unsigned int *counter, double *out) {
+  double acc[1] = {0.0};
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const double rv = b[q] - ax[q];
+    acc[0] = fma(rv, rv, acc[0]);
+  }
+  grid_reduce_sum<1>(acc, partials, counter, out);
 }
 // p = r + beta (p - omega v)   (it == 1: p = r)
 __global__ void k_bicg32_update_p(long n, int it, const float *__restrict__ r, const float *__restrict__ v,

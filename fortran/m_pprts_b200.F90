@@ -34,7 +34,7 @@ module m_pprts_b200
     integer(c_int) :: coeff_fp32, by_coeff_divergence
     real(c_double) :: rtol, atol
     integer(c_int) :: maxit_dir, maxit_diff, precond, device, keep_solutions, nxproc, nyproc, xrank, yrank, &
-      & diff_explicit, krylov_fp32
+      & diff_explicit, krylov_fp32, collapseindex
   end type
 
   interface

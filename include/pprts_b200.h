@@ -104,6 +104,11 @@ typedef struct {
    * iterative refinement (the convergence test is always evaluated on an fp64 residual).  Halves the vector traffic
    * of the iteration.  Single-domain runs only (a decomposed run keeps fp64 vectors). Default 0. */
   int krylov_fp32;
+  /* init_pprts collapseindex (src/pprts.F90:692-706, handle_atm_collapse :2080-2198): > 1 merges the top
+   * `collapseindex` atmosphere layers (forced 1-D) into ONE 1-D layer by the adding method; Nz, dz and all optical
+   * property arrays are then on the ATMOSPHERE grid (Nz layers) while the solver grid and every result array have
+   * Nz - collapseindex + 1 layers.  <= 1: off. */
+  int collapseindex;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);

@@ -47,7 +47,7 @@ class _Config(C.Structure):
                 ("dx", C.c_double), ("dy", C.c_double), ("dz", c_double_p), ("sundir", C.c_double * 3),
                 ("twostr_ratio", C.c_double), ("coeff_fp32", C.c_int), ("by_coeff_divergence", C.c_int),
                 ("diff_solver", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
-                ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("nthreads", C.c_int)]
+                ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("nthreads", C.c_int), ("collapseindex", C.c_int)]
 
 
 _lib = None
@@ -224,16 +224,18 @@ class OracleSolver:
 
     def __init__(self, lut: OracleLut, Nz, Nx, Ny, dx, dy, sundir, dz, solver_id=310, twostr_ratio=2.0,
                  coeff_fp32=False, by_coeff_divergence=True, diff_solver=0, rtol=-1.0, atol=-1.0,
-                 maxit_dir=0, maxit_diff=0, nthreads=0):
+                 maxit_dir=0, maxit_diff=0, nthreads=0, collapseindex=1):
         self.lut = lut
-        self.Nz, self.Nx, self.Ny = Nz, Nx, Ny
+        ci = max(1, int(collapseindex))
+        self.Nz_atm = Nz
+        self.Nz, self.Nx, self.Ny = Nz - ci + 1, Nx, Ny   # solver grid (results) after the collapse
         dz = np.asarray(dz, dtype=np.float64)
         if dz.ndim == 1:
             dz = np.broadcast_to(dz[:, None, None], (Nz, Nx, Ny))
         self._dz = f_order(dz)
         cfg = _Config(solver_id, Nz, Nx, Ny, dx, dy, _dp(self._dz), (C.c_double * 3)(*sundir), twostr_ratio,
                       int(coeff_fp32), int(by_coeff_divergence), diff_solver, rtol, atol, maxit_dir, maxit_diff,
-                      nthreads)
+                      nthreads, ci)
         self._h = lib().orc_solver_create(C.byref(cfg), C.byref(lut._lut))
         if not self._h:
             raise RuntimeError("orc_solver_create failed")

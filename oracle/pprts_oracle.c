@@ -206,6 +206,76 @@ void orc_delta_scale(double *kabs, double *ksca, double *g) {
   *ksca = dtau * w0;
 }
 
+/* src/schwarzschild.F90:69-80 (schwarzschild_radiance); the threshold is the default-real literal 1e-3 */
+static void schwarzschild_radiance(double tau, double B_near, double B_far, double *L) {
+  if (tau > (double)1e-3f) {
+    double tm1 = expm1(-tau);
+    *L = *L * (tm1 + 1) + (B_far - B_near) - (B_near - (B_far - B_near) / tau) * tm1;
+  } else {
+    *L = (B_near + B_far) * .5 * tau + *L * (1.0 - tau);
+  }
+}
+/* src/schwarzschild.F90:82-150 (schwarzschild, use_legendre branch) with Nmu = 2: Edn, Eup have ke+1 entries */
+void orc_schwarzschild2(int ke, const double *dtau, double albedo, double *Edn, double *Eup, const double *planck,
+                        const double *opt_srfc_emission) {
+  static const double pt[2] = {0.21132486540518713, 0.78867513459481287};
+  static const double wi[2] = {0.5, 0.5};
+  int imu, k;
+  double Bsrfc = opt_srfc_emission ? *opt_srfc_emission : planck[ke];
+  for (k = 0; k <= ke; ++k) { Edn[k] = 0; Eup[k] = 0; }
+  for (imu = 0; imu < 2; ++imu) {
+    double mu = pt[imu], Ldn = 0;
+    for (k = 0; k < ke; ++k) {
+      schwarzschild_radiance(dtau[k] / mu, planck[k], planck[k + 1], &Ldn);
+      Edn[k + 1] = Edn[k + 1] + Ldn * mu * wi[imu];
+    }
+  }
+  for (imu = 0; imu < 2; ++imu) {
+    double mu = pt[imu], Lup = Bsrfc * (1.0 - albedo) + albedo * Edn[ke] * 2;
+    Eup[ke] = Eup[ke] + Lup * mu * wi[imu];
+    for (k = ke - 1; k >= 0; --k) {
+      schwarzschild_radiance(dtau[k] / mu, planck[k + 1], planck[k], &Lup);
+      Eup[k] = Eup[k] + Lup * mu * wi[imu];
+    }
+  }
+  for (k = 0; k <= ke; ++k) { Eup[k] = Eup[k] * 2 * ORC_PI; Edn[k] = Edn[k] * 2 * ORC_PI; }
+}
+/* src/pprts.F90:2125-2198 (adding) */
+void orc_adding(int N, double *a11, double *a12, double *a21, double *a22, double *a13, double *a23, double *a33,
+                const double *dtau, const double *planck, double *Btop, double *Bbot) {
+  double t = a11[0], r = a12[0], tdir = a33[0], rdir = a13[0], sdir = a23[0];
+  double rl, tl, Tbot, Ttop, Rbot, Rtop;
+  int k;
+  for (k = 1; k < N; ++k) { /* reflectivity as seen from the top */
+    rl = r; tl = t;
+    r = r + (a12[k] * t * t) / (1.0 - r * a12[k]);
+    t = t * a11[k] / (1.0 - rl * a12[k]);
+    sdir = (a11[k] * sdir + tdir * a13[k] * rl * a11[k]) / (1.0 - rl * a12[k]) + tdir * a23[k];
+    rdir = rdir + (tdir * a13[k] + sdir * a12[k]) * tl;
+    tdir = tdir * a33[k];
+  }
+  Ttop = t; Rtop = r;
+  a13[N - 1] = rdir; a23[N - 1] = sdir; a33[N - 1] = tdir;
+  t = a22[N - 1]; r = a21[N - 1];
+  for (k = N - 2; k >= 0; --k) { /* reflectivity as seen from the bottom */
+    rl = r; tl = t;
+    r = a12[k] + (r * a11[k] * a11[k]) / (1.0 - r * a12[k]);
+    t = t * a11[k] / (1.0 - rl * a21[k]);
+  }
+  (void)tl;
+  Tbot = t; Rbot = r;
+  a12[N - 1] = Rtop; a22[N - 1] = Ttop; a11[N - 1] = Tbot; a21[N - 1] = Rbot;
+  for (k = 0; k < N - 1; ++k) a11[k] = a12[k] = a21[k] = a22[k] = a13[k] = a23[k] = a33[k] = 0.0;
+  if (planck) {
+    double *Edn = (double *)malloc(sizeof(double) * (N + 1)), *Eup = (double *)malloc(sizeof(double) * (N + 1));
+    const double zero = 0.0;
+    orc_schwarzschild2(N, dtau, 0.0, Edn, Eup, planck, &zero);
+    *Bbot = Edn[N] / ORC_PI;
+    *Btop = Eup[0] / ORC_PI;
+    free(Edn); free(Eup);
+  }
+}
+
 /* ================================================================================================================
  * stream tables and symmetry permutations
  * ================================================================================================================ */
@@ -438,6 +508,11 @@ struct orc_solver {
   double *dz;
   int *l1d;
   double unconstrained_fraction;
+  /* atmosphere collapse (src/pprts_base.F90:118-122, :1088-1093 atmk): the solver grid starts at atmosphere layer
+   * icollapse-1; dz_atm / l1d_atm live on the Nz_atm atmosphere layers, everything else on the Nz solver layers */
+  int Nz_atm, icollapse;
+  double *dz_atm, *Btop, *Bbot;
+  int *l1d_atm;
   /* t_suninfo, src/pprts_base.F90:128-135 */
   double phi, theta, mu, costheta, symmetry_phi, sundir[3];
   int xinc, yinc;
@@ -586,26 +661,31 @@ void orc_get_suninfo(orc_solver *s, double *phi, double *theta, double *symmetry
   *phi = s->phi; *theta = s->theta; *symmetry_phi = s->symmetry_phi; *xinc = s->xinc; *yinc = s->yinc;
 }
 
-/* src/pprts.F90:649-725 (determine_1d_layers), one rank, no collapse */
+/* src/pprts.F90:649-725 (determine_1d_layers), one rank; works on the atmosphere grid (C_one_atm) */
 static void determine_1d_layers(orc_solver *s) {
-  LOCALS
+  const int Nz = s->Nz_atm, Nx = s->Nx, Ny = s->Ny; /* A3 below indexes the atmosphere arrays */
   int k, i, j, any, kk, count3d = 0;
-  for (k = 0; k < Nz; ++k) s->l1d[k] = 0;
+  int *l1d = s->l1d_atm;
+  const double *dz = s->dz_atm;
+  for (k = 0; k < Nz; ++k) l1d[k] = 0;
   any = 0;
-  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) if (A3(s->dz, Nz - 1, i, j) / s->dx > s->cfg.twostr_ratio) any = 1;
-  s->l1d[Nz - 1] = any;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) if (A3(dz, Nz - 1, i, j) / s->dx > s->cfg.twostr_ratio) any = 1;
+  l1d[Nz - 1] = any;
   for (k = Nz - 2; k >= 0; --k) {
     any = 0;
-    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) if (A3(s->dz, k, i, j) / s->dx > s->cfg.twostr_ratio) any = 1;
-    if (any) { for (kk = 0; kk <= k; ++kk) s->l1d[kk] = 1; break; }
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) if (A3(dz, k, i, j) / s->dx > s->cfg.twostr_ratio) any = 1;
+    if (any) { for (kk = 0; kk <= k; ++kk) l1d[kk] = 1; break; }
   }
+  if (s->icollapse > 1) /* :692-706 layers that are collapsed have to be 1-D */
+    for (k = 0; k <= s->icollapse - 1; ++k) l1d[k] = 1;
   { /* :708-719: the 1-D block is contiguous from the top */
     int n1d = 0;
-    for (k = 0; k < Nz; ++k) n1d += s->l1d[k];
-    for (k = 0; k < n1d; ++k) s->l1d[k] = 1;
+    for (k = 0; k < Nz; ++k) n1d += l1d[k];
+    for (k = 0; k < n1d; ++k) l1d[k] = 1;
   }
-  for (k = 0; k < Nz; ++k) count3d += !s->l1d[k];
+  for (k = 0; k < Nz; ++k) count3d += !l1d[k];
   s->unconstrained_fraction = (double)count3d / (double)Nz;
+  for (k = 0; k < s->Nz; ++k) s->l1d[k] = l1d[k + s->icollapse - 1]; /* atmk, src/pprts_base.F90:1088-1093 */
 }
 
 /* src/pprts.F90:3901-3987 (gen_scale_dir_flx_vec_arr / gen_scale_diff_flx_vec_arr) */
@@ -644,12 +724,22 @@ orc_solver *orc_solver_create(const orc_config *cfg, const orc_lut *lut) {
   s->cfg = *cfg;
   if (orc_streams_init(&s->st, cfg->solver_id)) { free(s); return 0; }
   s->lut = lut;
-  s->Nz = cfg->Nz; s->Nx = cfg->Nx; s->Ny = cfg->Ny; s->Nz1 = cfg->Nz + 1;
+  s->icollapse = cfg->collapseindex > 1 ? cfg->collapseindex : 1;
+  if (s->icollapse > cfg->Nz) { free(s); return 0; }
+  s->Nz_atm = cfg->Nz;
+  s->Nz = cfg->Nz - s->icollapse + 1; s->Nx = cfg->Nx; s->Ny = cfg->Ny; s->Nz1 = s->Nz + 1;
   s->dx = cfg->dx; s->dy = cfg->dy;
+  nc = (long)s->Nz_atm * s->Nx * s->Ny;
+  s->dz_atm = (double *)malloc(sizeof(double) * nc);
+  memcpy(s->dz_atm, cfg->dz, sizeof(double) * nc);
   nc = (long)s->Nz * s->Nx * s->Ny;
   s->dz = (double *)malloc(sizeof(double) * nc);
-  memcpy(s->dz, cfg->dz, sizeof(double) * nc);
+  { int k, i, j; for (j = 0; j < s->Ny; ++j) for (i = 0; i < s->Nx; ++i) for (k = 0; k < s->Nz; ++k)
+      s->dz[k + (long)s->Nz * (i + (long)s->Nx * j)] = s->dz_atm[(k + s->icollapse - 1) + (long)s->Nz_atm * (i + (long)s->Nx * j)]; }
   s->l1d = (int *)calloc(s->Nz, sizeof(int));
+  s->l1d_atm = (int *)calloc(s->Nz_atm, sizeof(int));
+  s->Btop = (double *)calloc((long)s->Nx * s->Ny, sizeof(double));
+  s->Bbot = (double *)calloc((long)s->Nx * s->Ny, sizeof(double));
   determine_1d_layers(s);
   s->kabs = (double *)calloc(nc, sizeof(double));
   s->ksca = (double *)calloc(nc, sizeof(double));
@@ -683,6 +773,7 @@ void orc_solver_destroy(orc_solver *s) {
   int u;
   if (!s) return;
   for (u = 0; u <= ORC_UID_MAX - ORC_UID_MIN; ++u) free_solution(s->sol[u]);
+  free(s->dz_atm); free(s->l1d_atm); free(s->Btop); free(s->Bbot);
   free(s->dz); free(s->l1d); free(s->kabs); free(s->ksca); free(s->g); free(s->planck); free(s->Bsrfc);
   free(s->albedo); free(s->a11); free(s->a12); free(s->a13); free(s->a23); free(s->a33);
   free(s->dir2dir); free(s->dir2diff); free(s->diff2diff); free(s->b); free(s->dir_scale); free(s->diff_scale);
@@ -690,25 +781,43 @@ void orc_solver_destroy(orc_solver *s) {
 }
 
 /* ---- set_optical_properties (src/pprts.F90:1764-2076) --------------------------------------------------------- */
-int orc_set_optical_properties(orc_solver *s, double albedo, const double *kabs, const double *ksca, const double *g,
-                               const double *planck, const double *planck_srfc, const double *albedo_2d,
-                               int ldelta_scaling) {
+int orc_set_optical_properties(orc_solver *s, double albedo, const double *kabs_in, const double *ksca_in,
+                               const double *g_in, const double *planck_in, const double *planck_srfc,
+                               const double *albedo_2d, int ldelta_scaling) {
   LOCALS
-  long nc = (long)Nz * Nx * Ny, n;
+  const int Nza = s->Nz_atm, ic = s->icollapse, off = ic - 1; /* atmk(k) = k + icollapse - 1 */
+  const long nca = (long)Nza * Nx * Ny;
+  long n;
   int k, i, j;
+  /* atmosphere-sized working copies (atm%kabs ... live on C_one_atm); the solver-grid arrays are the layers from
+   * atmk(0) on.  Inputs that are not given keep their previous values (:1805-1860) -- only for icollapse == 1 */
+  double *kabs = (double *)malloc(sizeof(double) * nca), *ksca = (double *)malloc(sizeof(double) * nca),
+         *g = (double *)malloc(sizeof(double) * nca);
+  int rc = 0;
+#define ATM(a, k, i, j) (a)[(k) + (long)Nza * ((i) + (long)Nx * (j))]
+#define PATM(a, k, i, j) (a)[(k) + (long)(Nza + 1) * ((i) + (long)Nx * (j))]
   for (n = 0; n < (long)Nx * Ny; ++n) s->albedo[n] = albedo_2d ? albedo_2d[n] : albedo;
-  if (kabs) memcpy(s->kabs, kabs, sizeof(double) * nc);
-  if (ksca) memcpy(s->ksca, ksca, sizeof(double) * nc);
-  if (g) memcpy(s->g, g, sizeof(double) * nc);
-  s->have_planck = planck != 0;
-  if (planck) memcpy(s->planck, planck, sizeof(double) * (long)Nz1 * Nx * Ny);
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nza; ++k) {
+    const int ks = k - off; /* solver layer, < 0 inside the collapsed block */
+    ATM(kabs, k, i, j) = kabs_in ? ATM(kabs_in, k, i, j) : (ks >= 0 ? A3(s->kabs, ks, i, j) : 0.0);
+    ATM(ksca, k, i, j) = ksca_in ? ATM(ksca_in, k, i, j) : (ks >= 0 ? A3(s->ksca, ks, i, j) : 0.0);
+    ATM(g, k, i, j) = g_in ? ATM(g_in, k, i, j) : (ks >= 0 ? A3(s->g, ks, i, j) : 0.0);
+  }
+  s->have_planck = planck_in != 0;
+  if (planck_in)
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k)
+      P3(s->planck, k, i, j) = PATM(planck_in, k + off, i, j);
   s->have_Bsrfc = planck_srfc != 0;
   if (planck_srfc) memcpy(s->Bsrfc, planck_srfc, sizeof(double) * (long)Nx * Ny);
   if (ldelta_scaling) /* :1912-1914 */
-    for (n = 0; n < nc; ++n) orc_delta_scale(&s->kabs[n], &s->ksca[n], &s->g[n]);
-  for (n = 0; n < nc; ++n) /* :1929-1935 */
-    if (s->kabs[n] < 0 || s->ksca[n] < 0 || s->g[n] < 0 || isnan(s->kabs[n]) || isnan(s->ksca[n]) || isnan(s->g[n]))
-      return 1;
+    for (n = 0; n < nca; ++n) orc_delta_scale(&kabs[n], &ksca[n], &g[n]);
+  for (n = 0; n < nca; ++n) /* :1929-1935 */
+    if (kabs[n] < 0 || ksca[n] < 0 || g[n] < 0 || isnan(kabs[n]) || isnan(ksca[n]) || isnan(g[n])) { rc = 1; goto done; }
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
+    A3(s->kabs, k, i, j) = ATM(kabs, k + off, i, j);
+    A3(s->ksca, k, i, j) = ATM(ksca, k + off, i, j);
+    A3(s->g, k, i, j) = ATM(g, k + off, i, j);
+  }
   /* :1962-2007 Eddington coefficients in 1-D layers; a21 = a12, a22 = a11 (:2072-2073) */
   for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
     if (s->l1d[k]) {
@@ -718,8 +827,34 @@ int orc_set_optical_properties(orc_solver *s, double albedo, const double *kabs,
                              &A3(s->a23, k, i, j), &A3(s->a33, k, i, j));
     }
   }
+  if (ic > 1) { /* handle_atm_collapse :2080-2123: the top `ic` atmosphere layers become solver layer 0 */
+    double *c[7], *dtau = (double *)malloc(sizeof(double) * ic), *pl = (double *)malloc(sizeof(double) * (ic + 1));
+    int q;
+    for (q = 0; q < 7; ++q) c[q] = (double *)malloc(sizeof(double) * ic);
+    for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) {
+      for (k = 0; k < ic; ++k) {
+        double ext = dmax(DBL_MIN, ATM(kabs, k, i, j) + ATM(ksca, k, i, j));
+        orc_eddington_coeff_ec(ATM(s->dz_atm, k, i, j) * ext, ATM(ksca, k, i, j) / ext, ATM(g, k, i, j), s->costheta,
+                               &c[0][k], &c[1][k], &c[4][k], &c[5][k], &c[6][k]);
+        c[2][k] = c[1][k]; c[3][k] = c[0][k]; /* a21 = a12, a22 = a11 */
+        dtau[k] = ATM(s->dz_atm, k, i, j) * ATM(kabs, k, i, j);
+        if (planck_in) pl[k] = PATM(planck_in, k, i, j);
+      }
+      if (planck_in) pl[ic] = PATM(planck_in, ic, i, j);
+      orc_adding(ic, c[0], c[1], c[2], c[3], c[4], c[5], c[6], planck_in ? dtau : 0, planck_in ? pl : 0,
+                 &A2(s->Btop, i, j), &A2(s->Bbot, i, j));
+      A3(s->a11, 0, i, j) = c[0][ic - 1]; A3(s->a12, 0, i, j) = c[1][ic - 1];
+      A3(s->a13, 0, i, j) = c[4][ic - 1]; A3(s->a23, 0, i, j) = c[5][ic - 1]; A3(s->a33, 0, i, j) = c[6][ic - 1];
+    }
+    for (q = 0; q < 7; ++q) free(c[q]);
+    free(dtau); free(pl);
+  }
   s->have_optprop = 1;
-  return 0;
+done:
+  free(kabs); free(ksca); free(g);
+#undef ATM
+#undef PATM
+  return rc;
 }
 
 /* ---- coefficients (src/pprts.F90:3088-3494) ---------------------------------------------------------------------- */
@@ -943,10 +1078,15 @@ static void setup_b(orc_solver *s, orc_solution *sol) {
         double tauz = A3(s->kabs, k, i, j) * A3(s->dz, k, i, j), btop, bbot, bfac, emis;
         if (s->l1d[k]) {
           bfac = ORC_PI * Az / (double)(Nft / 2);
-          emis = 1.0 - A3(s->a11, k, i, j) - A3(s->a12, k, i, j);
-          emis = dmax(0.0, dmin(1.0, emis));
-          btop = orc_B_eff(b1, b0, tauz) * bfac * emis;
-          bbot = orc_B_eff(b0, b1, tauz) * bfac * emis;
+          if (s->icollapse > 1 && k == 0) { /* :4875-4877 */
+            btop = A2(s->Btop, i, j) * bfac;
+            bbot = A2(s->Bbot, i, j) * bfac;
+          } else {
+            emis = 1.0 - A3(s->a11, k, i, j) - A3(s->a12, k, i, j);
+            emis = dmax(0.0, dmin(1.0, emis));
+            btop = orc_B_eff(b1, b0, tauz) * bfac * emis;
+            bbot = orc_B_eff(b0, b1, tauz) * bfac * emis;
+          }
           for (src = 0; src < Nft; ++src) {
             if (s->st.ft_inward[src]) FG(xsrc, Nf, src, k + 1, i, j) += bbot;
             else FG(xsrc, Nf, src, k, i, j) += btop;

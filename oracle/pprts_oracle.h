@@ -59,6 +59,12 @@ void orc_eddington_coeff_ec(double dtau, double w0, double g, double mu0, double
                             double *sdir, double *tdir);                       /* src/eddington.F90:167-242 */
 double orc_B_eff(double B_far, double B_near, double tau);                     /* src/schwarzschild.F90:36-67 */
 void orc_delta_scale(double *kabs, double *ksca, double *g);                   /* helper_functions.fypp:1622-1666 */
+/* adding (src/pprts.F90:2125-2198): collapse n 1-D layers (TOA first) into the last one, in place; with dtau/planck
+ * (n / n+1 values, may be NULL) also the layer's thermal emission Btop, Bbot via schwarzschild (src/schwarzschild.F90:82-150) */
+void orc_adding(int n, double *a11, double *a12, double *a21, double *a22, double *a13, double *a23, double *a33,
+                const double *dtau, const double *planck, double *Btop, double *Bbot);
+void orc_schwarzschild2(int ke, const double *dtau, double albedo, double *Edn, double *Eup, const double *planck,
+                        const double *opt_srfc_emission);
 int orc_streams_init(orc_streams *st, int solver_id);                          /* src/pprts.F90:256-453 */
 void orc_dir2diff_symmetry(const orc_streams *st, double *c, int lswitch_east, int lswitch_north);
 void orc_dir2dir_symmetry(const orc_streams *st, double *c, int lswitch_east, int lswitch_north);
@@ -95,6 +101,9 @@ typedef struct {
   double rtol, atol;     /* <0: reference defaults (src/pprts_base.F90:1128-1131) */
   int maxit_dir, maxit_diff; /* <=0: reference defaults 1000 / 10000 */
   int nthreads;          /* OpenMP threads for the embarrassingly parallel loops (coefficients, MatMult) */
+  int collapseindex;     /* init_pprts argument (src/pprts.F90:692-706): > 1 merges the top `collapseindex` atmosphere
+                            layers into one 1-D layer; Nz above is then the ATMOSPHERE layer count, the solver grid and
+                            all results have Nz - collapseindex + 1 layers. <= 1: off */
 } orc_config;
 
 orc_solver *orc_solver_create(const orc_config *cfg, const orc_lut *lut);      /* init_pprts, src/pprts.F90:213 */

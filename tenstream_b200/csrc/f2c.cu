@@ -69,7 +69,7 @@ extern "C" void pprts_f2c_init(int fcomm, int *solver_id, int *Nz, int *Nx, int 
                                              "you must destroy the solver first");
     return;
   }
-  if (collapseindex && *collapseindex > 1) chkerr(1, "pprts_f2c_init: collapseindex > 1 is not supported by this build");
+  (void)collapseindex;  // broadcast back but never handed to init_pprts by the reference wrapper (f2c_pprts.F90:198-260)
   chkerr(open_default_lut(*solver_id), "pprts_f2c_init: loading LUT");
   pprts_b200_config cfg;
   pprts_b200_default_config(&cfg);

@@ -149,6 +149,86 @@ __global__ void k_eddington(Grid g, int n1d, double costheta, const double *__re
   a11[c] = t; a12[c] = r; a13[c] = rdir; a23[c] = sdir; a33[c] = tdir;
 }
 
+
+// handle_atm_collapse + adding (src/pprts.F90:2080-2198): the top `ic` ATMOSPHERE layers (all 1-D) of every column are
+// merged into solver layer 0.  One thread per column; Eddington coefficients of the block's layers are recomputed on
+// the fly (cheaper than a round trip through memory), the two recurrences of `adding` run top-down and bottom-up, and
+// for thermal bands the block's emission Btop / Bbot comes from schwarzschild (src/schwarzschild.F90:82-150, Nmu = 2,
+// albedo 0, no surface emission).  kabs/ksca/gg/dz/planck are the ATMOSPHERE arrays (layer 0 = TOA); a11..a33 the
+// solver's 1-D coefficient fields, of which layer 0 (the first ncol entries) is overwritten.
+__device__ __forceinline__ void schwarzschild_radiance(double tau, double B_near, double B_far, double &L) {
+  if (tau > (double)1e-3f) {  // src/schwarzschild.F90:73 compares with the default-real literal 1e-3
+    const double tm1 = expm1(-tau);
+    L = L * (tm1 + 1) + (B_far - B_near) - (B_near - (B_far - B_near) / tau) * tm1;
+  } else {
+    L = (B_near + B_far) * .5 * tau + L * (1.0 - tau);
+  }
+}
+__global__ void k_collapse(long ncol, int ic, double costheta, int have_planck, const double *__restrict__ kabs,
+                           const double *__restrict__ ksca, const double *__restrict__ gg,
+                           const double *__restrict__ dz, const double *__restrict__ planck,
+                           double *__restrict__ a11, double *__restrict__ a12, double *__restrict__ a13,
+                           double *__restrict__ a23, double *__restrict__ a33, double *__restrict__ Btop,
+                           double *__restrict__ Bbot) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  auto edd = [&](int k, double &t, double &r, double &rdir, double &sdir, double &tdir) {
+    const long c = (long)k * ncol + col;
+    const double ext = fmax(DBL_MIN, kabs[c] + ksca[c]);
+    eddington_ec(dz[c] * ext, ksca[c] / ext, gg[c], costheta, t, r, rdir, sdir, tdir);
+  };
+  double t, r, rdir, sdir, tdir;
+  edd(0, t, r, rdir, sdir, tdir);
+  double tN = t, rN = r;  // a11, a12 of the layer visited last (== layer ic-1 after the loop): a22(N), a21(N)
+  for (int k = 1; k < ic; ++k) {  // reflectivity as seen from the top
+    double tk, rk, rdk, sdk, tdk;
+    edd(k, tk, rk, rdk, sdk, tdk);
+    const double rl = r, tl = t;
+    r = r + (rk * t * t) / (1.0 - r * rk);
+    t = t * tk / (1.0 - rl * rk);
+    sdir = (tk * sdir + tdir * rdk * rl * tk) / (1.0 - rl * rk) + tdir * sdk;
+    rdir = rdir + (tdir * rdk + sdir * rk) * tl;
+    tdir = tdir * tdk;
+    tN = tk; rN = rk;
+  }
+  const double Rtop = r;
+  a13[col] = rdir; a23[col] = sdir; a33[col] = tdir;
+  t = tN; r = rN;  // a22(N) = a11(N), a21(N) = a12(N) (src/pprts.F90:2072-2073)
+  for (int k = ic - 2; k >= 0; --k) {  // reflectivity as seen from the bottom
+    double tk, rk, rdk, sdk, tdk;
+    edd(k, tk, rk, rdk, sdk, tdk);
+    const double rl = r;
+    r = rk + (r * tk * tk) / (1.0 - r * rk);
+    t = t * tk / (1.0 - rl * rk);
+  }
+  a12[col] = Rtop;  // the operator uses a11 / a12 for both directions (src/pprts.F90:5721-5729)
+  a11[col] = t;     // Tbot
+  if (have_planck) {
+    const double pt[2] = {0.21132486540518713, 0.78867513459481287}, wi[2] = {0.5, 0.5};
+    double Edn = 0.0, Eup = 0.0;
+    for (int imu = 0; imu < 2; ++imu) {
+      const double mu = pt[imu];
+      double Ldn = 0.0;
+      for (int k = 0; k < ic; ++k) {
+        const long c = (long)k * ncol + col;
+        schwarzschild_radiance(dz[c] * kabs[c] / mu, planck[c], planck[c + ncol], Ldn);
+      }
+      Edn = Edn + Ldn * mu * wi[imu];
+    }
+    for (int imu = 0; imu < 2; ++imu) {
+      const double mu = pt[imu];
+      double Lup = 0.0;  // Bsrfc = 0, albedo = 0
+      for (int k = ic - 1; k >= 0; --k) {
+        const long c = (long)k * ncol + col;
+        schwarzschild_radiance(dz[c] * kabs[c] / mu, planck[c + ncol], planck[c], Lup);
+      }
+      Eup = Eup + Lup * mu * wi[imu];
+    }
+    Bbot[col] = Edn * 2 * PB_PI / PB_PI;
+    Btop[col] = Eup * 2 * PB_PI / PB_PI;
+  }
+}
+
 // =================================================================================================================
 // HOT LOOP A: coefficient lookup (src/pprts.F90:3088-3494 -> pprts_base.F90:1491 get_coeff -> optprop.F90:550
 // get_coeff_cube -> optprop_LUT.F90:1452-1613 -> search.fypp:177 + interpolation.F90:317).
@@ -540,7 +620,8 @@ __device__ __forceinline__ double B_eff(double B_far, double B_near, double tau)
 
 template <class L>
 __global__ void __launch_bounds__(128)
-k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdiv_diff,
+k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ Btop, const double *__restrict__ Bbot,
+                 const double *__restrict__ cdiv_diff,
                  const double *__restrict__ a11, const double *__restrict__ a12, const double *__restrict__ kabs,
                  const double *__restrict__ dz, const double *__restrict__ planck, const double *__restrict__ Bsrfc,
                  const double *__restrict__ albedo, double *__restrict__ b) {
@@ -555,9 +636,15 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ cdi
   const double tauz = kabs[c] * dz[c];
   if (k < n1d) {
     double bfac = PB_PI * Az / (double)(Nft / 2);
-    double emis = fmax(0.0, fmin(1.0, 1.0 - a11[c] - a12[c]));
-    double btop = B_eff(b1, b0, tauz) * bfac * emis;
-    double bbot = B_eff(b0, b1, tauz) * bfac * emis;
+    double btop, bbot;
+    if (Btop != nullptr && k == 0) {  // collapsed block (src/pprts.F90:4875-4877)
+      btop = Btop[c] * bfac;
+      bbot = Bbot[c] * bfac;
+    } else {
+      double emis = fmax(0.0, fmin(1.0, 1.0 - a11[c] - a12[c]));
+      btop = B_eff(b1, b0, tauz) * bfac * emis;
+      bbot = B_eff(b0, b1, tauz) * bfac * emis;
+    }
 #pragma unroll
     for (int d = 0; d < Nft; ++d) {
       if (L::top_in(d)) b[(long)d * g.nlev + l_dn] = bbot;

@@ -196,6 +196,13 @@ struct pprts_b200_solver {
   int device = 0;
   Grid g;
   int Nd = 0, Nf = 0, n1d = 0;
+  // atmosphere collapse (src/pprts_base.F90:118-122, atmk :1088-1093): the solver grid g starts at atmosphere layer
+  // icollapse-1.  The atmosphere fields are allocated with all Nz_atm layers (atm_*); dz/kabs/ksca/gg/planck below point
+  // at layer icollapse-1 of them (k is the slowest index of the device layout, so the offset is a pointer shift).
+  int Nz_atm = 0, icollapse = 1;
+  long ncell_atm = 0, nlev_atm = 0;
+  double *atm_dz = nullptr, *atm_kabs = nullptr, *atm_ksca = nullptr, *atm_gg = nullptr, *atm_planck = nullptr;
+  double *Btop = nullptr, *Bbot = nullptr;
   double unconstrained_fraction = 1.0;
   std::vector<unsigned char> l1d;
   // sun (t_suninfo, src/pprts_base.F90:128-135)
@@ -448,6 +455,7 @@ extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   cfg->nxproc = cfg->nyproc = 1;
   cfg->diff_explicit = 0;
   cfg->krylov_fp32 = 0;
+  cfg->collapseindex = 1;
 }
 
 template <class T>
@@ -553,7 +561,10 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   if (cfg->device >= 0) { CU(cudaSetDevice(cfg->device)); s->device = cfg->device; }
   else CU(cudaGetDevice(&s->device));
   Grid &g = s->g;
-  g.Nz = cfg->Nz; g.Nx = cfg->Nx; g.Ny = cfg->Ny;
+  const int ci = cfg->collapseindex > 1 ? cfg->collapseindex : 1;
+  if (ci > cfg->Nz) { delete s; return set_err(1, "collapseindex %d exceeds the %d atmosphere layers", ci, cfg->Nz); }
+  s->icollapse = ci; s->Nz_atm = cfg->Nz;
+  g.Nz = cfg->Nz - ci + 1; g.Nx = cfg->Nx; g.Ny = cfg->Ny;
   g.ncol = (long)g.Nx * g.Ny; g.ncell = g.ncol * g.Nz; g.nlev = g.ncol * (g.Nz + 1);
   g.ncp = (g.ncell + PB_TILE - 1) / PB_TILE * PB_TILE;  // whole coefficient tiles (tile-blocked layout, common.cuh)
   g.dx = cfg->dx; g.dy = cfg->dy;
@@ -565,25 +576,33 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   s->use_tma = getenv("PPRTS_B200_NO_TMA") == nullptr;
   if (const char *v = getenv("PPRTS_B200_MM_VARIANT")) s->mm_variant = atoi(v);
 
-  // dz in device layout + determine_1d_layers (src/pprts.F90:649-725)
-  std::vector<double> hdz((size_t)g.ncell);
-  s->l1d.assign(g.Nz, 0);
-  std::vector<unsigned char> thick(g.Nz, 0);
-  for (int j = 0; j < g.Ny; ++j) for (int i = 0; i < g.Nx; ++i) for (int k = 0; k < g.Nz; ++k) {
-    double v = cfg->dz1d ? cfg->dz1d[k] : cfg->dz3d[k + (size_t)g.Nz * (i + (size_t)g.Nx * j)];
+  // dz in device layout + determine_1d_layers (src/pprts.F90:649-725), both on the atmosphere grid
+  const int Nza = s->Nz_atm;
+  s->ncell_atm = g.ncol * Nza; s->nlev_atm = g.ncol * (Nza + 1);
+  std::vector<double> hdz((size_t)s->ncell_atm);
+  std::vector<unsigned char> thick(Nza, 0), l1d_atm(Nza, 0);
+  for (int j = 0; j < g.Ny; ++j) for (int i = 0; i < g.Nx; ++i) for (int k = 0; k < Nza; ++k) {
+    double v = cfg->dz1d ? cfg->dz1d[k] : cfg->dz3d[k + (size_t)Nza * (i + (size_t)g.Nx * j)];
     hdz[((size_t)k * g.Ny + j) * g.Nx + i] = v;
     if (v / cfg->dx > s->cfg.twostr_ratio) thick[k] = 1;
   }
-  s->l1d[g.Nz - 1] = thick[g.Nz - 1];
-  for (int k = g.Nz - 2; k >= 0; --k) if (thick[k]) { for (int kk = 0; kk <= k; ++kk) s->l1d[kk] = 1; break; }
-  s->n1d = 0;
-  for (int k = 0; k < g.Nz; ++k) s->n1d += s->l1d[k];
-  for (int k = 0; k < g.Nz; ++k) s->l1d[k] = k < s->n1d;  // :708-719 contiguous from the top
-  s->unconstrained_fraction = (double)(g.Nz - s->n1d) / (double)g.Nz;
+  l1d_atm[Nza - 1] = thick[Nza - 1];
+  for (int k = Nza - 2; k >= 0; --k) if (thick[k]) { for (int kk = 0; kk <= k; ++kk) l1d_atm[kk] = 1; break; }
+  for (int k = 0; k < ci && ci > 1; ++k) l1d_atm[k] = 1;  // :692-706 layers that are collapsed have to be 1-D
+  int n1d_atm = 0;
+  for (int k = 0; k < Nza; ++k) n1d_atm += l1d_atm[k];  // :708-719 contiguous from the top
+  s->unconstrained_fraction = (double)(Nza - n1d_atm) / (double)Nza;
+  s->n1d = n1d_atm - (ci - 1);
+  s->l1d.assign(g.Nz, 0);
+  for (int k = 0; k < g.Nz; ++k) s->l1d[k] = k < s->n1d;
 
   const size_t n1c = (size_t)s->n1d * g.ncol;
-  DA(s->dz, g.ncell); DA(s->kabs, g.ncell); DA(s->ksca, g.ncell); DA(s->gg, g.ncell);
-  DA(s->planck, g.nlev); DA(s->Bsrfc, g.ncol); DA(s->albedo, g.ncol); DA(s->raw, g.nlev);
+  const size_t aoff = (size_t)(ci - 1) * g.ncol;
+  DA(s->atm_dz, s->ncell_atm); DA(s->atm_kabs, s->ncell_atm); DA(s->atm_ksca, s->ncell_atm); DA(s->atm_gg, s->ncell_atm);
+  DA(s->atm_planck, s->nlev_atm); DA(s->Bsrfc, g.ncol); DA(s->albedo, g.ncol); DA(s->raw, s->nlev_atm);
+  s->dz = s->atm_dz + aoff; s->kabs = s->atm_kabs + aoff; s->ksca = s->atm_ksca + aoff; s->gg = s->atm_gg + aoff;
+  s->planck = s->atm_planck + aoff;
+  if (ci > 1) { DA(s->Btop, g.ncol); DA(s->Bbot, g.ncol); }
   DA(s->a11, n1c); DA(s->a12, n1c); DA(s->a13, n1c); DA(s->a23, n1c); DA(s->a33, n1c);
   const size_t csz = cfg->coeff_fp32 ? 4 : 8;
   CU(cudaMalloc(&s->d2d, (size_t)Nd * Nd * g.ncp * csz)); CU(cudaMemset(s->d2d, 0, (size_t)Nd * Nd * g.ncp * csz));
@@ -605,7 +624,7 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   DA(s->sc, SC_COUNT); DA(s->counter, 4); DA(s->bad, 1);
   CU(cudaMallocHost((void **)&s->h_sc, SC_COUNT * sizeof(double)));
   CU(cudaMallocHost((void **)&s->h_bad, sizeof(int)));
-  CU(cudaMemcpy(s->dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->atm_dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
 
   // LUT to the device: the four shared axes, the diffuse table; direct tables are contracted per sun angle
   long lat4 = 1;
@@ -637,7 +656,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (auto &kv : s->solutions) free_solution(kv.second);
   for (auto &kv : s->staged) { cudaFree(kv.second.kabs); cudaFree(kv.second.ksca); cudaFree(kv.second.g);
                                cudaFree(kv.second.planck); cudaFree(kv.second.Bsrfc); cudaFree(kv.second.albedo2d); }
-  double *ptrs[] = {s->dz, s->kabs, s->ksca, s->gg, s->planck, s->Bsrfc, s->albedo, s->raw, s->a11, s->a12, s->a13,
+  double *ptrs[] = {s->atm_dz, s->atm_kabs, s->atm_ksca, s->atm_gg, s->atm_planck, s->Btop, s->Bbot, s->Bsrfc, s->albedo, s->raw, s->a11, s->a12, s->a13,
                     s->a23, s->a33, s->cdiv_dir, s->cdiv_diff, s->b, s->edir_tmp, s->precR, s->precInv, s->out_stage,
                     s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
   for (double *p : ptrs) cudaFree(p);
@@ -694,18 +713,23 @@ static int set_optprop_impl(pprts_b200_solver *s, double albedo, const double *k
     CU(cudaStreamSynchronize(s->stream));
   }
   // the staging buffer `raw` is reused: serialize the three uploads on the stream (copies are stream ordered)
-  if (kabs) { if ((rc = ingest_field(s, kabs, on_device, gr.Nz, s->kabs))) return rc; }
-  if (ksca) { if ((rc = ingest_field(s, ksca, on_device, gr.Nz, s->ksca))) return rc; }
-  if (g) { if ((rc = ingest_field(s, g, on_device, gr.Nz, s->gg))) return rc; }
+  // the caller's fields live on the atmosphere grid (Nz_atm layers); the solver grid is their lower part
+  if (kabs) { if ((rc = ingest_field(s, kabs, on_device, s->Nz_atm, s->atm_kabs))) return rc; }
+  if (ksca) { if ((rc = ingest_field(s, ksca, on_device, s->Nz_atm, s->atm_ksca))) return rc; }
+  if (g) { if ((rc = ingest_field(s, g, on_device, s->Nz_atm, s->atm_gg))) return rc; }
   s->have_planck = planck != nullptr;
-  if (planck) { if ((rc = ingest_field(s, planck, on_device, gr.Nz + 1, s->planck))) return rc; }
+  if (planck) { if ((rc = ingest_field(s, planck, on_device, s->Nz_atm + 1, s->atm_planck))) return rc; }
   s->have_Bsrfc = planck_srfc != nullptr;
   if (planck_srfc) { if ((rc = ingest_2d(s, planck_srfc, on_device, s->Bsrfc))) return rc; }
   CU(cudaMemsetAsync(s->bad, 0, sizeof(int), s->stream));
-  LAUNCH(s, FAM_IO, k_delta_scale, nblk(gr.ncell, 256), 256, gr.ncell, s->kabs, s->ksca, s->gg, ldelta, s->bad);
+  LAUNCH(s, FAM_IO, k_delta_scale, nblk(s->ncell_atm, 256), 256, s->ncell_atm, s->atm_kabs, s->atm_ksca, s->atm_gg, ldelta, s->bad);
   if (s->n1d > 0)
     LAUNCH(s, FAM_IO, k_eddington, nblk((long)s->n1d * gr.ncol, 256), 256, gr, s->n1d, s->costheta, s->kabs, s->ksca,
            s->gg, s->dz, s->a11, s->a12, s->a13, s->a23, s->a33);
+  if (s->icollapse > 1)  // handle_atm_collapse (src/pprts.F90:2080-2123)
+    LAUNCH(s, FAM_IO, k_collapse, nblk(gr.ncol, 128), 128, gr.ncol, s->icollapse, s->costheta, (int)s->have_planck,
+           s->atm_kabs, s->atm_ksca, s->atm_gg, s->atm_dz, s->atm_planck, s->a11, s->a12, s->a13, s->a23, s->a33,
+           s->Btop, s->Bbot);
   CU(cudaMemcpyAsync(s->h_bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
@@ -737,9 +761,9 @@ extern "C" int pprts_b200_stage_optical_properties(pprts_b200_solver *s, int slo
     return 0;
   };
   int rc;
-  if ((rc = up(&st.kabs, kabs, gr.ncell)) || (rc = up(&st.ksca, ksca, gr.ncell)) || (rc = up(&st.g, g, gr.ncell))) return rc;
+  if ((rc = up(&st.kabs, kabs, s->ncell_atm)) || (rc = up(&st.ksca, ksca, s->ncell_atm)) || (rc = up(&st.g, g, s->ncell_atm))) return rc;
   st.have_planck = planck != nullptr;
-  if (planck && (rc = up(&st.planck, planck, gr.nlev))) return rc;
+  if (planck && (rc = up(&st.planck, planck, s->nlev_atm))) return rc;
   st.have_Bsrfc = planck_srfc != nullptr;
   if (planck_srfc && (rc = up(&st.Bsrfc, planck_srfc, gr.ncol))) return rc;
   st.have_albedo2d = albedo_2d != nullptr;
@@ -874,7 +898,7 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   }
   if (sol.lthermal_rad) {
     DISPATCH_L(s, LAUNCH(s, FAM_SOURCE, (k_source_thermal<L>), nblk(g.ncell, 128), 128, g, s->n1d, (int)s->have_Bsrfc,
-                          s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, s->planck, s->Bsrfc, s->albedo, s->b));
+                          (const double *)(s->icollapse > 1 ? s->Btop : nullptr), (const double *)s->Bbot, s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, s->planck, s->Bsrfc, s->albedo, s->b));
   }
   // source emitted into a neighbour's face: stored there by its one producer (replaces halo_reduce_5pt, :4678)
   if (s->decomposed) {
@@ -1338,11 +1362,11 @@ static int stage_band_async(pprts_b200_solver *s, Staged &st, const pprts_b200_b
   };
   int rc;
   st.albedo = b->albedo;
-  if ((rc = up(&st.kabs, b->kabs + (long)ib * b->stride_kabs, gr.ncell))) return rc;
-  if ((rc = up(&st.ksca, b->ksca + (long)ib * b->stride_ksca, gr.ncell))) return rc;
-  if ((rc = up(&st.g, b->g + (long)ib * b->stride_g, gr.ncell))) return rc;
+  if ((rc = up(&st.kabs, b->kabs + (long)ib * b->stride_kabs, s->ncell_atm))) return rc;
+  if ((rc = up(&st.ksca, b->ksca + (long)ib * b->stride_ksca, s->ncell_atm))) return rc;
+  if ((rc = up(&st.g, b->g + (long)ib * b->stride_g, s->ncell_atm))) return rc;
   st.have_planck = b->planck != nullptr;
-  if (b->planck && (rc = up(&st.planck, b->planck + (long)ib * b->stride_planck, gr.nlev))) return rc;
+  if (b->planck && (rc = up(&st.planck, b->planck + (long)ib * b->stride_planck, s->nlev_atm))) return rc;
   st.have_Bsrfc = b->planck_srfc != nullptr;
   if (b->planck_srfc && (rc = up(&st.Bsrfc, b->planck_srfc + (long)ib * b->stride_planck_srfc, gr.ncol))) return rc;
   st.have_albedo2d = b->albedo_2d != nullptr;

@@ -43,7 +43,7 @@ class _Config(C.Structure):
                 ("by_coeff_divergence", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
-                ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int)]
+                ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int)]
 
 
 class _Bands(C.Structure):
@@ -167,10 +167,11 @@ class Lut:
 class Solver:
     """``class(t_solver)`` of the reference (src/pprts_base.F90:223-268); state lives on the GPU."""
 
-    def __init__(self, handle, lut, Nz, Nx, Ny, Nd, Nf):
+    def __init__(self, handle, lut, Nz, Nx, Ny, Nd, Nf, Nz_atm=None):
         self._h = handle
         self.lut = lut
-        self.Nz, self.Nx, self.Ny, self.Nd, self.Nf = Nz, Nx, Ny, Nd, Nf
+        self.Nz, self.Nx, self.Ny, self.Nd, self.Nf = Nz, Nx, Ny, Nd, Nf   # solver grid == shape of every result
+        self.Nz_atm = Nz if Nz_atm is None else Nz_atm                     # atmosphere grid == shape of the inputs
         self._pinned = []
 
     # -- introspection used by the parity tests -----------------------------------------------------------------
@@ -289,8 +290,6 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     columns every process owns along x / y, ``Nx, Ny`` are then this process's LOCAL sizes, and the process grid is
     x-fastest (``rank = xi + yi*len(nxproc)``).  ``rank`` is this process's rank in the communicator (default: the
     ``RANK`` environment variable); ``Solver.comm_init`` must be called before the first solve."""
-    if collapseindex is not None and collapseindex > 1:
-        raise PprtsError("collapseindex > 1 (atmosphere collapse, src/pprts.F90:2080-2198) is not supported")
     if (dz1d is None) == (dz3d is None):
         raise PprtsError("have to give either dz1d or dz3d in routine call....")
     cfg = _Config()
@@ -319,6 +318,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.precond, cfg.device, cfg.keep_solutions = int(precond), int(device), int(keep_solutions)
     cfg.diff_explicit = int(diff_explicit)
     cfg.krylov_fp32 = int(krylov_fp32)
+    cfg.collapseindex = int(collapseindex) if collapseindex is not None else 1
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
     if cfg.nxproc * cfg.nyproc > 1:
@@ -333,7 +333,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     h = C.c_void_p()
     _chk(lib().pprts_b200_create(C.byref(cfg), lut._h, C.byref(h)), "init_pprts")
     Nd, Nf = _lut.solver_dofs(int(solver))
-    return Solver(h, lut, Nz, Nx, Ny, Nd, Nf)
+    return Solver(h, lut, Nz - cfg.collapseindex + 1, Nx, Ny, Nd, Nf, Nz_atm=Nz)
 
 
 def set_angles(solver: Solver, sundir):
@@ -346,8 +346,8 @@ def set_optical_properties(solver: Solver, albedo, kabs=None, ksca=None, g=None,
                            albedo_2d=None, ldelta_scaling=True):
     """``set_optical_properties`` (src/pprts.F90:1764-2076): local arrays (Nz,Nx,Ny), planck (Nz+1,Nx,Ny)."""
     s = solver
-    for name, a, shp in (("kabs", kabs, (s.Nz, s.Nx, s.Ny)), ("ksca", ksca, (s.Nz, s.Nx, s.Ny)),
-                         ("g", g, (s.Nz, s.Nx, s.Ny)), ("planck", planck, (s.Nz + 1, s.Nx, s.Ny)),
+    for name, a, shp in (("kabs", kabs, (s.Nz_atm, s.Nx, s.Ny)), ("ksca", ksca, (s.Nz_atm, s.Nx, s.Ny)),
+                         ("g", g, (s.Nz_atm, s.Nx, s.Ny)), ("planck", planck, (s.Nz_atm + 1, s.Nx, s.Ny)),
                          ("planck_srfc", planck_srfc, (s.Nx, s.Ny)), ("albedo_2d", albedo_2d, (s.Nx, s.Ny))):
         if a is not None and tuple(np.shape(a)) != shp:
             raise PprtsError(f"set_optical_properties: {name} has shape {np.shape(a)}, expected {shp}")
@@ -383,7 +383,7 @@ def solve_bands(solver: Solver, lsolar, albedo, kabs, ksca, g, planck=None, plan
     reference's 1.. for solar, 501.. for thermal).  Returns (edn, eup, abso, edir, niter) -- the weighted sums; with
     ``download=False`` they stay in the device accumulator (``allreduce_accumulated`` / ``get_accumulated``)."""
     s = solver
-    c3, l3, c2 = (s.Nz, s.Nx, s.Ny), (s.Nz + 1, s.Nx, s.Ny), (s.Nx, s.Ny)
+    c3, l3, c2 = (s.Nz_atm, s.Nx, s.Ny), (s.Nz_atm + 1, s.Nx, s.Ny), (s.Nx, s.Ny)
     nb = None
     keep, ptr, stride = [], {}, {}
     for name, a, shp in (("kabs", kabs, c3), ("ksca", ksca, c3), ("g", g, c3), ("planck", planck, l3),

@@ -619,3 +619,33 @@ def test_gpu_vs_committed_golden(P, tmp_path, name):
     for nm, a in zip(("edn", "eup", "abso"), P.pprts_get_result(s, 3)):
         assert relerr(a, golden[f"{name}/thermal/{nm}"]) < 1e-5, nm
     P.destroy_pprts(s); lut.close()
+
+
+# ---- atmosphere collapse (src/pprts.F90:692-706, :2080-2198) -------------------------------------
+@pytest.mark.parametrize("solar", [True, False])
+@pytest.mark.parametrize("ci", [2, 5])
+def test_atmosphere_collapse_vs_oracle(P, gpu_lut, oracle_lut, solar, ci):
+    """collapseindex: the GPU's k_collapse (Eddington + adding + schwarzschild per column) against the oracle's
+    restatement of handle_atm_collapse; inputs on the atmosphere grid, results on the collapsed solver grid."""
+    from oracle import binding as ob
+    rng = np.random.default_rng(31)
+    Nz, Nx, Ny = 11, 6, 5
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    dz = np.full(Nz, 70.)
+    dz[:ci] = rng.uniform(250., 700., ci)
+    sd = P.sundir_from_angles(70., 55.)
+    tol = dict(rtol=1e-10, atol=1e-30)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, coeff_fp32=False, collapseindex=ci, **tol)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, coeff_fp32=False, diff_solver=1, collapseindex=ci, **tol)
+    assert s.Nz == Nz - ci + 1 == o.Nz
+    planck = None if solar else (np.linspace(60., 120., Nz + 1)[:, None, None] * rng.uniform(0.9, 1.1, (1, Nx, Ny)))
+    kw = {} if solar else dict(planck=planck, planck_srfc=np.full((Nx, Ny), 125.))
+    P.set_optical_properties(s, 0.25, kabs * (1 if solar else 5), ksca, g, **kw)
+    o.set_optical_properties(0.25, kabs * (1 if solar else 5), ksca, g, **kw)
+    P.solve_pprts(s, not solar, solar, 1000. if solar else 0.)
+    assert o.solve(not solar, solar, 1000. if solar else 0.) == 0
+    got, want = P.pprts_get_result(s), o.get_result()
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), got, want):
+        assert a.shape == b.shape
+        assert relerr(a, b) < 1e-7, (name, s.info(), o.info())
+    P.destroy_pprts(s); o.destroy()

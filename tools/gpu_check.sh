@@ -8,6 +8,6 @@ cat gpurun_out/bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/prof_step.log 2>&1
 PROF_MAXIT=3 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:'k_matmult_tma|k_prec_down|k_prec_up|k_bicg_update' -c 12 -f -o gpurun_out/prof_hot \
+    -k regex:'k_matmult_tma|k_prec_down|k_prec_up|k_bicg' -c 16 -f -o gpurun_out/prof_hot \
     python tools/profile_step.py > gpurun_out/prof_full.log 2>&1
 tail -3 gpurun_out/prof_full.log

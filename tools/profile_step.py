@@ -15,11 +15,12 @@ from tenstream_b200 import pprts as P  # noqa: E402
 
 nx = int(os.environ.get("PROF_NX", 256)); ny = int(os.environ.get("PROF_NY", 256)); nz = int(os.environ.get("PROF_NZ", 80))
 maxit = int(os.environ.get("PROF_MAXIT", 0))
+mixed = os.environ.get("PROF_KRYLOV", "mixed") == "mixed"
 cfg, paths = bench.ensure_lut(0)
 sc, bands = bench.make_workload(nx, ny, nz)
 lut = P.Lut(cfg, paths)
 s = P.init_pprts(0, nz, nx, ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]), dz1d=sc["dz1d"],
-                 lut=lut, keep_solutions=False, coeff_fp32=True, maxit_diff=maxit)
+                 lut=lut, keep_solutions=False, coeff_fp32=True, maxit_diff=maxit, krylov_fp32=mixed)
 for slot, b in enumerate(bands):
     s.stage_optical_properties(slot, b["albedo"], b["kabs"], b["ksca"], b["g"], b["planck"], b["planck_srfc"])
 

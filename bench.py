@@ -150,8 +150,8 @@ def run_ours(args):
         Nx, Ny = dec.xm, dec.ym
         s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]),
                          dz1d=sc["dz1d"], lut=lut, device=local, keep_solutions=False, coeff_fp32=True,
-                         nxproc=dec.nxproc, nyproc=dec.nyproc, rank=rank)
-        mixed = False   # a decomposed run keeps fp64 Krylov vectors (the halo exchange is fp64)
+                         nxproc=dec.nxproc, nyproc=dec.nyproc, rank=rank, krylov_fp32=(args.krylov == "mixed"))
+        mixed = args.krylov == "mixed"   # fp32 Krylov vectors travel as fp32 halos
     else:
         mixed = args.krylov == "mixed"
         s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]),
@@ -256,6 +256,15 @@ def run_ours(args):
     avg_ms = mm["ms"] / max(1, mm["launches"])
     peak, peak_src = measured_peak_gbs()
     achieved = bytes_mv / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    # DRAM traffic per launch of that kernel from the committed ncu --set full capture (only for the workload it was taken on)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if (args.nx, args.ny, Nz) == (256, 256, 80) and not decomp:
+            t = tj["k_matmult_tma_float" if mixed else "k_matmult_tma_double"]
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        traffic = None
     total_kernel_ms = sum(v["ms"] for v in stats.values())
 
     units = ncell * len(bands) * (1 if decomp else world)
@@ -282,7 +291,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_matmult<L310,float> (diffuse stencil MatMult)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
                      "bytes_per_launch": bytes_mv, "avg_launch_ms": avg_ms, "launches_per_step": mm["launches"],
                      "share_of_kernel_time": mm["ms"] / total_kernel_ms if total_kernel_ms else None},
         "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in stats.items()},

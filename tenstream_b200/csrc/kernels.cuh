@@ -1378,7 +1378,8 @@ __global__ void k_norm1(long n, const double *__restrict__ b, double *partials, 
 // 1622-1731).  dir = 0: x faces (plane i = 0, buffer [d][k][j]), dir = 1: y faces (plane j = 0, buffer [d][k][i]).
 // =================================================================================================================
 // buf[d][k][t] = v(d0 + d, k, low face) : what the west / south neighbour needs in its ghost block
-__global__ void k_halo_pack(Grid g, int dir, int d0, int nd, const double *__restrict__ v, double *__restrict__ buf) {
+template <class VT>
+__global__ void k_halo_pack(Grid g, int dir, int d0, int nd, const VT *__restrict__ v, VT *__restrict__ buf) {
   const int len = dir == 0 ? g.Ny : g.Nx;
   const long n = (long)nd * (g.Nz + 1) * len;
   long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1390,9 +1391,9 @@ __global__ void k_halo_pack(Grid g, int dir, int d0, int nd, const double *__res
 // v(d0 + d, k, low face) = buf[d][k][t] for the dofs in `mask` and the levels [k0, k1): rows of this rank that were
 // produced by the west / south neighbour (every row has exactly one producer, so this is a store, not an add).
 // NDOT > 0 adds the dot products of the stored rows to dots_out[0..NDOT) (the producer could not: it has no w0 there).
-template <int NDOT>
+template <int NDOT, class VT>
 __global__ void k_halo_unpack(Grid g, int dir, int d0, int nd, unsigned int mask, int k0, int k1,
-                              const double *__restrict__ buf, double *__restrict__ v, const double *__restrict__ w0,
+                              const VT *__restrict__ buf, VT *__restrict__ v, const VT *__restrict__ w0,
                               double *partials, unsigned int *counter, double *tmp, double *dots_out) {
   constexpr int NV = NDOT > 0 ? NDOT : 1;
   const int len = dir == 0 ? g.Ny : g.Nx;
@@ -1405,9 +1406,10 @@ __global__ void k_halo_unpack(Grid g, int dir, int d0, int nd, unsigned int mask
     const int t = (int)(q % len), k = (int)((q / len) % (g.Nz + 1)), d = (int)(q / ((long)len * (g.Nz + 1)));
     if (((mask >> d) & 1u) && k >= k0 && k < k1) {
       const long l = (long)(d0 + d) * g.nlev + (dir == 0 ? lidx(g, k, t, 0) : lidx(g, k, 0, t));
-      const double val = buf[q];
-      v[l] = val;
-      if (NDOT >= 1) dots[0] += val * w0[l];
+      const VT raw = buf[q];
+      v[l] = raw;
+      const double val = widen_any(raw);
+      if (NDOT >= 1) dots[0] += val * widen_any(w0[l]);
       if (NDOT >= 2) dots[1] += val * val;
     }
   }

@@ -279,7 +279,8 @@ static struct {
   fn_ncclSend Send; fn_ncclRecv Recv; fn_ncclGroup GroupStart, GroupEnd;
   fn_ncclCommDestroy CommDestroy; fn_ncclGetErrorString GetErrorString;
 } g_nccl;
-static const int NCCL_F64 = 8, NCCL_SUM = 0;  // ncclFloat64, ncclSum
+static const int NCCL_F64 = 8, NCCL_F32 = 7, NCCL_SUM = 0;  // ncclFloat64, ncclFloat32, ncclSum
+template <class VT> static constexpr int nccl_type() { return std::is_same<VT, float>::value ? NCCL_F32 : NCCL_F64; }
 static int load_nccl() {
   if (g_nccl.h) return 0;
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
@@ -371,21 +372,24 @@ static int allreduce_scalars(pprts_b200_solver *s, double *sc, int n) {
 }
 // Ghost FILL: my low faces (i = 0 / j = 0) -> the ghost block of the west / south neighbour; my ghost block <- the
 // low faces of the east / north neighbour.  fill_x / fill_y select the directions (the direct beam needs only one).
-static int halo_fill(pprts_b200_solver *s, double *v, int nd_total, HaloDofs h, bool fill_x, bool fill_y) {
+template <class VT>
+static int halo_fill(pprts_b200_solver *s, VT *v, int nd_total, HaloDofs h, bool fill_x, bool fill_y) {
+  constexpr int NT = nccl_type<VT>();
+  VT *hs0 = (VT *)s->hs[0], *hs1 = (VT *)s->hs[1];
   const Grid &g = s->g;
   fill_x = fill_x && g.gx; fill_y = fill_y && g.gy;
   if (!fill_x && !fill_y) return 0;
   const size_t nx = (size_t)h.ndx * (g.Nz + 1) * g.Ny, ny = (size_t)h.ndy * (g.Nz + 1) * g.Nx;
-  if (fill_x) LAUNCH(s, FAM_HALO, k_halo_pack, nblk((long)nx, 256), 256, g, 0, h.d0x, h.ndx, v, s->hs[0]);
-  if (fill_y) LAUNCH(s, FAM_HALO, k_halo_pack, nblk((long)ny, 256), 256, g, 1, h.d0y, h.ndy, v, s->hs[1]);
+  if (fill_x) LAUNCH(s, FAM_HALO, k_halo_pack<VT>, nblk((long)nx, 256), 256, g, 0, h.d0x, h.ndx, (const VT *)v, hs0);
+  if (fill_y) LAUNCH(s, FAM_HALO, k_halo_pack<VT>, nblk((long)ny, 256), 256, g, 1, h.d0y, h.ndy, (const VT *)v, hs1);
   NC(g_nccl.GroupStart());
   if (fill_x) {
-    NC(g_nccl.Send(s->hs[0], nx, NCCL_F64, s->nb_west, s->nccl_comm, s->stream));
-    NC(g_nccl.Recv(v + ghost_x_base(g, nd_total) + (size_t)h.d0x * (g.Nz + 1) * g.Ny, nx, NCCL_F64, s->nb_east, s->nccl_comm, s->stream));
+    NC(g_nccl.Send(hs0, nx, NT, s->nb_west, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(v + ghost_x_base(g, nd_total) + (size_t)h.d0x * (g.Nz + 1) * g.Ny, nx, NT, s->nb_east, s->nccl_comm, s->stream));
   }
   if (fill_y) {
-    NC(g_nccl.Send(s->hs[1], ny, NCCL_F64, s->nb_south, s->nccl_comm, s->stream));
-    NC(g_nccl.Recv(v + ghost_y_base(g, nd_total) + (size_t)h.d0y * (g.Nz + 1) * g.Nx, ny, NCCL_F64, s->nb_north, s->nccl_comm, s->stream));
+    NC(g_nccl.Send(hs1, ny, NT, s->nb_south, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(v + ghost_y_base(g, nd_total) + (size_t)h.d0y * (g.Nz + 1) * g.Nx, ny, NT, s->nb_north, s->nccl_comm, s->stream));
   }
   NC(g_nccl.GroupEnd());
   s->halo_exchanges++;
@@ -393,20 +397,23 @@ static int halo_fill(pprts_b200_solver *s, double *v, int nd_total, HaloDofs h, 
 }
 // Ghost PUSH: rows this rank produced on its high faces (its ghost block) -> the east / north neighbour, which stores
 // them on its low faces (dofs in maskx / masky, levels [n1d, Nz)); ndot > 0 adds the rows' dot products to `dots`.
-static int halo_push(pprts_b200_solver *s, double *v, int nd_total, HaloDofs h, bool push_x, bool push_y,
-                     unsigned int maskx, unsigned int masky, int ndot, const double *w0, double *dots) {
+template <class VT>
+static int halo_push(pprts_b200_solver *s, VT *v, int nd_total, HaloDofs h, bool push_x, bool push_y,
+                     unsigned int maskx, unsigned int masky, int ndot, const VT *w0, double *dots) {
+  constexpr int NT = nccl_type<VT>();
+  VT *hr[2] = {(VT *)s->hr[0], (VT *)s->hr[1]};
   const Grid &g = s->g;
   push_x = push_x && g.gx; push_y = push_y && g.gy;
   if (!push_x && !push_y) return 0;
   const size_t nx = (size_t)h.ndx * (g.Nz + 1) * g.Ny, ny = (size_t)h.ndy * (g.Nz + 1) * g.Nx;
   NC(g_nccl.GroupStart());
   if (push_x) {
-    NC(g_nccl.Send(v + ghost_x_base(g, nd_total) + (size_t)h.d0x * (g.Nz + 1) * g.Ny, nx, NCCL_F64, s->nb_east, s->nccl_comm, s->stream));
-    NC(g_nccl.Recv(s->hr[0], nx, NCCL_F64, s->nb_west, s->nccl_comm, s->stream));
+    NC(g_nccl.Send(v + ghost_x_base(g, nd_total) + (size_t)h.d0x * (g.Nz + 1) * g.Ny, nx, NT, s->nb_east, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(hr[0], nx, NT, s->nb_west, s->nccl_comm, s->stream));
   }
   if (push_y) {
-    NC(g_nccl.Send(v + ghost_y_base(g, nd_total) + (size_t)h.d0y * (g.Nz + 1) * g.Nx, ny, NCCL_F64, s->nb_north, s->nccl_comm, s->stream));
-    NC(g_nccl.Recv(s->hr[1], ny, NCCL_F64, s->nb_south, s->nccl_comm, s->stream));
+    NC(g_nccl.Send(v + ghost_y_base(g, nd_total) + (size_t)h.d0y * (g.Nz + 1) * g.Nx, ny, NT, s->nb_north, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(hr[1], ny, NT, s->nb_south, s->nccl_comm, s->stream));
   }
   NC(g_nccl.GroupEnd());
   s->halo_exchanges++;
@@ -417,11 +424,11 @@ static int halo_push(pprts_b200_solver *s, double *v, int nd_total, HaloDofs h, 
     const unsigned int mask = dir == 0 ? maskx : masky;
     double *tmp = s->sc + SC_TMP;
     if (ndot == 0)
-      LAUNCH(s, FAM_HALO, k_halo_unpack<0>, nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, s->hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+      LAUNCH(s, FAM_HALO, (k_halo_unpack<0, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
     else if (ndot == 1)
-      LAUNCH(s, FAM_HALO, k_halo_unpack<1>, nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, s->hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+      LAUNCH(s, FAM_HALO, (k_halo_unpack<1, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
     else
-      LAUNCH(s, FAM_HALO, k_halo_unpack<2>, nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, s->hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+      LAUNCH(s, FAM_HALO, (k_halo_unpack<2, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
   }
   return 0;
 }
@@ -833,7 +840,7 @@ static int edir_exchange(pprts_b200_solver *s, double *v) {
   const HaloDofs h = dir_halo(s);
   int rc = halo_fill(s, v, s->Nd, h, s->xinc == 0, s->yinc == 0);
   if (rc) return rc;
-  return halo_push(s, v, s->Nd, h, s->xinc != 0, s->yinc != 0, ~0u, ~0u, 0, nullptr, nullptr);
+  return halo_push<double>(s, v, s->Nd, h, s->xinc != 0, s->yinc != 0, ~0u, ~0u, 0, nullptr, nullptr);
 }
 
 static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
@@ -903,7 +910,7 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   // source emitted into a neighbour's face: stored there by its one producer (replaces halo_reduce_5pt, :4678)
   if (s->decomposed) {
     const unsigned int m = diff_inward_mask(s);
-    int rc = halo_push(s, s->b, s->Nf, diff_halo(s), true, true, m, m, 0, nullptr, nullptr);
+    int rc = halo_push<double>(s, s->b, s->Nf, diff_halo(s), true, true, m, m, 0, nullptr, nullptr);
     if (rc) return rc;
   }
   return 0;
@@ -957,15 +964,15 @@ static void launch_matmult_local(pprts_b200_solver *s, const VT *x, VT *y, const
 
 // y = (I - T) x on the decomposed domain: ghost fill of x, local kernel, rows produced for the neighbour pushed to
 // their owner (which also adds their share of the fused dot products), dot products summed over the ranks
-template <int NDOT>
-static int launch_matmult(pprts_b200_solver *s, double *x, double *y, const double *w, double *dots) {
-  if (!s->decomposed) { launch_matmult_local<NDOT>(s, x, y, w, dots); return 0; }
+template <int NDOT, class VT = double>
+static int launch_matmult(pprts_b200_solver *s, VT *x, VT *y, const VT *w, double *dots) {
+  if (!s->decomposed) { launch_matmult_local<NDOT, VT>(s, x, y, w, dots); return 0; }
   const HaloDofs h = diff_halo(s);
-  int rc = halo_fill(s, x, s->Nf, h, true, true);
+  int rc = halo_fill<VT>(s, x, s->Nf, h, true, true);
   if (rc) return rc;
-  launch_matmult_local<NDOT>(s, x, y, w, dots);
+  launch_matmult_local<NDOT, VT>(s, x, y, w, dots);
   const unsigned int m = diff_inward_mask(s);
-  if ((rc = halo_push(s, y, s->Nf, h, true, true, m, m, NDOT, w, dots))) return rc;
+  if ((rc = halo_push<VT>(s, y, s->Nf, h, true, true, m, m, NDOT, w, dots))) return rc;
   if (NDOT > 0) rc = allreduce_scalars(s, dots, NDOT);
   return rc;
 }
@@ -1031,7 +1038,7 @@ static int solve_ediff_explicit(pprts_b200_solver *s, Solution &sol) {
   bool converged = false;
   sol.niter_diff = 0;
   for (int it = 1; it <= maxit && !converged; ++it) {
-    if ((rc = launch_matmult<0>(s, x, r, nullptr, nullptr))) return rc;
+    if ((rc = launch_matmult<0, double>(s, x, r, nullptr, nullptr))) return rc;
     LAUNCH(s, FAM_VEC, k_relax_residual, vec_grid(n), VEC_BLOCK, n, s->b, r);
     if (prec) launch_prec(s, r, z);
     LAUNCH(s, FAM_VEC, k_relax_update, vec_grid(n), VEC_BLOCK, n, 1.0, prec ? z : r, x, s->partials, s->counter, s->sc + SC_TMP);
@@ -1067,7 +1074,7 @@ static int solve_ediff_explicit(pprts_b200_solver *s, Solution &sol) {
 // cycle plus two fp64 MatMults.
 static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, double atol, int maxit) {
   const Grid &g = s->g;
-  const long n = (long)s->Nf * g.nlev, n4 = (n + 3) & ~3L;
+  const long n = (long)s->Nf * g.nlev, n4 = (state_len(g, s->Nf) + 3) & ~3L;  // fp32 vectors carry their ghost blocks too
   double *x = sol.ediff, *ax = s->kr[0];
   float *r = (float *)s->kr[1], *rh = r + n4, *p = (float *)s->kr[2], *v = p + n4, *sv = (float *)s->kr[3], *t = sv + n4;
   const bool prec = precond_available(s);
@@ -1078,8 +1085,9 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   bool converged = false;
   sol.niter_diff = 0;
   for (int cycle = 0; !converged && cycle < 64; ++cycle) {
-    launch_matmult_local<0, double>(s, x, ax, nullptr, nullptr);
+    if ((rc = launch_matmult<0, double>(s, x, ax, nullptr, nullptr))) return rc;
     LAUNCH(s, FAM_VEC, k_mixed_init, vec_grid(n), VEC_BLOCK, n, s->b, ax, r, rh, s->partials, s->counter, s->sc);
+    if ((rc = allreduce_scalars(s, s->sc + SC_RR, 2))) return rc;
     if ((rc = read_scalars(s))) return rc;
     const double rc0 = std::sqrt(s->h_sc[SC_RR]);  // true residual this cycle starts from
     if (cycle == 0) r0 = std::max(DBL_MIN, rc0);
@@ -1094,11 +1102,12 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
     for (int it = 1; total < maxit && !restart && !converged; ++it) {
       LAUNCH(s, FAM_VEC, k_bicg32_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
       if (prec) launch_prec32(s, p, ph);
-      launch_matmult_local<1, float>(s, ph, v, rh, s->sc + SC_RHV);
+      if ((rc = launch_matmult<1, float>(s, ph, v, rh, s->sc + SC_RHV))) return rc;
       LAUNCH(s, FAM_VEC, k_bicg32_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
       if (prec) launch_prec32(s, sv, sh);
-      launch_matmult_local<2, float>(s, sh, t, sv, s->sc + SC_TS);
+      if ((rc = launch_matmult<2, float>(s, sh, t, sv, s->sc + SC_TS))) return rc;
       LAUNCH(s, FAM_VEC, k_bicg32_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, x, r, s->partials, s->counter, s->sc);
+      if ((rc = allreduce_scalars(s, s->sc + (((it + 1) & 1) ? SC_RR : SC_RHO0), 2))) return rc;
       if ((rc = read_scalars(s))) return rc;
       const double rn = std::sqrt(s->h_sc[SC_RR]);
       ++total;
@@ -1106,8 +1115,9 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
       sol.res_diff = rn;
       if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", total);
       if (rn <= inner && inner > floor32) {  // the recursion claims convergence: check the true residual in fp64
-        launch_matmult_local<0, double>(s, x, ax, nullptr, nullptr);
+        if ((rc = launch_matmult<0, double>(s, x, ax, nullptr, nullptr))) return rc;
         LAUNCH(s, FAM_VEC, k_residual_norm2, vec_grid(n), VEC_BLOCK, n, s->b, ax, s->partials, s->counter, s->sc + SC_TMP);
+        if ((rc = allreduce_scalars(s, s->sc + SC_TMP, 1))) return rc;
         if ((rc = read_scalars(s))) return rc;
         const double rtrue = std::sqrt(s->h_sc[SC_TMP]);
         sol.res_diff = rtrue;
@@ -1141,8 +1151,8 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
   if (s->cfg.diff_explicit) return solve_ediff_explicit(s, sol);
   int rc = need_comm(s);
   if (rc) return rc;
-  if (s->cfg.krylov_fp32 && !s->decomposed) return solve_ediff_mixed(s, sol, rtol, atol, maxit);
-  if ((rc = launch_matmult<0>(s, x, r, nullptr, nullptr))) return rc;
+  if (s->cfg.krylov_fp32) return solve_ediff_mixed(s, sol, rtol, atol, maxit);
+  if ((rc = launch_matmult<0, double>(s, x, r, nullptr, nullptr))) return rc;
   LAUNCH(s, FAM_VEC, k_bicg_init, vec_grid(n), VEC_BLOCK, n, s->b, r, rh, p, v, s->partials, s->counter, s->sc);
   if ((rc = allreduce_scalars(s, s->sc + SC_RR, 2))) return rc;
   if ((rc = read_scalars(s))) return rc;
@@ -1528,7 +1538,7 @@ extern "C" int pprts_b200_mat_mult_ediff(pprts_b200_solver *s, const double *x, 
   const long n = (long)s->Nf * g.nlev;
   CU(cudaMemcpyAsync(s->out_stage, x, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   LAUNCH(s, FAM_IO, k_state_from_host_layout, nblk(n, 256), 256, g, s->Nf, s->out_stage, s->kr[6]);
-  if ((rc = need_comm(s)) || (rc = launch_matmult<0>(s, s->kr[6], s->kr[7], nullptr, nullptr))) return rc;
+  if ((rc = need_comm(s)) || (rc = launch_matmult<0, double>(s, s->kr[6], s->kr[7], nullptr, nullptr))) return rc;
   LAUNCH(s, FAM_IO, k_state_to_host_layout, nblk(n, 256), 256, g, s->Nf, s->kr[7], s->out_stage);
   CU(cudaMemcpyAsync(y, s->out_stage, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));

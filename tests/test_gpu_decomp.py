@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, q):
+def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixed, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank))
@@ -28,7 +28,7 @@ def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, q):
         sc["dz1d"][:3] = 250.0
     sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
     dec = CartDecomposition(sc["Nx"], sc["Ny"], nxp, nyp, rank)
-    kw = dict(dz1d=sc["dz1d"], lut=lut, device=rank, rtol=1e-10, atol=1e-30, solver=solver_id)
+    kw = dict(dz1d=sc["dz1d"], lut=lut, device=rank, rtol=1e-10, atol=1e-30, solver=solver_id, krylov_fp32=mixed)
     s = P.init_pprts(0, sc["Nz"], dec.xm, dec.ym, sc["dx"], sc["dy"], sd, nxproc=dec.nxproc, nyproc=dec.nyproc,
                      rank=rank, **kw)
     uid = [P.nccl_unique_id() if rank == 0 else None]
@@ -66,7 +66,7 @@ def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, q):
     dist.destroy_process_group()
 
 
-def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False):
+def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False, mixed=False):
     import torch
     import torch.multiprocessing as mp
     world = nxp * nyp
@@ -77,7 +77,7 @@ def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixed, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -108,6 +108,14 @@ def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False):
 def test_decomposed_matches_single_gpu_3_10(small_lut, nxp, nyp, phi0):
     _, paths = small_lut
     _run(paths, nxp, nyp, 310, phi0)
+
+
+@pytest.mark.parametrize("nxp,nyp,phi0", [(2, 1, 120.0), (1, 2, 300.0)])
+def test_decomposed_mixed_precision_krylov(small_lut, nxp, nyp, phi0):
+    """fp32 Krylov vectors with fp32 halo exchange (krylov_fp32): the fp64 true residual still meets rtol 1e-10."""
+    _, paths = small_lut
+    _run(paths, nxp, nyp, 310, phi0, mixed=True)
+    _run(paths, nxp, nyp, 310, phi0, thick_top=True, mixed=True)
 
 
 def test_decomposed_with_1d_layers(small_lut):

@@ -98,6 +98,8 @@ def lib():
         L.orc_get_suninfo.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]
         L.orc_mat_mult_ediff.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_scale_flx_arr.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_int]
+        L.orc_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, c_double_p, c_double_p]
+        L.orc_get_buildings_result.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
         _lib = L
     return _lib
 
@@ -265,6 +267,28 @@ class OracleSolver:
         if rc:
             raise RuntimeError(f"orc_get_result -> {rc}")
         return edn, eup, abso, edir
+
+    def set_buildings(self, iface=None, albedo=None, planck=None):
+        """opt_buildings of solve_pprts (src/buildings.F90:40-69); iface None / empty removes them."""
+        if iface is None or len(iface) == 0:
+            lib().orc_set_buildings(self._h, 0, None, None, None)
+            self._nbld = 0
+            return
+        fi = np.ascontiguousarray(iface, dtype=np.int32)
+        al = np.ascontiguousarray(albedo, dtype=np.float64)
+        pl = np.ascontiguousarray(planck, dtype=np.float64) if planck is not None else None
+        rc = lib().orc_set_buildings(self._h, len(fi), fi.ctypes.data_as(c_int_p), _dp(al), _dp(pl))
+        if rc:
+            raise ValueError("set_buildings: face index out of range")
+        self._nbld = len(fi)
+
+    def get_buildings_result(self, uid=0):
+        n = getattr(self, "_nbld", 0)
+        edir, inc, out = np.zeros(n), np.zeros(n), np.zeros(n)
+        rc = lib().orc_get_buildings_result(self._h, uid, _dp(edir), _dp(inc), _dp(out))
+        if rc:
+            raise RuntimeError(f"orc_get_buildings_result -> {rc}")
+        return edir, inc, out
 
     def coeffs(self, which):
         n = {1: self.Nd ** 2, 2: self.Nd * self.Nf, 3: self.Nf ** 2}[which]

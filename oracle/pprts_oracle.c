@@ -523,6 +523,10 @@ struct orc_solver {
   double *dir2dir, *dir2diff, *diff2diff;
   double *b;
   double *dir_scale, *diff_scale; /* Wm2_to_W, interior layout */
+  /* opt_buildings (t_pprts_buildings, src/buildings.F90:40-69): faces of building cells */
+  int nbld, bld_have_planck;
+  int *bld_iface;
+  double *bld_albedo, *bld_planck;
   orc_solution *sol[ORC_UID_MAX - ORC_UID_MIN + 1];
 };
 
@@ -777,6 +781,7 @@ void orc_solver_destroy(orc_solver *s) {
   free(s->dz); free(s->l1d); free(s->kabs); free(s->ksca); free(s->g); free(s->planck); free(s->Bsrfc);
   free(s->albedo); free(s->a11); free(s->a12); free(s->a13); free(s->a23); free(s->a33);
   free(s->dir2dir); free(s->dir2diff); free(s->diff2diff); free(s->b); free(s->dir_scale); free(s->diff_scale);
+  free(s->bld_iface); free(s->bld_albedo); free(s->bld_planck);
   free(s);
 }
 
@@ -857,6 +862,73 @@ done:
   return rc;
 }
 
+/* ---- buildings (src/buildings.F90) ----------------------------------------------------------------------------------
+ * A building is a set of faces of grid cells: iface(m) is the 1-based flattened index into (6, Nz, Nx, Ny), first axis
+ * fastest (faceidx_by_cell_plus_offset, src/buildings.F90:215-222; ndarray_offsets helper_functions.fypp:2432-2437),
+ * face ids PPRTS_TOP_FACE = 1 (z+0), BOT = 2 (z+1), LEFT = 3 (x+0), RIGHT = 4 (x+1), REAR = 5 (y+0), FRONT = 6 (y+1)
+ * (src/boxmc_geometry.F90:45-51).  nfaces = 0 removes them (opt_buildings not present). */
+enum { ORC_TOP_FACE = 1, ORC_BOT_FACE, ORC_LEFT_FACE, ORC_RIGHT_FACE, ORC_REAR_FACE, ORC_FRONT_FACE };
+int orc_set_buildings(orc_solver *s, int nfaces, const int *iface, const double *albedo, const double *planck) {
+  int m;
+  free(s->bld_iface); free(s->bld_albedo); free(s->bld_planck);
+  s->bld_iface = 0; s->bld_albedo = s->bld_planck = 0; s->nbld = 0; s->bld_have_planck = 0;
+  if (nfaces <= 0) return 0;
+  for (m = 0; m < nfaces; ++m) if (iface[m] < 1 || (long)iface[m] > 6L * s->Nz * s->Nx * s->Ny) return 1;
+  s->nbld = nfaces;
+  s->bld_iface = (int *)malloc(sizeof(int) * nfaces); memcpy(s->bld_iface, iface, sizeof(int) * nfaces);
+  s->bld_albedo = (double *)malloc(sizeof(double) * nfaces); memcpy(s->bld_albedo, albedo, sizeof(double) * nfaces);
+  if (planck) {
+    s->bld_planck = (double *)malloc(sizeof(double) * nfaces); memcpy(s->bld_planck, planck, sizeof(double) * nfaces);
+    s->bld_have_planck = 1;
+  }
+  return 0;
+}
+/* ind_1d_to_nd (helper_functions.fypp:2439-2454) followed by idx(2:4) - 1: face id (1-based), cell (k,i,j) 0-based */
+static void bld_idx(const orc_solver *s, int m, int *face, int *k, int *i, int *j) {
+  long r = (long)s->bld_iface[m] - 1;
+  *face = (int)(r % 6) + 1; r /= 6;
+  *k = (int)(r % s->Nz); r /= s->Nz;
+  *i = (int)(r % s->Nx); r /= s->Nx;
+  *j = (int)r;
+}
+/* alloc_coeff_dir2dir::set_buildings_coeff (src/pprts.F90:3194-3212): a building cell passes no direct radiation */
+static void set_buildings_coeff_dir2dir(orc_solver *s) {
+  LOCALS
+  int m, face, k, i, j, n;
+  for (m = 0; m < s->nbld; ++m) {
+    bld_idx(s, m, &face, &k, &i, &j);
+    for (n = 0; n < Nd * Nd; ++n) CF(s->dir2dir, Nd * Nd, n, k, i, j) = 0.0;
+  }
+}
+/* alloc_coeff_diff2diff::set_buildings_coeff (src/pprts.F90:3579-3677): every stream leaving the cell through a
+ * building face receives nothing but the Lambertian reflection albedo/streams of the streams entering through that
+ * face.  v(src,dst) = c[dst*Nf + src]. */
+static void set_buildings_coeff_diff2diff(orc_solver *s) {
+  LOCALS
+  int m, face, k, i, j, isrc, idst, src;
+  for (m = 0; m < s->nbld; ++m) {
+    double *c;
+    bld_idx(s, m, &face, &k, &i, &j);
+    c = &CF(s->diff2diff, Nf * Nf, 0, k, i, j);
+    if (face == ORC_TOP_FACE || face == ORC_BOT_FACE) {
+      const int out_is_inward = face == ORC_BOT_FACE; /* top: eup leaves, bottom: edn leaves */
+      for (idst = 0; idst < Nft; ++idst) if (s->st.ft_inward[idst] == out_is_inward) {
+        for (src = 0; src < Nf; ++src) c[idst * Nf + src] = 0.0;
+        for (isrc = 0; isrc < Nft; ++isrc) if (s->st.ft_inward[isrc] != out_is_inward)
+          c[idst * Nf + isrc] = s->bld_albedo[m] / (double)(Nft / 2);
+      }
+    } else {
+      const int off = (face == ORC_LEFT_FACE || face == ORC_RIGHT_FACE) ? Nft : Nft + Nfs;
+      const int out_is_inward = face == ORC_RIGHT_FACE || face == ORC_FRONT_FACE;
+      for (idst = 0; idst < Nfs; ++idst) if (s->st.fs_inward[idst] == out_is_inward) {
+        for (src = 0; src < Nf; ++src) c[(off + idst) * Nf + src] = 0.0;
+        for (isrc = 0; isrc < Nfs; ++isrc) if (s->st.fs_inward[isrc] != out_is_inward)
+          c[(off + idst) * Nf + off + isrc] = s->bld_albedo[m] / (double)(Nfs / 2);
+      }
+    }
+  }
+}
+
 /* ---- coefficients (src/pprts.F90:3088-3494) ---------------------------------------------------------------------- */
 static void store_coeff(const orc_solver *s, const double *v, double *dst, int n) {
   int c;
@@ -882,6 +954,10 @@ static void alloc_coeffs(orc_solver *s, int lsolar) {
       orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 3, 0, 0, 0, 0, v);
       store_coeff(s, v, &CF(s->diff2diff, Nf * Nf, 0, k, i, j), Nf * Nf);
     }
+  }
+  if (s->nbld) { /* :3188-3190, :3492-3494 */
+    if (lsolar) set_buildings_coeff_dir2dir(s);
+    set_buildings_coeff_diff2diff(s);
   }
 }
 
@@ -1020,10 +1096,11 @@ static void setup_b(orc_solver *s, orc_solution *sol) {
   LOCALS
   const double eps = DBL_EPSILON;
   double *xsrc = (double *)calloc(ngh(s, Nf), sizeof(double));
+  double *xedir = 0;
   int k, i, j, src, dst, idof, idofdst, idiff, iside;
   if (sol->lsolar_rad) { /* set_solar_source :4684-4846 */
-    double *xedir = (double *)calloc(ngh(s, Nd), sizeof(double));
     const int xinc = s->xinc, yinc = s->yinc;
+    xedir = (double *)calloc(ngh(s, Nd), sizeof(double));
     interior_to_ghosted(s, Nd, sol->edir, xedir);
     halo_fill_5pt(s, Nd, xedir);
     for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz; ++k) {
@@ -1068,7 +1145,6 @@ static void setup_b(orc_solver *s, orc_solution *sol) {
     for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (dst = 0; dst < Nft; ++dst) if (!s->st.ft_inward[dst])
       for (src = 0; src < Ndt; ++src)
         FG(xsrc, Nf, dst, Nz, i, j) += FG(xedir, Nd, src, Nz, i, j) * A2(s->albedo, i, j) / (double)(Nft / 2);
-    free(xedir);
   }
   if (sol->lthermal_rad) { /* set_thermal_source :4848-4987 */
     const double Az = s->dx * s->dy; /* difftop%area_divider = 1 */
@@ -1133,6 +1209,61 @@ static void setup_b(orc_solver *s, orc_solution *sol) {
       }
     }
   }
+  if (s->nbld) { /* :4669-4672 */
+    int m, face;
+    if (sol->lsolar_rad) { /* set_buildings_reflection :4989-5080: the direct beam hitting a building face leaves as
+                              albedo/streams in every diffuse stream leaving through that face */
+      for (m = 0; m < s->nbld; ++m) {
+        const double ag = s->bld_albedo[m];
+        int kk, ii, jj, off, out_is_inward, s0, ns;
+        bld_idx(s, m, &face, &k, &i, &j);
+        kk = k; ii = i; jj = j;
+        if (face == ORC_BOT_FACE) kk = k + 1;
+        if (face == ORC_RIGHT_FACE) ii = i + 1;
+        if (face == ORC_FRONT_FACE) jj = j + 1;
+        if (face == ORC_TOP_FACE || face == ORC_BOT_FACE) {
+          out_is_inward = face == ORC_BOT_FACE;
+          for (idiff = 0; idiff < Nft; ++idiff) if (s->st.ft_inward[idiff] == out_is_inward) FG(xsrc, Nf, idiff, kk, ii, jj) = 0.0;
+          for (src = 0; src < Ndt; ++src) for (idiff = 0; idiff < Nft; ++idiff) if (s->st.ft_inward[idiff] == out_is_inward)
+            FG(xsrc, Nf, idiff, kk, ii, jj) += FG(xedir, Nd, src, kk, ii, jj) * ag / (double)(Nft / 2);
+        } else {
+          const int lx = face == ORC_LEFT_FACE || face == ORC_RIGHT_FACE;
+          off = lx ? Nft : Nft + Nfs;
+          s0 = lx ? Ndt : Ndt + Nds; ns = Nds;
+          out_is_inward = face == ORC_RIGHT_FACE || face == ORC_FRONT_FACE;
+          for (idiff = 0; idiff < Nfs; ++idiff) if (s->st.fs_inward[idiff] == out_is_inward) FG(xsrc, Nf, off + idiff, kk, ii, jj) = 0.0;
+          for (src = s0; src < s0 + ns; ++src) for (idiff = 0; idiff < Nfs; ++idiff) if (s->st.fs_inward[idiff] == out_is_inward)
+            FG(xsrc, Nf, off + idiff, kk, ii, jj) += FG(xedir, Nd, src, kk, ii, jj) * ag / (double)(Nfs / 2);
+        }
+      }
+    }
+    if (sol->lthermal_rad && s->bld_have_planck) { /* set_buildings_emission :5082-5145 */
+      const double Az = s->dx * s->dy;
+      for (m = 0; m < s->nbld; ++m) {
+        double emis, Ax, Ay;
+        int kk, ii, jj, off, out_is_inward;
+        bld_idx(s, m, &face, &k, &i, &j);
+        Ax = s->dy * A3(s->dz, k, i, j); Ay = s->dx * A3(s->dz, k, i, j); /* diffside%area_divider = 1 */
+        emis = ORC_PI * s->bld_planck[m] * (1.0 - s->bld_albedo[m]);
+        kk = k; ii = i; jj = j;
+        if (face == ORC_BOT_FACE) kk = k + 1;
+        if (face == ORC_RIGHT_FACE) ii = i + 1;
+        if (face == ORC_FRONT_FACE) jj = j + 1;
+        if (face == ORC_TOP_FACE || face == ORC_BOT_FACE) {
+          out_is_inward = face == ORC_BOT_FACE;
+          for (idiff = 0; idiff < Nft; ++idiff) if (s->st.ft_inward[idiff] == out_is_inward)
+            FG(xsrc, Nf, idiff, kk, ii, jj) = Az * emis / (double)(Nft / 2);
+        } else {
+          const int lx = face == ORC_LEFT_FACE || face == ORC_RIGHT_FACE;
+          off = lx ? Nft : Nft + Nfs;
+          out_is_inward = face == ORC_RIGHT_FACE || face == ORC_FRONT_FACE;
+          for (idiff = 0; idiff < Nfs; ++idiff) if (s->st.fs_inward[idiff] == out_is_inward)
+            FG(xsrc, Nf, off + idiff, kk, ii, jj) = (lx ? Ax : Ay) * emis / (double)(Nfs / 2);
+        }
+      }
+    }
+  }
+  free(xedir);
   halo_reduce_5pt(s, Nf, xsrc);
   ghosted_to_interior(s, Nf, xsrc, s->b);
   free(xsrc);
@@ -1570,6 +1701,64 @@ int orc_get_result(orc_solver *s, int uid, double *edn, double *eup, double *abs
     }
     for (k = 0; k < Nz; ++k) A3(abso, k, i, j) = A3(sol->abso, k, i, j) * (sol->lsolar_rad ? s->mu : 1.0);
   }
+  return 0;
+}
+
+/* pprts_get_result::fill_buildings_arr (src/pprts.F90:6011-6160): per face the direct flux hitting it (edir, NULL if
+ * not wanted / not solar), the diffuse flux entering the building through it (incoming) and leaving it (outgoing),
+ * W/m2.  The -pprts_fill_1D_side_walls branch only concerns solvers without side streams and is not restated. */
+int orc_get_buildings_result(orc_solver *s, int uid, double *edir, double *incoming, double *outgoing) {
+  LOCALS
+  orc_solution *sol;
+  double *ledir = 0, *lediff;
+  int m, face, k, i, j, d;
+  if (uid < ORC_UID_MIN || uid > ORC_UID_MAX || !(sol = s->sol[uid - ORC_UID_MIN])) return 1;
+  if (sol->lchanged || !sol->lWm2_diff) return 2;
+  if (sol->lsolar_rad && edir) {
+    ledir = (double *)calloc(ngh(s, Nd), sizeof(double));
+    interior_to_ghosted(s, Nd, sol->edir, ledir);
+    halo_fill_5pt(s, Nd, ledir);
+  }
+  lediff = (double *)calloc(ngh(s, Nf), sizeof(double));
+  interior_to_ghosted(s, Nf, sol->ediff, lediff);
+  halo_fill_5pt(s, Nf, lediff);
+  for (m = 0; m < s->nbld; ++m) {
+    const double mu = sol->lsolar_rad ? s->mu : 1.0;
+    int kk, ii, jj;
+    double in = 0, out = 0;
+    bld_idx(s, m, &face, &k, &i, &j);
+    kk = k; ii = i; jj = j;
+    if (face == ORC_BOT_FACE) kk = k + 1;
+    if (face == ORC_RIGHT_FACE) ii = i + 1;
+    if (face == ORC_FRONT_FACE) jj = j + 1;
+    if (ledir) {
+      double sum = 0;
+      if (face == ORC_TOP_FACE || face == ORC_BOT_FACE) {
+        for (d = 0; d < Ndt; ++d) sum += FG(ledir, Nd, d, kk, ii, jj) * s->mu;
+        edir[m] = sum / (double)s->st.dirtop_adiv;
+      } else {
+        const int s0 = (face == ORC_LEFT_FACE || face == ORC_RIGHT_FACE) ? Ndt : Ndt + Nds;
+        for (d = s0; d < s0 + Nds; ++d) sum += FG(ledir, Nd, d, kk, ii, jj) * s->mu;
+        edir[m] = sum / (double)s->st.dirside_adiv;
+      }
+    } else if (edir) edir[m] = 0.0;
+    if (face == ORC_TOP_FACE || face == ORC_BOT_FACE) {
+      /* top face: inward (down) streams enter the building; bottom face: the other way round */
+      for (d = 0; d < Nft; ++d) {
+        const double v = FG(lediff, Nf, d, kk, ii, jj) * mu;
+        if ((s->st.ft_inward[d] != 0) == (face == ORC_TOP_FACE)) in += v; else out += v;
+      }
+    } else {
+      const int off = (face == ORC_LEFT_FACE || face == ORC_RIGHT_FACE) ? Nft : Nft + Nfs;
+      const int low = face == ORC_LEFT_FACE || face == ORC_REAR_FACE;
+      for (d = 0; d < Nfs; ++d) {
+        const double v = FG(lediff, Nf, off + d, kk, ii, jj) * mu;
+        if ((s->st.fs_inward[d] != 0) == low) in += v; else out += v;
+      }
+    }
+    incoming[m] = in / 1.0; outgoing[m] = out / 1.0; /* difftop/diffside%area_divider = 1 */
+  }
+  free(ledir); free(lediff);
   return 0;
 }
 

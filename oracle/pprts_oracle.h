@@ -118,6 +118,12 @@ int orc_solve(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid);
 /* pprts_get_result (src/pprts.F90:5799-5917): edn,eup,edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny); edir may be NULL */
 int orc_get_result(orc_solver *s, int uid, double *edn, double *eup, double *abso, double *edir);
 
+/* opt_buildings of solve_pprts / pprts_get_result (src/buildings.F90:40-69, src/pprts.F90:3194-3212, :3579-3677,
+ * :4989-5145, :6011-6160).  iface: 1-based flattened index into (6,Nz,Nx,Ny), first axis fastest; face ids 1..6 =
+ * top, bottom, left (x+0), right (x+1), rear (y+0), front (y+1).  planck may be NULL.  nfaces = 0: no buildings. */
+int orc_set_buildings(orc_solver *s, int nfaces, const int *iface, const double *albedo, const double *planck);
+int orc_get_buildings_result(orc_solver *s, int uid, double *edir, double *incoming, double *outgoing);
+
 /* introspection used by the parity tests */
 const double *orc_coeff_ptr(orc_solver *s, int which); /* 1 dir2dir, 2 dir2diff, 3 diff2diff: (ncoef,Nz,Nx,Ny) */
 const double *orc_state_ptr(orc_solver *s, int uid, int which); /* 1 edir (Nd,Nz+1,Nx,Ny), 2 ediff, 3 abso, 4 b */

@@ -180,6 +180,21 @@ int pprts_b200_comm_init(pprts_b200_solver *solver, int nranks, int rank, const 
 /* sum of the accumulated spectral integrals over all ranks (final flux / heating-rate reduction) */
 int pprts_b200_allreduce_accumulated(pprts_b200_solver *solver);
 
+/* ---- buildings: the opt_buildings argument of solve_pprts / pprts_get_result ------------------------------------
+ * Replaces type(t_pprts_buildings) (src/buildings.F90:40-69) as consumed by alloc_coeff_dir2dir / alloc_coeff_diff2diff
+ * (src/pprts.F90:3194-3212, :3579-3677), setup_b (:4989-5145) and pprts_get_result (:6011-6160).
+ * iface[m]: 1-based flattened index of face m in a (6, Nz, Nx, Ny) array, first axis fastest
+ * (faceidx_by_cell_plus_offset, src/buildings.F90:215-222); face ids 1..6 = PPRTS_TOP_FACE, BOT, LEFT (x+0),
+ * RIGHT (x+1), REAR (y+0), FRONT (y+1) (src/boxmc_geometry.F90:45-51).  albedo[m]: Lambertian albedo of the face;
+ * planck[m]: emitted Planck radiance (NULL: no emission).  The list stays attached until replaced; nfaces = 0
+ * removes it.  Periodic single-GPU domains only (error 60 on a decomposed solver). */
+int pprts_b200_set_buildings(pprts_b200_solver *solver, int nfaces, const int *iface, const double *albedo,
+                             const double *planck);
+/* per face, W/m2: direct flux on the face (0 for thermal solutions; may be NULL), diffuse flux entering the building
+ * through it (incoming) and leaving it (outgoing) */
+int pprts_b200_get_buildings_result(pprts_b200_solver *solver, int uid, double *edir, double *incoming,
+                                    double *outgoing);
+
 /* introspection (parity tests, profiling) */
 /* which: 1 dir2dir, 2 dir2diff, 3 diff2diff -> out (ncoef, Nz, Nx, Ny) column-major, zeros in 1-D layers */
 int pprts_b200_get_coeffs(pprts_b200_solver *solver, int which, double *out);

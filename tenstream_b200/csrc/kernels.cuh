@@ -1231,6 +1231,13 @@ __global__ void k_bicg_update_xr(long n, int it, const double *__restrict__ ph, 
   double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
   grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
 }
+// Breakdown restart (rho = (rh, r) vanished although r has not converged): new shadow residual rh = r, so that
+// rho(1) = (r, r) -- already in SC_RR -- and the recursion starts over from the current x and r with p = r.
+__global__ void k_bicg_restart(long n, const double *__restrict__ r, double *__restrict__ rh, double *sc) {
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) rh[q] = r[q];
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc[sc_rho_slot(1)] = sc[SC_RR];
+}
+
 // ---- mixed precision: fp32 Krylov work vectors (r, rh, p, v, s, t, ph, sh), fp64 solution x and fp64 TRUE residual.
 // Every cycle starts from r64 = b - A x evaluated in fp64 (iterative refinement), so the convergence test of
 // MyKSPConverged is applied to a residual that carries no fp32 rounding.  Vector arithmetic is fp32 (the operands are
@@ -1425,6 +1432,163 @@ __global__ void k_halo_unpack(Grid g, int dir, int d0, int nd, unsigned int mask
 // v[0] <- sqrt(v[0]) / nranks : local 2-norm -> this rank's share of the mean over ranks (src/pprts_explicit.F90:182)
 __global__ void k_sqrt_mean(double *v, int n, double inv_nranks) {
   if (threadIdx.x < n) v[threadIdx.x] = sqrt(v[threadIdx.x]) * inv_nranks;
+}
+
+// =================================================================================================================
+// Buildings (opt_buildings of solve_pprts / pprts_get_result; src/buildings.F90, src/pprts.F90:3194-3212, :3579-3677,
+// :4989-5145, :6011-6160).  A building is a list of faces of grid cells: iface[m] is the 1-based flattened index into
+// (6, Nz, Nx, Ny), first axis fastest; face ids 1..6 = top (z+0), bottom (z+1), left (x+0), right (x+1), rear (y+0),
+// front (y+1).  One thread per face; the lists are tiny next to the grid, so these kernels are latency-sized.
+// Single-GPU (periodic) domains only: the host refuses buildings on a decomposed solver.
+// =================================================================================================================
+struct BldFace { int face, k, i, j; };
+__device__ __forceinline__ BldFace bld_decode(const Grid &g, int iface) {
+  long r = (long)iface - 1;
+  BldFace f;
+  f.face = (int)(r % 6) + 1; r /= 6;
+  f.k = (int)(r % g.Nz); r /= g.Nz;
+  f.i = (int)(r % g.Nx); r /= g.Nx;
+  f.j = (int)r;
+  return f;
+}
+// level-cell index of the face: bottom -> level k+1, right -> column i+1, front -> row j+1 (periodic image)
+__device__ __forceinline__ long bld_face_loc(const Grid &g, const BldFace &f) {
+  const int kk = f.face == 2 ? f.k + 1 : f.k;
+  const int ii = f.face == 4 ? wrap_p(f.i, g.Nx) : f.i;
+  const int jj = f.face == 6 ? wrap_p(f.j, g.Ny) : f.j;
+  return lidx(g, kk, jj, ii);
+}
+// set_buildings_coeff of alloc_coeff_dir2dir (:3194-3212: a building cell passes no direct radiation) and of
+// alloc_coeff_diff2diff (:3579-3677: a stream leaving the cell through a building face receives only the Lambertian
+// reflection albedo/streams of the streams entering through that face).  The tile is demoted to the exact-cvt class.
+template <class L, class CT>
+__global__ void k_buildings_coeff(Grid g, int lsolar, int nb, const int *__restrict__ iface,
+                                  const double *__restrict__ albedo, CT *__restrict__ d2d, CT *__restrict__ f2f,
+                                  unsigned char *__restrict__ tile_class) {
+  constexpr int Nd = L::Nd, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  const BldFace f = bld_decode(g, iface[m]);
+  const long c = lidx(g, f.k, f.j, f.i);
+  if (lsolar) {
+    const long cb = cbase<Nd * Nd>(c);
+    for (int n = 0; n < Nd * Nd; ++n) d2d[cb + n * PB_TILE] = (CT)0;
+  }
+  const long cb = cbase<Nf * Nf>(c);
+  const double ag = albedo[m];
+  if (f.face <= 2) {
+    const bool out_in = f.face == 2;  // top face: E_up leaves; bottom face: E_dn leaves
+    for (int dst = 0; dst < Nft; ++dst) {
+      if (L::top_in(dst) != out_in) continue;
+      for (int src = 0; src < Nf; ++src) {
+        const bool refl = src < Nft && L::top_in(src) != out_in;
+        f2f[cb + (dst * Nf + src) * PB_TILE] = refl ? (CT)(ag / (double)(Nft / 2)) : (CT)0;
+      }
+    }
+  } else {
+    const int off = f.face <= 4 ? Nft : Nft + Nfs;
+    const bool out_in = f.face == 4 || f.face == 6;
+    for (int d = 0; d < Nfs; ++d) {
+      if (L::side_in(d) != out_in) continue;
+      for (int src = 0; src < Nf; ++src) {
+        const bool refl = src >= off && src < off + Nfs && L::side_in(src - off) != out_in;
+        f2f[cb + ((off + d) * Nf + src) * PB_TILE] = refl ? (CT)(ag / (double)(Nfs / 2)) : (CT)0;
+      }
+    }
+  }
+  atomicMax(reinterpret_cast<unsigned int *>(tile_class) + (c >> PB_TILE_SHIFT), 2u);
+}
+// divergence factors of the patched cells, summed exactly as k_lookup does (all faces of a cell write the same values)
+template <class L, class CT>
+__global__ void k_buildings_cdiv(Grid g, int lsolar, int nb, const int *__restrict__ iface,
+                                 const CT *__restrict__ d2d, const CT *__restrict__ d2f, const CT *__restrict__ f2f,
+                                 double *__restrict__ cdiv_dir, double *__restrict__ cdiv_diff) {
+  constexpr int Nd = L::Nd, Nf = L::Nf;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  const BldFace f = bld_decode(g, iface[m]);
+  const long c = lidx(g, f.k, f.j, f.i);
+  const long cb_ff = cbase<Nf * Nf>(c), cb_dd = cbase<Nd * Nd>(c), cb_df = cbase<Nd * Nf>(c);
+  for (int s = 0; s < Nf; ++s) {
+    double sum = 0.0;
+    for (int dst = 0; dst < Nf; ++dst) sum += (double)f2f[cb_ff + (dst * Nf + s) * PB_TILE];
+    cdiv_diff[(long)s * g.ncp + c] = 1.0 - sum;
+  }
+  if (!lsolar) return;
+  for (int s = 0; s < Nd; ++s) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int dst = 0; dst < Nd; ++dst) s1 += (double)d2d[cb_dd + (dst * Nd + s) * PB_TILE];
+    for (int dst = 0; dst < Nf; ++dst) s2 += (double)d2f[cb_df + (dst * Nd + s) * PB_TILE];
+    cdiv_dir[(long)s * g.ncp + c] = 1.0 - s1 - s2;
+  }
+}
+// setup_b::set_buildings_reflection (:4989-5080) and set_buildings_emission (:5082-5145): the source entries of the
+// streams leaving through a building face are REPLACED by the reflected direct beam / the wall's emission.
+// Every (face, stream) pair owns its b entry, so plain stores suffice.  planck == nullptr: no emission.
+template <class L>
+__global__ void k_buildings_source(Grid g, int lsolar, int lthermal, int nb, const int *__restrict__ iface,
+                                   const double *__restrict__ albedo, const double *__restrict__ planck,
+                                   const double *__restrict__ dz, const double *__restrict__ edir,
+                                   double *__restrict__ b) {
+  constexpr int Ndt = L::Ndt, Nds = L::Nds, Nft = L::Nft, Nfs = L::Nfs;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  const BldFace f = bld_decode(g, iface[m]);
+  const long l = bld_face_loc(g, f);
+  const double ag = albedo[m];
+  const bool top = f.face <= 2, xface = f.face == 3 || f.face == 4;
+  const bool out_in = f.face == 2 || f.face == 4 || f.face == 6;
+  const int off = top ? 0 : (xface ? Nft : Nft + Nfs), nout = top ? Nft : Nfs;
+  const double streams = (double)((top ? Nft : Nfs) / 2);
+  if (lsolar) {
+    const int s0 = top ? 0 : (xface ? Ndt : Ndt + Nds), ns = top ? Ndt : Nds;
+    for (int d = 0; d < nout; ++d) {
+      if ((top ? L::top_in(d) : L::side_in(d)) != out_in) continue;
+      double acc = 0.0;  // xsrc = 0, then += edir(src) * albedo / streams in ascending src order
+      for (int src = s0; src < s0 + ns; ++src) acc = acc + edir[(long)src * g.nlev + l] * ag / streams;
+      b[(long)(off + d) * g.nlev + l] = acc;
+    }
+  }
+  if (lthermal && planck != nullptr) {
+    const long c = lidx(g, f.k, f.j, f.i);
+    const double A = top ? g.dx * g.dy : (xface ? g.dy * dz[c] : g.dx * dz[c]);  // diff area_divider = 1
+    const double emis = M_PI * planck[m] * (1.0 - ag);
+    for (int d = 0; d < nout; ++d) {
+      if ((top ? L::top_in(d) : L::side_in(d)) != out_in) continue;
+      b[(long)(off + d) * g.nlev + l] = A * emis / streams;
+    }
+  }
+}
+// pprts_get_result::fill_buildings_arr (:6011-6160), fluxes already in W/m2: direct flux on the face, diffuse flux
+// entering (incoming) and leaving (outgoing) the building through it; solar results carry the factor mu.
+template <class L>
+__global__ void k_buildings_result(Grid g, int lsolar, double mu, int nb, const int *__restrict__ iface,
+                                   const double *__restrict__ edir, const double *__restrict__ ediff,
+                                   double *__restrict__ out_edir, double *__restrict__ out_in,
+                                   double *__restrict__ out_out) {
+  constexpr int Ndt = L::Ndt, Nds = L::Nds, Nft = L::Nft, Nfs = L::Nfs;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  const BldFace f = bld_decode(g, iface[m]);
+  const long l = bld_face_loc(g, f);
+  const bool top = f.face <= 2, xface = f.face == 3 || f.face == 4;
+  const bool low = f.face == 1 || f.face == 3 || f.face == 5;  // inward streams ENTER the building through a low face
+  double e = 0.0;
+  if (lsolar) {
+    const int s0 = top ? 0 : (xface ? Ndt : Ndt + Nds), ns = top ? Ndt : Nds;
+    for (int d = s0; d < s0 + ns; ++d) e += edir[(long)d * g.nlev + l] * mu;
+    e = e / (double)(top ? L::dirtop_adiv : L::dirside_adiv);
+  }
+  out_edir[m] = e;
+  const double fmu = lsolar ? mu : 1.0;
+  const int off = top ? 0 : (xface ? Nft : Nft + Nfs), n = top ? Nft : Nfs;
+  double in = 0.0, out = 0.0;
+  for (int d = 0; d < n; ++d) {
+    const double v = ediff[(long)(off + d) * g.nlev + l] * fmu;
+    if ((top ? L::top_in(d) : L::side_in(d)) == low) in += v; else out += v;
+  }
+  out_in[m] = in;
+  out_out[m] = out;
 }
 
 // =================================================================================================================

@@ -259,6 +259,11 @@ struct pprts_b200_solver {
   long halo_exchanges = 0;
   int num_sms = 148;
   bool use_tma = true;
+  // opt_buildings (t_pprts_buildings, src/buildings.F90:40-69): faces of building cells, device copies
+  int nbld = 0;
+  bool bld_have_planck = false;
+  int *bld_iface = nullptr;
+  double *bld_albedo = nullptr, *bld_planck = nullptr, *bld_out = nullptr;  // bld_out: edir | incoming | outgoing
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -668,6 +673,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
                     s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
+  cudaFree(s->bld_iface); cudaFree(s->bld_albedo); cudaFree(s->bld_planck); cudaFree(s->bld_out);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
   cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
   for (int q = 0; q < 2; ++q) { cudaFree(s->hs[q]); cudaFree(s->hr[q]); }
@@ -805,6 +811,14 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
                            s->n1d, s->kabs, s->ksca, s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f,
                            s->cdiv_dir, s->cdiv_diff, (unsigned char *)s->tile_class));
   }
+  if (s->nbld > 0) {  // set_buildings_coeff (src/pprts.F90:3188-3212, :3492-3494, :3579-3677)
+    DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_buildings_coeff<L, CT>), nblk(s->nbld, 128), 128, g, (int)lsolar, s->nbld,
+                           (const int *)s->bld_iface, (const double *)s->bld_albedo, (CT *)s->d2d, (CT *)s->f2f,
+                           (unsigned char *)s->tile_class));
+    DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_buildings_cdiv<L, CT>), nblk(s->nbld, 128), 128, g, (int)lsolar, s->nbld,
+                           (const int *)s->bld_iface, (const CT *)s->d2d, (const CT *)s->d2f, (const CT *)s->f2f,
+                           s->cdiv_dir, s->cdiv_diff));
+  }
   s->coeffs_dirty = false;
   s->coeffs_have_dir = lsolar;
   s->prec_ready = false;
@@ -906,6 +920,12 @@ static int setup_b(pprts_b200_solver *s, Solution &sol) {
   if (sol.lthermal_rad) {
     DISPATCH_L(s, LAUNCH(s, FAM_SOURCE, (k_source_thermal<L>), nblk(g.ncell, 128), 128, g, s->n1d, (int)s->have_Bsrfc,
                           (const double *)(s->icollapse > 1 ? s->Btop : nullptr), (const double *)s->Bbot, s->cdiv_diff, s->a11, s->a12, s->kabs, s->dz, s->planck, s->Bsrfc, s->albedo, s->b));
+  }
+  if (s->nbld > 0) {  // set_buildings_reflection / set_buildings_emission (src/pprts.F90:4669-4672)
+    DISPATCH_L(s, LAUNCH(s, FAM_SOURCE, (k_buildings_source<L>), nblk(s->nbld, 128), 128, g, (int)sol.lsolar_rad,
+                          (int)sol.lthermal_rad, s->nbld, (const int *)s->bld_iface, (const double *)s->bld_albedo,
+                          (const double *)(s->bld_have_planck ? s->bld_planck : nullptr), (const double *)s->dz,
+                          (const double *)sol.edir, s->b));
   }
   // source emitted into a neighbour's face: stored there by its one producer (replaces halo_reduce_5pt, :4678)
   if (s->decomposed) {
@@ -1125,6 +1145,8 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
         else inner = std::min(0.5 * inner, 0.5 * inner * target / rtrue);  // keep the Krylov space, aim lower
       }
       if (!converged && rn <= floor32) restart = true;  // refine from a fresh fp64 residual
+      // breakdown: rho = (rh, r) vanished with r not converged -> new cycle, i.e. new shadow residual rh = r
+      if (!converged && std::fabs(s->h_sc[((it + 1) & 1) ? SC_RHO1 : SC_RHO0]) <= 1e-30 * rn * rc0) restart = true;
     }
     if (!restart && !converged) break;  // maxit
   }
@@ -1161,7 +1183,9 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
   sol.res_diff = r0;
   bool converged = false;
   if (r0 <= atol) converged = true;  // x already solves the system to tolerance (warm start)
-  for (int it = 1; it <= maxit && !converged; ++it) {
+  // `it` is the index inside the current Krylov recursion: a breakdown (rho = (rh, r) = 0 with r not converged, e.g.
+  // when the source and its first images have disjoint supports in a vacuum) restarts it with rh = r
+  for (int total = 1, it = 1; total <= maxit && !converged; ++total, ++it) {
     LAUNCH(s, FAM_VEC, k_bicg_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
     if (prec) launch_prec(s, p, ph);
     if ((rc = launch_matmult<1>(s, ph, v, rh, s->sc + SC_RHV))) return rc;
@@ -1172,10 +1196,14 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
     if ((rc = allreduce_scalars(s, s->sc + (((it + 1) & 1) ? SC_RR : SC_RHO0), 2))) return rc;
     if ((rc = read_scalars(s))) return rc;
     const double rn = std::sqrt(s->h_sc[SC_RR]);
-    sol.niter_diff = it;
+    sol.niter_diff = total;
     sol.res_diff = rn;
-    if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", it);
+    if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", total);
     if (rn / r0 <= rtol || rn <= atol) converged = true;
+    else if (std::fabs(s->h_sc[((it + 1) & 1) ? SC_RHO1 : SC_RHO0]) <= 1e-30 * rn * r0) {
+      LAUNCH(s, FAM_VEC, k_bicg_restart, vec_grid(n), VEC_BLOCK, n, r, rh, s->sc);
+      it = 0;
+    }
   }
   sol.first_diff = false;
   sol.lchanged = true;
@@ -1527,6 +1555,57 @@ extern "C" int pprts_b200_get_info(pprts_b200_solver *s, int uid, int *niter_dir
   if (it == s->solutions.end()) return set_err(30, "no solution for uid %d", uid);
   *niter_dir = it->second.niter_dir; *niter_diff = it->second.niter_diff;
   *res_dir = it->second.res_dir; *res_diff = it->second.res_diff;
+  return 0;
+}
+// opt_buildings of solve_pprts (src/pprts.F90:2487-2494): the faces stay attached to the solver until replaced or
+// removed (nfaces = 0).  Coefficients are re-derived on the next solve, as alloc_coeff_* does on every call (:2682-2687).
+extern "C" int pprts_b200_set_buildings(pprts_b200_solver *s, int nfaces, const int *iface, const double *albedo,
+                                        const double *planck) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  if (nfaces > 0 && s->decomposed) return set_err(60, "buildings are not supported on an x/y-decomposed solver yet");
+  if (nfaces > 0 && (!iface || !albedo)) return set_err(2, "set_buildings: iface and albedo are required");
+  const Grid &g = s->g;
+  for (int m = 0; m < nfaces; ++m)
+    if (iface[m] < 1 || (long)iface[m] > 6L * g.ncell)
+      return set_err(61, "building face %d: index %d outside the (6,%d,%d,%d) grid", m + 1, iface[m], g.Nz, g.Nx, g.Ny);
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(s->bld_iface); cudaFree(s->bld_albedo); cudaFree(s->bld_planck); cudaFree(s->bld_out);
+  s->bld_iface = nullptr; s->bld_albedo = s->bld_planck = s->bld_out = nullptr;
+  if (s->nbld > 0 || nfaces > 0) s->coeffs_dirty = true;
+  s->nbld = std::max(0, nfaces);
+  s->bld_have_planck = false;
+  if (nfaces <= 0) return 0;
+  DA(s->bld_iface, (size_t)nfaces); DA(s->bld_albedo, (size_t)nfaces); DA(s->bld_planck, (size_t)nfaces);
+  DA(s->bld_out, (size_t)3 * nfaces);
+  CU(cudaMemcpy(s->bld_iface, iface, sizeof(int) * nfaces, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(s->bld_albedo, albedo, sizeof(double) * nfaces, cudaMemcpyHostToDevice));
+  if (planck) {
+    CU(cudaMemcpy(s->bld_planck, planck, sizeof(double) * nfaces, cudaMemcpyHostToDevice));
+    s->bld_have_planck = true;
+  }
+  return 0;
+}
+// pprts_get_result(..., opt_buildings): fill_buildings_arr (src/pprts.F90:6011-6160); edir may be NULL
+extern "C" int pprts_b200_get_buildings_result(pprts_b200_solver *s, int uid, double *edir, double *incoming,
+                                               double *outgoing) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  if (s->nbld <= 0) return set_err(62, "no buildings attached to the solver");
+  Solution *sol;
+  int rc = find_solution(s, uid, &sol);
+  if (rc) return rc;
+  const Grid &g = s->g;
+  const int n = s->nbld;
+  DISPATCH_L(s, LAUNCH(s, FAM_ABSO, (k_buildings_result<L>), nblk(n, 128), 128, g, (int)sol->lsolar_rad, s->mu, n,
+                        (const int *)s->bld_iface, (const double *)sol->edir, (const double *)sol->ediff, s->bld_out,
+                        s->bld_out + n, s->bld_out + 2 * n));
+  std::vector<double> h((size_t)3 * n);
+  CU(cudaMemcpyAsync(h.data(), s->bld_out, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (edir) std::copy(h.begin(), h.begin() + n, edir);
+  if (incoming) std::copy(h.begin() + n, h.begin() + 2 * n, incoming);
+  if (outgoing) std::copy(h.begin() + 2 * n, h.end(), outgoing);
   return 0;
 }
 extern "C" int pprts_b200_mat_mult_ediff(pprts_b200_solver *s, const double *x, double *y) {

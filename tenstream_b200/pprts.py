@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "pprts_b200_comm_init", "pprts_b200_allreduce_accumulated", "pprts_b200_get_coeffs", "pprts_b200_get_state",
     "pprts_b200_get_info", "pprts_b200_mat_mult_ediff", "pprts_b200_lookup_coeffs", "pprts_b200_kernel_launches",
     "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error", "pprts_b200_stream",
-    "pprts_b200_solve_bands",
+    "pprts_b200_solve_bands", "pprts_b200_set_buildings", "pprts_b200_get_buildings_result",
 ]
 
 
@@ -110,6 +110,8 @@ def lib():
     L.pprts_b200_get_info.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p]
     L.pprts_b200_mat_mult_ediff.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.pprts_b200_lookup_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_long] + [c_double_p] * 5
+    L.pprts_b200_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p]
+    L.pprts_b200_get_buildings_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_kernel_launches.restype = C.c_long
     L.pprts_b200_kernel_launches.argtypes = [C.c_void_p]
     L.pprts_b200_stream.restype = C.c_void_p
@@ -356,18 +358,48 @@ def set_optical_properties(solver: Solver, albedo, kabs=None, ksca=None, g=None,
          "set_optical_properties")
 
 
-def solve_pprts(solver: Solver, lthermal, lsolar, edirTOA, opt_solution_uid=0, opt_solution_time=None):
-    """``solve_pprts`` (src/pprts.F90:2487-2665)"""
+def _attach_buildings(solver: Solver, opt_buildings):
+    """Hand the face list of a ``tenstream_b200.buildings.PprtsBuildings`` (or None) to the device solver."""
+    cur = getattr(solver, "_buildings", None)
+    if opt_buildings is None:
+        if cur is not None:
+            _chk(lib().pprts_b200_set_buildings(solver._h, 0, None, None, None), "solve_pprts(opt_buildings)")
+            solver._buildings = None
+        return
+    iface = np.ascontiguousarray(opt_buildings.iface, dtype=np.int32)
+    albedo = np.ascontiguousarray(opt_buildings.albedo, dtype=np.float64)
+    planck = None if opt_buildings.planck is None else np.ascontiguousarray(opt_buildings.planck, dtype=np.float64)
+    if len(albedo) != len(iface) or (planck is not None and len(planck) != len(iface)):
+        raise PprtsError("opt_buildings: iface, albedo and planck must have one entry per face")
+    key = (iface.tobytes(), albedo.tobytes(), None if planck is None else planck.tobytes())
+    if cur is not None and cur == key:
+        return
+    _chk(lib().pprts_b200_set_buildings(solver._h, len(iface), iface.ctypes.data_as(c_int_p), _vp(albedo),
+                                        _vp(planck) if planck is not None else None), "solve_pprts(opt_buildings)")
+    solver._buildings = key
+
+
+def solve_pprts(solver: Solver, lthermal, lsolar, edirTOA, opt_solution_uid=0, opt_solution_time=None,
+                opt_buildings=None):
+    """``solve_pprts`` (src/pprts.F90:2487-2665); ``opt_buildings``: a ``buildings.PprtsBuildings`` (:2494)"""
+    _attach_buildings(solver, opt_buildings)
     _chk(lib().pprts_b200_solve(solver._h, int(bool(lthermal)), int(bool(lsolar)), float(edirTOA),
                                 int(opt_solution_uid)), "solve_pprts")
 
 
-def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None):
+def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None, opt_buildings=None):
     """``pprts_get_result`` (src/pprts.F90:5799-5917) -> (edn, eup, abso, edir) in W/m2 resp. W/m3,
-    shapes (Nz+1,Nx,Ny) / (Nz,Nx,Ny).  ``out`` may carry preallocated Fortran-ordered arrays."""
+    shapes (Nz+1,Nx,Ny) / (Nz,Nx,Ny).  ``out`` may carry preallocated Fortran-ordered arrays.  With ``opt_buildings``
+    (the object given to solve_pprts) its ``edir / incoming / outgoing`` per-face fluxes are filled (:5906-5910)."""
     edn, eup, abso, edir = out if out is not None else _alloc_results(solver)
     _chk(lib().pprts_b200_get_result(solver._h, int(opt_solution_uid), _vp(edn), _vp(eup), _vp(abso), _vp(edir)),
          "pprts_get_result")
+    if opt_buildings is not None:
+        n = len(opt_buildings.iface)
+        be, bi, bo = np.zeros(n), np.zeros(n), np.zeros(n)
+        _chk(lib().pprts_b200_get_buildings_result(solver._h, int(opt_solution_uid), _vp(be), _vp(bi), _vp(bo)),
+             "pprts_get_result(opt_buildings)")
+        opt_buildings.edir, opt_buildings.incoming, opt_buildings.outgoing = be, bi, bo
     return edn, eup, abso, edir
 
 

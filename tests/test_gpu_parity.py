@@ -649,3 +649,132 @@ def test_atmosphere_collapse_vs_oracle(P, gpu_lut, oracle_lut, solar, ci):
         assert a.shape == b.shape
         assert relerr(a, b) < 1e-7, (name, s.info(), o.info())
     P.destroy_pprts(s); o.destroy()
+
+
+# ---- buildings (opt_buildings) ------------------------------------------------------------------------------------------
+def _buildings_case(P, gpu_lut, oracle_lut, solar, cells, box_albedo, box_planck, phi0, theta0, mixed=False, coeff_fp32=False):
+    from oracle import binding as ob
+    from tenstream_b200 import buildings as B
+    rng = np.random.default_rng(77)
+    Nz, Nx, Ny = 7, 8, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny, cloudy=False)
+    ksca *= 20.0
+    sd = P.sundir_from_angles(phi0, theta0)
+    dz = np.full(Nz, 80.)
+    tol = dict(rtol=1e-10, atol=1e-30)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, coeff_fp32=coeff_fp32, krylov_fp32=mixed, **tol)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, coeff_fp32=coeff_fp32, diff_solver=0, rtol=1e-11,
+                        atol=1e-30, maxit_diff=20000)
+    bld = B.box_buildings(Nz, Nx, Ny, cells, box_albedo, None if solar else box_planck)
+    bld.albedo[:] = box_albedo * rng.uniform(0.5, 1.5, len(bld.albedo))          # every face its own albedo
+    if not solar:
+        bld.planck[:] = box_planck * rng.uniform(0.8, 1.2, len(bld.planck))
+    assert B.check_buildings_consistency(bld, Nz, Nx, Ny) == 0
+    planck = None if solar else (np.linspace(60., 120., Nz + 1)[:, None, None] * rng.uniform(0.9, 1.1, (1, Nx, Ny)))
+    kw = {} if solar else dict(planck=planck, planck_srfc=np.full((Nx, Ny), 125.))
+    P.set_optical_properties(s, 0.2, kabs * (1 if solar else 5), ksca, g, **kw)
+    o.set_optical_properties(0.2, kabs * (1 if solar else 5), ksca, g, **kw)
+    o.set_buildings(bld.iface, bld.albedo, bld.planck)
+    P.solve_pprts(s, not solar, solar, 1000. if solar else 0., opt_buildings=bld)
+    assert o.solve(not solar, solar, 1000. if solar else 0.) == 0
+    got = P.pprts_get_result(s, opt_buildings=bld)
+    want = o.get_result()
+    wb = o.get_buildings_result()
+    out = dict(got=got, want=want, bld=bld, wb=wb, coeffs=[(w, s.coeffs(w), o.coeffs(w)) for w in ((1, 2, 3) if solar else (3,))],
+               b=(s.state(4), o.state(4)), info=(s.info(), o.info()))
+    P.destroy_pprts(s); o.destroy()
+    return out
+
+
+@pytest.mark.parametrize("solar", [True, False])
+@pytest.mark.parametrize("phi0,theta0", [(30., 40.), (210., 55.)])
+def test_buildings_vs_oracle(P, gpu_lut, oracle_lut, solar, phi0, theta0):
+    """Coefficient blocking / Lambertian reflection, reflected-beam and emission sources, fluxes, absorption and the
+    per-face building results against the oracle; two boxes (a 1x1x2 tower on the ground, one hovering cell at the
+    periodic domain edge so that the right/front faces wrap)."""
+    cells = [(7, 3, 3), (6, 3, 3), (4, 8, 6)]
+    out = _buildings_case(P, gpu_lut, oracle_lut, solar, cells, 0.3, 90.0, phi0, theta0)
+    for w, a, b in out["coeffs"]:
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()       # interpolated coefficients: 1e-12 (north_star)
+        for (k, i, j) in cells:                                     # patched dir2dir / diff2diff blocks: exact constants
+            if w != 2:
+                assert np.array_equal(a[:, k - 1, i - 1, j - 1], b[:, k - 1, i - 1, j - 1])
+    bg, bo = out["b"]
+    # thermal: closed form; solar: b inherits the direct beam, which both sides iterate to their sweep tolerance
+    assert np.abs(bg - bo).max() <= (1e-9 if solar else 1e-12) * np.abs(bo).max()
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), out["got"], out["want"]):
+        assert relerr(a, b) < 1e-6, (name, relerr(a, b), out["info"])
+    bld = out["bld"]
+    for name, a, b in zip(("edir", "incoming", "outgoing"), (bld.edir, bld.incoming, bld.outgoing), out["wb"]):
+        scale = max(np.abs(b).max(), 1e-300)
+        assert np.abs(a - b).max() <= 1e-6 * scale, (name, a, b)
+    if solar:   # (edir + incoming) * albedo = outgoing on every face (test_buildings.F90:265)
+        np.testing.assert_allclose((bld.edir + bld.incoming) * bld.albedo, bld.outgoing, rtol=1e-6, atol=1e-9)
+    else:       # outgoing = reflected + emitted
+        np.testing.assert_allclose(bld.incoming * bld.albedo + np.pi * bld.planck * (1 - bld.albedo), bld.outgoing,
+                                   rtol=1e-6, atol=1e-9)
+
+
+def test_buildings_mixed_precision_and_fp32_coefficients(P, gpu_lut, oracle_lut):
+    out = _buildings_case(P, gpu_lut, oracle_lut, True, [(7, 3, 3), (4, 8, 6)], 0.3, 0.0, 120., 35., mixed=True, coeff_fp32=True)
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), out["got"], out["want"]):
+        assert relerr(a, b) < 1e-6, (name, relerr(a, b), out["info"])
+
+
+def test_buildings_reference_known_answers(P, gpu_lut):
+    """tests/test_buildings/test_buildings.F90:151-320 through the CUDA path: vacuum 6x6x3 domain, one hovering box."""
+    from tenstream_b200 import buildings as B
+    Nx = Ny = 6
+    Nlay = 3
+    k, i, j = 1, 2, 2
+    z = np.zeros((Nlay, Nx, Ny))
+
+    def run(lthermal, box_albedo, box_planck, theta0, Ag):
+        s = P.init_pprts(0, Nlay, Nx, Ny, 100., 100., P.sundir_from_angles(0., theta0), dz1d=np.full(Nlay, 100.),
+                         lut=gpu_lut, rtol=1e-10, atol=1e-30)
+        bld = B.box_buildings(Nlay, Nx, Ny, [(2, 3, 3)], box_albedo, box_planck if lthermal else None)
+        plck = np.full((Nlay + 1, Nx, Ny), 100. / np.pi) if lthermal else None
+        P.set_optical_properties(s, Ag, z, z, z, planck=plck)
+        P.solve_pprts(s, lthermal, not lthermal, 1.0, opt_buildings=bld)
+        res = P.pprts_get_result(s, opt_buildings=bld)
+        P.destroy_pprts(s)
+        return res, bld
+
+    (edn, eup, abso, edir), bld = run(False, 0.0, 0.0, 0.0, 0.0)        # overhead sun, black box
+    assert abs(edir[Nlay, i, j]) < 1e-5 and abs(edir[k + 1, i, j]) < 1e-5
+    assert abso[k, i, j] == pytest.approx(1.0 / 100., abs=1e-5)
+    assert bld.edir[0] == pytest.approx(1.0, abs=1e-5) and np.abs(bld.edir[1:]).max() < 1e-5
+    assert np.abs(bld.incoming).max() < 1e-5 and np.abs(bld.outgoing).max() < 1e-5
+    (edn, eup, abso, edir), bld = run(False, 0.5, 0.0, 0.0, 1.0)        # box albedo 0.5 over a white ground
+    assert edir[k, i, j] == pytest.approx(1.0, abs=1e-5) and eup[k, i, j] == pytest.approx(0.5, abs=1e-5)
+    np.testing.assert_allclose((bld.edir + bld.incoming) * 0.5, bld.outgoing, atol=1e-5)
+    (edn, eup, abso, edir), bld = run(True, 0.0, 1.0, 180.0, 0.0)       # emission
+    assert eup[k, i, j] == pytest.approx(np.pi, abs=1e-5) and edn[k + 1, i, j] == pytest.approx(np.pi, abs=1e-5)
+    np.testing.assert_allclose(bld.outgoing, np.pi, atol=1e-5)
+
+
+def test_buildings_removed_and_errors(P, gpu_lut):
+    from tenstream_b200 import buildings as B
+    rng = np.random.default_rng(5)
+    Nz, Nx, Ny = 5, 6, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny, cloudy=False)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(20., 30.), dz1d=np.full(Nz, 80.), lut=gpu_lut,
+                     rtol=1e-10, atol=1e-30)
+    P.set_optical_properties(s, 0.2, kabs, ksca * 20, g)
+    P.solve_pprts(s, False, True, 100.0, 1)
+    base = [a.copy() for a in P.pprts_get_result(s, 1)]
+    bld = B.box_buildings(Nz, Nx, Ny, [(4, 3, 3)], 0.4)
+    P.solve_pprts(s, False, True, 100.0, 2, opt_buildings=bld)
+    withb = P.pprts_get_result(s, 2, opt_buildings=bld)
+    assert np.abs(withb[1] - base[1]).max() > 1e-3
+    P.solve_pprts(s, False, True, 100.0, 3)                 # opt_buildings absent again: plain coefficients
+    again = P.pprts_get_result(s, 3)
+    for a, b in zip(base, again):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
+    with pytest.raises(P.PprtsError, match="no buildings"):
+        P.pprts_get_result(s, 3, opt_buildings=bld)
+    bad = B.box_buildings(Nz, Nx, Ny, [(4, 3, 3)], 0.4)
+    bad.iface[0] = 6 * Nz * Nx * Ny + 1
+    with pytest.raises(P.PprtsError, match="outside"):
+        P.solve_pprts(s, False, True, 100.0, 4, opt_buildings=bad)
+    P.destroy_pprts(s)

@@ -12,7 +12,7 @@ module m_pprts_b200
   implicit none
   private
   public :: t_solver_b200, t_lut_b200, lut_open, lut_close, init_pprts, set_angles, set_optical_properties, &
-    & solve_pprts, pprts_get_result, destroy_pprts
+    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200
 
   integer, parameter :: ireals = c_double, iintegers = c_int
 
@@ -22,6 +22,14 @@ module m_pprts_b200
   type t_solver_b200
     type(c_ptr) :: h = c_null_ptr
     integer(iintegers) :: Nz = 0, Nx = 0, Ny = 0
+  end type
+
+  !> the data members of t_pprts_buildings (src/buildings.F90:40-69) that the pprts path reads and fills; a host that
+  !> already holds a type(t_pprts_buildings) passes its iface / albedo / planck arrays on unchanged
+  type t_pprts_buildings_b200
+    integer(c_int), allocatable :: iface(:)   !< 1-based flattened (6,Nz,Nx,Ny) face indices (buildings.F90:215-222)
+    real(ireals), allocatable :: albedo(:), planck(:)
+    real(ireals), allocatable :: edir(:), incoming(:), outgoing(:)
   end type
 
   !> mirrors pprts_b200_config (include/pprts_b200.h)
@@ -87,6 +95,17 @@ module m_pprts_b200
       import; type(c_ptr), value :: solver
       integer(c_int), value :: nranks, rank
       character(kind=c_char), intent(in) :: id(128)
+    end function
+    integer(c_int) function c_set_buildings(solver, nfaces, iface, albedo, planck) bind(c, name='pprts_b200_set_buildings')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver, iface, albedo, planck
+      integer(c_int), value :: nfaces
+    end function
+    integer(c_int) function c_get_buildings_result(solver, uid, edir, incoming, outgoing) &
+        & bind(c, name='pprts_b200_get_buildings_result')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver, edir, incoming, outgoing
+      integer(c_int), value :: uid
     end function
     function c_last_error() bind(c, name='pprts_b200_last_error') result(msg)
       import; type(c_ptr) :: msg
@@ -193,22 +212,33 @@ contains
   end subroutine
 
   !> solve_pprts (src/pprts.F90:2487)
-  subroutine solve_pprts(solver, lthermal, lsolar, edirTOA, opt_solution_uid)
+  subroutine solve_pprts(solver, lthermal, lsolar, edirTOA, opt_solution_uid, opt_buildings)
     type(t_solver_b200), intent(inout) :: solver
     logical, intent(in) :: lthermal, lsolar
     real(ireals), intent(in) :: edirTOA
     integer(iintegers), intent(in), optional :: opt_solution_uid
+    type(t_pprts_buildings_b200), intent(in), target, optional :: opt_buildings
     integer(c_int) :: uid
+    type(c_ptr) :: ppl
     uid = 0; if (present(opt_solution_uid)) uid = opt_solution_uid
+    if (present(opt_buildings)) then  ! src/pprts.F90:2494; the list stays attached until the next call without it
+      ppl = c_null_ptr
+      if (allocated(opt_buildings%planck)) ppl = c_loc(opt_buildings%planck)
+      call chkerr(c_set_buildings(solver%h, size(opt_buildings%iface), c_loc(opt_buildings%iface), &
+        & c_loc(opt_buildings%albedo), ppl), 'solve_pprts(opt_buildings)')
+    else
+      call chkerr(c_set_buildings(solver%h, 0_c_int, c_null_ptr, c_null_ptr, c_null_ptr), 'solve_pprts')
+    end if
     call chkerr(c_solve(solver%h, merge(1, 0, lthermal), merge(1, 0, lsolar), edirTOA, uid), 'solve_pprts')
   end subroutine
 
   !> pprts_get_result (src/pprts.F90:5799): allocates the outputs if needed, like the reference
-  subroutine pprts_get_result(solver, redn, reup, rabso, redir, opt_solution_uid)
+  subroutine pprts_get_result(solver, redn, reup, rabso, redir, opt_solution_uid, opt_buildings)
     type(t_solver_b200), intent(inout) :: solver
     real(ireals), allocatable, target, intent(inout) :: redn(:, :, :), reup(:, :, :), rabso(:, :, :)
     real(ireals), allocatable, target, intent(inout), optional :: redir(:, :, :)
     integer(iintegers), intent(in), optional :: opt_solution_uid
+    type(t_pprts_buildings_b200), intent(inout), target, optional :: opt_buildings
     integer(c_int) :: uid
     type(c_ptr) :: pdir
     uid = 0; if (present(opt_solution_uid)) uid = opt_solution_uid
@@ -221,6 +251,13 @@ contains
       pdir = c_loc(redir)
     end if
     call chkerr(c_get_result(solver%h, uid, c_loc(redn), c_loc(reup), c_loc(rabso), pdir), 'pprts_get_result')
+    if (present(opt_buildings)) then  ! fill_buildings_arr, src/pprts.F90:5906-5910, :6011-6160
+      if (.not. allocated(opt_buildings%edir)) allocate (opt_buildings%edir(size(opt_buildings%iface)))
+      if (.not. allocated(opt_buildings%incoming)) allocate (opt_buildings%incoming(size(opt_buildings%iface)))
+      if (.not. allocated(opt_buildings%outgoing)) allocate (opt_buildings%outgoing(size(opt_buildings%iface)))
+      call chkerr(c_get_buildings_result(solver%h, uid, c_loc(opt_buildings%edir), c_loc(opt_buildings%incoming), &
+        & c_loc(opt_buildings%outgoing)), 'pprts_get_result(opt_buildings)')
+    end if
   end subroutine
 
   subroutine destroy_pprts(solver, lfinalizepetsc)

@@ -1,0 +1,163 @@
+"""BASELINE.json's full sizes on the GPU, checked through size-independent properties (the oracle needs minutes per band
+at these sizes): energy closure, linearity in the source, idempotence of a warm-started solve, mirror symmetry of the
+reference's tests/test_pprts_symmetry, agreement of the mixed-precision and the fp64 Krylov paths, and the band loop's
+spectral sum.  Run with the bench tables (real LUT axes) at the reference's default solver tolerances unless stated.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from tenstream_b200 import pprts
+    pprts.lib()
+    return pprts
+
+
+@pytest.fixture(scope="module")
+def bench_lut(P, tmp_path_factory):
+    from tenstream_b200 import lut as L
+    cfg = L.bench_config(310)
+    base = os.path.join(os.environ.get("PPRTS_B200_LUT_DIR", "/tmp/pprts_b200_luts"), "LUT")
+    os.makedirs(os.path.dirname(base), exist_ok=True)
+    paths = L.write_synthetic_lut(cfg, base)       # reuses the files bench.py wrote, if any
+    lut = P.Lut(cfg, paths)
+    yield lut
+    lut.close()
+
+
+def closure(sc, res):
+    """(absorbed + leaving) / entering for one band; abso in W/m3, fluxes in W/m2 on a regular grid"""
+    edn, eup, abso, edir = res
+    inc = edir[0].sum() + edn[0].sum()
+    out = eup[0].sum() + (edir[-1].sum() + edn[-1].sum() - eup[-1].sum()) + (abso * sc["dz1d"][:, None, None]).sum()
+    return out / inc
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_c2_solar_properties(P, bench_lut):
+    """configs[1], 256x256x80 solar band: closure, linearity, idempotence, mixed == fp64 vectors"""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field()
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    assert (Nx, Ny, Nz) == (256, 256, 80)
+    sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
+    s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], sd, dz1d=sc["dz1d"], lut=bench_lut, coeff_fp32=True,
+                     krylov_fp32=True)
+    P.set_optical_properties(s, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+    P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+    r1 = [a.copy() for a in P.pprts_get_result(s, 1)]
+    it1 = s.info(1)["niter_diff"]
+    assert all(np.isfinite(a).all() for a in r1) and min(a.min() for a in (r1[0], r1[1], r1[3])) > -1.0
+    # default tolerances: rtol 1e-5 on the residual -> closure to a few 1e-5
+    assert abs(closure(sc, r1) - 1) < 2e-4, closure(sc, r1)
+    # the direct beam is independent of the Krylov tolerance: TOA value and monotone decrease along the beam
+    assert r1[3][0] == pytest.approx(sc["edirTOA"] * np.cos(np.deg2rad(sc["theta0"])), rel=1e-12)
+    assert r1[3].mean(axis=(1, 2))[-1] < r1[3].mean(axis=(1, 2))[0]
+    # idempotence: solving the same uid again starts from the stored solution (nonzero initial guess, the relative
+    # test is against the NEW initial residual, src/pprts.F90:4437-4486) and reproduces it
+    P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+    assert s.info(1)["niter_diff"] <= it1
+    r1b = P.pprts_get_result(s, 1)
+    for a, b in zip(r1b, r1):
+        assert relmax(a, b) < 1e-4
+    # linearity in the source: twice the sun, twice every flux (to the solver tolerance)
+    P.solve_pprts(s, False, True, 2 * sc["edirTOA"], 7)
+    r2 = P.pprts_get_result(s, 7)
+    assert relmax(r2[3], 2 * r1[3]) < 1e-12
+    for a, b in zip(r2[:3], r1[:3]):
+        assert relmax(a, 2 * b) < 2e-4
+    P.destroy_pprts(s)
+    # fp64 Krylov vectors, tight tolerance: the default-tolerance mixed result lies within the solver tolerance of it
+    s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], sd, dz1d=sc["dz1d"], lut=bench_lut, coeff_fp32=True,
+                     rtol=1e-9, atol=1e-30)
+    P.set_optical_properties(s, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+    P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+    rt = P.pprts_get_result(s, 1)
+    assert abs(closure(sc, rt) - 1) < 1e-7, closure(sc, rt)
+    for name, a, b in zip(("edn", "eup", "abso"), r1[:3], rt[:3]):
+        assert relmax(a, b) < 5e-4, name
+    P.destroy_pprts(s)
+
+
+def test_c2_thermal_properties(P, bench_lut):
+    """configs[1] thermal band: closure with emission, linearity in the Planck source, mixed vs fp64"""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field()
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
+    res = {}
+    for mixed, tol in ((True, {}), (False, dict(rtol=1e-9, atol=1e-30))):
+        s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], sd, dz1d=sc["dz1d"], lut=bench_lut, coeff_fp32=True,
+                         krylov_fp32=mixed, **tol)
+        P.set_optical_properties(s, sc["albedo_th"], sc["kabs_th"], sc["ksca_th"], sc["g_th"], planck=sc["planck"],
+                                 planck_srfc=sc["planck_srfc"])
+        P.solve_pprts(s, True, False, 0.0, 501)
+        res[mixed] = [a.copy() for a in P.pprts_get_result(s, 501)]
+        if mixed:
+            P.set_optical_properties(s, sc["albedo_th"], sc["kabs_th"], sc["ksca_th"], sc["g_th"],
+                                     planck=3 * sc["planck"], planck_srfc=3 * sc["planck_srfc"])
+            P.solve_pprts(s, True, False, 0.0, 502)
+            r3 = P.pprts_get_result(s, 502)
+            for a, b in zip(r3[:3], res[True][:3]):
+                assert relmax(a, 3 * b) < 2e-4
+        P.destroy_pprts(s)
+    edn, eup, abso, _ = res[False]
+    # net radiative balance of the domain: what the atmosphere absorbs net (abso < 0 = cooling) equals net flux convergence
+    net_in = (edn[0] - eup[0]).sum() - (edn[-1] - eup[-1]).sum()
+    assert abs((abso * sc["dz1d"][:, None, None]).sum() - net_in) < 1e-7 * edn[-1].sum()
+    for name, a, b in zip(("edn", "eup", "abso"), res[True][:3], res[False][:3]):
+        assert relmax(a, b) < 5e-4, name
+
+
+def test_c2_mirror_symmetry(P, bench_lut):
+    """tests/test_pprts_symmetry/test_pprts_symmetry.F90:393-521 at 256x256x80: the solve for (phi, field) and for
+    (phi + 180, field mirrored in x and y) are mirror images"""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field()
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    out = []
+    for phi0, flip in ((120., False), (300., True)):
+        s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(phi0, sc["theta0"]), dz1d=sc["dz1d"],
+                         lut=bench_lut, coeff_fp32=True, krylov_fp32=True, rtol=1e-7)
+        f = (lambda a: np.ascontiguousarray(a[:, ::-1, ::-1])) if flip else (lambda a: a)
+        P.set_optical_properties(s, sc["albedo"], f(sc["kabs"]), f(sc["ksca"]), f(sc["g"]))
+        P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+        out.append([f(a) for a in P.pprts_get_result(s, 1)])
+        P.destroy_pprts(s)
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), out[0], out[1]):
+        assert relmax(a, b) < 1e-4, name     # tables are mirror symmetric up to fp32 rounding; solves to rtol 1e-7
+
+
+def test_c3_shaped_band_loop(P, bench_lut):
+    """configs[2]-shaped: 512x512x100, a few pseudo g-points through solve_bands; the device-side spectral sum equals
+    the sum of the individual band solves, and every band closes its energy budget"""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field(Nx=512, Ny=512, Nz=100)
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    bands = [b for b in scenarios.spectral_bands(sc) if b["kind"] == "solar"][::45]      # 3 of the 112 solar g-points
+    s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]), dz1d=sc["dz1d"],
+                     lut=bench_lut, coeff_fp32=True, krylov_fp32=True, keep_solutions=False, rtol=1e-8, atol=1e-30)
+    kabs = np.stack([sc["kabs"] * b["scale"] for b in bands], axis=-1)
+    edirTOA = np.array([b["edirTOA"] for b in bands])
+    total = P.solve_bands(s, True, sc["albedo"], kabs, sc["ksca"], sc["g"], edirTOA=edirTOA)
+    acc = None
+    for ib, b in enumerate(bands):
+        P.set_optical_properties(s, sc["albedo"], kabs[..., ib], sc["ksca"], sc["g"])
+        P.solve_pprts(s, False, True, b["edirTOA"], b["uid"])
+        r = [a.copy() for a in P.pprts_get_result(s, b["uid"])]
+        assert abs(closure(sc, r) - 1) < 1e-6, (ib, closure(sc, r))
+        acc = r if acc is None else [x + y for x, y in zip(acc, r)]
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), total[:4], acc):
+        assert relmax(a, b) < 1e-6, name       # the band loop warm-starts from the previous band, the plain loop too
+    P.destroy_pprts(s)

@@ -64,6 +64,20 @@ def cloud_field(Nx=256, Ny=256, Nz=80, dx=100.0, dz=50.0, phi0=120.0, theta0=40.
                 planck_srfc=planck_srfc, albedo_th=0.02)
 
 
+def hill_field(Nx=256, Ny=256, Nz=80, **kw):
+    """C5: the cloud field over a Lorentzian hill in y (examples/pprts_hill/pprts_hill.F90:29-34), expressed as a 3-D
+    layer thickness: every layer of a column shrinks with the surface pressure drop dP(j) = dP0 / (1 + ((j - Ny/2) / w)^2),
+    theta0 = 40, phi0 = 180 (examples/pprts_hill/hill.sh:26)."""
+    kw.setdefault("phi0", 180.0)
+    kw.setdefault("theta0", 40.0)
+    sc = cloud_field(Nx=Nx, Ny=Ny, Nz=Nz, **kw)
+    j = np.arange(Ny)
+    dP = 0.30 / (1.0 + ((j - Ny / 2.0) / (Ny / 8.0)) ** 2)          # fraction of the surface pressure
+    sc["dz3d"] = np.ascontiguousarray(np.broadcast_to((sc["dz1d"][:, None, None] * (1.0 - dP)[None, None, :]),
+                                                      (Nz, Nx, Ny)))
+    return sc
+
+
 def spectral_bands(base, n_sw=112, n_lw=140):
     """C3: pseudo g-points on top of a cloud_field: kabs scaled by 10^(-3+4u), u = (b-1/2)/N; solar weights
     ~ exp(-3u) normalised (RRTMG counts: rrtmg/rrtm_sw/parrrsw.f90:36, rrtmg/rrtm_lw/parrrtm.f90:39)."""

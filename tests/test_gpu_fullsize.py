@@ -161,3 +161,34 @@ def test_c3_shaped_band_loop(P, bench_lut):
     for name, a, b in zip(("edn", "eup", "abso", "edir"), total[:4], acc):
         assert relmax(a, b) < 1e-6, name       # the band loop warm-starts from the previous band, the plain loop too
     P.destroy_pprts(s)
+
+
+@pytest.mark.parametrize("solver_id", [810, 324])
+def test_c5_hill_stream_variants(P, solver_id, capsys):
+    """configs[4]: hill topography (3-D layer thickness) at 256x256x80 with the 8_10 and 3_24 coefficient layouts:
+    energy closure of the solar band on the terrain-following grid, and the direct beam's TOA value"""
+    from tenstream_b200 import lut as L
+    from tenstream_b200 import scenarios
+    cfg = L.bench_config(solver_id)
+    base = os.path.join(os.environ.get("PPRTS_B200_LUT_DIR", "/tmp/pprts_b200_luts"), "LUT")
+    os.makedirs(os.path.dirname(base), exist_ok=True)
+    lut = P.Lut(cfg, L.write_synthetic_lut(cfg, base))
+    sc = scenarios.hill_field()
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]), dz3d=sc["dz3d"],
+                     lut=lut, solver=solver_id, coeff_fp32=True, krylov_fp32=True, rtol=1e-7, atol=1e-30)
+    P.set_optical_properties(s, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+    import time
+    t0 = time.time()
+    P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+    edn, eup, abso, edir = P.pprts_get_result(s, 1)
+    dt = time.time() - t0
+    info = s.info(1)
+    with capsys.disabled():
+        print(f"\n[c5] solver {solver_id}: {info['niter_diff']} Krylov iterations, {info['niter_dir']} edir passes, {dt:.2f} s")
+    inc = edir[0].sum() + edn[0].sum()
+    out = eup[0].sum() + (edir[-1].sum() + edn[-1].sum() - eup[-1].sum()) + (abso * sc["dz3d"]).sum()
+    assert abs(out / inc - 1) < 1e-5, out / inc
+    assert edir[0] == pytest.approx(sc["edirTOA"] * np.cos(np.deg2rad(sc["theta0"])), rel=1e-12)
+    P.destroy_pprts(s)
+    lut.close()

@@ -98,8 +98,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_workload(nx, ny, nz):
-    sc = scenarios.cloud_field(Nx=nx, Ny=ny, Nz=nz)
+def make_workload(nx, ny, nz, dx=100.0, dz=50.0):
+    sc = scenarios.cloud_field(Nx=nx, Ny=ny, Nz=nz, dx=dx, dz=dz)
     solar = dict(albedo=sc["albedo"], kabs=sc["kabs"], ksca=sc["ksca"], g=sc["g"], planck=None, planck_srfc=None,
                  edirTOA=sc["edirTOA"], lsolar=True, uid=1)
     thermal = dict(albedo=sc["albedo_th"], kabs=sc["kabs_th"], ksca=sc["ksca_th"], g=sc["g_th"], planck=sc["planck"],
@@ -134,7 +134,7 @@ def run_ours(args):
     cfg, paths = ensure_lut(rank)
     if world > 1:
         dist.barrier()
-    sc, bands = make_workload(args.nx, args.ny, args.nz)
+    sc, bands = make_workload(args.nx, args.ny, args.nz, args.dx, args.dz)
     Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
     ncell = Nz * Nx * Ny
     lut = P.Lut(cfg, paths)
@@ -150,7 +150,8 @@ def run_ours(args):
         Nx, Ny = dec.xm, dec.ym
         s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]),
                          dz1d=sc["dz1d"], lut=lut, device=local, keep_solutions=False, coeff_fp32=True,
-                         nxproc=dec.nxproc, nyproc=dec.nyproc, rank=rank, krylov_fp32=(args.krylov == "mixed"))
+                         nxproc=dec.nxproc, nyproc=dec.nyproc, rank=rank, krylov_fp32=(args.krylov == "mixed"),
+                         twostr_ratio=args.twostr_ratio)
         mixed = args.krylov == "mixed"   # fp32 Krylov vectors travel as fp32 halos
     else:
         mixed = args.krylov == "mixed"
@@ -277,7 +278,9 @@ def run_ours(args):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if decomp else "weak",
         "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pprts 3_10 solar+thermal, synthetic cloud field {args.nx}x{args.ny}x{Nz} (BASELINE configs[1])",
+        "config": {"workload": (f"pprts 3_10 solar+thermal, synthetic cloud field {args.nx}x{args.ny}x{Nz} " +
+                                ("(BASELINE configs[1])" if (args.nx, args.ny, Nz) == (256, 256, 80) else
+                                 f"dx={args.dx:g} m dz={args.dz:g} m (BASELINE configs[3]-shaped)" if decomp else "")),
                    "bands_per_step_per_gpu": len(bands), "cells": ncell, "coefficient_storage": "fp32",
                    "state": ("fp64 solution + fp64 true residual (iterative refinement), fp32 Krylov work vectors"
                              if mixed else "fp64"), "tolerances": "reference defaults rtol=1e-5 atol=1e-4*Nx*Ny*(Nz+1)",
@@ -412,6 +415,9 @@ def main():
     ap.add_argument("--nx", type=int, default=256)
     ap.add_argument("--ny", type=int, default=256)
     ap.add_argument("--nz", type=int, default=80)
+    ap.add_argument("--dx", type=float, default=100.0, help="horizontal grid spacing [m] (C4: 25)")
+    ap.add_argument("--dz", type=float, default=50.0, help="layer thickness [m] (C4: 25)")
+    ap.add_argument("--twostr-ratio", type=float, default=2.0, help="-twostr_ratio of the reference (C4: 3), --decomp runs")
     ap.add_argument("--cpu-nx", type=int, default=48)
     ap.add_argument("--cpu-ny", type=int, default=48)
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: replicas run side by side (0 = host threads)")

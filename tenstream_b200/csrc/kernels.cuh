@@ -1166,6 +1166,282 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
 }
 
 // =================================================================================================================
+// Block variant of the column preconditioner for layouts with NP = Nft/2 > 1 up/down pairs of top streams (3_24:
+// NP = 4).  Same adding-method recurrence with NP x NP matrices:
+//   Inv_k = (I - Tud R_{k+1})^-1,  R_k = Tdu + Tuu R_{k+1} Inv_k Tdd,  S_k = f_U + Tuu (S_{k+1} + R_{k+1} Inv_k (Tud S_{k+1} + f_D))
+//   D_{k+1} = Inv_k (Tdd D_k + Tud S_{k+1} + f_D),  U_{k+1} = R_{k+1} D_{k+1} + S_{k+1}
+// with Txy(a,b) the coefficient from top stream pair b, direction x, to pair a, direction y.  The surface couples
+// inv_dof pairs with the full albedo (src/pprts_shell.F90:500-505), so R_Nz = albedo I.  R and Inv are stored as
+// NP*NP planes; arithmetic is fp64 whatever the vector type (the kernels are bound by the coefficient loads).
+// =================================================================================================================
+template <class L, class CT, int NP>
+__device__ __forceinline__ void precb_top_blocks(const Grid &g, int n1d, int k, long c, const CT *__restrict__ T,
+                                                 const double *__restrict__ a11, const double *__restrict__ a12,
+                                                 bool need_uu, bool need_du, bool need_ud, bool need_dd,
+                                                 double (&tuu)[NP][NP], double (&tdu)[NP][NP], double (&tud)[NP][NP],
+                                                 double (&tdd)[NP][NP]) {
+  constexpr int Nf = L::Nf;
+  if (k < n1d) {
+    const double t = a11[c], r = a12[c];
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        tuu[a][b] = tdd[a][b] = (a == b) ? t : 0.0;
+        tdu[a][b] = tud[a][b] = (a == b) ? r : 0.0;
+      }
+  } else {
+    const long cb = cbase<Nf * Nf>(c);
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        if (need_uu) tuu[a][b] = (double)T[cb + ((2 * a) * Nf + 2 * b) * PB_TILE];
+        if (need_du) tdu[a][b] = (double)T[cb + ((2 * a) * Nf + 2 * b + 1) * PB_TILE];
+        if (need_ud) tud[a][b] = (double)T[cb + ((2 * a + 1) * Nf + 2 * b) * PB_TILE];
+        if (need_dd) tdd[a][b] = (double)T[cb + ((2 * a + 1) * Nf + 2 * b + 1) * PB_TILE];
+      }
+  }
+}
+template <int NP>
+__device__ __forceinline__ void precb_matvec(const double (&M)[NP][NP], const double (&x)[NP], double (&y)[NP]) {
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    double acc = 0.0;
+#pragma unroll
+    for (int b = 0; b < NP; ++b) acc = fma(M[a][b], x[b], acc);
+    y[a] = acc;
+  }
+}
+template <int NP, class PT>
+__device__ __forceinline__ void precb_load_mat(const PT *__restrict__ p, long stride, long l, double (&M)[NP][NP]) {
+#pragma unroll
+  for (int a = 0; a < NP; ++a)
+#pragma unroll
+    for (int b = 0; b < NP; ++b) M[a][b] = (double)p[(long)(a * NP + b) * stride + l];
+}
+
+template <class L, class CT>
+__global__ void __launch_bounds__(PREC_BLOCK)
+k_precb_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
+              const double *__restrict__ a12, const double *__restrict__ albedo, double *__restrict__ R,
+              double *__restrict__ inv, float *__restrict__ Rf, float *__restrict__ invf) {
+  constexpr int NP = L::Nft / 2;
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.ncol) return;
+  double Rn[NP][NP];
+  const double alb = albedo[col];
+#pragma unroll
+  for (int a = 0; a < NP; ++a)
+#pragma unroll
+    for (int b = 0; b < NP; ++b) {
+      Rn[a][b] = (a == b) ? alb : 0.0;
+      R[(long)(a * NP + b) * g.nlev + (long)g.Nz * g.ncol + col] = Rn[a][b];
+      Rf[(long)(a * NP + b) * g.nlev + (long)g.Nz * g.ncol + col] = (float)Rn[a][b];  // fp32 copies for the fp32 sweeps
+    }
+  for (int k = g.Nz - 1; k >= 0; --k) {
+    const long c = (long)k * g.ncol + col;
+    double tuu[NP][NP], tdu[NP][NP], tud[NP][NP], tdd[NP][NP];
+    precb_top_blocks<L, CT, NP>(g, n1d, k, c, T, a11, a12, true, true, true, true, tuu, tdu, tud, tdd);
+    // A = I - Tud Rn, inverted by Gauss-Jordan (no pivoting: ||Tud Rn|| < 1, A is strictly diagonally dominant enough)
+    double A[NP][NP], Iv[NP][NP];
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        double acc = (a == b) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc = fma(-tud[a][q], Rn[q][b], acc);
+        A[a][b] = acc;
+        Iv[a][b] = (a == b) ? 1.0 : 0.0;
+      }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double ip = 1.0 / A[p][p];
+#pragma unroll
+      for (int b = 0; b < NP; ++b) { A[p][b] *= ip; Iv[p][b] *= ip; }
+#pragma unroll
+      for (int a = 0; a < NP; ++a) {
+        if (a == p) continue;
+        const double f = A[a][p];
+#pragma unroll
+        for (int b = 0; b < NP; ++b) { A[a][b] = fma(-f, A[p][b], A[a][b]); Iv[a][b] = fma(-f, Iv[p][b], Iv[a][b]); }
+      }
+    }
+    // G = Rn Iv Tdd ; R_k = Tdu + Tuu G
+    double G[NP][NP], H[NP][NP];
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc = fma(Iv[a][q], tdd[q][b], acc);
+        H[a][b] = acc;
+      }
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc = fma(Rn[a][q], H[q][b], acc);
+        G[a][b] = acc;
+      }
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        double acc = tdu[a][b];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc = fma(tuu[a][q], G[q][b], acc);
+        H[a][b] = acc;
+      }
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        Rn[a][b] = H[a][b];
+        inv[(long)(a * NP + b) * g.ncell + c] = Iv[a][b];
+        R[(long)(a * NP + b) * g.nlev + c] = Rn[a][b];
+        invf[(long)(a * NP + b) * g.ncell + c] = (float)Iv[a][b];
+        Rf[(long)(a * NP + b) * g.nlev + c] = (float)Rn[a][b];
+      }
+  }
+}
+
+// upward sweep: z_U(k) <- S_k, z_D(k+1) <- f_D, inward side dofs copied (all side dofs in 1-D layers)
+// 32-thread blocks, 14 per SM: 148 x 448 = 66 304 resident columns, so 256 x 256 columns run in ONE wave (the sweeps are
+// one dependent chain per column: two waves would double their run time)
+#define PRECB_BLOCK 32
+template <class L, class CT, class VT>
+__global__ void __launch_bounds__(PRECB_BLOCK, 14)
+k_precb_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
+           const VT *__restrict__ R, const VT *__restrict__ inv, const VT *__restrict__ r,
+           VT *__restrict__ z, int sides) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs, NP = Nft / 2;
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.ncol) return;
+  const long lz = (long)g.Nz * g.ncol + col;
+  double S[NP];
+#pragma unroll
+  for (int a = 0; a < NP; ++a) { S[a] = (double)r[(long)(2 * a) * g.nlev + lz]; z[(long)(2 * a) * g.nlev + lz] = (VT)S[a]; }
+#pragma unroll
+  for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + lz] = r[(long)d * g.nlev + lz];
+  for (int k = g.Nz - 1; k >= 0; --k) {
+    const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+    double fU[NP], fD[NP];
+#pragma unroll
+    for (int a = 0; a < NP; ++a) { fU[a] = (double)r[(long)(2 * a) * g.nlev + c]; fD[a] = (double)r[(long)(2 * a + 1) * g.nlev + l1]; }
+    if (k < n1d) {
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = r[(long)(Nft + d) * g.nlev + c];
+    } else {
+      const long cb = cbase<Nf * Nf>(c);
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        if (!L::side_in(d % Nfs)) continue;
+        const VT rv = r[(long)(Nft + d) * g.nlev + c];
+        z[(long)(Nft + d) * g.nlev + c] = rv;
+        if (sides) {
+          const double rs = (double)rv;
+#pragma unroll
+          for (int a = 0; a < NP; ++a) {
+            fU[a] = fma((double)T[cb + ((2 * a) * Nf + Nft + d) * PB_TILE], rs, fU[a]);
+            fD[a] = fma((double)T[cb + ((2 * a + 1) * Nf + Nft + d) * PB_TILE], rs, fD[a]);
+          }
+        }
+      }
+    }
+    double tuu[NP][NP], tdu[NP][NP], tud[NP][NP], tdd[NP][NP], M[NP][NP];
+    precb_top_blocks<L, CT, NP>(g, n1d, k, c, T, a11, a12, true, false, true, false, tuu, tdu, tud, tdd);
+    double w[NP], y[NP];
+    precb_matvec<NP>(tud, S, w);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) w[a] += fD[a];
+    precb_load_mat<NP, VT>(inv, g.ncell, c, M);
+    precb_matvec<NP>(M, w, y);
+    precb_load_mat<NP, VT>(R, g.nlev, l1, M);
+    precb_matvec<NP>(M, y, w);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) w[a] += S[a];
+    precb_matvec<NP>(tuu, w, y);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      S[a] = fU[a] + y[a];
+      z[(long)(2 * a) * g.nlev + c] = (VT)S[a];
+      z[(long)(2 * a + 1) * g.nlev + l1] = (VT)fD[a];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NP; ++a) z[(long)(2 * a + 1) * g.nlev + col] = r[(long)(2 * a + 1) * g.nlev + col];  // f_D(0) = r_D(0)
+}
+
+template <class L, class CT, class VT>
+__global__ void __launch_bounds__(PRECB_BLOCK, 14)
+k_precb_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
+             const VT *__restrict__ R, const VT *__restrict__ inv, const VT *__restrict__ r, VT *z, int sides) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs, NP = Nft / 2;
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.ncol) return;
+  double D[NP], U[NP], M[NP][NP];
+#pragma unroll
+  for (int a = 0; a < NP; ++a) D[a] = (double)z[(long)(2 * a + 1) * g.nlev + col];
+  precb_load_mat<NP, VT>(R, g.nlev, col, M);
+  precb_matvec<NP>(M, D, U);
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    U[a] += (double)z[(long)(2 * a) * g.nlev + col];
+    z[(long)(2 * a) * g.nlev + col] = (VT)U[a];
+  }
+  for (int k = 0; k < g.Nz; ++k) {
+    const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+    double S1[NP], w[NP], y[NP], D1[NP], U1[NP];
+    double tuu[NP][NP], tdu[NP][NP], tud[NP][NP], tdd[NP][NP];
+    precb_top_blocks<L, CT, NP>(g, n1d, k, c, T, a11, a12, false, false, true, true, tuu, tdu, tud, tdd);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) S1[a] = (double)z[(long)(2 * a) * g.nlev + l1];
+    precb_matvec<NP>(tdd, D, w);
+    precb_matvec<NP>(tud, S1, y);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) w[a] += y[a] + (double)z[(long)(2 * a + 1) * g.nlev + l1];
+    precb_load_mat<NP, VT>(inv, g.ncell, c, M);
+    precb_matvec<NP>(M, w, D1);
+    precb_load_mat<NP, VT>(R, g.nlev, l1, M);
+    precb_matvec<NP>(M, D1, U1);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) U1[a] += S1[a];
+    if (k >= n1d) {  // outgoing side streams through the column's own faces
+      const long cb = cbase<Nf * Nf>(c);
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        if (L::side_in(d % Nfs)) continue;
+        const int dof = Nft + d;
+        double acc = (double)r[(long)dof * g.nlev + c];
+        if (sides) {
+#pragma unroll
+          for (int b = 0; b < NP; ++b) {
+            acc = fma((double)T[cb + (dof * Nf + 2 * b) * PB_TILE], U1[b], acc);
+            acc = fma((double)T[cb + (dof * Nf + 2 * b + 1) * PB_TILE], D[b], acc);
+          }
+#pragma unroll
+          for (int q = 0; q < 2 * Nfs; ++q)
+            if (L::side_in(q % Nfs))
+              acc = fma((double)T[cb + (dof * Nf + Nft + q) * PB_TILE], (double)r[(long)(Nft + q) * g.nlev + c], acc);
+        }
+        z[(long)dof * g.nlev + c] = (VT)acc;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      z[(long)(2 * a) * g.nlev + l1] = (VT)U1[a];
+      z[(long)(2 * a + 1) * g.nlev + l1] = (VT)D1[a];
+      D[a] = D1[a];
+    }
+  }
+}
+
+// =================================================================================================================
 // BiCGStab vector kernels.  Scalars live in device memory (sc[]); every kernel derives alpha/beta/omega from the raw
 // dot products itself, the last block of the reducing kernels rotates them -> no host round trip inside an iteration
 // except the convergence read.

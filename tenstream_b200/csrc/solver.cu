@@ -222,6 +222,7 @@ struct pprts_b200_solver {
   int mm_variant = 2;  // 0: 2 stages + register prefetch, 1: 2 stages, 2: 1 stage x 4 CTAs/SM (fastest measured)
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
+  float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the block (3_24) sweeps on fp32 vectors
   bool prec_ready = false;
   int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
@@ -629,7 +630,12 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
     const size_t hx = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Ny, hy = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Nx;
     DA(s->hs[0], hx); DA(s->hr[0], hx); DA(s->hs[1], hy); DA(s->hr[1], hy);
   }
-  DA(s->precR, g.nlev); DA(s->precInv, g.ncell);
+  {
+    int np = 1;  // up/down pairs of top streams: the column preconditioner keeps np x np matrices per level
+    DISPATCH_L(s, np = L::Nft / 2);
+    DA(s->precR, (size_t)np * np * g.nlev); DA(s->precInv, (size_t)np * np * g.ncell);
+    if (np > 1) { DA(s->precRf, (size_t)np * np * g.nlev); DA(s->precInvf, (size_t)np * np * g.ncell); }
+  }
   for (int q = 0; q < 4; ++q) { DA(s->res[q], g.nlev); DA(s->acc[q], g.nlev); }
   DA(s->out_stage, (size_t)std::max(Nd, Nf) * g.nlev);
   DA(s->partials, (size_t)4 * (nblk(g.ncell, 128) + 148 * 16 + 64));
@@ -673,6 +679,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
                     s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
+  cudaFree(s->precRf); cudaFree(s->precInvf);
   cudaFree(s->bld_iface); cudaFree(s->bld_albedo); cudaFree(s->bld_planck); cudaFree(s->bld_out);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
   cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
@@ -997,7 +1004,7 @@ static int launch_matmult(pprts_b200_solver *s, VT *x, VT *y, const VT *w, doubl
   return rc;
 }
 
-static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond >= 1 && s->cfg.solver_id != 324; }
+static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond >= 1; }
 
 // Column kernels are one thread per column and latency-bound per thread, so their run time is (number of waves) x
 // (time of one column): pick the block size (<= PREC_BLOCK) for which all columns are resident in the fewest waves.
@@ -1034,6 +1041,19 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
            s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
     LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
+  } else {  // several up/down pairs of top streams (3_24): block recurrence, no software pipelining
+    const Grid &g = s->g;
+    if (!s->prec_ready) {
+      LAUNCH(s, FAM_PRECOND, (k_precb_setup<L, CT>), nblk(g.ncol, 32), 32, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+             s->albedo, s->precR, s->precInv, s->precRf, s->precInvf);
+      s->prec_ready = true;
+    }
+    const VT *pR, *pI;
+    if constexpr (std::is_same<VT, float>::value) { pR = s->precRf; pI = s->precInvf; } else { pR = s->precR; pI = s->precInv; }
+    LAUNCH(s, FAM_PRECOND, (k_precb_up<L, CT, VT>), nblk(g.ncol, PRECB_BLOCK), PRECB_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+           pR, pI, r, z, (int)(s->cfg.precond != 2));
+    LAUNCH(s, FAM_PRECOND, (k_precb_down<L, CT, VT>), nblk(g.ncol, PRECB_BLOCK), PRECB_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+           pR, pI, r, z, (int)(s->cfg.precond != 2));
   }
 }
 static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, (launch_prec_t<L, CT, double>(s, r, z))); }

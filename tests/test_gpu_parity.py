@@ -590,7 +590,7 @@ def test_mixed_precision_default_tolerances_match_fp64_vectors(P, gpu_lut):
 
 
 # ---- committed golden vectors (no oracle in the loop) -------------------------------------------------------------
-@pytest.mark.parametrize("name", ["s310_a", "s310_b", "s310_c", "s810_a", "s324_a"])
+@pytest.mark.parametrize("name", ["s310_a", "s310_b", "s310_c", "s810_a", "s324_a", "s310_bld", "s310_col"])
 def test_gpu_vs_committed_golden(P, tmp_path, name):
     """tests/golden/pprts_cases.npz: fluxes and absorption of five small cases (3_10 incl. an all-1-D atmosphere,
     8_10, 3_24; solar and thermal), frozen from the oracle by tests/golden/make_golden.py.  Tolerance 1e-5 relative
@@ -603,21 +603,34 @@ def test_gpu_vs_committed_golden(P, tmp_path, name):
     spec.loader.exec_module(mg)
     from tenstream_b200 import lut as L
     golden = np.load(os.path.join(here, "golden", "pprts_cases.npz"))
-    sid, seed, (Nz, Nx, Ny), dz, phi0, theta0, albedo, ratio = mg.CASES[name]
+    sid, seed, (Nz, Nx, Ny), dz, phi0, theta0, albedo, ratio = mg.CASES[name][:8]
     cfg = L.small_test_config(sid)
     lut = P.Lut(cfg, L.write_synthetic_lut(cfg, str(tmp_path / f"LUT{sid}")))
     kabs, ksca, g = mg.atmosphere(seed, Nz, Nx, Ny)
-    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(phi0, theta0), solver=sid, dz1d=np.full(Nz, dz),
-                     lut=lut, coeff_fp32=False, rtol=1e-11, atol=1e-30, twostr_ratio=ratio)
+    dz1d, ci = mg.case_dz(name)
+    bld = mg.case_buildings(name)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(phi0, theta0), solver=sid, dz1d=dz1d,
+                     lut=lut, coeff_fp32=False, rtol=1e-11, atol=1e-30, twostr_ratio=ratio, collapseindex=ci)
     P.set_optical_properties(s, albedo, kabs, ksca, g)
-    P.solve_pprts(s, False, True, 1364.)
-    for nm, a in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s)):
+    if bld is not None:
+        pl, bld.planck = bld.planck, None
+    P.solve_pprts(s, False, True, 1364., opt_buildings=bld)
+    for nm, a in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s, opt_buildings=bld)):
         assert relerr(a, golden[f"{name}/solar/{nm}"]) < 1e-5, nm
+    if bld is not None:
+        for nm, a in zip(("bld_edir", "bld_incoming", "bld_outgoing"), (bld.edir, bld.incoming, bld.outgoing)):
+            b = golden[f"{name}/solar/{nm}"]
+            assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), nm
+        bld.planck = pl
     planck = np.broadcast_to(np.linspace(60., 120., Nz + 1)[:, None, None], (Nz + 1, Nx, Ny)).copy()
     P.set_optical_properties(s, albedo / 4, kabs * 5, ksca, g, planck=planck, planck_srfc=np.full((Nx, Ny), 130.))
-    P.solve_pprts(s, True, False, 0., 3)
-    for nm, a in zip(("edn", "eup", "abso"), P.pprts_get_result(s, 3)):
+    P.solve_pprts(s, True, False, 0., 3, opt_buildings=bld)
+    for nm, a in zip(("edn", "eup", "abso"), P.pprts_get_result(s, 3, opt_buildings=bld)):
         assert relerr(a, golden[f"{name}/thermal/{nm}"]) < 1e-5, nm
+    if bld is not None:
+        for nm, a in zip(("bld_incoming", "bld_outgoing"), (bld.incoming, bld.outgoing)):
+            b = golden[f"{name}/thermal/{nm}"]
+            assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), nm
     P.destroy_pprts(s); lut.close()
 
 

@@ -12,7 +12,7 @@ module m_pprts_b200
   implicit none
   private
   public :: t_solver_b200, t_lut_b200, lut_open, lut_close, init_pprts, set_angles, set_optical_properties, &
-    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200
+    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200, need_new_solution
 
   integer, parameter :: ireals = c_double, iintegers = c_int
 
@@ -43,6 +43,7 @@ module m_pprts_b200
     real(c_double) :: rtol, atol
     integer(c_int) :: maxit_dir, maxit_diff, precond, device, keep_solutions, nxproc, nyproc, xrank, yrank, &
       & diff_explicit, krylov_fp32, collapseindex
+    real(c_double) :: max_solution_err, max_solution_time
   end type
 
   interface
@@ -95,6 +96,19 @@ module m_pprts_b200
       import; type(c_ptr), value :: solver
       integer(c_int), value :: nranks, rank
       character(kind=c_char), intent(in) :: id(128)
+    end function
+    integer(c_int) function c_solve_at_time(solver, lthermal, lsolar, edirTOA, uid, time) bind(c, name='pprts_b200_solve_at_time')
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: solver
+      integer(c_int), value :: lthermal, lsolar, uid
+      real(c_double), value :: edirTOA, time
+    end function
+    integer(c_int) function c_need_new_solution(solver, uid, time, have_time, need) bind(c, name='pprts_b200_need_new_solution')
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: solver
+      integer(c_int), value :: uid, have_time
+      real(c_double), value :: time
+      integer(c_int), intent(out) :: need
     end function
     integer(c_int) function c_set_buildings(solver, nfaces, iface, albedo, planck) bind(c, name='pprts_b200_set_buildings')
       import :: c_ptr, c_int
@@ -212,11 +226,12 @@ contains
   end subroutine
 
   !> solve_pprts (src/pprts.F90:2487)
-  subroutine solve_pprts(solver, lthermal, lsolar, edirTOA, opt_solution_uid, opt_buildings)
+  subroutine solve_pprts(solver, lthermal, lsolar, edirTOA, opt_solution_uid, opt_solution_time, opt_buildings)
     type(t_solver_b200), intent(inout) :: solver
     logical, intent(in) :: lthermal, lsolar
     real(ireals), intent(in) :: edirTOA
     integer(iintegers), intent(in), optional :: opt_solution_uid
+    real(ireals), intent(in), optional :: opt_solution_time
     type(t_pprts_buildings_b200), intent(in), target, optional :: opt_buildings
     integer(c_int) :: uid
     type(c_ptr) :: ppl
@@ -229,8 +244,28 @@ contains
     else
       call chkerr(c_set_buildings(solver%h, 0_c_int, c_null_ptr, c_null_ptr, c_null_ptr), 'solve_pprts')
     end if
-    call chkerr(c_solve(solver%h, merge(1, 0, lthermal), merge(1, 0, lsolar), edirTOA, uid), 'solve_pprts')
+    if (present(opt_solution_time)) then
+      call chkerr(c_solve_at_time(solver%h, merge(1, 0, lthermal), merge(1, 0, lsolar), edirTOA, uid, opt_solution_time), &
+        & 'solve_pprts')
+    else
+      call chkerr(c_solve(solver%h, merge(1, 0, lthermal), merge(1, 0, lsolar), edirTOA, uid), 'solve_pprts')
+    end if
   end subroutine
+
+  !> need_new_solution (src/adaptive_spectral_integration.F90:38): the band loops' test before every solve
+  !> (rrtmg/rrtmg/pprts_rrtmg.F90:1001); the solution is addressed by its uid instead of solver%solutions(uid)
+  logical function need_new_solution(solver, uid, time)
+    type(t_solver_b200), intent(in) :: solver
+    integer(iintegers), intent(in) :: uid
+    real(ireals), intent(in), optional :: time
+    integer(c_int) :: need
+    if (present(time)) then
+      call chkerr(c_need_new_solution(solver%h, uid, time, 1_c_int, need), 'need_new_solution')
+    else
+      call chkerr(c_need_new_solution(solver%h, uid, 0._c_double, 0_c_int, need), 'need_new_solution')
+    end if
+    need_new_solution = need .ne. 0
+  end function
 
   !> pprts_get_result (src/pprts.F90:5799): allocates the outputs if needed, like the reference
   subroutine pprts_get_result(solver, redn, reup, rabso, redir, opt_solution_uid, opt_buildings)

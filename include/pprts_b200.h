@@ -102,13 +102,17 @@ typedef struct {
   int diff_explicit;
   /* 1: mixed-precision Krylov solve -- fp32 work vectors inside BiCGStab, fp64 solution and fp64 true residual with
    * iterative refinement (the convergence test is always evaluated on an fp64 residual).  Halves the vector traffic
-   * of the iteration.  Single-domain runs only (a decomposed run keeps fp64 vectors). Default 0. */
+   * of the iteration; on a decomposed solver the halos travel as fp32 too.  Default 0. */
   int krylov_fp32;
   /* init_pprts collapseindex (src/pprts.F90:692-706, handle_atm_collapse :2080-2198): > 1 merges the top
    * `collapseindex` atmosphere layers (forced 1-D) into ONE 1-D layer by the adding method; Nz, dz and all optical
    * property arrays are then on the ATMOSPHERE grid (Nz layers) while the solver grid and every result array have
    * Nz - collapseindex + 1 layers.  <= 1: off. */
   int collapseindex;
+  /* error-growth tracking of stored solutions (src/adaptive_spectral_integration.F90): -max_solution_err [W]
+   * (default 5e3/86400, src/tenstream_options.F90:90) and -max_solution_time [s] (default 0).  Both > 0 enables
+   * lenable_solutions_err_estimates (src/pprts.F90:456-457). */
+  double max_solution_err, max_solution_time;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);
@@ -125,6 +129,16 @@ int pprts_b200_set_optical_properties(pprts_b200_solver *solver, double albedo, 
                                       const double *planck_srfc, const double *albedo_2d, int ldelta_scaling);
 /* solve_pprts (src/pprts.F90:2487-2665). uid in [-1000, 1000]. */
 int pprts_b200_solve(pprts_b200_solver *solver, int lthermal, int lsolar, double edirTOA, int uid);
+/* solve_pprts(..., opt_solution_time = time) (src/pprts.F90:2487-2493, restore_solution :3991-4049): as
+ * pprts_b200_solve, and records `time` and -- with the error estimates enabled -- the inf-norm of the change of the
+ * absorption in the solution's history */
+int pprts_b200_solve_at_time(pprts_b200_solver *solver, int lthermal, int lsolar, double edirTOA, int uid, double time);
+/* need_new_solution(comm, solver%solutions(uid), time, solver%lenable_solutions_err_estimates)
+ * (src/adaptive_spectral_integration.F90:38-172), the test the band loops make before every solve
+ * (rrtmg/rrtmg/pprts_rrtmg.F90:623, :1001).  have_time = 0: `time` not present.  *need: 1 = solve again. */
+int pprts_b200_need_new_solution(pprts_b200_solver *solver, int uid, double time, int have_time, int *need);
+/* solution%time(30), solution%maxnorm(30) (src/pprts_base.F90:161-162), newest first */
+int pprts_b200_get_solution_times(pprts_b200_solver *solver, int uid, double time[30], double maxnorm[30]);
 /* pprts_get_result (src/pprts.F90:5799-5917): caller-allocated, edir may be NULL */
 int pprts_b200_get_result(pprts_b200_solver *solver, int uid, double *edn, double *eup, double *abso,
                           double *edir);

@@ -47,7 +47,8 @@ class _Config(C.Structure):
                 ("dx", C.c_double), ("dy", C.c_double), ("dz", c_double_p), ("sundir", C.c_double * 3),
                 ("twostr_ratio", C.c_double), ("coeff_fp32", C.c_int), ("by_coeff_divergence", C.c_int),
                 ("diff_solver", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
-                ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("nthreads", C.c_int), ("collapseindex", C.c_int)]
+                ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("nthreads", C.c_int), ("collapseindex", C.c_int),
+                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double)]
 
 
 _lib = None
@@ -98,6 +99,10 @@ def lib():
         L.orc_get_suninfo.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]
         L.orc_mat_mult_ediff.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.orc_scale_flx_arr.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_int]
+        L.orc_solve_t.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+        L.orc_need_new_solution.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.orc_polyfit.argtypes = [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
+        L.orc_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
         L.orc_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, c_double_p, c_double_p]
         L.orc_get_buildings_result.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
         _lib = L
@@ -226,7 +231,8 @@ class OracleSolver:
 
     def __init__(self, lut: OracleLut, Nz, Nx, Ny, dx, dy, sundir, dz, solver_id=310, twostr_ratio=2.0,
                  coeff_fp32=False, by_coeff_divergence=True, diff_solver=0, rtol=-1.0, atol=-1.0,
-                 maxit_dir=0, maxit_diff=0, nthreads=0, collapseindex=1):
+                 maxit_dir=0, maxit_diff=0, nthreads=0, collapseindex=1, max_solution_err=5e3 / 86400.,
+                 max_solution_time=0.0):
         self.lut = lut
         ci = max(1, int(collapseindex))
         self.Nz_atm = Nz
@@ -237,7 +243,7 @@ class OracleSolver:
         self._dz = f_order(dz)
         cfg = _Config(solver_id, Nz, Nx, Ny, dx, dy, _dp(self._dz), (C.c_double * 3)(*sundir), twostr_ratio,
                       int(coeff_fp32), int(by_coeff_divergence), diff_solver, rtol, atol, maxit_dir, maxit_diff,
-                      nthreads, ci)
+                      nthreads, ci, max_solution_err, max_solution_time)
         self._h = lib().orc_solver_create(C.byref(cfg), C.byref(lut._lut))
         if not self._h:
             raise RuntimeError("orc_solver_create failed")
@@ -254,8 +260,19 @@ class OracleSolver:
         if rc:
             raise ValueError(f"set_optical_properties: illegal optical properties ({rc})")
 
-    def solve(self, lthermal, lsolar, edirTOA, uid=0):
+    def solve(self, lthermal, lsolar, edirTOA, uid=0, time=None):
+        if time is not None:   # solve_pprts(..., opt_solution_time=time)
+            return lib().orc_solve_t(self._h, int(lthermal), int(lsolar), float(edirTOA), uid, float(time))
         return lib().orc_solve(self._h, int(lthermal), int(lsolar), float(edirTOA), uid)
+
+    def need_new_solution(self, uid, time=None):
+        """need_new_solution(comm, solver%solutions(uid), time, lenable) (src/adaptive_spectral_integration.F90:38)"""
+        return bool(lib().orc_need_new_solution(self._h, uid, 0.0 if time is None else float(time), int(time is not None)))
+
+    def solution_times(self, uid):
+        t, m = np.zeros(30), np.zeros(30)
+        lib().orc_get_solution_times(self._h, uid, _dp(t), _dp(m))
+        return t, m
 
     def get_result(self, uid=0):
         Nz, Nx, Ny = self.Nz, self.Nx, self.Ny
@@ -341,6 +358,14 @@ class OracleSolver:
             self.destroy()
         except Exception:
             pass
+
+
+def polyfit(vx, vy, d):
+    vx = np.ascontiguousarray(vx, dtype=np.float64)
+    vy = np.ascontiguousarray(vy, dtype=np.float64)
+    out = np.zeros(d + 1)
+    ierr = lib().orc_polyfit(_dp(vx), _dp(vy), len(vx), d, _dp(out))
+    return out, ierr
 
 
 def sundir_from_angles(phi0, theta0):

@@ -489,11 +489,13 @@ int orc_get_coeff(const orc_lut *lut, const orc_streams *st, double kabs, double
 #define ORC_UID_MIN (-1000)
 #define ORC_UID_MAX (1000)
 #define ORC_NHIST 100
+#define ORC_NTIME 30
 
 typedef struct {
   int lset, lsolar_rad, lthermal_rad, lchanged, lWm2_dir, lWm2_diff;
   double *edir, *ediff, *abso; /* interior (dof, Nz+1, Nx, Ny) / (Nz,Nx,Ny) */
   double dir_hist[ORC_NHIST], diff_hist[ORC_NHIST];
+  double time[ORC_NTIME], maxnorm[ORC_NTIME]; /* error-growth tracking, src/pprts_base.F90:161-162 */
   int Niter_dir, Niter_diff;
   double final_res_dir, final_res_diff;
   double diff_sor_omega;
@@ -1616,11 +1618,97 @@ static orc_solution *prepare_solution(orc_solver *s, int lsolar, int lthermal) {
   sol->ediff = (double *)calloc(nin(s, s->st.Nf), sizeof(double));
   sol->abso = (double *)calloc((long)s->Nz * s->Nx * s->Ny, sizeof(double));
   for (h = 0; h < ORC_NHIST; ++h) { sol->dir_hist[h] = -1; sol->diff_hist[h] = -1; }
+  for (h = 0; h < ORC_NTIME; ++h) { sol->time[h] = -1.0; sol->maxnorm[h] = 0.0; }
   sol->diff_sor_omega = -1;
   return sol;
 }
 
+/* ---- error-growth tracking (src/adaptive_spectral_integration.F90, restore_solution src/pprts.F90:3991-4049) ------ */
+/* polyfit :174-257: least squares through the normal equations, (X^T X)^-1 by LU with partial pivoting (LAPACK
+ * dgetrf + dgetri there), coefficients = ((X^T X)^-1 X^T) y.  ierr 1: two equal abscissae, 2: singular. */
+int orc_polyfit(const double *vx, const double *vy, int n, int d, double *coef) {
+  double X[16][4], XTX[4][4], inv[4][4], M[4][16];
+  int i, j, k, m = d + 1, p;
+  if (n > 16 || m > 4) return 9;
+  for (i = 0; i < n; ++i) for (j = i + 1; j < n; ++j) if (approx_d(vx[i], vx[j])) {
+    for (k = 0; k < m; ++k) coef[k] = 0.0;
+    coef[0] = -9999999.0; /* nil */
+    return 1;
+  }
+  for (i = 0; i < m; ++i) for (j = 0; j < n; ++j) X[j][i] = pow(vx[j], (double)i);
+  for (i = 0; i < m; ++i) for (j = 0; j < m; ++j) {
+    double acc = 0; for (k = 0; k < n; ++k) acc += X[k][i] * X[k][j];
+    XTX[i][j] = acc; inv[i][j] = (i == j) ? 1.0 : 0.0;
+  }
+  for (p = 0; p < m; ++p) { /* Gauss-Jordan with partial pivoting */
+    int piv = p; double best = fabs(XTX[p][p]), ip;
+    for (i = p + 1; i < m; ++i) if (fabs(XTX[i][p]) > best) { best = fabs(XTX[i][p]); piv = i; }
+    if (best == 0.0) return 2;
+    if (piv != p) for (j = 0; j < m; ++j) {
+      double t = XTX[p][j]; XTX[p][j] = XTX[piv][j]; XTX[piv][j] = t;
+      t = inv[p][j]; inv[p][j] = inv[piv][j]; inv[piv][j] = t;
+    }
+    ip = 1.0 / XTX[p][p];
+    for (j = 0; j < m; ++j) { XTX[p][j] *= ip; inv[p][j] *= ip; }
+    for (i = 0; i < m; ++i) if (i != p) {
+      double f = XTX[i][p];
+      for (j = 0; j < m; ++j) { XTX[i][j] -= f * XTX[p][j]; inv[i][j] -= f * inv[p][j]; }
+    }
+  }
+  for (i = 0; i < m; ++i) for (j = 0; j < n; ++j) {
+    double acc = 0; for (k = 0; k < m; ++k) acc += inv[i][k] * X[j][k];
+    M[i][j] = acc;
+  }
+  for (i = 0; i < m; ++i) { double acc = 0; for (j = 0; j < n; ++j) acc += M[i][j] * vy[j]; coef[i] = acc; }
+  return 0;
+}
+/* need_new_solution :38-172.  have_time = 0: `time` not present.  Returns 1 if the band has to be recomputed. */
+int orc_need_new_solution(orc_solver *s, int uid, double time, int have_time) {
+  enum { Nfit = 3, Nporder = 2 };
+  const double max_err = s->cfg.max_solution_err, max_time = s->cfg.max_solution_time;
+  const int lenable = max_err > 0.0 && max_time > 0.0; /* src/pprts.F90:456-457 */
+  orc_solution *sol;
+  double t[Nfit], tm[Nfit], err[2][2 * (Nfit - 1)], polyc[Nporder + 1], estimate[Nporder], error_estimate = 0.0;
+  int k, ipoly, need;
+  if (uid < ORC_UID_MIN || uid > ORC_UID_MAX) return 1;
+  if (!have_time) return 1;                      /* 'time not provided' */
+  if (!lenable) return 1;                        /* 'solutions_err_estimates disabled' */
+  sol = s->sol[uid - ORC_UID_MIN];
+  if (!sol || !sol->lset) return 1;              /* 'no solution yet' */
+  for (k = 1; k <= Nfit; ++k) t[k - 1] = sol->time[Nfit - k];        /* t(k) = time(Nfit-k+1) */
+  for (k = 1; k <= Nfit - 1; ++k) tm[k - 1] = (t[k - 1] + t[k]) * .5;
+  tm[Nfit - 1] = (t[Nfit - 1] + time) * .5;
+  for (k = 1; k <= Nfit - 1; ++k) {
+    err[0][2 * k - 2] = tm[k - 1]; err[0][2 * k - 1] = t[k];
+    err[1][2 * k - 2] = 0.0;       err[1][2 * k - 1] = sol->maxnorm[Nfit - k - 1];  /* maxnorm(Nfit-k) */
+  }
+  for (ipoly = 1; ipoly <= Nporder; ++ipoly) {
+    double tp = 1.0;
+    if (orc_polyfit(err[0], err[1], 2 * (Nfit - 1), ipoly, polyc)) return 1; /* 'problem fitting error curve' */
+    estimate[ipoly - 1] = 0.0;
+    for (k = 1; k <= ipoly + 1; ++k) { estimate[ipoly - 1] += polyc[k - 1] * tp; tp *= time; }
+  }
+  for (k = 0; k < Nporder; ++k) error_estimate = dmax(error_estimate, fabs(estimate[k]));
+  need = !(error_estimate <= max_err);           /* ERR_TOL_IN_BOUND / ERR_TOL_EXCEEDED */
+  for (k = 0; k < Nfit; ++k) if (t[k] < 0.0) need = 1;   /* FEW_SOLUTIONS */
+  if (time - sol->time[0] > max_time) need = 1;          /* MIN_TIME_EXCEEDED */
+  return need;
+}
+void orc_get_solution_times(orc_solver *s, int uid, double *time, double *maxnorm) {
+  orc_solution *sol = s->sol[uid - ORC_UID_MIN];
+  int k;
+  for (k = 0; k < ORC_NTIME; ++k) { time[k] = sol ? sol->time[k] : -1.0; maxnorm[k] = sol ? sol->maxnorm[k] : 0.0; }
+}
+
+static int solve_impl(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid, double time, int have_time);
 int orc_solve(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid) {
+  return solve_impl(s, lthermal, lsolar, edirTOA, uid, 0.0, 0);
+}
+/* solve_pprts(..., opt_solution_time = time) */
+int orc_solve_t(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid, double time) {
+  return solve_impl(s, lthermal, lsolar, edirTOA, uid, time, 1);
+}
+static int solve_impl(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid, double time, int have_time) {
   orc_solution *sol;
   int derived_lsolar, rc = 0;
   long n, N;
@@ -1669,10 +1757,28 @@ int orc_solve(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid) 
   }
   sol->lchanged = 1;
   sol->lWm2_diff = 0;
-  /* restore_solution :3991-4033 */
-  calc_flx_div(s, sol);
-  scale_flx(s, sol, 1);
-  sol->lchanged = 0;
+  /* restore_solution :3991-4049 */
+  {
+    const int lenable = s->cfg.max_solution_err > 0.0 && s->cfg.max_solution_time > 0.0;
+    const long nc = (long)s->Nz * s->Nx * s->Ny;
+    double *abso_old = 0;
+    int k;
+    if (have_time) { /* eoshift(time, -1); time(1) = time */
+      for (k = ORC_NTIME - 1; k > 0; --k) sol->time[k] = sol->time[k - 1];
+      sol->time[0] = time;
+    }
+    if (have_time && lenable) { abso_old = (double *)malloc(sizeof(double) * nc); memcpy(abso_old, sol->abso, sizeof(double) * nc); }
+    calc_flx_div(s, sol);
+    scale_flx(s, sol, 1);
+    sol->lchanged = 0;
+    if (abso_old) { /* :4036-4049 inf-norm of the change of the absorption */
+      double inf_norm = 0.0;
+      for (n = 0; n < nc; ++n) inf_norm = dmax(inf_norm, fabs(abso_old[n] - sol->abso[n]));
+      for (k = ORC_NTIME - 1; k > 0; --k) sol->maxnorm[k] = sol->maxnorm[k - 1];
+      sol->maxnorm[0] = inf_norm;
+      free(abso_old);
+    }
+  }
   return rc;
 }
 

@@ -104,6 +104,8 @@ typedef struct {
   int collapseindex;     /* init_pprts argument (src/pprts.F90:692-706): > 1 merges the top `collapseindex` atmosphere
                             layers into one 1-D layer; Nz above is then the ATMOSPHERE layer count, the solver grid and
                             all results have Nz - collapseindex + 1 layers. <= 1: off */
+  double max_solution_err;  /* -max_solution_err [W], src/tenstream_options.F90:90 default 5e3/86400; <= 0 disables */
+  double max_solution_time; /* -max_solution_time [s], :94 default 0 = error estimates disabled */
 } orc_config;
 
 orc_solver *orc_solver_create(const orc_config *cfg, const orc_lut *lut);      /* init_pprts, src/pprts.F90:213 */
@@ -117,6 +119,14 @@ int orc_set_optical_properties(orc_solver *s, double albedo, const double *kabs,
 int orc_solve(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid); /* src/pprts.F90:2487-3033 */
 /* pprts_get_result (src/pprts.F90:5799-5917): edn,eup,edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny); edir may be NULL */
 int orc_get_result(orc_solver *s, int uid, double *edn, double *eup, double *abso, double *edir);
+
+/* error-growth tracking (src/adaptive_spectral_integration.F90:38-257; restore_solution src/pprts.F90:3991-4049):
+ * orc_solve_t = solve_pprts(..., opt_solution_time = time); need_new_solution tells the band loop whether the stored
+ * solution of `uid` is still good at `time` (have_time = 0: time not present -> always 1) */
+int orc_solve_t(orc_solver *s, int lthermal, int lsolar, double edirTOA, int uid, double time);
+int orc_need_new_solution(orc_solver *s, int uid, double time, int have_time);
+int orc_polyfit(const double *vx, const double *vy, int n, int d, double *coef);
+void orc_get_solution_times(orc_solver *s, int uid, double *time30, double *maxnorm30);
 
 /* opt_buildings of solve_pprts / pprts_get_result (src/buildings.F90:40-69, src/pprts.F90:3194-3212, :3579-3677,
  * :4989-5145, :6011-6160).  iface: 1-based flattened index into (6,Nz,Nx,Ny), first axis fastest; face ids 1..6 =

@@ -1710,6 +1710,18 @@ __global__ void k_sqrt_mean(double *v, int n, double inv_nranks) {
   if (threadIdx.x < n) v[threadIdx.x] = sqrt(v[threadIdx.x]) * inv_nranks;
 }
 
+// max |a - b| over n entries -> *out (restore_solution's VecNorm(abso_old - abso, NORM_INFINITY), src/pprts.F90:4036-4040).
+// Non-negative doubles order like their bit patterns, so the grid maximum is an integer atomicMax; *out is zeroed first.
+__global__ void k_absdiff_max(long n, const double *__restrict__ a, const double *__restrict__ b, double *out) {
+  double m = 0.0;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(a[q] - b[q]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(m));
+}
+
 // =================================================================================================================
 // Buildings (opt_buildings of solve_pprts / pprts_get_result; src/buildings.F90, src/pprts.F90:3194-3212, :3579-3677,
 // :4989-5145, :6011-6160).  A building is a list of faces of grid cells: iface[m] is the 1-based flattened index into

@@ -180,6 +180,9 @@ struct Solution {  // t_state_container (src/pprts_base.F90:137-169)
   bool first_dir = true, first_diff = true;  // residual_history(1) < 0
   int niter_dir = 0, niter_diff = 0;
   double res_dir = 0, res_diff = 0;
+  // error-growth tracking (src/pprts_base.F90:161-162): times of the last solves, inf-norm of the change of abso
+  double time[30], maxnorm[30];
+  Solution() { for (int k = 0; k < 30; ++k) { time[k] = -1.0; maxnorm[k] = 0.0; } }
 };
 
 enum { FAM_LOOKUP = 0, FAM_EDIR, FAM_SOURCE, FAM_MATMULT, FAM_PRECOND, FAM_VEC, FAM_ABSO, FAM_IO, FAM_HALO, FAM_COUNT };
@@ -285,7 +288,7 @@ static struct {
   fn_ncclSend Send; fn_ncclRecv Recv; fn_ncclGroup GroupStart, GroupEnd;
   fn_ncclCommDestroy CommDestroy; fn_ncclGetErrorString GetErrorString;
 } g_nccl;
-static const int NCCL_F64 = 8, NCCL_F32 = 7, NCCL_SUM = 0;  // ncclFloat64, ncclFloat32, ncclSum
+static const int NCCL_F64 = 8, NCCL_F32 = 7, NCCL_SUM = 0, NCCL_MAX = 2;  // ncclFloat64, ncclFloat32, ncclSum, ncclMax
 template <class VT> static constexpr int nccl_type() { return std::is_same<VT, float>::value ? NCCL_F32 : NCCL_F64; }
 static int load_nccl() {
   if (g_nccl.h) return 0;
@@ -469,6 +472,8 @@ extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   cfg->diff_explicit = 0;
   cfg->krylov_fp32 = 0;
   cfg->collapseindex = 1;
+  cfg->max_solution_err = 5e3 / (3600.0 * 24.0);  // src/tenstream_options.F90:90
+  cfg->max_solution_time = 0.0;                    // :94 -> error estimates disabled unless the caller sets it
 }
 
 template <class T>
@@ -1284,7 +1289,16 @@ static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool ltherma
   return 0;
 }
 
+static int solve_impl(pprts_b200_solver *s, int lthermal, int lsolar, double edirTOA, int uid, bool have_time, double time);
 extern "C" int pprts_b200_solve(pprts_b200_solver *s, int lthermal, int lsolar, double edirTOA, int uid) {
+  return solve_impl(s, lthermal, lsolar, edirTOA, uid, false, 0.0);
+}
+// solve_pprts(..., opt_solution_time = time): restore_solution also records the time and, with the error estimates
+// enabled, the inf-norm of the change of the absorption (src/pprts.F90:4005-4049)
+extern "C" int pprts_b200_solve_at_time(pprts_b200_solver *s, int lthermal, int lsolar, double edirTOA, int uid, double time) {
+  return solve_impl(s, lthermal, lsolar, edirTOA, uid, true, time);
+}
+static int solve_impl(pprts_b200_solver *s, int lthermal, int lsolar, double edirTOA, int uid, bool have_time, double time) {
   if (!s) return set_err(1, "null solver");
   if (!s->have_optprop) return set_err(10, "atmosphere%%kabs is not allocated! - maybe you need to call set_optical_properties() first");
   if (uid < -1000 || uid > 1000) return set_err(11, "solution uid %d out of range", uid);
@@ -1328,11 +1342,112 @@ extern "C" int pprts_b200_solve(pprts_b200_solver *s, int lthermal, int lsolar, 
   }
   sol.lchanged = true;
   sol.lWm2_diff = false;
-  // restore_solution (src/pprts.F90:3991-4033)
+  // restore_solution (src/pprts.F90:3991-4049)
+  const bool lenable = s->cfg.max_solution_err > 0.0 && s->cfg.max_solution_time > 0.0;  // :456-457
+  if (have_time) {  // eoshift(time, -1); time(1) = time
+    for (int k = 29; k > 0; --k) sol.time[k] = sol.time[k - 1];
+    sol.time[0] = time;
+  }
+  const bool track = have_time && lenable;
+  if (track) CU(cudaMemcpyAsync(s->out_stage, sol.abso, (size_t)g.ncell * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
   if ((rc = calc_flx_div(s, sol))) return rc;
   if ((rc = scale_flx(s, sol, true))) return rc;
   sol.lchanged = false;
+  if (track) {
+    CU(cudaMemsetAsync(s->sc + SC_TMP, 0, sizeof(double), s->stream));
+    LAUNCH(s, FAM_ABSO, k_absdiff_max, vec_grid(g.ncell), VEC_BLOCK, g.ncell, (const double *)s->out_stage,
+           (const double *)sol.abso, s->sc + SC_TMP);
+    if (s->decomposed) NC(g_nccl.AllReduce(s->sc + SC_TMP, s->sc + SC_TMP, 1, NCCL_F64, NCCL_MAX, s->nccl_comm, s->stream));
+    if ((rc = read_scalars(s))) return rc;
+    for (int k = 29; k > 0; --k) sol.maxnorm[k] = sol.maxnorm[k - 1];
+    sol.maxnorm[0] = s->h_sc[SC_TMP];
+  }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// error-growth tracking: need_new_solution / polyfit (src/adaptive_spectral_integration.F90:38-257), host logic
+// ---------------------------------------------------------------------------------------------------------------
+static bool approx_eq(double a, double b) {  // helper_functions.fypp:1272-1287, default precision 10 * epsilon
+  const double eps = 10.0 * DBL_EPSILON;
+  return a <= b + eps && a >= b - eps;
+}
+// least squares through the normal equations, (X^T X)^-1 by Gauss-Jordan with partial pivoting; 0 on success
+static int polyfit(const double *vx, const double *vy, int n, int d, double *coef) {
+  double X[16][4], A[4][4], inv[4][4];
+  const int m = d + 1;
+  if (n > 16 || m > 4) return 9;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (approx_eq(vx[i], vx[j])) return 1;  // equal abscissae: the matrix is singular (:198-207)
+  for (int i = 0; i < m; ++i) for (int j = 0; j < n; ++j) X[j][i] = std::pow(vx[j], (double)i);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += X[k][i] * X[k][j];
+      A[i][j] = acc; inv[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int p = 0; p < m; ++p) {
+    int piv = p;
+    for (int i = p + 1; i < m; ++i) if (std::fabs(A[i][p]) > std::fabs(A[piv][p])) piv = i;
+    if (A[piv][p] == 0.0) return 2;
+    if (piv != p) for (int j = 0; j < m; ++j) { std::swap(A[p][j], A[piv][j]); std::swap(inv[p][j], inv[piv][j]); }
+    const double ip = 1.0 / A[p][p];
+    for (int j = 0; j < m; ++j) { A[p][j] *= ip; inv[p][j] *= ip; }
+    for (int i = 0; i < m; ++i) {
+      if (i == p) continue;
+      const double f = A[i][p];
+      for (int j = 0; j < m; ++j) { A[i][j] -= f * A[p][j]; inv[i][j] -= f * inv[p][j]; }
+    }
+  }
+  for (int i = 0; i < m; ++i) {
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) {
+      double mij = 0.0;
+      for (int k = 0; k < m; ++k) mij += inv[i][k] * X[j][k];
+      acc += mij * vy[j];
+    }
+    coef[i] = acc;
+  }
+  return 0;
+}
+// need_new_solution(comm, solver%solutions(uid), time, lenable_solutions_err_estimates): *need = 1 if the band has to
+// be solved again at `time`, 0 if the stored solution is still within -max_solution_err.  have_time = 0: time absent.
+extern "C" int pprts_b200_need_new_solution(pprts_b200_solver *s, int uid, double time, int have_time, int *need) {
+  if (!s || !need) return set_err(1, "null solver");
+  constexpr int Nfit = 3, Nporder = 2;
+  *need = 1;
+  if (!have_time) return 0;  // 'time not provided'
+  if (!(s->cfg.max_solution_err > 0.0 && s->cfg.max_solution_time > 0.0)) return 0;  // 'solutions_err_estimates disabled'
+  auto it = s->solutions.find(s->cfg.keep_solutions ? uid : 0);
+  if (it == s->solutions.end() || !it->second.lset) return 0;  // 'no solution yet -- not initialized'
+  const Solution &sol = it->second;
+  double t[Nfit], tm[Nfit], ex[2 * (Nfit - 1)], ey[2 * (Nfit - 1)], polyc[Nporder + 1], est = 0.0;
+  for (int k = 1; k <= Nfit; ++k) t[k - 1] = sol.time[Nfit - k];
+  for (int k = 1; k <= Nfit - 1; ++k) tm[k - 1] = (t[k - 1] + t[k]) * .5;
+  tm[Nfit - 1] = (t[Nfit - 1] + time) * .5;
+  for (int k = 1; k <= Nfit - 1; ++k) {  // error time series: zero in between two updates, the recorded norm at an update
+    ex[2 * k - 2] = tm[k - 1]; ey[2 * k - 2] = 0.0;
+    ex[2 * k - 1] = t[k];      ey[2 * k - 1] = sol.maxnorm[Nfit - k - 1];
+  }
+  for (int ipoly = 1; ipoly <= Nporder; ++ipoly) {
+    if (polyfit(ex, ey, 2 * (Nfit - 1), ipoly, polyc)) return 0;  // 'problem fitting error curve'
+    double e = 0.0, tp = 1.0;
+    for (int k = 0; k <= ipoly; ++k) { e += polyc[k] * tp; tp *= time; }
+    est = std::max(est, std::fabs(e));
+  }
+  int n = !(est <= s->cfg.max_solution_err);                 // ERR_TOL_IN_BOUND / ERR_TOL_EXCEEDED
+  for (int k = 0; k < Nfit; ++k) if (t[k] < 0.0) n = 1;      // FEW_SOLUTIONS
+  if (time - sol.time[0] > s->cfg.max_solution_time) n = 1;  // MIN_TIME_EXCEEDED
+  *need = n;
+  return 0;
+}
+extern "C" int pprts_b200_get_solution_times(pprts_b200_solver *s, int uid, double time[30], double maxnorm[30]) {
+  if (!s) return set_err(1, "null solver");
+  auto it = s->solutions.find(s->cfg.keep_solutions ? uid : 0);
+  if (it == s->solutions.end()) return set_err(30, "no solution for uid %d", uid);
+  for (int k = 0; k < 30; ++k) { time[k] = it->second.time[k]; maxnorm[k] = it->second.maxnorm[k]; }
   return 0;
 }
 

@@ -43,7 +43,8 @@ class _Config(C.Structure):
                 ("by_coeff_divergence", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
-                ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int)]
+                ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int),
+                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double)]
 
 
 class _Bands(C.Structure):
@@ -72,6 +73,7 @@ ABI_SYMBOLS = [
     "pprts_b200_get_info", "pprts_b200_mat_mult_ediff", "pprts_b200_lookup_coeffs", "pprts_b200_kernel_launches",
     "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error", "pprts_b200_stream",
     "pprts_b200_solve_bands", "pprts_b200_set_buildings", "pprts_b200_get_buildings_result",
+    "pprts_b200_solve_at_time", "pprts_b200_need_new_solution", "pprts_b200_get_solution_times",
 ]
 
 
@@ -110,6 +112,9 @@ def lib():
     L.pprts_b200_get_info.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p]
     L.pprts_b200_mat_mult_ediff.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.pprts_b200_lookup_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_long] + [c_double_p] * 5
+    L.pprts_b200_solve_at_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.pprts_b200_need_new_solution.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, c_int_p]
+    L.pprts_b200_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
     L.pprts_b200_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_get_buildings_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_kernel_launches.restype = C.c_long
@@ -283,7 +288,8 @@ def _alloc_results(s):
 def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=None, nxproc=None, nyproc=None,
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
-               keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False) -> Solver:
+               keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
+               max_solution_time=None) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -321,6 +327,10 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.diff_explicit = int(diff_explicit)
     cfg.krylov_fp32 = int(krylov_fp32)
     cfg.collapseindex = int(collapseindex) if collapseindex is not None else 1
+    if max_solution_err is not None:      # -max_solution_err / -max_solution_time (src/tenstream_options.F90:90-96)
+        cfg.max_solution_err = float(max_solution_err)
+    if max_solution_time is not None:
+        cfg.max_solution_time = float(max_solution_time)
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
     if cfg.nxproc * cfg.nyproc > 1:
@@ -383,8 +393,28 @@ def solve_pprts(solver: Solver, lthermal, lsolar, edirTOA, opt_solution_uid=0, o
                 opt_buildings=None):
     """``solve_pprts`` (src/pprts.F90:2487-2665); ``opt_buildings``: a ``buildings.PprtsBuildings`` (:2494)"""
     _attach_buildings(solver, opt_buildings)
+    if opt_solution_time is not None:
+        _chk(lib().pprts_b200_solve_at_time(solver._h, int(bool(lthermal)), int(bool(lsolar)), float(edirTOA),
+                                            int(opt_solution_uid), float(opt_solution_time)), "solve_pprts")
+        return
     _chk(lib().pprts_b200_solve(solver._h, int(bool(lthermal)), int(bool(lsolar)), float(edirTOA),
                                 int(opt_solution_uid)), "solve_pprts")
+
+
+def need_new_solution(solver: Solver, uid, time=None):
+    """``need_new_solution(comm, solver%solutions(uid), time, solver%lenable_solutions_err_estimates)``
+    (src/adaptive_spectral_integration.F90:38-172): does the band have to be solved again at ``time``?"""
+    need = C.c_int(1)
+    _chk(lib().pprts_b200_need_new_solution(solver._h, int(uid), 0.0 if time is None else float(time),
+                                            int(time is not None), C.byref(need)), "need_new_solution")
+    return bool(need.value)
+
+
+def solution_times(solver: Solver, uid):
+    """``solution%time`` and ``solution%maxnorm`` (src/pprts_base.F90:161-162), newest first"""
+    t, m = np.zeros(30), np.zeros(30)
+    _chk(lib().pprts_b200_get_solution_times(solver._h, int(uid), _dp(t), _dp(m)), "solution_times")
+    return t, m
 
 
 def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None, opt_buildings=None):

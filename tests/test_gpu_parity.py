@@ -791,3 +791,49 @@ def test_buildings_removed_and_errors(P, gpu_lut):
     with pytest.raises(P.PprtsError, match="outside"):
         P.solve_pprts(s, False, True, 100.0, 4, opt_buildings=bad)
     P.destroy_pprts(s)
+
+
+# ---- error-growth tracking of stored solutions (src/adaptive_spectral_integration.F90) ------------------------------------
+def test_error_growth_tracking(P, gpu_lut, oracle_lut):
+    """tests/pprts_error_growth_tracking/pprts_error_growth_tracking.F90:66-125 through the CUDA path (options
+    -max_solution_time 60, -solar_diff_ksp_rtol 1e-4), and the recorded history against the oracle's"""
+    from oracle import binding as ob
+    kabs = np.full((3, 3, 3), 1. / 3)
+    g = np.zeros((3, 3, 3))
+    sd = P.sundir_from_angles(0., 60.)
+    s = P.init_pprts(0, 3, 3, 3, 100., 100., sd, dz1d=np.full(3, 100.), lut=gpu_lut, coeff_fp32=False, rtol=1e-4,
+                     max_solution_time=60.)
+    o = ob.OracleSolver(oracle_lut, 3, 3, 3, 100., 100., sd, np.full(3, 100.), diff_solver=1, rtol=1e-4, max_solution_time=60.)
+    for it in range(1, 6):
+        for k in (1, 2):
+            lneed = P.need_new_solution(s, k, float(it))
+            assert lneed == o.need_new_solution(k, float(it)) == (it <= 3), (it, k)
+            P.set_optical_properties(s, 0.1, kabs, kabs, g)
+            o.set_optical_properties(0.1, kabs, kabs, g)
+            P.solve_pprts(s, False, True, 1000., k, opt_solution_time=float(it))
+            assert o.solve(False, True, 1000., k, time=float(it)) == 0
+            P.pprts_get_result(s, k)
+    t, m = P.solution_times(s, 1)
+    to, mo = o.solution_times(1)
+    assert np.array_equal(t, to) and list(t[:6]) == [5., 4., 3., 2., 1., -1.]
+    assert m[4] == pytest.approx(mo[4], rel=1e-6)            # the first solve: change of abso from zero
+    assert np.all(m[:4] < 1e-3 * m[4])
+    assert P.need_new_solution(s, 1, None) and P.need_new_solution(s, 1, 66.) and P.need_new_solution(s, 9, 6.)
+    P.destroy_pprts(s); o.destroy()
+    # drifting inputs: the extrapolated error exceeds -max_solution_err on both sides
+    s = P.init_pprts(0, 3, 3, 3, 100., 100., sd, dz1d=np.full(3, 100.), lut=gpu_lut, coeff_fp32=False, rtol=1e-6,
+                     max_solution_time=600.)
+    for it in range(1, 5):
+        k = np.full((3, 3, 3), 2e-3 * (1. + 0.5 * it))
+        P.set_optical_properties(s, 0.1, k, k, g)
+        P.solve_pprts(s, False, True, 1000., 1, opt_solution_time=float(it))
+    assert P.need_new_solution(s, 1, 5.)
+    P.destroy_pprts(s)
+    # default options: -max_solution_time 0 disables the estimates, every call asks for a new solution
+    s = P.init_pprts(0, 3, 3, 3, 100., 100., sd, dz1d=np.full(3, 100.), lut=gpu_lut)
+    P.set_optical_properties(s, 0.1, kabs, kabs, g)
+    for it in range(1, 6):
+        assert P.need_new_solution(s, 1, float(it))
+        P.solve_pprts(s, False, True, 1000., 1, opt_solution_time=float(it))
+    assert np.all(P.solution_times(s, 1)[1] == 0)
+    P.destroy_pprts(s)

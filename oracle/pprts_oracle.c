@@ -631,14 +631,15 @@ static void halo_reduce_5pt(const orc_solver *s, int nd, double *v) {
 
 /* helper_functions.fypp:1993-2016 (cartesian_2_spherical) */
 static void cartesian_2_spherical(const double sundir[3], double *phi, double *theta) {
-  double n = sqrt(sundir[0] * sundir[0] + sundir[1] * sundir[1] + sundir[2] * sundir[2]);
+  /* norm2() does not underflow for tiny components (tests/test_helper_functions: sundir = [0, -tiny, -1]): hypot */
+  double n = hypot(hypot(sundir[0], sundir[1]), sundir[2]);
   double sn[3] = {sundir[0], sundir[1], sundir[2]}, proj[3], pn, az, c;
   if (n > 0) { sn[0] /= n; sn[1] /= n; sn[2] /= n; }
   c = dmax(-1.0, dmin(1.0, -sn[2])); /* dot(sundir_normed, -e_z) */
   *theta = acos(c) * 180.0 / ORC_PI;
   /* vec_proj_on_plane(sundir, -e_z) = v - dot(v,n) n */
   proj[0] = sundir[0]; proj[1] = sundir[1]; proj[2] = 0.0;
-  pn = sqrt(proj[0] * proj[0] + proj[1] * proj[1]);
+  pn = hypot(proj[0], proj[1]);
   if (pn > 0) { proj[0] /= pn; proj[1] /= pn; }
   c = dmax(-1.0, dmin(1.0, -proj[1])); /* angle to -e_y */
   az = acos(c);

@@ -487,10 +487,11 @@ static int dalloc(T **p, size_t n) {
 // src/pprts.F90:1118-1183 (setup_suninfo) incl. cartesian_2_spherical (helper_functions.fypp:1993-2016)
 static void setup_suninfo(pprts_b200_solver *s, const double sundir[3]) {
   const double d2r = PB_PI / 180.0;
-  double n = std::sqrt(sundir[0] * sundir[0] + sundir[1] * sundir[1] + sundir[2] * sundir[2]);
+  // norm2() of the reference does not underflow for tiny components (test_helper_functions.F90:774-792): hypot
+  double n = std::hypot(std::hypot(sundir[0], sundir[1]), sundir[2]);
   double sn2 = n > 0 ? sundir[2] / n : sundir[2];
   double theta = std::acos(std::max(-1.0, std::min(1.0, -sn2))) / d2r;
-  double px = sundir[0], py = sundir[1], pn = std::sqrt(px * px + py * py);
+  double px = sundir[0], py = sundir[1], pn = std::hypot(px, py);
   if (pn > 0) { px /= pn; py /= pn; }
   double az = std::acos(std::max(-1.0, std::min(1.0, -py)));
   az = az * ((-px) >= 0 ? 1.0 : -1.0);

@@ -241,3 +241,43 @@ def test_synthetic_lut_symmetry_and_energy(solver_id):
     S = S.reshape(-1, Nf, Nd).astype(np.float64)
     tot = T.sum(1) + S.sum(1)
     assert T.min() >= 0 and S.min() >= 0 and tot.max() <= 1 + 1e-6
+
+
+# tests/test_helper_functions/test_helper_functions.F90:767-823 (cartesian_2_spherical, as used by setup_suninfo
+# src/pprts.F90:1118-1183) -- phi is folded into [0, 360) by setup_suninfo, the reference test states it in (-180, 180]
+@pytest.mark.parametrize("sundir,phi,theta", [
+    ((0., -np.finfo(float).tiny, -1.), 0., 0.), ((0., np.finfo(float).tiny, -1.), 180., 0.),
+    ((-np.finfo(float).tiny, 0., -1.), 90., 0.), ((np.finfo(float).tiny, 0., -1.), -90., 0.),
+    ((0., -1., -1.), 0., 45.), ((-1., -1., -1.), 45., 54.73561), ((1., 1., -1.), -135., 54.73561)])
+def test_cartesian_2_spherical_known_answers(oracle_lut, sundir, phi, theta):
+    eps = 1e-5
+    s = ob.OracleSolver(oracle_lut, 2, 3, 3, 100., 100., np.array(sundir), np.full(2, 50.))
+    info = s.suninfo()
+    d = (info["phi"] - phi + 180.) % 360. - 180.          # compare azimuths modulo 360
+    assert abs(d) < eps or abs(abs(d) - 360.) < eps or (abs(phi) == 180. and abs(abs(info["phi"]) % 360. - 180.) < eps)
+    assert abs(info["theta"] - theta) < eps
+    s.destroy()
+
+
+def test_spherical_cartesian_roundtrip(oracle_lut):
+    """:810-822: 1000 random unit vectors -> (phi, theta) -> spherical_2_cartesian reproduces them"""
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        v = rng.random(3)
+        v[2] = -abs(v[2]) - 0.05        # a sun above the horizon (theta < 90), which is what the solver accepts
+        v /= np.linalg.norm(v)
+        s = ob.OracleSolver(oracle_lut, 2, 3, 3, 100., 100., v, np.full(2, 50.))
+        info = s.suninfo()
+        s.destroy()
+        assert np.abs(ob.sundir_from_angles(info["phi"], info["theta"]) - v).max() < 1e-5
+
+
+def test_ndarray_idx():
+    """tests/test_helper_functions/test_helper_functions.F90:695-729 (the face numbering of the buildings)"""
+    from tenstream_b200 import buildings as B
+    off = B.ndarray_offsets((2, 3, 2))
+    assert list(off) == [1, 2, 6]
+    assert B.ind_nd_to_1d(off, (1, 1, 1)) == 1 and B.ind_1d_to_nd(off, 1) == [1, 1, 1]
+    assert B.ind_nd_to_1d(off, (2, 3, 2)) == 12 and B.ind_1d_to_nd(off, 12) == [2, 3, 2]
+    for i1d in range(1, 13):
+        assert B.ind_nd_to_1d(off, B.ind_1d_to_nd(off, i1d)) == i1d

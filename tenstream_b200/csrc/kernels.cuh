@@ -1591,47 +1591,53 @@ __global__ void k_bicg32_update_s(long n, int it, const float *__restrict__ r, c
   }
   for (long q = (n4 << 2) + t0; q < n; q += stride) s[q] = fmaf(-alpha, v[q], r[q]);
 }
-// x (fp64) += alpha ph + omega sh ; r = s - omega t ; rr = (r,r), rho(it+1) = (rh, r)
+// xc (fp32 correction of the cycle) += alpha ph + omega sh ; r = s - omega t ; rr = (r,r), rho(it+1) = (rh, r).
+// The fp64 solution is only touched when the correction is flushed into it (k_mixed_flush: before every true-residual
+// evaluation and at the end of a cycle), which takes 8 of the 40 bytes per entry off this kernel.
 __global__ void k_bicg32_update_xr(long n, int it, const float *__restrict__ ph, const float *__restrict__ sh,
                                    const float *__restrict__ s, const float *__restrict__ t,
-                                   const float *__restrict__ rh, double *__restrict__ x, float *__restrict__ r,
+                                   const float *__restrict__ rh, float *__restrict__ xc, float *__restrict__ r,
                                    double *partials, unsigned int *counter, double *sc) {
   const BicgScalars k = bicg_scalars(sc, it, false);
-  const double alpha = k.alpha, omega = k.omega;
-  const float omegaf = (float)omega;
+  const float alphaf = (float)k.alpha, omegaf = (float)k.omega;
   const bool rho_first = sc_rho_slot(it + 1) == SC_RHO0;  // output run is (RHO0, RR) or (RR, RHO1)
   double rr = 0.0, rhr = 0.0;
-  auto one = [&](float phv, float shv, float sv, float tv, float rhv, double xv, float &rout) -> double {
+  auto one = [&](float phv, float shv, float sv, float tv, float rhv, float xv, float &rout) -> float {
     rout = fmaf(-omegaf, tv, sv);
     const double rd = widen_any(rout);
     rr = fma(rd, rd, rr);
     rhr = fma(rd, widen_any(rhv), rhr);
-    return fma(omega, widen_any(shv), fma(alpha, widen_any(phv), xv));
+    return fmaf(omegaf, shv, fmaf(alphaf, phv, xv));
   };
   const long n4 = n >> 2, stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const float4 *ph4 = reinterpret_cast<const float4 *>(ph), *sh4 = reinterpret_cast<const float4 *>(sh),
                *s4 = reinterpret_cast<const float4 *>(s), *t4 = reinterpret_cast<const float4 *>(t),
                *rh4 = reinterpret_cast<const float4 *>(rh);
-  float4 *r4 = reinterpret_cast<float4 *>(r);
-  double2 *x2 = reinterpret_cast<double2 *>(x);
+  float4 *r4 = reinterpret_cast<float4 *>(r), *x4 = reinterpret_cast<float4 *>(xc);
   for (long q = t0; q < n4; q += stride) {
     const float4 a = ph4[q], b = sh4[q], c = s4[q], d = t4[q], e = rh4[q];
-    double2 xa = x2[2 * q], xb = x2[2 * q + 1];
-    float4 ro;
-    xa.x = one(a.x, b.x, c.x, d.x, e.x, xa.x, ro.x);
-    xa.y = one(a.y, b.y, c.y, d.y, e.y, xa.y, ro.y);
-    xb.x = one(a.z, b.z, c.z, d.z, e.z, xb.x, ro.z);
-    xb.y = one(a.w, b.w, c.w, d.w, e.w, xb.y, ro.w);
-    x2[2 * q] = xa; x2[2 * q + 1] = xb;
+    float4 xv = x4[q], ro;
+    xv.x = one(a.x, b.x, c.x, d.x, e.x, xv.x, ro.x);
+    xv.y = one(a.y, b.y, c.y, d.y, e.y, xv.y, ro.y);
+    xv.z = one(a.z, b.z, c.z, d.z, e.z, xv.z, ro.z);
+    xv.w = one(a.w, b.w, c.w, d.w, e.w, xv.w, ro.w);
+    x4[q] = xv;
     r4[q] = ro;
   }
   for (long q = (n4 << 2) + t0; q < n; q += stride) {
     float ro;
-    x[q] = one(ph[q], sh[q], s[q], t[q], rh[q], x[q], ro);
+    xc[q] = one(ph[q], sh[q], s[q], t[q], rh[q], xc[q], ro);
     r[q] = ro;
   }
   double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
   grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
+}
+// x (fp64) += xc ; xc = 0
+__global__ void k_mixed_flush(long n, float *__restrict__ xc, double *__restrict__ x) {
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    x[q] += widen_any(xc[q]);
+    xc[q] = 0.f;
+  }
 }
 // explicit relaxation (explicit_ediff analogue): r = b - Ax (Ax in `r` on entry)
 __global__ void k_relax_residual(long n, const double *__restrict__ b, double *__restrict__ r) {

@@ -1125,8 +1125,11 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   float *r = (float *)s->kr[1], *rh = r + n4, *p = (float *)s->kr[2], *v = p + n4, *sv = (float *)s->kr[3], *t = sv + n4;
   const bool prec = precond_available(s);
   float *ph = prec ? (float *)s->kr[4] : p, *sh = prec ? ph + n4 : sv;
+  float *xc = (float *)s->kr[5];  // the cycle's correction of x, flushed into the fp64 solution before it is looked at
   int rc;
   double r0 = 0.0;
+  bool dirty = false;
+  CU(cudaMemsetAsync(xc, 0, (size_t)n * sizeof(float), s->stream));
   int total = 0;
   bool converged = false;
   sol.niter_diff = 0;
@@ -1152,7 +1155,8 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
       LAUNCH(s, FAM_VEC, k_bicg32_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
       if (prec) launch_prec32(s, sv, sh);
       if ((rc = launch_matmult<2, float>(s, sh, t, sv, s->sc + SC_TS))) return rc;
-      LAUNCH(s, FAM_VEC, k_bicg32_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, x, r, s->partials, s->counter, s->sc);
+      LAUNCH(s, FAM_VEC, k_bicg32_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, xc, r, s->partials, s->counter, s->sc);
+      dirty = true;
       if ((rc = allreduce_scalars(s, s->sc + (((it + 1) & 1) ? SC_RR : SC_RHO0), 2))) return rc;
       if ((rc = read_scalars(s))) return rc;
       const double rn = std::sqrt(s->h_sc[SC_RR]);
@@ -1161,6 +1165,8 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
       sol.res_diff = rn;
       if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", total);
       if (rn <= inner && inner > floor32) {  // the recursion claims convergence: check the true residual in fp64
+        LAUNCH(s, FAM_VEC, k_mixed_flush, vec_grid(n), VEC_BLOCK, n, xc, x);
+        dirty = false;
         if ((rc = launch_matmult<0, double>(s, x, ax, nullptr, nullptr))) return rc;
         LAUNCH(s, FAM_VEC, k_residual_norm2, vec_grid(n), VEC_BLOCK, n, s->b, ax, s->partials, s->counter, s->sc + SC_TMP);
         if ((rc = allreduce_scalars(s, s->sc + SC_TMP, 1))) return rc;
@@ -1174,6 +1180,7 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
       // breakdown: rho = (rh, r) vanished with r not converged -> new cycle, i.e. new shadow residual rh = r
       if (!converged && std::fabs(s->h_sc[((it + 1) & 1) ? SC_RHO1 : SC_RHO0]) <= 1e-30 * rn * rc0) restart = true;
     }
+    if (dirty) { LAUNCH(s, FAM_VEC, k_mixed_flush, vec_grid(n), VEC_BLOCK, n, xc, x); dirty = false; }
     if (!restart && !converged) break;  // maxit
   }
   sol.first_diff = false;

@@ -1019,9 +1019,12 @@ static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precon
 template <class K>
 static int column_block(pprts_b200_solver *s, K kernel, int *cache) {
   if (*cache) return *cache;
-  int best = PREC_BLOCK;
+  cudaFuncAttributes fa;
+  int bs0 = PREC_BLOCK;  // a kernel compiled with __launch_bounds__(32, ...) cannot be launched with 64 threads
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) bs0 = std::min(bs0, std::max(32, fa.maxThreadsPerBlock / 32 * 32));
+  int best = bs0;
   long best_waves = -1;
-  for (int bs = PREC_BLOCK; bs >= 32; bs >>= 1) {
+  for (int bs = bs0; bs >= 32; bs >>= 1) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, bs, 0) != cudaSuccess || per_sm < 1) continue;
     const long slots = (long)per_sm * s->num_sms, blocks = (s->g.ncol + bs - 1) / bs;

@@ -102,7 +102,7 @@ typedef struct {
   int diff_explicit;
   /* 1: mixed-precision Krylov solve -- fp32 work vectors inside BiCGStab, fp64 solution and fp64 true residual with
    * iterative refinement (the convergence test is always evaluated on an fp64 residual).  Halves the vector traffic
-   * of the iteration; on a decomposed solver the halos travel as fp32 too.  Default 0. */
+   * of the iteration; on a decomposed solver the halos travel as fp32 too.  Default 1 (pprts_b200_default_config). */
   int krylov_fp32;
   /* init_pprts collapseindex (src/pprts.F90:692-706, handle_atm_collapse :2080-2198): > 1 merges the top
    * `collapseindex` atmosphere layers (forced 1-D) into ONE 1-D layer by the adding method; Nz, dz and all optical
@@ -181,6 +181,11 @@ typedef struct {
   const double *edirTOA;      /* (nbands), solar */
   const double *weights;      /* (nbands) or NULL: 1 */
   int accumulate_only;        /* 1: add to the device accumulator without resetting it first */
+  /* opt_time of the spectral callers (rrtmg/rrtmg/pprts_rrtmg.F90:1001, :623): with have_time = 1 every band is first
+   * asked need_new_solution(uid, time); bands that do not need one are not uploaded or solved, their stored solution
+   * enters the sum (niter_diff = -1), the others are solved with opt_solution_time = time.  Needs keep_solutions. */
+  int have_time;
+  double time;
 } pprts_b200_bands;
 /* edn/eup/edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny): spectral sums, any may be NULL (NULL for all four leaves the sums in the
  * device accumulator for pprts_b200_allreduce_accumulated / pprts_b200_get_accumulated); niter_diff (nbands) or NULL */

@@ -470,7 +470,7 @@ extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   cfg->keep_solutions = 1;
   cfg->nxproc = cfg->nyproc = 1;
   cfg->diff_explicit = 0;
-  cfg->krylov_fp32 = 0;
+  cfg->krylov_fp32 = 1;  // fp32 Krylov work vectors; the convergence test still sees an fp64 true residual
   cfg->collapseindex = 1;
   cfg->max_solution_err = 5e3 / (3600.0 * 24.0);  // src/tenstream_options.F90:90
   cfg->max_solution_time = 0.0;                    // :94 -> error estimates disabled unless the caller sets it
@@ -1574,24 +1574,45 @@ extern "C" int pprts_b200_solve_bands(pprts_b200_solver *s, const pprts_b200_ban
   }
   int rc;
   if (!b->accumulate_only && (rc = pprts_b200_reset_accumulator(s))) return rc;
-  if (b->nbands > 0) {
-    if ((rc = stage_band_async(s, s->staged[BAND_SLOT0], b, 0))) return rc;
+  // Adaptive spectral integration (rrtmg/rrtmg/pprts_rrtmg.F90:1001, src/adaptive_spectral_integration.F90:38): with a
+  // time, a band whose stored solution is still within -max_solution_err is not solved again -- its stored result
+  // goes into the sum as it is.  The decisions are taken up front: they only depend on each uid's own history.
+  std::vector<char> need((size_t)std::max(0, b->nbands), 1);
+  if (b->have_time) {
+    if (!s->cfg.keep_solutions) return set_err(2, "solve_bands: a solution time needs keep_solutions = 1");
+    for (int ib = 0; ib < b->nbands; ++ib) {
+      int n = 1;
+      if ((rc = pprts_b200_need_new_solution(s, b->uid0 + ib, b->time, 1, &n))) return rc;
+      need[ib] = (char)n;
+    }
+  }
+  auto next_needed = [&](int from) { while (from < b->nbands && !need[from]) ++from; return from; };
+  int slot = 0, staged_band = next_needed(0);
+  if (staged_band < b->nbands) {
+    if ((rc = stage_band_async(s, s->staged[BAND_SLOT0], b, staged_band))) return rc;
     CU(cudaEventRecord(s->band_uploaded[0], s->copy_stream));
   }
   for (int ib = 0; ib < b->nbands; ++ib) {
-    Staged &st = s->staged[BAND_SLOT0 + (ib & 1)];
-    CU(cudaStreamWaitEvent(s->stream, s->band_uploaded[ib & 1], 0));
+    const int uid = b->uid0 + ib;
+    if (!need[ib]) {  // reuse solver%solutions(uid): pprts_get_result of the stored solution
+      if (niter_diff) niter_diff[ib] = -1;
+      if ((rc = compute_result(s, uid, true, b->weights ? b->weights[ib] : 1.0))) return rc;
+      continue;
+    }
+    Staged &st = s->staged[BAND_SLOT0 + slot];
+    CU(cudaStreamWaitEvent(s->stream, s->band_uploaded[slot], 0));
     // returns after the ingest kernels have run: this slot and the other one (consumed one band earlier) are free
     rc = set_optprop_impl(s, st.albedo, st.kabs, st.ksca, st.g, st.have_planck ? st.planck : nullptr,
                           st.have_Bsrfc ? st.Bsrfc : nullptr, st.have_albedo2d ? st.albedo2d : nullptr,
                           b->ldelta_scaling, true);
     if (rc) return rc;
-    if (ib + 1 < b->nbands) {
-      if ((rc = stage_band_async(s, s->staged[BAND_SLOT0 + ((ib + 1) & 1)], b, ib + 1))) return rc;
-      CU(cudaEventRecord(s->band_uploaded[(ib + 1) & 1], s->copy_stream));
+    staged_band = next_needed(ib + 1);
+    slot ^= 1;
+    if (staged_band < b->nbands) {  // upload of the next band to solve overlaps this band's solve
+      if ((rc = stage_band_async(s, s->staged[BAND_SLOT0 + slot], b, staged_band))) return rc;
+      CU(cudaEventRecord(s->band_uploaded[slot], s->copy_stream));
     }
-    const int uid = b->uid0 + ib;
-    rc = pprts_b200_solve(s, !b->lsolar, b->lsolar, b->lsolar ? b->edirTOA[ib] : 0.0, uid);
+    rc = solve_impl(s, !b->lsolar, b->lsolar, b->lsolar ? b->edirTOA[ib] : 0.0, uid, b->have_time != 0, b->time);
     if (rc) {
       char msg[sizeof(g_err)];
       snprintf(msg, sizeof(msg), "%s", g_err);

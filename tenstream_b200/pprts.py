@@ -54,7 +54,8 @@ class _Bands(C.Structure):
                 ("stride_kabs", C.c_long), ("stride_ksca", C.c_long), ("stride_g", C.c_long),
                 ("planck", C.c_void_p), ("planck_srfc", C.c_void_p),
                 ("stride_planck", C.c_long), ("stride_planck_srfc", C.c_long),
-                ("edirTOA", C.c_void_p), ("weights", C.c_void_p), ("accumulate_only", C.c_int)]
+                ("edirTOA", C.c_void_p), ("weights", C.c_void_p), ("accumulate_only", C.c_int),
+                ("have_time", C.c_int), ("time", C.c_double)]
 
 
 _lib = None
@@ -435,7 +436,7 @@ def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None, opt_buildings
 
 def solve_bands(solver: Solver, lsolar, albedo, kabs, ksca, g, planck=None, planck_srfc=None, edirTOA=None,
                 weights=None, uid0=None, albedo_2d=None, ldelta_scaling=True, out=None, download=True,
-                accumulate_only=False):
+                accumulate_only=False, opt_time=None):
     """The band loop of the spectral callers (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053 solar, :621-708 thermal) in one call:
     ``set_optical_properties -> solve_pprts -> pprts_get_result -> sum`` for every band, with the upload of band ib+1
     overlapping the solve of band ib and the spectral sum kept on the device.
@@ -443,7 +444,11 @@ def solve_bands(solver: Solver, lsolar, albedo, kabs, ksca, g, planck=None, plan
     ``kabs/ksca/g``: (Nz,Nx,Ny,nbands), or (Nz,Nx,Ny) to share a field between all bands; ``planck`` (Nz+1,Nx,Ny[,nbands]);
     ``planck_srfc`` (Nx,Ny[,nbands]); ``edirTOA``, ``weights``: (nbands).  Solution uids are ``uid0 + ib`` (default: the
     reference's 1.. for solar, 501.. for thermal).  Returns (edn, eup, abso, edir, niter) -- the weighted sums; with
-    ``download=False`` they stay in the device accumulator (``allreduce_accumulated`` / ``get_accumulated``)."""
+    ``download=False`` they stay in the device accumulator (``allreduce_accumulated`` / ``get_accumulated``).
+
+    ``opt_time``: the callers' adaptive spectral integration (pprts_rrtmg.F90:1001): bands for which
+    ``need_new_solution(uid, opt_time)`` is false are neither uploaded nor solved (``niter`` = -1), their stored
+    solution enters the sum; the others are solved with ``opt_solution_time=opt_time``."""
     s = solver
     c3, l3, c2 = (s.Nz_atm, s.Nx, s.Ny), (s.Nz_atm + 1, s.Nx, s.Ny), (s.Nx, s.Ny)
     nb = None
@@ -493,6 +498,7 @@ def solve_bands(solver: Solver, lsolar, albedo, kabs, ksca, g, planck=None, plan
     b.stride_planck, b.stride_planck_srfc = stride["planck"], stride["planck_srfc"]
     b.edirTOA, b.weights = _vp(e), _vp(w)
     b.accumulate_only = int(accumulate_only)
+    b.have_time, b.time = int(opt_time is not None), float(opt_time if opt_time is not None else 0.0)
     niter = np.zeros(nb, dtype=np.int32)
     if download:
         edn, eup, abso, edir = out if out is not None else _alloc_results(s)

@@ -837,3 +837,48 @@ def test_error_growth_tracking(P, gpu_lut, oracle_lut):
         P.solve_pprts(s, False, True, 1000., 1, opt_solution_time=float(it))
     assert np.all(P.solution_times(s, 1)[1] == 0)
     P.destroy_pprts(s)
+
+
+def test_solve_bands_adaptive_spectral_integration(P, gpu_lut):
+    """The band loop with opt_time (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053): every band is asked need_new_solution first;
+    after three time steps with unchanged inputs no band is solved again and the stored solutions give the same sum,
+    until -max_solution_time has passed."""
+    rng = np.random.default_rng(9)
+    Nz, Nx, Ny, nb = 6, 5, 4, 3
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    kb = np.stack([kabs * f for f in (0.5, 1.0, 3.0)], axis=-1)
+    e = np.array([300., 500., 200.])
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(40., 35.), dz1d=np.full(Nz, 70.), lut=gpu_lut,
+                     rtol=1e-8, max_solution_time=10.)
+    sums = {}
+    for t in range(1, 6):
+        edn, eup, abso, edir, niter = P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e, opt_time=float(t))
+        sums[t] = [a.copy() for a in (edn, eup, abso, edir)]
+        if t <= 3:
+            assert np.all(niter >= 0), (t, niter)               # no history yet: every band is solved
+        else:
+            assert np.all(niter == -1), (t, niter)              # stored solutions are reused
+            for a, b in zip(sums[t], sums[3]):
+                assert np.array_equal(a, b)
+    for ib in range(nb):                                        # solved bands carry the time stamps of their solves
+        assert list(P.solution_times(s, 1 + ib)[0][:4]) == [3., 2., 1., -1.]
+    # without a time every band is solved (and the history is left alone)
+    *_, niter = P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e)
+    assert np.all(niter >= 0)
+    # older than -max_solution_time: solved again
+    *_, niter = P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e, opt_time=3. + 10.5)
+    assert np.all(niter >= 0)
+    # mixed: one band's inputs drift between two explicit solves -> only that band is solved again
+    P.set_optical_properties(s, 0.2, kb[..., 1], ksca, g)
+    P.solve_pprts(s, False, True, e[1], 2, opt_solution_time=14.0)
+    P.set_optical_properties(s, 0.2, 4 * kb[..., 1], ksca, g)
+    P.solve_pprts(s, False, True, e[1], 2, opt_solution_time=14.5)
+    *_, niter = P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e, opt_time=15.0)
+    assert niter[0] == -1 and niter[1] >= 0 and niter[2] == -1, niter
+    P.destroy_pprts(s)
+    # a solver that does not keep its solutions cannot skip bands
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(40., 35.), dz1d=np.full(Nz, 70.), lut=gpu_lut,
+                     keep_solutions=False, max_solution_time=10.)
+    with pytest.raises(P.PprtsError, match="keep_solutions"):
+        P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e, opt_time=1.0)
+    P.destroy_pprts(s)

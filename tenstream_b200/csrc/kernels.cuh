@@ -494,42 +494,99 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
       d2sum[0] += df * df;
       xnew[q] = inc_top;
     }
-    for (int k = 0; k < g.Nz; ++k) {
-      const long lk = (long)k * g.ncol, lk1 = (long)(k + 1) * g.ncol;
+    // Everything a level reads -- coefficients, the side inputs of the previous pass and the old values of its outputs
+    // (for the norm) -- is independent of the vertical recurrence, so it is loaded ahead of it into rotating register
+    // sets (see k_prec_up: the rotation is unrolled, a set is never copied).  Three sets (two levels ahead) for the
+    // 3-stream layouts, two for the 8-stream ones (64 coefficients per level).
+    struct In { CT c[Nd * Nd]; double sx[Nds], sy[Nds], old[Nd], a33; };
+    auto load = [&](int k, In &in) {
+      const long lk = (long)k * g.ncol, lk1 = lk + g.ncol;
+      if (k < n1d) {
+        in.a33 = a33[lk + o_own];
+#pragma unroll
+        for (int d = 0; d < Ndt; ++d) in.old[d] = xold[(long)d * g.nlev + lk1 + o_own];
+#pragma unroll
+        for (int d = Ndt; d < Nd; ++d) in.old[d] = xold[(long)d * g.nlev + lk + o_own];
+      } else {
+#pragma unroll
+        for (int d = 0; d < Nds; ++d) in.sx[d] = xold[xin0 + (Ndt + d) * xins + k * xink];
+#pragma unroll
+        for (int d = 0; d < Nds; ++d) in.sy[d] = xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
+        const long cb = cbase<Nd * Nd>(lk + o_own);
+#pragma unroll
+        for (int n = 0; n < Nd * Nd; ++n) in.c[n] = d2d[cb + n * PB_TILE];
+#pragma unroll
+        for (int dst = 0; dst < Nd; ++dst) {
+          long q;
+          if (dst < Ndt) q = (long)dst * g.nlev + lk1 + o_own;
+          else if (dst < Ndt + Nds) q = xout0 + dst * xouts + k * xoutk;
+          else q = yout0 + dst * youts + k * youtk;
+          in.old[dst] = xold[q];
+        }
+      }
+    };
+    auto level = [&](int k, const In &in) {
+      const long lk = (long)k * g.ncol, lk1 = lk + g.ncol;
       if (k < n1d) {  // 1-D layer: top(k+1) = top(k) * a33 (:383-391); side dofs are left untouched
-        const double t = a33[lk + o_own];
 #pragma unroll
         for (int d = 0; d < Ndt; ++d) {
-          top[d] = top[d] * t;
-          long q = (long)d * g.nlev + lk1 + o_own;
-          double df = top[d] - xold[q];
+          top[d] = top[d] * in.a33;
+          const double df = top[d] - in.old[d];
           d2sum[0] += df * df;
-          xnew[q] = top[d];
+          xnew[(long)d * g.nlev + lk1 + o_own] = top[d];
         }
 #pragma unroll
-        for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lk + o_own] = xold[(long)d * g.nlev + lk + o_own];
+        for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lk + o_own] = in.old[d];
       } else {
         double src[Nd];
 #pragma unroll
         for (int d = 0; d < Ndt; ++d) src[d] = top[d];
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) src[Ndt + d] = xold[xin0 + (Ndt + d) * xins + k * xink];
+        for (int d = 0; d < Nds; ++d) src[Ndt + d] = in.sx[d];
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
-        const long cb = cbase<Nd * Nd>(lk + o_own);
+        for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = in.sy[d];
 #pragma unroll
         for (int dst = 0; dst < Nd; ++dst) {
           double acc = 0.0;
 #pragma unroll
-          for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)d2d[cb + (dst * Nd + s) * PB_TILE];
+          for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)in.c[dst * Nd + s];
           long q;
           if (dst < Ndt) { q = (long)dst * g.nlev + lk1 + o_own; top[dst] = acc; }
           else if (dst < Ndt + Nds) q = xout0 + dst * xouts + k * xoutk;
           else q = yout0 + dst * youts + k * youtk;
-          double df = acc - xold[q];
+          const double df = acc - in.old[dst];
           d2sum[0] += df * df;
           xnew[q] = acc;
         }
+      }
+    };
+    const int Nz = g.Nz;
+    int k = 0;
+    if constexpr (Nd <= 3) {
+      In A, B, C3;
+      load(0, A);
+      if (Nz > 1) load(1, B);
+      while (k < Nz) {
+        if (k + 2 < Nz) load(k + 2, C3);
+        level(k, A);
+        if (++k >= Nz) break;
+        if (k + 2 < Nz) load(k + 2, A);
+        level(k, B);
+        if (++k >= Nz) break;
+        if (k + 2 < Nz) load(k + 2, B);
+        level(k, C3);
+        ++k;
+      }
+    } else {
+      In A, B;
+      load(0, A);
+      while (k < Nz) {
+        if (k + 1 < Nz) load(k + 1, B);
+        level(k, A);
+        if (++k >= Nz) break;
+        if (k + 1 < Nz) load(k + 1, A);
+        level(k, B);
+        ++k;
       }
     }
     // side dofs below the ground are never written by the sweep

@@ -882,3 +882,23 @@ def test_solve_bands_adaptive_spectral_integration(P, gpu_lut):
     with pytest.raises(P.PprtsError, match="keep_solutions"):
         P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e, opt_time=1.0)
     P.destroy_pprts(s)
+
+
+def test_twostr_properties_in_all_1d_atmosphere(P, gpu_lut):
+    """tests/test_twostr/test_twostr.F90:41-59 through the CUDA path with every layer 1-D (see the oracle's twin in
+    tests/test_oracle_known_answers.py)"""
+    ke, mu0, inc, albedo = 9, 0.5, 1e2, 0.1
+    dz, dtau, w0, g = 300.0, 1.0 / 9, 0.5, 0.5
+    kabs = np.full((ke, 3, 3), dtau * (1 - w0) / dz)
+    ksca = np.full((ke, 3, 3), dtau * w0 / dz)
+    s = P.init_pprts(0, ke, 3, 3, 100., 100., P.sundir_from_angles(0., 60.), dz1d=np.full(ke, dz), lut=gpu_lut,
+                     rtol=1e-12, atol=1e-30)
+    P.set_optical_properties(s, albedo, kabs, ksca, np.full((ke, 3, 3), g), ldelta_scaling=False)
+    P.solve_pprts(s, False, True, inc)
+    edn, eup, abso, edir = P.pprts_get_result(s)
+    assert np.allclose(edir[0] / mu0, inc, rtol=1e-12)
+    assert np.allclose(edir[ke] / mu0, np.exp(-ke * dtau / mu0) * inc, rtol=1e-7)
+    assert np.abs(edn[0]).max() == 0
+    assert np.allclose(eup[ke], (edir[ke] + edn[ke]) * albedo, rtol=1e-9)
+    assert np.ptp(eup[0]) < 1e-9 * eup[0].mean()
+    P.destroy_pprts(s)

@@ -281,3 +281,29 @@ def test_ndarray_idx():
     assert B.ind_nd_to_1d(off, (2, 3, 2)) == 12 and B.ind_1d_to_nd(off, 12) == [2, 3, 2]
     for i1d in range(1, 13):
         assert B.ind_nd_to_1d(off, B.ind_1d_to_nd(off, i1d)) == i1d
+
+
+def test_twostr_properties_in_all_1d_atmosphere(oracle_lut):
+    """tests/test_twostr/test_twostr.F90:41-59 (mu0 = .5, incSolar = 100, albedo = .1, 9 layers with dtau = 1/9,
+    w0 = g = .5) stated for the pprts path with every layer 1-D (dz/dx > twostr_ratio), where pprts IS a delta-Eddington
+    two-stream column: S(1) = incSolar, S(ke1) = exp(-sum(dtau)/mu0) incSolar, Edn(1) = 0,
+    Eup(ke1) = (S(ke1) + Edn(ke1)) albedo.  pprts_get_result reports the direct beam on a horizontal surface, i.e. x mu0."""
+    ke, mu0, inc, albedo = 9, 0.5, 1e2, 0.1
+    dz = 300.0                                   # dz/dx = 3 > twostr_ratio = 2
+    dtau, w0, g = 1.0 / ke, 0.5, 0.5
+    kabs = np.full((ke, 3, 3), dtau * (1 - w0) / dz)
+    ksca = np.full((ke, 3, 3), dtau * w0 / dz)
+    s = ob.OracleSolver(oracle_lut, ke, 3, 3, 100., 100., ob.sundir_from_angles(0., 60.), np.full(ke, dz),
+                        diff_solver=1, rtol=1e-12, atol=1e-30)
+    assert all(s.l1d)
+    s.set_optical_properties(albedo, kabs, ksca, np.full((ke, 3, 3), g), ldelta_scaling=False)
+    assert s.solve(False, True, inc) == 0
+    edn, eup, abso, edir = s.get_result()
+    S = edir / mu0
+    assert np.allclose(S[0], inc, rtol=1e-12)
+    assert np.allclose(S[ke], np.exp(-ke * dtau / mu0) * inc, rtol=1e-7)
+    assert np.abs(edn[0]).max() == 0
+    assert np.allclose(eup[ke], (edir[ke] + edn[ke]) * albedo, rtol=1e-9)
+    # every column is the same two-stream problem: no horizontal structure
+    assert np.ptp(eup[0]) < 1e-9 * eup[0].mean()
+    s.destroy()

@@ -103,6 +103,7 @@ def lib():
         L.orc_need_new_solution.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.orc_polyfit.argtypes = [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
         L.orc_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
+        L.orc_dir2dir3_geometric_coeffs.argtypes = [c_double_p, c_double_p, C.c_double, C.c_int, c_double_p]
         L.orc_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, c_double_p, c_double_p]
         L.orc_get_buildings_result.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
         _lib = L
@@ -358,6 +359,25 @@ class OracleSolver:
             self.destroy()
         except Exception:
             pass
+
+
+def dir2dir3_geometric_coeffs(vertices, sundir, c_ext, num_intervals=0):
+    """src/geometric_coeffs.F90:34 -> (9,) coefficients"""
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    sd = np.ascontiguousarray(sundir, dtype=np.float64)
+    out = np.zeros(9)
+    if lib().orc_dir2dir3_geometric_coeffs(_dp(v), _dp(sd), float(c_ext), int(num_intervals), _dp(out)):
+        raise ValueError("Extinction coeff too small")
+    return out
+
+
+def setup_default_unit_cube_geometry(dx, dy, dz):
+    """src/boxmc_geometry.F90:157-173: a,b,c,d at z = 0, e,f,g,h at z = dz"""
+    v = np.zeros(24)
+    v[0:2] = (0, 0); v[3:5] = (dx, 0); v[6:8] = (0, dy); v[9:11] = (dx, dy)
+    v[12:14] = (0, 0); v[15:17] = (dx, 0); v[18:20] = (0, dy); v[21:23] = (dx, dy)
+    v[[14, 17, 20, 23]] = dz
+    return v
 
 
 def polyfit(vx, vy, d):

@@ -128,6 +128,11 @@ int orc_need_new_solution(orc_solver *s, int uid, double time, int have_time);
 int orc_polyfit(const double *vx, const double *vy, int n, int d, double *coef);
 void orc_get_solution_times(orc_solver *s, int uid, double *time30, double *maxnorm30);
 
+/* dir2dir3_geometric_coeffs (src/geometric_coeffs.F90:34-133): analytic dir2dir (9 values, flat index dst*3 + src as
+ * everywhere) of a 3-stream box with vertices a..h (24 values) for the sun vector `sundir` and extinction c_ext [1/m];
+ * num_intervals <= 0: the reference default of 10 */
+int orc_dir2dir3_geometric_coeffs(const double *vertices, const double *sundir, double c_ext, int num_intervals, double *coeffs);
+
 /* opt_buildings of solve_pprts / pprts_get_result (src/buildings.F90:40-69, src/pprts.F90:3194-3212, :3579-3677,
  * :4989-5145, :6011-6160).  iface: 1-based flattened index into (6,Nz,Nx,Ny), first axis fastest; face ids 1..6 =
  * top, bottom, left (x+0), right (x+1), rear (y+0), front (y+1).  planck may be NULL.  nfaces = 0: no buildings. */

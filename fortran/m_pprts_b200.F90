@@ -44,6 +44,7 @@ module m_pprts_b200
     integer(c_int) :: maxit_dir, maxit_diff, precond, device, keep_solutions, nxproc, nyproc, xrank, yrank, &
       & diff_explicit, krylov_fp32, collapseindex
     real(c_double) :: max_solution_err, max_solution_time
+    integer(c_int) :: geometric_coeffs
   end type
 
   interface

@@ -113,6 +113,11 @@ typedef struct {
    * (default 5e3/86400, src/tenstream_options.F90:90) and -max_solution_time [s] (default 0).  Both > 0 enables
    * lenable_solutions_err_estimates (src/pprts.F90:456-457). */
   double max_solution_err, max_solution_time;
+  /* -pprts_geometric_coeffs (src/pprts.F90:3046-3053): the direct-beam coefficients of every 3-D cell come from its
+   * geometry (src/geometric_coeffs.F90; sloped top/bottom faces of a dz3d terrain-following grid, planar faces and
+   * parallel planes as in the reference's defaults) instead of the LUT, and dir2diff is rescaled to conserve the LUT's
+   * absorption (-pprts_conserve_lut_atm_abso, :3324-3351).  3 direct streams only (3_10, 3_24).  Default 0. */
+  int geometric_coeffs;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);

@@ -48,7 +48,7 @@ class _Config(C.Structure):
                 ("twostr_ratio", C.c_double), ("coeff_fp32", C.c_int), ("by_coeff_divergence", C.c_int),
                 ("diff_solver", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("nthreads", C.c_int), ("collapseindex", C.c_int),
-                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double)]
+                ("geometric_coeffs", C.c_int), ("max_solution_err", C.c_double), ("max_solution_time", C.c_double)]
 
 
 _lib = None
@@ -233,7 +233,7 @@ class OracleSolver:
     def __init__(self, lut: OracleLut, Nz, Nx, Ny, dx, dy, sundir, dz, solver_id=310, twostr_ratio=2.0,
                  coeff_fp32=False, by_coeff_divergence=True, diff_solver=0, rtol=-1.0, atol=-1.0,
                  maxit_dir=0, maxit_diff=0, nthreads=0, collapseindex=1, max_solution_err=5e3 / 86400.,
-                 max_solution_time=0.0):
+                 max_solution_time=0.0, geometric_coeffs=False):
         self.lut = lut
         ci = max(1, int(collapseindex))
         self.Nz_atm = Nz
@@ -244,7 +244,7 @@ class OracleSolver:
         self._dz = f_order(dz)
         cfg = _Config(solver_id, Nz, Nx, Ny, dx, dy, _dp(self._dz), (C.c_double * 3)(*sundir), twostr_ratio,
                       int(coeff_fp32), int(by_coeff_divergence), diff_solver, rtol, atol, maxit_dir, maxit_diff,
-                      nthreads, ci, max_solution_err, max_solution_time)
+                      nthreads, ci, int(geometric_coeffs), max_solution_err, max_solution_time)
         self._h = lib().orc_solver_create(C.byref(cfg), C.byref(lut._lut))
         if not self._h:
             raise RuntimeError("orc_solver_create failed")

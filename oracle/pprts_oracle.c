@@ -1146,17 +1146,71 @@ static void store_coeff(const orc_solver *s, const double *v, double *dst, int n
   if (s->cfg.coeff_fp32) for (c = 0; c < n; ++c) dst[c] = (double)(float)v[c];
   else for (c = 0; c < n; ++c) dst[c] = v[c];
 }
-static void alloc_coeffs(orc_solver *s, int lsolar) {
+/* determine_vertex_heights (src/pprts.F90:726-755): height of vertex (k, i, j), k an atmosphere level, i in -1..Nx,
+ * j in -1..Ny: minus the layer thicknesses above it in the column it belongs to, clamped into the local domain */
+static double vert_height(const orc_solver *s, int katm, int i, int j) {
+  const int Nza = s->Nz_atm, Nx = s->Nx;
+  const int ci = i < 0 ? 0 : (i > s->Nx - 1 ? s->Nx - 1 : i), cj = j < 0 ? 0 : (j > s->Ny - 1 ? s->Ny - 1 : j);
+  double h = 0.0;
+  int k;
+  for (k = 0; k < katm; ++k) h = h - s->dz_atm[k + (long)Nza * (ci + (long)Nx * cj)];
+  return h;
+}
+/* setup_default_unit_cube_geometry(dx, dy, -1) + init_vertices (src/pprts.F90:3057-3085, :3130-3143) with
+ * ltop_bottom_faces_planar = ltop_bottom_planes_parallel = .true. (their defaults under -pprts_geometric_coeffs),
+ * then the z shift of :3143 */
+static void cell_vertices(const orc_solver *s, int k, int i, int j, double *v) {
+  const int ka = k + s->icollapse - 1; /* atmk(k) */
+  const double dz = s->dz_atm[ka + (long)s->Nz_atm * (i + (long)s->Nx * j)];
+  double zmin;
+  int q;
+  for (q = 0; q < 24; ++q) v[q] = 0.0;
+  v[3] = s->dx; v[7] = s->dy; v[9] = s->dx; v[10] = s->dy;
+  v[15] = s->dx; v[19] = s->dy; v[21] = s->dx; v[22] = s->dy;
+  v[2] = vert_height(s, ka + 1, i, j);       /* hs(2,1,1) */
+  v[5] = vert_height(s, ka + 1, i + 1, j);   /* hs(2,2,1) */
+  v[8] = vert_height(s, ka + 1, i, j + 1);   /* hs(2,1,2) */
+  v[11] = v[8] + (v[5] - v[2]);              /* planar faces */
+  for (q = 0; q < 4; ++q) v[14 + 3 * q] = v[2 + 3 * q] + dz; /* parallel planes */
+  zmin = v[2];
+  for (q = 1; q < 8; ++q) zmin = dmin(zmin, v[2 + 3 * q]);
+  for (q = 0; q < 8; ++q) v[2 + 3 * q] -= zmin;
+}
+static int alloc_coeffs(orc_solver *s, int lsolar) {
   LOCALS
   long col;
-#pragma omp parallel for schedule(static)
+  int bad = 0;
+  if (s->cfg.geometric_coeffs && lsolar && Nd != 3) return 1; /* 'only implemented for 3 direct streams', :3124-3125 */
+#pragma omp parallel for schedule(static) reduction(| : bad)
   for (col = 0; col < (long)Nx * Ny; ++col) {
     int i = (int)(col % Nx), j = (int)(col / Nx), k;
     double v[ORC_MAX_DOF * ORC_MAX_DOF];
     for (k = 0; k < Nz; ++k) {
       if (s->l1d[k]) continue;
       double ka = A3(s->kabs, k, i, j), ks = A3(s->ksca, k, i, j), gg = A3(s->g, k, i, j), dz = A3(s->dz, k, i, j);
-      if (lsolar) {
+      if (lsolar && s->cfg.geometric_coeffs) {
+        /* -pprts_geometric_coeffs (:3142-3149) with -pprts_conserve_lut_atm_abso (its default then, :3272-3273, :3324-3351):
+         * dir2dir from the geometry of the cell, dir2diff = the LUT's distribution over the diffuse streams scaled so
+         * that every source loses to absorption exactly what the LUT says */
+        double T_LUT[9], S_LUT[3 * ORC_MAX_DOF], T_G[9], vert[24];
+        int src, dst;
+        orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 1, s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
+        store_coeff(s, v, T_LUT, Nd * Nd);
+        orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 2, s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
+        store_coeff(s, v, S_LUT, Nd * Nf);
+        cell_vertices(s, k, i, j, vert);
+        if (orc_dir2dir3_geometric_coeffs(vert, s->sundir, ka + ks, 0, T_G)) { bad |= 2; continue; }
+        for (src = 0; src < Nd; ++src) {
+          double Sn = 0, Tn = 0, Tg = 0;
+          for (dst = 0; dst < Nf; ++dst) Sn += S_LUT[dst * Nd + src];
+          for (dst = 0; dst < Nd; ++dst) { Tn += T_LUT[dst * Nd + src]; Tg += T_G[dst * Nd + src]; }
+          for (dst = 0; dst < Nf; ++dst) {
+            double sg = (Sn <= DBL_EPSILON) ? 0.0 : S_LUT[dst * Nd + src] / Sn;
+            CF(s->dir2diff, Nd * Nf, dst * Nd + src, k, i, j) = sg * (1.0 - (1.0 - Tn - Sn) - Tg);
+          }
+        }
+        for (dst = 0; dst < Nd * Nd; ++dst) CF(s->dir2dir, Nd * Nd, dst, k, i, j) = T_G[dst];
+      } else if (lsolar) {
         orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 1, s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
         store_coeff(s, v, &CF(s->dir2dir, Nd * Nd, 0, k, i, j), Nd * Nd);
         orc_get_coeff(s->lut, &s->st, ka, ks, gg, dz, s->dx, 2, s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
@@ -1166,10 +1220,12 @@ static void alloc_coeffs(orc_solver *s, int lsolar) {
       store_coeff(s, v, &CF(s->diff2diff, Nf * Nf, 0, k, i, j), Nf * Nf);
     }
   }
+  if (bad) return bad;
   if (s->nbld) { /* :3188-3190, :3492-3494 */
     if (lsolar) set_buildings_coeff_dir2dir(s);
     set_buildings_coeff_diff2diff(s);
   }
+  return 0;
 }
 
 /* ---- scale_flx (src/pprts.F90:3682-3741) ------------------------------------------------------------------------ */
@@ -1949,7 +2005,7 @@ static int solve_impl(orc_solver *s, int lthermal, int lsolar, double edirTOA, i
     return 0;
   }
   /* pprts(), :2668-3033 */
-  alloc_coeffs(s, sol->lsolar_rad);
+  { int ec = alloc_coeffs(s, sol->lsolar_rad); if (ec) return 20 + ec; } /* 21: geometric coeffs need 3 direct streams, 22: extinction too small */
   scale_flx(s, sol, 0);
   if (sol->lsolar_rad) rc |= explicit_edir(s, edirTOA, sol);
   setup_b(s, sol);

@@ -9,6 +9,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "geometric_coeffs.cuh"
 
 #define PB_PI 3.14159265358979323846
 
@@ -397,6 +398,79 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
   }
 #pragma unroll
   for (int s = 0; s < Nd; ++s) cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1[s] - sum2[s];  // src/pprts.F90:5315
+}
+
+// -pprts_geometric_coeffs (src/pprts.F90:3046-3053, :3130-3149, :3272-3273, :3324-3351): after k_lookup has stored the
+// LUT's dir2dir (T_LUT) and dir2diff (S_LUT), the direct-beam coefficients of every 3-D cell are replaced by the
+// analytic ones of its (sloped) geometry and dir2diff is rescaled per source stream so that the cell absorbs exactly
+// what the LUT says: S_G(:, src) = S_LUT(:, src) / |S_LUT| * (|T_LUT| + |S_LUT| - |T_G|).
+// Vertices: setup_default_unit_cube_geometry + init_vertices with planar faces and parallel planes (the defaults under
+// -pprts_geometric_coeffs); vh is determine_vertex_heights (:726-755) on the solver levels, clamped to the local domain.
+__global__ void k_vert_heights(long ncol, int nz, const double *__restrict__ dz, double *__restrict__ vh) {
+  long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double h = 0.0;
+  vh[col] = h;
+  for (int k = 0; k < nz; ++k) { h = h - dz[(long)k * ncol + col]; vh[(long)(k + 1) * ncol + col] = h; }
+}
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_geometric_coeffs(Grid g, int kstart, double sunx, double suny, double sunz, const double *__restrict__ kabs,
+                   const double *__restrict__ ksca, const double *__restrict__ dz, const double *__restrict__ vh,
+                   CT *__restrict__ d2d, CT *__restrict__ d2f, double *__restrict__ cdiv_dir, int *__restrict__ bad) {
+  constexpr int Nd = L::Nd, Nf = L::Nf;
+  static_assert(Nd == 3, "geometric coeffs are only implemented for 3 direct streams (src/pprts.F90:3124-3125)");
+  long c = (long)kstart * g.ncol + (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.ncell) return;
+  const int k = (int)(c / g.ncol);
+  const long col = c - (long)k * g.ncol;
+  const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
+  const int ip = min(i + 1, g.Nx - 1), jp = min(j + 1, g.Ny - 1);
+  const long l1 = (long)(k + 1) * g.ncol;
+  double v[24];
+#pragma unroll
+  for (int q = 0; q < 24; ++q) v[q] = 0.0;
+  v[3] = g.dx; v[7] = g.dy; v[9] = g.dx; v[10] = g.dy;
+  v[15] = g.dx; v[19] = g.dy; v[21] = g.dx; v[22] = g.dy;
+  v[2] = vh[l1 + (long)j * g.Nx + i];
+  v[5] = vh[l1 + (long)j * g.Nx + ip];
+  v[8] = vh[l1 + (long)jp * g.Nx + i];
+  v[11] = v[8] + (v[5] - v[2]);
+  const double dzc = dz[c];
+  double zmin = v[2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { v[14 + 3 * q] = v[2 + 3 * q] + dzc; zmin = fmin(zmin, fmin(v[2 + 3 * q], v[14 + 3 * q])); }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[2 + 3 * q] -= zmin;
+  const double sundir[3] = {sunx, suny, sunz};
+  double TG[9];
+  if (geom_dir2dir3_coeffs(v, sundir, kabs[c] + ksca[c], 0, TG)) { atomicOr(bad, 4); return; }
+  const long cb_dd = cbase<Nd * Nd>(c), cb_df = cbase<Nd * Nf>(c);
+#pragma unroll
+  for (int s = 0; s < Nd; ++s) {
+    double Sn = 0.0, Tn = 0.0, Tg = 0.0;
+    for (int dst = 0; dst < Nf; ++dst) Sn += (double)d2f[cb_df + (dst * Nd + s) * PB_TILE];
+#pragma unroll
+    for (int dst = 0; dst < Nd; ++dst) { Tn += (double)d2d[cb_dd + (dst * Nd + s) * PB_TILE]; Tg += TG[dst * Nd + s]; }
+    const double scale = 1.0 - (1.0 - Tn - Sn) - Tg;
+    // The divergence factor is summed from the fp64 values: the reference keeps the analytic coefficients in fp64
+    // (ireals), and with fp32 storage 1 - sum(T) - sum(S) of the ROUNDED values would lose the small absorbed fraction
+    // of clear-air cells to the rounding (5e-4 of abso in the parity test).
+    double sum2 = 0.0;
+    for (int dst = 0; dst < Nf; ++dst) {
+      const double sl = (double)d2f[cb_df + (dst * Nd + s) * PB_TILE];
+      const double sg = ((Sn <= DBL_EPSILON) ? 0.0 : sl / Sn) * scale;
+      d2f[cb_df + (dst * Nd + s) * PB_TILE] = (CT)sg;
+      sum2 += sg;
+    }
+    double sum1 = 0.0;
+#pragma unroll
+    for (int dst = 0; dst < Nd; ++dst) {
+      d2d[cb_dd + (dst * Nd + s) * PB_TILE] = (CT)TG[dst * Nd + s];
+      sum1 += TG[dst * Nd + s];
+    }
+    cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1 - sum2;
+  }
 }
 
 // fp64 lookup of n arbitrary sample cells (coefficient probe / parity hook); out[(coef) + ncoef*n]

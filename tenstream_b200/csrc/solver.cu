@@ -225,6 +225,7 @@ struct pprts_b200_solver {
   int mm_variant = 2;  // 0: 2 stages + register prefetch, 1: 2 stages, 2: 1 stage x 4 CTAs/SM (fastest measured)
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
+  double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
   float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the block (3_24) sweeps on fp32 vectors
   bool prec_ready = false;
   int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
@@ -649,6 +650,12 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   CU(cudaMallocHost((void **)&s->h_sc, SC_COUNT * sizeof(double)));
   CU(cudaMallocHost((void **)&s->h_bad, sizeof(int)));
   CU(cudaMemcpy(s->atm_dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (cfg->geometric_coeffs) {  // determine_vertex_heights (src/pprts.F90:726-755)
+    if (Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
+    DA(s->vh_atm, s->nlev_atm);
+    k_vert_heights<<<nblk(g.ncol, 128), 128, 0, s->stream>>>(g.ncol, s->Nz_atm, s->atm_dz, s->vh_atm);
+    s->vh = s->vh_atm + (size_t)(s->icollapse - 1) * g.ncol;
+  }
 
   // LUT to the device: the four shared axes, the diffuse table; direct tables are contracted per sun angle
   long lat4 = 1;
@@ -685,7 +692,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
                     s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
-  cudaFree(s->precRf); cudaFree(s->precInvf);
+  cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->vh_atm);
   cudaFree(s->bld_iface); cudaFree(s->bld_albedo); cudaFree(s->bld_planck); cudaFree(s->bld_out);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
   cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
@@ -823,6 +830,26 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
     DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_lookup<L, CT>), nblk(n3d, 128), 128, g, s->lutdev, s->sym, (int)lsolar,
                            s->n1d, s->kabs, s->ksca, s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f,
                            s->cdiv_dir, s->cdiv_diff, (unsigned char *)s->tile_class));
+  }
+  if (s->cfg.geometric_coeffs && lsolar && n3d > 0) {  // src/pprts.F90:3142-3149, :3324-3351
+    const double d2r = PB_PI / 180.0;  // sun%sundir = spherical_2_cartesian(phi, theta) (:1148)
+    const double th = s->theta < 0 ? 90.0 : s->theta;
+    const double sx = -std::sin(th * d2r) * std::sin(s->phi * d2r), sy = -std::sin(th * d2r) * std::cos(s->phi * d2r),
+                 sz = -std::cos(th * d2r);
+    CU(cudaMemsetAsync(s->bad, 0, sizeof(int), s->stream));
+    bool launched = false;
+    DISPATCH_LC(s, {
+      if constexpr (L::Nd == 3) {
+        LAUNCH(s, FAM_LOOKUP, (k_geometric_coeffs<L, CT>), nblk(n3d, 128), 128, g, s->n1d, sx, sy, sz,
+               (const double *)s->kabs, (const double *)s->ksca, (const double *)s->dz, (const double *)s->vh,
+               (CT *)s->d2d, (CT *)s->d2f, s->cdiv_dir, s->bad);
+        launched = true;
+      }
+    });
+    if (!launched) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
+    CU(cudaMemcpyAsync(s->h_bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (*s->h_bad) return set_err(24, "Extinction coeff too small for the geometric coefficients (kabs + ksca < tiny in a 3-D cell)");
   }
   if (s->nbld > 0) {  // set_buildings_coeff (src/pprts.F90:3188-3212, :3492-3494, :3579-3677)
     DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_buildings_coeff<L, CT>), nblk(s->nbld, 128), 128, g, (int)lsolar, s->nbld,

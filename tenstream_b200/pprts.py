@@ -44,7 +44,7 @@ class _Config(C.Structure):
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
                 ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int),
-                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double)]
+                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double), ("geometric_coeffs", C.c_int)]
 
 
 class _Bands(C.Structure):
@@ -290,7 +290,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
                keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
-               max_solution_time=None) -> Solver:
+               max_solution_time=None, geometric_coeffs=False) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -332,6 +332,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
         cfg.max_solution_err = float(max_solution_err)
     if max_solution_time is not None:
         cfg.max_solution_time = float(max_solution_time)
+    cfg.geometric_coeffs = int(bool(geometric_coeffs))      # -pprts_geometric_coeffs
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
     if cfg.nxproc * cfg.nyproc > 1:

@@ -192,3 +192,26 @@ def test_c5_hill_stream_variants(P, solver_id, capsys):
     assert edir[0] == pytest.approx(sc["edirTOA"] * np.cos(np.deg2rad(sc["theta0"])), rel=1e-12)
     P.destroy_pprts(s)
     lut.close()
+
+
+def test_c5_hill_geometric_coeffs(P, bench_lut):
+    """configs[4] with the option examples/pprts_hill/hill.sh runs it with (-pprts_geometric_coeffs): 3_10 on the hill at
+    256x256x80, analytic direct-beam coefficients of the sloped cells; energy closure and the LUT's absorption are kept"""
+    from tenstream_b200 import scenarios
+    sc = scenarios.hill_field()
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    res = {}
+    for geo in (False, True):
+        s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]), dz3d=sc["dz3d"],
+                         lut=bench_lut, coeff_fp32=True, krylov_fp32=True, rtol=1e-7, atol=1e-30, geometric_coeffs=geo)
+        P.set_optical_properties(s, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+        P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+        edn, eup, abso, edir = P.pprts_get_result(s, 1)
+        inc = edir[0].sum() + edn[0].sum()
+        out = eup[0].sum() + (edir[-1].sum() + edn[-1].sum() - eup[-1].sum()) + (abso * sc["dz3d"]).sum()
+        assert abs(out / inc - 1) < 1e-5, (geo, out / inc)
+        res[geo] = (edir[-1].mean(), edn[-1].mean(), (abso * sc["dz3d"]).sum())
+        P.destroy_pprts(s)
+    # same absorbed fraction per cell and stream by construction -> domain absorption close; the beam is redistributed
+    assert abs(res[True][2] / res[False][2] - 1) < 0.05
+    assert abs(res[True][0] / res[False][0] - 1) < 0.10

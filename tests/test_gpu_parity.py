@@ -902,3 +902,52 @@ def test_twostr_properties_in_all_1d_atmosphere(P, gpu_lut):
     assert np.allclose(eup[ke], (edir[ke] + edn[ke]) * albedo, rtol=1e-9)
     assert np.ptp(eup[0]) < 1e-9 * eup[0].mean()
     P.destroy_pprts(s)
+
+
+# ---- -pprts_geometric_coeffs (src/geometric_coeffs.F90, src/pprts.F90:3130-3149, :3324-3351) --------------
+@pytest.mark.parametrize("phi0,theta0", [(200., 35.), (40., 60.), (300., 10.)])
+@pytest.mark.parametrize("coeff_fp32", [False, True])
+def test_geometric_coeffs_vs_oracle(P, gpu_lut, oracle_lut, phi0, theta0, coeff_fp32):
+    """Terrain-following grid (dz3d hill): analytic dir2dir of the sloped cells and the absorption-conserving dir2diff
+    on the GPU against the oracle (whose routine is pinned on the reference's Monte-Carlo targets), then the fluxes."""
+    from oracle import binding as ob
+    rng = np.random.default_rng(3)
+    Nz, Nx, Ny = 6, 5, 8
+    j = np.arange(Ny)
+    dz3d = np.broadcast_to(60. * (1.0 - 0.35 / (1.0 + ((j - Ny / 2.0) / (Ny / 6.0)) ** 2))[None, None, :], (Nz, Nx, Ny)).copy()
+    kabs = 10 ** rng.uniform(-6, -4, (Nz, Nx, Ny))
+    ksca = 10 ** rng.uniform(-5, -3, (Nz, Nx, Ny))
+    g = rng.uniform(0, 0.8, (Nz, Nx, Ny))
+    sd = P.sundir_from_angles(phi0, theta0)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz3d=dz3d, lut=gpu_lut, coeff_fp32=coeff_fp32, rtol=1e-10, atol=1e-30,
+                     geometric_coeffs=True)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz3d, coeff_fp32=coeff_fp32, diff_solver=1, rtol=1e-10,
+                        atol=1e-30, geometric_coeffs=True)
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    o.set_optical_properties(0.2, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000.)
+    assert o.solve(False, True, 1000.) == 0
+    ctol = 1e-6 if coeff_fp32 else 1e-11       # fp32 storage rounds the analytic values, the oracle keeps them in fp64
+    for w in (1, 2):
+        a, b = s.coeffs(w), o.coeffs(w)
+        assert np.abs(a - b).max() <= ctol * np.abs(b).max(), w
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b) < (1e-5 if coeff_fp32 else 1e-7), (name, relerr(a, b))
+    P.destroy_pprts(s); o.destroy()
+
+
+def test_geometric_coeffs_errors(P, gpu_lut, tmp_path):
+    from tenstream_b200 import lut as L
+    z = np.zeros((4, 3, 4))
+    s = P.init_pprts(0, 4, 3, 4, 100., 100., P.sundir_from_angles(10., 30.), dz1d=np.full(4, 60.), lut=gpu_lut,
+                     geometric_coeffs=True)
+    P.set_optical_properties(s, 0.1, z, z, z)                  # vacuum (geometric_coeffs.F90:42-43)
+    with pytest.raises(P.PprtsError, match="Extinction coeff too small"):
+        P.solve_pprts(s, False, True, 1000.)
+    P.destroy_pprts(s)
+    cfg = L.small_test_config(810)                              # 8 direct streams (src/pprts.F90:3124-3125)
+    lut = P.Lut(cfg, L.write_synthetic_lut(cfg, str(tmp_path / "LUT810")))
+    with pytest.raises(P.PprtsError, match="only implemented for 3 direct streams"):
+        P.init_pprts(0, 4, 3, 4, 100., 100., P.sundir_from_angles(10., 30.), dz1d=np.full(4, 60.), lut=lut, solver=810,
+                     geometric_coeffs=True)
+    lut.close()

@@ -70,3 +70,70 @@ def test_too_small_extinction_is_an_error():
     verts = ob.setup_default_unit_cube_geometry(1., 1., 1.)
     with pytest.raises(ValueError):
         ob.dir2dir3_geometric_coeffs(verts, sun(180., 0.), 0.0)
+
+
+# ---- the solver with -pprts_geometric_coeffs (src/pprts.F90:3130-3149, :3324-3351) ---------------------------------------
+def hill_dz(Nz, Nx, Ny, dz=60.):
+    """terrain-following layers: every layer of a column shrinks with a Lorentzian hill in y (examples/pprts_hill)"""
+    j = np.arange(Ny)
+    dP = 0.35 / (1.0 + ((j - Ny / 2.0) / (Ny / 6.0)) ** 2)
+    return np.broadcast_to(dz * (1.0 - dP)[None, None, :], (Nz, Nx, Ny)).copy()
+
+
+def make_atm(Nz, Nx, Ny, seed=3):
+    rng = np.random.default_rng(seed)
+    kabs = 10 ** rng.uniform(-6, -4, (Nz, Nx, Ny))
+    ksca = 10 ** rng.uniform(-5, -3, (Nz, Nx, Ny))
+    g = rng.uniform(0, 0.8, (Nz, Nx, Ny))
+    return kabs, ksca, g
+
+
+def solve(oracle_lut, dz, geometric, phi=200., theta=35., **kw):
+    Nz, Nx, Ny = dz.shape
+    kabs, ksca, g = make_atm(Nz, Nx, Ny)
+    s = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., ob.sundir_from_angles(phi, theta), dz, diff_solver=1,
+                        rtol=1e-10, atol=1e-30, geometric_coeffs=geometric, **kw)
+    s.set_optical_properties(0.2, kabs, ksca, g)
+    assert s.solve(False, True, 1000.) == 0
+    out = dict(res=s.get_result(), T=s.coeffs(1).copy(), S=s.coeffs(2).copy())
+    s.destroy()
+    return out
+
+
+def test_solver_conserves_the_luts_absorption(oracle_lut):
+    """-pprts_conserve_lut_atm_abso: per cell and source stream sum(T_G) + sum(S_G) == sum(T_LUT) + sum(S_LUT)"""
+    dz = hill_dz(6, 5, 8)
+    lut, geo = solve(oracle_lut, dz, False), solve(oracle_lut, dz, True)
+    Nd = 3
+    for src in range(Nd):
+        tot_lut = lut["T"][src::Nd].sum(axis=0) + lut["S"][src::Nd].sum(axis=0)
+        tot_geo = geo["T"][src::Nd].sum(axis=0) + geo["S"][src::Nd].sum(axis=0)
+        assert np.abs(tot_lut - tot_geo).max() < 1e-12
+    assert np.abs(lut["T"] - geo["T"]).max() > 1e-3           # and it does change the direct transport on the slope
+    assert (geo["T"] >= 0).all() and (geo["S"] >= -1e-15).all()
+
+
+def test_solver_energy_closure_on_a_hill(oracle_lut):
+    dz = hill_dz(6, 5, 8)
+    edn, eup, abso, edir = solve(oracle_lut, dz, True)["res"]
+    inc = edir[0].sum() + edn[0].sum()
+    out = eup[0].sum() + (edir[-1].sum() + edn[-1].sum() - eup[-1].sum()) + (abso * dz).sum()
+    assert abs(out / inc - 1) < 1e-8
+
+
+def test_flat_grid_geometric_close_to_table(oracle_lut):
+    """On a regular box the analytic coefficients and the (synthetic, also geometric) table describe the same beam:
+    the surface irradiance differs by a few per cent at most"""
+    dz = np.full((6, 5, 6), 60.)
+    lut, geo = solve(oracle_lut, dz, False)["res"], solve(oracle_lut, dz, True)["res"]
+    assert abs(geo[3][-1].mean() / lut[3][-1].mean() - 1) < 0.05
+    assert abs(geo[0][-1].mean() / lut[0][-1].mean() - 1) < 0.10
+
+
+def test_errors(oracle_lut):
+    dz = hill_dz(4, 3, 4)
+    s = ob.OracleSolver(oracle_lut, 4, 3, 4, 100., 100., ob.sundir_from_angles(10., 30.), dz, geometric_coeffs=True)
+    z = np.zeros((4, 3, 4))
+    s.set_optical_properties(0.1, z, z, z)            # vacuum: 'Extinction coeff too small' (geometric_coeffs.F90:42-43)
+    assert s.solve(False, True, 1000.) == 22
+    s.destroy()

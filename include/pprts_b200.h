@@ -204,6 +204,14 @@ int pprts_b200_comm_init(pprts_b200_solver *solver, int nranks, int rank, const 
 /* sum of the accumulated spectral integrals over all ranks (final flux / heating-rate reduction) */
 int pprts_b200_allreduce_accumulated(pprts_b200_solver *solver);
 
+/* slope_correction_fluxes(solver, edir) (src/pprts_postprocess.F90:130-196), the spectral callers' post-processing of
+ * the direct flux on a terrain-following grid: lslope = -pprts_slope_correction (surface level x max(0, sundir.n /
+ * sundir.ez), n the surface normal from hgrad, src/pprts.F90:621-638), latm = -pprts_atm_correction (every level x
+ * sundir.ez / sundir.n).  edir: host (Nz+1,Nx,Ny) column-major, in place.  Needs dz3d; single periodic domain. */
+int pprts_b200_slope_correction_fluxes(pprts_b200_solver *solver, int lslope, int latm, double *edir);
+/* the same applied to the direct flux of the device-side spectral sum (before pprts_b200_get_accumulated) */
+int pprts_b200_slope_correct_accumulated(pprts_b200_solver *solver, int lslope, int latm);
+
 /* ---- buildings: the opt_buildings argument of solve_pprts / pprts_get_result ------------------------------------
  * Replaces type(t_pprts_buildings) (src/buildings.F90:40-69) as consumed by alloc_coeff_dir2dir / alloc_coeff_diff2diff
  * (src/pprts.F90:3194-3212, :3579-3677), setup_b (:4989-5145) and pprts_get_result (:6011-6160).

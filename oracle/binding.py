@@ -104,6 +104,7 @@ def lib():
         L.orc_polyfit.argtypes = [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
         L.orc_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
         L.orc_dir2dir3_geometric_coeffs.argtypes = [c_double_p, c_double_p, C.c_double, C.c_int, c_double_p]
+        L.orc_slope_correction_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]
         L.orc_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, c_double_p, c_double_p]
         L.orc_get_buildings_result.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
         _lib = L
@@ -239,6 +240,7 @@ class OracleSolver:
         self.Nz_atm = Nz
         self.Nz, self.Nx, self.Ny = Nz - ci + 1, Nx, Ny   # solver grid (results) after the collapse
         dz = np.asarray(dz, dtype=np.float64)
+        self._dz3d = dz.ndim == 3          # init_pprts(dz3d=...): atm%hgrad exists (src/pprts.F90:621)
         if dz.ndim == 1:
             dz = np.broadcast_to(dz[:, None, None], (Nz, Nx, Ny))
         self._dz = f_order(dz)
@@ -307,6 +309,15 @@ class OracleSolver:
         if rc:
             raise RuntimeError(f"orc_get_buildings_result -> {rc}")
         return edir, inc, out
+
+    def slope_correction_fluxes(self, edir, lslope=True, latm=False):
+        """slope_correction_fluxes(solver, edir) (src/pprts_postprocess.F90:130); returns the corrected copy"""
+        e = f_order(edir).copy(order="F")
+        rc = lib().orc_slope_correction_fluxes(self._h, int(lslope), int(latm), int(self._dz.ndim == 3 and self._dz3d),
+                                               _dp(e))
+        if rc:
+            raise RuntimeError("slope correction needs a 3-D dz (atm%hgrad)")
+        return e
 
     def coeffs(self, which):
         n = {1: self.Nd ** 2, 2: self.Nd * self.Nf, 3: self.Nf ** 2}[which]

@@ -2133,6 +2133,31 @@ int orc_get_buildings_result(orc_solver *s, int uid, double *edir, double *incom
   return 0;
 }
 
+/* slope_correction_fluxes (src/pprts_postprocess.F90:130-196), the callers' post-processing of the direct flux on a
+ * terrain-following grid: hgrad (src/pprts.F90:621-638) = centred differences of the level heights hhl = -cumsum(dz)
+ * with the periodic halo of one rank; -pprts_atm_correction scales every level by (sundir.ez)/(sundir.n),
+ * -pprts_slope_correction the surface level by max(0, (sundir.n)/(sundir.ez)), n the normal of the level surface.
+ * edir: (Nz+1, Nx, Ny) Fortran order on the solver grid, in place.  Returns 1 without a 3-D dz (hgrad missing). */
+int orc_slope_correction_fluxes(orc_solver *s, int lslope, int latm, int have_dz3d, double *edir) {
+  LOCALS
+  int k, i, j;
+  if (!lslope && !latm) return 0;
+  if (!have_dz3d) return 1;
+  for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) {
+    const int ka = k + s->icollapse - 1;
+    const int im = (i + Nx - 1) % Nx, ip = (i + 1) % Nx, jm = (j + Ny - 1) % Ny, jp = (j + 1) % Ny;
+    const double gx = (vert_height(s, ka, ip, j) - vert_height(s, ka, im, j)) / (2.0 * s->dx);
+    const double gy = (vert_height(s, ka, i, jp) - vert_height(s, ka, i, jm)) / (2.0 * s->dy);
+    /* n = cross([1,0,gx],[0,1,gy]) normalised */
+    double n[3] = {-gx, -gy, 1.0}, nn = sqrt(gx * gx + gy * gy + 1.0), sn, sz = s->sundir[2];
+    n[0] /= nn; n[1] /= nn; n[2] /= nn;
+    sn = s->sundir[0] * n[0] + s->sundir[1] * n[1] + s->sundir[2] * n[2];
+    if (latm) P3(edir, k, i, j) = P3(edir, k, i, j) * (sz / sn);
+    if (lslope && k == Nz) P3(edir, k, i, j) = P3(edir, k, i, j) * dmax(0.0, sn / sz);
+  }
+  return 0;
+}
+
 const double *orc_coeff_ptr(orc_solver *s, int which) { return which == 1 ? s->dir2dir : which == 2 ? s->dir2diff : s->diff2diff; }
 const double *orc_state_ptr(orc_solver *s, int uid, int which) {
   orc_solution *sol = s->sol[uid - ORC_UID_MIN];

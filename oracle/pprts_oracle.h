@@ -142,6 +142,10 @@ int orc_dir2dir3_geometric_coeffs(const double *vertices, const double *sundir, 
 int orc_set_buildings(orc_solver *s, int nfaces, const int *iface, const double *albedo, const double *planck);
 int orc_get_buildings_result(orc_solver *s, int uid, double *edir, double *incoming, double *outgoing);
 
+/* slope_correction_fluxes (src/pprts_postprocess.F90:130-196): -pprts_slope_correction / -pprts_atm_correction applied
+ * to a direct-flux result (Nz+1,Nx,Ny) in place; have_dz3d = 0 (no hgrad) with a correction requested returns 1 */
+int orc_slope_correction_fluxes(orc_solver *s, int lslope, int latm, int have_dz3d, double *edir);
+
 /* introspection used by the parity tests */
 const double *orc_coeff_ptr(orc_solver *s, int which); /* 1 dir2dir, 2 dir2diff, 3 diff2diff: (ncoef,Nz,Nx,Ny) */
 const double *orc_state_ptr(orc_solver *s, int uid, int which); /* 1 edir (Nd,Nz+1,Nx,Ny), 2 ediff, 3 abso, 4 b */

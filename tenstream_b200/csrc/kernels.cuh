@@ -473,6 +473,28 @@ k_geometric_coeffs(Grid g, int kstart, double sunx, double suny, double sunz, co
   }
 }
 
+// slope_correction_fluxes (src/pprts_postprocess.F90:130-196) on a direct-flux level field in the device layout:
+// hgrad (src/pprts.F90:621-638) = centred differences of the level heights (vh = -cumsum dz, periodic single domain);
+// latm scales every level by (sundir.ez)/(sundir.n), lslope the surface level by max(0, (sundir.n)/(sundir.ez)).
+__global__ void k_slope_correction(Grid g, int lslope, int latm, double sunx, double suny, double sunz,
+                                   const double *__restrict__ vh, double *__restrict__ edir) {
+  long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= g.nlev) return;
+  const int k = (int)(l / g.ncol);
+  const long col = l - (long)k * g.ncol;
+  const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
+  const int im = i == 0 ? g.Nx - 1 : i - 1, ip = wrap_p(i, g.Nx), jm = j == 0 ? g.Ny - 1 : j - 1, jp = wrap_p(j, g.Ny);
+  const long lk = (long)k * g.ncol;
+  const double gx = (vh[lk + (long)j * g.Nx + ip] - vh[lk + (long)j * g.Nx + im]) / (2.0 * g.dx);
+  const double gy = (vh[lk + (long)jp * g.Nx + i] - vh[lk + (long)jm * g.Nx + i]) / (2.0 * g.dy);
+  const double nn = sqrt(gx * gx + gy * gy + 1.0);
+  const double sn = sunx * (-gx / nn) + suny * (-gy / nn) + sunz * (1.0 / nn);
+  double e = edir[l];
+  if (latm) e = e * (sunz / sn);
+  if (lslope && k == g.Nz) e = e * fmax(0.0, sn / sunz);
+  edir[l] = e;
+}
+
 // fp64 lookup of n arbitrary sample cells (coefficient probe / parity hook); out[(coef) + ncoef*n]
 template <class L>
 __global__ void k_lookup_probe(LutDev lut, SymMaps sym, int mode, long n, double dx, const double *__restrict__ kabs,

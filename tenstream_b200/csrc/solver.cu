@@ -226,6 +226,7 @@ struct pprts_b200_solver {
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
   double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
+  bool have_dz3d = false;                   // init_pprts(dz3d=...): atm%hgrad exists (src/pprts.F90:621)
   float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the block (3_24) sweeps on fp32 vectors
   bool prec_ready = false;
   int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
@@ -576,6 +577,7 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   s->cfg = *cfg;
   if (s->cfg.twostr_ratio <= 0) s->cfg.twostr_ratio = 2.0;
   s->cfg.dz1d = s->cfg.dz3d = nullptr;
+  s->have_dz3d = cfg->dz3d != nullptr;
   s->lut = lut;
   s->Nd = Nd; s->Nf = Nf;
   if (cfg->device >= 0) { CU(cudaSetDevice(cfg->device)); s->device = cfg->device; }
@@ -650,8 +652,8 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   CU(cudaMallocHost((void **)&s->h_sc, SC_COUNT * sizeof(double)));
   CU(cudaMallocHost((void **)&s->h_bad, sizeof(int)));
   CU(cudaMemcpy(s->atm_dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
-  if (cfg->geometric_coeffs) {  // determine_vertex_heights (src/pprts.F90:726-755)
-    if (Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
+  if (cfg->geometric_coeffs && Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
+  if (cfg->geometric_coeffs || cfg->dz3d) {  // determine_vertex_heights / atm%hhl (src/pprts.F90:585-600, :726-755)
     DA(s->vh_atm, s->nlev_atm);
     k_vert_heights<<<nblk(g.ncol, 128), 128, 0, s->stream>>>(g.ncol, s->Nz_atm, s->atm_dz, s->vh_atm);
     s->vh = s->vh_atm + (size_t)(s->icollapse - 1) * g.ncol;
@@ -1801,6 +1803,52 @@ extern "C" int pprts_b200_get_buildings_result(pprts_b200_solver *s, int uid, do
   if (incoming) std::copy(h.begin() + n, h.begin() + 2 * n, incoming);
   if (outgoing) std::copy(h.begin() + 2 * n, h.end(), outgoing);
   return 0;
+}
+// slope_correction_fluxes(solver, edir) (src/pprts_postprocess.F90:130-196), the spectral callers' post-processing of
+// the direct flux on a terrain-following grid (rrtmg/rrtmg/pprts_rrtmg.F90 after the band sum).  edir: host array
+// (Nz+1,Nx,Ny) column-major, corrected in place.  Needs init with dz3d (atm%hgrad, src/pprts.F90:621) and one domain.
+static void sun_vector(const pprts_b200_solver *s, double v[3]) {  // sun%sundir = spherical_2_cartesian(phi, theta)
+  const double d2r = PB_PI / 180.0, th = s->theta < 0 ? 90.0 : s->theta;
+  v[0] = -std::sin(th * d2r) * std::sin(s->phi * d2r);
+  v[1] = -std::sin(th * d2r) * std::cos(s->phi * d2r);
+  v[2] = -std::cos(th * d2r);
+}
+static int slope_correct_device(pprts_b200_solver *s, int lslope, int latm, double *field) {
+  if (!lslope && !latm) return 0;
+  if (!s->have_dz3d || !s->vh) return set_err(70, "slope correction needs a solver initialised with dz3d (atm%%hgrad not initialized!)");
+  if (s->decomposed) return set_err(71, "slope correction is not supported on an x/y-decomposed solver yet");
+  double sv[3];
+  sun_vector(s, sv);
+  const Grid &g = s->g;
+  LAUNCH(s, FAM_ABSO, k_slope_correction, nblk(g.nlev, 256), 256, g, lslope, latm, sv[0], sv[1], sv[2], (const double *)s->vh, field);
+  return 0;
+}
+extern "C" int pprts_b200_slope_correction_fluxes(pprts_b200_solver *s, int lslope, int latm, double *edir) {
+  if (!s || !edir) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const Grid &g = s->g;
+  const size_t n = (size_t)g.nlev;
+  double *dev = s->out_stage, *tmp = s->kr[7];
+  CU(cudaMemcpyAsync(tmp, edir, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  {
+    dim3 block(32, 8), grid((unsigned int)((g.Nx + 31) / 32), (unsigned int)((g.Nz + 1 + 31) / 32), (unsigned int)g.Ny);
+    LAUNCH(s, FAM_IO, k_zxy_to_kji<double>, grid, block, g.Nz + 1, g.Nx, g.Ny, (const double *)tmp, dev);
+  }
+  int rc = slope_correct_device(s, lslope, latm, dev);
+  if (rc) return rc;
+  {
+    dim3 block(32, 8), grid((unsigned int)((g.Nx + 31) / 32), (unsigned int)((g.Nz + 1 + 31) / 32), (unsigned int)g.Ny);
+    LAUNCH(s, FAM_IO, k_kji_to_zxy<double>, grid, block, g.Nz + 1, g.Nx, g.Ny, (const double *)dev, tmp, 1.0);
+  }
+  CU(cudaMemcpyAsync(edir, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+// the same on the device-side spectral sum of the direct flux (pprts_b200_accumulate_result / solve_bands)
+extern "C" int pprts_b200_slope_correct_accumulated(pprts_b200_solver *s, int lslope, int latm) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  return slope_correct_device(s, lslope, latm, s->acc[2]);  // accumulator order: edn, eup, edir, abso
 }
 extern "C" int pprts_b200_mat_mult_ediff(pprts_b200_solver *s, const double *x, double *y) {
   if (!s) return set_err(1, "null solver");

@@ -75,6 +75,7 @@ ABI_SYMBOLS = [
     "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error", "pprts_b200_stream",
     "pprts_b200_solve_bands", "pprts_b200_set_buildings", "pprts_b200_get_buildings_result",
     "pprts_b200_solve_at_time", "pprts_b200_need_new_solution", "pprts_b200_get_solution_times",
+    "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated",
 ]
 
 
@@ -116,6 +117,8 @@ def lib():
     L.pprts_b200_solve_at_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
     L.pprts_b200_need_new_solution.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, c_int_p]
     L.pprts_b200_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
+    L.pprts_b200_slope_correction_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.pprts_b200_slope_correct_accumulated.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.pprts_b200_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_get_buildings_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_kernel_launches.restype = C.c_long
@@ -410,6 +413,17 @@ def need_new_solution(solver: Solver, uid, time=None):
     _chk(lib().pprts_b200_need_new_solution(solver._h, int(uid), 0.0 if time is None else float(time),
                                             int(time is not None), C.byref(need)), "need_new_solution")
     return bool(need.value)
+
+
+def slope_correction_fluxes(solver: Solver, edir, lslope_correction=True, latm_correction=False):
+    """``slope_correction_fluxes(solver, edir)`` (src/pprts_postprocess.F90:130-196) with the options
+    ``-pprts_slope_correction`` / ``-pprts_atm_correction`` as arguments; ``edir`` (Nz+1,Nx,Ny) is corrected in place
+    (it has to be Fortran-ordered float64, as ``pprts_get_result`` returns it) and returned."""
+    if not (edir.flags["F_CONTIGUOUS"] and edir.dtype == np.float64):
+        raise PprtsError("slope_correction_fluxes: edir must be a Fortran-ordered float64 array")
+    _chk(lib().pprts_b200_slope_correction_fluxes(solver._h, int(bool(lslope_correction)), int(bool(latm_correction)),
+                                                  _vp(edir)), "slope_correction_fluxes")
+    return edir
 
 
 def solution_times(solver: Solver, uid):

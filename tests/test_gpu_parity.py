@@ -951,3 +951,40 @@ def test_geometric_coeffs_errors(P, gpu_lut, tmp_path):
         P.init_pprts(0, 4, 3, 4, 100., 100., P.sundir_from_angles(10., 30.), dz1d=np.full(4, 60.), lut=lut, solver=810,
                      geometric_coeffs=True)
     lut.close()
+
+
+def test_slope_correction_vs_oracle(P, gpu_lut, oracle_lut):
+    """slope_correction_fluxes (src/pprts_postprocess.F90:130-196) on the GPU against the oracle, both options, and
+    on the device-side spectral sum of solve_bands"""
+    from oracle import binding as ob
+    Nz, Nx, Ny = 5, 6, 7
+    j = np.arange(Ny)
+    dz3d = np.broadcast_to(90. * (1.0 - 0.3 / (1.0 + ((j - 3.0) / 2.0) ** 2))[None, None, :], (Nz, Nx, Ny)).copy()
+    rng = np.random.default_rng(4)
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny, cloudy=False)
+    sd = P.sundir_from_angles(150., 35.)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz3d=dz3d, lut=gpu_lut, rtol=1e-9)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz3d, diff_solver=1, rtol=1e-9)
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000.)
+    edir = P.pprts_get_result(s)[3]
+    for lslope, latm in ((True, False), (False, True), (True, True)):
+        want = o.slope_correction_fluxes(edir, lslope=lslope, latm=latm)
+        got = P.slope_correction_fluxes(s, np.asfortranarray(edir.copy()), lslope, latm)
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max(), (lslope, latm)
+    # band loop: the correction applied to the accumulated direct flux on the device
+    kb = np.stack([kabs, 2 * kabs], axis=-1)
+    e = np.array([600., 400.])
+    tot = P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=e, download=False)
+    plain = [a.copy() for a in s.get_accumulated()]
+    P._chk(P.lib().pprts_b200_slope_correct_accumulated(s._h, 1, 0), "slope_correct_accumulated")
+    corr = s.get_accumulated()
+    want = o.slope_correction_fluxes(plain[3], lslope=True, latm=False)
+    assert np.abs(corr[3] - want).max() <= 1e-13 * np.abs(want).max()
+    for q in (0, 1, 2):
+        assert np.array_equal(corr[q], plain[q])
+    P.destroy_pprts(s); o.destroy()
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=np.full(Nz, 90.), lut=gpu_lut)     # no dz3d: no hgrad
+    with pytest.raises(P.PprtsError, match="hgrad"):
+        P.slope_correction_fluxes(s, np.asfortranarray(edir.copy()))
+    P.destroy_pprts(s)

@@ -277,7 +277,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if decomp else "weak",
         "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64 (solution, residual, fluxes) + f32 (Krylov work vectors, stored coefficients)" if mixed else "f64",
+        "data": "synthetic",
         "config": {"workload": (f"pprts 3_10 solar+thermal, synthetic cloud field {args.nx}x{args.ny}x{Nz} " +
                                 ("(BASELINE configs[1])" if (args.nx, args.ny, Nz) == (256, 256, 80) else
                                  f"dx={args.dx:g} m dz={args.dz:g} m (BASELINE configs[3]-shaped)" if decomp else "")),

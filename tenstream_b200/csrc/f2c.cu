@@ -87,7 +87,6 @@ extern "C" void pprts_f2c_init(int fcomm, int *solver_id, int *Nz, int *Nx, int 
   g_solver_id = *solver_id;
 }
 
-static int g_Nz = 0;
 extern "C" void pprts_f2c_set_global_optical_properties(int Nz, int Nx, int Ny, float *albedo, float *kabs, float *ksca,
                                                         float *g, float *planck) {
   if (!g_solver) return;
@@ -97,7 +96,6 @@ extern "C" void pprts_f2c_set_global_optical_properties(int Nz, int Nx, int Ny, 
   bool any = false;
   if (planck) for (size_t q = 0; q < nl; ++q) if (planck[q] > 0.f) { any = true; break; }
   if (any) { pl.resize(nl); for (size_t q = 0; q < nl; ++q) pl[q] = planck[q]; }  // f2c_pprts.F90:303-307
-  g_Nz = Nz;
   chkerr(pprts_b200_set_optical_properties(g_solver, (double)*albedo, k.data(), s.data(), gg.data(),
                                            any ? pl.data() : nullptr, nullptr, nullptr, 1),
          "pprts_f2c_set_global_optical_properties");
@@ -144,11 +142,9 @@ extern "C" void pprts_f2c_opp_init(const int comm, const int solver_id, void **o
     return;
   }
   auto *c = new OppContainer();
-  bool had = g_lut != nullptr;
   chkerr(open_default_lut(solver_id), "pprts_f2c_opp_init: loading LUT");
   c->lut = g_lut;
   c->lut_owned = false;
-  (void)had;
   pprts_b200_config cfg;
   pprts_b200_default_config(&cfg);
   cfg.solver_id = solver_id;

@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(128)
 k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, const double *__restrict__ a13,
                const double *__restrict__ a23, const double *__restrict__ albedo, const double *__restrict__ edir,
                double *__restrict__ b) {
-  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft;
   long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.ncell) return;
   const Faces fd = cell_faces<Nd>(g, c), ff = cell_faces<Nf>(g, c);  // faces in the edir / in the b vector
@@ -2065,7 +2065,7 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
              const double *__restrict__ a11, const double *__restrict__ a12, const double *__restrict__ kabs,
              const double *__restrict__ dz, const double *__restrict__ edir, const double *__restrict__ ediff,
              const double *__restrict__ bsrc, double *__restrict__ abso) {
-  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, Nf = L::Nf, Nft = L::Nft;
   long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.ncell) return;
   const Faces fd = cell_faces<Nd>(g, c), ff = cell_faces<Nf>(g, c);

@@ -822,6 +822,18 @@ static void determine_ksp_tolerances(const pprts_b200_solver *s, double &rtol, d
   atol = std::max(1e-8, 1e-4 * s->glob_ncol * (double)(s->g.Nz + 1) * s->unconstrained_fraction);
 }
 
+template <class L, class CT>
+static bool launch_geometric(pprts_b200_solver *s, long n3d, double sx, double sy, double sz) {
+  if constexpr (L::Nd == 3) {
+    const Grid &g = s->g;
+    LAUNCH(s, FAM_LOOKUP, (k_geometric_coeffs<L, CT>), nblk(n3d, 128), 128, g, s->n1d, sx, sy, sz,
+           (const double *)s->kabs, (const double *)s->ksca, (const double *)s->dz, (const double *)s->vh,
+           (CT *)s->d2d, (CT *)s->d2f, s->cdiv_dir, s->bad);
+    return true;
+  } else {
+    return false;
+  }
+}
 static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
   if (!s->coeffs_dirty && (!lsolar || s->coeffs_have_dir)) return 0;
   const Grid &g = s->g;
@@ -840,14 +852,7 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
                  sz = -std::cos(th * d2r);
     CU(cudaMemsetAsync(s->bad, 0, sizeof(int), s->stream));
     bool launched = false;
-    DISPATCH_LC(s, {
-      if constexpr (L::Nd == 3) {
-        LAUNCH(s, FAM_LOOKUP, (k_geometric_coeffs<L, CT>), nblk(n3d, 128), 128, g, s->n1d, sx, sy, sz,
-               (const double *)s->kabs, (const double *)s->ksca, (const double *)s->dz, (const double *)s->vh,
-               (CT *)s->d2d, (CT *)s->d2f, s->cdiv_dir, s->bad);
-        launched = true;
-      }
-    });
+    DISPATCH_LC(s, (launched = launch_geometric<L, CT>(s, n3d, sx, sy, sz)));
     if (!launched) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
     CU(cudaMemcpyAsync(s->h_bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));

@@ -1802,6 +1802,24 @@ __global__ void k_bicg32_update_xr(long n, int it, const float *__restrict__ ph,
   double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
   grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
 }
+// Residual replacement (reliable update): the recursion's fp32 residual is replaced by the TRUE residual b - A x
+// (fp64, A x in `ax`), the search directions p, v are kept.  Writes the same pair of slots k_bicg32_update_xr wrote for
+// iteration `it` -- (r, r) and rho(it+1) = (rh, r) -- so the next iteration continues the same Krylov recursion.
+__global__ void k_mixed_replace_r(long n, int it, const double *__restrict__ b, const double *__restrict__ ax,
+                                  const float *__restrict__ rh, float *__restrict__ r, double *partials,
+                                  unsigned int *counter, double *sc) {
+  const bool rho_first = sc_rho_slot(it + 1) == SC_RHO0;
+  double rr = 0.0, rhr = 0.0;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const float rf = (float)(b[q] - ax[q]);
+    r[q] = rf;
+    const double rd = widen_any(rf);
+    rr = fma(rd, rd, rr);
+    rhr = fma(rd, widen_any(rh[q]), rhr);
+  }
+  double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
+  grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
+}
 // x (fp64) += xc ; xc = 0
 __global__ void k_mixed_flush(long n, float *__restrict__ xc, double *__restrict__ x) {
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {

@@ -1073,6 +1073,14 @@ int orc_dir2dir3_geometric_coeffs(const double *vertices, const double *sundir, 
   return 0;
 }
 
+/* test hooks for the geometry helpers above (tests/test_intersection/test_intersection.F90) */
+double orc_hit_plane(const double *p_loc, const double *p_dir, const double *po, const double *pn) { return g_hit_plane(p_loc, p_dir, po, pn); }
+void orc_compute_normal_3d(const double *p1, const double *p2, const double *p3, double *n) { g_normal(p1, p2, p3, n); }
+int orc_line_intersection_3d(const double *p1, const double *d1, const double *p3, const double *d2, double *c1, double *c2) {
+  return g_line_intersection(p1, d1, p3, d2, c1, c2);
+}
+double orc_triangle_area_by_vertices(const double *v1, const double *v2, const double *v3) { return g_tri(v1, v2, v3); }
+
 /* ---- buildings (src/buildings.F90) ----------------------------------------------------------------------------------
  * A building is a set of faces of grid cells: iface(m) is the 1-based flattened index into (6, Nz, Nx, Ny), first axis
  * fastest (faceidx_by_cell_plus_offset, src/buildings.F90:215-222; ndarray_offsets helper_functions.fypp:2432-2437),

@@ -136,6 +136,13 @@ void orc_get_solution_times(orc_solver *s, int uid, double *time30, double *maxn
  * num_intervals <= 0: the reference default of 10 */
 int orc_dir2dir3_geometric_coeffs(const double *vertices, const double *sundir, double c_ext, int num_intervals, double *coeffs);
 
+/* the helpers of the geometric coefficients: hit_plane, line_intersection_3d (src/intersection.fypp:79-91, :395-434),
+ * compute_normal_3d, triangle_area_by_vertices (src/helper_functions.fypp:1960-1974, :2116-2136) */
+double orc_hit_plane(const double *p_loc, const double *p_dir, const double *po, const double *pn);
+void orc_compute_normal_3d(const double *p1, const double *p2, const double *p3, double *n);
+int orc_line_intersection_3d(const double *p1, const double *d1, const double *p3, const double *d2, double *c1, double *c2);
+double orc_triangle_area_by_vertices(const double *v1, const double *v2, const double *v3);
+
 /* opt_buildings of solve_pprts / pprts_get_result (src/buildings.F90:40-69, src/pprts.F90:3194-3212, :3579-3677,
  * :4989-5145, :6011-6160).  iface: 1-based flattened index into (6,Nz,Nx,Ny), first axis fastest; face ids 1..6 =
  * top, bottom, left (x+0), right (x+1), rear (y+0), front (y+1).  planck may be NULL.  nfaces = 0: no buildings. */

@@ -137,3 +137,51 @@ def test_errors(oracle_lut):
     s.set_optical_properties(0.1, z, z, z)            # vacuum: 'Extinction coeff too small' (geometric_coeffs.F90:42-43)
     assert s.solve(False, True, 1000.) == 22
     s.destroy()
+
+
+# ---- geometry helpers (tests/test_intersection/test_intersection.F90:25-92, :241-279) ----------------------------------------
+def _v(*a):
+    import ctypes as C
+    arr = np.array(a, dtype=np.float64)
+    return arr, arr.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_hit_plane_and_normals():
+    import ctypes as C
+    L = ob.lib()
+    L.orc_hit_plane.restype = C.c_double
+    L.orc_triangle_area_by_vertices.restype = C.c_double
+    dx = 100.0
+    A, B_, Cc = (0., 0.), (dx, 0.), (dx / 2, np.sqrt(dx ** 2 - (dx / 2) ** 2))
+    n = np.zeros(3)
+    a3, pa = _v(A[0], A[1], 0.); b3, pb = _v(B_[0], B_[1], 0.); c3, pc = _v(Cc[0], Cc[1], 0.)
+    L.orc_compute_normal_3d(pa, pb, pc, n.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.allclose(n, [0, 0, 1]) and np.linalg.norm(n) == pytest.approx(1.0)
+    n2 = np.zeros(3)
+    L.orc_compute_normal_3d(pa, pc, pb, n2.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.allclose(-n2, [0, 0, 1])
+    pn = n.ctypes.data_as(C.POINTER(C.c_double))
+    loc, ploc = _v(A[0], A[1], 1.)
+    dn, pdn = _v(0., 0., -1.); up, pup = _v(0., 0., 1.)
+    assert L.orc_hit_plane(ploc, pdn, pa, pn) == pytest.approx(1.0)       # distance calculation 1
+    assert L.orc_hit_plane(ploc, pup, pa, pn) == pytest.approx(-1.0)      # 2
+    assert L.orc_hit_plane(ploc, pdn, pc, pn) == pytest.approx(1.0)       # 3
+    assert L.orc_hit_plane(ploc, pup, pc, pn) == pytest.approx(-1.0)      # 4
+    # equilateral triangle: area = sqrt(3)/4 dx^2 (Heron, helper_functions.fypp:2116-2136)
+    assert L.orc_triangle_area_by_vertices(pa, pb, pc) == pytest.approx(np.sqrt(3) / 4 * dx ** 2, rel=1e-12)
+
+
+def test_line_intersection_3d():
+    import ctypes as C
+    L = ob.lib()
+    atol = np.sqrt(np.finfo(float).eps)
+    huge = np.finfo(float).max
+    o1, po1 = _v(1., 0., 0.); o2, po2 = _v(0., 1., 0.); o3, po3 = _v(0., 0., 1.)
+    d1, pd1 = _v(1., 0., 0.); d2, pd2 = _v(0., 1., 0.); d3, pd3 = _v(0., 0., 1.)
+    c1, c2 = C.c_double(), C.c_double()
+    for (pa, da, pb, db) in ((po1, pd1, po2, pd2), (po1, pd1, po3, pd3), (po2, pd2, po3, pd3)):
+        assert L.orc_line_intersection_3d(pa, da, pb, db, C.byref(c1), C.byref(c2)) == 0
+        assert c1.value == pytest.approx(-1.0, abs=atol) and c2.value == pytest.approx(-1.0, abs=atol)
+    for (pa, da, pb, db) in ((po1, pd1, po2, pd1), (po1, pd1, po3, pd1), (po2, pd2, po3, pd2)):   # parallel lines
+        assert L.orc_line_intersection_3d(pa, da, pb, db, C.byref(c1), C.byref(c2)) == 1
+        assert c1.value == -huge and c2.value == -huge

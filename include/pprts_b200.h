@@ -142,6 +142,9 @@ int pprts_b200_solve_at_time(pprts_b200_solver *solver, int lthermal, int lsolar
  * (src/adaptive_spectral_integration.F90:38-172), the test the band loops make before every solve
  * (rrtmg/rrtmg/pprts_rrtmg.F90:623, :1001).  have_time = 0: `time` not present.  *need: 1 = solve again. */
 int pprts_b200_need_new_solution(pprts_b200_solver *solver, int uid, double time, int have_time, int *need);
+/* polyfit (src/adaptive_spectral_integration.F90:174-257): least-squares polynomial of degree d through n points;
+ * 0 on success, 1 for equal abscissae, 2 for a singular system.  Pure host code (no device needed). */
+int pprts_b200_polyfit(const double *vx, const double *vy, int n, int d, double *coef);
 /* solution%time(30), solution%maxnorm(30) (src/pprts_base.F90:161-162), newest first */
 int pprts_b200_get_solution_times(pprts_b200_solver *solver, int uid, double time[30], double maxnorm[30]);
 /* pprts_get_result (src/pprts.F90:5799-5917): caller-allocated, edir may be NULL */

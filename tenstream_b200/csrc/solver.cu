@@ -1468,6 +1468,11 @@ static int polyfit(const double *vx, const double *vy, int n, int d, double *coe
   }
   return 0;
 }
+// polyfit (src/adaptive_spectral_integration.F90:174-257) as a plain host function: usable without a device
+extern "C" int pprts_b200_polyfit(const double *vx, const double *vy, int n, int d, double *coef) {
+  if (!vx || !vy || !coef || n < 1 || d < 0) return 9;
+  return polyfit(vx, vy, n, d, coef);
+}
 // need_new_solution(comm, solver%solutions(uid), time, lenable_solutions_err_estimates): *need = 1 if the band has to
 // be solved again at `time`, 0 if the stored solution is still within -max_solution_err.  have_time = 0: time absent.
 extern "C" int pprts_b200_need_new_solution(pprts_b200_solver *s, int uid, double time, int have_time, int *need) {

@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "pprts_b200_kernel_stats", "pprts_b200_enable_kernel_timing", "pprts_b200_last_error", "pprts_b200_stream",
     "pprts_b200_solve_bands", "pprts_b200_set_buildings", "pprts_b200_get_buildings_result",
     "pprts_b200_solve_at_time", "pprts_b200_need_new_solution", "pprts_b200_get_solution_times",
-    "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated",
+    "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated", "pprts_b200_polyfit",
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
     L.pprts_b200_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
     L.pprts_b200_slope_correction_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.pprts_b200_slope_correct_accumulated.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pprts_b200_polyfit.argtypes = [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
     L.pprts_b200_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_get_buildings_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_kernel_launches.restype = C.c_long
@@ -424,6 +425,15 @@ def slope_correction_fluxes(solver: Solver, edir, lslope_correction=True, latm_c
     _chk(lib().pprts_b200_slope_correction_fluxes(solver._h, int(bool(lslope_correction)), int(bool(latm_correction)),
                                                   _vp(edir)), "slope_correction_fluxes")
     return edir
+
+
+def polyfit(vx, vy, d):
+    """``polyfit`` (src/adaptive_spectral_integration.F90:174-257) -> (coefficients, ierr); host code, no GPU needed"""
+    vx = np.ascontiguousarray(vx, dtype=np.float64)
+    vy = np.ascontiguousarray(vy, dtype=np.float64)
+    out = np.zeros(d + 1)
+    ierr = lib().pprts_b200_polyfit(_dp(vx), _dp(vy), len(vx), int(d), _dp(out))
+    return out, ierr
 
 
 def solution_times(solver: Solver, uid):

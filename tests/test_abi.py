@@ -58,3 +58,22 @@ def test_product_does_not_import_oracle():
         if f.endswith((".py", ".cu", ".cuh", ".h")):
             txt = open(f).read()
             assert "from oracle" not in txt and "import oracle" not in txt and "pprts_oracle" not in txt, f
+
+
+def test_host_polyfit_matches_oracle(built_lib):
+    """polyfit of the error-growth tracking (src/adaptive_spectral_integration.F90:174-257) is plain host code in the
+    library: checked on the CPU against the oracle's restatement and numpy"""
+    import numpy as np
+    from oracle import binding as ob
+    from tenstream_b200 import pprts as P
+    rng = np.random.default_rng(2)
+    for d in (1, 2):
+        x = np.sort(rng.uniform(0, 10, 4))
+        y = rng.uniform(-1, 1, 4)
+        c, ierr = P.polyfit(x, y, d)
+        co, ierro = ob.polyfit(x, y, d)
+        assert ierr == ierro == 0
+        assert np.allclose(c, co, rtol=1e-9, atol=1e-12)
+        assert np.allclose(c, np.polyfit(x, y, d)[::-1], rtol=1e-7, atol=1e-9)
+    c, ierr = P.polyfit(np.array([0., 1., 1., 2.]), np.array([0., 1., 0., 1.]), 1)
+    assert ierr == 1                                   # equal abscissae (:198-207)

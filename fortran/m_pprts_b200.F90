@@ -12,7 +12,7 @@ module m_pprts_b200
   implicit none
   private
   public :: t_solver_b200, t_lut_b200, lut_open, lut_close, init_pprts, set_angles, set_optical_properties, &
-    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200, need_new_solution
+    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200, need_new_solution, slope_correction_fluxes
 
   integer, parameter :: ireals = c_double, iintegers = c_int
 
@@ -111,6 +111,11 @@ module m_pprts_b200
       real(c_double), value :: time
       integer(c_int), intent(out) :: need
     end function
+    integer(c_int) function c_slope_correction(solver, lslope, latm, edir) bind(c, name='pprts_b200_slope_correction_fluxes')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver, edir
+      integer(c_int), value :: lslope, latm
+    end function
     integer(c_int) function c_set_buildings(solver, nfaces, iface, albedo, planck) bind(c, name='pprts_b200_set_buildings')
       import :: c_ptr, c_int
       type(c_ptr), value :: solver, iface, albedo, planck
@@ -165,7 +170,11 @@ contains
   !> exactly the reference's optional arguments) the domain is decomposed DMDA-style: Nx, Ny are then LOCAL sizes, the
   !> process grid is x-fastest (rank = xi + yi*size(nxproc), src/pprts_base.F90:745-773), and the NCCL communicator of
   !> the halo exchange is bootstrapped over icomm (rank 0 creates the NCCL id, MPI_Bcast distributes it).
-  subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, nxproc, nyproc, device)
+  !> The trailing optional arguments carry what the reference reads from its options database:
+  !> collapseindex (init_pprts argument), -pprts_geometric_coeffs, -max_solution_err, -max_solution_time,
+  !> -twostr_ratio, -solar_diff_ksp_rtol / -thermal_diff_ksp_rtol (one value for both here)
+  subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, nxproc, nyproc, device, &
+      & collapseindex, lgeometric_coeffs, max_solution_err, max_solution_time, twostr_ratio, ksp_rtol)
     use mpi
     integer, intent(in) :: icomm
     integer(iintegers), intent(in) :: Nz, Nx, Ny
@@ -176,6 +185,9 @@ contains
     real(ireals), intent(in), target, optional :: dz1d(:), dz3d(:, :, :)
     integer(iintegers), intent(in), optional :: nxproc(:), nyproc(:)
     integer(iintegers), intent(in), optional :: device
+    integer(iintegers), intent(in), optional :: collapseindex
+    logical, intent(in), optional :: lgeometric_coeffs
+    real(ireals), intent(in), optional :: max_solution_err, max_solution_time, twostr_ratio, ksp_rtol
     type(c_config) :: cfg
     character(kind=c_char) :: nccl_id(128)
     integer :: myid, nranks, ierr
@@ -184,6 +196,12 @@ contains
     if (present(dz1d)) cfg%dz1d = c_loc(dz1d)
     if (present(dz3d)) cfg%dz3d = c_loc(dz3d)
     if (present(device)) cfg%device = device
+    if (present(collapseindex)) cfg%collapseindex = collapseindex
+    if (present(lgeometric_coeffs)) cfg%geometric_coeffs = merge(1, 0, lgeometric_coeffs)
+    if (present(max_solution_err)) cfg%max_solution_err = max_solution_err
+    if (present(max_solution_time)) cfg%max_solution_time = max_solution_time
+    if (present(twostr_ratio)) cfg%twostr_ratio = twostr_ratio
+    if (present(ksp_rtol)) cfg%rtol = ksp_rtol
     if (present(nxproc) .and. present(nyproc)) then
       call mpi_comm_rank(icomm, myid, ierr)
       call mpi_comm_size(icomm, nranks, ierr)
@@ -191,7 +209,8 @@ contains
       cfg%xrank = modulo(myid, cfg%nxproc); cfg%yrank = myid / cfg%nxproc
     end if
     call chkerr(c_create(cfg, lut%h, solver%h), 'init_pprts')
-    solver%Nz = Nz; solver%Nx = Nx; solver%Ny = Ny
+    solver%Nz = Nz - max(cfg%collapseindex, 1) + 1  ! results live on the collapsed solver grid (src/pprts.F90:692-706)
+    solver%Nx = Nx; solver%Ny = Ny
     if (cfg%nxproc * cfg%nyproc .gt. 1) then
       if (myid .eq. 0) call chkerr(c_nccl_unique_id(nccl_id), 'nccl_unique_id')
       call mpi_bcast(nccl_id, 128, MPI_CHARACTER, 0, icomm, ierr)
@@ -294,6 +313,16 @@ contains
       call chkerr(c_get_buildings_result(solver%h, uid, c_loc(opt_buildings%edir), c_loc(opt_buildings%incoming), &
         & c_loc(opt_buildings%outgoing)), 'pprts_get_result(opt_buildings)')
     end if
+  end subroutine
+
+  !> slope_correction_fluxes (src/pprts_postprocess.F90:130); the options -pprts_slope_correction / -pprts_atm_correction
+  !> are arguments here
+  subroutine slope_correction_fluxes(solver, edir, lslope_correction, latm_correction)
+    type(t_solver_b200), intent(inout) :: solver
+    real(ireals), allocatable, target, intent(inout) :: edir(:, :, :)
+    logical, intent(in) :: lslope_correction, latm_correction
+    call chkerr(c_slope_correction(solver%h, merge(1, 0, lslope_correction), merge(1, 0, latm_correction), c_loc(edir)), &
+      & 'slope_correction_fluxes')
   end subroutine
 
   subroutine destroy_pprts(solver, lfinalizepetsc)

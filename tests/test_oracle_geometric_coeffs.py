@@ -185,3 +185,31 @@ def test_line_intersection_3d():
     for (pa, da, pb, db) in ((po1, pd1, po2, pd1), (po1, pd1, po3, pd1), (po2, pd2, po3, pd2)):   # parallel lines
         assert L.orc_line_intersection_3d(pa, da, pb, db, C.byref(c1), C.byref(c2)) == 1
         assert c1.value == -huge and c2.value == -huge
+
+
+def test_geometric_coeffs_with_collapse_and_1d_layers(oracle_lut):
+    """The vertex heights live on the atmosphere grid (atmk, src/pprts_base.F90:1088-1093): a collapsed / 1-D top block
+    only shifts them; closure still holds and the 3-D layers below see the same geometry"""
+    Nz, Nx, Ny, ci = 8, 4, 6, 3
+    j = np.arange(Ny)
+    shrink = 1.0 - 0.3 / (1.0 + ((j - Ny / 2.0) / 2.0) ** 2)
+    dz = np.empty((Nz, Nx, Ny))
+    dz[:ci] = 400.0                                             # thick, 1-D, collapsed into one layer
+    dz[ci:] = 60.0 * shrink[None, None, :]
+    kabs, ksca, g = make_atm(Nz, Nx, Ny, seed=8)
+    s = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., ob.sundir_from_angles(130., 40.), dz, diff_solver=1,
+                        rtol=1e-10, atol=1e-30, geometric_coeffs=True, collapseindex=ci)
+    s.set_optical_properties(0.2, kabs, ksca, g)
+    assert s.solve(False, True, 1000.) == 0
+    edn, eup, abso, edir = s.get_result()
+    assert edn.shape[0] == Nz - ci + 2
+    T = s.coeffs(1)
+    assert np.abs(T[:, 0]).max() == 0 and np.abs(T[:, 1:]).max() > 0          # solver layer 0 is the collapsed 1-D layer
+    s.destroy()
+    # the same 3-D layers without the block on top: identical geometric coefficients
+    s2 = ob.OracleSolver(oracle_lut, Nz - ci, Nx, Ny, 100., 100., ob.sundir_from_angles(130., 40.), dz[ci:], diff_solver=1,
+                         geometric_coeffs=True)
+    s2.set_optical_properties(0.2, kabs[ci:], ksca[ci:], g[ci:])
+    assert s2.solve(False, True, 1000.) == 0
+    assert np.abs(s2.coeffs(1) - T[:, 1:]).max() < 1e-13
+    s2.destroy()

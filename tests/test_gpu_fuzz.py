@@ -1,6 +1,6 @@
 """Seeded random configurations of the whole path -- stream layout, grid shape, sun position, 1-D layers, atmosphere
-collapse, terrain-following dz, 2-D albedo, surface Planck emission, coefficient storage, Krylov precision,
-preconditioner -- solved on the GPU and by the CPU oracle; fluxes and absorption must agree to 1e-5 relative
+collapse, terrain-following dz, geometric direct-beam coefficients, 2-D albedo, surface Planck emission, coefficient
+storage, Krylov precision, preconditioner -- solved on the GPU and by the CPU oracle; fluxes and absorption must agree to 1e-5 relative
 (north_star), both sides converged to 1e-10."""
 import numpy as np
 import pytest
@@ -66,9 +66,10 @@ def test_random_configuration(P, luts, seed):
     coeff_fp32 = bool(rng.integers(0, 2))
     mixed = bool(rng.integers(0, 2))
     precond = int(rng.integers(0, 3))
+    geometric = bool(solar and sid != 810 and rng.random() < 0.4)       # -pprts_geometric_coeffs (3 direct streams)
     sd = P.sundir_from_angles(phi0, theta0)
     glut, olut = luts[sid]
-    common = dict(coeff_fp32=coeff_fp32, rtol=1e-10, atol=1e-30, collapseindex=ci)
+    common = dict(coeff_fp32=coeff_fp32, rtol=1e-10, atol=1e-30, collapseindex=ci, geometric_coeffs=geometric)
     s = P.init_pprts(0, Nz, Nx, Ny, dx, dx, sd, solver=sid, dz1d=None if dz3d is not None else dz1d, dz3d=dz3d, lut=glut,
                      krylov_fp32=mixed, precond=precond, **common)
     o = ob.OracleSolver(olut, Nz, Nx, Ny, dx, dx, sd, dz3d if dz3d is not None else dz1d, solver_id=sid, diff_solver=1,
@@ -88,7 +89,7 @@ def test_random_configuration(P, luts, seed):
         P.destroy_pprts(s); o.destroy()
         pytest.skip(f"the oracle's plain BiCGStab did not converge for this draw (rc {rc})")
     desc = dict(sid=sid, shape=(Nz, Nx, Ny), dx=dx, phi0=phi0, theta0=theta0, solar=solar, ci=ci, dz3d=dz3d is not None,
-                coeff_fp32=coeff_fp32, mixed=mixed, precond=precond, info=s.info(), oinfo=o.info())
+                coeff_fp32=coeff_fp32, mixed=mixed, precond=precond, geometric=geometric, info=s.info(), oinfo=o.info())
     for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
         assert a.shape == b.shape, desc
         assert relerr(a, b) < 1e-5, (name, relerr(a, b), desc)

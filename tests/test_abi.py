@@ -77,3 +77,22 @@ def test_host_polyfit_matches_oracle(built_lib):
         assert np.allclose(c, np.polyfit(x, y, d)[::-1], rtol=1e-7, atol=1e-9)
     c, ierr = P.polyfit(np.array([0., 1., 1., 2.]), np.array([0., 1., 0., 1.]), 1)
     assert ierr == 1                                   # equal abscissae (:198-207)
+
+
+def test_header_is_c99_and_links_from_c(built_lib, tmp_path):
+    """include/pprts_b200.h is the boundary a C host model compiles against: it must be plain C (no C++ / torch types)
+    and a C program must link against the shared library and call it (no device needed for the config defaults)"""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "t.c"
+    src.write_text('#include "pprts_b200.h"\n'
+                   'int main(void) { pprts_b200_config c; pprts_b200_default_config(&c);\n'
+                   '  return (c.solver_id == 310 && c.keep_solutions == 1 && c.geometric_coeffs == 0) ? 0 : 1; }\n')
+    libdir = os.path.dirname(built_lib)
+    exe = tmp_path / "t"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-L", libdir, "-lpprts_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    assert subprocess.call([str(exe)]) == 0

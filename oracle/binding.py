@@ -106,6 +106,10 @@ def lib():
         L.orc_dir2dir3_geometric_coeffs.argtypes = [c_double_p, c_double_p, C.c_double, C.c_int, c_double_p]
         L.orc_slope_correction_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]
         L.orc_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, c_double_p, c_double_p]
+        L.orc_convolve_ediff_srfc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]
+        L.orc_find_iter_and_kernelwidth.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, c_int_p, c_int_p]
+        L.orc_smooth_surface_fluxes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                                c_double_p, c_double_p]
         L.orc_get_buildings_result.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]
         _lib = L
     return _lib
@@ -397,6 +401,36 @@ def polyfit(vx, vy, d):
     out = np.zeros(d + 1)
     ierr = lib().orc_polyfit(_dp(vx), _dp(vy), len(vx), d, _dp(out))
     return out, ierr
+
+
+def convolve_ediff_srfc(arr, kernel_width):
+    """convolve_ediff_srfc(comm, C, kernel_width, arr) (src/pprts_base.F90:1733) on one rank; arr (dof, xm, ym),
+    returns the filtered copy"""
+    a = np.asfortranarray(arr, dtype=np.float64).copy(order="F")
+    rc = lib().orc_convolve_ediff_srfc(a.shape[0], a.shape[1], a.shape[2], int(kernel_width), _dp(a))
+    if rc:
+        raise ValueError("kernel_width does not fit the domain")
+    return a
+
+
+def find_iter_and_kernelwidth(radius, dx, dy, xm, ym):
+    """find_iter_and_kernelwidth (src/pprts_postprocess.F90:86-128) -> (Niter, kernel_width)"""
+    ni, kw = C.c_int(0), C.c_int(0)
+    rc = lib().orc_find_iter_and_kernelwidth(radius, dx, dy, xm, ym, C.byref(ni), C.byref(kw))
+    if rc:
+        raise ValueError(f"the smoothing iteration count would be larger than 250 ({rc})")
+    return ni.value, kw.value
+
+
+def smooth_surface_fluxes(edn, eup, dx, dy, radius):
+    """smooth_surface_fluxes(solver, edn, eup) (src/pprts_postprocess.F90:44-84) with -pprts_smooth_srfc_flx = radius;
+    edn, eup (Nz+1, Nx, Ny); returns the smoothed copies"""
+    a = np.asfortranarray(edn, dtype=np.float64).copy(order="F")
+    b = np.asfortranarray(eup, dtype=np.float64).copy(order="F")
+    rc = lib().orc_smooth_surface_fluxes(a.shape[0], a.shape[1], a.shape[2], dx, dy, radius, _dp(a), _dp(b))
+    if rc:
+        raise ValueError(f"smooth_surface_fluxes -> {rc}")
+    return a, b
 
 
 def sundir_from_angles(phi0, theta0):

@@ -2166,6 +2166,145 @@ int orc_slope_correction_fluxes(orc_solver *s, int lslope, int latm, int have_dz
   return 0;
 }
 
+/* box_blur_1d inside convolve_ediff_srfc (src/pprts_base.F90:1816-1866), iter = 1: running window sum of 2k+1 entries
+ * along the second (slow) index of im(n1, n2) (Fortran order), the window walked with the reference's bounce at both
+ * array ends (an index that steps past an end repeats the end value and turns round), then scaled by 1/(2k+1). */
+static void box_blur_1d(const double *im, int n1, int n2, int k, double *img) {
+  double *tmp = (double *)malloc(sizeof(double) * (size_t)n1 * n2);
+  const int lb = 0, ub = n2 - 1;
+  int a, i, ki, l, r, inc;
+#define IM(a_, b_) im[(a_) + (size_t)n1 * (b_)]
+#define TMP(a_, b_) tmp[(a_) + (size_t)n1 * (b_)]
+  for (a = 0; a < n1; ++a) TMP(a, lb) = IM(a, lb);
+  inc = -1; l = lb;
+  for (ki = 0; ki < k; ++ki) {
+    l += inc;
+    if (l == lb - 1) { l = lb; inc = 1; }
+    if (l == ub + 1) { l = ub; inc = -1; }
+    for (a = 0; a < n1; ++a) TMP(a, lb) += IM(a, l);
+  }
+  r = lb; inc = 1;
+  for (ki = 0; ki < k; ++ki) {
+    r += inc;
+    if (r == ub + 1) { r = ub; inc = -1; }
+    if (r == lb - 1) { r = lb; inc = 1; }
+    for (a = 0; a < n1; ++a) TMP(a, lb) += IM(a, r);
+  }
+  for (i = lb + 1; i <= ub; ++i) {
+    l = i - 1; inc = -1;
+    for (ki = 0; ki < k; ++ki) {
+      l += inc;
+      if (l == lb - 1) { l = lb; inc = 1; }
+      if (l == ub + 1) { l = ub; inc = -1; }
+    }
+    r = i; inc = 1;
+    for (ki = 0; ki < k; ++ki) {
+      r += inc;
+      if (r == ub + 1) { r = ub; inc = -1; }
+      if (r == lb - 1) { r = lb; inc = 1; }
+    }
+    for (a = 0; a < n1; ++a) TMP(a, i) = TMP(a, i - 1) + IM(a, r) - IM(a, l);
+  }
+  for (a = 0; a < n1 * n2; ++a) img[a] = tmp[a] * (1.0 / (double)(2 * k + 1));
+#undef IM
+#undef TMP
+  free(tmp);
+}
+
+/* convolve_ediff_srfc (src/pprts_base.F90:1733-1868) on one rank (every neighbour is the rank itself, so the ghost
+ * exchange is the periodic wrap): arr(dof, xm, ym), Fortran order, in place.  Extended array with kw ghosts per side,
+ * x ghosts first, then y ghosts over the full extended x range (corners), box_filter = blur along x then along y
+ * (`box_filter` transposes so that the blurred index is the slow one), interior copied back.  Returns 1 if kw does
+ * not fit the domain (the reference's sections xm+1:xm+kw would leave the interior). */
+int orc_convolve_ediff_srfc(int dof, int xm, int ym, int kw, double *arr) {
+  const int gx = xm + 2 * kw, gy = ym + 2 * kw;
+  double *wg, *imT, *tmpT, *tmp;
+  int d, i, j;
+  if (kw < 0 || kw > xm || kw > ym) return 1;
+  wg = (double *)calloc((size_t)gx * gy, sizeof(double));
+  imT = (double *)malloc(sizeof(double) * (size_t)gx * gy);
+  tmpT = (double *)malloc(sizeof(double) * (size_t)gx * gy);
+  tmp = (double *)malloc(sizeof(double) * (size_t)gx * gy);
+#define ARR(d_, i_, j_) arr[(d_) + (size_t)dof * ((i_) + (size_t)xm * (j_))]
+#define WG(i_, j_) wg[(i_) + (size_t)gx * (j_)]
+  for (d = 0; d < dof; ++d) {
+    for (j = 0; j < ym; ++j) for (i = 0; i < xm; ++i) WG(kw + i, kw + j) = ARR(d, i, j);
+    /* pass 1: x ghosts of the interior rows: west ghost <- the east-most kw interior columns, and vice versa */
+    for (j = 0; j < ym; ++j) for (i = 0; i < kw; ++i) {
+      WG(i, kw + j) = WG(xm + i, kw + j);
+      WG(xm + kw + i, kw + j) = WG(kw + i, kw + j);
+    }
+    /* pass 2: y ghosts over the full extended x range */
+    for (j = 0; j < kw; ++j) for (i = 0; i < gx; ++i) {
+      WG(i, j) = WG(i, ym + j);
+      WG(i, ym + kw + j) = WG(i, kw + j);
+    }
+    /* box_filter: im_T(y, x) blurred along x, transposed back, blurred along y */
+    for (j = 0; j < gy; ++j) for (i = 0; i < gx; ++i) imT[j + (size_t)gy * i] = WG(i, j);
+    box_blur_1d(imT, gy, gx, kw, tmpT);
+    for (j = 0; j < gy; ++j) for (i = 0; i < gx; ++i) tmp[i + (size_t)gx * j] = tmpT[j + (size_t)gy * i];
+    box_blur_1d(tmp, gx, gy, kw, wg);
+    for (j = 0; j < ym; ++j) for (i = 0; i < xm; ++i) ARR(d, i, j) = WG(kw + i, kw + j);
+  }
+#undef ARR
+#undef WG
+  free(wg); free(imT); free(tmpT); free(tmp);
+  return 0;
+}
+
+/* find_iter_and_kernelwidth (src/pprts_postprocess.F90:86-128): Niter box blurs of half width kernel_width approximate
+ * a Gaussian of the given radius [m]; the width closest to an integer among 500 candidate iteration counts, the
+ * candidates whose width does not fit the local domain skipped.  Returns the reference's error (min_iter) if more
+ * than 250 iterations would be needed. */
+int orc_find_iter_and_kernelwidth(double radius, double dx, double dy, int xm, int ym, int *Niter, int *kernel_width) {
+  enum { test_Ni = 500, Ni_limit = 250 };
+  double test_k[test_Ni], best = 0.0;
+  const double rpix = radius / ((dx + dy) / 2);
+  const int mloc = xm < ym ? xm : ym;
+  int i, min_iter = 1, arg = -1;
+  for (i = 1; i <= test_Ni; ++i) {
+    test_k[i - 1] = (sqrt((12 * rpix * rpix + (double)i) / (double)i + 1) - 1) / 2;
+    if ((int)lround(test_k[i - 1]) >= mloc) min_iter = i + 1;
+  }
+  if (min_iter > Ni_limit) return min_iter;
+  for (i = min_iter; i <= test_Ni; ++i) {
+    const double res = fabs(test_k[i - 1] - (double)lround(test_k[i - 1]));
+    if (arg < 0 || res < best) { best = res; arg = i; } /* minloc: first minimum */
+  }
+  *Niter = arg;
+  *kernel_width = (int)lround(test_k[arg - 1]);
+  if (*kernel_width == 0) *Niter = 0;
+  return 0;
+}
+
+/* smooth_surface_fluxes (src/pprts_postprocess.F90:44-84), the spectral callers' post-processing of the diffuse
+ * surface fluxes (rrtmg/rrtmg/pprts_rrtmg.F90:319), option -pprts_smooth_srfc_flx <radius> passed as an argument:
+ * radius < 0 replaces the surface level of edn and eup by its domain mean (meanval = sum / size), radius >= 0 applies
+ * Niter box blurs of half width kernel_width to it.  edn, eup: (Nz1, Nx, Ny) Fortran order, in place. */
+int orc_smooth_surface_fluxes(int Nz1, int Nx, int Ny, double dx, double dy, double radius, double *edn, double *eup) {
+  double *f[2], *srfc;
+  const size_t n = (size_t)Nx * Ny;
+  size_t c;
+  int q, it, Niter = 0, kw = 0, rc = 0;
+  f[0] = edn; f[1] = eup;
+  srfc = (double *)malloc(sizeof(double) * n);
+  if (radius >= 0 && (rc = orc_find_iter_and_kernelwidth(radius, dx, dy, Nx, Ny, &Niter, &kw))) { free(srfc); return rc; }
+  for (q = 0; q < 2; ++q) {
+    for (c = 0; c < n; ++c) srfc[c] = f[q][(Nz1 - 1) + (size_t)Nz1 * c];
+    if (radius < 0) {
+      double sum = 0.0;
+      for (c = 0; c < n; ++c) sum += srfc[c];
+      sum = sum / (double)n * (double)n / (double)n; /* imp_allreduce_mean: meanval(v) * size(v) / global_size */
+      for (c = 0; c < n; ++c) srfc[c] = sum;
+    } else {
+      for (it = 0; it < Niter && !rc; ++it) rc = orc_convolve_ediff_srfc(1, Nx, Ny, kw, srfc);
+    }
+    for (c = 0; c < n; ++c) f[q][(Nz1 - 1) + (size_t)Nz1 * c] = srfc[c];
+  }
+  free(srfc);
+  return rc;
+}
+
 const double *orc_coeff_ptr(orc_solver *s, int which) { return which == 1 ? s->dir2dir : which == 2 ? s->dir2diff : s->diff2diff; }
 const double *orc_state_ptr(orc_solver *s, int uid, int which) {
   orc_solution *sol = s->sol[uid - ORC_UID_MIN];

@@ -152,6 +152,11 @@ int orc_get_buildings_result(orc_solver *s, int uid, double *edir, double *incom
 /* slope_correction_fluxes (src/pprts_postprocess.F90:130-196): -pprts_slope_correction / -pprts_atm_correction applied
  * to a direct-flux result (Nz+1,Nx,Ny) in place; have_dz3d = 0 (no hgrad) with a correction requested returns 1 */
 int orc_slope_correction_fluxes(orc_solver *s, int lslope, int latm, int have_dz3d, double *edir);
+/* smooth_surface_fluxes (src/pprts_postprocess.F90:44-128) and the separable box blur it applies, convolve_ediff_srfc
+ * (src/pprts_base.F90:1733-1868), restated for one rank; pinned on tests/test_convolution/test_convolution.F90 */
+int orc_convolve_ediff_srfc(int dof, int xm, int ym, int kw, double *arr);
+int orc_find_iter_and_kernelwidth(double radius, double dx, double dy, int xm, int ym, int *Niter, int *kernel_width);
+int orc_smooth_surface_fluxes(int Nz1, int Nx, int Ny, double dx, double dy, double radius, double *edn, double *eup);
 
 /* introspection used by the parity tests */
 const double *orc_coeff_ptr(orc_solver *s, int which); /* 1 dir2dir, 2 dir2diff, 3 diff2diff: (ncoef,Nz,Nx,Ny) */

@@ -12,7 +12,8 @@ module m_pprts_b200
   implicit none
   private
   public :: t_solver_b200, t_lut_b200, lut_open, lut_close, init_pprts, set_angles, set_optical_properties, &
-    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200, need_new_solution, slope_correction_fluxes
+    & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200, need_new_solution, slope_correction_fluxes, &
+    & smooth_surface_fluxes
 
   integer, parameter :: ireals = c_double, iintegers = c_int
 
@@ -115,6 +116,11 @@ module m_pprts_b200
       import :: c_ptr, c_int
       type(c_ptr), value :: solver, edir
       integer(c_int), value :: lslope, latm
+    end function
+    integer(c_int) function c_smooth_surface_fluxes(solver, radius, edn, eup) bind(c, name='pprts_b200_smooth_surface_fluxes')
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: solver, edn, eup
+      real(c_double), value :: radius
     end function
     integer(c_int) function c_set_buildings(solver, nfaces, iface, albedo, planck) bind(c, name='pprts_b200_set_buildings')
       import :: c_ptr, c_int
@@ -323,6 +329,16 @@ contains
     logical, intent(in) :: lslope_correction, latm_correction
     call chkerr(c_slope_correction(solver%h, merge(1, 0, lslope_correction), merge(1, 0, latm_correction), c_loc(edir)), &
       & 'slope_correction_fluxes')
+  end subroutine
+
+  !> smooth_surface_fluxes (src/pprts_postprocess.F90:44); the value of -pprts_smooth_srfc_flx is the argument radius
+  !> (absent = option not set: nothing happens, as in the reference)
+  subroutine smooth_surface_fluxes(solver, edn, eup, radius)
+    type(t_solver_b200), intent(inout) :: solver
+    real(ireals), allocatable, target, intent(inout) :: edn(:, :, :), eup(:, :, :)
+    real(ireals), intent(in), optional :: radius
+    if (.not. present(radius)) return
+    call chkerr(c_smooth_surface_fluxes(solver%h, real(radius, c_double), c_loc(edn), c_loc(eup)), 'smooth_surface_fluxes')
   end subroutine
 
   subroutine destroy_pprts(solver, lfinalizepetsc)

@@ -215,6 +215,18 @@ int pprts_b200_slope_correction_fluxes(pprts_b200_solver *solver, int lslope, in
 /* the same applied to the direct flux of the device-side spectral sum (before pprts_b200_get_accumulated) */
 int pprts_b200_slope_correct_accumulated(pprts_b200_solver *solver, int lslope, int latm);
 
+/* smooth_surface_fluxes(solver, edn, eup) (src/pprts_postprocess.F90:44-84), the callers' post-processing of the diffuse
+ * surface fluxes (rrtmg/rrtmg/pprts_rrtmg.F90:319); radius = the value of -pprts_smooth_srfc_flx [m] (the caller skips
+ * the call when the option is absent).  radius < 0: the surface level of edn and eup becomes its domain mean;
+ * radius >= 0: Niter passes of the separable periodic box blur of half width kernel_width (convolve_ediff_srfc,
+ * src/pprts_base.F90:1733-1868), both from find_iter_and_kernelwidth (src/pprts_postprocess.F90:86-128, pure host
+ * arithmetic: no solver, no GPU).  edn, eup: host (Nz+1,Nx,Ny) column-major, in place.  Single periodic domain. */
+int pprts_b200_find_iter_and_kernelwidth(double radius, double dx, double dy, int xm, int ym, int *Niter,
+                                         int *kernel_width);
+int pprts_b200_smooth_surface_fluxes(pprts_b200_solver *solver, double radius, double *edn, double *eup);
+/* the same applied to edn / eup of the device-side spectral sum (before pprts_b200_get_accumulated) */
+int pprts_b200_smooth_accumulated(pprts_b200_solver *solver, double radius);
+
 /* ---- buildings: the opt_buildings argument of solve_pprts / pprts_get_result ------------------------------------
  * Replaces type(t_pprts_buildings) (src/buildings.F90:40-69) as consumed by alloc_coeff_dir2dir / alloc_coeff_diff2diff
  * (src/pprts.F90:3194-3212, :3579-3677), setup_b (:4989-5145) and pprts_get_result (:6011-6160).

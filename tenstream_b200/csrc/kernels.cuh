@@ -495,6 +495,53 @@ __global__ void k_slope_correction(Grid g, int lslope, int latm, double sunx, do
   edir[l] = e;
 }
 
+// convolve_ediff_srfc (src/pprts_base.F90:1733-1868) on one level field [Ny][Nx] of a single periodic domain: one pass
+// of the separable box blur (window 2 kw + 1, scaled by 1 / (2 kw + 1)) along x (along_y = 0) or along y.  The
+// reference's ghost-extended running sums reduce to the periodic window on the interior; here every output sums its
+// window directly (the field is one level, L2-resident: the pass is launch-bound, not bandwidth-bound).
+__global__ void k_box_blur(int Nx, int Ny, int kw, int along_y, const double *__restrict__ in, double *__restrict__ out) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= (long)Nx * Ny) return;
+  const int i = (int)(c % Nx), j = (int)(c / Nx);
+  double acc = 0.0;
+  if (along_y) {
+    int jj = (j - kw) % Ny;
+    if (jj < 0) jj += Ny;
+    for (int d = 0; d <= 2 * kw; ++d) {
+      acc += in[(long)jj * Nx + i];
+      if (++jj == Ny) jj = 0;
+    }
+  } else {
+    int ii = (i - kw) % Nx;
+    if (ii < 0) ii += Nx;
+    for (int d = 0; d <= 2 * kw; ++d) {
+      acc += in[(long)j * Nx + ii];
+      if (++ii == Nx) ii = 0;
+    }
+  }
+  out[c] = acc * (1.0 / (double)(2 * kw + 1));
+}
+
+// smooth_surface_fluxes with a negative radius (src/pprts_postprocess.F90:66-71): the level field is replaced by its
+// domain mean.  One block per field; warp-shuffle partial sums, fixed order (deterministic).
+__global__ void k_fill_mean(long n, double *__restrict__ field) {
+  __shared__ double part[32];
+  __shared__ double mean;
+  double acc = 0.0;
+  for (long c = threadIdx.x; c < n; c += blockDim.x) acc += field[c];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    mean = t / (double)n;
+  }
+  __syncthreads();
+  const double m = mean;
+  for (long c = threadIdx.x; c < n; c += blockDim.x) field[c] = m;
+}
+
 // fp64 lookup of n arbitrary sample cells (coefficient probe / parity hook); out[(coef) + ncoef*n]
 template <class L>
 __global__ void k_lookup_probe(LutDev lut, SymMaps sym, int mode, long n, double dx, const double *__restrict__ kabs,

@@ -1871,6 +1871,75 @@ extern "C" int pprts_b200_slope_correct_accumulated(pprts_b200_solver *s, int ls
   CU(cudaSetDevice(s->device));
   return slope_correct_device(s, lslope, latm, s->acc[2]);  // accumulator order: edn, eup, edir, abso
 }
+// smooth_surface_fluxes(solver, edn, eup) (src/pprts_postprocess.F90:44-84), the other post-processing step of the
+// spectral callers (rrtmg/rrtmg/pprts_rrtmg.F90:319); the option -pprts_smooth_srfc_flx <radius> arrives as an argument.
+// find_iter_and_kernelwidth (src/pprts_postprocess.F90:86-128) is pure host arithmetic.
+extern "C" int pprts_b200_find_iter_and_kernelwidth(double radius, double dx, double dy, int xm, int ym, int *Niter,
+                                                    int *kernel_width) {
+  if (!Niter || !kernel_width) return set_err(1, "null output");
+  const int test_Ni = 500, Ni_limit = 250;
+  std::vector<double> test_k(test_Ni);
+  const double rpix = radius / ((dx + dy) / 2);
+  int min_iter = 1;
+  for (int i = 1; i <= test_Ni; ++i) {
+    test_k[i - 1] = (std::sqrt((12 * rpix * rpix + (double)i) / (double)i + 1) - 1) / 2;
+    if (std::lround(test_k[i - 1]) >= std::min(xm, ym)) min_iter = i + 1;
+  }
+  if (min_iter > Ni_limit)
+    return set_err(72, "the smoothing iteration count would be larger than %d... this could become expensive (%d)", Ni_limit, min_iter);
+  int arg = min_iter;
+  double best = std::fabs(test_k[arg - 1] - (double)std::lround(test_k[arg - 1]));
+  for (int i = min_iter + 1; i <= test_Ni; ++i) {
+    const double res = std::fabs(test_k[i - 1] - (double)std::lround(test_k[i - 1]));
+    if (res < best) { best = res; arg = i; }
+  }
+  *Niter = arg;
+  *kernel_width = (int)std::lround(test_k[arg - 1]);
+  if (*kernel_width == 0) *Niter = 0;
+  return 0;
+}
+// field: one level [Ny][Nx] on the device, smoothed in place; scratch: at least ncol doubles
+static int smooth_level_device(pprts_b200_solver *s, double radius, double *field, double *scratch) {
+  const Grid &g = s->g;
+  if (s->decomposed) return set_err(71, "smooth_surface_fluxes is not supported on an x/y-decomposed solver yet");
+  if (radius < 0) {
+    LAUNCH(s, FAM_ABSO, k_fill_mean, 1, 1024, (long)g.ncol, field);
+    return 0;
+  }
+  int niter = 0, kw = 0;
+  int rc = pprts_b200_find_iter_and_kernelwidth(radius, g.dx, g.dy, g.Nx, g.Ny, &niter, &kw);
+  if (rc) return rc;
+  for (int it = 0; it < niter; ++it) {
+    LAUNCH(s, FAM_ABSO, k_box_blur, nblk(g.ncol, 256), 256, g.Nx, g.Ny, kw, 0, (const double *)field, scratch);
+    LAUNCH(s, FAM_ABSO, k_box_blur, nblk(g.ncol, 256), 256, g.Nx, g.Ny, kw, 1, (const double *)scratch, field);
+  }
+  return 0;
+}
+// edn, eup: host arrays (Nz+1,Nx,Ny) column-major; only the surface level changes
+extern "C" int pprts_b200_smooth_surface_fluxes(pprts_b200_solver *s, double radius, double *edn, double *eup) {
+  if (!s || !edn || !eup) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const Grid &g = s->g;
+  const size_t nc = (size_t)g.ncol, nz1 = (size_t)g.Nz + 1;
+  std::vector<double> h(2 * nc);
+  for (size_t c = 0; c < nc; ++c) { h[c] = edn[g.Nz + nz1 * c]; h[nc + c] = eup[g.Nz + nz1 * c]; }
+  double *dev = s->out_stage;
+  CU(cudaMemcpyAsync(dev, h.data(), 2 * nc * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  int rc;
+  if ((rc = smooth_level_device(s, radius, dev, s->kr[7])) || (rc = smooth_level_device(s, radius, dev + nc, s->kr[7]))) return rc;
+  CU(cudaMemcpyAsync(h.data(), dev, 2 * nc * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (size_t c = 0; c < nc; ++c) { edn[g.Nz + nz1 * c] = h[c]; eup[g.Nz + nz1 * c] = h[nc + c]; }
+  return 0;
+}
+// the same on the device-side spectral sums of edn and eup (pprts_b200_accumulate_result / solve_bands)
+extern "C" int pprts_b200_smooth_accumulated(pprts_b200_solver *s, double radius) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  const size_t srfc = (size_t)s->g.Nz * s->g.ncol;
+  int rc = smooth_level_device(s, radius, s->acc[0] + srfc, s->kr[7]);
+  return rc ? rc : smooth_level_device(s, radius, s->acc[1] + srfc, s->kr[7]);
+}
 extern "C" int pprts_b200_mat_mult_ediff(pprts_b200_solver *s, const double *x, double *y) {
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));

@@ -76,6 +76,7 @@ ABI_SYMBOLS = [
     "pprts_b200_solve_bands", "pprts_b200_set_buildings", "pprts_b200_get_buildings_result",
     "pprts_b200_solve_at_time", "pprts_b200_need_new_solution", "pprts_b200_get_solution_times",
     "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated", "pprts_b200_polyfit",
+    "pprts_b200_find_iter_and_kernelwidth", "pprts_b200_smooth_surface_fluxes", "pprts_b200_smooth_accumulated",
 ]
 
 
@@ -119,6 +120,10 @@ def lib():
     L.pprts_b200_get_solution_times.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
     L.pprts_b200_slope_correction_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.pprts_b200_slope_correct_accumulated.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pprts_b200_find_iter_and_kernelwidth.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pprts_b200_smooth_surface_fluxes.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    L.pprts_b200_smooth_accumulated.argtypes = [C.c_void_p, C.c_double]
     L.pprts_b200_polyfit.argtypes = [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
     L.pprts_b200_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_get_buildings_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -425,6 +430,27 @@ def slope_correction_fluxes(solver: Solver, edir, lslope_correction=True, latm_c
     _chk(lib().pprts_b200_slope_correction_fluxes(solver._h, int(bool(lslope_correction)), int(bool(latm_correction)),
                                                   _vp(edir)), "slope_correction_fluxes")
     return edir
+
+
+def find_iter_and_kernelwidth(radius, dx, dy, xm, ym):
+    """``find_iter_and_kernelwidth`` (src/pprts_postprocess.F90:86-128) -> (Niter, kernel_width); host code, no GPU"""
+    ni, kw = C.c_int(0), C.c_int(0)
+    _chk(lib().pprts_b200_find_iter_and_kernelwidth(float(radius), float(dx), float(dy), int(xm), int(ym),
+                                                    C.byref(ni), C.byref(kw)), "find_iter_and_kernelwidth")
+    return ni.value, kw.value
+
+
+def smooth_surface_fluxes(solver: Solver, edn, eup, radius):
+    """``smooth_surface_fluxes(solver, edn, eup)`` (src/pprts_postprocess.F90:44-84) with the value of
+    ``-pprts_smooth_srfc_flx`` as ``radius`` (``None`` = option absent: nothing happens); the surface level of ``edn``
+    and ``eup`` (Nz+1,Nx,Ny; Fortran-ordered float64, as ``pprts_get_result`` returns them) is smoothed in place."""
+    if radius is None:
+        return edn, eup
+    for a in (edn, eup):
+        if not (a.flags["F_CONTIGUOUS"] and a.dtype == np.float64):
+            raise PprtsError("smooth_surface_fluxes: edn / eup must be Fortran-ordered float64 arrays")
+    _chk(lib().pprts_b200_smooth_surface_fluxes(solver._h, float(radius), _vp(edn), _vp(eup)), "smooth_surface_fluxes")
+    return edn, eup
 
 
 def polyfit(vx, vy, d):

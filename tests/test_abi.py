@@ -79,6 +79,22 @@ def test_host_polyfit_matches_oracle(built_lib):
     assert ierr == 1                                   # equal abscissae (:198-207)
 
 
+def test_host_find_iter_and_kernelwidth_matches_oracle(built_lib):
+    """find_iter_and_kernelwidth of smooth_surface_fluxes (src/pprts_postprocess.F90:86-128) is plain host code in the
+    library: checked on the CPU against the oracle's restatement, including the reference's error for radii that
+    would need more than 250 iterations"""
+    import pytest
+    from oracle import binding as ob
+    from tenstream_b200 import pprts as P
+    for radius, dx, dy, xm, ym in [(0., 100., 100., 8, 8), (120., 100., 100., 8, 6), (300., 100., 50., 32, 40),
+                                   (1000., 100., 100., 256, 256), (2500., 25., 25., 1024, 1024), (40., 100., 100., 5, 5)]:
+        assert P.find_iter_and_kernelwidth(radius, dx, dy, xm, ym) == ob.find_iter_and_kernelwidth(radius, dx, dy, xm, ym)
+    with pytest.raises(P.PprtsError, match="smoothing iteration count"):
+        P.find_iter_and_kernelwidth(1e5, 100., 100., 4, 4)
+    with pytest.raises(ValueError):
+        ob.find_iter_and_kernelwidth(1e5, 100., 100., 4, 4)
+
+
 def test_header_is_c99_and_links_from_c(built_lib, tmp_path):
     """include/pprts_b200.h is the boundary a C host model compiles against: it must be plain C (no C++ / torch types)
     and a C program must link against the shared library and call it (no device needed for the config defaults)"""

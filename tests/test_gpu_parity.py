@@ -988,3 +988,66 @@ def test_slope_correction_vs_oracle(P, gpu_lut, oracle_lut):
     with pytest.raises(P.PprtsError, match="hgrad"):
         P.slope_correction_fluxes(s, np.asfortranarray(edir.copy()))
     P.destroy_pprts(s)
+
+
+def test_smooth_surface_fluxes_vs_oracle(P, gpu_lut, oracle_lut):
+    """smooth_surface_fluxes (src/pprts_postprocess.F90:44-128, convolve_ediff_srfc src/pprts_base.F90:1733-1868) on the
+    GPU against the oracle: the reference's test_convolution cases through the C-ABI, box blurs of several radii and
+    the domain mean on a solved cloud field, and the same on the device-side spectral sum of solve_bands"""
+    from oracle import binding as ob
+    eps = np.sqrt(np.finfo(np.float64).eps)
+    # tests/test_convolution/test_convolution.F90:159-214 (pulse, kernel width 1) and :40-157 (two ranks, on their global
+    # domain); radius 100 m at dx = 100 m gives one pass of width 1 on the 5x5 domain
+    z = np.zeros((2, 5, 5))
+    s = P.init_pprts(0, 2, 5, 5, 100., 100., P.sundir_from_angles(0., 60.), dz1d=np.full(2, 100.), lut=gpu_lut)
+    radius = next(r for r in np.arange(60., 140., 1.) if ob.find_iter_and_kernelwidth(r, 100., 100., 5, 5) == (1, 1))
+    edn, eup = np.zeros((3, 5, 5), order="F"), np.zeros((3, 5, 5), order="F")
+    edn[:, 2, 2], eup[:, 2, 2] = 1., 10.
+    P.smooth_surface_fluxes(s, edn, eup, radius)
+    assert edn[2, 2, 2] == pytest.approx(1 / 9., abs=eps) and eup[2, 2, 2] == pytest.approx(10 / 9., abs=eps)
+    assert edn[0, 2, 2] == 1. and edn[1, 2, 2] == 1. and eup[1, 2, 2] == 10.        # only the surface level changes
+    assert P.smooth_surface_fluxes(s, edn, eup, None)[0] is edn                       # option absent
+    P.destroy_pprts(s)
+    s = P.init_pprts(0, 2, 8, 16, 100., 100., P.sundir_from_angles(0., 60.), dz1d=np.full(2, 100.), lut=gpu_lut)
+    radius = next(r for r in np.arange(60., 140., 1.) if ob.find_iter_and_kernelwidth(r, 100., 100., 8, 16) == (1, 1))
+    edn = np.zeros((3, 8, 16), order="F"); edn[:, :, 8:] = 1.
+    eup = edn.copy(order="F")
+    P.smooth_surface_fluxes(s, edn, eup, radius)
+    assert edn[2, 0, 0] == pytest.approx(1 / 3., abs=eps) and edn[2, 0, 8] == pytest.approx(2 / 3., abs=eps)
+    P.smooth_surface_fluxes(s, edn, eup, radius)                                      # test_convolution.F90:124-152
+    assert edn[2, 0, 0] == pytest.approx(1 / 3., abs=eps) and edn[2, 0, 8] == pytest.approx(2 / 3., abs=eps)
+    assert edn[2, 0, 1] == pytest.approx(1 / 9., abs=eps) and edn[2, 0, 9] == pytest.approx(8 / 9., abs=eps)
+    P.destroy_pprts(s)
+    # a solved cloud field
+    Nz, Nx, Ny = 6, 24, 18
+    rng = np.random.default_rng(8)
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    sd = P.sundir_from_angles(200., 40.)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=np.full(Nz, 70.), lut=gpu_lut)   # the reference wants dx == dy
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000.)
+    edn, eup = P.pprts_get_result(s)[:2]
+    assert np.ptp(edn[-1]) > 0
+    for radius in (-1., 0., 90., 250., 650.):              # (Niter, kernel_width) = (2,1), (11,1), (22,2)
+        want = ob.smooth_surface_fluxes(edn, eup, 100., 100., radius)
+        got = P.smooth_surface_fluxes(s, edn.copy(order="F"), eup.copy(order="F"), radius)
+        if radius >= 0:
+            assert P.find_iter_and_kernelwidth(radius, 100., 100., Nx, Ny) == ob.find_iter_and_kernelwidth(radius, 100., 100., Nx, Ny)
+        for a, b in zip(got, want):
+            assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), radius
+            assert np.array_equal(a[:-1], b[:-1])
+    with pytest.raises(P.PprtsError, match="smoothing iteration count"):
+        P.smooth_surface_fluxes(s, edn.copy(order="F"), eup.copy(order="F"), 1e6)
+    # band loop: smoothing of the accumulated edn / eup on the device
+    kb = np.stack([kabs, 2 * kabs], axis=-1)
+    P.solve_bands(s, True, 0.2, kb, ksca, g, edirTOA=np.array([600., 400.]), download=False)
+    plain = [a.copy() for a in s.get_accumulated()]
+    P._chk(P.lib().pprts_b200_smooth_accumulated(s._h, 650.), "smooth_accumulated")
+    sm = s.get_accumulated()
+    want = ob.smooth_surface_fluxes(plain[0], plain[1], 100., 100., 650.)
+    for q in (0, 1):
+        assert np.abs(sm[q] - want[q]).max() <= 1e-12 * np.abs(want[q]).max()
+        assert not np.array_equal(sm[q][-1], plain[q][-1])
+    for q in (2, 3):
+        assert np.array_equal(sm[q], plain[q])
+    P.destroy_pprts(s)

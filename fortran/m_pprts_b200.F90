@@ -180,7 +180,8 @@ contains
   !> collapseindex (init_pprts argument), -pprts_geometric_coeffs, -max_solution_err, -max_solution_time,
   !> -twostr_ratio, -solar_diff_ksp_rtol / -thermal_diff_ksp_rtol (one value for both here)
   subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, nxproc, nyproc, device, &
-      & collapseindex, lgeometric_coeffs, max_solution_err, max_solution_time, twostr_ratio, ksp_rtol)
+      & collapseindex, lgeometric_coeffs, max_solution_err, max_solution_time, twostr_ratio, ksp_rtol, &
+      & ltop_bottom_faces_planar, ltop_bottom_planes_parallel)
     use mpi
     integer, intent(in) :: icomm
     integer(iintegers), intent(in) :: Nz, Nx, Ny
@@ -192,7 +193,7 @@ contains
     integer(iintegers), intent(in), optional :: nxproc(:), nyproc(:)
     integer(iintegers), intent(in), optional :: device
     integer(iintegers), intent(in), optional :: collapseindex
-    logical, intent(in), optional :: lgeometric_coeffs
+    logical, intent(in), optional :: lgeometric_coeffs, ltop_bottom_faces_planar, ltop_bottom_planes_parallel
     real(ireals), intent(in), optional :: max_solution_err, max_solution_time, twostr_ratio, ksp_rtol
     type(c_config) :: cfg
     character(kind=c_char) :: nccl_id(128)
@@ -204,6 +205,10 @@ contains
     if (present(device)) cfg%device = device
     if (present(collapseindex)) cfg%collapseindex = collapseindex
     if (present(lgeometric_coeffs)) cfg%geometric_coeffs = merge(1, 0, lgeometric_coeffs)
+    if (cfg%geometric_coeffs .ne. 0) then ! -pprts_top_bottom_faces_planar no / -pprts_top_bottom_planes_parallel no
+      if (present(ltop_bottom_faces_planar)) cfg%geometric_coeffs = cfg%geometric_coeffs + merge(0, 2, ltop_bottom_faces_planar)
+      if (present(ltop_bottom_planes_parallel)) cfg%geometric_coeffs = cfg%geometric_coeffs + merge(0, 4, ltop_bottom_planes_parallel)
+    end if
     if (present(max_solution_err)) cfg%max_solution_err = max_solution_err
     if (present(max_solution_time)) cfg%max_solution_time = max_solution_time
     if (present(twostr_ratio)) cfg%twostr_ratio = twostr_ratio

@@ -116,7 +116,10 @@ typedef struct {
   /* -pprts_geometric_coeffs (src/pprts.F90:3046-3053): the direct-beam coefficients of every 3-D cell come from its
    * geometry (src/geometric_coeffs.F90; sloped top/bottom faces of a dz3d terrain-following grid, planar faces and
    * parallel planes as in the reference's defaults) instead of the LUT, and dir2diff is rescaled to conserve the LUT's
-   * absorption (-pprts_conserve_lut_atm_abso, :3324-3351).  3 direct streams only (3_10, 3_24).  Default 0. */
+   * absorption (-pprts_conserve_lut_atm_abso, :3324-3351).  3 direct streams only (3_10, 3_24).  Default 0.
+   * Bit flags on top of 1 select the non-default vertex variants of init_vertices (:3057-3085): + 2 =
+   * -pprts_top_bottom_faces_planar no (the fourth vertex of a face keeps its own height), + 4 =
+   * -pprts_top_bottom_planes_parallel no (the top face takes the level heights instead of bottom + dz). */
   int geometric_coeffs;
 } pprts_b200_config;
 

@@ -115,6 +115,11 @@ def lib():
     return _lib
 
 
+def _geometric_flags(geometric_coeffs, planar, parallel):
+    """cfg.geometric_coeffs: 0 off, 1 on; + 2 = -pprts_top_bottom_faces_planar no, + 4 = -pprts_top_bottom_planes_parallel no"""
+    return (1 | (0 if planar else 2) | (0 if parallel else 4)) if geometric_coeffs else 0
+
+
 def _dp(a):
     return a.ctypes.data_as(c_double_p) if a is not None else None
 
@@ -238,7 +243,8 @@ class OracleSolver:
     def __init__(self, lut: OracleLut, Nz, Nx, Ny, dx, dy, sundir, dz, solver_id=310, twostr_ratio=2.0,
                  coeff_fp32=False, by_coeff_divergence=True, diff_solver=0, rtol=-1.0, atol=-1.0,
                  maxit_dir=0, maxit_diff=0, nthreads=0, collapseindex=1, max_solution_err=5e3 / 86400.,
-                 max_solution_time=0.0, geometric_coeffs=False):
+                 max_solution_time=0.0, geometric_coeffs=False, top_bottom_faces_planar=True,
+                 top_bottom_planes_parallel=True):
         self.lut = lut
         ci = max(1, int(collapseindex))
         self.Nz_atm = Nz
@@ -250,7 +256,8 @@ class OracleSolver:
         self._dz = f_order(dz)
         cfg = _Config(solver_id, Nz, Nx, Ny, dx, dy, _dp(self._dz), (C.c_double * 3)(*sundir), twostr_ratio,
                       int(coeff_fp32), int(by_coeff_divergence), diff_solver, rtol, atol, maxit_dir, maxit_diff,
-                      nthreads, ci, int(geometric_coeffs), max_solution_err, max_solution_time)
+                      nthreads, ci, _geometric_flags(geometric_coeffs, top_bottom_faces_planar, top_bottom_planes_parallel),
+                      max_solution_err, max_solution_time)
         self._h = lib().orc_solver_create(C.byref(cfg), C.byref(lut._lut))
         if not self._h:
             raise RuntimeError("orc_solver_create failed")

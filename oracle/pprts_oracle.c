@@ -1165,8 +1165,9 @@ static double vert_height(const orc_solver *s, int katm, int i, int j) {
   return h;
 }
 /* setup_default_unit_cube_geometry(dx, dy, -1) + init_vertices (src/pprts.F90:3057-3085, :3130-3143) with
- * ltop_bottom_faces_planar = ltop_bottom_planes_parallel = .true. (their defaults under -pprts_geometric_coeffs),
- * then the z shift of :3143 */
+ * ltop_bottom_faces_planar = ltop_bottom_planes_parallel = .true. (their defaults under -pprts_geometric_coeffs)
+ * unless cfg.geometric_coeffs carries bit 2 (-pprts_top_bottom_faces_planar no) / bit 4
+ * (-pprts_top_bottom_planes_parallel no), then the z shift of :3143 */
 static void cell_vertices(const orc_solver *s, int k, int i, int j, double *v) {
   const int ka = k + s->icollapse - 1; /* atmk(k) */
   const double dz = s->dz_atm[ka + (long)s->Nz_atm * (i + (long)s->Nx * j)];
@@ -1178,8 +1179,16 @@ static void cell_vertices(const orc_solver *s, int k, int i, int j, double *v) {
   v[2] = vert_height(s, ka + 1, i, j);       /* hs(2,1,1) */
   v[5] = vert_height(s, ka + 1, i + 1, j);   /* hs(2,2,1) */
   v[8] = vert_height(s, ka + 1, i, j + 1);   /* hs(2,1,2) */
-  v[11] = v[8] + (v[5] - v[2]);              /* planar faces */
-  for (q = 0; q < 4; ++q) v[14 + 3 * q] = v[2 + 3 * q] + dz; /* parallel planes */
+  v[11] = vert_height(s, ka + 1, i + 1, j + 1); /* hs(2,2,2) */
+  v[14] = vert_height(s, ka, i, j);          /* hs(1,1,1) */
+  v[17] = vert_height(s, ka, i + 1, j);      /* hs(1,2,1) */
+  v[20] = vert_height(s, ka, i, j + 1);      /* hs(1,1,2) */
+  v[23] = vert_height(s, ka, i + 1, j + 1);  /* hs(1,2,2) */
+  if (!(s->cfg.geometric_coeffs & 2)) {      /* planar faces */
+    v[11] = v[8] + (v[5] - v[2]);
+    v[23] = v[20] + (v[17] - v[14]);
+  }
+  if (!(s->cfg.geometric_coeffs & 4)) for (q = 0; q < 4; ++q) v[14 + 3 * q] = v[2 + 3 * q] + dz; /* parallel planes */
   zmin = v[2];
   for (q = 1; q < 8; ++q) zmin = dmin(zmin, v[2 + 3 * q]);
   for (q = 0; q < 8; ++q) v[2 + 3 * q] -= zmin;

@@ -106,7 +106,8 @@ typedef struct {
                             all results have Nz - collapseindex + 1 layers. <= 1: off */
   int geometric_coeffs;     /* -pprts_geometric_coeffs (src/pprts.F90:3046-3053): dir2dir from the cell geometry
                                (src/geometric_coeffs.F90), planar and parallel top/bottom faces, dir2diff rescaled to
-                               conserve the LUT's absorption (-pprts_conserve_lut_atm_abso, :3324-3351); 3 direct streams */
+                               conserve the LUT's absorption (-pprts_conserve_lut_atm_abso, :3324-3351); 3 direct streams;
+                               + 2 = -pprts_top_bottom_faces_planar no, + 4 = -pprts_top_bottom_planes_parallel no */
   double max_solution_err;  /* -max_solution_err [W], src/tenstream_options.F90:90 default 5e3/86400; <= 0 disables */
   double max_solution_time; /* -max_solution_time [s], :94 default 0 = error estimates disabled */
 } orc_config;

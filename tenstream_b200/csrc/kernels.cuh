@@ -404,8 +404,10 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
 // LUT's dir2dir (T_LUT) and dir2diff (S_LUT), the direct-beam coefficients of every 3-D cell are replaced by the
 // analytic ones of its (sloped) geometry and dir2diff is rescaled per source stream so that the cell absorbs exactly
 // what the LUT says: S_G(:, src) = S_LUT(:, src) / |S_LUT| * (|T_LUT| + |S_LUT| - |T_G|).
-// Vertices: setup_default_unit_cube_geometry + init_vertices with planar faces and parallel planes (the defaults under
-// -pprts_geometric_coeffs); vh is determine_vertex_heights (:726-755) on the solver levels, clamped to the local domain.
+// Vertices: setup_default_unit_cube_geometry + init_vertices (:3057-3085) with planar faces and parallel planes (the
+// defaults under -pprts_geometric_coeffs) unless vmode carries bit 2 (-pprts_top_bottom_faces_planar no) / bit 4
+// (-pprts_top_bottom_planes_parallel no); vh is determine_vertex_heights (:726-755) on the solver levels, clamped to
+// the local domain.
 __global__ void k_vert_heights(long ncol, int nz, const double *__restrict__ dz, double *__restrict__ vh) {
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
@@ -415,7 +417,7 @@ __global__ void k_vert_heights(long ncol, int nz, const double *__restrict__ dz,
 }
 template <class L, class CT>
 __global__ void __launch_bounds__(128)
-k_geometric_coeffs(Grid g, int kstart, double sunx, double suny, double sunz, const double *__restrict__ kabs,
+k_geometric_coeffs(Grid g, int kstart, int vmode, double sunx, double suny, double sunz, const double *__restrict__ kabs,
                    const double *__restrict__ ksca, const double *__restrict__ dz, const double *__restrict__ vh,
                    CT *__restrict__ d2d, CT *__restrict__ d2f, double *__restrict__ cdiv_dir, int *__restrict__ bad) {
   constexpr int Nd = L::Nd, Nf = L::Nf;
@@ -426,7 +428,7 @@ k_geometric_coeffs(Grid g, int kstart, double sunx, double suny, double sunz, co
   const long col = c - (long)k * g.ncol;
   const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
   const int ip = min(i + 1, g.Nx - 1), jp = min(j + 1, g.Ny - 1);
-  const long l1 = (long)(k + 1) * g.ncol;
+  const long l0 = (long)k * g.ncol, l1 = (long)(k + 1) * g.ncol;
   double v[24];
 #pragma unroll
   for (int q = 0; q < 24; ++q) v[q] = 0.0;
@@ -435,11 +437,20 @@ k_geometric_coeffs(Grid g, int kstart, double sunx, double suny, double sunz, co
   v[2] = vh[l1 + (long)j * g.Nx + i];
   v[5] = vh[l1 + (long)j * g.Nx + ip];
   v[8] = vh[l1 + (long)jp * g.Nx + i];
-  v[11] = v[8] + (v[5] - v[2]);
+  v[11] = (vmode & 2) ? vh[l1 + (long)jp * g.Nx + ip] : v[8] + (v[5] - v[2]);
   const double dzc = dz[c];
+  if (vmode & 4) {  // top face from the level heights above the cell
+    v[14] = vh[l0 + (long)j * g.Nx + i];
+    v[17] = vh[l0 + (long)j * g.Nx + ip];
+    v[20] = vh[l0 + (long)jp * g.Nx + i];
+    v[23] = (vmode & 2) ? vh[l0 + (long)jp * g.Nx + ip] : v[20] + (v[17] - v[14]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[14 + 3 * q] = v[2 + 3 * q] + dzc;
+  }
   double zmin = v[2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { v[14 + 3 * q] = v[2 + 3 * q] + dzc; zmin = fmin(zmin, fmin(v[2 + 3 * q], v[14 + 3 * q])); }
+  for (int q = 1; q < 8; ++q) zmin = fmin(zmin, v[2 + 3 * q]);
 #pragma unroll
   for (int q = 0; q < 8; ++q) v[2 + 3 * q] -= zmin;
   const double sundir[3] = {sunx, suny, sunz};

@@ -826,7 +826,7 @@ template <class L, class CT>
 static bool launch_geometric(pprts_b200_solver *s, long n3d, double sx, double sy, double sz) {
   if constexpr (L::Nd == 3) {
     const Grid &g = s->g;
-    LAUNCH(s, FAM_LOOKUP, (k_geometric_coeffs<L, CT>), nblk(n3d, 128), 128, g, s->n1d, sx, sy, sz,
+    LAUNCH(s, FAM_LOOKUP, (k_geometric_coeffs<L, CT>), nblk(n3d, 128), 128, g, s->n1d, s->cfg.geometric_coeffs, sx, sy, sz,
            (const double *)s->kabs, (const double *)s->ksca, (const double *)s->dz, (const double *)s->vh,
            (CT *)s->d2d, (CT *)s->d2f, s->cdiv_dir, s->bad);
     return true;

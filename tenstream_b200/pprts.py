@@ -299,7 +299,8 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
                keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
-               max_solution_time=None, geometric_coeffs=False) -> Solver:
+               max_solution_time=None, geometric_coeffs=False, top_bottom_faces_planar=True,
+               top_bottom_planes_parallel=True) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -341,7 +342,9 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
         cfg.max_solution_err = float(max_solution_err)
     if max_solution_time is not None:
         cfg.max_solution_time = float(max_solution_time)
-    cfg.geometric_coeffs = int(bool(geometric_coeffs))      # -pprts_geometric_coeffs
+    # -pprts_geometric_coeffs; + 2 = -pprts_top_bottom_faces_planar no, + 4 = -pprts_top_bottom_planes_parallel no
+    cfg.geometric_coeffs = ((1 | (0 if top_bottom_faces_planar else 2) | (0 if top_bottom_planes_parallel else 4))
+                            if geometric_coeffs else 0)
     cfg.nxproc = len(nxproc) if nxproc is not None else 1
     cfg.nyproc = len(nyproc) if nyproc is not None else 1
     if cfg.nxproc * cfg.nyproc > 1:

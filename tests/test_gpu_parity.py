@@ -1051,3 +1051,35 @@ def test_smooth_surface_fluxes_vs_oracle(P, gpu_lut, oracle_lut):
     for q in (2, 3):
         assert np.array_equal(sm[q], plain[q])
     P.destroy_pprts(s)
+
+
+def test_geometric_vertex_variants_vs_oracle(P, gpu_lut, oracle_lut):
+    """-pprts_top_bottom_faces_planar no / -pprts_top_bottom_planes_parallel no (init_vertices, src/pprts.F90:3057-3085)
+    on a hill in x and y whose layers shrink differently with height: coefficients and fluxes against the oracle (whose
+    vertices are checked against a numpy restatement of init_vertices in tests/test_oracle_geometric_coeffs.py)"""
+    from oracle import binding as ob
+    rng = np.random.default_rng(6)
+    Nz, Nx, Ny = 4, 5, 6
+    i, j, k = np.arange(Nx)[None, :, None], np.arange(Ny)[None, None, :], np.arange(Nz)[:, None, None]
+    dz3d = 60. * (1.0 - 0.3 / (1.0 + ((i - Nx / 2.0) / 1.5) ** 2 + ((j - Ny / 2.0) / 2.0) ** 2) * (0.6 + 0.4 * k / Nz))
+    kabs = 10 ** rng.uniform(-6, -4, (Nz, Nx, Ny))
+    ksca = 10 ** rng.uniform(-5, -3, (Nz, Nx, Ny))
+    g = rng.uniform(0, 0.8, (Nz, Nx, Ny))
+    sd = P.sundir_from_angles(130., 40.)
+    T = {}
+    for planar, parallel in ((True, True), (False, True), (True, False), (False, False)):
+        kw = dict(geometric_coeffs=True, top_bottom_faces_planar=planar, top_bottom_planes_parallel=parallel)
+        s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz3d=dz3d, lut=gpu_lut, coeff_fp32=False, rtol=1e-10, atol=1e-30, **kw)
+        o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz3d, diff_solver=1, rtol=1e-10, atol=1e-30, **kw)
+        P.set_optical_properties(s, 0.2, kabs, ksca, g)
+        o.set_optical_properties(0.2, kabs, ksca, g)
+        P.solve_pprts(s, False, True, 1000.)
+        assert o.solve(False, True, 1000.) == 0
+        for w in (1, 2):
+            a, b = s.coeffs(w), o.coeffs(w)
+            assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max(), (planar, parallel, w)
+        for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
+            assert relerr(a, b) < 1e-7, (planar, parallel, name, relerr(a, b))
+        T[planar, parallel] = s.coeffs(1).copy()
+        P.destroy_pprts(s); o.destroy()
+    assert np.abs(T[False, True] - T[True, True]).max() > 1e-4 and np.abs(T[True, False] - T[True, True]).max() > 1e-4

@@ -213,3 +213,67 @@ def test_geometric_coeffs_with_collapse_and_1d_layers(oracle_lut):
     assert s2.solve(False, True, 1000.) == 0
     assert np.abs(s2.coeffs(1) - T[:, 1:]).max() < 1e-13
     s2.destroy()
+
+
+def hill_dz_2d(Nz, Nx, Ny, dz=60.):
+    """layers that shrink over a hill in x AND y, and differently per layer: neither planar faces nor parallel planes"""
+    i, j, k = np.arange(Nx)[None, :, None], np.arange(Ny)[None, None, :], np.arange(Nz)[:, None, None]
+    bump = 0.3 / (1.0 + ((i - Nx / 2.0) / 1.5) ** 2 + ((j - Ny / 2.0) / 2.0) ** 2)
+    return dz * (1.0 - bump * (0.6 + 0.4 * k / Nz))
+
+
+def reference_vertices(dz, k, i, j, dx, planar, parallel):
+    """init_vertices (src/pprts.F90:3057-3085) after setup_default_unit_cube_geometry(dx, dy, -1), and the z shift of
+    :3143, written out independently of the oracle: hs = vert_heights(k:k+1, i:i+1, j:j+1), heights clamped to the
+    local domain (determine_vertex_heights, :726-755)"""
+    Nz, Nx, Ny = dz.shape
+    h = np.concatenate([np.zeros((1, Nx, Ny)), -np.cumsum(dz, axis=0)])
+    ip, jp = min(i + 1, Nx - 1), min(j + 1, Ny - 1)
+    hs = lambda lev, a, b: h[lev, a, b]
+    v = np.zeros(24)
+    v[[3, 9, 15, 21]] = dx
+    v[[7, 10, 19, 22]] = dx
+    v[2], v[5], v[8], v[11] = hs(k + 1, i, j), hs(k + 1, ip, j), hs(k + 1, i, jp), hs(k + 1, ip, jp)
+    v[14], v[17], v[20], v[23] = hs(k, i, j), hs(k, ip, j), hs(k, i, jp), hs(k, ip, jp)
+    if planar:
+        v[11] = v[8] + (v[5] - v[2])
+        v[23] = v[20] + (v[17] - v[14])
+    if parallel:
+        v[14::3] = v[2:12:3] + dz[k, i, j]
+    v[2::3] -= v[2::3].min()
+    return v
+
+
+@pytest.mark.parametrize("planar,parallel", [(True, True), (False, True), (True, False), (False, False)])
+def test_vertex_variants_of_init_vertices(oracle_lut, planar, parallel):
+    """-pprts_top_bottom_faces_planar / -pprts_top_bottom_planes_parallel (src/pprts.F90:3046-3085): the solver's
+    dir2dir of every cell equals dir2dir3_geometric_coeffs on the vertices init_vertices builds for the variant"""
+    Nz, Nx, Ny = 4, 5, 6
+    dz = hill_dz_2d(Nz, Nx, Ny)
+    out = solve(oracle_lut, dz, True, phi=130., theta=40., top_bottom_faces_planar=planar,
+                top_bottom_planes_parallel=parallel)
+    kabs, ksca, g = make_atm(Nz, Nx, Ny)
+    ksca = ksca * (1.0 - g * g)                      # delta scaling with f = g^2 (src/pprts.F90:1903-1917) leaves kabs alone
+    sd = ob.sundir_from_angles(130., 40.)
+    for (k, i, j) in [(0, 0, 0), (1, 2, 3), (2, 4, 5), (3, 1, 2), (3, 4, 0)]:
+        v = reference_vertices(dz, k, i, j, 100., planar, parallel)
+        want = ob.dir2dir3_geometric_coeffs(v, sd, kabs[k, i, j] + ksca[k, i, j])
+        assert np.abs(out["T"][:, k, i, j] - want).max() < 1e-13, (k, i, j)
+    # energy closure holds for every variant (dir2diff is rescaled to conserve the table's absorption)
+    edn, eup, abso, edir = out["res"]
+    inc = edir[0].sum() + edn[0].sum()
+    bal = eup[0].sum() + (edir[-1].sum() + edn[-1].sum() - eup[-1].sum()) + (abso * dz).sum()
+    assert abs(bal / inc - 1) < 1e-8
+
+
+def test_vertex_variants_differ_only_where_the_geometry_does(oracle_lut):
+    dz = hill_dz_2d(4, 5, 6)
+    base = solve(oracle_lut, dz, True)["T"]
+    assert np.abs(solve(oracle_lut, dz, True, top_bottom_faces_planar=False)["T"] - base).max() > 1e-4
+    assert np.abs(solve(oracle_lut, dz, True, top_bottom_planes_parallel=False)["T"] - base).max() > 1e-4
+    # a hill in y only has planar faces anyway; a flat grid has parallel planes anyway
+    dzy = hill_dz(4, 5, 6)
+    assert np.abs(solve(oracle_lut, dzy, True, top_bottom_faces_planar=False)["T"] - solve(oracle_lut, dzy, True)["T"]).max() < 1e-13
+    flat = np.full((4, 5, 6), 60.)
+    assert np.abs(solve(oracle_lut, flat, True, top_bottom_faces_planar=False, top_bottom_planes_parallel=False)["T"]
+                  - solve(oracle_lut, flat, True)["T"]).max() < 1e-13

@@ -118,3 +118,25 @@ def box_buildings(Nz, Nx, Ny, cells, albedo, planck=None):
     if planck is not None:
         b.planck = np.full(len(b.iface), float(planck))
     return b
+
+
+def check_buildings_energy_balance(buildings, lsolar, balance_limit=-1.0):
+    """pprts_get_result::check_buildings_energy_balance (src/pprts.F90:5942-5984) with the value of
+    ``-pprts_check_buildings_energy_balance`` as ``balance_limit`` (negative: off, the default).  For a solar result
+    every face has to reflect what hits it: ``(edir + incoming) * albedo - outgoing``; faces whose imbalance reaches
+    the limit are reported and the check fails, as CHKERR(errcnt) does in the reference.  Thermal results are not
+    checked there either.  Returns the per-face balance (None when the check is off or not solar)."""
+    if balance_limit < 0 or not lsolar:
+        return None
+    b = buildings
+    balance = (np.asarray(b.edir) + np.asarray(b.incoming)) * np.asarray(b.albedo) - np.asarray(b.outgoing)
+    bad = np.flatnonzero(np.abs(balance) >= balance_limit)
+    if len(bad):
+        lines = []
+        for m in bad:
+            face, k, i, j = ind_1d_to_nd(b.da_offsets, b.iface[m])
+            lines.append(f"face nr. {m + 1} faceidx {int(b.iface[m])} cell_kij {(k, i, j)} {buildingid2str(face)} "
+                         f"edir {b.edir[m]} ediff {b.incoming[m]} albedo {b.albedo[m]} outgoing {b.outgoing[m]} "
+                         f"balance {balance[m]}")
+        raise ValueError(f"failed energy balance on buildings faces ({len(bad)}):\n" + "\n".join(lines))
+    return balance

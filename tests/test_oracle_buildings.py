@@ -111,6 +111,14 @@ def test_buildings_example_albedo(oracle_lut):
     assert bld.edir[0] == pytest.approx(S0, abs=ATOL)
     assert np.abs(bld.edir[1:]).max() <= ATOL
     np.testing.assert_allclose((bld.edir + bld.incoming) * box_albedo, bld.outgoing, atol=ATOL)
+    # -pprts_check_buildings_energy_balance (src/pprts.F90:5942-5984): passes at the test's tolerance, fails when a face
+    # does not reflect what hits it, off by default and for thermal results
+    bal = B.check_buildings_energy_balance(bld, True, ATOL)
+    assert bal.shape == bld.iface.shape and np.abs(bal).max() < ATOL
+    assert B.check_buildings_energy_balance(bld, True) is None and B.check_buildings_energy_balance(bld, False, ATOL) is None
+    bld.outgoing[2] += 0.1
+    with pytest.raises(ValueError, match=r"failed energy balance on buildings faces \(1\)[\s\S]*face nr. 3 .*PPRTS_LEFT_FACE"):
+        B.check_buildings_energy_balance(bld, True, ATOL)
 
 
 def test_buildings_example_emission(oracle_lut):

@@ -206,8 +206,10 @@ contains
     if (present(collapseindex)) cfg%collapseindex = collapseindex
     if (present(lgeometric_coeffs)) cfg%geometric_coeffs = merge(1, 0, lgeometric_coeffs)
     if (cfg%geometric_coeffs .ne. 0) then ! -pprts_top_bottom_faces_planar no / -pprts_top_bottom_planes_parallel no
-      if (present(ltop_bottom_faces_planar)) cfg%geometric_coeffs = cfg%geometric_coeffs + merge(0, 2, ltop_bottom_faces_planar)
-      if (present(ltop_bottom_planes_parallel)) cfg%geometric_coeffs = cfg%geometric_coeffs + merge(0, 4, ltop_bottom_planes_parallel)
+      if (present(ltop_bottom_faces_planar)) &
+        & cfg%geometric_coeffs = cfg%geometric_coeffs + merge(0, 2, ltop_bottom_faces_planar)
+      if (present(ltop_bottom_planes_parallel)) &
+        & cfg%geometric_coeffs = cfg%geometric_coeffs + merge(0, 4, ltop_bottom_planes_parallel)
     end if
     if (present(max_solution_err)) cfg%max_solution_err = max_solution_err
     if (present(max_solution_time)) cfg%max_solution_time = max_solution_time

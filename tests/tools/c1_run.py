@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """BASELINE configs[0]: the box-cloud example (examples/pprts/pprts_box_cld.F90), 3_10, one solar band, 32x32x40.
 GPU solve time (cold start each time) next to the CPU oracle on one host core, fluxes compared.
-   python tools/c1_run.py"""
+   python tests/tools/c1_run.py"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import binding as ob  # noqa: E402  (tool, not product)
 from tenstream_b200 import lut as L  # noqa: E402

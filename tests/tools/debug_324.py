@@ -1,10 +1,11 @@
 """Per-quantity comparison of the 3_24 solve against the oracle (diagnostic; run on a GPU box)."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 from tenstream_b200 import pprts as P, lut as L
 from oracle import binding as ob
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_gpu_parity import relerr, random_atm
 
 cfg = L.small_test_config(324)

@@ -456,6 +456,18 @@ def smooth_surface_fluxes(solver: Solver, edn, eup, radius):
     return edn, eup
 
 
+def postprocess_accumulated(solver: Solver, smooth_srfc_flx=None, lslope_correction=False, latm_correction=False):
+    """The spectral callers' post-processing of the band sum (rrtmg/rrtmg/pprts_rrtmg.F90:319-320:
+    ``smooth_surface_fluxes(solver, edn, eup)`` then ``slope_correction_fluxes(solver, edir)``) applied to the
+    device-side accumulator of ``solve_bands(..., download=False)`` before ``get_accumulated``; the arguments carry
+    the values of ``-pprts_smooth_srfc_flx`` (``None`` = absent), ``-pprts_slope_correction``, ``-pprts_atm_correction``."""
+    if smooth_srfc_flx is not None:
+        _chk(lib().pprts_b200_smooth_accumulated(solver._h, float(smooth_srfc_flx)), "smooth_accumulated")
+    if lslope_correction or latm_correction:
+        _chk(lib().pprts_b200_slope_correct_accumulated(solver._h, int(bool(lslope_correction)),
+                                                        int(bool(latm_correction))), "slope_correct_accumulated")
+
+
 def polyfit(vx, vy, d):
     """``polyfit`` (src/adaptive_spectral_integration.F90:174-257) -> (coefficients, ierr); host code, no GPU needed"""
     vx = np.ascontiguousarray(vx, dtype=np.float64)

@@ -46,6 +46,7 @@ module m_pprts_b200
       & diff_explicit, krylov_fp32, collapseindex
     real(c_double) :: max_solution_err, max_solution_time
     integer(c_int) :: geometric_coeffs
+    integer(c_int) :: accept_incomplete_solve, gmres_restart
   end type
 
   interface
@@ -178,10 +179,10 @@ contains
   !> the halo exchange is bootstrapped over icomm (rank 0 creates the NCCL id, MPI_Bcast distributes it).
   !> The trailing optional arguments carry what the reference reads from its options database:
   !> collapseindex (init_pprts argument), -pprts_geometric_coeffs, -max_solution_err, -max_solution_time,
-  !> -twostr_ratio, -solar_diff_ksp_rtol / -thermal_diff_ksp_rtol (one value for both here)
+  !> -twostr_ratio, -solar_diff_ksp_rtol / -thermal_diff_ksp_rtol (one value for both here), -accept_incomplete_solve
   subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, nxproc, nyproc, device, &
       & collapseindex, lgeometric_coeffs, max_solution_err, max_solution_time, twostr_ratio, ksp_rtol, &
-      & ltop_bottom_faces_planar, ltop_bottom_planes_parallel)
+      & ltop_bottom_faces_planar, ltop_bottom_planes_parallel, laccept_incomplete_solve)
     use mpi
     integer, intent(in) :: icomm
     integer(iintegers), intent(in) :: Nz, Nx, Ny
@@ -194,6 +195,7 @@ contains
     integer(iintegers), intent(in), optional :: device
     integer(iintegers), intent(in), optional :: collapseindex
     logical, intent(in), optional :: lgeometric_coeffs, ltop_bottom_faces_planar, ltop_bottom_planes_parallel
+    logical, intent(in), optional :: laccept_incomplete_solve  !< -accept_incomplete_solve (src/pprts.F90:4270-4275)
     real(ireals), intent(in), optional :: max_solution_err, max_solution_time, twostr_ratio, ksp_rtol
     type(c_config) :: cfg
     character(kind=c_char) :: nccl_id(128)
@@ -215,6 +217,7 @@ contains
     if (present(max_solution_time)) cfg%max_solution_time = max_solution_time
     if (present(twostr_ratio)) cfg%twostr_ratio = twostr_ratio
     if (present(ksp_rtol)) cfg%rtol = ksp_rtol
+    if (present(laccept_incomplete_solve)) cfg%accept_incomplete_solve = merge(1, 0, laccept_incomplete_solve)
     if (present(nxproc) .and. present(nyproc)) then
       call mpi_comm_rank(icomm, myid, ierr)
       call mpi_comm_size(icomm, nranks, ierr)

@@ -121,6 +121,12 @@ typedef struct {
    * -pprts_top_bottom_faces_planar no (the fourth vertex of a face keeps its own height), + 4 =
    * -pprts_top_bottom_planes_parallel no (the top face takes the level heights instead of bottom + dz). */
   int geometric_coeffs;
+  /* -accept_incomplete_solve (src/pprts.F90:4270-4275, src/pprts_explicit.F90:134-136, :213-217): 1 = a solve that
+   * hits its iteration limit returns its last iterate instead of an error.  Default 0: a failed diffuse Krylov solve is
+   * first retried from a zero initial guess with restarted GMRES, as the reference does (src/pprts.F90:4277-4296), and
+   * only then reported (error 22). */
+  int accept_incomplete_solve;
+  int gmres_restart;   /* restart length of that GMRES, <= 0: 30 (PETSc's default) */
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);
@@ -267,6 +273,10 @@ void *pprts_b200_stream(pprts_b200_solver *solver);
  * 8 halo pack/unpack; entries 9..15 are reserved (zero) */
 int pprts_b200_kernel_stats(pprts_b200_solver *solver, int reset, double ms[16], long launches[16]);
 int pprts_b200_enable_kernel_timing(pprts_b200_solver *solver, int on);
+/* how often the GMRES retry of a failed diffuse solve ran since creation (src/pprts.F90:4277-4296), and a fault
+ * injection hook for testing it: the next n primary Krylov solves report "did not converge" without iterating */
+long pprts_b200_krylov_retries(pprts_b200_solver *solver);
+int pprts_b200_debug_fail_next_krylov(pprts_b200_solver *solver, int n);
 
 const char *pprts_b200_last_error(void);
 

@@ -524,6 +524,7 @@ struct orc_solver {
   double *a11, *a12, *a13, *a23, *a33;
   double *dir2dir, *dir2diff, *diff2diff;
   double *b;
+  double *mm_xx, *mm_xb;          /* ghosted scratch of orc_mat_mult_ediff (kept between calls) */
   double *dir_scale, *diff_scale; /* Wm2_to_W, interior layout */
   /* opt_buildings (t_pprts_buildings, src/buildings.F90:40-69): faces of building cells */
   int nbld, bld_have_planck;
@@ -551,12 +552,14 @@ static void interior_to_ghosted(const orc_solver *s, int nd, const double *in, d
   LOCALS
   int d, k, i, j;
   memset(gh, 0, sizeof(double) * ngh(s, nd));
+#pragma omp parallel for schedule(static) private(i, k, d)
   for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d)
     FG(gh, nd, d, k, i, j) = FI(in, nd, d, k, i, j);
 }
 static void ghosted_to_interior(const orc_solver *s, int nd, const double *gh, double *out) {
   LOCALS
   int d, k, i, j;
+#pragma omp parallel for schedule(static) private(i, k, d)
   for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (d = 0; d < nd; ++d)
     FI(out, nd, d, k, i, j) = FG(gh, nd, d, k, i, j);
 }
@@ -785,6 +788,7 @@ void orc_solver_destroy(orc_solver *s) {
   free(s->albedo); free(s->a11); free(s->a12); free(s->a13); free(s->a23); free(s->a33);
   free(s->dir2dir); free(s->dir2diff); free(s->diff2diff); free(s->b); free(s->dir_scale); free(s->diff_scale);
   free(s->bld_iface); free(s->bld_albedo); free(s->bld_planck);
+  free(s->mm_xx); free(s->mm_xb);
   free(s);
 }
 
@@ -1562,13 +1566,24 @@ static int inv_dof(const orc_solver *s, int dof) { /* src/pprts_explicit.F90:100
 /* src/pprts_shell.F90:366-541 (op_mat_mult_ediff) */
 void orc_mat_mult_ediff(orc_solver *s, const double *x, double *y) {
   LOCALS
-  double *xx = (double *)malloc(sizeof(double) * ngh(s, Nf));
-  double *xb = (double *)calloc(ngh(s, Nf), sizeof(double));
-  long col, n, N = nin(s, Nf);
+  double *xx, *xb;
+  long n, N = nin(s, Nf);
+  int colour, jj;
+  if (!s->mm_xx) { s->mm_xx = (double *)malloc(sizeof(double) * ngh(s, Nf)); s->mm_xb = (double *)malloc(sizeof(double) * ngh(s, Nf)); }
+  xx = s->mm_xx; xb = s->mm_xb;
+  memset(xb, 0, sizeof(double) * ngh(s, Nf));
   interior_to_ghosted(s, Nf, x, xx);
   halo_fill_5pt(s, Nf, xx); /* DMGlobalToLocal */
-  for (col = 0; col < (long)Nx * Ny; ++col) {
-    int i = (int)(col % Nx), j = (int)(col / Nx), k, idst, isrc, dst, src, mdst, msrc;
+  /* The reference's cell loop scatter-adds into the cell's own faces and the faces i+1 / j+1 / k+1; every entry of xb
+   * has exactly ONE producing cell, so the result does not depend on the order of the cells.  Rows j of one parity
+   * never write the same entries (row j touches rows j and j+1 of the ghosted array), so the cell loop runs as two
+   * OpenMP-parallel half sweeps over j -- bitwise identical to the serial loop. */
+  for (colour = 0; colour < 2; ++colour) {
+#pragma omp parallel for schedule(static)
+  for (jj = colour; jj < Ny; jj += 2) {
+  int i;
+  for (i = 0; i < Nx; ++i) {
+    int j = jj, k, idst, isrc, dst, src, mdst, msrc;
     for (k = 0; k < Nz; ++k) {
       if (s->l1d[k]) {
         for (idst = 0; idst < Nft; ++idst) {
@@ -1607,10 +1622,12 @@ void orc_mat_mult_ediff(orc_solver *s, const double *x, double *y) {
     for (idst = 0; idst < Nft; ++idst) if (!s->st.ft_inward[idst]) /* albedo row :500-505 */
       FG(xb, Nf, idst, Nz, i, j) -= FG(xx, Nf, inv_dof(s, idst), Nz, i, j) * A2(s->albedo, i, j);
   }
+  }
+  }
   halo_reduce_5pt(s, Nf, xb); /* DMLocalToGlobal(ADD_VALUES) */
   ghosted_to_interior(s, Nf, xb, y);
+#pragma omp parallel for schedule(static)
   for (n = 0; n < N; ++n) y[n] += x[n]; /* VecAXPY: diagonal */
-  free(xx); free(xb);
 }
 
 /* src/pprts_explicit.F90:715-848 (exchange_diffuse_boundary), one periodic rank */
@@ -1739,7 +1756,22 @@ static int explicit_ediff(orc_solver *s, orc_solution *sol) {
 /* Unpreconditioned BiCGStab on the shell operator with the convergence test of MyKSPConverged
  * (src/pprts.F90:4437-4486: r/r0 <= rtol or r <= atol, checked from iteration 1; nonzero initial guess :4343).
  * PETSc's KSPFBCGS+ILU itself is third-party and not restated; any converged Krylov method yields the same x. */
-static double dot_(const double *a, const double *b, long n) { double s = 0; long i; for (i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+/* blocked sum: fixed blocks of 65536 entries added in index order, so the value does not depend on the thread count */
+static double dot_(const double *a, const double *b, long n) {
+  const long B = 65536, nb = (n + B - 1) / B;
+  double *part = (double *)malloc(sizeof(double) * (nb > 0 ? nb : 1)), s = 0;
+  long ib;
+#pragma omp parallel for schedule(static)
+  for (ib = 0; ib < nb; ++ib) {
+    long i, e = (ib + 1) * B < n ? (ib + 1) * B : n;
+    double acc = 0;
+    for (i = ib * B; i < e; ++i) acc += a[i] * b[i];
+    part[ib] = acc;
+  }
+  for (ib = 0; ib < nb; ++ib) s += part[ib];
+  free(part);
+  return s;
+}
 static int bicgstab_ediff(orc_solver *s, orc_solution *sol) {
   long n = nin(s, s->st.Nf), i;
   int maxit = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 1000, it, converged = 0;
@@ -1752,6 +1784,7 @@ static int bicgstab_ediff(orc_solver *s, orc_solution *sol) {
   atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
   if (sol->diff_hist[0] < 0) { rtol = dmin(rtol, rtol_d); atol = dmin(atol, atol_d); }
   orc_mat_mult_ediff(s, x, r);
+#pragma omp parallel for schedule(static)
   for (i = 0; i < n; ++i) { r[i] = s->b[i] - r[i]; rh[i] = r[i]; }
   r0n = dmax(DBL_MIN, sqrt(dot_(r, r, n)));
   sol->diff_hist[0] = r0n;
@@ -1759,13 +1792,16 @@ static int bicgstab_ediff(orc_solver *s, orc_solution *sol) {
   for (it = 1; it <= maxit; ++it) {
     rho1 = dot_(rh, r, n);
     beta = (rho1 / rho) * (alpha / omega);
+#pragma omp parallel for schedule(static)
     for (i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
     orc_mat_mult_ediff(s, p, v);
     alpha = rho1 / dot_(rh, v, n);
+#pragma omp parallel for schedule(static)
     for (i = 0; i < n; ++i) sv[i] = r[i] - alpha * v[i];
     orc_mat_mult_ediff(s, sv, t);
     tt = dot_(t, t, n);
     omega = tt > 0 ? dot_(t, sv, n) / tt : 0.0;
+#pragma omp parallel for schedule(static)
     for (i = 0; i < n; ++i) { x[i] += alpha * p[i] + omega * sv[i]; r[i] = sv[i] - omega * t[i]; }
     rho = rho1;
     rn = sqrt(dot_(r, r, n));

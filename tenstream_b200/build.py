@@ -1,6 +1,7 @@
 """In-tree build of libpprts_b200.so with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot)."""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -9,7 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpprts_b200.so")
 SOURCES = ["solver.cu", "f2c.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "internal.h", "lut_axes.h", os.path.join("..", "..", "include", "pprts_b200.h")]
+
+# every header under csrc/ (kernels.cuh includes geometric_coeffs.cuh, ...) plus the public one
+HEADERS = sorted(os.path.basename(f) for f in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))) \
+    + [os.path.join("..", "..", "include", "pprts_b200.h")]
 
 
 def nvcc_path() -> str:

@@ -28,7 +28,12 @@ struct Grid {
   long ncp;    // ncell padded to a multiple of PB_TILE
   double dx, dy;
   int gx, gy;  // 1: the domain is split across GPUs in x / y -> the high-x / high-y faces are ghost planes
+  int kb1d;    // first layer of the 1-D block at the BOTTOM of the column (Nz if there is none), see is1d()
 };
+// determine_1d_layers (src/pprts.F90:649-725) yields a 1-D block of n1d layers contiguous from the top and, when only
+// the lowest layer is thicker than twostr_ratio * dx, that layer on its own: l1d = [T..T, F..F, T].  Kernels get the top
+// block as `n1d` and the bottom one through the grid.
+__host__ __device__ __forceinline__ bool is1d(const Grid &g, int n1d, int k) { return k < n1d || k >= g.kb1d; }
 
 // x/y decomposition (src/pprts_base.F90:721-828, halo exchange src/pprts_explicit.F90:232-328, :715-848).
 // A state vector of ND dofs is [ND*nlev main][ND*(Nz+1)*Ny ghost-x][ND*(Nz+1)*Nx ghost-y]: the ghost-x block holds the

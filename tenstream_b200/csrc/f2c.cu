@@ -15,6 +15,7 @@
 static pprts_b200_solver *g_solver = nullptr;
 static pprts_b200_lut *g_lut = nullptr;
 static bool g_lut_owned = false;
+static int g_lut_users = 0;  // the module-level solver and every live OPP container hold the default table set
 static int g_solver_id = 0;
 static void (*g_abort_handler)(const char *) = nullptr;
 
@@ -30,8 +31,16 @@ static void chkerr(int rc, const char *where) {
 extern "C" void pprts_b200_f2c_set_abort_handler(void (*h)(const char *)) { g_abort_handler = h; }
 // Register an already opened table set for the module-level solver (tests use reduced parameter spaces).
 extern "C" void pprts_b200_f2c_set_lut(pprts_b200_lut *lut) {
-  if (g_lut && g_lut_owned) pprts_b200_lut_close(g_lut);
+  if (g_lut && g_lut_owned && g_lut_users == 0) pprts_b200_lut_close(g_lut);
   g_lut = lut;
+  g_lut_owned = false;
+}
+// the default table set is closed when its last user (module-level solver or OPP container) goes away
+static void release_default_lut() {
+  if (g_lut_users > 0) --g_lut_users;
+  if (g_lut_users > 0) return;
+  if (g_lut && g_lut_owned) pprts_b200_lut_close(g_lut);
+  g_lut = nullptr;
   g_lut_owned = false;
 }
 
@@ -84,6 +93,7 @@ extern "C" void pprts_f2c_init(int fcomm, int *solver_id, int *Nz, int *Nx, int 
   cfg.sundir[1] = -std::sin(t * d2r) * std::cos(p * d2r);
   cfg.sundir[2] = -std::cos(t * d2r);
   chkerr(pprts_b200_create(&cfg, g_lut, &g_solver), "pprts_f2c_init: init_pprts");
+  if (g_solver) ++g_lut_users;
   g_solver_id = *solver_id;
 }
 
@@ -119,17 +129,14 @@ extern "C" void pprts_f2c_get_result(int Nz, int Nx, int Ny, float *edn, float *
 
 extern "C" void pprts_f2c_destroy(int lfinalizepetsc) {
   (void)lfinalizepetsc;
-  if (g_solver) { pprts_b200_destroy(g_solver); g_solver = nullptr; }
-  if (g_lut && g_lut_owned) { pprts_b200_lut_close(g_lut); }
-  g_lut = nullptr;
-  g_lut_owned = false;
+  if (g_solver) { pprts_b200_destroy(g_solver); g_solver = nullptr; release_default_lut(); }
 }
 
 // ---- coefficient probe (f2c_pprts.F90:591-758) ---------------------------------------------------------------------
 struct OppContainer {
   pprts_b200_solver *solver;
   pprts_b200_lut *lut;
-  bool lut_owned;
+  bool holds_default_lut;
   double phi, theta;
 };
 extern "C" void pprts_f2c_opp_init(const int comm, const int solver_id, void **opp, int *ierr) {
@@ -144,7 +151,7 @@ extern "C" void pprts_f2c_opp_init(const int comm, const int solver_id, void **o
   auto *c = new OppContainer();
   chkerr(open_default_lut(solver_id), "pprts_f2c_opp_init: loading LUT");
   c->lut = g_lut;
-  c->lut_owned = false;
+  c->holds_default_lut = false;
   pprts_b200_config cfg;
   pprts_b200_default_config(&cfg);
   cfg.solver_id = solver_id;
@@ -154,6 +161,7 @@ extern "C" void pprts_f2c_opp_init(const int comm, const int solver_id, void **o
   cfg.dz1d = &dz;
   cfg.sundir[0] = 0; cfg.sundir[1] = 0; cfg.sundir[2] = -1;
   chkerr(pprts_b200_create(&cfg, c->lut, &c->solver), "pprts_f2c_opp_init");
+  if (c->solver) { ++g_lut_users; c->holds_default_lut = true; }
   c->phi = c->theta = -999;
   *opp = c;
 }
@@ -179,6 +187,7 @@ extern "C" void pprts_f2c_opp_destroy(void *opp, int *ierr) {
   *ierr = 0;
   if (!c) return;
   pprts_b200_destroy(c->solver);
+  if (c->holds_default_lut && c->lut == g_lut) release_default_lut();
   delete c;
 }
 extern "C" void pprts_f2c_opp_get_info(void *opp, int *Ndir, int *Ndiff, float *diff_tauz_range, float *diff_w0_range,

@@ -137,13 +137,14 @@ __device__ __forceinline__ void eddington_ec(double dtau, double w0, double g, d
     tdir = 1.0 - dtau_slant;
   }
 }
-// a11..a33 are cell fields over the first n1d layers only (the 1-D block is contiguous from the top)
-__global__ void k_eddington(Grid g, int n1d, double costheta, const double *__restrict__ kabs,
+// a11..a33 are cell fields over the 1-D layers: the first n1d layers only, or all layers when the bottom layer is 1-D
+// too (is1d); one launch per 1-D block, cells [cbeg, cend)
+__global__ void k_eddington(long cbeg, long cend, double costheta, const double *__restrict__ kabs,
                             const double *__restrict__ ksca, const double *__restrict__ gg,
                             const double *__restrict__ dz, double *__restrict__ a11, double *__restrict__ a12,
                             double *__restrict__ a13, double *__restrict__ a23, double *__restrict__ a33) {
-  long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= (long)n1d * g.ncol) return;
+  long c = cbeg + (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cend) return;
   double ext = fmax(DBL_MIN, kabs[c] + ksca[c]);
   double t, r, rdir, sdir, tdir;
   eddington_ec(dz[c] * ext, ksca[c] / ext, gg[c], costheta, t, r, rdir, sdir, tdir);
@@ -322,8 +323,8 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
          CT *__restrict__ d2d, CT *__restrict__ d2f, CT *__restrict__ f2f, double *__restrict__ cdiv_dir,
          double *__restrict__ cdiv_diff, unsigned char *__restrict__ tile_class) {
   constexpr int Nd = L::Nd, Nf = L::Nf;
-  long c = (long)kstart * g.ncol + (long)blockIdx.x * blockDim.x + threadIdx.x;  // 3-D layers start at kstart
-  if (c >= g.ncell) return;
+  long c = (long)kstart * g.ncol + (long)blockIdx.x * blockDim.x + threadIdx.x;  // 3-D layers are [kstart, kb1d)
+  if (c >= (long)g.kb1d * g.ncol) return;
   float sample[4];
   lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
   InterpPlan p;
@@ -423,7 +424,7 @@ k_geometric_coeffs(Grid g, int kstart, int vmode, double sunx, double suny, doub
   constexpr int Nd = L::Nd, Nf = L::Nf;
   static_assert(Nd == 3, "geometric coeffs are only implemented for 3 direct streams (src/pprts.F90:3124-3125)");
   long c = (long)kstart * g.ncol + (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= g.ncell) return;
+  if (c >= (long)g.kb1d * g.ncol) return;
   const int k = (int)(c / g.ncol);
   const long col = c - (long)k * g.ncol;
   const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
@@ -655,7 +656,7 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
     struct In { CT c[Nd * Nd]; double sx[Nds], sy[Nds], old[Nd], a33; };
     auto load = [&](int k, In &in) {
       const long lk = (long)k * g.ncol, lk1 = lk + g.ncol;
-      if (k < n1d) {
+      if (is1d(g, n1d, k)) {
         in.a33 = a33[lk + o_own];
 #pragma unroll
         for (int d = 0; d < Ndt; ++d) in.old[d] = xold[(long)d * g.nlev + lk1 + o_own];
@@ -681,7 +682,7 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
     };
     auto level = [&](int k, const In &in) {
       const long lk = (long)k * g.ncol, lk1 = lk + g.ncol;
-      if (k < n1d) {  // 1-D layer: top(k+1) = top(k) * a33 (:383-391); side dofs are left untouched
+      if (is1d(g, n1d, k)) {  // 1-D layer: top(k+1) = top(k) * a33 (:383-391); side dofs are left untouched
 #pragma unroll
         for (int d = 0; d < Ndt; ++d) {
           top[d] = top[d] * in.a33;
@@ -772,7 +773,7 @@ k_source_solar(Grid g, int xinc, int yinc, int n1d, const CT *__restrict__ d2f, 
 #pragma unroll
   for (int d = 0; d < Nd; ++d) any = any || (edir[(long)d * g.nlev + l_own] > DBL_EPSILON);
   if (any) {
-    if (k < n1d) {
+    if (is1d(g, n1d, k)) {
       double acc_dn = 0.0, acc_up = 0.0;
 #pragma unroll
       for (int s = 0; s < Ndt; ++s) {
@@ -845,7 +846,7 @@ k_source_thermal(Grid g, int n1d, int have_Bsrfc, const double *__restrict__ Bto
   const double Az = g.dx * g.dy;
   const double b0 = planck[l_own], b1 = planck[l_dn];
   const double tauz = kabs[c] * dz[c];
-  if (k < n1d) {
+  if (is1d(g, n1d, k)) {
     double bfac = PB_PI * Az / (double)(Nft / 2);
     double btop, bbot;
     if (Btop != nullptr && k == 0) {  // collapsed block (src/pprts.F90:4875-4877)
@@ -955,7 +956,7 @@ __device__ __forceinline__ void matmult_emit(const Grid &g, int n1d, COEF coef, 
   };
   const long l_own = f.own, l_dn = f.dn;
   const int k = f.k;
-  if (k < n1d) {
+  if (is1d(g, n1d, k)) {
     const AT t = (AT)a11[l_own], r = (AT)a12[l_own];
 #pragma unroll
     for (int d = 0; d < Nft; ++d) {  // xb(dst) = x(dst) - x(d, other side)*a11 - x(inv_dof, same level)*a12
@@ -1065,6 +1066,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
   __shared__ __align__(8) unsigned long long bar[2];
   const int tid = threadIdx.x;
   const long c1d = (long)n1d * g.ncol;  // cells below this index are in 1-D layers and need no plane data
+  const long cb1d = (long)g.kb1d * g.ncol;  // ... and so are the cells from this index on (1-D bottom layer)
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -1075,7 +1077,7 @@ k_matmult_tma(Grid g, int n1d, long ntiles, const float *__restrict__ T,
   auto issue = [&](long tile, int st) {
     const long c0 = tile * PB_TILE;
     unsigned long long *b = &bar[st];
-    if (c0 + PB_TILE <= c1d) { mbar_arrive(b); return; }
+    if (c0 + PB_TILE <= c1d || c0 >= cb1d) { mbar_arrive(b); return; }
     mbar_expect_tx(b, STAGE_BYTES);
     bulk_g2s(stage(st), T + tile * (long)(NP * PB_TILE), STAGE_BYTES, b);  // one contiguous run
   };
@@ -1186,7 +1188,7 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
   for (int k = g.Nz - 1; k >= 0; --k) {
     const long c = (long)k * g.ncol + col;
     double tuu, tdu, tdd, tud;
-    if (k < n1d) { tuu = tdd = a11[c]; tdu = tud = a12[c]; }
+    if (is1d(g, n1d, k)) { tuu = tdd = a11[c]; tdu = tud = a12[c]; }
     else {
       const long cb = cbase<Nf * Nf>(c);
       tuu = (double)T[cb + (0 * Nf + 0) * PB_TILE]; tdu = (double)T[cb + (0 * Nf + 1) * PB_TILE];
@@ -1223,7 +1225,7 @@ __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long
   in.fD = r[1 * g.nlev + l1];
   in.iv = (VT)inv[c];
   in.Rc = (VT)R[c];
-  if (k < n1d) {
+  if (is1d(g, n1d, k)) {
     in.tuu = (VT)a11[c]; in.tud = (VT)a12[c];
 #pragma unroll
     for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
@@ -1262,7 +1264,7 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   auto level = [&](int k, const PrecUpIn<L, CT, VT> &cur) {
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     VT fU = cur.fU, fD = cur.fD;
-    if (k < n1d) {
+    if (is1d(g, n1d, k)) {
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
     } else {
@@ -1324,7 +1326,7 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
   in.fD = z[1 * g.nlev + l1];
   in.iv = (VT)inv[c];
   in.R1 = (VT)R[l1];
-  if (k < n1d) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
+  if (is1d(g, n1d, k)) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
   else {
     const long cb = cbase<Nf * Nf>(c);
     in.tdd = (VT)T[cb + (1 * Nf + 1) * PB_TILE];
@@ -1367,7 +1369,7 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
     const VT S1 = cur.S1;
     const VT D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
     const VT U1 = cur.R1 * D1 + S1;
-    if (k >= n1d) {  // outgoing side streams through the column's own faces
+    if (!is1d(g, n1d, k)) {  // outgoing side streams through the column's own faces
       int o = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
@@ -1409,7 +1411,7 @@ __device__ __forceinline__ void precb_top_blocks(const Grid &g, int n1d, int k, 
                                                  double (&tuu)[NP][NP], double (&tdu)[NP][NP], double (&tud)[NP][NP],
                                                  double (&tdd)[NP][NP]) {
   constexpr int Nf = L::Nf;
-  if (k < n1d) {
+  if (is1d(g, n1d, k)) {
     const double t = a11[c], r = a12[c];
 #pragma unroll
     for (int a = 0; a < NP; ++a)
@@ -1561,7 +1563,7 @@ k_precb_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__
     double fU[NP], fD[NP];
 #pragma unroll
     for (int a = 0; a < NP; ++a) { fU[a] = (double)r[(long)(2 * a) * g.nlev + c]; fD[a] = (double)r[(long)(2 * a + 1) * g.nlev + l1]; }
-    if (k < n1d) {
+    if (is1d(g, n1d, k)) {
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = r[(long)(Nft + d) * g.nlev + c];
     } else {
@@ -1639,7 +1641,7 @@ k_precb_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
     precb_matvec<NP>(M, D1, U1);
 #pragma unroll
     for (int a = 0; a < NP; ++a) U1[a] += S1[a];
-    if (k >= n1d) {  // outgoing side streams through the column's own faces
+    if (!is1d(g, n1d, k)) {  // outgoing side streams through the column's own faces
       const long cb = cbase<Nf * Nf>(c);
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
@@ -1885,6 +1887,55 @@ __global__ void k_mixed_flush(long n, float *__restrict__ xc, double *__restrict
     xc[q] = 0.f;
   }
 }
+// ---- restarted GMRES (the reference's retry after a failed KSP solve, src/pprts.F90:4277-4296) ---------------------
+// fp64 throughout; the Krylov basis V is (m+1) state vectors `stride` apart.  Orthogonalisation is classical
+// Gram-Schmidt applied twice (two fused passes instead of 2 (j+1) dependent ones); the small Hessenberg problem lives on
+// the host.
+// out[q] = (V_{j0+q}, w), q < nv <= NV
+template <int NV>
+__global__ void k_multi_dot(long n, const double *__restrict__ V, long stride, int j0, int nv,
+                            const double *__restrict__ w, double *partials, unsigned int *counter, double *out) {
+  double acc[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double wv = w[i];
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+      if (q < nv) acc[q] = fma(V[(long)(j0 + q) * stride + i], wv, acc[q]);
+  }
+  grid_reduce_sum<NV>(acc, partials, counter, out);
+}
+// w -= sum_q h[q] V_q (q < nvec); out_norm2 = (w, w) afterwards
+__global__ void k_gmres_orth(long n, const double *__restrict__ V, long stride, int nvec, const double *__restrict__ h,
+                             double *__restrict__ w, double *partials, unsigned int *counter, double *out_norm2) {
+  double acc[1] = {0.0};
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double wv = w[i];
+    for (int q = 0; q < nvec; ++q) wv = fma(-h[q], V[(long)q * stride + i], wv);
+    w[i] = wv;
+    acc[0] = fma(wv, wv, acc[0]);
+  }
+  grid_reduce_sum<1>(acc, partials, counter, out_norm2);
+}
+// v = w * scale
+__global__ void k_scale_to(long n, double scale, const double *__restrict__ w, double *__restrict__ v) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) v[i] = w[i] * scale;
+}
+// u = sum_q y[q] V_q (q < nvec)
+__global__ void k_lincomb(long n, const double *__restrict__ V, long stride, int nvec, const double *__restrict__ y,
+                          double *__restrict__ u) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int q = 0; q < nvec; ++q) acc = fma(y[q], V[(long)q * stride + i], acc);
+    u[i] = acc;
+  }
+}
+// x += a z
+__global__ void k_axpy(long n, double a, const double *__restrict__ z, double *__restrict__ x) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] = fma(a, z[i], x[i]);
+}
+
 // explicit relaxation (explicit_ediff analogue): r = b - Ax (Ax in `r` on entry)
 __global__ void k_relax_residual(long n, const double *__restrict__ b, double *__restrict__ r) {
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) r[q] = b[q] - r[q];
@@ -2153,7 +2204,7 @@ k_absorption(Grid g, int xinc, int yinc, int n1d, int lsolar, int lthermal, int 
     if (s < Ndt + Nds) return ((xinc != 0) == in) ? (long)s * g.nlev + l_own : fd.xp + s * fd.xps;
     return ((yinc != 0) == in) ? (long)s * g.nlev + l_own : fd.yp + s * fd.yps;
   };
-  const bool l1d = k < n1d;
+  const bool l1d = is1d(g, n1d, k);
   double a = 0.0;
   if (by_coeff) {
     if (lsolar) {

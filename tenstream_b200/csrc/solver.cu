@@ -81,6 +81,15 @@ static int mmap4_open(const char *path, const float **data, long *ncoef, long *n
   if (ndim != 2) { close(fd); return set_err(2, "%s: expected a 2-d table", path); }
   *ncoef = (long)header[3];
   *nlat = (long)header[4];
+  // header consistency (src/mmap.F90:85-93: [dtype_size, n_elements, n_bytes, dims...]) and the real file size: a
+  // truncated table would otherwise only show up as a SIGBUS in the middle of a lookup
+  struct stat stt;
+  if (header[1] != header[3] * header[4] || header[2] != header[1] * sizeof(float) || fstat(fd, &stt) != 0 ||
+      (size_t)stt.st_size < header[2] + (size_t)pagesize) {
+    close(fd);
+    return set_err(2, "%s: header (%zu elements, %zu bytes, %zu x %zu) does not match the file size", path, header[1],
+                   header[2], header[3], header[4]);
+  }
   *maplen = header[2] + (size_t)pagesize;
   *map = mmap(0, *maplen, PROT_READ, MAP_PRIVATE | MAP_NORESERVE, fd, 0);
   close(fd);
@@ -207,7 +216,7 @@ struct pprts_b200_solver {
   double *atm_dz = nullptr, *atm_kabs = nullptr, *atm_ksca = nullptr, *atm_gg = nullptr, *atm_planck = nullptr;
   double *Btop = nullptr, *Bbot = nullptr;
   double unconstrained_fraction = 1.0;
-  std::vector<unsigned char> l1d;
+  std::vector<unsigned char> l1d, l1d_atm;
   // sun (t_suninfo, src/pprts_base.F90:128-135)
   double phi = 0, theta = 0, mu = 0, costheta = 0, symmetry_phi = 0;
   int xinc = 0, yinc = 0;
@@ -263,6 +272,8 @@ struct pprts_b200_solver {
   double glob_ncol = 0;  // global number of columns (KSP tolerances use the global domain, pprts_base.F90:1128-1131)
   double *hs[2] = {nullptr, nullptr}, *hr[2] = {nullptr, nullptr};  // send / receive staging, [0] x faces, [1] y faces
   long halo_exchanges = 0;
+  int fail_next_krylov = 0;  // test hook: the next n primary Krylov solves report non-convergence
+  long krylov_retries = 0;
   int num_sms = 148;
   bool use_tma = true;
   // opt_buildings (t_pprts_buildings, src/buildings.F90:40-69): faces of building cells, device copies
@@ -435,11 +446,11 @@ static int halo_push(pprts_b200_solver *s, VT *v, int nd_total, HaloDofs h, bool
     const unsigned int mask = dir == 0 ? maskx : masky;
     double *tmp = s->sc + SC_TMP;
     if (ndot == 0)
-      LAUNCH(s, FAM_HALO, (k_halo_unpack<0, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+      LAUNCH(s, FAM_HALO, (k_halo_unpack<0, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.kb1d, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
     else if (ndot == 1)
-      LAUNCH(s, FAM_HALO, (k_halo_unpack<1, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+      LAUNCH(s, FAM_HALO, (k_halo_unpack<1, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.kb1d, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
     else
-      LAUNCH(s, FAM_HALO, (k_halo_unpack<2, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.Nz, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
+      LAUNCH(s, FAM_HALO, (k_halo_unpack<2, VT>), nblk((long)n, 256), 256, g, dir, d0, nd, mask, s->n1d, g.kb1d, (const VT *)hr[dir], v, w0, s->partials, s->counter, tmp, dots);
   }
   return 0;
 }
@@ -558,6 +569,35 @@ static int contract_direct_tables(pprts_b200_solver *s) {
   return 0;
 }
 
+
+// determine_1d_layers, second half (src/pprts.F90:708-724): the number of 1-D layers is made the same on all ranks
+// (N1dlayers_max) and the first N1dlayers_max layers become 1-D -- note that a 1-D BOTTOM layer found on its own stays
+// 1-D as well: l1d = [T..T, F..F, T].  count3d_frac < 0: single rank (fraction from the local mask).
+static int finalize_1d_layers(pprts_b200_solver *s, int n1d_max, double unconstrained_fraction) {
+  Grid &g = s->g;
+  const int Nza = s->Nz_atm, ci = s->icollapse;
+  for (int k = 0; k < n1d_max && k < Nza; ++k) s->l1d_atm[k] = 1;
+  int count3d = 0;
+  for (int k = 0; k < Nza; ++k) count3d += !s->l1d_atm[k];
+  s->unconstrained_fraction = unconstrained_fraction >= 0.0 ? unconstrained_fraction : (double)count3d / (double)Nza;
+  s->l1d.assign(g.Nz, 0);
+  for (int k = 0; k < g.Nz; ++k) s->l1d[k] = s->l1d_atm[k + ci - 1];  // atmk, src/pprts_base.F90:1088-1093
+  const int n1d_old = s->n1d, kb1d_old = g.kb1d;
+  s->n1d = 0;
+  while (s->n1d < g.Nz && s->l1d[s->n1d]) ++s->n1d;
+  g.kb1d = (s->n1d < g.Nz && s->l1d[g.Nz - 1]) ? g.Nz - 1 : g.Nz;
+  if (s->a11 && s->n1d == n1d_old && g.kb1d == kb1d_old) return 0;
+  for (int k = s->n1d; k < g.kb1d; ++k)
+    if (s->l1d[k]) return set_err(1, "1-D layer mask is neither contiguous from the top nor the bottom layer alone");
+  // Eddington coefficients: fields over the top n1d layers, or over all layers when the bottom layer is 1-D too
+  const size_t n1c = (size_t)(g.kb1d < g.Nz ? g.Nz : s->n1d) * g.ncol;
+  double **a[5] = {&s->a11, &s->a12, &s->a13, &s->a23, &s->a33};
+  for (auto pp : a) { if (*pp) { cudaFree(*pp); *pp = nullptr; } DA(*pp, n1c); }
+  s->coeffs_dirty = true; s->prec_ready = false; s->have_optprop = false;
+  return 0;
+}
+
+static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, pprts_b200_solver *s, int Nd, int Nf);
 extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_lut *lut, pprts_b200_solver **out) {
   if (!cfg || !lut || !out) return set_err(1, "null argument");
   int Nd, Nf;
@@ -573,7 +613,21 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return set_err(90, "no CUDA device: libpprts_b200 has no CPU fallback");
+  if (cfg->geometric_coeffs && Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
+  if ((cfg->collapseindex > 1 ? cfg->collapseindex : 1) > cfg->Nz)
+    return set_err(1, "collapseindex %d exceeds the %d atmosphere layers", cfg->collapseindex, cfg->Nz);
   auto *s = new pprts_b200_solver();
+  const int rc = create_impl(cfg, lut, s, Nd, Nf);
+  if (rc) {  // every allocation made so far hangs off the solver object: one cleanup path for all failures
+    char msg[sizeof(g_err)];
+    snprintf(msg, sizeof(msg), "%s", g_err);
+    pprts_b200_destroy(s);
+    return set_err(rc, "%s", msg);
+  }
+  *out = s;
+  return 0;
+}
+static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, pprts_b200_solver *s, int Nd, int Nf) {
   s->cfg = *cfg;
   if (s->cfg.twostr_ratio <= 0) s->cfg.twostr_ratio = 2.0;
   s->cfg.dz1d = s->cfg.dz3d = nullptr;
@@ -584,7 +638,6 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   else CU(cudaGetDevice(&s->device));
   Grid &g = s->g;
   const int ci = cfg->collapseindex > 1 ? cfg->collapseindex : 1;
-  if (ci > cfg->Nz) { delete s; return set_err(1, "collapseindex %d exceeds the %d atmosphere layers", ci, cfg->Nz); }
   s->icollapse = ci; s->Nz_atm = cfg->Nz;
   g.Nz = cfg->Nz - ci + 1; g.Nx = cfg->Nx; g.Ny = cfg->Ny;
   g.ncol = (long)g.Nx * g.Ny; g.ncell = g.ncol * g.Nz; g.nlev = g.ncol * (g.Nz + 1);
@@ -611,21 +664,17 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   l1d_atm[Nza - 1] = thick[Nza - 1];
   for (int k = Nza - 2; k >= 0; --k) if (thick[k]) { for (int kk = 0; kk <= k; ++kk) l1d_atm[kk] = 1; break; }
   for (int k = 0; k < ci && ci > 1; ++k) l1d_atm[k] = 1;  // :692-706 layers that are collapsed have to be 1-D
+  s->l1d_atm = l1d_atm;
   int n1d_atm = 0;
-  for (int k = 0; k < Nza; ++k) n1d_atm += l1d_atm[k];  // :708-719 contiguous from the top
-  s->unconstrained_fraction = (double)(Nza - n1d_atm) / (double)Nza;
-  s->n1d = n1d_atm - (ci - 1);
-  s->l1d.assign(g.Nz, 0);
-  for (int k = 0; k < g.Nz; ++k) s->l1d[k] = k < s->n1d;
+  for (int k = 0; k < Nza; ++k) n1d_atm += l1d_atm[k];
+  { int rc_ = finalize_1d_layers(s, n1d_atm, -1.0); if (rc_) return rc_; }
 
-  const size_t n1c = (size_t)s->n1d * g.ncol;
   const size_t aoff = (size_t)(ci - 1) * g.ncol;
   DA(s->atm_dz, s->ncell_atm); DA(s->atm_kabs, s->ncell_atm); DA(s->atm_ksca, s->ncell_atm); DA(s->atm_gg, s->ncell_atm);
   DA(s->atm_planck, s->nlev_atm); DA(s->Bsrfc, g.ncol); DA(s->albedo, g.ncol); DA(s->raw, s->nlev_atm);
   s->dz = s->atm_dz + aoff; s->kabs = s->atm_kabs + aoff; s->ksca = s->atm_ksca + aoff; s->gg = s->atm_gg + aoff;
   s->planck = s->atm_planck + aoff;
   if (ci > 1) { DA(s->Btop, g.ncol); DA(s->Bbot, g.ncol); }
-  DA(s->a11, n1c); DA(s->a12, n1c); DA(s->a13, n1c); DA(s->a23, n1c); DA(s->a33, n1c);
   const size_t csz = cfg->coeff_fp32 ? 4 : 8;
   CU(cudaMalloc(&s->d2d, (size_t)Nd * Nd * g.ncp * csz)); CU(cudaMemset(s->d2d, 0, (size_t)Nd * Nd * g.ncp * csz));
   CU(cudaMalloc(&s->d2f, (size_t)Nd * Nf * g.ncp * csz)); CU(cudaMemset(s->d2f, 0, (size_t)Nd * Nf * g.ncp * csz));
@@ -652,7 +701,6 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   CU(cudaMallocHost((void **)&s->h_sc, SC_COUNT * sizeof(double)));
   CU(cudaMallocHost((void **)&s->h_bad, sizeof(int)));
   CU(cudaMemcpy(s->atm_dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
-  if (cfg->geometric_coeffs && Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
   if (cfg->geometric_coeffs || cfg->dz3d) {  // determine_vertex_heights / atm%hhl (src/pprts.F90:585-600, :726-755)
     DA(s->vh_atm, s->nlev_atm);
     k_vert_heights<<<nblk(g.ncol, 128), 128, 0, s->stream>>>(g.ncol, s->Nz_atm, s->atm_dz, s->vh_atm);
@@ -673,7 +721,6 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   s->lutdev.Tdir4 = s->d_Tdir4; s->lutdev.Sdir4 = s->d_Sdir4; s->lutdev.Sdiff = s->d_Sdiff;
   build_sym_maps(cfg->solver_id, false, false, s->sym);
   setup_suninfo(s, cfg->sundir);
-  *out = s;
   return 0;
 }
 
@@ -685,7 +732,7 @@ static void free_solution(Solution &sol) {
 extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   if (!s) return 0;
   cudaSetDevice(s->device);
-  cudaStreamSynchronize(s->stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   for (auto &kv : s->solutions) free_solution(kv.second);
   for (auto &kv : s->staged) { cudaFree(kv.second.kabs); cudaFree(kv.second.ksca); cudaFree(kv.second.g);
                                cudaFree(kv.second.planck); cudaFree(kv.second.Bsrfc); cudaFree(kv.second.albedo2d); }
@@ -704,7 +751,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (auto e : s->evpool) cudaEventDestroy(e);
   if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
   for (int q = 0; q < 2; ++q) if (s->band_uploaded[q]) cudaEventDestroy(s->band_uploaded[q]);
-  cudaStreamDestroy(s->stream);
+  if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return 0;
 }
@@ -759,8 +806,11 @@ static int set_optprop_impl(pprts_b200_solver *s, double albedo, const double *k
   CU(cudaMemsetAsync(s->bad, 0, sizeof(int), s->stream));
   LAUNCH(s, FAM_IO, k_delta_scale, nblk(s->ncell_atm, 256), 256, s->ncell_atm, s->atm_kabs, s->atm_ksca, s->atm_gg, ldelta, s->bad);
   if (s->n1d > 0)
-    LAUNCH(s, FAM_IO, k_eddington, nblk((long)s->n1d * gr.ncol, 256), 256, gr, s->n1d, s->costheta, s->kabs, s->ksca,
-           s->gg, s->dz, s->a11, s->a12, s->a13, s->a23, s->a33);
+    LAUNCH(s, FAM_IO, k_eddington, nblk((long)s->n1d * gr.ncol, 256), 256, 0L, (long)s->n1d * gr.ncol, s->costheta, s->kabs,
+           s->ksca, s->gg, s->dz, s->a11, s->a12, s->a13, s->a23, s->a33);
+  if (gr.kb1d < gr.Nz)  // the bottom layer on its own (is1d, common.cuh)
+    LAUNCH(s, FAM_IO, k_eddington, nblk((long)(gr.Nz - gr.kb1d) * gr.ncol, 256), 256, (long)gr.kb1d * gr.ncol, gr.ncell,
+           s->costheta, s->kabs, s->ksca, s->gg, s->dz, s->a11, s->a12, s->a13, s->a23, s->a33);
   if (s->icollapse > 1)  // handle_atm_collapse (src/pprts.F90:2080-2123)
     LAUNCH(s, FAM_IO, k_collapse, nblk(gr.ncol, 128), 128, gr.ncol, s->icollapse, s->costheta, (int)s->have_planck,
            s->atm_kabs, s->atm_ksca, s->atm_gg, s->atm_dz, s->atm_planck, s->a11, s->a12, s->a13, s->a23, s->a33,
@@ -838,7 +888,7 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
   if (!s->coeffs_dirty && (!lsolar || s->coeffs_have_dir)) return 0;
   const Grid &g = s->g;
   if (lsolar && s->angles_dirty) { int rc = contract_direct_tables(s); if (rc) return rc; }
-  const long n3d = (long)(g.Nz - s->n1d) * g.ncol;
+  const long n3d = (long)(g.kb1d - s->n1d) * g.ncol;
   if (n3d > 0) {
     CU(cudaMemsetAsync(s->tile_class, 0, (size_t)(g.ncp / PB_TILE) * sizeof(unsigned int), s->stream));
     DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_lookup<L, CT>), nblk(n3d, 128), 128, g, s->lutdev, s->sym, (int)lsolar,
@@ -953,7 +1003,8 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   sol.first_dir = false;
   sol.lchanged = true;
   sol.lWm2_dir = false;
-  if (!converged) return set_err(20, "solar_dir_ did not converge in %d passes (res %g)", iter, sol.res_dir);
+  if (!converged && !s->cfg.accept_incomplete_solve)  // src/pprts_explicit.F90:213-217
+    return set_err(20, "solar_dir_ did not converge in %d passes (res %g); use accept_incomplete_solve to continue", iter, sol.res_dir);
   return 0;
 }
 
@@ -989,9 +1040,13 @@ static bool launch_matmult_tma_v(pprts_b200_solver *s, const VT *x, VT *y, const
   if constexpr (smem > 200 * 1024) return false;
   else {
     const Grid &g = s->g;
-    static bool attr_set = false;
+    static bool attr_set[64] = {false};  // the opt-in above 48 KB is per device (one process may drive several)
     auto kern = k_matmult_tma<L, NDOT, NSTAGE, PREFETCH, VT>;
-    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const int dev = s->device & 63;
+    if (!attr_set[dev]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+      attr_set[dev] = true;
+    }
     const long ntiles = (g.ncell + PB_TILE - 1) / PB_TILE;
     const int per_sm = std::max(1, std::min<int>(NSTAGE == 1 ? 4 : 2, (int)((220 * 1024) / smem)));
     const unsigned int grid = (unsigned int)std::min<long>(ntiles, (long)per_sm * s->num_sms);
@@ -1238,22 +1293,128 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   return 0;
 }
 
+
+// Restarted GMRES(m), right-preconditioned with the column solve, fp64: what the reference falls back to when the
+// KSP solve did not converge -- "Resetted initial guess to zero and try again with gmres" (src/pprts.F90:4277-4296).
+// Same tolerances and iteration limit as the failed solve (the KSP object keeps them), same convergence test
+// (MyKSPConverged on the GMRES residual estimate, confirmed by the true residual at the end of every cycle).
+static int solve_ediff_gmres(pprts_b200_solver *s, Solution &sol, double rtol, double atol, int maxit) {
+  const Grid &g = s->g;
+  const long n = (long)s->Nf * g.nlev, stride = (state_len(g, s->Nf) + 3) & ~3L;
+  const int m = s->cfg.gmres_restart > 0 ? std::min(s->cfg.gmres_restart, 60) : 30;
+  const bool prec = precond_available(s);
+  double *x = sol.ediff, *w = s->kr[0], *z = s->kr[1], *u = s->kr[2];
+  double *V = nullptr, *dh = nullptr;
+  CU(cudaMalloc((void **)&V, (size_t)(m + 1) * stride * sizeof(double)));
+  struct Guard { double *a, *b; ~Guard() { cudaFree(a); cudaFree(b); } } guard{V, nullptr};
+  CU(cudaMemsetAsync(V, 0, (size_t)(m + 1) * stride * sizeof(double), s->stream));
+  CU(cudaMalloc((void **)&dh, 128 * sizeof(double)));
+  guard.b = dh;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gv(m + 1), y(m), hcol(m + 2);
+  int rc, total = 0;
+  double r0 = 0.0;
+  bool converged = false;
+  auto dots_to_host = [&](int cnt) -> int {  // dh[0..cnt) summed over the ranks -> hcol
+    int e = allreduce_scalars(s, dh, cnt);
+    if (e) return e;
+    CU(cudaMemcpyAsync(hcol.data(), dh, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+  };
+  sol.niter_diff = 0;
+  for (int cycle = 0; !converged && total < maxit; ++cycle) {
+    if ((rc = launch_matmult<0, double>(s, x, w, nullptr, nullptr))) return rc;
+    LAUNCH(s, FAM_VEC, k_relax_residual, vec_grid(n), VEC_BLOCK, n, s->b, w);  // w = b - A x
+    LAUNCH(s, FAM_VEC, (k_multi_dot<1>), vec_grid(n), VEC_BLOCK, n, (const double *)w, stride, 0, 1, (const double *)w, s->partials, s->counter, dh);
+    if ((rc = dots_to_host(1))) return rc;
+    const double beta = std::sqrt(hcol[0]);
+    if (!(beta == beta)) return set_err(21, "GMRES retry broke down (NaN residual) in cycle %d", cycle);
+    if (cycle == 0) r0 = std::max(DBL_MIN, beta);
+    sol.res_diff = beta;
+    if (beta / r0 <= rtol || beta <= atol) { converged = true; break; }
+    LAUNCH(s, FAM_VEC, k_scale_to, vec_grid(n), VEC_BLOCK, n, 1.0 / beta, (const double *)w, V);
+    std::fill(gv.begin(), gv.end(), 0.0);
+    gv[0] = beta;
+    int j = 0;
+    for (; j < m && total < maxit; ++j) {
+      double *vj = V + (size_t)j * stride, *vn = V + (size_t)(j + 1) * stride;
+      if (prec) launch_prec(s, vj, z);
+      if ((rc = launch_matmult<0, double>(s, prec ? z : vj, w, nullptr, nullptr))) return rc;
+      std::vector<double> h(j + 2, 0.0);
+      double wnorm2 = 0.0;
+      for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
+        for (int j0 = 0; j0 <= j; j0 += 8) {
+          const int nv = std::min(8, j + 1 - j0);
+          LAUNCH(s, FAM_VEC, (k_multi_dot<8>), vec_grid(n), VEC_BLOCK, n, (const double *)V, stride, j0, nv, (const double *)w, s->partials, s->counter, dh + j0);
+        }
+        if ((rc = dots_to_host(j + 1))) return rc;
+        for (int q = 0; q <= j; ++q) h[q] += hcol[q];
+        LAUNCH(s, FAM_VEC, k_gmres_orth, vec_grid(n), VEC_BLOCK, n, (const double *)V, stride, j + 1, (const double *)dh, w, s->partials, s->counter, dh + 64);
+        if ((rc = allreduce_scalars(s, dh + 64, 1))) return rc;
+        CU(cudaMemcpyAsync(&wnorm2, dh + 64, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+      }
+      h[j + 1] = std::sqrt(wnorm2);
+      ++total;
+      if (!(h[j + 1] == h[j + 1])) return set_err(21, "GMRES retry broke down (NaN) at iteration %d", total);
+      if (h[j + 1] > 0.0) LAUNCH(s, FAM_VEC, k_scale_to, vec_grid(n), VEC_BLOCK, n, 1.0 / h[j + 1], (const double *)w, vn);
+      for (int q = 0; q < j; ++q) {  // previous Givens rotations, then the new one
+        const double t = cs[q] * h[q] + sn[q] * h[q + 1];
+        h[q + 1] = -sn[q] * h[q] + cs[q] * h[q + 1];
+        h[q] = t;
+      }
+      const double den = std::hypot(h[j], h[j + 1]);
+      cs[j] = den > 0 ? h[j] / den : 1.0; sn[j] = den > 0 ? h[j + 1] / den : 0.0;
+      h[j] = den; h[j + 1] = 0.0;
+      gv[j + 1] = -sn[j] * gv[j];
+      gv[j] = cs[j] * gv[j];
+      for (int q = 0; q <= j; ++q) H[(size_t)q * m + j] = h[q];
+      const double rn = std::fabs(gv[j + 1]);
+      sol.niter_diff = total;
+      sol.res_diff = rn;
+      if (rn / r0 <= rtol || rn <= atol || den == 0.0) { ++j; break; }
+    }
+    // x += M^-1 V y,  H(0:j,0:j) y = g
+    for (int q = j - 1; q >= 0; --q) {
+      double acc = gv[q];
+      for (int c = q + 1; c < j; ++c) acc -= H[(size_t)q * m + c] * y[c];
+      y[q] = H[(size_t)q * m + q] != 0.0 ? acc / H[(size_t)q * m + q] : 0.0;
+    }
+    if (j > 0) {
+      CU(cudaMemcpyAsync(dh, y.data(), j * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+      LAUNCH(s, FAM_VEC, k_lincomb, vec_grid(n), VEC_BLOCK, n, (const double *)V, stride, j, (const double *)dh, u);
+      if (prec) launch_prec(s, u, z);
+      LAUNCH(s, FAM_VEC, k_axpy, vec_grid(n), VEC_BLOCK, n, 1.0, (const double *)(prec ? z : u), x);
+      CU(cudaStreamSynchronize(s->stream));  // y is host memory reused by the next cycle
+    }
+  }
+  if (!converged) {  // the loop ended on the estimate or on maxit: the true residual decides
+    if ((rc = launch_matmult<0, double>(s, x, w, nullptr, nullptr))) return rc;
+    LAUNCH(s, FAM_VEC, k_residual_norm2, vec_grid(n), VEC_BLOCK, n, s->b, w, s->partials, s->counter, dh);
+    if ((rc = dots_to_host(1))) return rc;
+    sol.res_diff = std::sqrt(hcol[0]);
+    converged = sol.res_diff / r0 <= rtol || sol.res_diff <= atol;
+  }
+  sol.first_diff = false;
+  sol.lchanged = true;
+  sol.lWm2_diff = false;
+  return converged ? 0 : 22;
+}
+
 // Right-preconditioned BiCGStab on the matrix-free operator; convergence test of MyKSPConverged
 // (src/pprts.F90:4437-4486): ||r||/||r0|| <= rtol or ||r|| <= atol, nonzero initial guess (:4343).
-static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
+static int solve_ediff_krylov(pprts_b200_solver *s, Solution &sol, double rtol, double atol, int maxit) {
   const Grid &g = s->g;
   const long n = (long)s->Nf * g.nlev;
-  int maxit = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 1000;
-  double rtol_d, atol_d;
-  determine_ksp_tolerances(s, rtol_d, atol_d);
-  double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
-  if (sol.first_diff) { rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
   double *x = sol.ediff, *r = s->kr[0], *rh = s->kr[1], *p = s->kr[2], *v = s->kr[3], *sv = s->kr[4], *t = s->kr[5];
   const bool prec = precond_available(s);
   double *ph = prec ? s->kr[6] : p, *sh = prec ? s->kr[7] : sv;
-  if (s->cfg.diff_explicit) return solve_ediff_explicit(s, sol);
-  int rc = need_comm(s);
-  if (rc) return rc;
+  int rc;
+  if (s->fail_next_krylov > 0) {  // fault injection for the tests of the retry path (internal.h)
+    --s->fail_next_krylov;
+    sol.first_diff = false; sol.lchanged = true; sol.lWm2_diff = false;
+    return set_err(22, "***** SOLVER did NOT converge :( -- injected failure");
+  }
   if (s->cfg.krylov_fp32) return solve_ediff_mixed(s, sol, rtol, atol, maxit);
   if ((rc = launch_matmult<0, double>(s, x, r, nullptr, nullptr))) return rc;
   LAUNCH(s, FAM_VEC, k_bicg_init, vec_grid(n), VEC_BLOCK, n, s->b, r, rh, p, v, s->partials, s->counter, s->sc);
@@ -1291,6 +1452,35 @@ static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
   sol.lWm2_diff = false;
   if (!converged) return set_err(22, "***** SOLVER did NOT converge :( -- %d iterations, residual %g", sol.niter_diff, sol.res_diff);
   return 0;
+}
+
+
+// solve (src/pprts.F90:4206-4303): the Krylov solve and what the reference does when it fails -- with
+// -accept_incomplete_solve the iterate is taken as it is; otherwise the initial guess is reset to zero and the system
+// is solved again with GMRES, and only if that fails too the error is raised.
+static int solve_ediff(pprts_b200_solver *s, Solution &sol) {
+  const Grid &g = s->g;
+  const int maxit = s->cfg.maxit_diff > 0 ? s->cfg.maxit_diff : 1000;
+  double rtol_d, atol_d;
+  determine_ksp_tolerances(s, rtol_d, atol_d);
+  double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
+  if (sol.first_diff) { rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
+  int rc = need_comm(s);
+  if (rc) return rc;
+  if (s->cfg.diff_explicit) {  // explicit solvers: src/pprts_explicit.F90:692-696
+    rc = solve_ediff_explicit(s, sol);
+    return (rc == 22 && s->cfg.accept_incomplete_solve) ? 0 : rc;
+  }
+  rc = solve_ediff_krylov(s, sol, rtol, atol, maxit);
+  if (rc != 21 && rc != 22) return rc;
+  if (s->cfg.accept_incomplete_solve) return 0;
+  s->krylov_retries++;
+  CU(cudaMemsetAsync(sol.ediff, 0, (size_t)state_len(g, s->Nf) * sizeof(double), s->stream));  // VecSet(x, zero)
+  rc = solve_ediff_gmres(s, sol, rtol, atol, maxit);
+  if (rc == 22)
+    return set_err(22, "***** SOLVER did NOT converge :( -- %d iterations, residual %g; if you know what you are doing, you "
+                       "can use the option -accept_incomplete_solve to continue", sol.niter_diff, sol.res_diff);
+  return rc;
 }
 
 static int calc_flx_div(pprts_b200_solver *s, Solution &sol) {
@@ -1557,6 +1747,7 @@ extern "C" int pprts_b200_compute_result_device(pprts_b200_solver *s, int uid) {
 }
 extern "C" int pprts_b200_synchronize(pprts_b200_solver *s) {
   if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -1574,6 +1765,7 @@ extern "C" int pprts_b200_accumulate_result(pprts_b200_solver *s, int uid, doubl
 }
 extern "C" int pprts_b200_reset_accumulator(pprts_b200_solver *s) {
   if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
   for (int q = 0; q < 4; ++q) CU(cudaMemsetAsync(s->acc[q], 0, (size_t)s->g.nlev * sizeof(double), s->stream));
   return 0;
 }
@@ -1714,6 +1906,24 @@ extern "C" int pprts_b200_comm_init(pprts_b200_solver *s, int nranks, int rank, 
     CU(cudaMemcpyAsync(h, s->sc + SC_TMP, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     s->glob_ncol = h[0];
+    // determine_1d_layers (src/pprts.F90:708-724): with dz3d the ranks may find different numbers of 1-D layers; the
+    // maximum over the ranks becomes 1-D on all of them, unconstrained_fraction is the global share of 3-D layers
+    int n1d_loc = 0;
+    for (unsigned char f : s->l1d_atm) n1d_loc += f;
+    h[0] = (double)n1d_loc;
+    CU(cudaMemcpyAsync(s->sc + SC_TMP, h, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    NC(g_nccl.AllReduce(s->sc + SC_TMP, s->sc + SC_TMP, 1, NCCL_F64, NCCL_MAX, s->nccl_comm, s->stream));
+    CU(cudaMemcpyAsync(h, s->sc + SC_TMP, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if ((rc = finalize_1d_layers(s, (int)std::lround(h[0]), -1.0))) return rc;
+    int c3 = 0;
+    for (unsigned char f : s->l1d_atm) c3 += !f;
+    h[0] = (double)c3; h[1] = (double)s->Nz_atm;
+    CU(cudaMemcpyAsync(s->sc + SC_TMP, h, 2 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    NC(g_nccl.AllReduce(s->sc + SC_TMP, s->sc + SC_TMP, 2, NCCL_F64, NCCL_SUM, s->nccl_comm, s->stream));
+    CU(cudaMemcpyAsync(h, s->sc + SC_TMP, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->unconstrained_fraction = h[0] / h[1];
   }
   return 0;
 }
@@ -1987,6 +2197,8 @@ int pprts_b200_internal_opp_probe(pprts_b200_solver *s, int mode, const float sa
   build_sym_maps(s->cfg.solver_id, le != 0, ln != 0, sym);
   return lookup_probe(s, mode, 1, nullptr, nullptr, nullptr, nullptr, sample, sym, out);
 }
+extern "C" int pprts_b200_debug_fail_next_krylov(pprts_b200_solver *s, int n) { if (!s) return set_err(1, "null solver"); s->fail_next_krylov = n; return 0; }
+extern "C" long pprts_b200_krylov_retries(pprts_b200_solver *s) { return s ? s->krylov_retries : 0; }
 int pprts_b200_internal_force_angles(pprts_b200_solver *s, double symmetry_phi, double theta) {
   s->symmetry_phi = symmetry_phi; s->theta = theta; s->angles_dirty = true; s->coeffs_dirty = true;
   return 0;

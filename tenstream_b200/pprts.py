@@ -44,7 +44,8 @@ class _Config(C.Structure):
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("precond", C.c_int), ("device", C.c_int),
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
                 ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int),
-                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double), ("geometric_coeffs", C.c_int)]
+                ("max_solution_err", C.c_double), ("max_solution_time", C.c_double), ("geometric_coeffs", C.c_int),
+                ("accept_incomplete_solve", C.c_int), ("gmres_restart", C.c_int)]
 
 
 class _Bands(C.Structure):
@@ -77,6 +78,7 @@ ABI_SYMBOLS = [
     "pprts_b200_solve_at_time", "pprts_b200_need_new_solution", "pprts_b200_get_solution_times",
     "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated", "pprts_b200_polyfit",
     "pprts_b200_find_iter_and_kernelwidth", "pprts_b200_smooth_surface_fluxes", "pprts_b200_smooth_accumulated",
+    "pprts_b200_krylov_retries", "pprts_b200_debug_fail_next_krylov",
 ]
 
 
@@ -134,6 +136,9 @@ def lib():
     L.pprts_b200_kernel_stats.argtypes = [C.c_void_p, C.c_int, c_double_p, c_long_p]
     L.pprts_b200_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.pprts_b200_solve_bands.argtypes = [C.c_void_p, C.POINTER(_Bands)] + [C.c_void_p] * 4 + [c_int_p]
+    L.pprts_b200_krylov_retries.restype = C.c_long
+    L.pprts_b200_krylov_retries.argtypes = [C.c_void_p]
+    L.pprts_b200_debug_fail_next_krylov.argtypes = [C.c_void_p, C.c_int]
     _lib = L
     return L
 
@@ -233,6 +238,13 @@ class Solver:
     def kernel_launches(self):
         return int(lib().pprts_b200_kernel_launches(self._h))
 
+    def krylov_retries(self):
+        """how often a failed diffuse Krylov solve was retried with GMRES (src/pprts.F90:4277-4296)"""
+        return int(lib().pprts_b200_krylov_retries(self._h))
+
+    def debug_fail_next_krylov(self, n=1):
+        _chk(lib().pprts_b200_debug_fail_next_krylov(self._h, int(n)), "debug_fail_next_krylov")
+
     def enable_kernel_timing(self, on=True):
         _chk(lib().pprts_b200_enable_kernel_timing(self._h, int(on)), "enable_kernel_timing")
 
@@ -300,7 +312,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
                keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
                max_solution_time=None, geometric_coeffs=False, top_bottom_faces_planar=True,
-               top_bottom_planes_parallel=True) -> Solver:
+               top_bottom_planes_parallel=True, accept_incomplete_solve=False, gmres_restart=0) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -337,6 +349,8 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.precond, cfg.device, cfg.keep_solutions = int(precond), int(device), int(keep_solutions)
     cfg.diff_explicit = int(diff_explicit)
     cfg.krylov_fp32 = int(krylov_fp32)
+    cfg.accept_incomplete_solve = int(accept_incomplete_solve)   # -accept_incomplete_solve
+    cfg.gmres_restart = int(gmres_restart)
     cfg.collapseindex = int(collapseindex) if collapseindex is not None else 1
     if max_solution_err is not None:      # -max_solution_err / -max_solution_time (src/tenstream_options.F90:90-96)
         cfg.max_solution_err = float(max_solution_err)

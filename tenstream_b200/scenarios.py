@@ -91,3 +91,49 @@ def spectral_bands(base, n_sw=112, n_lw=140):
     for b in range(n_lw):
         bands.append(dict(kind="thermal", uid=500 + b + 1, scale=10.0 ** (-3 + 4 * u[b]), weight=1.0 / n_lw))
     return bands
+
+
+def config_case(name):
+    """BASELINE.json configs as (scenario, bands): "c1" = configs[0] (box cloud 32x32x40, one solar band), "c2" =
+    configs[1] (cloud field 256x256x80, solar + thermal).  The golden generator, the GPU tests and bench.py share it."""
+    if name == "c1":
+        sc = box_cloud()
+        bands = [dict(name="solar", lsolar=True, albedo=sc["albedo"], kabs=sc["kabs"], ksca=sc["ksca"], g=sc["g"],
+                      planck=None, planck_srfc=None, edirTOA=sc["edirTOA"], uid=1)]
+    elif name == "c2":
+        sc = cloud_field()
+        bands = [dict(name="solar", lsolar=True, albedo=sc["albedo"], kabs=sc["kabs"], ksca=sc["ksca"], g=sc["g"],
+                      planck=None, planck_srfc=None, edirTOA=sc["edirTOA"], uid=1),
+                 dict(name="thermal", lsolar=False, albedo=sc["albedo_th"], kabs=sc["kabs_th"], ksca=sc["ksca_th"],
+                      g=sc["g_th"], planck=sc["planck"], planck_srfc=sc["planck_srfc"], edirTOA=0.0, uid=501)]
+    else:
+        raise KeyError(name)
+    return sc, bands
+
+
+GOLDEN_FIELDS = ("edn", "eup", "abso", "edir")
+
+
+def golden_errors(golden, case, band, fields, floor_frac=1e-6):
+    """Largest relative deviation of (edn, eup, abso, edir) from the stored columns / slices / mean profiles of
+    tests/golden/config_goldens.npz (tests/golden/make_config_goldens.py), per field; entries below floor_frac of the
+    field maximum are not compared (BASELINE.md parity gate)."""
+    cols, levels = golden[f"{case}/cols"], golden[f"{case}/levels"]
+    out = {}
+    for nm, a in zip(GOLDEN_FIELDS, fields):
+        if a is None or (nm == "edir" and band != "solar"):
+            continue
+        a = np.asarray(a)
+        nz = a.shape[0]
+        scale = float(golden[f"{case}/{band}/{nm}_max"])
+        worst = 0.0
+        st = 2 if a.shape[1] > 64 else 1
+        parts = [(a[:, cols[:, 0], cols[:, 1]], golden[f"{case}/{band}/{nm}_cols"]),
+                 (np.stack([a[min(int(k), nz - 1)][::st, ::st] for k in levels]), golden[f"{case}/{band}/{nm}_rows"]),
+                 (a.reshape(nz, -1).mean(axis=1), golden[f"{case}/{band}/{nm}_mean"])]
+        for got, want in parts:
+            m = np.abs(want) > floor_frac * scale
+            if m.any():
+                worst = max(worst, float((np.abs(got - want)[m] / np.abs(want)[m]).max()))
+        out[nm] = worst
+    return out

@@ -194,6 +194,92 @@ def test_1d_layers_and_topography(P, gpu_lut, oracle_lut):
     check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-6)  # abso = absorbed - emitted cancels
 
 
+@pytest.mark.parametrize("krylov_fp32", [False, True])
+def test_lone_1d_bottom_layer(P, gpu_lut, oracle_lut, krylov_fp32):
+    """Only the LOWEST layer is thicker than twostr_ratio * dx: determine_1d_layers (src/pprts.F90:667-719) keeps it 1-D on
+    its own and, through the N1dlayers_max fill, makes the top layer 1-D as well: l1d = [T, F, ..., F, T]."""
+    from oracle import binding as ob
+    rng = np.random.default_rng(21)
+    Nz, Nx, Ny = 8, 6, 5
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    dz = np.array([100., 100., 100., 100., 100., 100., 100., 500.])
+    sd = P.sundir_from_angles(200., 35.)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz)
+    assert list(o.l1d()) == [1, 0, 0, 0, 0, 0, 0, 1]
+    o.destroy()
+    out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., dz, 200., 35., 0.25, kabs, ksca, g)
+    assert relerr(*out["edir"], 1e-9) < 1e-9
+    check_fluxes(out, 1e-7)
+    T = np.linspace(220, 290, Nz + 1)[:, None, None] * np.ones((Nz + 1, Nx, Ny))
+    out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., dz, 200., 35., 0.25, kabs * 20, ksca, g, solar=False,
+                   planck=5.67e-8 * T ** 4 / np.pi)
+    check_fluxes(dict(out, gpu=out["gpu"][:3], oracle=out["oracle"][:3]), 1e-6)
+    # default tolerances: atol carries unconstrained_fraction = 6/8, and the mixed-precision solver takes the same path
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, krylov_fp32=krylov_fp32)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, diff_solver=1)
+    P.set_optical_properties(s, 0.25, kabs, ksca, g)
+    o.set_optical_properties(0.25, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000.)
+    assert o.solve(False, True, 1000.) == 0
+    for a, b in zip(P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b, 1e-3) < 2e-3      # both stop at the same (loose) default tolerance
+    P.destroy_pprts(s); o.destroy()
+
+
+@pytest.mark.parametrize("krylov_fp32", [False, True])
+@pytest.mark.parametrize("solar", [True, False])
+def test_gmres_retry_after_failed_solve(P, gpu_lut, oracle_lut, krylov_fp32, solar):
+    """solve (src/pprts.F90:4270-4302): a KSP solve that did not converge is repeated from a zero initial guess with
+    GMRES; the result must be the converged one.  The failure of the first solve is injected."""
+    from oracle import binding as ob
+    rng = np.random.default_rng(33)
+    Nz, Nx, Ny = 8, 6, 7
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    sd = P.sundir_from_angles(130., 50.)
+    dz = np.full(Nz, 60.)
+    T = np.linspace(220, 290, Nz + 1)[:, None, None] * np.ones((Nz + 1, Nx, Ny))
+    planck = None if solar else 5.67e-8 * T ** 4 / np.pi
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, coeff_fp32=False, rtol=1e-10, atol=1e-30,
+                     krylov_fp32=krylov_fp32, gmres_restart=12)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, rtol=1e-10, atol=1e-30, diff_solver=1, maxit_diff=5000)
+    P.set_optical_properties(s, 0.2, kabs, ksca, g, planck=planck)
+    o.set_optical_properties(0.2, kabs, ksca, g, planck=planck)
+    s.debug_fail_next_krylov(1)
+    P.solve_pprts(s, not solar, solar, 1000. if solar else 0.)
+    assert s.krylov_retries() == 1
+    assert o.solve(not solar, solar, 1000. if solar else 0.) == 0
+    nfo = s.info()
+    assert nfo["niter_diff"] > 12          # more than one GMRES cycle ran
+    for name, a, b in zip(["edn", "eup", "abso"], P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b) < (1e-5 if name == "abso" and not solar else 1e-7), (name, relerr(a, b), nfo)
+    # a second solve (no injected failure) does not retry
+    P.solve_pprts(s, not solar, solar, 1000. if solar else 0.)
+    assert s.krylov_retries() == 1
+    P.destroy_pprts(s); o.destroy()
+
+
+def test_accept_incomplete_solve(P, gpu_lut):
+    """-accept_incomplete_solve (src/pprts.F90:4270-4275, src/pprts_explicit.F90:134-136, :213-217)"""
+    rng = np.random.default_rng(34)
+    Nz, Nx, Ny = 8, 6, 6
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    sd = P.sundir_from_angles(30., 40.)
+    for accept in (False, True):
+        s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=np.full(Nz, 60.), lut=gpu_lut, rtol=1e-12, atol=1e-30,
+                         maxit_diff=3, accept_incomplete_solve=accept)
+        P.set_optical_properties(s, 0.2, kabs, ksca, g)
+        if accept:
+            P.solve_pprts(s, False, True, 1000.)       # three iterations of BiCGStab, result taken as it is
+            assert s.krylov_retries() == 0
+            edn, eup, abso, edir = P.pprts_get_result(s)
+            assert np.isfinite(edn).all() and edn.max() > 0
+        else:
+            with pytest.raises(P.PprtsError, match="did NOT converge"):   # BiCGStab and the GMRES retry both hit maxit
+                P.solve_pprts(s, False, True, 1000.)
+            assert s.krylov_retries() == 1
+        P.destroy_pprts(s)
+
+
 def test_fp32_coefficient_storage(P, gpu_lut, oracle_lut):
     rng = np.random.default_rng(9)
     Nz, Nx, Ny = 8, 6, 6

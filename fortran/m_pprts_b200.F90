@@ -46,7 +46,7 @@ module m_pprts_b200
       & diff_explicit, krylov_fp32, collapseindex
     real(c_double) :: max_solution_err, max_solution_time
     integer(c_int) :: geometric_coeffs
-    integer(c_int) :: accept_incomplete_solve, gmres_restart
+    integer(c_int) :: accept_incomplete_solve, gmres_restart, max_cached_solutions
   end type
 
   interface

@@ -127,6 +127,9 @@ typedef struct {
    * only then reported (error 22). */
   int accept_incomplete_solve;
   int gmres_restart;   /* restart length of that GMRES, <= 0: 30 (PETSc's default) */
+  /* keep_solutions = 1 only: at most this many solutions stay cached (least recently used dropped first, never the
+   * uid being solved or uid - 1); <= 0: unlimited, like solver%solutions(-1000:1000) */
+  int max_cached_solutions;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);
@@ -167,6 +170,16 @@ int pprts_b200_stage_optical_properties(pprts_b200_solver *solver, int slot, dou
                                         const double *ksca, const double *g, const double *planck,
                                         const double *planck_srfc, const double *albedo_2d);
 int pprts_b200_set_optical_properties_staged(pprts_b200_solver *solver, int slot, int ldelta_scaling);
+/* Overlapped host transfers for a caller's own band loop (what pprts_b200_solve_bands does internally):
+ * stage_optical_properties_async only ENQUEUES the upload of the next band on a copy stream (the host arrays must stay
+ * valid, and should be page-locked, until set_optical_properties_staged(slot) has consumed them); get_result_async
+ * returns once the result is on its way to the host arrays, which are complete after wait_results. */
+int pprts_b200_stage_optical_properties_async(pprts_b200_solver *solver, int slot, double albedo, const double *kabs,
+                                              const double *ksca, const double *g, const double *planck,
+                                              const double *planck_srfc, const double *albedo_2d);
+int pprts_b200_get_result_async(pprts_b200_solver *solver, int uid, double *edn, double *eup, double *abso,
+                                double *edir);
+int pprts_b200_wait_results(pprts_b200_solver *solver);
 int pprts_b200_compute_result_device(pprts_b200_solver *solver, int uid);
 int pprts_b200_synchronize(pprts_b200_solver *solver);
 

@@ -401,6 +401,169 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
   for (int s = 0; s < Nd; ++s) cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1[s] - sum2[s];  // src/pprts.F90:5315
 }
 
+// ---- cooperative per-tile formulation ---------------------------------------------------------------------------
+// k_lookup above is bound by its gathers and its stores, not by HBM (ncu, profiles/r1_others.txt: 1.7 TB/s algorithmic,
+// write traffic 1.32x algorithmic): every thread walks ITS corner rows with 4-byte loads -- a warp-wide load touches 32
+// different table rows -- and the plane stores of a thread reach DRAM as partial sectors.  Here one CTA of four warps owns
+// one coefficient tile (PB_TILE cells):
+//   plan    : lane l of a warp computes search + corner offsets + weights of the warp's cell l (registers);
+//   gather  : the warp then walks its 32 cells ONE AT A TIME -- the plan of the cell travels by shuffle -- and reads
+//             every corner row of the diffuse table as one coalesced 16-byte-per-lane request (a 3_10 row is 400
+//             contiguous bytes = 25 lanes), the two (phi,theta)-contracted direct rows as 8-byte requests; each lane
+//             accumulates its slice of the row in fp64 in the reference's corner order (same fma chain as k_lookup:
+//             bit-identical results);
+//   store   : the warp's 32 x ncoef block sits in shared memory (odd row stride: conflict-free both ways) and leaves
+//             plane by plane -- lane = cell -- as full 128-byte lines; the divergence factors 1 - sum_dst and the
+//             widening class of the tile fall out of the same pass.
+// Coefficient rows longer than 128 floats (3_24: 576) are processed in chunks of 128.
+template <class L>
+struct LookupCfg {
+  static constexpr int NFF = L::Nf * L::Nf, NDD = L::Nd * L::Nd, NDF = L::Nd * L::Nf, NDIR = NDD + NDF;
+  static constexpr int CHUNK = 128;                                   // floats of a diffuse row per pass (32 lanes x float4)
+  static constexpr int NCHUNK = (NFF + CHUNK - 1) / CHUNK;
+  static constexpr int DIR_PER_LANE = (NDIR + 31) / 32;
+  static constexpr int STRIDE = ((NDIR > CHUNK ? NDIR : CHUNK) | 1);  // odd: rows of consecutive cells hit different banks
+  static_assert(NFF % 4 == 0, "diffuse rows are read as float4");
+};
+template <class L, class CT>
+__global__ void __launch_bounds__(PB_TILE)
+k_lookup_tile(Grid g, LutDev lut, SymMaps sym, int lsolar, long tile0, long c_begin, long c_end,
+              const double *__restrict__ kabs, const double *__restrict__ ksca, const double *__restrict__ gg,
+              const double *__restrict__ dz, CT *__restrict__ d2d, CT *__restrict__ d2f, CT *__restrict__ f2f,
+              double *__restrict__ cdiv_dir, double *__restrict__ cdiv_diff, unsigned int *__restrict__ tile_class) {
+  using K = LookupCfg<L>;
+  constexpr int Nd = L::Nd, Nf = L::Nf;
+  extern __shared__ __align__(16) unsigned char lk_smem[];
+  __shared__ short s_sym[K::NDIR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CT *stage = reinterpret_cast<CT *>(lk_smem) + (size_t)warp * 32 * K::STRIDE;
+  for (int n = threadIdx.x; n < K::NDIR; n += blockDim.x) s_sym[n] = n < K::NDD ? sym.d2d[n] : sym.d2f[n - K::NDD];
+  __syncthreads();
+  const long tile = tile0 + blockIdx.x;
+  const long cw = tile * PB_TILE + warp * 32;  // first cell of this warp
+  const long c = cw + lane;
+  const bool valid = c >= c_begin && c < c_end;
+  // ---- plan of my cell
+  int p_nc = 0;
+  int p_ofs[16];
+  double p_w[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) { p_ofs[b] = 0; p_w[b] = 0.0; }
+  if (valid) {
+    float sample[4];
+    lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
+    InterpPlan p;
+    make_plan(lut, sample, p);
+    p_nc = p.ncorner;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) if (b < p.ncorner) { p_ofs[b] = (int)p.ofs[b]; p_w[b] = p.w[b]; }
+  }
+  const unsigned int anyvalid = __ballot_sync(0xffffffffu, valid);
+  if (anyvalid == 0u) return;  // warp-uniform; no block-wide barrier follows
+  const long tb_ff = tile * (long)(K::NFF * PB_TILE) + warp * 32 + lane;  // + n*PB_TILE: plane n, my cell
+  int wclass = 0;
+  double colsum[Nf];
+#pragma unroll
+  for (int s = 0; s < Nf; ++s) colsum[s] = 0.0;
+  // ---- diff2diff, CHUNK floats of every row at a time
+#pragma unroll
+  for (int ch = 0; ch < K::NCHUNK; ++ch) {
+    constexpr int dummy = 0; (void)dummy;
+    const int n0 = ch * K::CHUNK;
+    const int nthis = (K::NFF - n0 < K::CHUNK) ? K::NFF - n0 : K::CHUNK;  // floats in this chunk
+    const bool lane_on = 4 * lane < nthis;
+    for (int q = 0; q < 32; ++q) {
+      const int nc = __shfl_sync(0xffffffffu, p_nc, q);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        if (b < nc) {  // warp-uniform
+          const int ofs = __shfl_sync(0xffffffffu, p_ofs[b], q);
+          const double w = __shfl_sync(0xffffffffu, p_w[b], q);
+          if (lane_on) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(lut.Sdiff + (long)ofs * K::NFF + n0) + lane);
+            a0 = fma(w, widen_any(v.x), a0); a1 = fma(w, widen_any(v.y), a1);
+            a2 = fma(w, widen_any(v.z), a2); a3 = fma(w, widen_any(v.w), a3);
+          }
+        }
+      }
+      if (lane_on) {
+        CT *row = stage + q * K::STRIDE + 4 * lane;
+        row[0] = (CT)a0; row[1] = (CT)a1; row[2] = (CT)a2; row[3] = (CT)a3;
+      }
+    }
+    __syncwarp();
+    if (valid) {  // lane = cell: plane stores, 128 contiguous bytes per warp and plane
+      const CT *row = stage + lane * K::STRIDE;
+#pragma unroll
+      for (int m = 0; m < K::CHUNK; ++m) {
+        const int n = n0 + m;
+        if (n < K::NFF) {
+          const CT st = row[m];
+          if (sizeof(CT) == 4) wclass = max(wclass, widen_class((float)st));
+          f2f[tb_ff + (long)n * PB_TILE] = st;
+          colsum[n % Nf] += (double)st;  // ascending dst for every src, as calc_flx_div sums (src/pprts.F90:5343)
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (valid) {
+#pragma unroll
+    for (int s = 0; s < Nf; ++s) cdiv_diff[(long)s * g.ncp + c] = 1.0 - colsum[s];
+  }
+  if (sizeof(CT) == 4) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wclass = max(wclass, __shfl_xor_sync(0xffffffffu, wclass, o));
+    if (lane == 0 && wclass > 0) atomicMax(tile_class + tile, (unsigned int)wclass);
+  }
+  if (!lsolar) return;
+  // ---- dir2dir | dir2diff from the (phi,theta)-contracted fp64 tables: value n of the concatenated row per lane slot
+  for (int q = 0; q < 32; ++q) {
+    const int nc = __shfl_sync(0xffffffffu, p_nc, q);
+    double acc[K::DIR_PER_LANE];
+    int src[K::DIR_PER_LANE];
+#pragma unroll
+    for (int r = 0; r < K::DIR_PER_LANE; ++r) {
+      acc[r] = 0.0;
+      const int n = lane + 32 * r;
+      src[r] = n < K::NDIR ? (int)s_sym[n] : 0;
+    }
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      if (b < nc) {
+        const int ofs = __shfl_sync(0xffffffffu, p_ofs[b], q);
+        const double w = __shfl_sync(0xffffffffu, p_w[b], q);
+#pragma unroll
+        for (int r = 0; r < K::DIR_PER_LANE; ++r) {
+          const int n = lane + 32 * r;
+          if (n < K::NDD) acc[r] = fma(w, __ldg(lut.Tdir4 + (long)ofs * K::NDD + src[r]), acc[r]);
+          else if (n < K::NDIR) acc[r] = fma(w, __ldg(lut.Sdir4 + (long)ofs * K::NDF + src[r]), acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < K::DIR_PER_LANE; ++r) {
+      const int n = lane + 32 * r;
+      if (n < K::NDIR) stage[q * K::STRIDE + n] = (CT)acc[r];
+    }
+  }
+  __syncwarp();
+  if (valid) {
+    const CT *row = stage + lane * K::STRIDE;
+    const long tb_dd = tile * (long)(K::NDD * PB_TILE) + warp * 32 + lane, tb_df = tile * (long)(K::NDF * PB_TILE) + warp * 32 + lane;
+    double sum1[Nd], sum2[Nd];
+#pragma unroll
+    for (int s = 0; s < Nd; ++s) { sum1[s] = 0.0; sum2[s] = 0.0; }
+#pragma unroll
+    for (int n = 0; n < K::NDD; ++n) { const CT st = row[n]; d2d[tb_dd + (long)n * PB_TILE] = st; sum1[n % Nd] += (double)st; }
+#pragma unroll
+    for (int n = 0; n < K::NDF; ++n) { const CT st = row[K::NDD + n]; d2f[tb_df + (long)n * PB_TILE] = st; sum2[n % Nd] += (double)st; }
+#pragma unroll
+    for (int s = 0; s < Nd; ++s) cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1[s] - sum2[s];  // src/pprts.F90:5315
+  }
+}
+
 // -pprts_geometric_coeffs (src/pprts.F90:3046-3053, :3130-3149, :3272-3273, :3324-3351): after k_lookup has stored the
 // LUT's dir2dir (T_LUT) and dir2diff (S_LUT), the direct-beam coefficients of every 3-D cell are replaced by the
 // analytic ones of its (sloped) geometry and dir2diff is rescaled per source stream so that the cell absorbs exactly

@@ -187,6 +187,7 @@ struct Solution {  // t_state_container (src/pprts_base.F90:137-169)
   bool lset = false, lsolar_rad = false, lthermal_rad = false, lchanged = true, lWm2_dir = true, lWm2_diff = true;
   double *edir = nullptr, *ediff = nullptr, *abso = nullptr;
   bool first_dir = true, first_diff = true;  // residual_history(1) < 0
+  long last_use = 0;  // max_cached_solutions: the least recently used stored solution is dropped first
   int niter_dir = 0, niter_diff = 0;
   double res_dir = 0, res_diff = 0;
   // error-growth tracking (src/pprts_base.F90:161-162): times of the last solves, inf-norm of the change of abso
@@ -200,6 +201,7 @@ struct Staged {
   double albedo = 0;
   double *kabs = nullptr, *ksca = nullptr, *g = nullptr, *planck = nullptr, *Bsrfc = nullptr, *albedo2d = nullptr;
   bool have_planck = false, have_Bsrfc = false, have_albedo2d = false;
+  cudaEvent_t ready = nullptr;  // stage_optical_properties_async: recorded on the copy stream behind the slot's uploads
 };
 
 struct pprts_b200_solver {
@@ -272,6 +274,10 @@ struct pprts_b200_solver {
   double glob_ncol = 0;  // global number of columns (KSP tolerances use the global domain, pprts_base.F90:1128-1131)
   double *hs[2] = {nullptr, nullptr}, *hr[2] = {nullptr, nullptr};  // send / receive staging, [0] x faces, [1] y faces
   long halo_exchanges = 0;
+  double *egress[4] = {nullptr, nullptr, nullptr, nullptr};  // get_result_async: results in the caller's layout
+  cudaEvent_t egress_ready = nullptr, egress_done = nullptr;
+  bool egress_pending = false;
+  long use_clock = 0;
   int fail_next_krylov = 0;  // test hook: the next n primary Krylov solves report non-convergence
   long krylov_retries = 0;
   int num_sms = 148;
@@ -742,6 +748,10 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->vh_atm);
+  for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
+  if (s->egress_ready) cudaEventDestroy(s->egress_ready);
+  if (s->egress_done) cudaEventDestroy(s->egress_done);
+  for (auto &kv : s->staged) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
   cudaFree(s->bld_iface); cudaFree(s->bld_albedo); cudaFree(s->bld_planck); cudaFree(s->bld_out);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
   cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
@@ -860,8 +870,46 @@ extern "C" int pprts_b200_set_optical_properties_staged(pprts_b200_solver *s, in
   auto it = s->staged.find(slot);
   if (it == s->staged.end()) return set_err(1, "no optical properties staged in slot %d", slot);
   Staged &st = it->second;
+  CU(cudaSetDevice(s->device));
+  if (st.ready) CU(cudaStreamWaitEvent(s->stream, st.ready, 0));  // uploaded by stage_optical_properties_async
   return set_optprop_impl(s, st.albedo, st.kabs, st.ksca, st.g, st.have_planck ? st.planck : nullptr,
                           st.have_Bsrfc ? st.Bsrfc : nullptr, st.have_albedo2d ? st.albedo2d : nullptr, ldelta, true);
+}
+static int ensure_copy_stream(pprts_b200_solver *s) {
+  if (s->copy_stream) return 0;
+  CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (int q = 0; q < 2; ++q) CU(cudaEventCreateWithFlags(&s->band_uploaded[q], cudaEventDisableTiming));
+  return 0;
+}
+// As stage_optical_properties, but the upload is only ENQUEUED (copy stream): it overlaps whatever the solver's stream
+// is doing -- the solve of the previous band in a caller's band loop.  The host arrays must stay valid (and should be
+// page-locked) until the slot has been consumed by set_optical_properties_staged, which waits for the upload.
+extern "C" int pprts_b200_stage_optical_properties_async(pprts_b200_solver *s, int slot, double albedo, const double *kabs,
+                                                         const double *ksca, const double *g, const double *planck,
+                                                         const double *planck_srfc, const double *albedo_2d) {
+  if (!s) return set_err(1, "null solver");
+  if (!kabs || !ksca || !g) return set_err(2, "stage_optical_properties_async: kabs, ksca and g are required");
+  CU(cudaSetDevice(s->device));
+  int rc = ensure_copy_stream(s);
+  if (rc) return rc;
+  const Grid &gr = s->g;
+  Staged &st = s->staged[slot];
+  st.albedo = albedo;
+  auto up = [&](double **dst, const double *src, size_t n) -> int {
+    if (!*dst) CU(cudaMalloc((void **)dst, n * sizeof(double)));
+    CU(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));
+    return 0;
+  };
+  if ((rc = up(&st.kabs, kabs, s->ncell_atm)) || (rc = up(&st.ksca, ksca, s->ncell_atm)) || (rc = up(&st.g, g, s->ncell_atm))) return rc;
+  st.have_planck = planck != nullptr;
+  if (planck && (rc = up(&st.planck, planck, s->nlev_atm))) return rc;
+  st.have_Bsrfc = planck_srfc != nullptr;
+  if (planck_srfc && (rc = up(&st.Bsrfc, planck_srfc, gr.ncol))) return rc;
+  st.have_albedo2d = albedo_2d != nullptr;
+  if (albedo_2d && (rc = up(&st.albedo2d, albedo_2d, gr.ncol))) return rc;
+  if (!st.ready) CU(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+  CU(cudaEventRecord(st.ready, s->copy_stream));
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -884,6 +932,31 @@ static bool launch_geometric(pprts_b200_solver *s, long n3d, double sx, double s
     return false;
   }
 }
+
+template <class L, class CT>
+static bool launch_lookup_tile(pprts_b200_solver *s, bool lsolar) {
+  using K = LookupCfg<L>;
+  const Grid &g = s->g;
+  constexpr size_t smem = (size_t)4 * 32 * K::STRIDE * sizeof(CT);
+  static bool attr_set[64] = {false};
+  auto kern = k_lookup_tile<L, CT>;
+  const int dev = s->device & 63;
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    attr_set[dev] = true;
+  }
+  const long c_begin = (long)s->n1d * g.ncol, c_end = (long)g.kb1d * g.ncol;
+  const long tile0 = c_begin / PB_TILE, ntile = (c_end - 1) / PB_TILE - tile0 + 1;
+  cudaEvent_t ea = nullptr, eb = nullptr;
+  if (s->timing) { ea = get_event(s); eb = get_event(s); cudaEventRecord(ea, s->stream); }
+  kern<<<(unsigned int)ntile, PB_TILE, smem, s->stream>>>(g, s->lutdev, s->sym, (int)lsolar, tile0, c_begin, c_end, s->kabs, s->ksca,
+                                                        s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f, s->cdiv_dir,
+                                                        s->cdiv_diff, s->tile_class);
+  if (s->timing) { cudaEventRecord(eb, s->stream); s->evs.push_back({FAM_LOOKUP, ea, eb}); }
+  s->launches++;
+  s->fam_launch[FAM_LOOKUP]++;
+  return true;
+}
 static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
   if (!s->coeffs_dirty && (!lsolar || s->coeffs_have_dir)) return 0;
   const Grid &g = s->g;
@@ -891,9 +964,16 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
   const long n3d = (long)(g.kb1d - s->n1d) * g.ncol;
   if (n3d > 0) {
     CU(cudaMemsetAsync(s->tile_class, 0, (size_t)(g.ncp / PB_TILE) * sizeof(unsigned int), s->stream));
-    DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_lookup<L, CT>), nblk(n3d, 128), 128, g, s->lutdev, s->sym, (int)lsolar,
-                           s->n1d, s->kabs, s->ksca, s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f,
-                           s->cdiv_dir, s->cdiv_diff, (unsigned char *)s->tile_class));
+    static const bool old_lookup = getenv("PPRTS_B200_LOOKUP_PER_THREAD") != nullptr;  // the round-1 kernel, for comparison
+    if (old_lookup)
+      DISPATCH_LC(s, LAUNCH(s, FAM_LOOKUP, (k_lookup<L, CT>), nblk(n3d, 128), 128, g, s->lutdev, s->sym, (int)lsolar,
+                             s->n1d, s->kabs, s->ksca, s->gg, s->dz, (CT *)s->d2d, (CT *)s->d2f, (CT *)s->f2f,
+                             s->cdiv_dir, s->cdiv_diff, (unsigned char *)s->tile_class));
+    else {
+      bool ok = true;
+      DISPATCH_LC(s, ok = (launch_lookup_tile<L, CT>(s, lsolar)));
+      if (!ok) return set_err(100, "k_lookup_tile: cannot reserve its shared-memory stage");
+    }
   }
   if (s->cfg.geometric_coeffs && lsolar && n3d > 0) {  // src/pprts.F90:3142-3149, :3324-3351
     const double d2r = PB_PI / 180.0;  // sun%sundir = spherical_2_cartesian(phi, theta) (:1148)
@@ -961,6 +1041,15 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   determine_ksp_tolerances(s, rtol_d, atol_d);
   double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
   if (sol.first_dir) { maxiter += 2; rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
+  // The reference's test ||x_n - x_{n-1}|| < atol or < rtol * first (:186-196) is written for its Gauss-Seidel sweep,
+  // whose change per sweep IS its error (the sweep solves everything but the periodic wrap exactly).  A lagged pass
+  // moves information one column per pass, so its change only says how much arrived in this pass, not how much is still
+  // on its way: stopping at the same numbers left edir 8e-5 (C1) away from the reference's result at the same
+  // tolerances (tests/test_gpu_config_goldens.py).  The passes therefore run until the change is 1e-4 of what the
+  // reference asks for -- in practice until the recurrence has ended (it is finite: the beam leaves the domain) -- which
+  // puts edir within 1e-6 of the reference at any tolerance for ~15 % more passes.
+  const double lag = 1e-4;
+  rtol *= lag; atol *= lag;
   int adiv = 1;
   DISPATCH_L(s, adiv = L::dirtop_adiv);
   const double fac = edirTOA * g.dx * g.dy / (double)adiv;
@@ -1500,7 +1589,23 @@ static int calc_flx_div(pprts_b200_solver *s, Solution &sol) {
 static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool lthermal, Solution **out) {
   const Grid &g = s->g;
   const int key = s->cfg.keep_solutions ? uid : 0;
+  // max_cached_solutions: a band loop over hundreds of g-points on a large domain cannot keep every solution in HBM
+  // (3 GB each at 512x512x100); beyond the cap the least recently used ones are dropped -- never `uid` itself or
+  // uid - 1, the warm start of a first solve.  (The reference's answer to the same problem is bf16 compression of the
+  // stored solutions, -pprts_compress_solutions, src/pprts_base.F90:411-502.)
+  if (s->cfg.keep_solutions && s->cfg.max_cached_solutions > 0 && !s->solutions.count(key)) {
+    while ((int)s->solutions.size() >= s->cfg.max_cached_solutions) {
+      int victim = 0; long oldest = -1; bool found = false;
+      for (auto &kv : s->solutions)
+        if (kv.first != uid && kv.first != uid - 1 && (!found || kv.second.last_use < oldest)) { victim = kv.first; oldest = kv.second.last_use; found = true; }
+      if (!found) break;
+      CU(cudaStreamSynchronize(s->stream));
+      free_solution(s->solutions[victim]);
+      s->solutions.erase(victim);
+    }
+  }
   Solution &sol = s->solutions[key];
+  sol.last_use = ++s->use_clock;
   auto prepare = [&]() -> int {  // prepare_solution (src/pprts_base.F90:297-344)
     if (!sol.edir) { DA(sol.edir, (size_t)state_len(g, s->Nd)); DA(sol.ediff, (size_t)state_len(g, s->Nf)); DA(sol.abso, g.ncell); }
     else {
@@ -1758,6 +1863,47 @@ extern "C" int pprts_b200_get_result(pprts_b200_solver *s, int uid, double *edn,
   if (rc) return rc;
   return download_fields(s, s->res, edn, eup, abso, edir);
 }
+// pprts_get_result whose device->host copies run on the copy stream: the call returns as soon as the result reduction
+// and the layout conversion are enqueued, the solver's stream is free for the next band while the four fields travel.
+// The host arrays (page-locked for the copy to be asynchronous) are complete after pprts_b200_wait_results.
+extern "C" int pprts_b200_get_result_async(pprts_b200_solver *s, int uid, double *edn, double *eup, double *abso, double *edir) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  int rc = ensure_copy_stream(s);
+  if (rc) return rc;
+  const Grid &g = s->g;
+  if (!s->egress[0]) {
+    for (int q = 0; q < 4; ++q) DA(s->egress[q], (size_t)g.nlev);
+    CU(cudaEventCreateWithFlags(&s->egress_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->egress_done, cudaEventDisableTiming));
+  }
+  if ((rc = compute_result(s, uid, false, 1.0))) return rc;
+  if (s->egress_pending) CU(cudaStreamWaitEvent(s->stream, s->egress_done, 0));  // the previous copies still read egress
+  double *hosts[4] = {edn, eup, edir, abso};
+  for (int q = 0; q < 4; ++q) {
+    if (!hosts[q]) continue;
+    const int nz = q == 3 ? g.Nz : g.Nz + 1;
+    dim3 grid((g.Nx + 31) / 32, (nz + 31) / 32, g.Ny), block(32, 8);
+    LAUNCH(s, FAM_IO, k_kji_to_zxy<double>, grid, block, nz, g.Nx, g.Ny, s->res[q], s->egress[q], 1.0);
+  }
+  CU(cudaEventRecord(s->egress_ready, s->stream));
+  CU(cudaStreamWaitEvent(s->copy_stream, s->egress_ready, 0));
+  for (int q = 0; q < 4; ++q) {
+    if (!hosts[q]) continue;
+    const int nz = q == 3 ? g.Nz : g.Nz + 1;
+    CU(cudaMemcpyAsync(hosts[q], s->egress[q], (size_t)nz * g.ncol * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+  }
+  CU(cudaEventRecord(s->egress_done, s->copy_stream));
+  s->egress_pending = true;
+  return 0;
+}
+extern "C" int pprts_b200_wait_results(pprts_b200_solver *s) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
+  s->egress_pending = false;
+  return 0;
+}
 extern "C" int pprts_b200_accumulate_result(pprts_b200_solver *s, int uid, double weight) {
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));
@@ -1810,11 +1956,8 @@ extern "C" int pprts_b200_solve_bands(pprts_b200_solver *s, const pprts_b200_ban
     return set_err(12, "you asked to compute thermal radiation but did not provide planck emissions in set_optical_properties");
   if (b->uid0 < -1000 || b->uid0 + std::max(0, b->nbands - 1) > 1000) return set_err(11, "solution uids %d.. out of range", b->uid0);
   CU(cudaSetDevice(s->device));
-  if (!s->copy_stream) {
-    CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < 2; ++q) CU(cudaEventCreateWithFlags(&s->band_uploaded[q], cudaEventDisableTiming));
-  }
-  int rc;
+  int rc = ensure_copy_stream(s);
+  if (rc) return rc;
   if (!b->accumulate_only && (rc = pprts_b200_reset_accumulator(s))) return rc;
   // Adaptive spectral integration (rrtmg/rrtmg/pprts_rrtmg.F90:1001, src/adaptive_spectral_integration.F90:38): with a
   // time, a band whose stored solution is still within -max_solution_err is not solved again -- its stored result

@@ -45,7 +45,7 @@ class _Config(C.Structure):
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
                 ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int),
                 ("max_solution_err", C.c_double), ("max_solution_time", C.c_double), ("geometric_coeffs", C.c_int),
-                ("accept_incomplete_solve", C.c_int), ("gmres_restart", C.c_int)]
+                ("accept_incomplete_solve", C.c_int), ("gmres_restart", C.c_int), ("max_cached_solutions", C.c_int)]
 
 
 class _Bands(C.Structure):
@@ -78,7 +78,8 @@ ABI_SYMBOLS = [
     "pprts_b200_solve_at_time", "pprts_b200_need_new_solution", "pprts_b200_get_solution_times",
     "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated", "pprts_b200_polyfit",
     "pprts_b200_find_iter_and_kernelwidth", "pprts_b200_smooth_surface_fluxes", "pprts_b200_smooth_accumulated",
-    "pprts_b200_krylov_retries", "pprts_b200_debug_fail_next_krylov",
+    "pprts_b200_krylov_retries", "pprts_b200_debug_fail_next_krylov", "pprts_b200_stage_optical_properties_async",
+    "pprts_b200_get_result_async", "pprts_b200_wait_results",
 ]
 
 
@@ -136,6 +137,9 @@ def lib():
     L.pprts_b200_kernel_stats.argtypes = [C.c_void_p, C.c_int, c_double_p, c_long_p]
     L.pprts_b200_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.pprts_b200_solve_bands.argtypes = [C.c_void_p, C.POINTER(_Bands)] + [C.c_void_p] * 4 + [c_int_p]
+    L.pprts_b200_stage_optical_properties_async.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 6
+    L.pprts_b200_get_result_async.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.pprts_b200_wait_results.argtypes = [C.c_void_p]
     L.pprts_b200_krylov_retries.restype = C.c_long
     L.pprts_b200_krylov_retries.argtypes = [C.c_void_p]
     L.pprts_b200_debug_fail_next_krylov.argtypes = [C.c_void_p, C.c_int]
@@ -263,6 +267,24 @@ class Solver:
         _chk(lib().pprts_b200_stage_optical_properties(self._h, slot, float(albedo), *[_vp(a) for a in arrs]),
              "stage_optical_properties")
 
+    def stage_optical_properties_async(self, slot, albedo, kabs, ksca, g, planck=None, planck_srfc=None, albedo_2d=None):
+        """enqueue the upload of a band on the copy stream; the arrays must be Fortran-ordered float64 (no copies are made
+        here) and stay alive, ideally page-locked, until set_optical_properties_staged(slot) returns"""
+        arrs = (kabs, ksca, g, planck, planck_srfc, albedo_2d)
+        for a in arrs:
+            if a is not None and not (a.dtype == np.float64 and (a.flags.f_contiguous or a.ndim == 1)):
+                raise PprtsError("stage_optical_properties_async needs Fortran-ordered float64 arrays")
+        _chk(lib().pprts_b200_stage_optical_properties_async(self._h, slot, float(albedo), *[_vp(a) for a in arrs]),
+             "stage_optical_properties_async")
+
+    def get_result_async(self, uid, out):
+        """pprts_get_result into the caller's (edn, eup, abso, edir) arrays, complete after wait_results()"""
+        edn, eup, abso, edir = out
+        _chk(lib().pprts_b200_get_result_async(self._h, uid, _vp(edn), _vp(eup), _vp(abso), _vp(edir)), "get_result_async")
+
+    def wait_results(self):
+        _chk(lib().pprts_b200_wait_results(self._h), "wait_results")
+
     def set_optical_properties_staged(self, slot, ldelta_scaling=True):
         _chk(lib().pprts_b200_set_optical_properties_staged(self._h, slot, int(ldelta_scaling)),
              "set_optical_properties_staged")
@@ -286,11 +308,15 @@ class Solver:
     def allreduce_accumulated(self):
         _chk(lib().pprts_b200_allreduce_accumulated(self._h), "allreduce_accumulated")
 
-    def get_accumulated(self):
-        out = _alloc_results(self)
+    def get_accumulated(self, out=None):
+        out = _alloc_results(self) if out is None else out
         _chk(lib().pprts_b200_get_accumulated(self._h, *[_vp(a) for a in out]), "get_accumulated")
         edn, eup, abso, edir = out
         return edn, eup, abso, edir
+
+    def get_accumulated_into(self, out):
+        """the spectral sums into caller-provided (edn, eup, abso, edir) Fortran-ordered arrays"""
+        return self.get_accumulated(out)
 
 
 def nccl_unique_id() -> bytes:
@@ -312,7 +338,8 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
                by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
                keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
                max_solution_time=None, geometric_coeffs=False, top_bottom_faces_planar=True,
-               top_bottom_planes_parallel=True, accept_incomplete_solve=False, gmres_restart=0) -> Solver:
+               top_bottom_planes_parallel=True, accept_incomplete_solve=False, gmres_restart=0,
+               max_cached_solutions=0) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -351,6 +378,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.krylov_fp32 = int(krylov_fp32)
     cfg.accept_incomplete_solve = int(accept_incomplete_solve)   # -accept_incomplete_solve
     cfg.gmres_restart = int(gmres_restart)
+    cfg.max_cached_solutions = int(max_cached_solutions)
     cfg.collapseindex = int(collapseindex) if collapseindex is not None else 1
     if max_solution_err is not None:      # -max_solution_err / -max_solution_time (src/tenstream_options.F90:90-96)
         cfg.max_solution_err = float(max_solution_err)

@@ -31,9 +31,13 @@ def _periodic_gaussian_filter(field, sigma):
 
 
 def cloud_field(Nx=256, Ny=256, Nz=80, dx=100.0, dz=50.0, phi0=120.0, theta0=40.0, albedo=0.15, seed=20240229,
-                cover=0.30, sigma_px=6.0):
+                cover=0.30, sigma_px=6.0, window=None):
     """C2: seeded filtered-noise cloud field with 30 % cover, cloud base at 65 % of the column from the top,
-    thickness 5-20 % of the column; in-cloud ksca U(10,40)/km, g = 0.85; clear air ksca = 1.2e-5 exp(-z/8km)."""
+    thickness 5-20 % of the column; in-cloud ksca U(10,40)/km, g = 0.85; clear air ksca = 1.2e-5 exp(-z/8km).
+
+    ``window = (xs, xm, ys, ym)``: only the columns [xs, xs+xm) x [ys, ys+ym) of the (Nx, Ny) domain are built (a rank's
+    block of an x/y-decomposed domain); the 2-D cloud mask is always drawn for the whole domain, so the blocks of all
+    ranks tile the same global field.  The returned Nx / Ny are the GLOBAL sizes, the arrays are local."""
     rng = np.random.default_rng(seed)
     noise = _periodic_gaussian_filter(rng.standard_normal((Nx, Ny)), sigma_px * min(1.0, Nx / 64.0))
     thresh = np.quantile(noise, 1.0 - cover)
@@ -42,12 +46,16 @@ def cloud_field(Nx=256, Ny=256, Nz=80, dx=100.0, dz=50.0, phi0=120.0, theta0=40.
     kbase = int(round(0.65 * Nz))
     tmin, tmax = max(1, int(round(0.05 * Nz))), max(2, int(round(0.20 * Nz)))
     thick = (tmin + np.round(strength * (tmax - tmin))).astype(int)
+    kcld = rng.uniform(10.0, 40.0, size=(Nx, Ny)) / 1000.0
+    if window is not None:
+        xs, xm, ys, ym = window
+        cloudy, thick, kcld = (a[xs:xs + xm, ys:ys + ym] for a in (cloudy, thick, kcld))
+    lx, ly = cloudy.shape
     zmid = (Nz - 0.5 - np.arange(Nz)) * dz                       # height of layer centres above ground [m]
-    ksca = np.empty((Nz, Nx, Ny))
+    ksca = np.empty((Nz, lx, ly))
     ksca[:] = (1.2e-5 * np.exp(-zmid / 8000.0))[:, None, None]
     kabs = 0.25 * ksca
-    g = np.zeros((Nz, Nx, Ny))
-    kcld = rng.uniform(10.0, 40.0, size=(Nx, Ny)) / 1000.0
+    g = np.zeros((Nz, lx, ly))
     kk = np.arange(Nz)[:, None, None]
     incloud = cloudy[None] & (kk < kbase) & (kk >= kbase - thick[None])
     ksca = np.where(incloud, kcld[None], ksca)
@@ -56,8 +64,8 @@ def cloud_field(Nx=256, Ny=256, Nz=80, dx=100.0, dz=50.0, phi0=120.0, theta0=40.
     # thermal band: T(z) = 288 K - 6.5 K/km, planck = sigma T^4 / pi on levels, kabs_th = 10 kabs, no scattering
     zlev = (Nz - np.arange(Nz + 1)) * dz
     T = 288.0 - 6.5e-3 * zlev
-    planck = np.broadcast_to((SIGMA_SB * T ** 4 / np.pi)[:, None, None], (Nz + 1, Nx, Ny)).copy()
-    planck_srfc = np.full((Nx, Ny), SIGMA_SB * 288.0 ** 4 / np.pi)
+    planck = np.broadcast_to((SIGMA_SB * T ** 4 / np.pi)[:, None, None], (Nz + 1, lx, ly)).copy()
+    planck_srfc = np.full((lx, ly), SIGMA_SB * 288.0 ** 4 / np.pi)
     return dict(Nx=Nx, Ny=Ny, Nz=Nz, dx=dx, dy=dx, dz1d=np.full(Nz, dz), phi0=phi0, theta0=theta0, albedo=albedo,
                 edirTOA=1364.0, kabs=kabs, ksca=ksca, g=g,
                 kabs_th=10.0 * kabs, ksca_th=np.zeros_like(ksca), g_th=np.zeros_like(g), planck=planck,

@@ -205,7 +205,7 @@ def test_lone_1d_bottom_layer(P, gpu_lut, oracle_lut, krylov_fp32):
     dz = np.array([100., 100., 100., 100., 100., 100., 100., 500.])
     sd = P.sundir_from_angles(200., 35.)
     o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz)
-    assert list(o.l1d()) == [1, 0, 0, 0, 0, 0, 0, 1]
+    assert [int(v) for v in o.l1d] == [1, 0, 0, 0, 0, 0, 0, 1]
     o.destroy()
     out = run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, 100., dz, 200., 35., 0.25, kabs, ksca, g)
     assert relerr(*out["edir"], 1e-9) < 1e-9

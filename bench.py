@@ -543,32 +543,48 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
         keep.append(t)
         return v
 
-    def band_stack(base, scales):   # (Nz,Nx,Ny,nb) page-locked, Fortran order: band ib is one contiguous block
-        t, v = pinned_f(torch, base.shape + (len(scales),))
-        for ib, f in enumerate(scales):
-            np.multiply(base, f, out=v[..., ib])
+    # Host memory stays bounded: the per-band absorption fields of a rank live in TWO page-locked stacks of CHUNK bands
+    # (Fortran order: band ib is one contiguous block); a host thread fills the next stack -- the host model computing
+    # the optical properties of the next g-points -- while solve_bands works through the current one.
+    from concurrent.futures import ThreadPoolExecutor
+    CHUNK = 8
+    stacks = []
+    for _ in range(2):
+        t, v = pinned_f(torch, sc["kabs"].shape + (CHUNK,))
         keep.append(t)
-        return v
+        stacks.append(v)
+    pool = ThreadPoolExecutor(1)
+
+    def fill(stack, base, scales):
+        for ib, f in enumerate(scales):
+            np.multiply(base, f, out=stack[..., ib])
+        return stack[..., :len(scales)]
 
     ksca, g = pinned_copy(sc["ksca"]), pinned_copy(sc["g"])
     zero = pinned_copy(np.zeros_like(sc["ksca"]))
     planck, planck_srfc = pinned_copy(sc["planck"]), pinned_copy(sc["planck_srfc"])
-    kabs_sw = band_stack(sc["kabs"], [b["scale"] for b in my_sw]) if my_sw else None
-    kabs_lw = band_stack(sc["kabs_th"], [b["scale"] for b in my_lw]) if my_lw else None
-    e_sw = np.array([b["edirTOA"] for b in my_sw])
-    w_lw = np.array([b["weight"] for b in my_lw])
     h2d = (len(my_sw) * 3 + len(my_lw) * 4) * ncell * 8
     outs = tuple(pinned_f(torch, shp)[1] for shp in ((nz + 1, nx, ny), (nz + 1, nx, ny), (nz, nx, ny), (nz + 1, nx, ny)))
+    work = [(True, my_sw[i:i + CHUNK]) for i in range(0, len(my_sw), CHUNK)] + \
+           [(False, my_lw[i:i + CHUNK]) for i in range(0, len(my_lw), CHUNK)]
+
+    def submit(iw):
+        lsol, bs = work[iw]
+        return pool.submit(fill, stacks[iw & 1], sc["kabs"] if lsol else sc["kabs_th"], [b["scale"] for b in bs])
 
     def spectral_integration():
         it = []
-        first = True
-        if my_sw:
-            r = P.solve_bands(s, True, sc["albedo"], kabs_sw, ksca, g, edirTOA=e_sw, uid0=my_sw[0]["uid"], download=False)
-            it += list(r[4]); first = False
-        if my_lw:
-            r = P.solve_bands(s, False, sc["albedo_th"], kabs_lw, zero, zero, planck=planck, planck_srfc=planck_srfc,
-                              weights=w_lw, uid0=my_lw[0]["uid"], download=False, accumulate_only=not first)
+        fut = submit(0) if work else None
+        for iw, (lsol, bs) in enumerate(work):
+            kabs = fut.result()
+            fut = submit(iw + 1) if iw + 1 < len(work) else None
+            if lsol:
+                r = P.solve_bands(s, True, sc["albedo"], kabs, ksca, g, edirTOA=np.array([b["edirTOA"] for b in bs]),
+                                  uid0=bs[0]["uid"], download=False, accumulate_only=iw > 0)
+            else:
+                r = P.solve_bands(s, False, sc["albedo_th"], kabs, zero, zero, planck=planck, planck_srfc=planck_srfc,
+                                  weights=np.array([b["weight"] for b in bs]), uid0=bs[0]["uid"], download=False,
+                                  accumulate_only=iw > 0)
             it += list(r[4])
         if world > 1:
             s.allreduce_accumulated()
@@ -577,7 +593,8 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
 
     # warm-up: one solar band (lazy allocations, first-touch of the pinned pages)
     if my_sw:
-        P.solve_bands(s, True, sc["albedo"], kabs_sw[..., :1], ksca, g, edirTOA=e_sw[:1], uid0=900, download=False)
+        P.solve_bands(s, True, sc["albedo"], fill(stacks[1], sc["kabs"], [my_sw[0]["scale"]]), ksca, g,
+                      edirTOA=np.array([my_sw[0]["edirTOA"]]), uid0=900, download=False)
     timer = Timer(torch, dist, world, s)
     box = {}
     ms, launches = timer.run(lambda: box.__setitem__("it", spectral_integration()), 1, 0)

@@ -402,19 +402,21 @@ k_lookup(Grid g, LutDev lut, SymMaps sym, int lsolar, int kstart, const double *
 }
 
 // ---- cooperative per-tile formulation ---------------------------------------------------------------------------
-// k_lookup above is bound by its gathers and its stores, not by HBM (ncu, profiles/r1_others.txt: 1.7 TB/s algorithmic,
-// write traffic 1.32x algorithmic): every thread walks ITS corner rows with 4-byte loads -- a warp-wide load touches 32
-// different table rows -- and the plane stores of a thread reach DRAM as partial sectors.  Here one CTA of four warps owns
-// one coefficient tile (PB_TILE cells):
-//   plan    : lane l of a warp computes search + corner offsets + weights of the warp's cell l (registers);
-//   gather  : the warp then walks its 32 cells ONE AT A TIME -- the plan of the cell travels by shuffle -- and reads
-//             every corner row of the diffuse table as one coalesced 16-byte-per-lane request (a 3_10 row is 400
-//             contiguous bytes = 25 lanes), the two (phi,theta)-contracted direct rows as 8-byte requests; each lane
-//             accumulates its slice of the row in fp64 in the reference's corner order (same fma chain as k_lookup:
-//             bit-identical results);
-//   store   : the warp's 32 x ncoef block sits in shared memory (odd row stride: conflict-free both ways) and leaves
-//             plane by plane -- lane = cell -- as full 128-byte lines; the divergence factors 1 - sum_dst and the
-//             widening class of the tile fall out of the same pass.
+// k_lookup above (one thread per cell) is bound by its gathers, not by HBM (ncu, profiles/r1_others.txt: 1.7 TB/s
+// algorithmic): every thread walks ITS 16 corner rows with 4-byte loads, a warp-wide load touches up to 32 different
+// table rows.  Here one CTA of four warps owns one coefficient tile (PB_TILE cells), a warp 32 consecutive cells:
+//   plan    : lane l maps its cell into LUT space (get_coeff's fp32 sample).  Neighbouring cells with the SAME sample
+//             -- horizontally homogeneous clear air, everything the table clamps -- have the same coefficients: only
+//             the first cell of such a run (a "leader") is interpolated, the others copy its row.
+//   gather  : the warp walks its leaders one at a time -- the leader's corner offsets and weights travel by shuffle --
+//             and reads every corner row of the diffuse table as ONE coalesced 16-byte-per-lane request (a 3_10 row is
+//             400 contiguous bytes = 25 lanes), the two (phi,theta)-contracted direct rows as 8-byte requests.  All 16
+//             corner loads are issued before the first use (plans with fewer corners are padded with weight 0, which
+//             leaves the fp64 fma chain bit-identical), each lane accumulates its slice of the row in fp64 in the
+//             reference's corner order (same chain as k_lookup).
+//   store   : the leaders' rows sit in shared memory (odd row stride: conflict-free); lane = cell reads the row of its
+//             leader and the block leaves plane by plane as full 128-byte lines; the divergence factors 1 - sum_dst
+//             and the widening class of the tile fall out of the same pass.
 // Coefficient rows longer than 128 floats (3_24: 576) are processed in chunks of 128.
 template <class L>
 struct LookupCfg {
@@ -433,6 +435,7 @@ k_lookup_tile(Grid g, LutDev lut, SymMaps sym, int lsolar, long tile0, long c_be
               double *__restrict__ cdiv_dir, double *__restrict__ cdiv_diff, unsigned int *__restrict__ tile_class) {
   using K = LookupCfg<L>;
   constexpr int Nd = L::Nd, Nf = L::Nf;
+  constexpr unsigned int FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char lk_smem[];
   __shared__ short s_sym[K::NDIR];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -440,26 +443,36 @@ k_lookup_tile(Grid g, LutDev lut, SymMaps sym, int lsolar, long tile0, long c_be
   for (int n = threadIdx.x; n < K::NDIR; n += blockDim.x) s_sym[n] = n < K::NDD ? sym.d2d[n] : sym.d2f[n - K::NDD];
   __syncthreads();
   const long tile = tile0 + blockIdx.x;
-  const long cw = tile * PB_TILE + warp * 32;  // first cell of this warp
-  const long c = cw + lane;
+  const long c = tile * PB_TILE + warp * 32 + lane;
   const bool valid = c >= c_begin && c < c_end;
-  // ---- plan of my cell
-  int p_nc = 0;
+  // ---- LUT-space sample of my cell, runs of identical samples
+  float sample[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
+  const int prev_valid = __shfl_up_sync(FULL, (int)valid, 1);  // every lane takes part in every shuffle
+  bool same = lane > 0 && valid && prev_valid != 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const float prev = __shfl_up_sync(FULL, sample[d], 1);
+    same = same && __float_as_uint(prev) == __float_as_uint(sample[d]);
+  }
+  const bool leader = valid && !same;
+  const unsigned int leaders = __ballot_sync(FULL, leader);
+  if (leaders == 0u) return;  // warp-uniform; no block-wide barrier follows
+  const int myrow = 31 - __clz((int)(leaders & (FULL >> (31 - lane))));  // nearest leader at or below my lane
+  // ---- plan of a leader: 16 corners, padded with (first corner, weight 0)
   int p_ofs[16];
   double p_w[16];
 #pragma unroll
   for (int b = 0; b < 16; ++b) { p_ofs[b] = 0; p_w[b] = 0.0; }
-  if (valid) {
-    float sample[4];
-    lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
+  if (leader) {
     InterpPlan p;
     make_plan(lut, sample, p);
-    p_nc = p.ncorner;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) if (b < p.ncorner) { p_ofs[b] = (int)p.ofs[b]; p_w[b] = p.w[b]; }
+    for (int b = 0; b < 16; ++b) {
+      p_ofs[b] = (int)p.ofs[b < p.ncorner ? b : 0];
+      p_w[b] = b < p.ncorner ? p.w[b] : 0.0;
+    }
   }
-  const unsigned int anyvalid = __ballot_sync(0xffffffffu, valid);
-  if (anyvalid == 0u) return;  // warp-uniform; no block-wide barrier follows
   const long tb_ff = tile * (long)(K::NFF * PB_TILE) + warp * 32 + lane;  // + n*PB_TILE: plane n, my cell
   int wclass = 0;
   double colsum[Nf];
@@ -468,24 +481,25 @@ k_lookup_tile(Grid g, LutDev lut, SymMaps sym, int lsolar, long tile0, long c_be
   // ---- diff2diff, CHUNK floats of every row at a time
 #pragma unroll
   for (int ch = 0; ch < K::NCHUNK; ++ch) {
-    constexpr int dummy = 0; (void)dummy;
     const int n0 = ch * K::CHUNK;
     const int nthis = (K::NFF - n0 < K::CHUNK) ? K::NFF - n0 : K::CHUNK;  // floats in this chunk
     const bool lane_on = 4 * lane < nthis;
-    for (int q = 0; q < 32; ++q) {
-      const int nc = __shfl_sync(0xffffffffu, p_nc, q);
+    const float4 *base4 = reinterpret_cast<const float4 *>(lut.Sdiff + n0) + (lane_on ? lane : 0);
+    for (unsigned int rem = leaders; rem; rem &= rem - 1) {
+      const int q = __ffs((int)rem) - 1;
+      float4 v[16];
+      double w[16];
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const int ofs = __shfl_sync(FULL, p_ofs[b], q);
+        w[b] = __shfl_sync(FULL, p_w[b], q);
+        v[b] = __ldg(base4 + (long)ofs * (K::NFF / 4));
+      }
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
       for (int b = 0; b < 16; ++b) {
-        if (b < nc) {  // warp-uniform
-          const int ofs = __shfl_sync(0xffffffffu, p_ofs[b], q);
-          const double w = __shfl_sync(0xffffffffu, p_w[b], q);
-          if (lane_on) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(lut.Sdiff + (long)ofs * K::NFF + n0) + lane);
-            a0 = fma(w, widen_any(v.x), a0); a1 = fma(w, widen_any(v.y), a1);
-            a2 = fma(w, widen_any(v.z), a2); a3 = fma(w, widen_any(v.w), a3);
-          }
-        }
+        a0 = fma(w[b], widen(v[b].x), a0); a1 = fma(w[b], widen(v[b].y), a1);
+        a2 = fma(w[b], widen(v[b].z), a2); a3 = fma(w[b], widen(v[b].w), a3);
       }
       if (lane_on) {
         CT *row = stage + q * K::STRIDE + 4 * lane;
@@ -494,7 +508,7 @@ k_lookup_tile(Grid g, LutDev lut, SymMaps sym, int lsolar, long tile0, long c_be
     }
     __syncwarp();
     if (valid) {  // lane = cell: plane stores, 128 contiguous bytes per warp and plane
-      const CT *row = stage + lane * K::STRIDE;
+      const CT *row = stage + myrow * K::STRIDE;
 #pragma unroll
       for (int m = 0; m < K::CHUNK; ++m) {
         const int n = n0 + m;
@@ -514,53 +528,48 @@ k_lookup_tile(Grid g, LutDev lut, SymMaps sym, int lsolar, long tile0, long c_be
   }
   if (sizeof(CT) == 4) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wclass = max(wclass, __shfl_xor_sync(0xffffffffu, wclass, o));
+    for (int o = 16; o > 0; o >>= 1) wclass = max(wclass, __shfl_xor_sync(FULL, wclass, o));
     if (lane == 0 && wclass > 0) atomicMax(tile_class + tile, (unsigned int)wclass);
   }
-  if (!lsolar) return;
   // ---- dir2dir | dir2diff from the (phi,theta)-contracted fp64 tables: value n of the concatenated row per lane slot
-  for (int q = 0; q < 32; ++q) {
-    const int nc = __shfl_sync(0xffffffffu, p_nc, q);
-    double acc[K::DIR_PER_LANE];
-    int src[K::DIR_PER_LANE];
+  if (lsolar) {
+    for (unsigned int rem = leaders; rem; rem &= rem - 1) {
+      const int q = __ffs((int)rem) - 1;
+      int ofs[16];
+      double w[16];
 #pragma unroll
-    for (int r = 0; r < K::DIR_PER_LANE; ++r) {
-      acc[r] = 0.0;
-      const int n = lane + 32 * r;
-      src[r] = n < K::NDIR ? (int)s_sym[n] : 0;
-    }
+      for (int b = 0; b < 16; ++b) { ofs[b] = __shfl_sync(FULL, p_ofs[b], q); w[b] = __shfl_sync(FULL, p_w[b], q); }
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-      if (b < nc) {
-        const int ofs = __shfl_sync(0xffffffffu, p_ofs[b], q);
-        const double w = __shfl_sync(0xffffffffu, p_w[b], q);
+      for (int r = 0; r < K::DIR_PER_LANE; ++r) {
+        const int n = lane + 32 * r;
+        const bool on = n < K::NDIR;
+        const bool isT = n < K::NDD;
+        const int src = on ? (int)s_sym[n] : 0;
+        const double *tab = isT ? lut.Tdir4 + src : lut.Sdir4 + src;
+        const long rowlen = isT ? K::NDD : K::NDF;
+        double x[16];
 #pragma unroll
-        for (int r = 0; r < K::DIR_PER_LANE; ++r) {
-          const int n = lane + 32 * r;
-          if (n < K::NDD) acc[r] = fma(w, __ldg(lut.Tdir4 + (long)ofs * K::NDD + src[r]), acc[r]);
-          else if (n < K::NDIR) acc[r] = fma(w, __ldg(lut.Sdir4 + (long)ofs * K::NDF + src[r]), acc[r]);
-        }
+        for (int b = 0; b < 16; ++b) x[b] = __ldg(tab + (long)ofs[b] * rowlen);
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) acc = fma(w[b], x[b], acc);
+        if (on) stage[q * K::STRIDE + n] = (CT)acc;
       }
     }
+    __syncwarp();
+    if (valid) {
+      const CT *row = stage + myrow * K::STRIDE;
+      const long tb_dd = tile * (long)(K::NDD * PB_TILE) + warp * 32 + lane, tb_df = tile * (long)(K::NDF * PB_TILE) + warp * 32 + lane;
+      double sum1[Nd], sum2[Nd];
 #pragma unroll
-    for (int r = 0; r < K::DIR_PER_LANE; ++r) {
-      const int n = lane + 32 * r;
-      if (n < K::NDIR) stage[q * K::STRIDE + n] = (CT)acc[r];
+      for (int s = 0; s < Nd; ++s) { sum1[s] = 0.0; sum2[s] = 0.0; }
+#pragma unroll
+      for (int n = 0; n < K::NDD; ++n) { const CT st = row[n]; d2d[tb_dd + (long)n * PB_TILE] = st; sum1[n % Nd] += (double)st; }
+#pragma unroll
+      for (int n = 0; n < K::NDF; ++n) { const CT st = row[K::NDD + n]; d2f[tb_df + (long)n * PB_TILE] = st; sum2[n % Nd] += (double)st; }
+#pragma unroll
+      for (int s = 0; s < Nd; ++s) cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1[s] - sum2[s];  // src/pprts.F90:5315
     }
-  }
-  __syncwarp();
-  if (valid) {
-    const CT *row = stage + lane * K::STRIDE;
-    const long tb_dd = tile * (long)(K::NDD * PB_TILE) + warp * 32 + lane, tb_df = tile * (long)(K::NDF * PB_TILE) + warp * 32 + lane;
-    double sum1[Nd], sum2[Nd];
-#pragma unroll
-    for (int s = 0; s < Nd; ++s) { sum1[s] = 0.0; sum2[s] = 0.0; }
-#pragma unroll
-    for (int n = 0; n < K::NDD; ++n) { const CT st = row[n]; d2d[tb_dd + (long)n * PB_TILE] = st; sum1[n % Nd] += (double)st; }
-#pragma unroll
-    for (int n = 0; n < K::NDF; ++n) { const CT st = row[K::NDD + n]; d2f[tb_df + (long)n * PB_TILE] = st; sum2[n % Nd] += (double)st; }
-#pragma unroll
-    for (int s = 0; s < Nd; ++s) cdiv_dir[(long)s * g.ncp + c] = 1.0 - sum1[s] - sum2[s];  // src/pprts.F90:5315
   }
 }
 
@@ -1926,20 +1935,23 @@ __device__ __forceinline__ BicgScalars bicg_scalars(const double *__restrict__ s
   }
   return o;
 }
-// r64 = b - Ax (Ax in `ax`); r = rh = (float) r64;  SC_RR = (r64, r64) [true residual], SC_RHO1 = (r, r) = rho(1)
+// r64 = b - Ax (Ax in `ax`); r = rh = (float) r64;  SC_RR = (r64, r64) [true residual], SC_RHO1 = (r, r) = rho(1),
+// SC_RHV = (b, b) (only read right after this kernel: the rounding floor of the true residual, solve_ediff_mixed)
 __global__ void k_mixed_init(long n, const double *__restrict__ b, const double *__restrict__ ax,
                              float *__restrict__ r, float *__restrict__ rh, double *partials, unsigned int *counter,
                              double *sc) {
-  double acc[2] = {0.0, 0.0};
+  double acc[3] = {0.0, 0.0, 0.0};
   for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
-    const double rv = b[q] - ax[q];
+    const double bv = b[q];
+    const double rv = bv - ax[q];
     const float rf = (float)rv;
     r[q] = rf; rh[q] = rf;
     acc[0] += rv * rv;
     const double rd = widen_any(rf);
     acc[1] += rd * rd;
+    acc[2] += bv * bv;
   }
-  grid_reduce_sum<2>(acc, partials, counter, &sc[SC_RR]);
+  grid_reduce_sum<3>(acc, partials, counter, &sc[SC_RR]);
 }
 // SC_TMP = ||b - Ax||^2 (Ax in `ax`): fp64 check of the true residual that leaves the fp32 recursion untouched
 __global__ void k_residual_norm2(long n, const double *__restrict__ b, const double *__restrict__ ax,

@@ -1189,6 +1189,8 @@ static int launch_matmult(pprts_b200_solver *s, VT *x, VT *y, const VT *w, doubl
 }
 
 static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond >= 1; }
+// PPRTS_B200_KRYLOV_TRACE: residual history of the diffuse solves on stderr (tools/krylov_trace.py)
+static bool krylov_trace() { static const bool on = getenv("PPRTS_B200_KRYLOV_TRACE") != nullptr; return on; }
 
 // Column kernels are one thread per column and latency-bound per thread, so their run time is (number of waves) x
 // (time of one column): pick the block size (<= PREC_BLOCK) for which all columns are resident in the fewest waves.
@@ -1320,14 +1322,17 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   for (int cycle = 0; !converged && cycle < 64; ++cycle) {
     if ((rc = launch_matmult<0, double>(s, x, ax, nullptr, nullptr))) return rc;
     LAUNCH(s, FAM_VEC, k_mixed_init, vec_grid(n), VEC_BLOCK, n, s->b, ax, r, rh, s->partials, s->counter, s->sc);
-    if ((rc = allreduce_scalars(s, s->sc + SC_RR, 2))) return rc;
+    if ((rc = allreduce_scalars(s, s->sc + SC_RR, 3))) return rc;
     if ((rc = read_scalars(s))) return rc;
     const double rc0 = std::sqrt(s->h_sc[SC_RR]);  // true residual this cycle starts from
     if (cycle == 0) r0 = std::max(DBL_MIN, rc0);
     sol.res_diff = rc0;
     if (!(rc0 == rc0)) return set_err(21, "diffuse solve broke down (NaN residual) in refinement cycle %d", cycle);
     const double target = std::max(rtol * r0, atol);  // MyKSPConverged: rn/r0 <= rtol or rn <= atol
-    if (rc0 <= target) { converged = true; break; }
+    // A TRUE residual at the rounding floor of b - A x cannot be reduced any further (e.g. a warm start from a solution
+    // that is already converged, asked for another rtol): the reference's test, which sees a recursive residual, passes
+    // there because the recursion keeps dropping; here it is the end of the solve as well.
+    if (rc0 <= target || rc0 <= 1e-14 * std::sqrt(s->h_sc[SC_RHV])) { converged = true; break; }
     if (total >= maxit) break;
     const double floor32 = 2e-6 * rc0;
     double inner = 0.9 * target;  // a little below: the recursive residual drifts from the true one by O(eps32)
@@ -1347,6 +1352,7 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
       ++total;
       sol.niter_diff = total;
       sol.res_diff = rn;
+      if (krylov_trace()) fprintf(stderr, "[krylov32] it %d rn/r0 %.3e\n", total, rn / r0);
       if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", total);
       if (rn <= inner && inner > floor32) {  // the recursion claims convergence: check the true residual in fp64
         LAUNCH(s, FAM_VEC, k_mixed_flush, vec_grid(n), VEC_BLOCK, n, xc, x);
@@ -1357,6 +1363,7 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
         if ((rc = read_scalars(s))) return rc;
         const double rtrue = std::sqrt(s->h_sc[SC_TMP]);
         sol.res_diff = rtrue;
+        if (krylov_trace()) fprintf(stderr, "[krylov32] it %d true residual %.3e (recursive %.3e) target %.3e\n", total, rtrue / r0, rn / r0, target / r0);
         if (rtrue <= target) converged = true;
         else {
           inner = std::min(0.5 * inner, 0.5 * inner * target / rtrue);  // keep the Krylov space, aim lower
@@ -1529,6 +1536,7 @@ static int solve_ediff_krylov(pprts_b200_solver *s, Solution &sol, double rtol, 
     const double rn = std::sqrt(s->h_sc[SC_RR]);
     sol.niter_diff = total;
     sol.res_diff = rn;
+    if (krylov_trace()) fprintf(stderr, "[krylov64] it %d rn/r0 %.3e\n", total, rn / r0);
     if (!(rn == rn)) return set_err(21, "diffuse solve broke down (NaN residual) at iteration %d", total);
     if (rn / r0 <= rtol || rn <= atol) converged = true;
     else if (std::fabs(s->h_sc[((it + 1) & 1) ? SC_RHO1 : SC_RHO0]) <= 1e-30 * rn * r0) {

@@ -38,7 +38,13 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-        "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warp_latency_issue_stalled_short_scoreboard.pct", "smsp__average_warp_latency_issue_stalled_lg_throttle.pct",
+        "smsp__average_warp_latency_issue_stalled_mio_throttle.pct", "smsp__average_warp_latency_issue_stalled_barrier.pct",
+        "smsp__average_warp_latency_issue_stalled_wait.pct", "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.pct",
+        "smsp__average_warp_latency_issue_stalled_drain.pct", "smsp__average_warp_latency_issue_stalled_not_selected.pct",
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
 def kernels(src, dst):

@@ -924,6 +924,234 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
   grid_reduce_sum<1>(d2sum, partials, counter, out_norm2);
 }
 
+// ---- sun-ordered wavefront sweep ----------------------------------------------------------------------------------
+// explicit_edir_forward_sweep (src/pprts_explicit.F90:330-459) is a Gauss-Seidel sweep in sun order: a cell reads the
+// beam that entered through its top face from the level above and through its upstream x / y faces from the cells the
+// sweep has ALREADY updated.  k_edir_pass above lags BOTH horizontal inputs by one pass, so it needs one pass per column
+// the beam crosses (72-200 at the BASELINE sizes).  Here the sweep is exact inside a tile of 32 x EDIR_TY columns and
+// lagged only ACROSS tiles -- one pass per tile boundary the beam crosses (a handful):
+//   * threads are arranged in sun order (ip, jp increase along the beam); warp b of a CTA owns 32 x-consecutive columns
+//     of row jp and marches down the levels, one level per step, b steps behind warp 0 (the wavefront jp + k = const);
+//   * x: inside a level the beam that leaves cell a through its x face enters cell a+1: x_out(a) = M_a x_out(a-1) + r_a
+//     with M_a = dir2dir(x <- x) and r_a the part fed by the top and y inputs -- a first-order linear recurrence over
+//     the 32 lanes, solved by a warp scan over the affine maps (5 shuffle rounds); lane 0 takes the previous pass's
+//     value of the upstream tile (or of the periodic wrap / the neighbouring rank);
+//   * y: warp b reads what warp b-1 wrote one step earlier (shared memory); warp 0 reads the previous pass;
+//   * top: kept in registers from level to level, exactly as in k_edir_pass.
+// Every output is then evaluated from its three inputs in the reference's order of operations.  Ping-pong buffers keep
+// the lagged inputs those of the previous pass (deterministic); all loads of a warp are 128 contiguous bytes.
+#define EDIR_TY 8
+template <int NS>
+struct EdirAffine { double m[NS][NS], r[NS]; };
+template <class L, class CT>
+__global__ void __launch_bounds__(32 * EDIR_TY)
+k_edir_tile_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__restrict__ d2d,
+                 const double *__restrict__ a33, const double *__restrict__ xold, double *__restrict__ xnew,
+                 double *partials, unsigned int *counter, double *out_norm2) {
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, TY = EDIR_TY;
+  constexpr unsigned int FULL = 0xffffffffu;
+  __shared__ double ybuf[2][TY][Nds][32];
+  const int NI = (g.Nx + 31) / 32;
+  const int I = blockIdx.x % NI, J = blockIdx.x / NI;
+  const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
+  const int ip = I * 32 + a, jp = J * TY + b;  // sun-ordered column indices
+  const bool active = ip < g.Nx && jp < g.Ny;
+  const int i = active ? (xinc ? ip : g.Nx - 1 - ip) : 0, j = active ? (yinc ? jp : g.Ny - 1 - jp) : 0;
+  const long o_own = (long)j * g.Nx + i;
+  long xp0, xps, xpk, yp0, yps, ypk;  // high faces: periodic image or ghost block (see k_edir_pass)
+  if (g.gx && i + 1 == g.Nx) { xp0 = ghost_x_base(g, Nd) + j; xps = (long)(g.Nz + 1) * g.Ny; xpk = g.Ny; }
+  else { xp0 = (long)j * g.Nx + wrap_p(i, g.Nx); xps = g.nlev; xpk = g.ncol; }
+  if (g.gy && j + 1 == g.Ny) { yp0 = ghost_y_base(g, Nd) + i; yps = (long)(g.Nz + 1) * g.Nx; ypk = g.Nx; }
+  else { yp0 = (long)wrap_p(j, g.Ny) * g.Nx + i; yps = g.nlev; ypk = g.ncol; }
+  const long xin0 = xinc ? o_own : xp0, xins = xinc ? g.nlev : xps, xink = xinc ? g.ncol : xpk;
+  const long xout0 = xinc ? xp0 : o_own, xouts = xinc ? xps : g.nlev, xoutk = xinc ? xpk : g.ncol;
+  const long yin0 = yinc ? o_own : yp0, yins = yinc ? g.nlev : yps, yink = yinc ? g.ncol : ypk;
+  const long yout0 = yinc ? yp0 : o_own, youts = yinc ? yps : g.nlev, youtk = yinc ? ypk : g.ncol;
+  const int Nz = g.Nz, T = Nz + TY - 1;
+  double d2sum[1] = {0.0};
+  double top[Ndt];
+#pragma unroll
+  for (int d = 0; d < Ndt; ++d) top[d] = inc_top;
+  if (active) {  // setup_incSolar (src/pprts_base.F90:1146-1181)
+#pragma unroll
+    for (int d = 0; d < Ndt; ++d) {
+      const long q = (long)d * g.nlev + o_own;
+      const double df = inc_top - xold[q];
+      d2sum[0] += df * df;
+      xnew[q] = inc_top;
+    }
+  }
+  // what a level reads besides the beam of this pass: coefficients, the lagged inputs of the tile's upstream edges, the
+  // old values of its outputs (for the norm) -- loaded two levels ahead into rotating register sets
+  struct In { CT c[Nd * Nd]; double sx[Nds], sy[Nds], old[Nd], a33; };
+  auto load = [&](int k, In &in) {
+    const long lk = (long)k * g.ncol, lk1 = lk + g.ncol;
+    if (is1d(g, n1d, k)) {
+      in.a33 = a33[lk + o_own];
+#pragma unroll
+      for (int d = 0; d < Ndt; ++d) in.old[d] = xold[(long)d * g.nlev + lk1 + o_own];
+#pragma unroll
+      for (int d = Ndt; d < Nd; ++d) in.old[d] = xold[(long)d * g.nlev + lk + o_own];
+    } else {
+      if (a == 0) {
+#pragma unroll
+        for (int d = 0; d < Nds; ++d) in.sx[d] = xold[xin0 + (Ndt + d) * xins + k * xink];
+      }
+      if (b == 0) {
+#pragma unroll
+        for (int d = 0; d < Nds; ++d) in.sy[d] = xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
+      }
+      const long cb = cbase<Nd * Nd>(lk + o_own);
+#pragma unroll
+      for (int n = 0; n < Nd * Nd; ++n) in.c[n] = d2d[cb + n * PB_TILE];
+#pragma unroll
+      for (int dst = 0; dst < Nd; ++dst) {
+        long q;
+        if (dst < Ndt) q = (long)dst * g.nlev + lk1 + o_own;
+        else if (dst < Ndt + Nds) q = xout0 + dst * xouts + k * xoutk;
+        else q = yout0 + dst * youts + k * youtk;
+        in.old[dst] = xold[q];
+      }
+    }
+  };
+  auto level = [&](int t, int k, const In &in) {  // executed by whole warps (k is warp-uniform)
+    const long lk = (long)k * g.ncol, lk1 = lk + g.ncol;
+    if (is1d(g, n1d, k)) {  // 1-D layer: top(k+1) = top(k) * a33 (:383-391); side dofs are left untouched
+      if (active) {
+#pragma unroll
+        for (int d = 0; d < Ndt; ++d) {
+          top[d] = top[d] * in.a33;
+          const double df = top[d] - in.old[d];
+          d2sum[0] += df * df;
+          xnew[(long)d * g.nlev + lk1 + o_own] = top[d];
+        }
+#pragma unroll
+        for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lk + o_own] = in.old[d];
+      }
+      return;
+    }
+    double sy[Nds], sx[Nds];
+#pragma unroll
+    for (int d = 0; d < Nds; ++d) sy[d] = (b == 0) ? in.sy[d] : ybuf[(t + 1) & 1][b - 1][d][a];
+    // affine map of my cell: x_out = M x_in + r
+    EdirAffine<Nds> f;
+#pragma unroll
+    for (int p = 0; p < Nds; ++p) {
+      double r = 0.0;
+#pragma unroll
+      for (int s = 0; s < Ndt; ++s) r = fma(top[s], (double)in.c[(Ndt + p) * Nd + s], r);
+#pragma unroll
+      for (int s = 0; s < Nds; ++s) r = fma(sy[s], (double)in.c[(Ndt + p) * Nd + Ndt + Nds + s], r);
+#pragma unroll
+      for (int q = 0; q < Nds; ++q) f.m[p][q] = active ? (double)in.c[(Ndt + p) * Nd + Ndt + q] : (p == q ? 1.0 : 0.0);
+      f.r[p] = active ? r : 0.0;
+    }
+    if (a == 0) {  // the tile's upstream edge: the lagged value goes into r, nothing is taken from "lane -1"
+#pragma unroll
+      for (int p = 0; p < Nds; ++p) {
+        double r = f.r[p];
+#pragma unroll
+        for (int q = 0; q < Nds; ++q) { r = fma(f.m[p][q], in.sx[q], r); }
+        f.r[p] = r;
+      }
+#pragma unroll
+      for (int p = 0; p < Nds; ++p)
+#pragma unroll
+        for (int q = 0; q < Nds; ++q) f.m[p][q] = 0.0;
+    }
+    // inclusive warp scan: after round o lane a holds the composition of the maps of lanes a-2o+1 .. a
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      EdirAffine<Nds> pv;
+#pragma unroll
+      for (int p = 0; p < Nds; ++p) {
+        pv.r[p] = __shfl_up_sync(FULL, f.r[p], o);
+#pragma unroll
+        for (int q = 0; q < Nds; ++q) pv.m[p][q] = __shfl_up_sync(FULL, f.m[p][q], o);
+      }
+      if (a >= o) {
+        EdirAffine<Nds> n;
+#pragma unroll
+        for (int p = 0; p < Nds; ++p) {
+          double r = f.r[p];
+#pragma unroll
+          for (int q = 0; q < Nds; ++q) r = fma(f.m[p][q], pv.r[q], r);
+          n.r[p] = r;
+#pragma unroll
+          for (int q = 0; q < Nds; ++q) {
+            double m = 0.0;
+#pragma unroll
+            for (int u = 0; u < Nds; ++u) m = fma(f.m[p][u], pv.m[u][q], m);
+            n.m[p][q] = m;
+          }
+        }
+        f = n;
+      }
+    }
+    // f.r is now x_out of my cell as the scan sees it; my x input is the x output of lane a-1
+#pragma unroll
+    for (int p = 0; p < Nds; ++p) sx[p] = __shfl_up_sync(FULL, f.r[p], 1);
+    if (a == 0) {
+#pragma unroll
+      for (int p = 0; p < Nds; ++p) sx[p] = in.sx[p];
+    }
+    if (!active) return;
+    double src[Nd];
+#pragma unroll
+    for (int d = 0; d < Ndt; ++d) src[d] = top[d];
+#pragma unroll
+    for (int d = 0; d < Nds; ++d) src[Ndt + d] = sx[d];
+#pragma unroll
+    for (int d = 0; d < Nds; ++d) src[Ndt + Nds + d] = sy[d];
+#pragma unroll
+    for (int dst = 0; dst < Nd; ++dst) {
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < Nd; ++s) acc = acc + src[s] * (double)in.c[dst * Nd + s];
+      long q;
+      if (dst < Ndt) { q = (long)dst * g.nlev + lk1 + o_own; top[dst] = acc; }
+      else if (dst < Ndt + Nds) q = xout0 + dst * xouts + k * xoutk;
+      else { q = yout0 + dst * youts + k * youtk; ybuf[t & 1][b][dst - Ndt - Nds][a] = acc; }
+      const double df = acc - in.old[dst];
+      d2sum[0] += df * df;
+      xnew[q] = acc;
+    }
+  };
+  // step t: warp b is at level t - b.  Register sets rotate by level (selected by k mod NSET, warp-uniform), no set is
+  // ever copied; the 8-stream layouts (64 coefficients per level) keep two sets, i.e. one level of look-ahead.
+  if constexpr (Nd <= 3) {
+    In A, B, C3;
+    if (active) { load(0, A); if (Nz > 1) load(1, B); }
+    for (int t = 0; t < T; ++t) {
+      __syncthreads();  // y outputs of step t-1 are in ybuf
+      const int k = t - b;
+      if (k >= 0 && k < Nz) {
+        const int sel = k % 3;
+        if (sel == 0) { if (active && k + 2 < Nz) load(k + 2, C3); level(t, k, A); }
+        else if (sel == 1) { if (active && k + 2 < Nz) load(k + 2, A); level(t, k, B); }
+        else { if (active && k + 2 < Nz) load(k + 2, B); level(t, k, C3); }
+      }
+    }
+  } else {
+    In A, B;
+    if (active) load(0, A);
+    for (int t = 0; t < T; ++t) {
+      __syncthreads();
+      const int k = t - b;
+      if (k >= 0 && k < Nz) {
+        if ((k & 1) == 0) { if (active && k + 1 < Nz) load(k + 1, B); level(t, k, A); }
+        else { if (active && k + 1 < Nz) load(k + 1, A); level(t, k, B); }
+      }
+    }
+  }
+  if (active) {  // side dofs below the ground are never written by the sweep
+    const long lz = (long)g.Nz * g.ncol;
+#pragma unroll
+    for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lz + o_own] = xold[(long)d * g.nlev + lz + o_own];
+  }
+  grid_reduce_sum<1>(d2sum, partials, counter, out_norm2);
+}
+
 // =================================================================================================================
 // HOT LOOP C: source term (src/pprts.F90:4641-4987 setup_b).  The reference scatter-adds into the six faces of a
 // cell and folds ghosts with halo_reduce_5pt; here every b entry has exactly one producing cell (the cell for which

@@ -1035,19 +1035,21 @@ static int edir_exchange(pprts_b200_solver *s, double *v) {
 }
 
 static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
+  static const bool jacobi = getenv("PPRTS_B200_EDIR_JACOBI") != nullptr;  // the round-1 fully lagged passes, for comparison
   const Grid &g = s->g;
   int maxiter = s->cfg.maxit_dir > 0 ? s->cfg.maxit_dir : 1000;
   double rtol_d, atol_d;
   determine_ksp_tolerances(s, rtol_d, atol_d);
   double rtol = s->cfg.rtol >= 0 ? s->cfg.rtol : rtol_d, atol = s->cfg.atol >= 0 ? s->cfg.atol : atol_d;
   if (sol.first_dir) { maxiter += 2; rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
-  // The reference's test ||x_n - x_{n-1}|| < atol or < rtol * first (:186-196) is written for its Gauss-Seidel sweep,
-  // whose change per sweep IS its error (the sweep solves everything but the periodic wrap exactly).  A lagged pass
-  // moves information one column per pass, so its change only says how much arrived in this pass, not how much is still
-  // on its way: stopping at the same numbers left edir 8e-5 (C1) away from the reference's result at the same
-  // tolerances (tests/test_gpu_config_goldens.py).  The passes therefore run until the change is 1e-4 of what the
-  // reference asks for -- in practice until the recurrence has ended (it is finite: the beam leaves the domain) -- which
-  // puts edir within 1e-6 of the reference at any tolerance for ~15 % more passes.
+  // A pass (k_edir_tile_pass) is the reference's sun-ordered Gauss-Seidel sweep inside a tile of 32 x EDIR_TY columns
+  // and lags the inputs ACROSS tiles (and across the periodic wrap / the rank boundaries, like the reference) by one
+  // pass: the beam needs one pass per tile boundary it crosses, after which a pass changes nothing.
+  // The reference's test ||x_n - x_{n-1}|| < atol or < rtol * first (:186-196) is written for a sweep whose change IS
+  // its error.  The change of a lagged pass only says how much arrived in this pass, not how much is still on its way:
+  // stopping at the same numbers left edir 8e-5 (C1) away from the reference's result at the same tolerances
+  // (tests/test_gpu_config_goldens.py).  The passes therefore run until the change is 1e-4 of what the reference asks
+  // for -- in practice until the recurrence has ended (it is finite: the beam leaves the domain).
   const double lag = 1e-4;
   rtol *= lag; atol *= lag;
   int adiv = 1;
@@ -1058,15 +1060,20 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   bool converged = false;
   // The horizontal inputs of a pass are one pass old, so information needs one pass per column it crosses; the
   // norm is only read back every `check` passes to keep the host out of the loop.
-  const int check = 4;
+  const int check = jacobi ? 4 : 2;
+  const int NI = (g.Nx + 31) / 32, NJ = (g.Ny + EDIR_TY - 1) / EDIR_TY;
   int iter = 0;
   int rc = edir_exchange(s, xold);  // warm-start ghosts from the previous solution (:167)
   if (rc) return rc;
   while (iter < maxiter && !converged) {
     int nb = std::min(check, maxiter - iter);
     for (int q = 0; q < nb; ++q) {
-      DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_pass<L, CT>), nblk(g.ncol, 128), 128, g, s->xinc, s->yinc, s->n1d, fac,
-                             (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
+      if (jacobi)
+        DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_pass<L, CT>), nblk(g.ncol, 128), 128, g, s->xinc, s->yinc, s->n1d, fac,
+                               (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
+      else
+        DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_tile_pass<L, CT>), NI * NJ, 32 * EDIR_TY, g, s->xinc, s->yinc, s->n1d, fac,
+                               (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
       if ((rc = edir_exchange(s, xnew))) return rc;
       if (s->decomposed) {  // residual = mean over ranks of the local 2-norms (:176-183)
         LAUNCH(s, FAM_VEC, k_sqrt_mean, 1, 32, s->sc + SC_EDIR0 + q, 1, 1.0 / (double)s->nranks);

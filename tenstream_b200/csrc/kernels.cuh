@@ -1579,12 +1579,13 @@ template <class L, class CT>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
              const double *__restrict__ a12, const double *__restrict__ albedo, double *__restrict__ R,
-             double *__restrict__ inv) {
+             double *__restrict__ inv, float *__restrict__ Rf, float *__restrict__ invf) {
   constexpr int Nf = L::Nf;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
   double Rn = albedo[col];
   R[(long)g.Nz * g.ncol + col] = Rn;
+  if (Rf) Rf[(long)g.Nz * g.ncol + col] = (float)Rn;
   for (int k = g.Nz - 1; k >= 0; --k) {
     const long c = (long)k * g.ncol + col;
     double tuu, tdu, tdd, tud;
@@ -1598,6 +1599,7 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
     Rn = tdu + tuu * Rn * tdd * iv;
     inv[c] = iv;
     R[c] = Rn;
+    if (Rf) { invf[c] = (float)iv; Rf[c] = (float)Rn; }  // what the fp32 sweeps used to convert on the fly
   }
 }
 
@@ -1617,7 +1619,7 @@ struct PrecUpIn {
 template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                              const double *__restrict__ a11, const double *__restrict__ a12,
-                                             const double *__restrict__ R, const double *__restrict__ inv,
+                                             const VT *__restrict__ R, const VT *__restrict__ inv,
                                              const VT *__restrict__ r, PrecUpIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
@@ -1648,7 +1650,7 @@ __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long
 template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
-          const double *__restrict__ R, const double *__restrict__ inv, const VT *__restrict__ r,
+          const VT *__restrict__ R, const VT *__restrict__ inv, const VT *__restrict__ r,
           VT *__restrict__ z, int sides) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   static_assert(Nft == 2, "column preconditioner needs one up/down pair of top streams");
@@ -1718,7 +1720,7 @@ struct PrecDownIn {
 template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                                const double *__restrict__ a11, const double *__restrict__ a12,
-                                               const double *__restrict__ R, const double *__restrict__ inv,
+                                               const VT *__restrict__ R, const VT *__restrict__ inv,
                                                const VT *__restrict__ r, const VT *z, PrecDownIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
@@ -1752,7 +1754,7 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
 template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK, 8)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
-            const double *__restrict__ a12, const double *__restrict__ R, const double *__restrict__ inv,
+            const double *__restrict__ a12, const VT *__restrict__ R, const VT *__restrict__ inv,
             const VT *__restrict__ r, VT *z, int sides) {
   constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -238,7 +238,7 @@ struct pprts_b200_solver {
   double *precR = nullptr, *precInv = nullptr;
   double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
   bool have_dz3d = false;                   // init_pprts(dz3d=...): atm%hgrad exists (src/pprts.F90:621)
-  float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the block (3_24) sweeps on fp32 vectors
+  float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the sweeps on fp32 vectors (krylov_fp32, 3_24 block form)
   bool prec_ready = false;
   int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
@@ -698,7 +698,7 @@ static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, 
     int np = 1;  // up/down pairs of top streams: the column preconditioner keeps np x np matrices per level
     DISPATCH_L(s, np = L::Nft / 2);
     DA(s->precR, (size_t)np * np * g.nlev); DA(s->precInv, (size_t)np * np * g.ncell);
-    if (np > 1) { DA(s->precRf, (size_t)np * np * g.nlev); DA(s->precInvf, (size_t)np * np * g.ncell); }
+    if (np > 1 || cfg->krylov_fp32) { DA(s->precRf, (size_t)np * np * g.nlev); DA(s->precInvf, (size_t)np * np * g.ncell); }
   }
   for (int q = 0; q < 4; ++q) { DA(s->res[q], g.nlev); DA(s->acc[q], g.nlev); }
   DA(s->out_stage, (size_t)std::max(Nd, Nf) * g.nlev);
@@ -1227,16 +1227,18 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
     const Grid &g = s->g;
     if (!s->prec_ready) {
       LAUNCH(s, FAM_PRECOND, (k_prec_setup<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-             s->albedo, s->precR, s->precInv);
+             s->albedo, s->precR, s->precInv, s->precRf, s->precInvf);
       s->prec_ready = true;
     }
     constexpr int slot = std::is_same<VT, float>::value ? 2 : 0;
     const int bu = column_block(s, k_prec_up<L, CT, VT>, &s->prec_block[slot]);
     const int bd = column_block(s, k_prec_down<L, CT, VT>, &s->prec_block[slot + 1]);
+    const VT *pR, *pI;  // the sweeps read R and Inv in the precision of their vectors
+    if constexpr (std::is_same<VT, float>::value) { pR = s->precRf; pI = s->precInvf; } else { pR = s->precR; pI = s->precInv; }
     LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
+           pR, pI, r, z, (int)(s->cfg.precond != 2));
     LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           s->precR, s->precInv, r, z, (int)(s->cfg.precond != 2));
+           pR, pI, r, z, (int)(s->cfg.precond != 2));
   } else {  // several up/down pairs of top streams (3_24): block recurrence, no software pipelining
     const Grid &g = s->g;
     if (!s->prec_ready) {

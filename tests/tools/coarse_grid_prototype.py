@@ -128,6 +128,42 @@ def main():
             print(f"  column + coarse {a}x{a}    :", bicgstab_iters(A, b, spla.LinearOperator((n, n), matvec=two_level)),
                   "| coarse first:", bicgstab_iters(A, b, spla.LinearOperator((n, n), matvec=coarse_first)), flush=True)
 
+            def additive(r, lu_c=lu_c, P=P):     # no fine-level MatMult inside the preconditioner
+                return col_solve(r) + P @ lu_c.solve(P.T @ r)
+            print(f"  additive {a}x{a}           :", bicgstab_iters(A, b, spla.LinearOperator((n, n), matvec=additive)), flush=True)
+            # inexact coarse solves: m sweeps of the coarse-level column relaxation (the coarse analogue of col_solve)
+            Ac = (P.T @ A @ P).tocsr()
+            ccol = cidx.reshape(Nf, Nl, Nx, Ny)[0, 0] if False else None
+            aggc = np.broadcast_to((np.arange(Nx // a)[:, None] * (Ny // a) + np.arange(Ny // a)[None, :])[None, None],
+                                   (Nf, Nl, Nx // a, Ny // a)).reshape(-1)
+            Acoo_c = Ac.tocoo()
+            keepc = aggc[Acoo_c.row] == aggc[Acoo_c.col]
+            Mc = sp.csc_matrix((Acoo_c.data[keepc], (Acoo_c.row[keepc], Acoo_c.col[keepc])), shape=Ac.shape)
+            permc = np.argsort(aggc, kind="stable")
+            lu_cc = spla.splu(Mc[permc][:, permc].tocsc(), permc_spec="NATURAL")
+            inv_permc = np.empty_like(permc); inv_permc[permc] = np.arange(nc)
+
+            def ccol_solve(rc):
+                return lu_cc.solve(rc[permc])[inv_permc]
+            for m in [int(v) for v in os.environ.get("COARSE_SWEEPS", "1,2,4,8").split(",")]:
+                def two_level_inexact(r, m=m, P=P, Ac=Ac):
+                    z = col_solve(r)
+                    rc = P.T @ (r - A @ z)
+                    xc = np.zeros(nc)
+                    for _ in range(m):
+                        xc = xc + ccol_solve(rc - Ac @ xc)
+                    return z + P @ xc
+
+                def additive_inexact(r, m=m, P=P, Ac=Ac):
+                    rc = P.T @ r
+                    xc = np.zeros(nc)
+                    for _ in range(m):
+                        xc = xc + ccol_solve(rc - Ac @ xc)
+                    return col_solve(r) + P @ xc
+                print(f"  {a}x{a}, {m} coarse column sweeps: multiplicative",
+                      bicgstab_iters(A, b, spla.LinearOperator((n, n), matvec=two_level_inexact)), "| additive",
+                      bicgstab_iters(A, b, spla.LinearOperator((n, n), matvec=additive_inexact)), flush=True)
+
 
 if __name__ == "__main__":
     main()

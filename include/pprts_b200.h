@@ -89,7 +89,9 @@ typedef struct {
   double rtol, atol;   /* < 0: reference defaults (src/pprts_base.F90:1128-1131) */
   int maxit_dir;       /* <= 0: 1000 (src/pprts_explicit.F90:78) */
   int maxit_diff;      /* <= 0: 1000 (src/pprts_base.F90:1126) */
-  int precond;         /* diffuse Krylov preconditioner: 0 none, 1 vertical-line (column two-stream) solve */
+  int precond;         /* diffuse Krylov preconditioner: 0 none, 1 vertical-line (column) solve, 2 two-stream column only,
+                        * 3 (default) column solve + coarse-grid correction on 4x4-column aggregates (3_10 / 8_10; other
+                        * layouts fall back to 1) */
   int device;          /* CUDA ordinal, < 0: current device */
   int keep_solutions;  /* 1: cache edir/ediff/abso per uid for warm starts like solver%solutions(uid) */
   /* x/y decomposition over the GPUs of one box (src/pprts_base.F90:721-828): this rank's cartesian position.

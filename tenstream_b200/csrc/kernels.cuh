@@ -1798,6 +1798,312 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
 }
 
 // =================================================================================================================
+// Coarse-grid correction on top of the column solve (cfg.precond = 3, layouts with one up/down pair of top streams).
+// The column solve moves information exactly in the vertical but only one column per application in the horizontal,
+// and the slow modes of I - T are horizontally smooth (a beam crosses 30-50 columns between the surface and the model
+// top): BiCGStab needs a polynomial of about that degree.  The correction solves the same system on horizontal
+// aggregates of AG x AG columns (piecewise-constant prolongation P per stream and level, Galerkin operator P^T A P) --
+// but only its COLUMN BLOCK, i.e. the couplings inside one column of aggregates, and adds the result to the fine column
+// solve:   z = M_col^-1 r + P (P^T A P)_col^-1 P^T r .
+// Inside an aggregate the streams that cross fine-cell faces have become self-couplings of the coarse cell, so one
+// aggregate-column solve transports over AG columns; no coarse MatMult, no halo exchange (aggregates never straddle
+// ranks), everything is local to a column of aggregates.  Measured with the operator probed from the oracle (CPU
+// prototype tests/tools/coarse_grid_prototype.py, 48x48x80, rtol 1e-5): 66 -> 25 iterations (19 with an exact coarse
+// solve), for one extra read of r and one update of z per application.
+//
+// Coarse cell (k, I, J): the 2*Nfs side dofs s living at its index are inputs AND outputs of the cell (feedback through
+// the interior faces), U(k+1) and D(k) are its top inputs:
+//     s      = Css s + csu U(k+1) + csd D(k) + r_s
+//     U(k)   = cus s + cuu U(k+1) + cud D(k) + r_U          D(k+1) = cds s + cdu U(k+1) + cdd D(k) + r_D
+// with C = (sum over the fine cells of the aggregate of their T, entries whose face lies outside the aggregate column
+// dropped) / (cells per aggregate).  Eliminating the sides, W = (I - Css)^-1, leaves a scalar two-stream column with
+//     a_uu = cuu + cus W csu, a_ud = cud + cus W csd, a_du = cdu + cds W csu, a_dd = cdd + cds W csd,
+//     f_U = r_U + (cus W) r_s,  f_D = r_D + (cds W) r_s
+// which the adding-method recurrence of k_prec_up / k_prec_down inverts; then s = (W csu) U(k+1) + (W csd) D(k) + W r_s.
+// Stored per coarse cell (fp32, plane-major [n][ncc]): a_uu a_ud a_du a_dd | gU = cus W | gD = cds W | wu = W csu |
+// wd = W csd | W.
+// =================================================================================================================
+struct CoarseGrid {
+  int AG, NxC, NyC, Nz;
+  long ncolC, ncc, nclev;  // aggregate columns, coarse cells, coarse level entries
+};
+template <int NS> struct CgLayout { static constexpr int A = 0, GU = 4, GD = 4 + NS, WU = 4 + 2 * NS, WD = 4 + 3 * NS, W = 4 + 4 * NS, N = 4 + 4 * NS + NS * NS; };
+
+template <class L, class CT>
+__global__ void __launch_bounds__(64)
+k_cg_build(Grid g, CoarseGrid cg, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
+           const double *__restrict__ a12, float *__restrict__ coef) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs, NS = 2 * Nfs;
+  static_assert(Nft == 2, "coarse correction needs one up/down pair of top streams");
+  using CL = CgLayout<NS>;
+  const long cc = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= cg.ncc) return;
+  const int I = (int)(cc % cg.NxC), J = (int)((cc / cg.NxC) % cg.NyC), k = (int)(cc / cg.ncolC);
+  const int i0 = I * cg.AG, i1 = min(g.Nx, i0 + cg.AG), j0 = J * cg.AG, j1 = min(g.Ny, j0 + cg.AG);
+  double C[Nf][Nf];
+#pragma unroll
+  for (int a = 0; a < Nf; ++a)
+#pragma unroll
+    for (int b = 0; b < Nf; ++b) C[a][b] = 0.0;
+  for (int j = j0; j < j1; ++j) {
+    // is the high-y face of row j (where the streams leaving towards +y arrive) inside this aggregate?
+    const bool yin = (j + 1 < g.Ny) ? ((j + 1) / cg.AG == J) : (!g.gy && J == 0);
+    for (int i = i0; i < i1; ++i) {
+      const bool xin = (i + 1 < g.Nx) ? ((i + 1) / cg.AG == I) : (!g.gx && I == 0);
+      const long c = lidx(g, k, j, i);
+      if (is1d(g, n1d, k)) {
+        C[0][0] += a11[c]; C[1][1] += a11[c]; C[0][1] += a12[c]; C[1][0] += a12[c];
+        continue;
+      }
+      const long cb = cbase<Nf * Nf>(c);
+      bool out_ok[Nf], in_ok[Nf];
+#pragma unroll
+      for (int d = 0; d < Nf; ++d) {
+        if (d < Nft) { out_ok[d] = true; in_ok[d] = true; }
+        else if (d < Nft + Nfs) { const bool in = L::side_in(d - Nft); out_ok[d] = in ? xin : true; in_ok[d] = in ? true : xin; }
+        else { const bool in = L::side_in(d - Nft - Nfs); out_ok[d] = in ? yin : true; in_ok[d] = in ? true : yin; }
+      }
+#pragma unroll
+      for (int dst = 0; dst < Nf; ++dst)
+#pragma unroll
+        for (int src = 0; src < Nf; ++src) {
+          const double v = (double)T[cb + (dst * Nf + src) * PB_TILE];
+          if (out_ok[dst] && in_ok[src]) C[dst][src] += v;
+        }
+    }
+  }
+  const double sc = 1.0 / (double)((i1 - i0) * (j1 - j0));
+#pragma unroll
+  for (int a = 0; a < Nf; ++a)
+#pragma unroll
+    for (int b = 0; b < Nf; ++b) C[a][b] *= sc;
+  // W = (I - Css)^-1 by Gauss-Jordan (I - Css is strictly diagonally dominant: the column sums of T are < 1)
+  double M[NS][NS], W[NS][NS];
+#pragma unroll
+  for (int p = 0; p < NS; ++p)
+#pragma unroll
+    for (int q = 0; q < NS; ++q) { M[p][q] = (p == q ? 1.0 : 0.0) - C[Nft + p][Nft + q]; W[p][q] = (p == q ? 1.0 : 0.0); }
+#pragma unroll
+  for (int p = 0; p < NS; ++p) {
+    const double piv = 1.0 / M[p][p];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) { M[p][q] *= piv; W[p][q] *= piv; }
+#pragma unroll
+    for (int r = 0; r < NS; ++r) {
+      if (r == p) continue;
+      const double f = M[r][p];
+#pragma unroll
+      for (int q = 0; q < NS; ++q) { M[r][q] -= f * M[p][q]; W[r][q] -= f * W[p][q]; }
+    }
+  }
+  double wu[NS], wd[NS], gU[NS], gD[NS];
+#pragma unroll
+  for (int p = 0; p < NS; ++p) {
+    double u = 0.0, d = 0.0, a = 0.0, b = 0.0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      u += W[p][q] * C[Nft + q][0]; d += W[p][q] * C[Nft + q][1];   // W csu, W csd
+      a += C[0][Nft + q] * W[q][p]; b += C[1][Nft + q] * W[q][p];   // cus W, cds W
+    }
+    wu[p] = u; wd[p] = d; gU[p] = a; gD[p] = b;
+  }
+  double auu = C[0][0], aud = C[0][1], adu = C[1][0], add = C[1][1];
+#pragma unroll
+  for (int p = 0; p < NS; ++p) {
+    auu += C[0][Nft + p] * wu[p]; aud += C[0][Nft + p] * wd[p];
+    adu += C[1][Nft + p] * wu[p]; add += C[1][Nft + p] * wd[p];
+  }
+  auto put = [&](int n, double v) { coef[(long)n * cg.ncc + cc] = (float)v; };
+  put(CL::A + 0, auu); put(CL::A + 1, aud); put(CL::A + 2, adu); put(CL::A + 3, add);
+#pragma unroll
+  for (int p = 0; p < NS; ++p) { put(CL::GU + p, gU[p]); put(CL::GD + p, gD[p]); put(CL::WU + p, wu[p]); put(CL::WD + p, wd[p]); }
+#pragma unroll
+  for (int p = 0; p < NS; ++p)
+#pragma unroll
+    for (int q = 0; q < NS; ++q) put(CL::W + p * NS + q, W[p][q]);
+}
+
+// reflectance R_k of everything below coarse level k and Inv_k = 1 / (1 - a_du R_{k+1}) (as k_prec_setup)
+__global__ void k_cg_setup(Grid g, CoarseGrid cg, const double *__restrict__ albedo, const float *__restrict__ coef,
+                           float *__restrict__ R, float *__restrict__ inv) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cg.ncolC) return;
+  const int I = (int)(col % cg.NxC), J = (int)(col / cg.NxC);
+  const int i0 = I * cg.AG, i1 = min(g.Nx, i0 + cg.AG), j0 = J * cg.AG, j1 = min(g.Ny, j0 + cg.AG);
+  double Rn = 0.0;
+  for (int j = j0; j < j1; ++j)
+    for (int i = i0; i < i1; ++i) Rn += albedo[(long)j * g.Nx + i];
+  Rn /= (double)((i1 - i0) * (j1 - j0));
+  R[(long)cg.Nz * cg.ncolC + col] = (float)Rn;
+  for (int k = cg.Nz - 1; k >= 0; --k) {
+    const long cc = (long)k * cg.ncolC + col;
+    const double auu = coef[0 * cg.ncc + cc], aud = coef[1 * cg.ncc + cc], adu = coef[2 * cg.ncc + cc], add = coef[3 * cg.ncc + cc];
+    const double iv = 1.0 / (1.0 - adu * Rn);
+    Rn = aud + auu * Rn * add * iv;
+    inv[cc] = (float)iv;
+    R[cc] = (float)Rn;
+  }
+}
+
+// rbar = P^T r / (cells per aggregate) for all Nf dofs of coarse level entry lc; e = (gU . rbar_s, gD . rbar_s)
+template <class L, class VT>
+__global__ void __launch_bounds__(128)
+k_cg_restrict(Grid g, CoarseGrid cg, const VT *__restrict__ r, const float *__restrict__ coef, float *__restrict__ rbar,
+              float *__restrict__ e) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, NS = 2 * L::Nfs;
+  using CL = CgLayout<NS>;
+  const long lc = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= cg.nclev) return;
+  const int I = (int)(lc % cg.NxC), J = (int)((lc / cg.NxC) % cg.NyC), k = (int)(lc / cg.ncolC);
+  const int i0 = I * cg.AG, i1 = min(g.Nx, i0 + cg.AG), j0 = J * cg.AG, j1 = min(g.Ny, j0 + cg.AG);
+  const float sc = 1.f / (float)((i1 - i0) * (j1 - j0));
+  const bool vec4 = std::is_same<VT, float>::value && cg.AG == 4 && (g.Nx & 3) == 0 && i1 - i0 == 4;
+  float rb[Nf];
+#pragma unroll
+  for (int d = 0; d < Nf; ++d) {
+    float acc = 0.f;
+    for (int j = j0; j < j1; ++j) {
+      const long q = (long)d * g.nlev + ((long)k * g.Ny + j) * g.Nx + i0;
+      if (vec4) {
+        const float4 v = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(r) + q);
+        acc += (v.x + v.y) + (v.z + v.w);
+      } else {
+        for (int i = 0; i < i1 - i0; ++i) acc += (float)r[q + i];
+      }
+    }
+    rb[d] = acc * sc;
+    rbar[(long)d * cg.nclev + lc] = rb[d];
+  }
+  if (k < cg.Nz) {
+    const long cc = lc;  // same (k, I, J) numbering for k < Nz
+    float eu = 0.f, ed = 0.f;
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+      eu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + cc], rb[Nft + p], eu);
+      ed = fmaf(coef[(long)(CL::GD + p) * cg.ncc + cc], rb[Nft + p], ed);
+    }
+    e[cc] = eu;
+    e[cg.ncc + cc] = ed;
+  }
+}
+
+// the condensed two-stream column of aggregates: upward sweep for S_k, downward sweep for D, U (xc planes 0 and 1)
+__global__ void __launch_bounds__(32)
+k_cg_column(CoarseGrid cg, const float *__restrict__ coef, const float *__restrict__ R, const float *__restrict__ inv,
+            const float *__restrict__ rbar, const float *__restrict__ e, float *__restrict__ xc) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cg.ncolC) return;
+  const long nl = cg.nclev, nc = cg.ncc, st = cg.ncolC;
+  const long lz = (long)cg.Nz * st + col;
+  float S = rbar[lz];
+  xc[lz] = S;
+  float Rn = R[lz];
+  constexpr int B = 8;  // levels whose inputs are loaded together, ahead of the recurrence
+  for (int kb = cg.Nz - 1; kb >= 0; kb -= B) {
+    float auu[B], adu[B], iv[B], Rc[B], fU[B], fD[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int k = kb - u;
+      if (k >= 0) {
+        const long cc = (long)k * st + col;
+        auu[u] = coef[cc]; adu[u] = coef[2 * nc + cc]; iv[u] = inv[cc]; Rc[u] = R[cc];
+        fU[u] = rbar[cc] + e[cc];
+        fD[u] = rbar[nl + cc + st] + e[nc + cc];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int k = kb - u;
+      if (k >= 0) {
+        const long cc = (long)k * st + col;
+        S = fU[u] + auu[u] * (S + Rn * (adu[u] * S + fD[u]) * iv[u]);
+        Rn = Rc[u];
+        xc[cc] = S;
+        xc[nl + cc + st] = fD[u];
+      }
+    }
+  }
+  float D = rbar[nl + col];
+  xc[nl + col] = D;
+  xc[col] = R[col] * D + xc[col];
+  for (int kb = 0; kb < cg.Nz; kb += B) {
+    float add[B], adu[B], iv[B], R1[B], S1[B], fD[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int k = kb + u;
+      if (k < cg.Nz) {
+        const long cc = (long)k * st + col;
+        add[u] = coef[3 * nc + cc]; adu[u] = coef[2 * nc + cc]; iv[u] = inv[cc]; R1[u] = R[cc + st];
+        S1[u] = xc[cc + st]; fD[u] = xc[nl + cc + st];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int k = kb + u;
+      if (k < cg.Nz) {
+        const long cc = (long)k * st + col;
+        const float D1 = (add[u] * D + adu[u] * S1[u] + fD[u]) * iv[u];
+        xc[cc + st] = R1[u] * D1 + S1[u];
+        xc[nl + cc + st] = D1;
+        D = D1;
+      }
+    }
+  }
+}
+
+// side streams of every coarse cell from its top inputs: s = wu U(k+1) + wd D(k) + W rbar_s
+template <class L>
+__global__ void __launch_bounds__(128)
+k_cg_sides(CoarseGrid cg, const float *__restrict__ coef, const float *__restrict__ rbar, float *__restrict__ xc) {
+  constexpr int Nft = L::Nft, NS = 2 * L::Nfs;
+  using CL = CgLayout<NS>;
+  const long lc = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= cg.nclev) return;
+  if (lc >= cg.ncc) {  // below the ground: no coupling, the fine solve has these rows already
+#pragma unroll
+    for (int p = 0; p < NS; ++p) xc[(long)(Nft + p) * cg.nclev + lc] = 0.f;
+    return;
+  }
+  const long cc = lc;
+  const float u = xc[lc + cg.ncolC], d = xc[cg.nclev + lc];
+  float rs[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) rs[q] = rbar[(long)(Nft + q) * cg.nclev + lc];
+#pragma unroll
+  for (int p = 0; p < NS; ++p) {
+    float acc = coef[(long)(CL::WU + p) * cg.ncc + cc] * u + coef[(long)(CL::WD + p) * cg.ncc + cc] * d;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) acc = fmaf(coef[(long)(CL::W + p * NS + q) * cg.ncc + cc], rs[q], acc);
+    xc[(long)(Nft + p) * cg.nclev + lc] = acc;
+  }
+}
+
+// z += P xc (piecewise constant over the aggregate); one thread per 4 x-consecutive fine entries when rows allow it
+template <class VT>
+__global__ void k_cg_prolong(Grid g, CoarseGrid cg, int nd, const float *__restrict__ xc, VT *__restrict__ z) {
+  const bool vec4 = std::is_same<VT, float>::value && cg.AG == 4 && (g.Nx & 3) == 0;
+  if (vec4) {
+    const long n4 = (long)nd * g.nlev / 4;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long)gridDim.x * blockDim.x) {
+      const long q = t * 4, d = q / g.nlev, l = q - d * g.nlev;
+      const int i = (int)(l % g.Nx), j = (int)((l / g.Nx) % g.Ny), k = (int)(l / g.ncol);
+      const float v = xc[d * cg.nclev + ((long)k * cg.NyC + j / 4) * cg.NxC + i / 4];
+      float4 *zp = reinterpret_cast<float4 *>(reinterpret_cast<float *>(z) + q);
+      float4 zv = *zp;
+      zv.x += v; zv.y += v; zv.z += v; zv.w += v;
+      *zp = zv;
+    }
+  } else {
+    const long n = (long)nd * g.nlev;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+      const long d = q / g.nlev, l = q - d * g.nlev;
+      const int i = (int)(l % g.Nx), j = (int)((l / g.Nx) % g.Ny), k = (int)(l / g.ncol);
+      z[q] += (VT)xc[d * cg.nclev + ((long)k * cg.NyC + j / cg.AG) * cg.NxC + i / cg.AG];
+    }
+  }
+}
+
+// =================================================================================================================
 // Block variant of the column preconditioner for layouts with NP = Nft/2 > 1 up/down pairs of top streams (3_24:
 // NP = 4).  Same adding-method recurrence with NP x NP matrices:
 //   Inv_k = (I - Tud R_{k+1})^-1,  R_k = Tdu + Tuu R_{k+1} Inv_k Tdd,  S_k = f_U + Tuu (S_{k+1} + R_{k+1} Inv_k (Tud S_{k+1} + f_D))

@@ -240,6 +240,10 @@ struct pprts_b200_solver {
   bool have_dz3d = false;                   // init_pprts(dz3d=...): atm%hgrad exists (src/pprts.F90:621)
   float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the sweeps on fp32 vectors (krylov_fp32, 3_24 block form)
   bool prec_ready = false;
+  // coarse-grid correction (cfg.precond = 3): aggregates of cg.AG x cg.AG columns, see kernels.cuh
+  bool cg_on = false;
+  CoarseGrid cg{};
+  float *cg_coef = nullptr, *cg_R = nullptr, *cg_inv = nullptr, *cg_rbar = nullptr, *cg_e = nullptr, *cg_x = nullptr;
   int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
   bool res_valid = false;
@@ -484,7 +488,7 @@ extern "C" void pprts_b200_default_config(pprts_b200_config *cfg) {
   cfg->coeff_fp32 = 1;
   cfg->by_coeff_divergence = 1;
   cfg->rtol = -1; cfg->atol = -1;
-  cfg->precond = 1;
+  cfg->precond = 3;
   cfg->device = -1;
   cfg->keep_solutions = 1;
   cfg->nxproc = cfg->nyproc = 1;
@@ -700,6 +704,20 @@ static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, 
     DA(s->precR, (size_t)np * np * g.nlev); DA(s->precInv, (size_t)np * np * g.ncell);
     if (np > 1 || cfg->krylov_fp32) { DA(s->precRf, (size_t)np * np * g.nlev); DA(s->precInvf, (size_t)np * np * g.ncell); }
   }
+  if (cfg->precond == 3) {  // coarse-grid correction: layouts with one up/down pair of top streams
+    int nft = 0, nfs = 0;
+    DISPATCH_L(s, (nft = L::Nft, nfs = L::Nfs));
+    if (nft == 2) {
+      const int ag = getenv("PPRTS_B200_CG_AGG") ? std::max(2, atoi(getenv("PPRTS_B200_CG_AGG"))) : 4;
+      CoarseGrid &c = s->cg;
+      c.AG = ag; c.NxC = (g.Nx + ag - 1) / ag; c.NyC = (g.Ny + ag - 1) / ag; c.Nz = g.Nz;
+      c.ncolC = (long)c.NxC * c.NyC; c.ncc = c.ncolC * g.Nz; c.nclev = c.ncolC * (g.Nz + 1);
+      const int ns = 2 * nfs, ncoef = 4 + 4 * ns + ns * ns;
+      DA(s->cg_coef, (size_t)ncoef * c.ncc); DA(s->cg_R, (size_t)c.nclev); DA(s->cg_inv, (size_t)c.ncc);
+      DA(s->cg_rbar, (size_t)Nf * c.nclev); DA(s->cg_e, (size_t)2 * c.ncc); DA(s->cg_x, (size_t)Nf * c.nclev);
+      s->cg_on = true;
+    }
+  }
   for (int q = 0; q < 4; ++q) { DA(s->res[q], g.nlev); DA(s->acc[q], g.nlev); }
   DA(s->out_stage, (size_t)std::max(Nd, Nf) * g.nlev);
   DA(s->partials, (size_t)4 * (nblk(g.ncell, 128) + 148 * 16 + 64));
@@ -748,6 +766,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->vh_atm);
+  cudaFree(s->cg_coef); cudaFree(s->cg_R); cudaFree(s->cg_inv); cudaFree(s->cg_rbar); cudaFree(s->cg_e); cudaFree(s->cg_x);
   for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
   if (s->egress_ready) cudaEventDestroy(s->egress_ready);
   if (s->egress_done) cudaEventDestroy(s->egress_done);
@@ -1228,6 +1247,11 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
     if (!s->prec_ready) {
       LAUNCH(s, FAM_PRECOND, (k_prec_setup<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
              s->albedo, s->precR, s->precInv, s->precRf, s->precInvf);
+      if (s->cg_on) {
+        const CoarseGrid &c = s->cg;
+        LAUNCH(s, FAM_PRECOND, (k_cg_build<L, CT>), nblk(c.ncc, 64), 64, g, c, s->n1d, (const CT *)s->f2f, s->a11, s->a12, s->cg_coef);
+        LAUNCH(s, FAM_PRECOND, k_cg_setup, nblk(c.ncolC, 64), 64, g, c, (const double *)s->albedo, (const float *)s->cg_coef, s->cg_R, s->cg_inv);
+      }
       s->prec_ready = true;
     }
     constexpr int slot = std::is_same<VT, float>::value ? 2 : 0;
@@ -1239,6 +1263,14 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
            pR, pI, r, z, (int)(s->cfg.precond != 2));
     LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            pR, pI, r, z, (int)(s->cfg.precond != 2));
+    if (s->cg_on) {  // z += P (P^T A P)_col^-1 P^T r
+      const CoarseGrid &c = s->cg;
+      LAUNCH(s, FAM_PRECOND, (k_cg_restrict<L, VT>), nblk(c.nclev, 128), 128, g, c, r, (const float *)s->cg_coef, s->cg_rbar, s->cg_e);
+      LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float *)s->cg_coef, (const float *)s->cg_R,
+             (const float *)s->cg_inv, (const float *)s->cg_rbar, (const float *)s->cg_e, s->cg_x);
+      LAUNCH(s, FAM_PRECOND, (k_cg_sides<L>), nblk(c.nclev, 128), 128, c, (const float *)s->cg_coef, (const float *)s->cg_rbar, s->cg_x);
+      LAUNCH(s, FAM_PRECOND, (k_cg_prolong<VT>), vec_grid((long)L::Nf * g.nlev / 4), VEC_BLOCK, g, c, (int)L::Nf, (const float *)s->cg_x, z);
+    }
   } else {  // several up/down pairs of top streams (3_24): block recurrence, no software pipelining
     const Grid &g = s->g;
     if (!s->prec_ready) {

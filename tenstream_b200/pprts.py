@@ -335,7 +335,7 @@ def _alloc_results(s):
 # ---------------------------------------------------------------------------------------------------------------
 def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=None, nxproc=None, nyproc=None,
                collapseindex=None, solvername=None, *, lut: Lut, twostr_ratio=2.0, coeff_fp32=True,
-               by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=1, device=-1,
+               by_coeff_divergence=True, rtol=-1.0, atol=-1.0, maxit_dir=0, maxit_diff=0, precond=3, device=-1,
                keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
                max_solution_time=None, geometric_coeffs=False, top_bottom_faces_planar=True,
                top_bottom_planes_parallel=True, accept_incomplete_solve=False, gmres_restart=0,

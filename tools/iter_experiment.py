@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Krylov iteration counts / time of the C2 workload for preconditioner variants (precond = 0, 1, 2)."""
+"""Krylov iteration counts / time of the C2 workload for preconditioner variants (precond = 0, 1, 2, 3).
+   PRECONDS=3,1 KRYLOV=mixed|fp64 [PPRTS_B200_CG_AGG=4] python tools/iter_experiment.py"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,7 +13,8 @@ sc, bands = bench.make_workload(nx, ny, nz)
 lut = P.Lut(cfg, paths)
 for precond in [int(v) for v in os.environ.get("PRECONDS", "1,2,0").split(",")]:
     s = P.init_pprts(0, nz, nx, ny, sc["dx"], sc["dy"], P.sundir_from_angles(sc["phi0"], sc["theta0"]), dz1d=sc["dz1d"],
-                     lut=lut, keep_solutions=False, coeff_fp32=True, precond=precond)
+                     lut=lut, keep_solutions=False, coeff_fp32=True, precond=precond,
+                     krylov_fp32=os.environ.get("KRYLOV", "mixed") == "mixed")
     for slot, b in enumerate(bands):
         s.stage_optical_properties(slot, b["albedo"], b["kabs"], b["ksca"], b["g"], b["planck"], b["planck_srfc"])
     for rep in range(2):

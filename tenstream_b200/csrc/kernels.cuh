@@ -1609,25 +1609,40 @@ __device__ __forceinline__ AT cw(T c) {
   if constexpr (std::is_same<AT, double>::value) return widen(c);
   else return (AT)c;
 }
+// Coarse-grid correction folded into the sweeps' final stores (see "Coarse-grid correction" below): every z entry is
+// written exactly once with its final value by one of the two sweeps, which adds xc of the entry's aggregate there
+// (z = M_col^-1 r + P xc) instead of a separate read-modify-write pass over z.  xc == nullptr: plain column solve.
+struct CgAdd {
+  const float *xc;
+  long nclev, ncolC;
+  int AG, NxC;
+};
 // upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied
 template <class L, class CT, class AT>
 struct PrecUpIn {
   AT fU, fD, tuu, tud, iv, Rc;
   AT rs[2 * L::Nfs];         // all side dofs of the level (1-D layers copy them, 3-D layers use the inward ones)
+  AT xs[2 * L::Nfs];         // coarse correction of the side dofs this sweep finalises
   CT t0[L::Nfs], t1[L::Nfs];     // T(0, inward side), T(1, inward side)
 };
 template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                              const double *__restrict__ a11, const double *__restrict__ a12,
                                              const VT *__restrict__ R, const VT *__restrict__ inv,
-                                             const VT *__restrict__ r, PrecUpIn<L, CT, VT> &in) {
+                                             const VT *__restrict__ r, const CgAdd &cg, long ccol, PrecUpIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
   in.fU = r[0 * g.nlev + c];
   in.fD = r[1 * g.nlev + l1];
   in.iv = (VT)inv[c];
   in.Rc = (VT)R[c];
-  if (is1d(g, n1d, k)) {
+  const bool l1d = is1d(g, n1d, k);
+#pragma unroll
+  for (int d = 0; d < 2 * Nfs; ++d) {
+    in.xs[d] = (VT)0;
+    if (cg.xc && (l1d || L::side_in(d % Nfs))) in.xs[d] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + (long)k * cg.ncolC + ccol];
+  }
+  if (l1d) {
     in.tuu = (VT)a11[c]; in.tud = (VT)a12[c];
 #pragma unroll
     for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
@@ -1651,11 +1666,12 @@ template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
           const VT *__restrict__ R, const VT *__restrict__ inv, const VT *__restrict__ r,
-          VT *__restrict__ z, int sides) {
+          VT *__restrict__ z, int sides, CgAdd cg) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   static_assert(Nft == 2, "column preconditioner needs one up/down pair of top streams");
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
+  const long ccol = cg.xc ? (long)((int)(col / g.Nx) / cg.AG) * cg.NxC + (int)(col % g.Nx) / cg.AG : 0;
   const long lz = (long)g.Nz * g.ncol + col;
   VT S = r[0 * g.nlev + lz];  // f_U at the surface
   z[0 * g.nlev + lz] = S;
@@ -1668,13 +1684,13 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
     VT fU = cur.fU, fD = cur.fD;
     if (is1d(g, n1d, k)) {
 #pragma unroll
-      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
+      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d] + cur.xs[d];
     } else {
       int q = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (L::side_in(d % Nfs)) {
-          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d];
+          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d] + cur.xs[d];
           if (sides) {
             fU = fma(cw<VT>(cur.t0[q]), cur.rs[d], fU);
             fD = fma(cw<VT>(cur.t1[q]), cur.rs[d], fD);
@@ -1695,25 +1711,26 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   // under the one-wave register cap and was slower: it keeps the single look-ahead.)
   PrecUpIn<L, CT, VT> A, B, C3;
   int k = g.Nz - 1;
-  prec_up_load<L, CT, VT>(g, n1d, k, col, T, a11, a12, R, inv, r, A);
-  if (k >= 1) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, B);
+  prec_up_load<L, CT, VT>(g, n1d, k, col, T, a11, a12, R, inv, r, cg, ccol, A);
+  if (k >= 1) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, cg, ccol, B);
   while (k >= 0) {
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, C3);
+    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, C3);
     level(k, A);
     if (--k < 0) break;
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, A);
+    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, A);
     level(k, B);
     if (--k < 0) break;
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, B);
+    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, B);
     level(k, C3);
     --k;
   }
-  z[1 * g.nlev + col] = r[1 * g.nlev + col];  // f_D(0) = r_D(0)
+  z[1 * g.nlev + col] = r[1 * g.nlev + col] + (cg.xc ? (VT)cg.xc[cg.nclev + ccol] : (VT)0);  // f_D(0) = r_D(0)
 }
 
 template <class L, class CT, class AT>
 struct PrecDownIn {
   AT tdd, tud, S1, fD, iv, R1;
+  AT xU, xD, xo[L::Nfs];              // coarse correction of U(k+1), D(k+1) and of the outward side dofs of the cell
   AT rsd[2 * L::Nfs];                 // r of all side dofs at the cell
   CT tt[L::Nfs][2 + L::Nfs];              // per outward dof: T(dof,0), T(dof,1), T(dof, inward sides)
 };
@@ -1721,13 +1738,28 @@ template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                                const double *__restrict__ a11, const double *__restrict__ a12,
                                                const VT *__restrict__ R, const VT *__restrict__ inv,
-                                               const VT *__restrict__ r, const VT *z, PrecDownIn<L, CT, VT> &in) {
+                                               const VT *__restrict__ r, const VT *z, const CgAdd &cg, long ccol,
+                                               PrecDownIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
   in.S1 = z[0 * g.nlev + l1];
   in.fD = z[1 * g.nlev + l1];
   in.iv = (VT)inv[c];
   in.R1 = (VT)R[l1];
+  in.xU = (VT)0; in.xD = (VT)0;
+#pragma unroll
+  for (int o = 0; o < Nfs; ++o) in.xo[o] = (VT)0;
+  if (cg.xc) {
+    const long lc = (long)k * cg.ncolC + ccol;
+    in.xU = (VT)cg.xc[lc + cg.ncolC];
+    in.xD = (VT)cg.xc[cg.nclev + lc + cg.ncolC];
+    if (!is1d(g, n1d, k)) {
+      int o = 0;
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d)
+        if (!L::side_in(d % Nfs)) { in.xo[o] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + lc]; ++o; }
+    }
+  }
   if (is1d(g, n1d, k)) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
   else {
     const long cb = cbase<Nf * Nf>(c);
@@ -1755,18 +1787,20 @@ template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK, 8)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const VT *__restrict__ R, const VT *__restrict__ inv,
-            const VT *__restrict__ r, VT *z, int sides) {
+            const VT *__restrict__ r, VT *z, int sides, CgAdd cg) {
   constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
-  VT D = z[1 * g.nlev + col];
+  const long ccol = cg.xc ? (long)((int)(col / g.Nx) / cg.AG) * cg.NxC + (int)(col % g.Nx) / cg.AG : 0;
+  // z_D(0) already carries its coarse correction (k_prec_up): the recurrence starts from the column solve's own value
+  VT D = r[1 * g.nlev + col];
   VT U = (VT)R[col] * D + z[0 * g.nlev + col];
-  z[0 * g.nlev + col] = U;
+  z[0 * g.nlev + col] = U + (cg.xc ? (VT)cg.xc[ccol] : (VT)0);
   PrecDownIn<L, CT, VT> cur, nxt;
-  prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cur);
+  prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, cur);
   for (int k = 0; k < g.Nz; ++k) {
     // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
-    if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, nxt);
+    if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     const VT S1 = cur.S1;
     const VT D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
@@ -1785,13 +1819,13 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
           for (int s = 0; s < 2 * Nfs; ++s)
             if (L::side_in(s % Nfs)) { acc = fma(cw<VT>(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
           }
-          z[(long)(Nft + d) * g.nlev + c] = acc;
+          z[(long)(Nft + d) * g.nlev + c] = acc + cur.xo[o];
           ++o;
         }
       }
     }
-    z[0 * g.nlev + l1] = U1;
-    z[1 * g.nlev + l1] = D1;
+    z[0 * g.nlev + l1] = U1 + cur.xU;
+    z[1 * g.nlev + l1] = D1 + cur.xD;
     D = D1;
     if (k + 1 < g.Nz) cur = nxt;
   }
@@ -1923,9 +1957,13 @@ k_cg_build(Grid g, CoarseGrid cg, int n1d, const CT *__restrict__ T, const doubl
     for (int q = 0; q < NS; ++q) put(CL::W + p * NS + q, W[p][q]);
 }
 
-// reflectance R_k of everything below coarse level k and Inv_k = 1 / (1 - a_du R_{k+1}) (as k_prec_setup)
+// Column recurrences of the condensed two-stream system, made affine with STATIC multipliers so that a sweep is one
+// fma per level (R_k: reflectance of everything below level k, Inv_k = 1 / (1 - a_du R_{k+1}), as in k_prec_setup):
+//   up:    S_k     = alpha_k S_{k+1} + (f_U + gamma_k f_D)      alpha = a_uu (1 + R_{k+1} a_du Inv), gamma = a_uu R_{k+1} Inv
+//   down:  D_{k+1} = p_k D_k + (q_k S_{k+1} + Inv_k f_D)         p = a_dd Inv, q = a_du Inv;   U_{k+1} = R_{k+1} D_{k+1} + S_{k+1}
+// sA[cc] = (alpha, gamma, p, q), sB[cc] = (Inv, R_{k+1}), Rtop[col] = R_0.
 __global__ void k_cg_setup(Grid g, CoarseGrid cg, const double *__restrict__ albedo, const float *__restrict__ coef,
-                           float *__restrict__ R, float *__restrict__ inv) {
+                           float4 *__restrict__ sA, float2 *__restrict__ sB, float *__restrict__ Rtop) {
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cg.ncolC) return;
   const int I = (int)(col % cg.NxC), J = (int)(col / cg.NxC);
@@ -1934,22 +1972,22 @@ __global__ void k_cg_setup(Grid g, CoarseGrid cg, const double *__restrict__ alb
   for (int j = j0; j < j1; ++j)
     for (int i = i0; i < i1; ++i) Rn += albedo[(long)j * g.Nx + i];
   Rn /= (double)((i1 - i0) * (j1 - j0));
-  R[(long)cg.Nz * cg.ncolC + col] = (float)Rn;
   for (int k = cg.Nz - 1; k >= 0; --k) {
     const long cc = (long)k * cg.ncolC + col;
     const double auu = coef[0 * cg.ncc + cc], aud = coef[1 * cg.ncc + cc], adu = coef[2 * cg.ncc + cc], add = coef[3 * cg.ncc + cc];
     const double iv = 1.0 / (1.0 - adu * Rn);
+    sA[cc] = make_float4((float)(auu * (1.0 + Rn * adu * iv)), (float)(auu * Rn * iv), (float)(add * iv), (float)(adu * iv));
+    sB[cc] = make_float2((float)iv, (float)Rn);
     Rn = aud + auu * Rn * add * iv;
-    inv[cc] = (float)iv;
-    R[cc] = (float)Rn;
   }
+  Rtop[col] = (float)Rn;
 }
 
-// rbar = P^T r / (cells per aggregate) for all Nf dofs of coarse level entry lc; e = (gU . rbar_s, gD . rbar_s)
+// rbar = P^T r / (cells per aggregate) for all Nf dofs of coarse level entry lc; f = sources of the condensed column
 template <class L, class VT>
 __global__ void __launch_bounds__(128)
 k_cg_restrict(Grid g, CoarseGrid cg, const VT *__restrict__ r, const float *__restrict__ coef, float *__restrict__ rbar,
-              float *__restrict__ e) {
+              float2 *__restrict__ f) {
   constexpr int Nf = L::Nf, Nft = L::Nft, NS = 2 * L::Nfs;
   using CL = CgLayout<NS>;
   const long lc = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1976,76 +2014,88 @@ k_cg_restrict(Grid g, CoarseGrid cg, const VT *__restrict__ r, const float *__re
   }
   if (k < cg.Nz) {
     const long cc = lc;  // same (k, I, J) numbering for k < Nz
-    float eu = 0.f, ed = 0.f;
+    float fu = rb[0], fd = 0.f;  // f_U = r_U(k) + gU . r_s, f_D = r_D(k+1) + gD . r_s
+    for (int j = j0; j < j1; ++j) {
+      const long q = (long)1 * g.nlev + ((long)(k + 1) * g.Ny + j) * g.Nx + i0;
+      if (vec4) {
+        const float4 v = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(r) + q);
+        fd += (v.x + v.y) + (v.z + v.w);
+      } else {
+        for (int i = 0; i < i1 - i0; ++i) fd += (float)r[q + i];
+      }
+    }
+    fd *= sc;
 #pragma unroll
     for (int p = 0; p < NS; ++p) {
-      eu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + cc], rb[Nft + p], eu);
-      ed = fmaf(coef[(long)(CL::GD + p) * cg.ncc + cc], rb[Nft + p], ed);
+      fu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + cc], rb[Nft + p], fu);
+      fd = fmaf(coef[(long)(CL::GD + p) * cg.ncc + cc], rb[Nft + p], fd);
     }
-    e[cc] = eu;
-    e[cg.ncc + cc] = ed;
+    f[cc] = make_float2(fu, fd);
   }
 }
 
-// the condensed two-stream column of aggregates: upward sweep for S_k, downward sweep for D, U (xc planes 0 and 1)
+// the condensed two-stream column of aggregates: upward sweep for S_k, downward sweep for D, U (xc planes 0 and 1).
+// One thread per aggregate column; the inputs of CG_B levels are loaded together (they do not depend on the recurrence),
+// then the recurrence runs through them with one fma per level.
+#define CG_B 16
 __global__ void __launch_bounds__(32)
-k_cg_column(CoarseGrid cg, const float *__restrict__ coef, const float *__restrict__ R, const float *__restrict__ inv,
-            const float *__restrict__ rbar, const float *__restrict__ e, float *__restrict__ xc) {
+k_cg_column(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__restrict__ sB, const float *__restrict__ Rtop,
+            const float *__restrict__ rbar, const float2 *__restrict__ f, float *__restrict__ xc) {
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cg.ncolC) return;
-  const long nl = cg.nclev, nc = cg.ncc, st = cg.ncolC;
+  const long nl = cg.nclev, st = cg.ncolC;
   const long lz = (long)cg.Nz * st + col;
   float S = rbar[lz];
   xc[lz] = S;
-  float Rn = R[lz];
-  constexpr int B = 8;  // levels whose inputs are loaded together, ahead of the recurrence
-  for (int kb = cg.Nz - 1; kb >= 0; kb -= B) {
-    float auu[B], adu[B], iv[B], Rc[B], fU[B], fD[B];
+  for (int kb = cg.Nz - 1; kb >= 0; kb -= CG_B) {
+    float al[CG_B], be[CG_B];
 #pragma unroll
-    for (int u = 0; u < B; ++u) {
+    for (int u = 0; u < CG_B; ++u) {
       const int k = kb - u;
       if (k >= 0) {
         const long cc = (long)k * st + col;
-        auu[u] = coef[cc]; adu[u] = coef[2 * nc + cc]; iv[u] = inv[cc]; Rc[u] = R[cc];
-        fU[u] = rbar[cc] + e[cc];
-        fD[u] = rbar[nl + cc + st] + e[nc + cc];
+        const float4 a = sA[cc];
+        const float2 ff = f[cc];
+        al[u] = a.x;
+        be[u] = fmaf(a.y, ff.y, ff.x);
       }
     }
 #pragma unroll
-    for (int u = 0; u < B; ++u) {
+    for (int u = 0; u < CG_B; ++u) {
       const int k = kb - u;
       if (k >= 0) {
-        const long cc = (long)k * st + col;
-        S = fU[u] + auu[u] * (S + Rn * (adu[u] * S + fD[u]) * iv[u]);
-        Rn = Rc[u];
-        xc[cc] = S;
-        xc[nl + cc + st] = fD[u];
+        S = fmaf(al[u], S, be[u]);
+        xc[(long)k * st + col] = S;
       }
     }
   }
   float D = rbar[nl + col];
   xc[nl + col] = D;
-  xc[col] = R[col] * D + xc[col];
-  for (int kb = 0; kb < cg.Nz; kb += B) {
-    float add[B], adu[B], iv[B], R1[B], S1[B], fD[B];
+  xc[col] = fmaf(Rtop[col], D, xc[col]);
+  for (int kb = 0; kb < cg.Nz; kb += CG_B) {
+    float p[CG_B], q[CG_B], R1[CG_B], S1[CG_B];
 #pragma unroll
-    for (int u = 0; u < B; ++u) {
+    for (int u = 0; u < CG_B; ++u) {
       const int k = kb + u;
       if (k < cg.Nz) {
         const long cc = (long)k * st + col;
-        add[u] = coef[3 * nc + cc]; adu[u] = coef[2 * nc + cc]; iv[u] = inv[cc]; R1[u] = R[cc + st];
-        S1[u] = xc[cc + st]; fD[u] = xc[nl + cc + st];
+        const float4 a = sA[cc];
+        const float2 b = sB[cc];
+        const float2 ff = f[cc];
+        S1[u] = xc[cc + st];
+        p[u] = a.z;
+        q[u] = fmaf(a.w, S1[u], b.x * ff.y);
+        R1[u] = b.y;
       }
     }
 #pragma unroll
-    for (int u = 0; u < B; ++u) {
+    for (int u = 0; u < CG_B; ++u) {
       const int k = kb + u;
       if (k < cg.Nz) {
         const long cc = (long)k * st + col;
-        const float D1 = (add[u] * D + adu[u] * S1[u] + fD[u]) * iv[u];
-        xc[cc + st] = R1[u] * D1 + S1[u];
-        xc[nl + cc + st] = D1;
-        D = D1;
+        D = fmaf(p[u], D, q[u]);
+        xc[cc + st] = fmaf(R1[u], D, S1[u]);
+        xc[nl + cc + st] = D;
       }
     }
   }

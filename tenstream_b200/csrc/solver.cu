@@ -243,7 +243,7 @@ struct pprts_b200_solver {
   // coarse-grid correction (cfg.precond = 3): aggregates of cg.AG x cg.AG columns, see kernels.cuh
   bool cg_on = false;
   CoarseGrid cg{};
-  float *cg_coef = nullptr, *cg_R = nullptr, *cg_inv = nullptr, *cg_rbar = nullptr, *cg_e = nullptr, *cg_x = nullptr;
+  float *cg_coef = nullptr, *cg_R = nullptr, *cg_sA = nullptr, *cg_sB = nullptr, *cg_rbar = nullptr, *cg_e = nullptr, *cg_x = nullptr;
   int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
   bool res_valid = false;
@@ -713,7 +713,7 @@ static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, 
       c.AG = ag; c.NxC = (g.Nx + ag - 1) / ag; c.NyC = (g.Ny + ag - 1) / ag; c.Nz = g.Nz;
       c.ncolC = (long)c.NxC * c.NyC; c.ncc = c.ncolC * g.Nz; c.nclev = c.ncolC * (g.Nz + 1);
       const int ns = 2 * nfs, ncoef = 4 + 4 * ns + ns * ns;
-      DA(s->cg_coef, (size_t)ncoef * c.ncc); DA(s->cg_R, (size_t)c.nclev); DA(s->cg_inv, (size_t)c.ncc);
+      DA(s->cg_coef, (size_t)ncoef * c.ncc); DA(s->cg_R, (size_t)c.ncolC); DA(s->cg_sA, (size_t)4 * c.ncc); DA(s->cg_sB, (size_t)2 * c.ncc);
       DA(s->cg_rbar, (size_t)Nf * c.nclev); DA(s->cg_e, (size_t)2 * c.ncc); DA(s->cg_x, (size_t)Nf * c.nclev);
       s->cg_on = true;
     }
@@ -766,7 +766,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->vh_atm);
-  cudaFree(s->cg_coef); cudaFree(s->cg_R); cudaFree(s->cg_inv); cudaFree(s->cg_rbar); cudaFree(s->cg_e); cudaFree(s->cg_x);
+  cudaFree(s->cg_coef); cudaFree(s->cg_R); cudaFree(s->cg_sA); cudaFree(s->cg_sB); cudaFree(s->cg_rbar); cudaFree(s->cg_e); cudaFree(s->cg_x);
   for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
   if (s->egress_ready) cudaEventDestroy(s->egress_ready);
   if (s->egress_done) cudaEventDestroy(s->egress_done);
@@ -1215,6 +1215,7 @@ static int launch_matmult(pprts_b200_solver *s, VT *x, VT *y, const VT *w, doubl
 }
 
 static bool precond_available(const pprts_b200_solver *s) { return s->cfg.precond >= 1; }
+static const CoarseGrid &c_of(const pprts_b200_solver *s) { return s->cg; }
 // PPRTS_B200_KRYLOV_TRACE: residual history of the diffuse solves on stderr (tools/krylov_trace.py)
 static bool krylov_trace() { static const bool on = getenv("PPRTS_B200_KRYLOV_TRACE") != nullptr; return on; }
 
@@ -1250,7 +1251,7 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
       if (s->cg_on) {
         const CoarseGrid &c = s->cg;
         LAUNCH(s, FAM_PRECOND, (k_cg_build<L, CT>), nblk(c.ncc, 64), 64, g, c, s->n1d, (const CT *)s->f2f, s->a11, s->a12, s->cg_coef);
-        LAUNCH(s, FAM_PRECOND, k_cg_setup, nblk(c.ncolC, 64), 64, g, c, (const double *)s->albedo, (const float *)s->cg_coef, s->cg_R, s->cg_inv);
+        LAUNCH(s, FAM_PRECOND, k_cg_setup, nblk(c.ncolC, 64), 64, g, c, (const double *)s->albedo, (const float *)s->cg_coef, (float4 *)s->cg_sA, (float2 *)s->cg_sB, s->cg_R);
       }
       s->prec_ready = true;
     }
@@ -1259,18 +1260,23 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
     const int bd = column_block(s, k_prec_down<L, CT, VT>, &s->prec_block[slot + 1]);
     const VT *pR, *pI;  // the sweeps read R and Inv in the precision of their vectors
     if constexpr (std::is_same<VT, float>::value) { pR = s->precRf; pI = s->precInvf; } else { pR = s->precR; pI = s->precInv; }
-    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           pR, pI, r, z, (int)(s->cfg.precond != 2));
-    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           pR, pI, r, z, (int)(s->cfg.precond != 2));
-    if (s->cg_on) {  // z += P (P^T A P)_col^-1 P^T r
+    // coarse-grid correction: xc = (P^T A P)_col^-1 P^T r first, the sweeps add P xc to z where they store its entries
+    CgAdd add{nullptr, 0, 0, 1, 1};
+    static const bool cg_unfused = getenv("PPRTS_B200_CG_UNFUSED") != nullptr;  // separate prolongation pass, for comparison
+    if (s->cg_on) {
       const CoarseGrid &c = s->cg;
-      LAUNCH(s, FAM_PRECOND, (k_cg_restrict<L, VT>), nblk(c.nclev, 128), 128, g, c, r, (const float *)s->cg_coef, s->cg_rbar, s->cg_e);
-      LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float *)s->cg_coef, (const float *)s->cg_R,
-             (const float *)s->cg_inv, (const float *)s->cg_rbar, (const float *)s->cg_e, s->cg_x);
+      LAUNCH(s, FAM_PRECOND, (k_cg_restrict<L, VT>), nblk(c.nclev, 128), 128, g, c, r, (const float *)s->cg_coef, s->cg_rbar, (float2 *)s->cg_e);
+      LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float4 *)s->cg_sA, (const float2 *)s->cg_sB,
+             (const float *)s->cg_R, (const float *)s->cg_rbar, (const float2 *)s->cg_e, s->cg_x);
       LAUNCH(s, FAM_PRECOND, (k_cg_sides<L>), nblk(c.nclev, 128), 128, c, (const float *)s->cg_coef, (const float *)s->cg_rbar, s->cg_x);
-      LAUNCH(s, FAM_PRECOND, (k_cg_prolong<VT>), vec_grid((long)L::Nf * g.nlev / 4), VEC_BLOCK, g, c, (int)L::Nf, (const float *)s->cg_x, z);
+      if (!cg_unfused) add = CgAdd{s->cg_x, c.nclev, c.ncolC, c.AG, c.NxC};
     }
+    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+           pR, pI, r, z, (int)(s->cfg.precond != 2), add);
+    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+           pR, pI, r, z, (int)(s->cfg.precond != 2), add);
+    if (s->cg_on && cg_unfused)
+      LAUNCH(s, FAM_PRECOND, (k_cg_prolong<VT>), vec_grid((long)L::Nf * g.nlev / 4), VEC_BLOCK, g, c_of(s), (int)L::Nf, (const float *)s->cg_x, z);
   } else {  // several up/down pairs of top streams (3_24): block recurrence, no software pipelining
     const Grid &g = s->g;
     if (!s->prec_ready) {

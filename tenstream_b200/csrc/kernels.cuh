@@ -2034,6 +2034,58 @@ k_cg_restrict(Grid g, CoarseGrid cg, const VT *__restrict__ r, const float *__re
   }
 }
 
+// The same for a coarser level whose aggregates are unions of the parent level's (AG a multiple of the parent's): rbar
+// is the cell-count weighted mean of the parent's rbar -- a few MB instead of another pass over the fine vector.
+template <class L>
+__global__ void __launch_bounds__(128)
+k_cg_restrict_coarse(Grid g, CoarseGrid pc, CoarseGrid cg, const float *__restrict__ prbar, const float *__restrict__ coef,
+                     float *__restrict__ rbar, float2 *__restrict__ f) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, NS = 2 * L::Nfs;
+  using CL = CgLayout<NS>;
+  const long lc = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= cg.nclev) return;
+  const int I = (int)(lc % cg.NxC), J = (int)((lc / cg.NxC) % cg.NyC), k = (int)(lc / cg.ncolC);
+  const int ratio = cg.AG / pc.AG;
+  const int I0 = I * ratio, I1 = min(pc.NxC, I0 + ratio), J0 = J * ratio, J1 = min(pc.NyC, J0 + ratio);
+  float rb[Nf], fd = 0.f, wsum = 0.f;
+#pragma unroll
+  for (int d = 0; d < Nf; ++d) rb[d] = 0.f;
+  for (int jj = J0; jj < J1; ++jj) {
+    const float wj = (float)(min(g.Ny, (jj + 1) * pc.AG) - jj * pc.AG);
+    for (int ii = I0; ii < I1; ++ii) {
+      const float w = wj * (float)(min(g.Nx, (ii + 1) * pc.AG) - ii * pc.AG);
+      const long pl = ((long)k * pc.NyC + jj) * pc.NxC + ii;
+      wsum += w;
+#pragma unroll
+      for (int d = 0; d < Nf; ++d) rb[d] = fmaf(w, prbar[(long)d * pc.nclev + pl], rb[d]);
+      if (k < cg.Nz) fd = fmaf(w, prbar[pc.nclev + pl + pc.ncolC], fd);
+    }
+  }
+  const float sc = 1.f / wsum;
+#pragma unroll
+  for (int d = 0; d < Nf; ++d) { rb[d] *= sc; rbar[(long)d * cg.nclev + lc] = rb[d]; }
+  if (k < cg.Nz) {
+    float fu = rb[0];
+    fd *= sc;
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+      fu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + lc], rb[Nft + p], fu);
+      fd = fmaf(coef[(long)(CL::GD + p) * cg.ncc + lc], rb[Nft + p], fd);
+    }
+    f[lc] = make_float2(fu, fd);
+  }
+}
+// xc(parent level) += P xc(coarser level): the corrections of all levels reach z through the finest one
+__global__ void k_cg_add_coarser(CoarseGrid pc, CoarseGrid cg, int nd, const float *__restrict__ xc, float *__restrict__ pxc) {
+  const long n = (long)nd * pc.nclev;
+  const int ratio = cg.AG / pc.AG;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const long d = q / pc.nclev, l = q - d * pc.nclev;
+    const int i = (int)(l % pc.NxC), j = (int)((l / pc.NxC) % pc.NyC), k = (int)(l / pc.ncolC);
+    pxc[q] += xc[d * cg.nclev + ((long)k * cg.NyC + j / ratio) * cg.NxC + i / ratio];
+  }
+}
+
 // the condensed two-stream column of aggregates: upward sweep for S_k, downward sweep for D, U (xc planes 0 and 1).
 // One thread per aggregate column; the inputs of CG_B levels are loaded together (they do not depend on the recurrence),
 // then the recurrence runs through them with one fma per level.

@@ -2153,6 +2153,85 @@ k_cg_column(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__restri
   }
 }
 
+// The same column solve with ONE WARP per aggregate column (Nz <= 32 CG_C): both sweeps are first-order linear
+// recurrences with known coefficients, i.e. scans over affine maps.  Lane l owns the levels [l C, (l+1) C), composes
+// their maps, a warp scan (5 shuffle rounds) hands every lane the value entering its chunk, the lane replays its levels.
+// All loads of a sweep are issued at once: the latency of the kernel is a few memory round trips instead of one per
+// CG_B levels -- it matters because a column of aggregates is a short job (4096 columns at C2) on a latency-bound path
+// that runs twice per Krylov iteration.
+#define CG_C 8
+__global__ void __launch_bounds__(128)
+k_cg_column_scan(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__restrict__ sB, const float *__restrict__ Rtop,
+                 const float *__restrict__ rbar, const float2 *__restrict__ f, float *__restrict__ xc) {
+  constexpr unsigned int FULL = 0xffffffffu;
+  const long col = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (col >= cg.ncolC) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const long nl = cg.nclev, st = cg.ncolC;
+  const int Nz = cg.Nz, C = (Nz + 31) / 32;
+  const int k0 = lane * C, k1 = min(Nz, k0 + C);  // my levels [k0, k1)
+  float al[CG_C], be[CG_C], pp[CG_C], qa[CG_C], qb[CG_C], R1[CG_C], Sv[CG_C + 1];
+#pragma unroll
+  for (int u = 0; u < CG_C; ++u) {
+    const int k = k0 + u;
+    al[u] = 1.f; be[u] = 0.f; pp[u] = 1.f; qa[u] = 0.f; qb[u] = 0.f; R1[u] = 0.f;
+    if (u < C && k < k1) {
+      const long cc = (long)k * st + col;
+      const float4 a = sA[cc];
+      const float2 b = sB[cc];
+      const float2 ff = f[cc];
+      al[u] = a.x; be[u] = fmaf(a.y, ff.y, ff.x);
+      pp[u] = a.z; qa[u] = a.w; qb[u] = b.x * ff.y; R1[u] = b.y;
+    }
+  }
+  const float S_bottom = rbar[(long)Nz * st + col], D_top = rbar[nl + col], R0 = Rtop[col];
+  // ---- upward: S_k = al_k S_{k+1} + be_k; my chunk maps S(k1) to S(k0)
+  float m = 1.f, b = 0.f;
+#pragma unroll
+  for (int u = CG_C - 1; u >= 0; --u) { b = fmaf(al[u], b, be[u]); m *= al[u]; }  // identity entries are harmless
+  float sm = m, sb = b;  // suffix composition over lanes >= mine
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float om = __shfl_down_sync(FULL, sm, o), ob = __shfl_down_sync(FULL, sb, o);
+    if (lane + o < 32) { sb = fmaf(sm, ob, sb); sm *= om; }
+  }
+  float Sin = __shfl_down_sync(FULL, fmaf(sm, S_bottom, sb), 1);  // S leaving the chunk of lane + 1 = entering mine
+  if (lane == 31) Sin = S_bottom;
+  Sv[CG_C] = Sin;
+#pragma unroll
+  for (int u = CG_C - 1; u >= 0; --u) Sv[u] = fmaf(al[u], Sv[u + 1], be[u]);  // Sv[u] = S(k0 + u) for u < my count
+  // note: entries u >= k1 - k0 are identity maps, so Sv[u] = Sin there and Sv[k1 - k0] = S(k1) as it should
+  // ---- downward: D_{k+1} = pp_k D_k + (qa_k S_{k+1} + qb_k); my chunk maps D(k0) to D(k1)
+  float q[CG_C];
+#pragma unroll
+  for (int u = 0; u < CG_C; ++u) q[u] = fmaf(qa[u], Sv[u + 1], qb[u]);
+  m = 1.f; b = 0.f;
+#pragma unroll
+  for (int u = 0; u < CG_C; ++u) { b = fmaf(pp[u], b, q[u]); m *= pp[u]; }
+  float pm = m, pb = b;  // prefix composition over lanes <= mine
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float om = __shfl_up_sync(FULL, pm, o), ob = __shfl_up_sync(FULL, pb, o);
+    if (lane >= o) { pb = fmaf(pm, ob, pb); pm *= om; }
+  }
+  float D = __shfl_up_sync(FULL, fmaf(pm, D_top, pb), 1);  // D leaving the chunk of lane - 1 = entering mine
+  if (lane == 0) {
+    D = D_top;
+    xc[nl + col] = D_top;
+    xc[col] = fmaf(R0, D_top, Sv[0]);
+  }
+#pragma unroll
+  for (int u = 0; u < CG_C; ++u) {
+    const int k = k0 + u;
+    if (u < C && k < k1) {
+      const long l1 = (long)(k + 1) * st + col;
+      D = fmaf(pp[u], D, q[u]);
+      xc[l1] = fmaf(R1[u], D, Sv[u + 1]);
+      xc[nl + l1] = D;
+    }
+  }
+}
+
 // side streams of every coarse cell from its top inputs: s = wu U(k+1) + wd D(k) + W rbar_s
 template <class L>
 __global__ void __launch_bounds__(128)

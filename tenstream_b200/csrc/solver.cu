@@ -1289,8 +1289,13 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
     for (int l = 0; l < s->ncgl; ++l) {  // aggregate-column solves, independent of each other
       auto &lv = s->cgl[l];
       const CoarseGrid &c = lv.c;
-      LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float4 *)lv.sA, (const float2 *)lv.sB,
-             (const float *)lv.R, (const float *)lv.rbar, (const float2 *)lv.e, lv.x);
+      static const bool cg_serial = getenv("PPRTS_B200_CG_SERIAL_COLUMN") != nullptr;
+      if (g.Nz <= 32 * CG_C && !cg_serial)
+        LAUNCH(s, FAM_PRECOND, k_cg_column_scan, nblk(c.ncolC * 32, 128), 128, c, (const float4 *)lv.sA, (const float2 *)lv.sB,
+               (const float *)lv.R, (const float *)lv.rbar, (const float2 *)lv.e, lv.x);
+      else
+        LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float4 *)lv.sA, (const float2 *)lv.sB,
+               (const float *)lv.R, (const float *)lv.rbar, (const float2 *)lv.e, lv.x);
       LAUNCH(s, FAM_PRECOND, (k_cg_sides<L>), nblk(c.nclev, 128), 128, c, (const float *)lv.coef, (const float *)lv.rbar, lv.x);
     }
     for (int l = s->ncgl - 1; l >= 1; --l)  // coarser corrections are handed down to the finest level

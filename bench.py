@@ -342,7 +342,7 @@ def run_ours(args):
                        "bands_per_step_per_gpu": len(bands), "cells": ncell, "coefficient_storage": "fp32",
                        "state": ("fp64 solution + fp64 true residual (iterative refinement), fp32 Krylov work vectors"
                                  if mixed else "fp64"), "tolerances": "reference defaults rtol=1e-5 atol=1e-4*Nx*Ny*(Nz+1)",
-                       "krylov": "BiCGStab + vertical-line preconditioner", "start": "cold (zero initial guess)",
+                       "krylov": "BiCGStab, right-preconditioned: exact vertical-line (column) solve + additive coarse-grid correction on 4x4 and 8x8 column aggregates", "start": "cold (zero initial guess)",
                        "l2": "working set per step (3.4 GB coefficients + 4 GB vectors) is far larger than the 126 MB L2",
                        "parallelism": f"bands sharded over {world} GPU(s), one NCCL all-reduce of the flux sums per step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
@@ -408,16 +408,19 @@ def leg_variant(P, torch, dist, lut, sc, bands, local, args, krylov_fp32, rtol=N
     for slot, b in enumerate(bands):
         s.stage_optical_properties(slot, b["albedo"], b["kabs"], b["ksca"], b["g"], b["planck"], b["planck_srfc"])
 
+    its = {}
+
     def step():
         s.reset_accumulator()
         for slot, b in enumerate(bands):
             s.set_optical_properties_staged(slot)
             P.solve_pprts(s, not b["lsolar"], b["lsolar"], b["edirTOA"], b["uid"])
             s.accumulate_result(b["uid"], 1.0)
+            its[b["name"]] = s.info(b["uid"])["niter_diff"]   # one solution container is reused (keep_solutions = 0)
     steps = steps or args.steps
     ms, _ = Timer(torch, dist, 1, s).run(step, steps, 3)
     out = {"value": Nz * Nx * Ny * len(bands) * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
-           "krylov_iterations": [s.info(b["uid"])["niter_diff"] for b in bands]}
+           "krylov_iterations": [its[b["name"]] for b in bands]}
     P.destroy_pprts(s)
     return out
 
@@ -637,12 +640,15 @@ def leg_decomp(P, torch, dist, world, rank, local, lut, args, nx, ny, nz, dx, dz
         s.stage_optical_properties(slot, b["albedo"], b["kabs"], b["ksca"], b["g"], b["planck"], b["planck_srfc"])
     del sc["kabs"], sc["ksca"], sc["g"], sc["kabs_th"], sc["ksca_th"], sc["g_th"], sc["planck"]
 
+    seen = {}
+
     def step():
         s.reset_accumulator()
         for slot, b in enumerate(bands):
             s.set_optical_properties_staged(slot)
             P.solve_pprts(s, not b["lsolar"], b["lsolar"], b["edirTOA"], b["uid"])
             s.accumulate_result(b["uid"], 1.0)
+            seen[b["name"]] = s.info(b["uid"])   # one solution container is reused (keep_solutions = 0)
 
     # the warm-up step doubles as the per-family kernel timing (CUDA events around every launch)
     s.kernel_stats(reset=True)
@@ -651,8 +657,8 @@ def leg_decomp(P, torch, dist, world, rank, local, lut, args, nx, ny, nz, dx, dz
         step()
     stats = s.kernel_stats(reset=True)
     s.enable_kernel_timing(False)
-    iters = [{"band": b["name"], "edir_passes": s.info(b["uid"])["niter_dir"] if b["lsolar"] else 0,
-              "krylov_iterations": s.info(b["uid"])["niter_diff"]} for b in bands]
+    iters = [{"band": b["name"], "edir_passes": seen[b["name"]]["niter_dir"] if b["lsolar"] else 0,
+              "krylov_iterations": seen[b["name"]]["niter_diff"]} for b in bands]
     ms, launches = Timer(torch, dist, world, s).run(step, steps, 0)
     ncell_local = nz * dec.xm * dec.ym
     Sv = 4 if mixed else 8

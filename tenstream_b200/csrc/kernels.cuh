@@ -9,6 +9,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "geometric_coeffs.cuh"
 
 #define PB_PI 3.14159265358979323846
@@ -1603,6 +1604,64 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
   }
 }
 
+// Packed coefficients of the column sweeps on fp32 vectors.  The sweeps read 10 (up) and 26 (down) of a cell's 100
+// diff2diff entries, plus R and Inv: scattered 128-byte pieces of the 51 KB coefficient tile, 160 B per cell and
+// application -- more than half of what the sweeps move.  The preconditioner only has to be a good approximation of
+// the column operator, not the operator itself (the Krylov solver sees A through the MatMult alone), so its copy of the
+// coefficients is kept in HALF precision, pairwise (half2 planes, tile-blocked like T): 24 B (up) + 56 B (down) per cell.
+//   up   (PREC_PU planes): (tuu, tud) | (T(0,in_q), T(1,in_q)) q = 0..Nfs-1 | (R_k, Inv_k)
+//   down (PREC_PD planes): (tdd, tud) | per outward dof o: (T(o,0), T(o,1)), (T(o,in_0), T(o,in_1)), (T(o,in_2), T(o,in_3)) | (R_{k+1}, Inv_k)
+template <class L> struct PrecPack {
+  static constexpr int Nfs = L::Nfs;
+  static constexpr int PU = 2 + Nfs, PD = 2 + Nfs * ((2 + Nfs) / 2);
+  static_assert(Nfs % 2 == 0, "outward rows are packed pairwise");
+};
+template <class L, class CT>
+__global__ void __launch_bounds__(128)
+k_prec_pack(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
+            const float *__restrict__ R, const float *__restrict__ inv, __half2 *__restrict__ PU, __half2 *__restrict__ PD) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  using PK = PrecPack<L>;
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.ncell) return;
+  const int k = (int)(c / g.ncol);
+  const long pu = (c >> PB_TILE_SHIFT) * (long)(PK::PU * PB_TILE) + (c & (PB_TILE - 1));
+  const long pd = (c >> PB_TILE_SHIFT) * (long)(PK::PD * PB_TILE) + (c & (PB_TILE - 1));
+  const float Rc = R[c], R1 = R[c + g.ncol], iv = inv[c];
+  PU[pu + (PK::PU - 1) * PB_TILE] = __floats2half2_rn(Rc, iv);
+  PD[pd + (PK::PD - 1) * PB_TILE] = __floats2half2_rn(R1, iv);
+  if (is1d(g, n1d, k)) {
+    const float t = (float)a11[c], rr = (float)a12[c];
+    PU[pu] = __floats2half2_rn(t, rr);
+    PD[pd] = __floats2half2_rn(t, rr);
+    for (int n = 1; n < PK::PU - 1; ++n) PU[pu + n * PB_TILE] = __floats2half2_rn(0.f, 0.f);
+    for (int n = 1; n < PK::PD - 1; ++n) PD[pd + n * PB_TILE] = __floats2half2_rn(0.f, 0.f);
+    return;
+  }
+  const long cb = cbase<Nf * Nf>(c);
+  auto Tv = [&](int dst, int src) { return (float)T[cb + (dst * Nf + src) * PB_TILE]; };
+  PU[pu] = __floats2half2_rn(Tv(0, 0), Tv(1, 0));
+  PD[pd] = __floats2half2_rn(Tv(1, 1), Tv(1, 0));
+  int ins[Nfs], q = 0;
+#pragma unroll
+  for (int d = 0; d < 2 * Nfs; ++d)
+    if (L::side_in(d % Nfs)) { ins[q] = Nft + d; ++q; }
+#pragma unroll
+  for (int qq = 0; qq < Nfs; ++qq) PU[pu + (1 + qq) * PB_TILE] = __floats2half2_rn(Tv(0, ins[qq]), Tv(1, ins[qq]));
+  int o = 0;
+#pragma unroll
+  for (int d = 0; d < 2 * Nfs; ++d) {
+    if (!L::side_in(d % Nfs)) {
+      const int dof = Nft + d, base = 1 + o * ((2 + Nfs) / 2);
+      PD[pd + base * PB_TILE] = __floats2half2_rn(Tv(dof, 0), Tv(dof, 1));
+#pragma unroll
+      for (int h = 0; h < Nfs / 2; ++h)
+        PD[pd + (base + 1 + h) * PB_TILE] = __floats2half2_rn(Tv(dof, ins[2 * h]), Tv(dof, ins[2 * h + 1]));
+      ++o;
+    }
+  }
+}
+
 // coefficient -> arithmetic type of the column kernels: exact widening for fp64 vectors, as stored / rounded for fp32
 template <class AT, class T>
 __device__ __forceinline__ AT cw(T c) {
@@ -1629,14 +1688,42 @@ template <class L, class CT, class VT>
 __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                              const double *__restrict__ a11, const double *__restrict__ a12,
                                              const VT *__restrict__ R, const VT *__restrict__ inv,
-                                             const VT *__restrict__ r, const CgAdd &cg, long ccol, PrecUpIn<L, CT, VT> &in) {
+                                             const VT *__restrict__ r, const CgAdd &cg, long ccol, const __half2 *__restrict__ PU,
+                                             PrecUpIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
   in.fU = r[0 * g.nlev + c];
   in.fD = r[1 * g.nlev + l1];
+  const bool l1d = is1d(g, n1d, k);
+  if (PU) {  // packed half-precision copy (fp32 sweeps): warp-uniform branch
+    using PK = PrecPack<L>;
+    const long pu = (c >> PB_TILE_SHIFT) * (long)(PK::PU * PB_TILE) + (c & (PB_TILE - 1));
+    const float2 a = __half22float2(PU[pu]), ri = __half22float2(PU[pu + (PK::PU - 1) * PB_TILE]);
+    in.tuu = (VT)a.x; in.tud = (VT)a.y; in.Rc = (VT)ri.x; in.iv = (VT)ri.y;
+#pragma unroll
+    for (int d = 0; d < 2 * Nfs; ++d) {
+      in.xs[d] = (VT)0;
+      if (cg.xc && (l1d || L::side_in(d % Nfs))) in.xs[d] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + (long)k * cg.ncolC + ccol];
+    }
+    if (l1d) {
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+    } else {
+      int q = 0;
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        if (L::side_in(d % Nfs)) {
+          in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+          const float2 t = __half22float2(PU[pu + (1 + q) * PB_TILE]);
+          in.t0[q] = (CT)t.x; in.t1[q] = (CT)t.y;
+          ++q;
+        }
+      }
+    }
+    return;
+  }
   in.iv = (VT)inv[c];
   in.Rc = (VT)R[c];
-  const bool l1d = is1d(g, n1d, k);
 #pragma unroll
   for (int d = 0; d < 2 * Nfs; ++d) {
     in.xs[d] = (VT)0;
@@ -1666,7 +1753,7 @@ template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
           const VT *__restrict__ R, const VT *__restrict__ inv, const VT *__restrict__ r,
-          VT *__restrict__ z, int sides, CgAdd cg) {
+          VT *__restrict__ z, int sides, CgAdd cg, const __half2 *__restrict__ PU) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   static_assert(Nft == 2, "column preconditioner needs one up/down pair of top streams");
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1711,16 +1798,16 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   // under the one-wave register cap and was slower: it keeps the single look-ahead.)
   PrecUpIn<L, CT, VT> A, B, C3;
   int k = g.Nz - 1;
-  prec_up_load<L, CT, VT>(g, n1d, k, col, T, a11, a12, R, inv, r, cg, ccol, A);
-  if (k >= 1) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, cg, ccol, B);
+  prec_up_load<L, CT, VT>(g, n1d, k, col, T, a11, a12, R, inv, r, cg, ccol, PU, A);
+  if (k >= 1) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, cg, ccol, PU, B);
   while (k >= 0) {
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, C3);
+    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, C3);
     level(k, A);
     if (--k < 0) break;
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, A);
+    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, A);
     level(k, B);
     if (--k < 0) break;
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, B);
+    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, B);
     level(k, C3);
     --k;
   }
@@ -1739,13 +1826,15 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
                                                const double *__restrict__ a11, const double *__restrict__ a12,
                                                const VT *__restrict__ R, const VT *__restrict__ inv,
                                                const VT *__restrict__ r, const VT *z, const CgAdd &cg, long ccol,
-                                               PrecDownIn<L, CT, VT> &in) {
+                                               const __half2 *__restrict__ PD, PrecDownIn<L, CT, VT> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
   in.S1 = z[0 * g.nlev + l1];
   in.fD = z[1 * g.nlev + l1];
-  in.iv = (VT)inv[c];
-  in.R1 = (VT)R[l1];
+  if (!PD) {
+    in.iv = (VT)inv[c];
+    in.R1 = (VT)R[l1];
+  }
   in.xU = (VT)0; in.xD = (VT)0;
 #pragma unroll
   for (int o = 0; o < Nfs; ++o) in.xo[o] = (VT)0;
@@ -1759,6 +1848,25 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
       for (int d = 0; d < 2 * Nfs; ++d)
         if (!L::side_in(d % Nfs)) { in.xo[o] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + lc]; ++o; }
     }
+  }
+  if (PD) {  // packed half-precision copy (fp32 sweeps): warp-uniform branch
+    using PK = PrecPack<L>;
+    const long pd = (c >> PB_TILE_SHIFT) * (long)(PK::PD * PB_TILE) + (c & (PB_TILE - 1));
+    const float2 a = __half22float2(PD[pd]), ri = __half22float2(PD[pd + (PK::PD - 1) * PB_TILE]);
+    in.tdd = (VT)a.x; in.tud = (VT)a.y; in.R1 = (VT)ri.x; in.iv = (VT)ri.y;
+    if (!is1d(g, n1d, k)) {
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
+      constexpr int per = (2 + Nfs) / 2;
+#pragma unroll
+      for (int o = 0; o < Nfs; ++o)
+#pragma unroll
+        for (int h = 0; h < per; ++h) {
+          const float2 t = __half22float2(PD[pd + (1 + o * per + h) * PB_TILE]);
+          in.tt[o][2 * h] = (CT)t.x; in.tt[o][2 * h + 1] = (CT)t.y;
+        }
+    }
+    return;
   }
   if (is1d(g, n1d, k)) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
   else {
@@ -1787,7 +1895,7 @@ template <class L, class CT, class VT = double>
 __global__ void __launch_bounds__(PREC_BLOCK, 8)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const VT *__restrict__ R, const VT *__restrict__ inv,
-            const VT *__restrict__ r, VT *z, int sides, CgAdd cg) {
+            const VT *__restrict__ r, VT *z, int sides, CgAdd cg, const __half2 *__restrict__ PD) {
   constexpr int Nft = L::Nft, Nfs = L::Nfs;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= g.ncol) return;
@@ -1797,10 +1905,10 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
   VT U = (VT)R[col] * D + z[0 * g.nlev + col];
   z[0 * g.nlev + col] = U + (cg.xc ? (VT)cg.xc[ccol] : (VT)0);
   PrecDownIn<L, CT, VT> cur, nxt;
-  prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, cur);
+  prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, cur);
   for (int k = 0; k < g.Nz; ++k) {
     // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
-    if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, nxt);
+    if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     const VT S1 = cur.S1;
     const VT D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
@@ -2075,17 +2183,6 @@ k_cg_restrict_coarse(Grid g, CoarseGrid pc, CoarseGrid cg, const float *__restri
     f[lc] = make_float2(fu, fd);
   }
 }
-// xc(parent level) += P xc(coarser level): the corrections of all levels reach z through the finest one
-__global__ void k_cg_add_coarser(CoarseGrid pc, CoarseGrid cg, int nd, const float *__restrict__ xc, float *__restrict__ pxc) {
-  const long n = (long)nd * pc.nclev;
-  const int ratio = cg.AG / pc.AG;
-  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
-    const long d = q / pc.nclev, l = q - d * pc.nclev;
-    const int i = (int)(l % pc.NxC), j = (int)((l / pc.NxC) % pc.NyC), k = (int)(l / pc.ncolC);
-    pxc[q] += xc[d * cg.nclev + ((long)k * cg.NyC + j / ratio) * cg.NxC + i / ratio];
-  }
-}
-
 // the condensed two-stream column of aggregates: upward sweep for S_k, downward sweep for D, U (xc planes 0 and 1).
 // One thread per aggregate column; the inputs of CG_B levels are loaded together (they do not depend on the recurrence),
 // then the recurrence runs through them with one fma per level.
@@ -2232,17 +2329,27 @@ k_cg_column_scan(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__r
   }
 }
 
-// side streams of every coarse cell from its top inputs: s = wu U(k+1) + wd D(k) + W rbar_s
+// side streams of every coarse cell from its top inputs: s = wu U(k+1) + wd D(k) + W rbar_s.  With a coarser level (its
+// solve already complete in cxc) the thread also hands that level's correction down: it adds P cxc to its sides and to
+// the two top entries only it reads -- U(k+1), D(k) -- so that the corrections of all levels reach z through the finest.
 template <class L>
 __global__ void __launch_bounds__(128)
-k_cg_sides(CoarseGrid cg, const float *__restrict__ coef, const float *__restrict__ rbar, float *__restrict__ xc) {
+k_cg_sides(CoarseGrid cg, const float *__restrict__ coef, const float *__restrict__ rbar, float *__restrict__ xc,
+           CoarseGrid cc_grid, const float *__restrict__ cxc) {
   constexpr int Nft = L::Nft, NS = 2 * L::Nfs;
   using CL = CgLayout<NS>;
   const long lc = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lc >= cg.nclev) return;
+  long pl = 0;  // my entry on the coarser level
+  if (cxc) {
+    const int ratio = cc_grid.AG / cg.AG;
+    const int I = (int)(lc % cg.NxC), J = (int)((lc / cg.NxC) % cg.NyC), k = (int)(lc / cg.ncolC);
+    pl = ((long)k * cc_grid.NyC + J / ratio) * cc_grid.NxC + I / ratio;
+  }
   if (lc >= cg.ncc) {  // below the ground: no coupling, the fine solve has these rows already
 #pragma unroll
     for (int p = 0; p < NS; ++p) xc[(long)(Nft + p) * cg.nclev + lc] = 0.f;
+    if (cxc) xc[cg.nclev + lc] += cxc[cc_grid.nclev + pl];  // D at the surface: read by no cell
     return;
   }
   const long cc = lc;
@@ -2255,7 +2362,13 @@ k_cg_sides(CoarseGrid cg, const float *__restrict__ coef, const float *__restric
     float acc = coef[(long)(CL::WU + p) * cg.ncc + cc] * u + coef[(long)(CL::WD + p) * cg.ncc + cc] * d;
 #pragma unroll
     for (int q = 0; q < NS; ++q) acc = fmaf(coef[(long)(CL::W + p * NS + q) * cg.ncc + cc], rs[q], acc);
+    if (cxc) acc += cxc[(long)(Nft + p) * cc_grid.nclev + pl];
     xc[(long)(Nft + p) * cg.nclev + lc] = acc;
+  }
+  if (cxc) {
+    xc[lc + cg.ncolC] = u + cxc[pl + cc_grid.ncolC];
+    xc[cg.nclev + lc] = d + cxc[cc_grid.nclev + pl];
+    if (lc < cg.ncolC) xc[lc] += cxc[pl];  // U at the top of the column: read by no cell
   }
 }
 

@@ -1286,7 +1286,7 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
         LAUNCH(s, FAM_PRECOND, (k_cg_restrict_coarse<L>), nblk(c.nclev, 128), 128, g, s->cgl[l - 1].c, c, (const float *)s->cgl[l - 1].rbar,
                (const float *)lv.coef, lv.rbar, (float2 *)lv.e);
     }
-    for (int l = 0; l < s->ncgl; ++l) {  // aggregate-column solves, independent of each other
+    for (int l = s->ncgl - 1; l >= 0; --l) {  // aggregate-column solves, coarsest first: each level hands its result down
       auto &lv = s->cgl[l];
       const CoarseGrid &c = lv.c;
       static const bool cg_serial = getenv("PPRTS_B200_CG_SERIAL_COLUMN") != nullptr;
@@ -1296,11 +1296,10 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
       else
         LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float4 *)lv.sA, (const float2 *)lv.sB,
                (const float *)lv.R, (const float *)lv.rbar, (const float2 *)lv.e, lv.x);
-      LAUNCH(s, FAM_PRECOND, (k_cg_sides<L>), nblk(c.nclev, 128), 128, c, (const float *)lv.coef, (const float *)lv.rbar, lv.x);
+      const bool coarser = l + 1 < s->ncgl;
+      LAUNCH(s, FAM_PRECOND, (k_cg_sides<L>), nblk(c.nclev, 128), 128, c, (const float *)lv.coef, (const float *)lv.rbar, lv.x,
+             coarser ? s->cgl[l + 1].c : c, coarser ? (const float *)s->cgl[l + 1].x : (const float *)nullptr);
     }
-    for (int l = s->ncgl - 1; l >= 1; --l)  // coarser corrections are handed down to the finest level
-      LAUNCH(s, FAM_PRECOND, k_cg_add_coarser, vec_grid((long)L::Nf * s->cgl[l - 1].c.nclev), VEC_BLOCK, s->cgl[l - 1].c, s->cgl[l].c,
-             (int)L::Nf, (const float *)s->cgl[l].x, s->cgl[l - 1].x);
     if (s->ncgl > 0 && !cg_unfused) { const CoarseGrid &c = s->cgl[0].c; add = CgAdd{s->cgl[0].x, c.nclev, c.ncolC, c.AG, c.NxC}; }
     LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
            pR, pI, r, z, (int)(s->cfg.precond != 2), add);
@@ -1775,6 +1774,7 @@ static int solve_impl(pprts_b200_solver *s, int lthermal, int lsolar, double edi
   if ((rc = need_comm(s))) return rc;
   if ((rc = ensure_coeffs(s, sol.lsolar_rad))) return rc;
   if ((rc = scale_flx(s, sol, false))) return rc;
+  if (!sol.lsolar_rad) { sol.niter_dir = 0; sol.res_dir = 0.0; }  // a reused container must not report the previous band's direct solve
   if (sol.lsolar_rad && (rc = solve_edir(s, sol, edirTOA))) return rc;
   if ((rc = setup_b(s, sol))) return rc;
   // b_norm = sum(abs(b)); skip the diffuse solve if < atol (src/pprts.F90:2774-2785)

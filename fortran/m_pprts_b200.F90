@@ -134,6 +134,31 @@ module m_pprts_b200
       type(c_ptr), value :: solver, edir, incoming, outgoing
       integer(c_int), value :: uid
     end function
+    ! overlapped host transfers for a caller's own band loop (INTEGRATION.md section 3)
+    integer(c_int) function c_stage_optical_properties_async(solver, slot, albedo, kabs, ksca, g, planck, planck_srfc, albedo_2d) &
+        & bind(c, name='pprts_b200_stage_optical_properties_async')
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: solver
+      integer(c_int), value :: slot
+      real(c_double), value :: albedo
+      type(c_ptr), value :: kabs, ksca, g, planck, planck_srfc, albedo_2d   ! c_loc of the arrays, c_null_ptr if absent
+    end function
+    integer(c_int) function c_set_optical_properties_staged(solver, slot, ldelta_scaling) &
+        & bind(c, name='pprts_b200_set_optical_properties_staged')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver
+      integer(c_int), value :: slot, ldelta_scaling
+    end function
+    integer(c_int) function c_get_result_async(solver, uid, edn, eup, abso, edir) bind(c, name='pprts_b200_get_result_async')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver
+      integer(c_int), value :: uid
+      type(c_ptr), value :: edn, eup, abso, edir
+    end function
+    integer(c_int) function c_wait_results(solver) bind(c, name='pprts_b200_wait_results')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver
+    end function
     function c_last_error() bind(c, name='pprts_b200_last_error') result(msg)
       import; type(c_ptr) :: msg
     end function

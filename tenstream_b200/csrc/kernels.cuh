@@ -1611,6 +1611,15 @@ k_prec_setup(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict
 // coefficients is kept in HALF precision, pairwise (half2 planes, tile-blocked like T): 24 B (up) + 56 B (down) per cell.
 //   up   (PREC_PU planes): (tuu, tud) | (T(0,in_q), T(1,in_q)) q = 0..Nfs-1 | (R_k, Inv_k)
 //   down (PREC_PD planes): (tdd, tud) | per outward dof o: (T(o,0), T(o,1)), (T(o,in_0), T(o,in_1)), (T(o,in_2), T(o,in_3)) | (R_{k+1}, Inv_k)
+// Unpacking on the integer ALU: cvt.f32.f16 runs on the XU pipe (like cvt.f64.f32, common.cuh) and 20-28 conversions per
+// level made the packed sweeps SLOWER than the fp32 ones (measured: 2.0 vs 1.85 ms per Krylov iteration).  All packed
+// values are non-negative and far from the half-precision overflow, so a normal half widens with a shift and an exponent
+// re-bias; zeros and subnormals (< 6e-5) come out as values in [3e-5, 6e-5) -- an irrelevant perturbation of a
+// preconditioner, and nothing the operator itself ever sees.
+__device__ __forceinline__ float2 unpack_half2_pos(const __half2 h) {
+  const unsigned int w = *reinterpret_cast<const unsigned int *>(&h);
+  return make_float2(__uint_as_float(((w & 0xffffu) << 13) + 0x38000000u), __uint_as_float(((w >> 3) & 0x0fffe000u) + 0x38000000u));
+}
 template <class L> struct PrecPack {
   static constexpr int Nfs = L::Nfs;
   static constexpr int PU = 2 + Nfs, PD = 2 + Nfs * ((2 + Nfs) / 2);
@@ -1676,35 +1685,39 @@ struct CgAdd {
   long nclev, ncolC;
   int AG, NxC;
 };
-// upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied
-template <class L, class CT, class AT>
+// upward sweep: z_U <- S_k, z_D <- f_D, inward side dofs copied.
+// PK: the coefficients come from the packed half-precision planes.  The load functions only ISSUE loads -- a value that
+// is converted (or just moved) at load time makes the warp wait for it there and the look-ahead is gone -- so the packed
+// words stay raw in the register sets and are unpacked where the level is computed.
+template <class L, class CT, class AT, bool PK>
 struct PrecUpIn {
   AT fU, fD, tuu, tud, iv, Rc;
   AT rs[2 * L::Nfs];         // all side dofs of the level (1-D layers copy them, 3-D layers use the inward ones)
-  AT xs[2 * L::Nfs];         // coarse correction of the side dofs this sweep finalises
-  CT t0[L::Nfs], t1[L::Nfs];     // T(0, inward side), T(1, inward side)
+  float xs[2 * L::Nfs];      // coarse correction of the side dofs this sweep finalises
+  CT t0[PK ? 1 : L::Nfs], t1[PK ? 1 : L::Nfs];     // T(0, inward side), T(1, inward side)
+  __half2 pw[PK ? PrecPack<L>::PU : 1];            // packed planes, raw
 };
-template <class L, class CT, class VT>
+template <class L, class CT, class VT, bool PK>
 __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                              const double *__restrict__ a11, const double *__restrict__ a12,
                                              const VT *__restrict__ R, const VT *__restrict__ inv,
                                              const VT *__restrict__ r, const CgAdd &cg, long ccol, const __half2 *__restrict__ PU,
-                                             PrecUpIn<L, CT, VT> &in) {
+                                             PrecUpIn<L, CT, VT, PK> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
   in.fU = r[0 * g.nlev + c];
   in.fD = r[1 * g.nlev + l1];
   const bool l1d = is1d(g, n1d, k);
-  if (PU) {  // packed half-precision copy (fp32 sweeps): warp-uniform branch
-    using PK = PrecPack<L>;
-    const long pu = (c >> PB_TILE_SHIFT) * (long)(PK::PU * PB_TILE) + (c & (PB_TILE - 1));
-    const float2 a = __half22float2(PU[pu]), ri = __half22float2(PU[pu + (PK::PU - 1) * PB_TILE]);
-    in.tuu = (VT)a.x; in.tud = (VT)a.y; in.Rc = (VT)ri.x; in.iv = (VT)ri.y;
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) {
-      in.xs[d] = (VT)0;
-      if (cg.xc && (l1d || L::side_in(d % Nfs))) in.xs[d] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + (long)k * cg.ncolC + ccol];
-    }
+  for (int d = 0; d < 2 * Nfs; ++d) {
+    in.xs[d] = 0.f;
+    if (cg.xc && (l1d || L::side_in(d % Nfs))) in.xs[d] = cg.xc[(long)(Nft + d) * cg.nclev + (long)k * cg.ncolC + ccol];
+  }
+  if constexpr (PK) {
+    using PP = PrecPack<L>;
+    const long pu = (c >> PB_TILE_SHIFT) * (long)(PP::PU * PB_TILE) + (c & (PB_TILE - 1));
+    in.pw[0] = PU[pu];
+    in.pw[PP::PU - 1] = PU[pu + (PP::PU - 1) * PB_TILE];
     if (l1d) {
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
@@ -1714,42 +1727,36 @@ __device__ __forceinline__ void prec_up_load(const Grid &g, int n1d, int k, long
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (L::side_in(d % Nfs)) {
           in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
-          const float2 t = __half22float2(PU[pu + (1 + q) * PB_TILE]);
-          in.t0[q] = (CT)t.x; in.t1[q] = (CT)t.y;
+          in.pw[1 + q] = PU[pu + (1 + q) * PB_TILE];
           ++q;
         }
       }
     }
-    return;
-  }
-  in.iv = (VT)inv[c];
-  in.Rc = (VT)R[c];
-#pragma unroll
-  for (int d = 0; d < 2 * Nfs; ++d) {
-    in.xs[d] = (VT)0;
-    if (cg.xc && (l1d || L::side_in(d % Nfs))) in.xs[d] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + (long)k * cg.ncolC + ccol];
-  }
-  if (l1d) {
-    in.tuu = (VT)a11[c]; in.tud = (VT)a12[c];
-#pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
   } else {
-    const long cb = cbase<Nf * Nf>(c);
-    in.tuu = (VT)T[cb + (0 * Nf + 0) * PB_TILE];
-    in.tud = (VT)T[cb + (1 * Nf + 0) * PB_TILE];
-    int q = 0;
+    in.iv = inv[c];
+    in.Rc = R[c];
+    if (l1d) {
+      in.tuu = (VT)a11[c]; in.tud = (VT)a12[c];
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) {
-      if (L::side_in(d % Nfs)) {
-        in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
-        in.t0[q] = T[cb + (0 * Nf + Nft + d) * PB_TILE];
-        in.t1[q] = T[cb + (1 * Nf + Nft + d) * PB_TILE];
-        ++q;
+      for (int d = 0; d < 2 * Nfs; ++d) in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+    } else {
+      const long cb = cbase<Nf * Nf>(c);
+      in.tuu = (VT)T[cb + (0 * Nf + 0) * PB_TILE];
+      in.tud = (VT)T[cb + (1 * Nf + 0) * PB_TILE];
+      int q = 0;
+#pragma unroll
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        if (L::side_in(d % Nfs)) {
+          in.rs[d] = r[(long)(Nft + d) * g.nlev + c];
+          in.t0[q] = T[cb + (0 * Nf + Nft + d) * PB_TILE];
+          in.t1[q] = T[cb + (1 * Nf + Nft + d) * PB_TILE];
+          ++q;
+        }
       }
     }
   }
 }
-template <class L, class CT, class VT = double>
+template <class L, class CT, class VT = double, bool PK = false>
 __global__ void __launch_bounds__(PREC_BLOCK)
 k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11, const double *__restrict__ a12,
           const VT *__restrict__ R, const VT *__restrict__ inv, const VT *__restrict__ r,
@@ -1766,28 +1773,39 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   for (int d = Nft; d < Nf; ++d) z[(long)d * g.nlev + lz] = r[(long)d * g.nlev + lz];
   VT Rn = (VT)R[lz];
   // One level of the recurrence from its preloaded inputs.
-  auto level = [&](int k, const PrecUpIn<L, CT, VT> &cur) {
+  auto level = [&](int k, const PrecUpIn<L, CT, VT, PK> &cur) {
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     VT fU = cur.fU, fD = cur.fD;
+    VT tuu, tud, iv, Rc;
+    if constexpr (PK) {
+      const float2 a = unpack_half2_pos(cur.pw[0]), ri = unpack_half2_pos(cur.pw[PrecPack<L>::PU - 1]);
+      tuu = (VT)a.x; tud = (VT)a.y; Rc = (VT)ri.x; iv = (VT)ri.y;
+    } else { tuu = cur.tuu; tud = cur.tud; iv = cur.iv; Rc = cur.Rc; }
     if (is1d(g, n1d, k)) {
 #pragma unroll
-      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d] + cur.xs[d];
+      for (int d = 0; d < 2 * Nfs; ++d) z[(long)(Nft + d) * g.nlev + c] = cur.rs[d] + (VT)cur.xs[d];
     } else {
       int q = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) {
         if (L::side_in(d % Nfs)) {
-          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d] + cur.xs[d];
+          z[(long)(Nft + d) * g.nlev + c] = cur.rs[d] + (VT)cur.xs[d];
           if (sides) {
-            fU = fma(cw<VT>(cur.t0[q]), cur.rs[d], fU);
-            fD = fma(cw<VT>(cur.t1[q]), cur.rs[d], fD);
+            if constexpr (PK) {
+              const float2 t = unpack_half2_pos(cur.pw[1 + q]);
+              fU = fma((VT)t.x, cur.rs[d], fU);
+              fD = fma((VT)t.y, cur.rs[d], fD);
+            } else {
+              fU = fma(cw<VT>(cur.t0[q]), cur.rs[d], fU);
+              fD = fma(cw<VT>(cur.t1[q]), cur.rs[d], fD);
+            }
           }
           ++q;
         }
       }
     }
-    S = fU + cur.tuu * (S + Rn * (cur.tud * S + fD) * cur.iv);
-    Rn = cur.Rc;
+    S = fU + tuu * (S + Rn * (tud * S + fD) * iv);
+    Rn = Rc;
     z[0 * g.nlev + c] = S;
     z[1 * g.nlev + l1] = fD;
   };
@@ -1796,102 +1814,96 @@ k_prec_up(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ 
   // the single-copy version to one memory latency per level (ncu: 48 % DRAM, 0.16 eligible warps per cycle).
   // Measured at C2: 0.135 -> 0.11 ms per launch.  (The same rotation in k_prec_down needs 3 x 38 registers, spills
   // under the one-wave register cap and was slower: it keeps the single look-ahead.)
-  PrecUpIn<L, CT, VT> A, B, C3;
+  PrecUpIn<L, CT, VT, PK> A, B, C3;
   int k = g.Nz - 1;
-  prec_up_load<L, CT, VT>(g, n1d, k, col, T, a11, a12, R, inv, r, cg, ccol, PU, A);
-  if (k >= 1) prec_up_load<L, CT, VT>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, cg, ccol, PU, B);
+  prec_up_load<L, CT, VT, PK>(g, n1d, k, col, T, a11, a12, R, inv, r, cg, ccol, PU, A);
+  if (k >= 1) prec_up_load<L, CT, VT, PK>(g, n1d, k - 1, col, T, a11, a12, R, inv, r, cg, ccol, PU, B);
   while (k >= 0) {
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, C3);
+    if (k >= 2) prec_up_load<L, CT, VT, PK>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, C3);
     level(k, A);
     if (--k < 0) break;
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, A);
+    if (k >= 2) prec_up_load<L, CT, VT, PK>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, A);
     level(k, B);
     if (--k < 0) break;
-    if (k >= 2) prec_up_load<L, CT, VT>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, B);
+    if (k >= 2) prec_up_load<L, CT, VT, PK>(g, n1d, k - 2, col, T, a11, a12, R, inv, r, cg, ccol, PU, B);
     level(k, C3);
     --k;
   }
   z[1 * g.nlev + col] = r[1 * g.nlev + col] + (cg.xc ? (VT)cg.xc[cg.nclev + ccol] : (VT)0);  // f_D(0) = r_D(0)
 }
 
-template <class L, class CT, class AT>
+template <class L, class CT, class AT, bool PK>
 struct PrecDownIn {
   AT tdd, tud, S1, fD, iv, R1;
-  AT xU, xD, xo[L::Nfs];              // coarse correction of U(k+1), D(k+1) and of the outward side dofs of the cell
+  float xU, xD, xo[L::Nfs];           // coarse correction of U(k+1), D(k+1) and of the outward side dofs of the cell
   AT rsd[2 * L::Nfs];                 // r of all side dofs at the cell
-  CT tt[L::Nfs][2 + L::Nfs];              // per outward dof: T(dof,0), T(dof,1), T(dof, inward sides)
+  CT tt[PK ? 1 : L::Nfs][2 + L::Nfs];     // per outward dof: T(dof,0), T(dof,1), T(dof, inward sides)
+  __half2 pw[PK ? PrecPack<L>::PD : 1];   // packed planes, raw
 };
-template <class L, class CT, class VT>
+template <class L, class CT, class VT, bool PK>
 __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, long col, const CT *__restrict__ T,
                                                const double *__restrict__ a11, const double *__restrict__ a12,
                                                const VT *__restrict__ R, const VT *__restrict__ inv,
                                                const VT *__restrict__ r, const VT *z, const CgAdd &cg, long ccol,
-                                               const __half2 *__restrict__ PD, PrecDownIn<L, CT, VT> &in) {
+                                               const __half2 *__restrict__ PD, PrecDownIn<L, CT, VT, PK> &in) {
   constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
   in.S1 = z[0 * g.nlev + l1];
   in.fD = z[1 * g.nlev + l1];
-  if (!PD) {
-    in.iv = (VT)inv[c];
-    in.R1 = (VT)R[l1];
-  }
-  in.xU = (VT)0; in.xD = (VT)0;
+  in.xU = 0.f; in.xD = 0.f;
 #pragma unroll
-  for (int o = 0; o < Nfs; ++o) in.xo[o] = (VT)0;
+  for (int o = 0; o < Nfs; ++o) in.xo[o] = 0.f;
+  const bool l1d = is1d(g, n1d, k);
   if (cg.xc) {
     const long lc = (long)k * cg.ncolC + ccol;
-    in.xU = (VT)cg.xc[lc + cg.ncolC];
-    in.xD = (VT)cg.xc[cg.nclev + lc + cg.ncolC];
-    if (!is1d(g, n1d, k)) {
+    in.xU = cg.xc[lc + cg.ncolC];
+    in.xD = cg.xc[cg.nclev + lc + cg.ncolC];
+    if (!l1d) {
       int o = 0;
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d)
-        if (!L::side_in(d % Nfs)) { in.xo[o] = (VT)cg.xc[(long)(Nft + d) * cg.nclev + lc]; ++o; }
+        if (!L::side_in(d % Nfs)) { in.xo[o] = cg.xc[(long)(Nft + d) * cg.nclev + lc]; ++o; }
     }
   }
-  if (PD) {  // packed half-precision copy (fp32 sweeps): warp-uniform branch
-    using PK = PrecPack<L>;
-    const long pd = (c >> PB_TILE_SHIFT) * (long)(PK::PD * PB_TILE) + (c & (PB_TILE - 1));
-    const float2 a = __half22float2(PD[pd]), ri = __half22float2(PD[pd + (PK::PD - 1) * PB_TILE]);
-    in.tdd = (VT)a.x; in.tud = (VT)a.y; in.R1 = (VT)ri.x; in.iv = (VT)ri.y;
-    if (!is1d(g, n1d, k)) {
+  if constexpr (PK) {
+    using PP = PrecPack<L>;
+    const long pd = (c >> PB_TILE_SHIFT) * (long)(PP::PD * PB_TILE) + (c & (PB_TILE - 1));
+    in.pw[0] = PD[pd];
+    in.pw[PP::PD - 1] = PD[pd + (PP::PD - 1) * PB_TILE];
+    if (!l1d) {
 #pragma unroll
       for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
-      constexpr int per = (2 + Nfs) / 2;
 #pragma unroll
-      for (int o = 0; o < Nfs; ++o)
-#pragma unroll
-        for (int h = 0; h < per; ++h) {
-          const float2 t = __half22float2(PD[pd + (1 + o * per + h) * PB_TILE]);
-          in.tt[o][2 * h] = (CT)t.x; in.tt[o][2 * h + 1] = (CT)t.y;
-        }
+      for (int n = 1; n < PP::PD - 1; ++n) in.pw[n] = PD[pd + n * PB_TILE];
     }
-    return;
-  }
-  if (is1d(g, n1d, k)) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
-  else {
-    const long cb = cbase<Nf * Nf>(c);
-    in.tdd = (VT)T[cb + (1 * Nf + 1) * PB_TILE];
-    in.tud = (VT)T[cb + (1 * Nf + 0) * PB_TILE];
+  } else {
+    in.iv = inv[c];
+    in.R1 = R[l1];
+    if (l1d) { in.tdd = (VT)a11[c]; in.tud = (VT)a12[c]; }
+    else {
+      const long cb = cbase<Nf * Nf>(c);
+      in.tdd = (VT)T[cb + (1 * Nf + 1) * PB_TILE];
+      in.tud = (VT)T[cb + (1 * Nf + 0) * PB_TILE];
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
-    int o = 0;
+      for (int d = 0; d < 2 * Nfs; ++d) in.rsd[d] = r[(long)(Nft + d) * g.nlev + c];
+      int o = 0;
 #pragma unroll
-    for (int d = 0; d < 2 * Nfs; ++d) {
-      if (!L::side_in(d % Nfs)) {
-        const int dof = Nft + d;
-        in.tt[o][0] = T[cb + (dof * Nf + 0) * PB_TILE];
-        in.tt[o][1] = T[cb + (dof * Nf + 1) * PB_TILE];
-        int q = 0;
+      for (int d = 0; d < 2 * Nfs; ++d) {
+        if (!L::side_in(d % Nfs)) {
+          const int dof = Nft + d;
+          in.tt[o][0] = T[cb + (dof * Nf + 0) * PB_TILE];
+          in.tt[o][1] = T[cb + (dof * Nf + 1) * PB_TILE];
+          int q = 0;
 #pragma unroll
-        for (int s = 0; s < 2 * Nfs; ++s)
-          if (L::side_in(s % Nfs)) { in.tt[o][2 + q] = T[cb + (dof * Nf + Nft + s) * PB_TILE]; ++q; }
-        ++o;
+          for (int s = 0; s < 2 * Nfs; ++s)
+            if (L::side_in(s % Nfs)) { in.tt[o][2 + q] = T[cb + (dof * Nf + Nft + s) * PB_TILE]; ++q; }
+          ++o;
+        }
       }
     }
   }
 }
-template <class L, class CT, class VT = double>
+template <class L, class CT, class VT = double, bool PK = false>
 __global__ void __launch_bounds__(PREC_BLOCK, 8)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const VT *__restrict__ R, const VT *__restrict__ inv,
@@ -1904,15 +1916,20 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
   VT D = r[1 * g.nlev + col];
   VT U = (VT)R[col] * D + z[0 * g.nlev + col];
   z[0 * g.nlev + col] = U + (cg.xc ? (VT)cg.xc[ccol] : (VT)0);
-  PrecDownIn<L, CT, VT> cur, nxt;
-  prec_down_load<L, CT, VT>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, cur);
+  PrecDownIn<L, CT, VT, PK> cur, nxt;
+  prec_down_load<L, CT, VT, PK>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, cur);
   for (int k = 0; k < g.Nz; ++k) {
     // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
-    if (k + 1 < g.Nz) prec_down_load<L, CT, VT>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, nxt);
+    if (k + 1 < g.Nz) prec_down_load<L, CT, VT, PK>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, nxt);
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
+    VT tdd, tud, iv, R1;
+    if constexpr (PK) {
+      const float2 a = unpack_half2_pos(cur.pw[0]), ri = unpack_half2_pos(cur.pw[PrecPack<L>::PD - 1]);
+      tdd = (VT)a.x; tud = (VT)a.y; R1 = (VT)ri.x; iv = (VT)ri.y;
+    } else { tdd = cur.tdd; tud = cur.tud; iv = cur.iv; R1 = cur.R1; }
     const VT S1 = cur.S1;
-    const VT D1 = (cur.tdd * D + cur.tud * S1 + cur.fD) * cur.iv;
-    const VT U1 = cur.R1 * D1 + S1;
+    const VT D1 = (tdd * D + tud * S1 + cur.fD) * iv;
+    const VT U1 = R1 * D1 + S1;
     if (!is1d(g, n1d, k)) {  // outgoing side streams through the column's own faces
       int o = 0;
 #pragma unroll
@@ -1920,20 +1937,32 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
         if (!L::side_in(d % Nfs)) {
           VT acc = cur.rsd[d];
           if (sides) {
-          acc = fma(cw<VT>(cur.tt[o][0]), U1, acc);
-          acc = fma(cw<VT>(cur.tt[o][1]), D, acc);
-          int q = 0;
+            VT tt[2 + Nfs];
+            if constexpr (PK) {
+              constexpr int per = (2 + Nfs) / 2;
 #pragma unroll
-          for (int s = 0; s < 2 * Nfs; ++s)
-            if (L::side_in(s % Nfs)) { acc = fma(cw<VT>(cur.tt[o][2 + q]), cur.rsd[s], acc); ++q; }
+              for (int h = 0; h < per; ++h) {
+                const float2 t = unpack_half2_pos(cur.pw[1 + o * per + h]);
+                tt[2 * h] = (VT)t.x; tt[2 * h + 1] = (VT)t.y;
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2 + Nfs; ++h) tt[h] = cw<VT>(cur.tt[o][h]);
+            }
+            acc = fma(tt[0], U1, acc);
+            acc = fma(tt[1], D, acc);
+            int q = 0;
+#pragma unroll
+            for (int s = 0; s < 2 * Nfs; ++s)
+              if (L::side_in(s % Nfs)) { acc = fma(tt[2 + q], cur.rsd[s], acc); ++q; }
           }
-          z[(long)(Nft + d) * g.nlev + c] = acc + cur.xo[o];
+          z[(long)(Nft + d) * g.nlev + c] = acc + (VT)cur.xo[o];
           ++o;
         }
       }
     }
-    z[0 * g.nlev + l1] = U1 + cur.xU;
-    z[1 * g.nlev + l1] = D1 + cur.xD;
+    z[0 * g.nlev + l1] = U1 + (VT)cur.xU;
+    z[1 * g.nlev + l1] = D1 + (VT)cur.xD;
     D = D1;
     if (k + 1 < g.Nz) cur = nxt;
   }

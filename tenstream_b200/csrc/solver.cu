@@ -239,6 +239,7 @@ struct pprts_b200_solver {
   double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
   bool have_dz3d = false;                   // init_pprts(dz3d=...): atm%hgrad exists (src/pprts.F90:621)
   float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the sweeps on fp32 vectors (krylov_fp32, 3_24 block form)
+  void *precPU = nullptr, *precPD = nullptr;     // half2 planes: packed coefficients of the fp32 column sweeps (kernels.cuh PrecPack)
   bool prec_ready = false;
   // coarse-grid correction (cfg.precond = 3): aggregates of cg.AG x cg.AG columns, see kernels.cuh
   struct CgLevel {
@@ -247,7 +248,7 @@ struct pprts_b200_solver {
   };
   int ncgl = 0;       // number of aggregate levels in use (0: plain column solve)
   CgLevel cgl[3];     // [0] is folded into the column sweeps, further (coarser) ones are added by k_cg_prolong
-  int prec_block[4] = {0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
+  int prec_block[6] = {0, 0, 0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
   bool res_valid = false;
   int res_uid = 0;
@@ -706,6 +707,12 @@ static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, 
     DISPATCH_L(s, np = L::Nft / 2);
     DA(s->precR, (size_t)np * np * g.nlev); DA(s->precInv, (size_t)np * np * g.ncell);
     if (np > 1 || cfg->krylov_fp32) { DA(s->precRf, (size_t)np * np * g.nlev); DA(s->precInvf, (size_t)np * np * g.ncell); }
+    if (np == 1 && cfg->krylov_fp32 && !getenv("PPRTS_B200_PREC_FP32")) {  // PPRTS_B200_PREC_FP32: sweeps read T itself, for comparison
+      int pu = 0, pd = 0;
+      DISPATCH_L(s, (pu = PrecPack<L>::PU, pd = PrecPack<L>::PD));
+      CU(cudaMalloc(&s->precPU, (size_t)pu * g.ncp * sizeof(__half2)));
+      CU(cudaMalloc(&s->precPD, (size_t)pd * g.ncp * sizeof(__half2)));
+    }
   }
   if (cfg->precond == 3) {  // coarse-grid correction: layouts with one up/down pair of top streams
     int nft = 0, nfs = 0;
@@ -779,7 +786,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
                     s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
-  cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->vh_atm);
+  cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->precPU); cudaFree(s->precPD); cudaFree(s->vh_atm);
   for (auto &lv : s->cgl) { cudaFree(lv.coef); cudaFree(lv.R); cudaFree(lv.sA); cudaFree(lv.sB); cudaFree(lv.rbar); cudaFree(lv.e); cudaFree(lv.x); }
   for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
   if (s->egress_ready) cudaEventDestroy(s->egress_ready);
@@ -1261,6 +1268,9 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
     if (!s->prec_ready) {
       LAUNCH(s, FAM_PRECOND, (k_prec_setup<L, CT>), nblk(g.ncol, PREC_BLOCK), PREC_BLOCK, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
              s->albedo, s->precR, s->precInv, s->precRf, s->precInvf);
+      if (s->precPU)
+        LAUNCH(s, FAM_PRECOND, (k_prec_pack<L, CT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+               (const float *)s->precRf, (const float *)s->precInvf, (__half2 *)s->precPU, (__half2 *)s->precPD);
       for (int l = 0; l < s->ncgl; ++l) {
         auto &lv = s->cgl[l];
         const CoarseGrid &c = lv.c;
@@ -1269,9 +1279,13 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
       }
       s->prec_ready = true;
     }
-    constexpr int slot = std::is_same<VT, float>::value ? 2 : 0;
-    const int bu = column_block(s, k_prec_up<L, CT, VT>, &s->prec_block[slot]);
-    const int bd = column_block(s, k_prec_down<L, CT, VT>, &s->prec_block[slot + 1]);
+    constexpr bool can_pack = std::is_same<VT, float>::value;
+    const bool packed = can_pack && s->precPU;
+    const int slot = (std::is_same<VT, float>::value ? 2 : 0) + (packed ? 2 : 0);
+    const int bu = packed ? column_block(s, k_prec_up<L, CT, VT, can_pack>, &s->prec_block[slot])
+                          : column_block(s, k_prec_up<L, CT, VT, false>, &s->prec_block[slot]);
+    const int bd = packed ? column_block(s, k_prec_down<L, CT, VT, can_pack>, &s->prec_block[slot + 1])
+                          : column_block(s, k_prec_down<L, CT, VT, false>, &s->prec_block[slot + 1]);
     const VT *pR, *pI;  // the sweeps read R and Inv in the precision of their vectors
     if constexpr (std::is_same<VT, float>::value) { pR = s->precRf; pI = s->precInvf; } else { pR = s->precR; pI = s->precInv; }
     // coarse-grid correction: xc = (P^T A P)_col^-1 P^T r first, the sweeps add P xc to z where they store its entries
@@ -1301,10 +1315,17 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
              coarser ? s->cgl[l + 1].c : c, coarser ? (const float *)s->cgl[l + 1].x : (const float *)nullptr);
     }
     if (s->ncgl > 0 && !cg_unfused) { const CoarseGrid &c = s->cgl[0].c; add = CgAdd{s->cgl[0].x, c.nclev, c.ncolC, c.AG, c.NxC}; }
-    LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           pR, pI, r, z, (int)(s->cfg.precond != 2), add);
-    LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
-           pR, pI, r, z, (int)(s->cfg.precond != 2), add);
+    if (packed) {
+      LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT, can_pack>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+             pR, pI, r, z, (int)(s->cfg.precond != 2), add, (const __half2 *)s->precPU);
+      LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT, can_pack>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+             pR, pI, r, z, (int)(s->cfg.precond != 2), add, (const __half2 *)s->precPD);
+    } else {
+      LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT, false>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+             pR, pI, r, z, (int)(s->cfg.precond != 2), add, (const __half2 *)nullptr);
+      LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT, false>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
+             pR, pI, r, z, (int)(s->cfg.precond != 2), add, (const __half2 *)nullptr);
+    }
     if (s->ncgl > 0 && cg_unfused)
       LAUNCH(s, FAM_PRECOND, (k_cg_prolong<VT>), vec_grid((long)L::Nf * g.nlev / 4), VEC_BLOCK, g, s->cgl[0].c, (int)L::Nf, (const float *)s->cgl[0].x, z);
   } else {  // several up/down pairs of top streams (3_24): block recurrence, no software pipelining

@@ -65,7 +65,7 @@ def test_random_configuration(P, luts, seed):
     albedo_2d = rng.uniform(0, 0.6, (Nx, Ny)) if rng.random() < 0.3 else None
     coeff_fp32 = bool(rng.integers(0, 2))
     mixed = bool(rng.integers(0, 2))
-    precond = int(rng.integers(0, 3))
+    precond = int(rng.integers(0, 4))
     geometric = bool(solar and sid != 810 and rng.random() < 0.4)       # -pprts_geometric_coeffs (3 direct streams)
     sd = P.sundir_from_angles(phi0, theta0)
     glut, olut = luts[sid]

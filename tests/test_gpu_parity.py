@@ -120,7 +120,7 @@ def test_mat_mult_vs_oracle(P, gpu_lut, oracle_lut, twostr_ratio):
 
 # ---- full path ---------------------------------------------------------------------------------------------------
 def run_both(P, gpu_lut, oracle_lut, Nz, Nx, Ny, dx, dz, phi0, theta0, albedo, kabs, ksca, g, solar=True, edirTOA=1000.,
-             planck=None, planck_srfc=None, albedo_2d=None, dz3d=None, precond=1, tol=1e-10, **kw):
+             planck=None, planck_srfc=None, albedo_2d=None, dz3d=None, precond=3, tol=1e-10, **kw):
     from oracle import binding as ob
     sd = P.sundir_from_angles(phi0, theta0)
     s = P.init_pprts(0, Nz, Nx, Ny, dx, dx, sd, dz1d=None if dz3d is not None else dz, dz3d=dz3d, lut=gpu_lut,
@@ -149,7 +149,7 @@ def check_fluxes(out, tol=1e-5):
 
 
 @pytest.mark.parametrize("phi0,theta0", [(0., 70.), (30., 40.), (120., 40.), (200., 60.), (315., 25.), (90., 0.)])
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond", [0, 1, 3])
 def test_solar_vs_oracle(P, gpu_lut, oracle_lut, phi0, theta0, precond):
     rng = np.random.default_rng(3)
     Nz, Nx, Ny = 8, 7, 6
@@ -161,7 +161,7 @@ def test_solar_vs_oracle(P, gpu_lut, oracle_lut, phi0, theta0, precond):
     check_fluxes(out, 1e-7)
 
 
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond", [0, 1, 3])
 def test_thermal_vs_oracle(P, gpu_lut, oracle_lut, precond):
     rng = np.random.default_rng(4)
     Nz, Nx, Ny = 8, 5, 6

@@ -1904,7 +1904,7 @@ __device__ __forceinline__ void prec_down_load(const Grid &g, int n1d, int k, lo
   }
 }
 template <class L, class CT, class VT = double, bool PK = false>
-__global__ void __launch_bounds__(PREC_BLOCK, 8)
+__global__ void __launch_bounds__(PREC_BLOCK, PK ? 7 : 8)
 k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
             const double *__restrict__ a12, const VT *__restrict__ R, const VT *__restrict__ inv,
             const VT *__restrict__ r, VT *z, int sides, CgAdd cg, const __half2 *__restrict__ PD) {
@@ -1916,11 +1916,7 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
   VT D = r[1 * g.nlev + col];
   VT U = (VT)R[col] * D + z[0 * g.nlev + col];
   z[0 * g.nlev + col] = U + (cg.xc ? (VT)cg.xc[ccol] : (VT)0);
-  PrecDownIn<L, CT, VT, PK> cur, nxt;
-  prec_down_load<L, CT, VT, PK>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, cur);
-  for (int k = 0; k < g.Nz; ++k) {
-    // level k+1's inputs z(0:1, k+2) are only written by this thread at iteration k+1: safe to read ahead
-    if (k + 1 < g.Nz) prec_down_load<L, CT, VT, PK>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, nxt);
+  auto level = [&](int k, const PrecDownIn<L, CT, VT, PK> &cur) {
     const long c = (long)k * g.ncol + col, l1 = c + g.ncol;
     VT tdd, tud, iv, R1;
     if constexpr (PK) {
@@ -1964,7 +1960,35 @@ k_prec_down(Grid g, int n1d, const CT *__restrict__ T, const double *__restrict_
     z[0 * g.nlev + l1] = U1 + (VT)cur.xU;
     z[1 * g.nlev + l1] = D1 + (VT)cur.xD;
     D = D1;
-    if (k + 1 < g.Nz) cur = nxt;
+  };
+  // level k+1's inputs z(0:1, k+2) are only written by this thread at level k+1: safe to read ahead.  The packed sets
+  // are small enough for the two-level look-ahead of k_prec_up (three rotating sets, never copied); the unpacked ones
+  // (38 registers each) keep one level of look-ahead.
+  const int Nz = g.Nz;
+  if constexpr (PK) {
+    PrecDownIn<L, CT, VT, PK> A, B, C3;
+    int k = 0;
+    prec_down_load<L, CT, VT, PK>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, A);
+    if (Nz > 1) prec_down_load<L, CT, VT, PK>(g, n1d, 1, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, B);
+    while (k < Nz) {
+      if (k + 2 < Nz) prec_down_load<L, CT, VT, PK>(g, n1d, k + 2, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, C3);
+      level(k, A);
+      if (++k >= Nz) break;
+      if (k + 2 < Nz) prec_down_load<L, CT, VT, PK>(g, n1d, k + 2, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, A);
+      level(k, B);
+      if (++k >= Nz) break;
+      if (k + 2 < Nz) prec_down_load<L, CT, VT, PK>(g, n1d, k + 2, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, B);
+      level(k, C3);
+      ++k;
+    }
+  } else {
+    PrecDownIn<L, CT, VT, PK> cur, nxt;
+    prec_down_load<L, CT, VT, PK>(g, n1d, 0, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, cur);
+    for (int k = 0; k < Nz; ++k) {
+      if (k + 1 < Nz) prec_down_load<L, CT, VT, PK>(g, n1d, k + 1, col, T, a11, a12, R, inv, r, z, cg, ccol, PD, nxt);
+      level(k, cur);
+      if (k + 1 < Nz) cur = nxt;
+    }
   }
 }
 

@@ -262,10 +262,15 @@ def run_ours(args):
         s.stage_optical_properties_async(E2E_SLOT0 + (ib & 1), b["albedo"], hb["kabs"], hb["ksca"], hb["g"],
                                          hb["planck"], hb["planck_srfc"])
 
+    staged_ahead = [False]
+
     def step_e2e():
-        # the host-side band loop: upload of band ib+1 and download of band ib-1 travel while band ib is solved
+        # the host-side band loop: upload of band ib+1 and download of band ib-1 travel while band ib is solved; the
+        # loop does not stop at the step boundary -- the first band of the NEXT step is on its way while the last result
+        # of this one is downloaded (every step still uploads all its inputs and downloads all its results)
         s.reset_accumulator()
-        stage_async(0)
+        if not staged_ahead[0]:
+            stage_async(0)
         for ib, b in enumerate(bands):
             s.set_optical_properties_staged(E2E_SLOT0 + (ib & 1))
             if ib + 1 < len(bands):
@@ -275,6 +280,8 @@ def run_ours(args):
             s.accumulate_result(b["uid"], 1.0)
         if world > 1:
             s.allreduce_accumulated()
+        stage_async(0)
+        staged_ahead[0] = True
         s.wait_results()
 
     clocks = ClockSampler(local)

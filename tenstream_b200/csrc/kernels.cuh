@@ -2024,54 +2024,112 @@ struct CoarseGrid {
 };
 template <int NS> struct CgLayout { static constexpr int A = 0, GU = 4, GD = 4 + NS, WU = 4 + 2 * NS, WD = 4 + 3 * NS, W = 4 + 4 * NS, N = 4 + 4 * NS + NS * NS; };
 
+// Galerkin column blocks of all levels in ONE pass over the fine coefficients.  Thread (coarsest-level cell, dst row):
+// walks the fine cells of its aggregate once, every T(dst, src) is loaded once and added to the row of each level
+// whose aggregate column it stays inside; the row of a finer level is written when its aggregate is complete.  The
+// raw rows land in the level's coefficient planes (plane dst * Nf + src), where k_cg_condense replaces them in place.
+struct CgLevels {
+  int n;  // 1 or 2 nested levels
+  CoarseGrid c[2];
+  float *coef[2];
+};
 template <class L, class CT>
-__global__ void __launch_bounds__(64)
-k_cg_build(Grid g, CoarseGrid cg, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
-           const double *__restrict__ a12, float *__restrict__ coef) {
-  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs, NS = 2 * Nfs;
+__global__ void __launch_bounds__(128)
+k_cg_accumulate(Grid g, CgLevels lv, int n1d, const CT *__restrict__ T, const double *__restrict__ a11,
+                const double *__restrict__ a12) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
   static_assert(Nft == 2, "coarse correction needs one up/down pair of top streams");
+  const CoarseGrid &top = lv.c[lv.n - 1];
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= top.ncc * Nf) return;
+  const int dst = (int)(t / top.ncc);  // dst-major: the threads of a warp share dst and walk neighbouring aggregates
+  const long cc = t - (long)dst * top.ncc;
+  const int I = (int)(cc % top.NxC), J = (int)((cc / top.NxC) % top.NyC), k = (int)(cc / top.ncolC);
+  const bool l1d = is1d(g, n1d, k);
+  const int i0 = I * top.AG, i1 = min(g.Nx, i0 + top.AG), j0 = J * top.AG, j1 = min(g.Ny, j0 + top.AG);
+  const int a0 = lv.c[0].AG;  // finest aggregates: the walk goes aggregate by aggregate of this level
+  double acc[2][Nf];  // lv.n <= 2: the walk keeps the fine cells of ONE level-0 aggregate together, level 1 is the whole walk
+#pragma unroll
+  for (int l = 0; l < 2; ++l)
+#pragma unroll
+    for (int s2 = 0; s2 < Nf; ++s2) acc[l][s2] = 0.0;
+  auto flush = [&](int l, double (&row)[Nf], int ii, int jj) {  // row of level l's aggregate holding fine column (ii, jj) is complete
+    const CoarseGrid &c = lv.c[l];
+    const int Il = ii / c.AG, Jl = jj / c.AG;
+    const int ni = min(g.Nx, (Il + 1) * c.AG) - Il * c.AG, nj = min(g.Ny, (Jl + 1) * c.AG) - Jl * c.AG;
+    const double sc = 1.0 / (double)(ni * nj);
+    const long ccl = ((long)k * c.NyC + Jl) * c.NxC + Il;
+#pragma unroll
+    for (int s2 = 0; s2 < Nf; ++s2) { lv.coef[l][(long)(dst * Nf + s2) * c.ncc + ccl] = (float)(row[s2] * sc); row[s2] = 0.0; }
+  };
+  // walk: blocks of the finest level (a0 x a0), inside a block row by row
+  for (int jb = j0; jb < j1; jb += a0) {
+    for (int ib = i0; ib < i1; ib += a0) {
+      for (int j = jb; j < min(j1, jb + a0); ++j) {
+        for (int i = ib; i < min(i1, ib + a0); ++i) {
+          const long c = lidx(g, k, j, i);
+          if (l1d) {
+            if (dst < Nft) {
+              const double t11 = a11[c], t12 = a12[c];
+#pragma unroll
+              for (int l = 0; l < 2; ++l)
+#pragma unroll
+                for (int s2 = 0; s2 < Nft; ++s2)
+                  if (l < lv.n) acc[l][s2] += (s2 == dst) ? t11 : t12;
+            }
+            continue;
+          }
+          const long cb = cbase<Nf * Nf>(c) + (long)dst * Nf * PB_TILE;
+          float v[Nf];
+#pragma unroll
+          for (int s2 = 0; s2 < Nf; ++s2) v[s2] = (float)T[cb + s2 * PB_TILE];
+#pragma unroll
+          for (int l = 0; l < 2; ++l) {
+            if (l >= lv.n) continue;
+            const int AG = lv.c[l].AG;
+            // is the high-x / high-y face of this fine cell inside level l's aggregate column?
+            const bool xin = (i + 1 < g.Nx) ? ((i + 1) / AG == i / AG) : (!g.gx && i / AG == 0);
+            const bool yin = (j + 1 < g.Ny) ? ((j + 1) / AG == j / AG) : (!g.gy && j / AG == 0);
+            bool out_ok = true;
+            if (dst >= Nft + Nfs) out_ok = L::side_in(dst - Nft - Nfs) ? yin : true;
+            else if (dst >= Nft) out_ok = L::side_in(dst - Nft) ? xin : true;
+            if (!out_ok) continue;
+#pragma unroll
+            for (int s2 = 0; s2 < Nf; ++s2) {
+              bool in_ok = true;
+              if (s2 >= Nft + Nfs) in_ok = L::side_in(s2 - Nft - Nfs) ? true : yin;
+              else if (s2 >= Nft) in_ok = L::side_in(s2 - Nft) ? true : xin;
+              if (in_ok) acc[l][s2] += (double)v[s2];
+            }
+          }
+        }
+      }
+      // aggregates complete after this block: level 0 always; level l when the block is the last one of its aggregate
+      const int il = min(i1, ib + a0) - 1, jl = min(j1, jb + a0) - 1;
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        if (l >= lv.n) continue;
+        const int AG = lv.c[l].AG;
+        const bool last_i = (il + 1 >= g.Nx) || ((il + 1) % AG == 0), last_j = (jl + 1 >= g.Ny) || ((jl + 1) % AG == 0);
+        if (last_i && last_j) flush(l, acc[l], il, jl);
+      }
+    }
+  }
+}
+// raw Galerkin rows (scaled) -> condensed two-stream coefficients and back-substitution matrices, in place
+template <class L>
+__global__ void __launch_bounds__(64)
+k_cg_condense(CoarseGrid cg, float *__restrict__ coef) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs, NS = 2 * Nfs;
   using CL = CgLayout<NS>;
+  static_assert(CL::N == Nf * Nf, "the condensed set reuses the planes of the raw rows");
   const long cc = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cc >= cg.ncc) return;
-  const int I = (int)(cc % cg.NxC), J = (int)((cc / cg.NxC) % cg.NyC), k = (int)(cc / cg.ncolC);
-  const int i0 = I * cg.AG, i1 = min(g.Nx, i0 + cg.AG), j0 = J * cg.AG, j1 = min(g.Ny, j0 + cg.AG);
   double C[Nf][Nf];
 #pragma unroll
   for (int a = 0; a < Nf; ++a)
 #pragma unroll
-    for (int b = 0; b < Nf; ++b) C[a][b] = 0.0;
-  for (int j = j0; j < j1; ++j) {
-    // is the high-y face of row j (where the streams leaving towards +y arrive) inside this aggregate?
-    const bool yin = (j + 1 < g.Ny) ? ((j + 1) / cg.AG == J) : (!g.gy && J == 0);
-    for (int i = i0; i < i1; ++i) {
-      const bool xin = (i + 1 < g.Nx) ? ((i + 1) / cg.AG == I) : (!g.gx && I == 0);
-      const long c = lidx(g, k, j, i);
-      if (is1d(g, n1d, k)) {
-        C[0][0] += a11[c]; C[1][1] += a11[c]; C[0][1] += a12[c]; C[1][0] += a12[c];
-        continue;
-      }
-      const long cb = cbase<Nf * Nf>(c);
-      bool out_ok[Nf], in_ok[Nf];
-#pragma unroll
-      for (int d = 0; d < Nf; ++d) {
-        if (d < Nft) { out_ok[d] = true; in_ok[d] = true; }
-        else if (d < Nft + Nfs) { const bool in = L::side_in(d - Nft); out_ok[d] = in ? xin : true; in_ok[d] = in ? true : xin; }
-        else { const bool in = L::side_in(d - Nft - Nfs); out_ok[d] = in ? yin : true; in_ok[d] = in ? true : yin; }
-      }
-#pragma unroll
-      for (int dst = 0; dst < Nf; ++dst)
-#pragma unroll
-        for (int src = 0; src < Nf; ++src) {
-          const double v = (double)T[cb + (dst * Nf + src) * PB_TILE];
-          if (out_ok[dst] && in_ok[src]) C[dst][src] += v;
-        }
-    }
-  }
-  const double sc = 1.0 / (double)((i1 - i0) * (j1 - j0));
-#pragma unroll
-  for (int a = 0; a < Nf; ++a)
-#pragma unroll
-    for (int b = 0; b < Nf; ++b) C[a][b] *= sc;
+    for (int b = 0; b < Nf; ++b) C[a][b] = (double)coef[(long)(a * Nf + b) * cg.ncc + cc];
   // W = (I - Css)^-1 by Gauss-Jordan (I - Css is strictly diagonally dominant: the column sums of T are < 1)
   double M[NS][NS], W[NS][NS];
 #pragma unroll

@@ -1271,11 +1271,20 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
       if (s->precPU)
         LAUNCH(s, FAM_PRECOND, (k_prec_pack<L, CT>), nblk(g.ncell, 128), 128, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
                (const float *)s->precRf, (const float *)s->precInvf, (__half2 *)s->precPU, (__half2 *)s->precPD);
-      for (int l = 0; l < s->ncgl; ++l) {
-        auto &lv = s->cgl[l];
-        const CoarseGrid &c = lv.c;
-        LAUNCH(s, FAM_PRECOND, (k_cg_build<L, CT>), nblk(c.ncc, 64), 64, g, c, s->n1d, (const CT *)s->f2f, s->a11, s->a12, lv.coef);
-        LAUNCH(s, FAM_PRECOND, k_cg_setup, nblk(c.ncolC, 64), 64, g, c, (const double *)s->albedo, (const float *)lv.coef, (float4 *)lv.sA, (float2 *)lv.sB, lv.R);
+      if (s->ncgl > 0) {
+        for (int l0 = 0; l0 < s->ncgl; l0 += 2) {  // one pass over the fine coefficients per pair of nested levels
+          CgLevels lv{};
+          lv.n = std::min(2, s->ncgl - l0);
+          for (int l = 0; l < lv.n; ++l) { lv.c[l] = s->cgl[l0 + l].c; lv.coef[l] = s->cgl[l0 + l].coef; }
+          const CoarseGrid &top = lv.c[lv.n - 1];
+          LAUNCH(s, FAM_PRECOND, (k_cg_accumulate<L, CT>), nblk(top.ncc * L::Nf, 128), 128, g, lv, s->n1d, (const CT *)s->f2f, s->a11, s->a12);
+        }
+        for (int l = 0; l < s->ncgl; ++l) {
+          const CoarseGrid &c = s->cgl[l].c;
+          LAUNCH(s, FAM_PRECOND, (k_cg_condense<L>), nblk(c.ncc, 64), 64, c, s->cgl[l].coef);
+          LAUNCH(s, FAM_PRECOND, k_cg_setup, nblk(c.ncolC, 64), 64, g, c, (const double *)s->albedo, (const float *)s->cgl[l].coef,
+                 (float4 *)s->cgl[l].sA, (float2 *)s->cgl[l].sB, s->cgl[l].R);
+        }
       }
       s->prec_ready = true;
     }

@@ -148,10 +148,13 @@ class Timer:
         self.torch, self.dist, self.world, self.s = torch, dist, world, solver
         self.stream = torch.cuda.ExternalStream(solver.cuda_stream())
 
-    def run(self, fn, steps, warmup):
+    def run(self, fn, steps, warmup, finish=None):
+        """finish: called after the last timed step, before the closing event (work a pipelined loop still has in flight)"""
         torch, dist, s = self.torch, self.dist, self.s
         for _ in range(warmup):
             fn()
+        if finish:
+            finish()
         s.synchronize()
         if self.world > 1:
             dist.barrier()
@@ -161,6 +164,8 @@ class Timer:
         e0.record(self.stream)
         for _ in range(steps):
             fn()
+        if finish:
+            finish()
         e1.record(self.stream)
         s.synchronize()
         torch.cuda.synchronize()
@@ -234,7 +239,8 @@ def run_ours(args):
             hb[k] = v
         host.append(hb)
     outs = []
-    for _ in bands:      # one set of result arrays per band, as the caller of pprts_get_result has them
+    for _ in range(2 * len(bands)):      # one set of result arrays per band (two steps' worth: the downloads of a step
+                                         # finish while the next step is already being solved)
         o = []
         for shp in ((Nz + 1, Nx, Ny), (Nz + 1, Nx, Ny), (Nz, Nx, Ny), (Nz + 1, Nx, Ny)):
             t, v = pinned_f(torch, shp)
@@ -242,7 +248,7 @@ def run_ours(args):
             o.append(v)
         outs.append(tuple(o))
     h2d = sum(sum(h[k].size * 8 for k in h if h[k] is not None) for h in host)
-    d2h = sum(sum(a.size * 8 for a in o) for o in outs)
+    d2h = sum(sum(a.size * 8 for a in o) for o in outs[:len(bands)])
     for slot, b in enumerate(bands):
         s.stage_optical_properties(slot, b["albedo"], b["kabs"], b["ksca"], b["g"], b["planck"], b["planck_srfc"])
 
@@ -263,6 +269,7 @@ def run_ours(args):
                                          hb["planck"], hb["planck_srfc"])
 
     staged_ahead = [False]
+    e2e_step = [0]
 
     def step_e2e():
         # the host-side band loop: upload of band ib+1 and download of band ib-1 travel while band ib is solved; the
@@ -276,19 +283,21 @@ def run_ours(args):
             if ib + 1 < len(bands):
                 stage_async(ib + 1)
             P.solve_pprts(s, not b["lsolar"], b["lsolar"], b["edirTOA"], b["uid"])
-            s.get_result_async(b["uid"], outs[ib])
+            if ib == 0:
+                s.wait_results()     # the previous step's results are complete (they travelled during this solve)
+            s.get_result_async(b["uid"], outs[(e2e_step[0] & 1) * len(bands) + ib])
             s.accumulate_result(b["uid"], 1.0)
         if world > 1:
             s.allreduce_accumulated()
         stage_async(0)
         staged_ahead[0] = True
-        s.wait_results()
+        e2e_step[0] += 1
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     ms_dev, launches = timer.run(step_device, args.steps, args.warmup)
-    ms_e2e, _ = timer.run(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _ = timer.run(step_e2e, args.steps, max(1, args.warmup // 2), finish=s.wait_results)
     clk = clocks.stop() if rank == 0 else None
 
     # roofline of the dominant kernel (diffuse MatMult), measured live with CUDA events on the launching stream
@@ -563,11 +572,18 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
         t, v = pinned_f(torch, sc["kabs"].shape + (CHUNK,))
         keep.append(t)
         stacks.append(v)
-    pool = ThreadPoolExecutor(1)
+    pool = ThreadPoolExecutor(2)
+    # Fortran-ordered bases: the scaling then streams through both arrays (a C-ordered source against the Fortran-ordered
+    # stack is a strided walk: 0.26 s per band measured, slower than the GPU solves the band)
+    base_f = {True: np.asfortranarray(sc["kabs"]), False: np.asfortranarray(sc["kabs_th"])}
+
+    def fill_one(stack, base, f, ib):
+        np.multiply(base, f, out=stack[..., ib])
 
     def fill(stack, base, scales):
-        for ib, f in enumerate(scales):
-            np.multiply(base, f, out=stack[..., ib])
+        futs = [pool.submit(fill_one, stack, base, f, ib) for ib, f in enumerate(scales)]
+        for ft in futs:
+            ft.result()
         return stack[..., :len(scales)]
 
     ksca, g = pinned_copy(sc["ksca"]), pinned_copy(sc["g"])
@@ -578,16 +594,34 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
     work = [(True, my_sw[i:i + CHUNK]) for i in range(0, len(my_sw), CHUNK)] + \
            [(False, my_lw[i:i + CHUNK]) for i in range(0, len(my_lw), CHUNK)]
 
+    class _Chunk:     # the bands of a chunk being filled by the pool; result() waits for all of them
+        def __init__(self, stack, base, scales):
+            self.view = stack[..., :len(scales)]
+            self.futs = [pool.submit(fill_one, stack, base, f, ib) for ib, f in enumerate(scales)]
+
+        def result(self):
+            for ft in self.futs:
+                ft.result()
+            return self.view
+
     def submit(iw):
         lsol, bs = work[iw]
-        return pool.submit(fill, stacks[iw & 1], sc["kabs"] if lsol else sc["kabs_th"], [b["scale"] for b in bs])
+        return _Chunk(stacks[iw & 1], base_f[lsol], [b["scale"] for b in bs])
+
+    # the first chunk is in host memory when the clock starts (as the inputs of every other leg are); the host thread
+    # then stays one chunk ahead of the GPU
+    first = [submit(0).result()] if work else [None]
+    wall = {"wait_host_fill": 0.0, "solve_bands": 0.0, "reduce_download": 0.0}
 
     def spectral_integration():
         it = []
-        fut = submit(0) if work else None
+        fut = None
         for iw, (lsol, bs) in enumerate(work):
-            kabs = fut.result()
+            t0 = time.perf_counter()
+            kabs = first[0] if iw == 0 else fut.result()
+            wall["wait_host_fill"] += time.perf_counter() - t0
             fut = submit(iw + 1) if iw + 1 < len(work) else None
+            t0 = time.perf_counter()
             if lsol:
                 r = P.solve_bands(s, True, sc["albedo"], kabs, ksca, g, edirTOA=np.array([b["edirTOA"] for b in bs]),
                                   uid0=bs[0]["uid"], download=False, accumulate_only=iw > 0)
@@ -596,18 +630,28 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
                                   weights=np.array([b["weight"] for b in bs]), uid0=bs[0]["uid"], download=False,
                                   accumulate_only=iw > 0)
             it += list(r[4])
+            wall["solve_bands"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
         if world > 1:
             s.allreduce_accumulated()
         s.get_accumulated_into(outs)
+        wall["reduce_download"] += time.perf_counter() - t0
         return it
 
     # warm-up: one solar band (lazy allocations, first-touch of the pinned pages)
     if my_sw:
-        P.solve_bands(s, True, sc["albedo"], fill(stacks[1], sc["kabs"], [my_sw[0]["scale"]]), ksca, g,
+        P.solve_bands(s, True, sc["albedo"], fill(stacks[1], base_f[True], [my_sw[0]["scale"]]), ksca, g,
                       edirTOA=np.array([my_sw[0]["edirTOA"]]), uid0=900, download=False)
     timer = Timer(torch, dist, world, s)
     box = {}
+    fam_timing = os.environ.get("C3_TIMING") is not None     # per-family kernel times (CUDA events around every launch)
+    if fam_timing:
+        s.kernel_stats(reset=True)
+        s.enable_kernel_timing(True)
     ms, launches = timer.run(lambda: box.__setitem__("it", spectral_integration()), 1, 0)
+    fam = s.kernel_stats(reset=True) if fam_timing else None
+    if fam_timing:
+        s.enable_kernel_timing(False)
     its = box["it"]
     n_sw, n_lw = len(my_sw), len(my_lw)
     nb_total = len(sw) + len(lw)
@@ -626,7 +670,8 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
             "ms_total": ms, "ms_per_band": ms * world / nb_total, "value": ncell * nb_total / (ms * 1e-3), "unit": UNIT,
             "scaling": "strong (fixed 252 bands)", "h2d_bytes_rank0": h2d, "d2h_bytes_rank0": sum(o.size * 8 for o in outs),
             "mean_krylov_iterations_per_band": (sum(r["krylov_iterations_sw"] + r["krylov_iterations_lw"] for r in gather) / nb_total),
-            "per_rank": gather, "gpu_launches_rank0": int(launches)}
+            "per_rank": gather, "gpu_launches_rank0": int(launches), "host_wall_s_rank0": {k: round(v, 3) for k, v in wall.items()},
+            **({"kernel_ms_rank0": {k: round(v["ms"], 1) for k, v in fam.items()}} if fam else {})}
 
 
 def leg_decomp(P, torch, dist, world, rank, local, lut, args, nx, ny, nz, dx, dz, twostr_ratio, steps=1, warmup=1):

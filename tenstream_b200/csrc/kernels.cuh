@@ -3125,6 +3125,9 @@ __global__ void k_halo_unpack(Grid g, int dir, int d0, int nd, unsigned int mask
   }
 }
 // v[0] <- sqrt(v[0]) / nranks : local 2-norm -> this rank's share of the mean over ranks (src/pprts_explicit.F90:182)
+// device scalars -> mapped host memory (read_scalars)
+__global__ void k_export_scalars(const double *__restrict__ sc, double *__restrict__ host) { host[threadIdx.x] = sc[threadIdx.x]; }
+__global__ void k_export_flag(const int *__restrict__ flag, int *__restrict__ host) { host[0] = flag[0]; }
 __global__ void k_sqrt_mean(double *v, int n, double inv_nranks) {
   if (threadIdx.x < n) v[threadIdx.x] = sqrt(v[threadIdx.x]) * inv_nranks;
 }

@@ -17,6 +17,7 @@
 #include <map>
 #include <type_traits>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/pprts_b200.h"
@@ -255,8 +256,8 @@ struct pprts_b200_solver {
   double *partials = nullptr, *sc = nullptr;
   unsigned int *counter = nullptr;
   int *bad = nullptr;
-  double *h_sc = nullptr;  // pinned
-  int *h_bad = nullptr;
+  double *h_sc = nullptr, *h_sc_dev = nullptr;  // pinned + mapped: the device writes the scalars straight into it
+  int *h_bad = nullptr, *h_bad_dev = nullptr;  // mapped, like h_sc
   // LUT on device
   float *d_ax[4] = {nullptr};
   double *d_Tdir4 = nullptr, *d_Sdir4 = nullptr;
@@ -286,6 +287,7 @@ struct pprts_b200_solver {
   cudaEvent_t egress_ready = nullptr, egress_done = nullptr;
   bool egress_pending = false;
   long use_clock = 0;
+  std::vector<std::array<double *, 3>> spare;  // (edir, ediff, abso) of dropped solutions, reused by the next new uid
   int fail_next_krylov = 0;  // test hook: the next n primary Krylov solves report non-convergence
   long krylov_retries = 0;
   int num_sms = 148;
@@ -743,8 +745,10 @@ static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, 
   DA(s->out_stage, (size_t)std::max(Nd, Nf) * g.nlev);
   DA(s->partials, (size_t)4 * (nblk(g.ncell, 128) + 148 * 16 + 64));
   DA(s->sc, SC_COUNT); DA(s->counter, 4); DA(s->bad, 1);
-  CU(cudaMallocHost((void **)&s->h_sc, SC_COUNT * sizeof(double)));
-  CU(cudaMallocHost((void **)&s->h_bad, sizeof(int)));
+  CU(cudaHostAlloc((void **)&s->h_sc, SC_COUNT * sizeof(double), cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void **)&s->h_sc_dev, s->h_sc, 0));
+  CU(cudaHostAlloc((void **)&s->h_bad, sizeof(int), cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void **)&s->h_bad_dev, s->h_bad, 0));
   CU(cudaMemcpy(s->atm_dz, hdz.data(), hdz.size() * sizeof(double), cudaMemcpyHostToDevice));
   if (cfg->geometric_coeffs || cfg->dz3d) {  // determine_vertex_heights / atm%hhl (src/pprts.F90:585-600, :726-755)
     DA(s->vh_atm, s->nlev_atm);
@@ -787,6 +791,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->precPU); cudaFree(s->precPD); cudaFree(s->vh_atm);
+  for (auto &sp : s->spare) { cudaFree(sp[0]); cudaFree(sp[1]); cudaFree(sp[2]); }
   for (auto &lv : s->cgl) { cudaFree(lv.coef); cudaFree(lv.R); cudaFree(lv.sA); cudaFree(lv.sB); cudaFree(lv.rbar); cudaFree(lv.e); cudaFree(lv.x); }
   for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
   if (s->egress_ready) cudaEventDestroy(s->egress_ready);
@@ -865,7 +870,7 @@ static int set_optprop_impl(pprts_b200_solver *s, double albedo, const double *k
     LAUNCH(s, FAM_IO, k_collapse, nblk(gr.ncol, 128), 128, gr.ncol, s->icollapse, s->costheta, (int)s->have_planck,
            s->atm_kabs, s->atm_ksca, s->atm_gg, s->atm_dz, s->atm_planck, s->a11, s->a12, s->a13, s->a23, s->a33,
            s->Btop, s->Bbot);
-  CU(cudaMemcpyAsync(s->h_bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  k_export_flag<<<1, 1, 0, s->stream>>>(s->bad, s->h_bad_dev);
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
   if (*s->h_bad) return set_err(5, "set_optical_properties :: found illegal value in delta_scaled optical properties!");
@@ -1024,7 +1029,7 @@ static int ensure_coeffs(pprts_b200_solver *s, bool lsolar) {
     bool launched = false;
     DISPATCH_LC(s, (launched = launch_geometric<L, CT>(s, n3d, sx, sy, sz)));
     if (!launched) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
-    CU(cudaMemcpyAsync(s->h_bad, s->bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    k_export_flag<<<1, 1, 0, s->stream>>>(s->bad, s->h_bad_dev);
     CU(cudaStreamSynchronize(s->stream));
     if (*s->h_bad) return set_err(24, "Extinction coeff too small for the geometric coefficients (kabs + ksca < tiny in a 3-D cell)");
   }
@@ -1058,7 +1063,10 @@ static int scale_flx(pprts_b200_solver *s, Solution &sol, bool lWm2) {
 }
 
 static int read_scalars(pprts_b200_solver *s) {
-  CU(cudaMemcpyAsync(s->h_sc, s->sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  // The scalars travel as stores of a one-warp kernel into mapped host memory, not as a D2H copy: a copy queues on the
+  // copy engine behind whatever bulk download is in flight (get_result_async of the previous band: ~7 ms at C2), which
+  // stalled every Krylov iteration that ran meanwhile (measured: end-to-end step 9 ms above the device-resident one).
+  k_export_scalars<<<1, SC_COUNT, 0, s->stream>>>(s->sc, s->h_sc_dev);
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -1728,18 +1736,26 @@ static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool ltherma
       for (auto &kv : s->solutions)
         if (kv.first != uid && kv.first != uid - 1 && (!found || kv.second.last_use < oldest)) { victim = kv.first; oldest = kv.second.last_use; found = true; }
       if (!found) break;
-      CU(cudaStreamSynchronize(s->stream));
-      free_solution(s->solutions[victim]);
+      // the victim's arrays go to a spare list instead of back to the driver: freeing and re-allocating 3 GB per band
+      // costs tens of milliseconds (cudaFree synchronises the device); work still queued on them is stream-ordered
+      // before whatever the next owner enqueues
+      Solution &v = s->solutions[victim];
+      s->spare.push_back({v.edir, v.ediff, v.abso});
+      v.edir = v.ediff = v.abso = nullptr;
       s->solutions.erase(victim);
     }
   }
   Solution &sol = s->solutions[key];
   sol.last_use = ++s->use_clock;
   auto prepare = [&]() -> int {  // prepare_solution (src/pprts_base.F90:297-344)
-    if (!sol.edir) { DA(sol.edir, (size_t)state_len(g, s->Nd)); DA(sol.ediff, (size_t)state_len(g, s->Nf)); DA(sol.abso, g.ncell); }
-    else {
-      CU(cudaMemsetAsync(sol.edir, 0, (size_t)s->Nd * g.nlev * sizeof(double), s->stream));
-      CU(cudaMemsetAsync(sol.ediff, 0, (size_t)s->Nf * g.nlev * sizeof(double), s->stream));
+    bool fresh = false;
+    if (!sol.edir) {
+      if (!s->spare.empty()) { sol.edir = s->spare.back()[0]; sol.ediff = s->spare.back()[1]; sol.abso = s->spare.back()[2]; s->spare.pop_back(); }
+      else { DA(sol.edir, (size_t)state_len(g, s->Nd)); DA(sol.ediff, (size_t)state_len(g, s->Nf)); DA(sol.abso, g.ncell); fresh = true; }
+    }
+    if (!fresh) {
+      CU(cudaMemsetAsync(sol.edir, 0, (size_t)state_len(g, s->Nd) * sizeof(double), s->stream));
+      CU(cudaMemsetAsync(sol.ediff, 0, (size_t)state_len(g, s->Nf) * sizeof(double), s->stream));
       CU(cudaMemsetAsync(sol.abso, 0, (size_t)g.ncell * sizeof(double), s->stream));
     }
     sol.lset = true; sol.lsolar_rad = lsolar; sol.lthermal_rad = lthermal; sol.lchanged = true;

@@ -2233,26 +2233,15 @@ k_cg_restrict(Grid g, CoarseGrid cg, const VT *__restrict__ r, const float *__re
   }
   if (k < cg.Nz) {
     const long cc = lc;  // same (k, I, J) numbering for k < Nz
-    float fu = rb[0], fd = 0.f;  // f_U = r_U(k) + gU . r_s, f_D = r_D(k+1) + gD . r_s
-    for (int j = j0; j < j1; ++j) {
-      const long q = (long)1 * g.nlev + ((long)(k + 1) * g.Ny + j) * g.Nx + i0;
-      if (vec4) {
-        const float4 v = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(r) + q);
-        fd += (v.x + v.y) + (v.z + v.w);
-      } else {
-        for (int i = 0; i < i1 - i0; ++i) fd += (float)r[q + i];
-      }
-    }
-    fd *= sc;
+    float fu = rb[0], ed = 0.f;  // f_U = r_U(k) + gU . r_s;  f_D = r_D(k+1) + gD . r_s: the column kernel adds r_D(k+1)
 #pragma unroll
     for (int p = 0; p < NS; ++p) {
       fu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + cc], rb[Nft + p], fu);
-      fd = fmaf(coef[(long)(CL::GD + p) * cg.ncc + cc], rb[Nft + p], fd);
+      ed = fmaf(coef[(long)(CL::GD + p) * cg.ncc + cc], rb[Nft + p], ed);
     }
-    f[cc] = make_float2(fu, fd);
+    f[cc] = make_float2(fu, ed);
   }
 }
-
 // The same for a coarser level whose aggregates are unions of the parent level's (AG a multiple of the parent's): rbar
 // is the cell-count weighted mean of the parent's rbar -- a few MB instead of another pass over the fine vector.
 template <class L>
@@ -2266,7 +2255,7 @@ k_cg_restrict_coarse(Grid g, CoarseGrid pc, CoarseGrid cg, const float *__restri
   const int I = (int)(lc % cg.NxC), J = (int)((lc / cg.NxC) % cg.NyC), k = (int)(lc / cg.ncolC);
   const int ratio = cg.AG / pc.AG;
   const int I0 = I * ratio, I1 = min(pc.NxC, I0 + ratio), J0 = J * ratio, J1 = min(pc.NyC, J0 + ratio);
-  float rb[Nf], fd = 0.f, wsum = 0.f;
+  float rb[Nf], wsum = 0.f;
 #pragma unroll
   for (int d = 0; d < Nf; ++d) rb[d] = 0.f;
   for (int jj = J0; jj < J1; ++jj) {
@@ -2277,21 +2266,19 @@ k_cg_restrict_coarse(Grid g, CoarseGrid pc, CoarseGrid cg, const float *__restri
       wsum += w;
 #pragma unroll
       for (int d = 0; d < Nf; ++d) rb[d] = fmaf(w, prbar[(long)d * pc.nclev + pl], rb[d]);
-      if (k < cg.Nz) fd = fmaf(w, prbar[pc.nclev + pl + pc.ncolC], fd);
     }
   }
   const float sc = 1.f / wsum;
 #pragma unroll
   for (int d = 0; d < Nf; ++d) { rb[d] *= sc; rbar[(long)d * cg.nclev + lc] = rb[d]; }
   if (k < cg.Nz) {
-    float fu = rb[0];
-    fd *= sc;
+    float fu = rb[0], ed = 0.f;
 #pragma unroll
     for (int p = 0; p < NS; ++p) {
       fu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + lc], rb[Nft + p], fu);
-      fd = fmaf(coef[(long)(CL::GD + p) * cg.ncc + lc], rb[Nft + p], fd);
+      ed = fmaf(coef[(long)(CL::GD + p) * cg.ncc + lc], rb[Nft + p], ed);
     }
-    f[lc] = make_float2(fu, fd);
+    f[lc] = make_float2(fu, ed);
   }
 }
 // the condensed two-stream column of aggregates: upward sweep for S_k, downward sweep for D, U (xc planes 0 and 1).
@@ -2317,7 +2304,7 @@ k_cg_column(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__restri
         const float4 a = sA[cc];
         const float2 ff = f[cc];
         al[u] = a.x;
-        be[u] = fmaf(a.y, ff.y, ff.x);
+        be[u] = fmaf(a.y, ff.y + rbar[nl + cc + st], ff.x);
       }
     }
 #pragma unroll
@@ -2344,7 +2331,7 @@ k_cg_column(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__restri
         const float2 ff = f[cc];
         S1[u] = xc[cc + st];
         p[u] = a.z;
-        q[u] = fmaf(a.w, S1[u], b.x * ff.y);
+        q[u] = fmaf(a.w, S1[u], b.x * (ff.y + rbar[nl + cc + st]));
         R1[u] = b.y;
       }
     }
@@ -2388,8 +2375,9 @@ k_cg_column_scan(CoarseGrid cg, const float4 *__restrict__ sA, const float2 *__r
       const float4 a = sA[cc];
       const float2 b = sB[cc];
       const float2 ff = f[cc];
-      al[u] = a.x; be[u] = fmaf(a.y, ff.y, ff.x);
-      pp[u] = a.z; qa[u] = a.w; qb[u] = b.x * ff.y; R1[u] = b.y;
+      const float fD = ff.y + rbar[nl + cc + st];
+      al[u] = a.x; be[u] = fmaf(a.y, fD, ff.x);
+      pp[u] = a.z; qa[u] = a.w; qb[u] = b.x * fD; R1[u] = b.y;
     }
   }
   const float S_bottom = rbar[(long)Nz * st + col], D_top = rbar[nl + col], R0 = Rtop[col];
@@ -2978,6 +2966,63 @@ __global__ void k_bicg32_update_xr(long n, int it, const float *__restrict__ ph,
   double acc[2] = {rho_first ? rhr : rr, rho_first ? rr : rhr};
   grid_reduce_sum<2>(acc, partials, counter, &sc[rho_first ? SC_RHO0 : SC_RR]);
 }
+// The two updates whose result is the INPUT of a preconditioner application (p before A M^-1 p, s before A M^-1 s), fused
+// with the restriction of the coarse-grid correction: a thread owns one 4 x 4 aggregate of one level, walks its Nf
+// streams (4 rows of 16 bytes each), writes the updated values and keeps their mean -- the restricted residual falls
+// out of the pass that produces the vector instead of another read of it (k_cg_restrict: 40 B per cell, 62 us at C2,
+// twice per iteration).  Needs full aggregates (Nx, Ny multiples of 4) and the finest level at AG = 4.
+//   OP 0: p = r + beta (p - omega v)   (it == 1: p = r)          OP 1: s = r - alpha v
+template <class L, int OP>
+__global__ void __launch_bounds__(128)
+k_bicg32_update_restrict(Grid g, CoarseGrid cg, int it, const float *__restrict__ r, const float *__restrict__ v,
+                         float *__restrict__ out, const double *__restrict__ sc, const float *__restrict__ coef,
+                         float *__restrict__ rbar, float2 *__restrict__ f) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, NS = 2 * L::Nfs;
+  using CL = CgLayout<NS>;
+  float c1 = 0.f, c2 = 0.f;  // OP 0: beta, omega; OP 1: alpha
+  if (OP == 0) { if (it > 1) { const BicgScalars k = bicg_scalars(sc, it, true); c1 = (float)k.beta; c2 = (float)k.omega; } }
+  else c1 = (float)(sc[sc_rho_slot(it)] / sc[SC_RHV]);
+  const long lc = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= cg.nclev) return;
+  const int I = (int)(lc % cg.NxC), J = (int)((lc / cg.NxC) % cg.NyC), k = (int)(lc / cg.ncolC);
+  const long base = ((long)k * g.Ny + 4 * J) * g.Nx + 4 * I;
+  float rb[Nf];
+#pragma unroll
+  for (int d = 0; d < Nf; ++d) {
+    float acc = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const long q = (long)d * g.nlev + base + (long)jj * g.Nx;
+      const float4 a = *reinterpret_cast<const float4 *>(r + q);
+      float4 o;
+      if (OP == 0) {
+        if (it == 1) o = a;
+        else {
+          const float4 pp = *reinterpret_cast<const float4 *>(out + q), vv = *reinterpret_cast<const float4 *>(v + q);
+          o.x = fmaf(c1, fmaf(-c2, vv.x, pp.x), a.x); o.y = fmaf(c1, fmaf(-c2, vv.y, pp.y), a.y);
+          o.z = fmaf(c1, fmaf(-c2, vv.z, pp.z), a.z); o.w = fmaf(c1, fmaf(-c2, vv.w, pp.w), a.w);
+        }
+      } else {
+        const float4 vv = *reinterpret_cast<const float4 *>(v + q);
+        o.x = fmaf(-c1, vv.x, a.x); o.y = fmaf(-c1, vv.y, a.y); o.z = fmaf(-c1, vv.z, a.z); o.w = fmaf(-c1, vv.w, a.w);
+      }
+      *reinterpret_cast<float4 *>(out + q) = o;
+      acc += (o.x + o.y) + (o.z + o.w);
+    }
+    rb[d] = acc * (1.f / 16.f);
+    rbar[(long)d * cg.nclev + lc] = rb[d];
+  }
+  if (k < cg.Nz) {
+    float fu = rb[0], ed = 0.f;
+#pragma unroll
+    for (int p = 0; p < NS; ++p) {
+      fu = fmaf(coef[(long)(CL::GU + p) * cg.ncc + lc], rb[Nft + p], fu);
+      ed = fmaf(coef[(long)(CL::GD + p) * cg.ncc + lc], rb[Nft + p], ed);
+    }
+    f[lc] = make_float2(fu, ed);
+  }
+}
+
 // Residual replacement (reliable update): the recursion's fp32 residual is replaced by the TRUE residual b - A x
 // (fp64, A x in `ax`), the search directions p, v are kept.  Writes the same pair of slots k_bicg32_update_xr wrote for
 // iteration `it` -- (r, r) and rho(it+1) = (rh, r) -- so the next iteration continues the same Krylov recursion.

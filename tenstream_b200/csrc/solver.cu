@@ -1269,8 +1269,9 @@ static int column_block(pprts_b200_solver *s, K kernel, int *cache) {
   return *cache = best;
 }
 
-template <class L, class CT, class VT>
-static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
+// once per set of coefficients: reflectances of the column solve, packed planes, Galerkin column blocks of the aggregates
+template <class L, class CT>
+static void prec_setup_t(pprts_b200_solver *s) {
   if constexpr (L::Nft == 2) {
     const Grid &g = s->g;
     if (!s->prec_ready) {
@@ -1296,6 +1297,20 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
       }
       s->prec_ready = true;
     }
+  }
+}
+// can the restriction of the coarse-grid correction ride on the vector update that produces the preconditioner's input?
+static bool cg_fused_restrict(const pprts_b200_solver *s) {
+  static const bool off = getenv("PPRTS_B200_CG_SEPARATE_RESTRICT") != nullptr;
+  const Grid &g = s->g;
+  return !off && s->ncgl > 0 && s->cgl[0].c.AG == 4 && (g.Nx & 3) == 0 && (g.Ny & 3) == 0;
+}
+
+template <class L, class CT, class VT>
+static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z, bool have_rbar = false) {
+  if constexpr (L::Nft == 2) {
+    const Grid &g = s->g;
+    prec_setup_t<L, CT>(s);
     constexpr bool can_pack = std::is_same<VT, float>::value;
     const bool packed = can_pack && s->precPU;
     const int slot = (std::is_same<VT, float>::value ? 2 : 0) + (packed ? 2 : 0);
@@ -1311,9 +1326,10 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
     for (int l = 0; l < s->ncgl; ++l) {  // restriction: the finest level reads r, the others their parent level
       auto &lv = s->cgl[l];
       const CoarseGrid &c = lv.c;
-      if (l == 0)
-        LAUNCH(s, FAM_PRECOND, (k_cg_restrict<L, VT>), nblk(c.nclev, 128), 128, g, c, r, (const float *)lv.coef, lv.rbar, (float2 *)lv.e);
-      else
+      if (l == 0) {
+        if (!have_rbar)
+          LAUNCH(s, FAM_PRECOND, (k_cg_restrict<L, VT>), nblk(c.nclev, 128), 128, g, c, r, (const float *)lv.coef, lv.rbar, (float2 *)lv.e);
+      } else
         LAUNCH(s, FAM_PRECOND, (k_cg_restrict_coarse<L>), nblk(c.nclev, 128), 128, g, s->cgl[l - 1].c, c, (const float *)s->cgl[l - 1].rbar,
                (const float *)lv.coef, lv.rbar, (float2 *)lv.e);
     }
@@ -1361,7 +1377,8 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z) {
   }
 }
 static void launch_prec(pprts_b200_solver *s, const double *r, double *z) { DISPATCH_LC(s, (launch_prec_t<L, CT, double>(s, r, z))); }
-static void launch_prec32(pprts_b200_solver *s, const float *r, float *z) { DISPATCH_LC(s, (launch_prec_t<L, CT, float>(s, r, z))); }
+static void launch_prec32(pprts_b200_solver *s, const float *r, float *z, bool have_rbar = false) { DISPATCH_LC(s, (launch_prec_t<L, CT, float>(s, r, z, have_rbar))); }
+static void prec_setup(pprts_b200_solver *s) { DISPATCH_LC(s, (prec_setup_t<L, CT>(s))); }
 
 // explicit_ediff (src/pprts_explicit.F90:461-713) analogue: stationary relaxation x += M^-1 (b - A x), all columns
 // at once; residual = ||x_n - x_{n-1}||_2 (mean over ranks of the local norms, :620-626), converged when it is < atol
@@ -1430,6 +1447,8 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   // experiment switch (tools/mixed_check.py): residual replacement after a failed true-residual check.  Measured on a
   // 320x320x128, dx = 25 m domain: solar 254 -> 229 iterations but thermal 198 -> 286, so it is off by default.
   static const bool replace_r = getenv("PPRTS_B200_REPLACE_R") != nullptr;
+  if (prec) prec_setup(s);  // the fused update + restriction kernels read the aggregates' coefficients
+  const bool fused = prec && cg_fused_restrict(s);
   static const int flush_every = getenv("PPRTS_B200_FLUSH_EVERY") ? std::max(1, atoi(getenv("PPRTS_B200_FLUSH_EVERY"))) : (1 << 30);
   CU(cudaMemsetAsync(xc, 0, (size_t)n * sizeof(float), s->stream));
   int total = 0;
@@ -1456,11 +1475,19 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
     double inner = 0.9 * target;  // a little below: the recursive residual drifts from the true one by O(eps32)
     bool restart = false;
     for (int it = 1; total < maxit && !restart && !converged; ++it) {
-      LAUNCH(s, FAM_VEC, k_bicg32_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
-      if (prec) launch_prec32(s, p, ph);
+      if (fused) {  // the update also leaves the restricted vector of the coarse-grid correction behind
+        const CoarseGrid &c0 = s->cgl[0].c;
+        DISPATCH_L(s, LAUNCH(s, FAM_VEC, (k_bicg32_update_restrict<L, 0>), nblk(c0.nclev, 128), 128, g, c0, it, (const float *)r, (const float *)v, p,
+                              (const double *)s->sc, (const float *)s->cgl[0].coef, s->cgl[0].rbar, (float2 *)s->cgl[0].e));
+      } else LAUNCH(s, FAM_VEC, k_bicg32_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
+      if (prec) launch_prec32(s, p, ph, fused);
       if ((rc = launch_matmult<1, float>(s, ph, v, rh, s->sc + SC_RHV))) return rc;
-      LAUNCH(s, FAM_VEC, k_bicg32_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
-      if (prec) launch_prec32(s, sv, sh);
+      if (fused) {
+        const CoarseGrid &c0 = s->cgl[0].c;
+        DISPATCH_L(s, LAUNCH(s, FAM_VEC, (k_bicg32_update_restrict<L, 1>), nblk(c0.nclev, 128), 128, g, c0, it, (const float *)r, (const float *)v, sv,
+                              (const double *)s->sc, (const float *)s->cgl[0].coef, s->cgl[0].rbar, (float2 *)s->cgl[0].e));
+      } else LAUNCH(s, FAM_VEC, k_bicg32_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
+      if (prec) launch_prec32(s, sv, sh, fused);
       if ((rc = launch_matmult<2, float>(s, sh, t, sv, s->sc + SC_TS))) return rc;
       LAUNCH(s, FAM_VEC, k_bicg32_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, xc, r, s->partials, s->counter, s->sc);
       dirty = true;

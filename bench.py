@@ -566,7 +566,7 @@ def leg_c3(P, torch, dist, world, rank, local, lut, args):
     # (Fortran order: band ib is one contiguous block); a host thread fills the next stack -- the host model computing
     # the optical properties of the next g-points -- while solve_bands works through the current one.
     from concurrent.futures import ThreadPoolExecutor
-    CHUNK = 8
+    CHUNK = 4
     stacks = []
     for _ in range(2):
         t, v = pinned_f(torch, sc["kabs"].shape + (CHUNK,))

@@ -248,6 +248,7 @@ struct pprts_b200_solver {
     float *coef = nullptr, *R = nullptr, *sA = nullptr, *sB = nullptr, *rbar = nullptr, *e = nullptr, *x = nullptr;
   };
   int ncgl = 0;       // number of aggregate levels in use (0: plain column solve)
+  bool cg_off = false;  // apply the column solve alone (stationary relaxation needs a convergent splitting)
   CgLevel cgl[3];     // [0] is folded into the column sweeps, further (coarser) ones are added by k_cg_prolong
   int prec_block[6] = {0, 0, 0, 0, 0, 0};  // chosen block sizes of k_prec_up / k_prec_down (column_block)
   double *res[4] = {nullptr}, *acc[4] = {nullptr}, *out_stage = nullptr;
@@ -1321,9 +1322,10 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z, bool have_rb
     const VT *pR, *pI;  // the sweeps read R and Inv in the precision of their vectors
     if constexpr (std::is_same<VT, float>::value) { pR = s->precRf; pI = s->precInvf; } else { pR = s->precR; pI = s->precInv; }
     // coarse-grid correction: xc = (P^T A P)_col^-1 P^T r first, the sweeps add P xc to z where they store its entries
+    const int ncgl = s->cg_off ? 0 : s->ncgl;
     CgAdd add{nullptr, 0, 0, 1, 1};
     static const bool cg_unfused = getenv("PPRTS_B200_CG_UNFUSED") != nullptr;  // separate prolongation pass, for comparison
-    for (int l = 0; l < s->ncgl; ++l) {  // restriction: the finest level reads r, the others their parent level
+    for (int l = 0; l < ncgl; ++l) {  // restriction: the finest level reads r, the others their parent level
       auto &lv = s->cgl[l];
       const CoarseGrid &c = lv.c;
       if (l == 0) {
@@ -1333,7 +1335,7 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z, bool have_rb
         LAUNCH(s, FAM_PRECOND, (k_cg_restrict_coarse<L>), nblk(c.nclev, 128), 128, g, s->cgl[l - 1].c, c, (const float *)s->cgl[l - 1].rbar,
                (const float *)lv.coef, lv.rbar, (float2 *)lv.e);
     }
-    for (int l = s->ncgl - 1; l >= 0; --l) {  // aggregate-column solves, coarsest first: each level hands its result down
+    for (int l = ncgl - 1; l >= 0; --l) {  // aggregate-column solves, coarsest first: each level hands its result down
       auto &lv = s->cgl[l];
       const CoarseGrid &c = lv.c;
       static const bool cg_serial = getenv("PPRTS_B200_CG_SERIAL_COLUMN") != nullptr;
@@ -1343,11 +1345,11 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z, bool have_rb
       else
         LAUNCH(s, FAM_PRECOND, k_cg_column, nblk(c.ncolC, 32), 32, c, (const float4 *)lv.sA, (const float2 *)lv.sB,
                (const float *)lv.R, (const float *)lv.rbar, (const float2 *)lv.e, lv.x);
-      const bool coarser = l + 1 < s->ncgl;
+      const bool coarser = l + 1 < ncgl;
       LAUNCH(s, FAM_PRECOND, (k_cg_sides<L>), nblk(c.nclev, 128), 128, c, (const float *)lv.coef, (const float *)lv.rbar, lv.x,
              coarser ? s->cgl[l + 1].c : c, coarser ? (const float *)s->cgl[l + 1].x : (const float *)nullptr);
     }
-    if (s->ncgl > 0 && !cg_unfused) { const CoarseGrid &c = s->cgl[0].c; add = CgAdd{s->cgl[0].x, c.nclev, c.ncolC, c.AG, c.NxC}; }
+    if (ncgl > 0 && !cg_unfused) { const CoarseGrid &c = s->cgl[0].c; add = CgAdd{s->cgl[0].x, c.nclev, c.ncolC, c.AG, c.NxC}; }
     if (packed) {
       LAUNCH(s, FAM_PRECOND, (k_prec_up<L, CT, VT, can_pack>), nblk(g.ncol, bu), bu, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
              pR, pI, r, z, (int)(s->cfg.precond != 2), add, (const __half2 *)s->precPU);
@@ -1359,7 +1361,7 @@ static void launch_prec_t(pprts_b200_solver *s, const VT *r, VT *z, bool have_rb
       LAUNCH(s, FAM_PRECOND, (k_prec_down<L, CT, VT, false>), nblk(g.ncol, bd), bd, g, s->n1d, (const CT *)s->f2f, s->a11, s->a12,
              pR, pI, r, z, (int)(s->cfg.precond != 2), add, (const __half2 *)nullptr);
     }
-    if (s->ncgl > 0 && cg_unfused)
+    if (ncgl > 0 && cg_unfused)
       LAUNCH(s, FAM_PRECOND, (k_cg_prolong<VT>), vec_grid((long)L::Nf * g.nlev / 4), VEC_BLOCK, g, s->cgl[0].c, (int)L::Nf, (const float *)s->cgl[0].x, z);
   } else {  // several up/down pairs of top streams (3_24): block recurrence, no software pipelining
     const Grid &g = s->g;
@@ -1393,6 +1395,9 @@ static int solve_ediff_explicit(pprts_b200_solver *s, Solution &sol) {
   if (sol.first_diff) { rtol = std::min(rtol, rtol_d); atol = std::min(atol, atol_d); }
   double *x = sol.ediff, *r = s->kr[0], *z = s->kr[1];
   const bool prec = precond_available(s);
+  // x += M^-1 (b - A x) converges for the column splitting; the ADDITIVE coarse-grid correction counts the smooth modes
+  // twice, which a Krylov method does not mind but a stationary iteration does: the relaxation uses the column solve alone
+  struct CgOff { pprts_b200_solver *s; bool was; CgOff(pprts_b200_solver *s_) : s(s_), was(s_->cg_off) { s->cg_off = true; } ~CgOff() { s->cg_off = was; } } cg_guard(s);
   int rc = need_comm(s);
   if (rc) return rc;
   double first = 0.0;

@@ -581,7 +581,7 @@ def test_solve_bands_equals_band_loop(P, gpu_lut):
 
 
 # ---- alternative HOT LOOP D: explicit relaxation -----------------------------------------------------
-@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("precond", [0, 1, 3])
 @pytest.mark.parametrize("solar", [True, False])
 def test_explicit_relaxation_vs_oracle_sor(P, gpu_lut, oracle_lut, precond, solar):
     """-solar_diff_explicit / -thermal_diff_explicit: the GPU's all-columns-at-once relaxation and the oracle's

@@ -322,7 +322,7 @@ def run_ours(args):
     achieved = bytes_mv / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     traffic = None
     try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload only)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if (args.nx, args.ny, Nz) == (256, 256, 80):
             t = tj["k_matmult_tma_float" if mixed else "k_matmult_tma_double"]
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]

@@ -48,7 +48,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def kernels(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: an .ncu-rep, or the output of `ncu -i <rep> --page raw --csv` taken on the GPU box (reports of many kernels exceed
+    # what gpurun copies back)
+    out = open(src).read() if src.endswith(".csv") else subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(out.splitlines()))
     hdr, units = r[0], r[1]
     with open(dst, "w") as f:

@@ -188,6 +188,7 @@ struct Solution {  // t_state_container (src/pprts_base.F90:137-169)
   bool lset = false, lsolar_rad = false, lthermal_rad = false, lchanged = true, lWm2_dir = true, lWm2_diff = true;
   double *edir = nullptr, *ediff = nullptr, *abso = nullptr;
   bool first_dir = true, first_diff = true;  // residual_history(1) < 0
+  bool ediff_zero = false;  // ediff is exactly zero (fresh container, no warm start): A x needs no MatMult
   long last_use = 0;  // max_cached_solutions: the least recently used stored solution is dropped first
   int niter_dir = 0, niter_diff = 0;
   double res_dir = 0, res_diff = 0;
@@ -1461,8 +1462,11 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   sol.niter_diff = 0;
   bool have_ax = false;  // ax = A x of the current x is already there (a true-residual check that led to a new cycle)
   for (int cycle = 0; !converged && cycle < 64; ++cycle) {
-    if (!have_ax && (rc = launch_matmult<0, double>(s, x, ax, nullptr, nullptr))) return rc;
+    if (cycle == 0 && sol.ediff_zero) {  // cold start: A x = 0 without looking (one fp64 MatMult per band)
+      CU(cudaMemsetAsync(ax, 0, (size_t)n * sizeof(double), s->stream));
+    } else if (!have_ax && (rc = launch_matmult<0, double>(s, x, ax, nullptr, nullptr))) return rc;
     have_ax = false;
+    sol.ediff_zero = false;
     LAUNCH(s, FAM_VEC, k_mixed_init, vec_grid(n), VEC_BLOCK, n, s->b, ax, r, rh, s->partials, s->counter, s->sc);
     if ((rc = allreduce_scalars(s, s->sc + SC_RR, 3))) return rc;
     if ((rc = read_scalars(s))) return rc;
@@ -1791,6 +1795,7 @@ static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool ltherma
       CU(cudaMemsetAsync(sol.abso, 0, (size_t)g.ncell * sizeof(double), s->stream));
     }
     sol.lset = true; sol.lsolar_rad = lsolar; sol.lthermal_rad = lthermal; sol.lchanged = true;
+    sol.ediff_zero = true;
     sol.lWm2_dir = sol.lWm2_diff = true; sol.first_dir = sol.first_diff = true;
     return 0;
   };
@@ -1806,6 +1811,7 @@ static int get_solution(pprts_b200_solver *s, int uid, bool lsolar, bool ltherma
           sol.lWm2_dir = last.lWm2_dir;
         }
         CU(cudaMemcpyAsync(sol.ediff, last.ediff, (size_t)s->Nf * g.nlev * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        sol.ediff_zero = false;
         sol.lWm2_diff = last.lWm2_diff;
       }
     }
@@ -1866,8 +1872,11 @@ static int solve_impl(pprts_b200_solver *s, int lthermal, int lsolar, double edi
     CU(cudaMemcpyAsync(sol.ediff, s->b, n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
     sol.niter_diff = 0;
     sol.res_diff = atol;
+    sol.ediff_zero = false;
   } else {
-    if ((rc = solve_ediff(s, sol))) return rc;
+    rc = solve_ediff(s, sol);
+    sol.ediff_zero = false;
+    if (rc) return rc;
   }
   sol.lchanged = true;
   sol.lWm2_diff = false;

@@ -85,8 +85,10 @@ def test_c2_solar_properties(P, bench_lut):
     P.solve_pprts(s, False, True, sc["edirTOA"], 1)
     rt = P.pprts_get_result(s, 1)
     assert abs(closure(sc, rt) - 1) < 1e-7, closure(sc, rt)
+    # (a residual criterion, not an error bound: MyKSPConverged stops the reference at the same point; the 1e-5 contract at
+    # equal tolerance is held against the committed converged oracle result in tests/test_gpu_config_goldens.py)
     for name, a, b in zip(("edn", "eup", "abso"), r1[:3], rt[:3]):
-        assert relmax(a, b) < 5e-4, name
+        assert relmax(a, b) < 2e-4, name
     P.destroy_pprts(s)
 
 
@@ -117,7 +119,7 @@ def test_c2_thermal_properties(P, bench_lut):
     net_in = (edn[0] - eup[0]).sum() - (edn[-1] - eup[-1]).sum()
     assert abs((abso * sc["dz1d"][:, None, None]).sum() - net_in) < 1e-7 * edn[-1].sum()
     for name, a, b in zip(("edn", "eup", "abso"), res[True][:3], res[False][:3]):
-        assert relmax(a, b) < 5e-4, name
+        assert relmax(a, b) < 2e-4, name
 
 
 def test_c2_mirror_symmetry(P, bench_lut):

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI, via tenstream_b200.pprts) against the CPU oracle on identical inputs
 and identical synthetic tables.  Tolerances: interpolated coefficients 1e-12 relative (fp64, north_star), fluxes and
 absorption 1e-5 relative with both sides converged well below that (rtol 1e-10)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -71,6 +73,49 @@ def test_lookup_probe_vs_oracle(P, gpu_lut, oracle_lut, phi0, theta0):
         if mode == 3:
             assert np.array_equal(got, want)   # same corner order, same fma chain: bit-identical
     P.destroy_pprts(s); osv.destroy()
+
+
+def test_lookup_on_a_direct_table_of_reference_size(P, tmp_path):
+    """The real LUT_3_10 direct tables are several GB (85 560 lattice points x the sun-angle lattice x 39 coefficients):
+    byte offsets beyond 2^32 in the mmap reader and in the (phi, theta) contraction of set_angles.  A synthetic table on the
+    reference's full tau / w0 / aspect / g axes with a 10 x 19 sun-angle lattice (2.5 GB) is written, opened by both sides,
+    and the direct coefficients of random cells at a sun position between lattice points -- far into the file -- have to
+    agree with the oracle, which interpolates in all six dimensions straight from the file."""
+    import shutil
+    from oracle import binding as ob
+    from tenstream_b200 import lut as L
+    cfg = L.LutConfig(solver_id=310, phi=L.linspace_f32(0, 90, 10), theta=L.linspace_f32(0, 90, 19))
+    free = shutil.disk_usage(str(tmp_path)).free
+    if free < 6e9:
+        pytest.skip("needs 3 GB of scratch space")
+    paths = L.write_synthetic_lut(cfg, os.path.join(str(tmp_path), "LUT"))
+    assert os.path.getsize(paths["Sdir"]) > 1.9e9
+    lut, olut = P.Lut(cfg, paths), ob.OracleLut(cfg, paths)
+    try:
+        rng = np.random.default_rng(5)
+        n = 200
+        kabs = 10 ** rng.uniform(-9, -1, n)
+        ksca = 10 ** rng.uniform(-9, -1, n)
+        g = rng.uniform(0, 1.0, n)
+        dz = 10 ** rng.uniform(0.3, 3.3, n)
+        dx = 100.0
+        for phi0, theta0 in ((77., 83.), (250., 61.5)):      # high phi / theta indices: the far end of the file
+            sd = P.sundir_from_angles(phi0, theta0)
+            s = P.init_pprts(0, 2, 3, 3, dx, dx, sd, dz1d=np.full(2, 50.), lut=lut)
+            osv = ob.OracleSolver(olut, 2, 3, 3, dx, dx, sd, np.full(2, 50.))
+            sun = osv.suninfo()
+            for mode in (1, 2):
+                got = s.lookup_coeffs(mode, kabs, ksca, g, dz)
+                want = np.array([olut.get_coeff(kabs[q], ksca[q], g[q], dz[q], dx, mode, sun["symmetry_phi"], sun["theta"],
+                                                sun["xinc"] == 0, sun["yinc"] == 0) for q in range(n)])
+                scale = np.abs(want).max()
+                err = np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * scale)
+                assert err.max() < 1e-12, (phi0, theta0, mode, err.max())
+            P.destroy_pprts(s); osv.destroy()
+    finally:
+        lut.close()
+        for f in paths.values():
+            os.remove(f)
 
 
 @pytest.mark.parametrize("coeff_fp32", [False, True])

@@ -661,8 +661,12 @@ k_geometric_coeffs(Grid g, int kstart, int vmode, double sunx, double suny, doub
 // slope_correction_fluxes (src/pprts_postprocess.F90:130-196) on a direct-flux level field in the device layout:
 // hgrad (src/pprts.F90:621-638) = centred differences of the level heights (vh = -cumsum dz, periodic single domain);
 // latm scales every level by (sundir.ez)/(sundir.n), lslope the surface level by max(0, (sundir.n)/(sundir.ez)).
+// Decomposed domain: the heights of the neighbouring ranks' edge columns (halo_fill_5pt of atm%hhl, src/pprts.F90:603)
+// arrive once, at comm_init, in four planes: gh[0] = column i = -1 (west neighbour's last), gh[1] = i = Nx, gh[2] = row
+// j = -1, gh[3] = j = Ny, each [level][j or i].
+struct HeightGhosts { const double *g[4]; };
 __global__ void k_slope_correction(Grid g, int lslope, int latm, double sunx, double suny, double sunz,
-                                   const double *__restrict__ vh, double *__restrict__ edir) {
+                                   const double *__restrict__ vh, HeightGhosts gh, double *__restrict__ edir) {
   long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= g.nlev) return;
   const int k = (int)(l / g.ncol);
@@ -670,14 +674,29 @@ __global__ void k_slope_correction(Grid g, int lslope, int latm, double sunx, do
   const int i = (int)(col % g.Nx), j = (int)(col / g.Nx);
   const int im = i == 0 ? g.Nx - 1 : i - 1, ip = wrap_p(i, g.Nx), jm = j == 0 ? g.Ny - 1 : j - 1, jp = wrap_p(j, g.Ny);
   const long lk = (long)k * g.ncol;
-  const double gx = (vh[lk + (long)j * g.Nx + ip] - vh[lk + (long)j * g.Nx + im]) / (2.0 * g.dx);
-  const double gy = (vh[lk + (long)jp * g.Nx + i] - vh[lk + (long)jm * g.Nx + i]) / (2.0 * g.dy);
+  const double hxp = (g.gx && i + 1 == g.Nx) ? gh.g[1][(long)k * g.Ny + j] : vh[lk + (long)j * g.Nx + ip];
+  const double hxm = (g.gx && i == 0) ? gh.g[0][(long)k * g.Ny + j] : vh[lk + (long)j * g.Nx + im];
+  const double hyp = (g.gy && j + 1 == g.Ny) ? gh.g[3][(long)k * g.Nx + i] : vh[lk + (long)jp * g.Nx + i];
+  const double hym = (g.gy && j == 0) ? gh.g[2][(long)k * g.Nx + i] : vh[lk + (long)jm * g.Nx + i];
+  const double gx = (hxp - hxm) / (2.0 * g.dx);
+  const double gy = (hyp - hym) / (2.0 * g.dy);
   const double nn = sqrt(gx * gx + gy * gy + 1.0);
   const double sn = sunx * (-gx / nn) + suny * (-gy / nn) + sunz * (1.0 / nn);
   double e = edir[l];
   if (latm) e = e * (sunz / sn);
   if (lslope && k == g.Nz) e = e * fmax(0.0, sn / sunz);
   edir[l] = e;
+}
+// edge columns / rows of a level field -> contiguous planes: which = 0: i = 0, 1: i = Nx-1 ([level][j]); 2: j = 0, 3: j = Ny-1
+__global__ void k_pack_edge(Grid g, int which, const double *__restrict__ f, double *__restrict__ out) {
+  const long n = (long)(g.Nz + 1) * (which < 2 ? g.Ny : g.Nx);
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int len = which < 2 ? g.Ny : g.Nx;
+  const int k = (int)(q / len), t = (int)(q % len);
+  const long lk = (long)k * g.ncol;
+  out[q] = which == 0 ? f[lk + (long)t * g.Nx] : which == 1 ? f[lk + (long)t * g.Nx + g.Nx - 1]
+         : which == 2 ? f[lk + t] : f[lk + (long)(g.Ny - 1) * g.Nx + t];
 }
 
 // convolve_ediff_srfc (src/pprts_base.F90:1733-1868) on one level field [Ny][Nx] of a single periodic domain: one pass

@@ -239,6 +239,7 @@ struct pprts_b200_solver {
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
   double *precR = nullptr, *precInv = nullptr;
   double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
+  double *vh_ghost[4] = {nullptr, nullptr, nullptr, nullptr};  // decomposed: level heights of the neighbours' edge columns (slope correction)
   bool have_dz3d = false;                   // init_pprts(dz3d=...): atm%hgrad exists (src/pprts.F90:621)
   float *precRf = nullptr, *precInvf = nullptr;  // fp32 copies for the sweeps on fp32 vectors (krylov_fp32, 3_24 block form)
   void *precPU = nullptr, *precPD = nullptr;     // half2 planes: packed coefficients of the fp32 column sweeps (kernels.cuh PrecPack)
@@ -793,6 +794,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->precPU); cudaFree(s->precPD); cudaFree(s->vh_atm);
+  for (double *p : s->vh_ghost) cudaFree(p);
   for (auto &sp : s->spare) { cudaFree(sp[0]); cudaFree(sp[1]); cudaFree(sp[2]); }
   for (auto &lv : s->cgl) { cudaFree(lv.coef); cudaFree(lv.R); cudaFree(lv.sA); cudaFree(lv.sB); cudaFree(lv.rbar); cudaFree(lv.e); cudaFree(lv.x); }
   for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
@@ -2254,6 +2256,32 @@ extern "C" int pprts_b200_comm_init(pprts_b200_solver *s, int nranks, int rank, 
     CU(cudaMemcpyAsync(h, s->sc + SC_TMP, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     s->unconstrained_fraction = h[0] / h[1];
+    // halo_fill_5pt of atm%hhl (src/pprts.F90:603): the level heights of the neighbours' edge columns, for the centred
+    // differences of atm%hgrad (:621-638) at the rank boundaries (slope_correction_fluxes); static, exchanged once
+    if (s->have_dz3d && s->vh) {
+      const Grid &g = s->g;
+      const size_t nx = (size_t)(g.Nz + 1) * g.Ny, ny = (size_t)(g.Nz + 1) * g.Nx;
+      double *send[4] = {nullptr, nullptr, nullptr, nullptr};
+      for (int q = 0; q < 4; ++q) {
+        const size_t n = q < 2 ? nx : ny;
+        if (!s->vh_ghost[q]) DA(s->vh_ghost[q], n);
+        CU(cudaMalloc((void **)&send[q], n * sizeof(double)));
+        LAUNCH(s, FAM_HALO, k_pack_edge, nblk((long)n, 256), 256, g, q, (const double *)s->vh, send[q]);
+      }
+      // my first column is the EAST ghost (i = Nx) of my west neighbour, my last column the WEST ghost of my east neighbour
+      NC(g_nccl.GroupStart());
+      NC(g_nccl.Send(send[0], nx, NCCL_F64, s->nb_west, s->nccl_comm, s->stream));
+      NC(g_nccl.Recv(s->vh_ghost[1], nx, NCCL_F64, s->nb_east, s->nccl_comm, s->stream));
+      NC(g_nccl.Send(send[1], nx, NCCL_F64, s->nb_east, s->nccl_comm, s->stream));
+      NC(g_nccl.Recv(s->vh_ghost[0], nx, NCCL_F64, s->nb_west, s->nccl_comm, s->stream));
+      NC(g_nccl.Send(send[2], ny, NCCL_F64, s->nb_south, s->nccl_comm, s->stream));
+      NC(g_nccl.Recv(s->vh_ghost[3], ny, NCCL_F64, s->nb_north, s->nccl_comm, s->stream));
+      NC(g_nccl.Send(send[3], ny, NCCL_F64, s->nb_north, s->nccl_comm, s->stream));
+      NC(g_nccl.Recv(s->vh_ghost[2], ny, NCCL_F64, s->nb_south, s->nccl_comm, s->stream));
+      NC(g_nccl.GroupEnd());
+      CU(cudaStreamSynchronize(s->stream));
+      for (double *p : send) cudaFree(p);
+    }
   }
   return 0;
 }
@@ -2377,11 +2405,12 @@ static void sun_vector(const pprts_b200_solver *s, double v[3]) {  // sun%sundir
 static int slope_correct_device(pprts_b200_solver *s, int lslope, int latm, double *field) {
   if (!lslope && !latm) return 0;
   if (!s->have_dz3d || !s->vh) return set_err(70, "slope correction needs a solver initialised with dz3d (atm%%hgrad not initialized!)");
-  if (s->decomposed) return set_err(71, "slope correction is not supported on an x/y-decomposed solver yet");
+  if (s->decomposed && !s->vh_ghost[0]) return set_err(71, "slope correction on a decomposed solver: call pprts_b200_comm_init first (it exchanges the level heights)");
   double sv[3];
   sun_vector(s, sv);
   const Grid &g = s->g;
-  LAUNCH(s, FAM_ABSO, k_slope_correction, nblk(g.nlev, 256), 256, g, lslope, latm, sv[0], sv[1], sv[2], (const double *)s->vh, field);
+  HeightGhosts gh{{s->vh_ghost[0], s->vh_ghost[1], s->vh_ghost[2], s->vh_ghost[3]}};
+  LAUNCH(s, FAM_ABSO, k_slope_correction, nblk(g.nlev, 256), 256, g, lslope, latm, sv[0], sv[1], sv[2], (const double *)s->vh, gh, field);
   return 0;
 }
 extern "C" int pprts_b200_slope_correction_fluxes(pprts_b200_solver *s, int lslope, int latm, double *edir) {

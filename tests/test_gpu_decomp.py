@@ -135,3 +135,76 @@ def test_decomposed_matches_single_gpu_8_10(tmp_path_factory, nxp, nyp, phi0):
 def test_decomposed_2x2_four_gpus(small_lut):
     _, paths = small_lut
     _run(paths, 2, 2, 310, 120.0)
+
+
+def _slope_worker(rank, world, port, paths, nxp, nyp, q):
+    """slope_correction_fluxes on a decomposed terrain-following domain: atm%hgrad uses the neighbours' heights at the rank
+    boundaries (halo_fill_5pt of atm%hhl, src/pprts.F90:603-638), exchanged once at comm_init"""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tenstream_b200 import lut as L
+    from tenstream_b200 import pprts as P
+    from tenstream_b200.parallel import CartDecomposition
+    cfg = L.small_test_config(310)
+    lut = P.Lut(cfg, paths)
+    Nz, Nx, Ny = 6, 16, 12
+    ii, jj = np.meshgrid(np.arange(Nx), np.arange(Ny), indexing="ij")
+    hill = 0.3 * np.exp(-((ii - 7.5) ** 2 + (jj - 5.0) ** 2) / 18.0) + 0.1 * np.sin(2 * np.pi * ii / Nx)   # periodic in x, y
+    dz3d = np.broadcast_to(70.0 * (1.0 - hill)[None], (Nz, Nx, Ny)).copy()
+    sd = P.sundir_from_angles(140., 50.)
+    dec = CartDecomposition(Nx, Ny, nxp, nyp, rank)
+    loc = lambda a: np.asfortranarray(dec.local(a))    # noqa: E731
+    s = P.init_pprts(0, Nz, dec.xm, dec.ym, 100., 100., sd, dz3d=loc(dz3d), lut=lut, device=rank, nxproc=dec.nxproc,
+                     nyproc=dec.nyproc, rank=rank)
+    uid = [P.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    s.comm_init(world, rank, uid[0])
+    field = np.random.default_rng(4).uniform(100., 900., (Nz + 1, Nx, Ny))
+    out = {}
+    for name, (lslope, latm) in (("slope", (True, False)), ("atm", (False, True)), ("both", (True, True))):
+        out[name] = P.slope_correction_fluxes(s, loc(field).copy(order="F"), lslope, latm)
+    ref = None
+    if rank == 0:
+        g = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz3d=dz3d, lut=lut, device=rank)
+        ref = {name: P.slope_correction_fluxes(g, np.asfortranarray(field).copy(order="F"), *flags)
+               for name, flags in (("slope", (True, False)), ("atm", (False, True)), ("both", (True, True)))}
+        P.destroy_pprts(g)
+    q.put((rank, (dec.xs, dec.xm, dec.ys, dec.ym), out, ref))
+    dist.barrier()
+    P.destroy_pprts(s)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nxp,nyp", [(2, 1), (1, 2)])
+def test_slope_correction_on_a_decomposed_hill(small_lut, nxp, nyp):
+    import torch
+    import torch.multiprocessing as mp
+    _, paths = small_lut
+    world = nxp * nyp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slope_worker, args=(r, world, port, paths, nxp, nyp, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, box, out, ref = q.get(timeout=600)
+        res[r] = (box, out, ref)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = res[0][2]
+    for r in range(world):
+        (xs, xm, ys, ym), out, _ = res[r]
+        for name in ("slope", "atm", "both"):
+            want = ref[name][:, xs:xs + xm, ys:ys + ym]
+            assert np.abs(out[name] - want).max() <= 1e-12 * np.abs(want).max(), (r, name)
+        assert np.abs(ref["both"] - ref["slope"]).max() > 1.0      # the corrections do something on this hill

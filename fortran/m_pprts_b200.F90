@@ -46,7 +46,7 @@ module m_pprts_b200
       & diff_explicit, krylov_fp32, collapseindex
     real(c_double) :: max_solution_err, max_solution_time
     integer(c_int) :: geometric_coeffs
-    integer(c_int) :: accept_incomplete_solve, gmres_restart, max_cached_solutions
+    integer(c_int) :: accept_incomplete_solve, gmres_restart, max_cached_solutions, open_bc
   end type
 
   interface
@@ -204,10 +204,11 @@ contains
   !> the halo exchange is bootstrapped over icomm (rank 0 creates the NCCL id, MPI_Bcast distributes it).
   !> The trailing optional arguments carry what the reference reads from its options database:
   !> collapseindex (init_pprts argument), -pprts_geometric_coeffs, -max_solution_err, -max_solution_time,
-  !> -twostr_ratio, -solar_diff_ksp_rtol / -thermal_diff_ksp_rtol (one value for both here), -accept_incomplete_solve
+  !> -twostr_ratio, -solar_diff_ksp_rtol / -thermal_diff_ksp_rtol (one value for both here), -accept_incomplete_solve,
+  !> -pprts_open_bc
   subroutine init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver, lut, solver_id, dz1d, dz3d, nxproc, nyproc, device, &
       & collapseindex, lgeometric_coeffs, max_solution_err, max_solution_time, twostr_ratio, ksp_rtol, &
-      & ltop_bottom_faces_planar, ltop_bottom_planes_parallel, laccept_incomplete_solve)
+      & ltop_bottom_faces_planar, ltop_bottom_planes_parallel, laccept_incomplete_solve, lopen_bc)
     use mpi
     integer, intent(in) :: icomm
     integer(iintegers), intent(in) :: Nz, Nx, Ny
@@ -221,6 +222,7 @@ contains
     integer(iintegers), intent(in), optional :: collapseindex
     logical, intent(in), optional :: lgeometric_coeffs, ltop_bottom_faces_planar, ltop_bottom_planes_parallel
     logical, intent(in), optional :: laccept_incomplete_solve  !< -accept_incomplete_solve (src/pprts.F90:4270-4275)
+    logical, intent(in), optional :: lopen_bc  !< -pprts_open_bc (src/pprts.F90:462-463, src/pprts_base.F90:1189-1316)
     real(ireals), intent(in), optional :: max_solution_err, max_solution_time, twostr_ratio, ksp_rtol
     type(c_config) :: cfg
     character(kind=c_char) :: nccl_id(128)
@@ -243,6 +245,7 @@ contains
     if (present(twostr_ratio)) cfg%twostr_ratio = twostr_ratio
     if (present(ksp_rtol)) cfg%rtol = ksp_rtol
     if (present(laccept_incomplete_solve)) cfg%accept_incomplete_solve = merge(1, 0, laccept_incomplete_solve)
+    if (present(lopen_bc)) cfg%open_bc = merge(1, 0, lopen_bc)
     if (present(nxproc) .and. present(nyproc)) then
       call mpi_comm_rank(icomm, myid, ierr)
       call mpi_comm_size(icomm, nranks, ierr)

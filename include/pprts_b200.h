@@ -132,6 +132,13 @@ typedef struct {
   /* keep_solutions = 1 only: at most this many solutions stay cached (least recently used dropped first, never the
    * uid being solved or uid - 1); <= 0: unlimited, like solver%solutions(-1000:1000) */
   int max_cached_solutions;
+  /* -pprts_open_bc (src/pprts.F90:462-463): open instead of cyclic boundaries for the DIRECT beam -- it enters through
+   * the sunward domain edges with the side fluxes of a single-column solve of the edge columns (set_open_bc /
+   * single_column_solve, src/pprts_base.F90:1189-1458) and leaves through the others without re-entering
+   * (exchange_direct_boundary sends zeros across the edge, src/pprts_explicit.F90:262-306; the sweep takes the inflow,
+   * :358-378).  As there, the stored solution keeps zeros on the inflow faces it owns, and the source term, absorption
+   * and the diffuse solve go on treating the stored beam periodically.  Not with geometric_coeffs or buildings. */
+  int open_bc;
 } pprts_b200_config;
 
 void pprts_b200_default_config(pprts_b200_config *cfg);

@@ -48,7 +48,8 @@ class _Config(C.Structure):
                 ("twostr_ratio", C.c_double), ("coeff_fp32", C.c_int), ("by_coeff_divergence", C.c_int),
                 ("diff_solver", C.c_int), ("rtol", C.c_double), ("atol", C.c_double),
                 ("maxit_dir", C.c_int), ("maxit_diff", C.c_int), ("nthreads", C.c_int), ("collapseindex", C.c_int),
-                ("geometric_coeffs", C.c_int), ("max_solution_err", C.c_double), ("max_solution_time", C.c_double)]
+                ("geometric_coeffs", C.c_int), ("max_solution_err", C.c_double), ("max_solution_time", C.c_double),
+                ("open_bc", C.c_int)]
 
 
 _lib = None
@@ -244,7 +245,7 @@ class OracleSolver:
                  coeff_fp32=False, by_coeff_divergence=True, diff_solver=0, rtol=-1.0, atol=-1.0,
                  maxit_dir=0, maxit_diff=0, nthreads=0, collapseindex=1, max_solution_err=5e3 / 86400.,
                  max_solution_time=0.0, geometric_coeffs=False, top_bottom_faces_planar=True,
-                 top_bottom_planes_parallel=True):
+                 top_bottom_planes_parallel=True, open_bc=False):
         self.lut = lut
         ci = max(1, int(collapseindex))
         self.Nz_atm = Nz
@@ -257,7 +258,7 @@ class OracleSolver:
         cfg = _Config(solver_id, Nz, Nx, Ny, dx, dy, _dp(self._dz), (C.c_double * 3)(*sundir), twostr_ratio,
                       int(coeff_fp32), int(by_coeff_divergence), diff_solver, rtol, atol, maxit_dir, maxit_diff,
                       nthreads, ci, _geometric_flags(geometric_coeffs, top_bottom_faces_planar, top_bottom_planes_parallel),
-                      max_solution_err, max_solution_time)
+                      max_solution_err, max_solution_time, int(open_bc))
         self._h = lib().orc_solver_create(C.byref(cfg), C.byref(lut._lut))
         if not self._h:
             raise RuntimeError("orc_solver_create failed")

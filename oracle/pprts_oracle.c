@@ -1273,14 +1273,97 @@ static void determine_ksp_tolerances(const orc_solver *s, double *rtol, double *
 static void exchange_direct_boundary(const orc_solver *s, int lsun_north, int lsun_east, double *x) {
   LOCALS
   int d, k, i, j;
+  /* one periodic rank is its own neighbour and owns both domain edges: with -pprts_open_bc the send buffer of the edge
+   * is zero (:262-263, :270-271, :287-288, :295-296) */
+  const int lopen = s->cfg.open_bc;
   for (d = Ndt; d < Ndt + Nds; ++d) for (j = 0; j < Ny; ++j) for (k = 0; k < Nz1; ++k) {
-    if (lsun_east) FG(x, Nd, d, k, Nx, j) = FG(x, Nd, d, k, 0, j);  /* send xs west, recv from east into xe+1 */
-    else           FG(x, Nd, d, k, 0, j) = FG(x, Nd, d, k, Nx, j);  /* send xe+1 east, recv from west into xs */
+    if (lsun_east) FG(x, Nd, d, k, Nx, j) = lopen ? 0.0 : FG(x, Nd, d, k, 0, j);  /* send xs west, recv from east into xe+1 */
+    else           FG(x, Nd, d, k, 0, j) = lopen ? 0.0 : FG(x, Nd, d, k, Nx, j);  /* send xe+1 east, recv from west into xs */
   }
   for (d = Ndt + Nds; d < Nd; ++d) for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) {
-    if (lsun_north) FG(x, Nd, d, k, i, Ny) = FG(x, Nd, d, k, i, 0);
-    else            FG(x, Nd, d, k, i, 0) = FG(x, Nd, d, k, i, Ny);
+    if (lsun_north) FG(x, Nd, d, k, i, Ny) = lopen ? 0.0 : FG(x, Nd, d, k, i, 0);
+    else            FG(x, Nd, d, k, i, 0) = lopen ? 0.0 : FG(x, Nd, d, k, i, Ny);
   }
+}
+
+/* single_column_solve (src/pprts_base.F90:1318-1458): the direct beam of ONE column that is its own horizontal
+ * neighbour, for unit incidence on every top stream.  The reference assembles  A = -I + T  over (dof, level) and calls
+ * KSPSolve with PETSc's defaults; A is block lower triangular in the levels with dense (side x side) diagonal blocks, so
+ * ILU(0) is the exact factorisation and the solve is a direct one.  Here: per 3-D layer the 2 Nds side unknowns from
+ * (I - M_ss) x_s = M_st top(k) by Gaussian elimination, then top(k+1); a 1-D layer has top(k+1) = exp(-kabs dz / cos
+ * theta) top(k) (:1355-1365 -- kabs alone, as written there) and no side flux.  col = (Nd, Nz1), sides of layer k at level k. */
+static void single_column_solve(const orc_solver *s, int i, int j, double *col) {
+  LOCALS
+  const int ns = 2 * Nds;
+  int k, p, q, r, src, dst;
+  double v[ORC_MAX_DOF * ORC_MAX_DOF], c[ORC_MAX_DOF * ORC_MAX_DOF];
+  double M[ORC_MAX_DOF][ORC_MAX_DOF + 1];
+  memset(col, 0, sizeof(double) * Nd * Nz1);
+  for (src = 0; src < Ndt; ++src) col[src] = 1.0;
+  for (k = 0; k < Nz; ++k) {
+    double *lev = col + (long)k * Nd, *nxt = lev + Nd;
+    if (s->l1d[k]) {
+      const double vv = exp(-(A3(s->kabs, k, i, j) * A3(s->dz, k, i, j) / s->costheta));
+      for (src = 0; src < Ndt; ++src) nxt[src] = vv * lev[src];
+      continue;
+    }
+    orc_get_coeff(s->lut, &s->st, A3(s->kabs, k, i, j), A3(s->ksca, k, i, j), A3(s->g, k, i, j), A3(s->dz, k, i, j), s->dx, 1,
+                  s->symmetry_phi, s->theta, s->xinc == 0, s->yinc == 0, v);
+    store_coeff(s, v, c, Nd * Nd); /* cdir2dir(src, dst) = c[dst * Nd + src] */
+    for (p = 0; p < ns; ++p) {
+      double rhs = 0;
+      for (q = 0; q < ns; ++q) M[p][q] = (p == q ? 1.0 : 0.0) - c[(Ndt + p) * Nd + Ndt + q];
+      for (src = 0; src < Ndt; ++src) rhs += c[(Ndt + p) * Nd + src] * lev[src];
+      M[p][ns] = rhs;
+    }
+    for (p = 0; p < ns; ++p) { /* no pivoting: I - M_ss is diagonally dominant by columns (energy conservation) */
+      for (r = p + 1; r < ns; ++r) {
+        const double f = M[r][p] / M[p][p];
+        for (q = p; q <= ns; ++q) M[r][q] -= f * M[p][q];
+      }
+    }
+    for (p = ns - 1; p >= 0; --p) {
+      double acc = M[p][ns];
+      for (q = p + 1; q < ns; ++q) acc -= M[p][q] * lev[Ndt + q];
+      lev[Ndt + p] = acc / M[p][p];
+    }
+    for (dst = 0; dst < Ndt; ++dst) {
+      double acc = 0;
+      for (src = 0; src < Nd; ++src) acc += c[dst * Nd + src] * lev[src];
+      nxt[dst] = acc;
+    }
+  }
+}
+
+/* set_open_bc (src/pprts_base.F90:1189-1316): side inflow through the sunward domain edges = the side fluxes of the
+ * single-column solution of the edge column, scaled like the TOA incidence.  lb is ghosted; after the reference's
+ * LocalToGlobal(ADD) + GlobalToLocal round trip the value sits both in the ghost face and in its periodic owner. */
+static void set_open_bc(const orc_solver *s, double fac, double *lb) {
+  LOCALS
+  const int lsun_north = s->yinc == 0, lsun_east = s->xinc == 0;
+  double *col = (double *)malloc(sizeof(double) * Nd * Nz1);
+  int i, j, k, src;
+  j = lsun_north ? Ny - 1 : 0;
+  for (i = 0; i < Nx; ++i) {
+    single_column_solve(s, i, j, col);
+    for (k = 0; k < Nz; ++k) for (src = 0; src < Nds; ++src) {
+      const int ioff = Ndt + Nds + src;
+      const double val = fac * col[(long)k * Nd + ioff];
+      FG(lb, Nd, ioff, k, i, j + 1 - s->yinc) = val;
+      if (lsun_north) FG(lb, Nd, ioff, k, i, 0) = val;
+    }
+  }
+  i = lsun_east ? Nx - 1 : 0;
+  for (j = 0; j < Ny; ++j) {
+    single_column_solve(s, i, j, col);
+    for (k = 0; k < Nz; ++k) for (src = 0; src < Nds; ++src) {
+      const int ioff = Ndt + src;
+      const double val = fac * col[(long)k * Nd + ioff];
+      FG(lb, Nd, ioff, k, i + 1 - s->xinc, j) = val;
+      if (lsun_east) FG(lb, Nd, ioff, k, 0, j) = val;
+    }
+  }
+  free(col);
 }
 
 static void explicit_edir_forward_sweep(const orc_solver *s, const int dxr[3], const int dyr[3], const double *b,
@@ -1290,6 +1373,13 @@ static void explicit_edir_forward_sweep(const orc_solver *s, const int dxr[3], c
   int i, j, k, idst, isrc, src, dst;
   for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (dst = 0; dst < Ndt; ++dst)
     FG(x, Nd, dst, 0, i, j) = FG(b, Nd, dst, 0, i, j);
+  if (s->cfg.open_bc) { /* :358-378: the sunward edge faces take the boundary inflow */
+    const int jb = yinc == 0 ? Ny : 0, ib = xinc == 0 ? Nx : 0;
+    for (i = 0; i < Nx; ++i) for (k = 0; k < Nz1; ++k) for (dst = Ndt + Nds; dst < Nd; ++dst)
+      FG(x, Nd, dst, k, i, jb) = FG(b, Nd, dst, k, i, jb);
+    for (j = 0; j < Ny; ++j) for (k = 0; k < Nz1; ++k) for (dst = Ndt; dst < Ndt + Nds; ++dst)
+      FG(x, Nd, dst, k, ib, j) = FG(b, Nd, dst, k, ib, j);
+  }
   for (k = 0; k < Nz; ++k) {
     if (s->l1d[k]) {
       for (j = dyr[0]; j != dyr[1] + dyr[2]; j += dyr[2]) for (i = dxr[0]; i != dxr[1] + dxr[2]; i += dxr[2])
@@ -1358,6 +1448,7 @@ static int explicit_edir(orc_solver *s, double edirTOA, orc_solution *sol) {
   /* setup_incSolar, src/pprts_base.F90:1146-1181 */
   fac = edirTOA * s->dx * s->dy / (double)s->st.dirtop_adiv;
   for (j = 0; j < Ny; ++j) for (i = 0; i < Nx; ++i) for (d = 0; d < Ndt; ++d) FG(lb, Nd, d, 0, i, j) = fac;
+  if (s->cfg.open_bc) set_open_bc(s, fac, lb);
   interior_to_ghosted(s, Nd, sol->edir, v0);
   exchange_direct_boundary(s, lsun_north, lsun_east, v0);
   sol->Niter_dir = 0;

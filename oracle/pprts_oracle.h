@@ -110,6 +110,9 @@ typedef struct {
                                + 2 = -pprts_top_bottom_faces_planar no, + 4 = -pprts_top_bottom_planes_parallel no */
   double max_solution_err;  /* -max_solution_err [W], src/tenstream_options.F90:90 default 5e3/86400; <= 0 disables */
   double max_solution_time; /* -max_solution_time [s], :94 default 0 = error estimates disabled */
+  int open_bc;              /* -pprts_open_bc (src/pprts.F90:462-463): the direct beam enters through the sunward domain
+                               edges with the side fluxes of a single-column solve and leaves through the others
+                               (src/pprts_base.F90:1189-1316, src/pprts_explicit.F90:262-306, :358-378) */
 } orc_config;
 
 orc_solver *orc_solver_create(const orc_config *cfg, const orc_lut *lut);      /* init_pprts, src/pprts.F90:213 */

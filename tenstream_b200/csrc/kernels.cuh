@@ -813,7 +813,8 @@ template <class L, class CT>
 __global__ void __launch_bounds__(128)
 k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__restrict__ d2d,
             const double *__restrict__ a33, const double *__restrict__ xold, double *__restrict__ xnew,
-            double *partials, unsigned int *counter, double *out_norm2) {
+            double *partials, unsigned int *counter, double *out_norm2, const double *__restrict__ bcx,
+            const double *__restrict__ bcy) {
   constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds;
   long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   double d2sum[1] = {0.0};
@@ -855,10 +856,14 @@ k_edir_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__res
 #pragma unroll
         for (int d = Ndt; d < Nd; ++d) in.old[d] = xold[(long)d * g.nlev + lk + o_own];
       } else {
+        // open boundaries: a column on the sunward domain edge takes the boundary inflow (k_open_bc_columns)
+        const bool ex = bcx != nullptr && i == (xinc ? 0 : g.Nx - 1), ey = bcy != nullptr && j == (yinc ? 0 : g.Ny - 1);
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) in.sx[d] = xold[xin0 + (Ndt + d) * xins + k * xink];
+        for (int d = 0; d < Nds; ++d)
+          in.sx[d] = ex ? bcx[((long)d * g.Nz + k) * g.Ny + j] : xold[xin0 + (Ndt + d) * xins + k * xink];
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) in.sy[d] = xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
+        for (int d = 0; d < Nds; ++d)
+          in.sy[d] = ey ? bcy[((long)d * g.Nz + k) * g.Nx + i] : xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
         const long cb = cbase<Nd * Nd>(lk + o_own);
 #pragma unroll
         for (int n = 0; n < Nd * Nd; ++n) in.c[n] = d2d[cb + n * PB_TILE];
@@ -967,7 +972,8 @@ template <class L, class CT>
 __global__ void __launch_bounds__(32 * EDIR_TY)
 k_edir_tile_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *__restrict__ d2d,
                  const double *__restrict__ a33, const double *__restrict__ xold, double *__restrict__ xnew,
-                 double *partials, unsigned int *counter, double *out_norm2) {
+                 double *partials, unsigned int *counter, double *out_norm2, const double *__restrict__ bcx,
+                 const double *__restrict__ bcy) {
   constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, TY = EDIR_TY;
   constexpr unsigned int FULL = 0xffffffffu;
   __shared__ double ybuf[2][TY][Nds][32];
@@ -1013,13 +1019,17 @@ k_edir_tile_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *
 #pragma unroll
       for (int d = Ndt; d < Nd; ++d) in.old[d] = xold[(long)d * g.nlev + lk + o_own];
     } else {
+      // the tile's upstream edges: the previous pass, or -- open boundaries, tile on the sunward domain edge -- the
+      // boundary inflow (src/pprts_explicit.F90:358-378; bcx / bcy from k_open_bc_columns, null otherwise)
       if (a == 0) {
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) in.sx[d] = xold[xin0 + (Ndt + d) * xins + k * xink];
+        for (int d = 0; d < Nds; ++d)
+          in.sx[d] = (bcx != nullptr && ip == 0) ? bcx[((long)d * g.Nz + k) * g.Ny + j] : xold[xin0 + (Ndt + d) * xins + k * xink];
       }
       if (b == 0) {
 #pragma unroll
-        for (int d = 0; d < Nds; ++d) in.sy[d] = xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
+        for (int d = 0; d < Nds; ++d)
+          in.sy[d] = (bcy != nullptr && jp == 0) ? bcy[((long)d * g.Nz + k) * g.Nx + i] : xold[yin0 + (Ndt + Nds + d) * yins + k * yink];
       }
       const long cb = cbase<Nd * Nd>(lk + o_own);
 #pragma unroll
@@ -1170,6 +1180,109 @@ k_edir_tile_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *
     for (int d = Ndt; d < Nd; ++d) xnew[(long)d * g.nlev + lz + o_own] = xold[(long)d * g.nlev + lz + o_own];
   }
   grid_reduce_sum<1>(d2sum, partials, counter, out_norm2);
+}
+
+// -pprts_open_bc (src/pprts_base.F90:1189-1458 set_open_bc / single_column_solve): the beam enters through the sunward
+// domain edges with the side fluxes of a column that is its own horizontal neighbour, solved for unit incidence and
+// scaled like the TOA incidence.  The reference assembles A = -I + T over (dof, level) of that column and calls KSPSolve;
+// A is block lower triangular in the levels with dense (side x side) diagonal blocks, so the solve is direct: per 3-D
+// layer (I - M_ss) x_s = M_st top(k) by Gaussian elimination (2 Nds unknowns), then top(k+1); a 1-D layer carries
+// top(k+1) = exp(-kabs dz / cos theta) top(k) (:1355-1365 -- kabs alone, as written there) and no side flux.
+// One thread per edge column: the first Ny threads the x edge (-> bcx[d][k][j]), the next Nx the y edge (-> bcy[d][k][i]).
+template <class L, class CT>
+__global__ void __launch_bounds__(64)
+k_open_bc_columns(Grid g, int xinc, int yinc, int n1d, double fac, double costheta, int do_x, int do_y,
+                  const CT *__restrict__ d2d, const double *__restrict__ kabs, const double *__restrict__ dz,
+                  double *__restrict__ bcx, double *__restrict__ bcy) {
+  constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, NS = 2 * L::Nds;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool isx = t < g.Ny;
+  int i, j;
+  if (isx) { if (!do_x) return; i = xinc ? 0 : g.Nx - 1; j = t; }
+  else { t -= g.Ny; if (t >= g.Nx || !do_y) return; i = t; j = yinc ? 0 : g.Ny - 1; }
+  const long o_own = (long)j * g.Nx + i;
+  double x[Nd];
+#pragma unroll
+  for (int d = 0; d < Nd; ++d) x[d] = d < Ndt ? 1.0 : 0.0;
+  for (int k = 0; k < g.Nz; ++k) {
+    const long c = (long)k * g.ncol + o_own;
+    if (is1d(g, n1d, k)) {
+      const double v = exp(-(kabs[c] * dz[c] / costheta));
+#pragma unroll
+      for (int d = 0; d < Ndt; ++d) x[d] = v * x[d];
+#pragma unroll
+      for (int d = Ndt; d < Nd; ++d) x[d] = 0.0;
+    } else {
+      double cf[Nd * Nd], M[NS][NS + 1];
+      const long cb = cbase<Nd * Nd>(c);
+#pragma unroll
+      for (int n = 0; n < Nd * Nd; ++n) cf[n] = (double)d2d[cb + n * PB_TILE];  // cf[dst * Nd + src]
+#pragma unroll
+      for (int p = 0; p < NS; ++p) {
+        double rhs = 0.0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) M[p][q] = (p == q ? 1.0 : 0.0) - cf[(Ndt + p) * Nd + Ndt + q];
+#pragma unroll
+        for (int sdof = 0; sdof < Ndt; ++sdof) rhs += cf[(Ndt + p) * Nd + sdof] * x[sdof];
+        M[p][NS] = rhs;
+      }
+#pragma unroll
+      for (int p = 0; p < NS; ++p) {  // no pivoting: I - M_ss is diagonally dominant by columns (energy conservation)
+#pragma unroll
+        for (int r = p + 1; r < NS; ++r) {
+          const double f = M[r][p] / M[p][p];
+#pragma unroll
+          for (int q = p; q <= NS; ++q) M[r][q] -= f * M[p][q];
+        }
+      }
+#pragma unroll
+      for (int p = NS - 1; p >= 0; --p) {
+        double acc = M[p][NS];
+#pragma unroll
+        for (int q = p + 1; q < NS; ++q) acc -= M[p][q] * x[Ndt + q];
+        x[Ndt + p] = acc / M[p][p];
+      }
+      double nt[Ndt];
+#pragma unroll
+      for (int dst = 0; dst < Ndt; ++dst) {
+        double acc = 0.0;
+#pragma unroll
+        for (int sdof = 0; sdof < Nd; ++sdof) acc += cf[dst * Nd + sdof] * x[sdof];
+        nt[dst] = acc;
+      }
+#pragma unroll
+      for (int d = 0; d < Nds; ++d) {  // the side fluxes of layer k live at level k
+        if (isx) bcx[((long)d * g.Nz + k) * g.Ny + j] = fac * x[Ndt + d];
+        else bcy[((long)d * g.Nz + k) * g.Nx + i] = fac * x[Ndt + Nds + d];
+      }
+#pragma unroll
+      for (int d = 0; d < Ndt; ++d) x[d] = nt[d];
+      continue;
+    }
+#pragma unroll
+    for (int d = 0; d < Nds; ++d) {
+      if (isx) bcx[((long)d * g.Nz + k) * g.Ny + j] = 0.0;
+      else bcy[((long)d * g.Nz + k) * g.Nx + i] = 0.0;
+    }
+  }
+}
+
+// what exchange_direct_boundary leaves in the stored solution (src/pprts_explicit.F90:262-306): the rank on the sunward
+// domain edge receives zeros from beyond it into the inflow faces it OWNS (the faces of index 0, i.e. xinc / yinc = 1;
+// the others live in the ghost and are dropped)
+template <class L>
+__global__ void k_open_bc_clear(Grid g, int do_x, int do_y, double *__restrict__ x) {
+  constexpr int Ndt = L::Ndt, Nds = L::Nds;
+  const long nx = do_x ? (long)Nds * (g.Nz + 1) * g.Ny : 0, ny = do_y ? (long)Nds * (g.Nz + 1) * g.Nx : 0;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nx) {
+    const int j = (int)(t % g.Ny), k = (int)((t / g.Ny) % (g.Nz + 1)), d = (int)(t / ((long)g.Ny * (g.Nz + 1)));
+    x[(long)(Ndt + d) * g.nlev + (long)k * g.ncol + (long)j * g.Nx] = 0.0;
+  } else if (t - nx < ny) {
+    t -= nx;
+    const int i = (int)(t % g.Nx), k = (int)((t / g.Nx) % (g.Nz + 1)), d = (int)(t / ((long)g.Nx * (g.Nz + 1)));
+    x[(long)(Ndt + Nds + d) * g.nlev + (long)k * g.ncol + i] = 0.0;
+  }
 }
 
 // =================================================================================================================

@@ -237,6 +237,7 @@ struct pprts_b200_solver {
   unsigned int *tile_class = nullptr;  // per coefficient tile: widening class of its diff2diff entries (common.cuh)
   int mm_variant = 2;  // 0: 2 stages + register prefetch, 1: 2 stages, 2: 1 stage x 4 CTAs/SM (fastest measured)
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
+  double *bcx = nullptr, *bcy = nullptr;  // -pprts_open_bc: boundary inflow of the sunward edge columns [d][k][j] / [d][k][i]
   double *precR = nullptr, *precInv = nullptr;
   double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
   double *vh_ghost[4] = {nullptr, nullptr, nullptr, nullptr};  // decomposed: level heights of the neighbours' edge columns (slope correction)
@@ -633,6 +634,9 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return set_err(90, "no CUDA device: libpprts_b200 has no CPU fallback");
   if (cfg->geometric_coeffs && Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
+  // the reference's boundary columns take LUT coefficients whatever the interior uses (src/pprts_base.F90:1368-1382);
+  // here they read the stored dir2dir of the edge columns, which is the same thing only without geometric coefficients
+  if (cfg->open_bc && cfg->geometric_coeffs) return set_err(25, "open_bc together with geometric_coeffs is not supported");
   if ((cfg->collapseindex > 1 ? cfg->collapseindex : 1) > cfg->Nz)
     return set_err(1, "collapseindex %d exceeds the %d atmosphere layers", cfg->collapseindex, cfg->Nz);
   auto *s = new pprts_b200_solver();
@@ -703,6 +707,7 @@ static int create_impl(const pprts_b200_config *cfg, const pprts_b200_lut *lut, 
   DA(s->b, (size_t)state_len(g, Nf));
   for (int q = 0; q < 8; ++q) DA(s->kr[q], (size_t)state_len(g, Nf) + 2);  // +2: two 16-byte aligned fp32 vectors fit in one
   DA(s->edir_tmp, (size_t)state_len(g, Nd));
+  if (cfg->open_bc) { DA(s->bcx, (size_t)Nd * g.Nz * g.Ny); DA(s->bcy, (size_t)Nd * g.Nz * g.Nx); }
   if (s->decomposed) {
     const size_t hx = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Ny, hy = (size_t)std::max(Nd, Nf) * (g.Nz + 1) * g.Nx;
     DA(s->hs[0], hx); DA(s->hr[0], hx); DA(s->hs[1], hy); DA(s->hr[1], hy);
@@ -793,6 +798,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
                     s->partials, s->sc, s->d_Tdir4, s->d_Sdir4};
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
+  cudaFree(s->bcx); cudaFree(s->bcy);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->precPU); cudaFree(s->precPD); cudaFree(s->vh_atm);
   for (double *p : s->vh_ghost) cudaFree(p);
   for (auto &sp : s->spare) { cudaFree(sp[0]); cudaFree(sp[1]); cudaFree(sp[2]); }
@@ -1110,6 +1116,15 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   double *xold = sol.edir, *xnew = s->edir_tmp;
   double res1 = 0;
   bool converged = false;
+  // -pprts_open_bc (src/pprts_base.F90:1189-1316): the ranks on the sunward domain edges take their side inflow from the
+  // single-column solution of their edge columns instead of the periodic image / the neighbour across the edge
+  const bool edge_x = s->cfg.open_bc && (s->xinc ? s->cfg.xrank == 0 : s->cfg.xrank == s->cfg.nxproc - 1);
+  const bool edge_y = s->cfg.open_bc && (s->yinc ? s->cfg.yrank == 0 : s->cfg.yrank == s->cfg.nyproc - 1);
+  const double *bcx = edge_x ? s->bcx : nullptr, *bcy = edge_y ? s->bcy : nullptr;
+  if (edge_x || edge_y)
+    DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_open_bc_columns<L, CT>), nblk(g.Nx + g.Ny, 64), 64, g, s->xinc, s->yinc, s->n1d, fac,
+                           s->costheta, (int)edge_x, (int)edge_y, (const CT *)s->d2d, (const double *)s->kabs,
+                           (const double *)s->dz, s->bcx, s->bcy));
   // The horizontal inputs of a pass are one pass old, so information needs one pass per column it crosses; the
   // norm is only read back every `check` passes to keep the host out of the loop.
   const int check = jacobi ? 4 : 2;
@@ -1122,10 +1137,10 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
     for (int q = 0; q < nb; ++q) {
       if (jacobi)
         DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_pass<L, CT>), nblk(g.ncol, 128), 128, g, s->xinc, s->yinc, s->n1d, fac,
-                               (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
+                               (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q, bcx, bcy));
       else
         DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_edir_tile_pass<L, CT>), NI * NJ, 32 * EDIR_TY, g, s->xinc, s->yinc, s->n1d, fac,
-                               (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q));
+                               (const CT *)s->d2d, s->a33, xold, xnew, s->partials, s->counter, s->sc + SC_EDIR0 + q, bcx, bcy));
       if ((rc = edir_exchange(s, xnew))) return rc;
       if (s->decomposed) {  // residual = mean over ranks of the local 2-norms (:176-183)
         LAUNCH(s, FAM_VEC, k_sqrt_mean, 1, 32, s->sc + SC_EDIR0 + q, 1, 1.0 / (double)s->nranks);
@@ -1147,6 +1162,11 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   if (xold != sol.edir) {  // result of the last pass lives in edir_tmp: swap the buffers
     s->edir_tmp = sol.edir;
     sol.edir = xold;
+  }
+  if ((edge_x && s->xinc) || (edge_y && s->yinc)) {  // the owned inflow faces keep what the last exchange received: zero
+    const int cx = edge_x && s->xinc, cy = edge_y && s->yinc;
+    const long n = (long)s->Nd * (g.Nz + 1) * (g.Nx + g.Ny);
+    DISPATCH_L(s, LAUNCH(s, FAM_EDIR, (k_open_bc_clear<L>), nblk(n, 128), 128, g, cx, cy, sol.edir));
   }
   sol.first_dir = false;
   sol.lchanged = true;
@@ -2349,6 +2369,7 @@ extern "C" int pprts_b200_set_buildings(pprts_b200_solver *s, int nfaces, const 
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));
   if (nfaces > 0 && s->decomposed) return set_err(60, "buildings are not supported on an x/y-decomposed solver yet");
+  if (nfaces > 0 && s->cfg.open_bc) return set_err(63, "buildings are not supported together with open_bc (the boundary columns read the stored dir2dir)");
   if (nfaces > 0 && (!iface || !albedo)) return set_err(2, "set_buildings: iface and albedo are required");
   const Grid &g = s->g;
   for (int m = 0; m < nfaces; ++m)

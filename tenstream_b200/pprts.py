@@ -45,7 +45,8 @@ class _Config(C.Structure):
                 ("keep_solutions", C.c_int), ("nxproc", C.c_int), ("nyproc", C.c_int), ("xrank", C.c_int),
                 ("yrank", C.c_int), ("diff_explicit", C.c_int), ("krylov_fp32", C.c_int), ("collapseindex", C.c_int),
                 ("max_solution_err", C.c_double), ("max_solution_time", C.c_double), ("geometric_coeffs", C.c_int),
-                ("accept_incomplete_solve", C.c_int), ("gmres_restart", C.c_int), ("max_cached_solutions", C.c_int)]
+                ("accept_incomplete_solve", C.c_int), ("gmres_restart", C.c_int), ("max_cached_solutions", C.c_int),
+                ("open_bc", C.c_int)]
 
 
 class _Bands(C.Structure):
@@ -339,7 +340,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
                keep_solutions=True, rank=None, diff_explicit=False, krylov_fp32=False, max_solution_err=None,
                max_solution_time=None, geometric_coeffs=False, top_bottom_faces_planar=True,
                top_bottom_planes_parallel=True, accept_incomplete_solve=False, gmres_restart=0,
-               max_cached_solutions=0) -> Solver:
+               max_cached_solutions=0, open_bc=False) -> Solver:
     """``init_pprts`` (src/pprts.F90:213-553).  ``icomm`` is accepted for signature compatibility: inside one box
     the library runs one process per GPU and never touches the caller's MPI communicator.  The keyword-only
     arguments carry what the reference reads from its options database (``-twostr_ratio``, ``-*_ksp_rtol`` ...).
@@ -379,6 +380,7 @@ def init_pprts(icomm, Nz, Nx, Ny, dx, dy, sundir, solver=310, dz1d=None, dz3d=No
     cfg.accept_incomplete_solve = int(accept_incomplete_solve)   # -accept_incomplete_solve
     cfg.gmres_restart = int(gmres_restart)
     cfg.max_cached_solutions = int(max_cached_solutions)
+    cfg.open_bc = int(open_bc)                                   # -pprts_open_bc
     cfg.collapseindex = int(collapseindex) if collapseindex is not None else 1
     if max_solution_err is not None:      # -max_solution_err / -max_solution_time (src/tenstream_options.F90:90-96)
         cfg.max_solution_err = float(max_solution_err)

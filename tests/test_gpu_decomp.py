@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixed, q):
+def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixed, open_bc, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank))
@@ -28,7 +28,8 @@ def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixe
         sc["dz1d"][:3] = 250.0
     sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
     dec = CartDecomposition(sc["Nx"], sc["Ny"], nxp, nyp, rank)
-    kw = dict(dz1d=sc["dz1d"], lut=lut, device=rank, rtol=1e-10, atol=1e-30, solver=solver_id, krylov_fp32=mixed)
+    kw = dict(dz1d=sc["dz1d"], lut=lut, device=rank, rtol=1e-10, atol=1e-30, solver=solver_id, krylov_fp32=mixed,
+              open_bc=open_bc)
     s = P.init_pprts(0, sc["Nz"], dec.xm, dec.ym, sc["dx"], sc["dy"], sd, nxproc=dec.nxproc, nyproc=dec.nyproc,
                      rank=rank, **kw)
     uid = [P.nccl_unique_id() if rank == 0 else None]
@@ -66,7 +67,7 @@ def _worker(rank, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixe
     dist.destroy_process_group()
 
 
-def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False, mixed=False):
+def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False, mixed=False, open_bc=False):
     import torch
     import torch.multiprocessing as mp
     world = nxp * nyp
@@ -77,7 +78,7 @@ def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False, mixed=False):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixed, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, paths, nxp, nyp, solver_id, phi0, thick_top, mixed, open_bc, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -108,6 +109,14 @@ def _run(paths, nxp, nyp, solver_id, phi0, thick_top=False, mixed=False):
 def test_decomposed_matches_single_gpu_3_10(small_lut, nxp, nyp, phi0):
     _, paths = small_lut
     _run(paths, nxp, nyp, 310, phi0)
+
+
+@pytest.mark.parametrize("nxp,nyp,phi0", [(2, 1, 120.0), (2, 1, 300.0), (1, 2, 30.0), (1, 2, 200.0)])
+def test_decomposed_open_bc(small_lut, nxp, nyp, phi0):
+    """-pprts_open_bc under the decomposition (src/pprts_explicit.F90:262-306): only the ranks on the sunward domain edge
+    take the boundary inflow, the edge across which the beam leaves sends nothing on; sun from both sides of the split."""
+    _, paths = small_lut
+    _run(paths, nxp, nyp, 310, phi0, open_bc=True)
 
 
 @pytest.mark.parametrize("nxp,nyp,phi0", [(2, 1, 120.0), (1, 2, 300.0)])

@@ -726,6 +726,61 @@ __global__ void k_box_blur(int Nx, int Ny, int kw, int along_y, const double *__
   out[c] = acc * (1.0 / (double)(2 * kw + 1));
 }
 
+// The same pass on one rank's part of an x/y-decomposed domain (src/pprts_base.F90:1766-1795: the reference extends the
+// local field by kernel_width ghost columns / rows from its four neighbours before filtering).  The two passes are
+// separable, so each needs only the halo along its own direction: `lo` holds the kw columns (rows) just below the local
+// range -- the neighbour's highest ones, [j][t] (resp. [t][i]) -- and `hi` the kw just above it.  Same summation order
+// as k_box_blur: the decomposed result is bitwise the one-GPU result.
+__global__ void k_box_blur_halo(int Nx, int Ny, int kw, int along_y, const double *__restrict__ in,
+                                const double *__restrict__ lo, const double *__restrict__ hi, double *__restrict__ out) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= (long)Nx * Ny) return;
+  const int i = (int)(c % Nx), j = (int)(c / Nx);
+  double acc = 0.0;
+  if (along_y) {
+    for (int jj = j - kw; jj <= j + kw; ++jj)
+      acc += jj < 0 ? lo[(long)(jj + kw) * Nx + i] : jj >= Ny ? hi[(long)(jj - Ny) * Nx + i] : in[(long)jj * Nx + i];
+  } else {
+    for (int ii = i - kw; ii <= i + kw; ++ii)
+      acc += ii < 0 ? lo[(long)j * kw + ii + kw] : ii >= Nx ? hi[(long)j * kw + ii - Nx] : in[(long)j * Nx + ii];
+  }
+  out[c] = acc * (1.0 / (double)(2 * kw + 1));
+}
+// the kw lowest / highest columns (rows) of the local field, in the halo layout of k_box_blur_halo
+__global__ void k_blur_pack(int Nx, int Ny, int kw, int along_y, const double *__restrict__ in, double *__restrict__ lo_blk,
+                            double *__restrict__ hi_blk) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n = (long)kw * (along_y ? Nx : Ny);
+  if (q >= n) return;
+  if (along_y) {
+    const int i = (int)(q % Nx), t = (int)(q / Nx);
+    lo_blk[q] = in[(long)t * Nx + i];
+    hi_blk[q] = in[(long)(Ny - kw + t) * Nx + i];
+  } else {
+    const int t = (int)(q % kw), j = (int)(q / kw);
+    lo_blk[q] = in[(long)j * Nx + t];
+    hi_blk[q] = in[(long)j * Nx + Nx - kw + t];
+  }
+}
+// sum of a level field -> out[0] (one block, fixed order), and field <- out[0] * scale: the domain mean over all ranks
+__global__ void k_field_sum(long n, const double *__restrict__ field, double *__restrict__ out) {
+  __shared__ double part[32];
+  double acc = 0.0;
+  for (long c = threadIdx.x; c < n; c += blockDim.x) acc += field[c];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    out[0] = t;
+  }
+}
+__global__ void k_field_fill(long n, double *__restrict__ field, const double *__restrict__ value, double scale) {
+  const double v = value[0] * scale;
+  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long)gridDim.x * blockDim.x) field[c] = v;
+}
+
 // smooth_surface_fluxes with a negative radius (src/pprts_postprocess.F90:66-71): the level field is replaced by its
 // domain mean.  One block per field; warp-shuffle partial sums, fixed order (deterministic).
 __global__ void k_fill_mean(long n, double *__restrict__ field) {
@@ -3326,7 +3381,8 @@ __global__ void k_absdiff_max(long n, const double *__restrict__ a, const double
 // :4989-5145, :6011-6160).  A building is a list of faces of grid cells: iface[m] is the 1-based flattened index into
 // (6, Nz, Nx, Ny), first axis fastest; face ids 1..6 = top (z+0), bottom (z+1), left (x+0), right (x+1), rear (y+0),
 // front (y+1).  One thread per face; the lists are tiny next to the grid, so these kernels are latency-sized.
-// Single-GPU (periodic) domains only: the host refuses buildings on a decomposed solver.
+// Under the x/y decomposition every rank holds the faces of ITS cells; a right / front face on the rank edge lives in the
+// ghost block: its source entries travel to the neighbour with setup_b's halo push, its fluxes are read after a ghost fill.
 // =================================================================================================================
 struct BldFace { int face, k, i, j; };
 __device__ __forceinline__ BldFace bld_decode(const Grid &g, int iface) {
@@ -3338,12 +3394,18 @@ __device__ __forceinline__ BldFace bld_decode(const Grid &g, int iface) {
   f.j = (int)r;
   return f;
 }
-// level-cell index of the face: bottom -> level k+1, right -> column i+1, front -> row j+1 (periodic image)
-__device__ __forceinline__ long bld_face_loc(const Grid &g, const BldFace &f) {
+// where the dofs of the face live in a state vector of ND dofs (dof d at base + d * stride): bottom -> level k+1,
+// right -> column i+1, front -> row j+1 -- the periodic image, or the ghost block when that face belongs to the
+// neighbouring rank (common.cuh: [d][k][j] / [d][k][i])
+struct BldLoc { long base, stride; };
+template <int ND>
+__device__ __forceinline__ BldLoc bld_face_loc(const Grid &g, const BldFace &f) {
   const int kk = f.face == 2 ? f.k + 1 : f.k;
+  if (f.face == 4 && g.gx && f.i + 1 == g.Nx) return BldLoc{ghost_x_base(g, ND) + (long)kk * g.Ny + f.j, (long)(g.Nz + 1) * g.Ny};
+  if (f.face == 6 && g.gy && f.j + 1 == g.Ny) return BldLoc{ghost_y_base(g, ND) + (long)kk * g.Nx + f.i, (long)(g.Nz + 1) * g.Nx};
   const int ii = f.face == 4 ? wrap_p(f.i, g.Nx) : f.i;
   const int jj = f.face == 6 ? wrap_p(f.j, g.Ny) : f.j;
-  return lidx(g, kk, jj, ii);
+  return BldLoc{lidx(g, kk, jj, ii), g.nlev};
 }
 // set_buildings_coeff of alloc_coeff_dir2dir (:3194-3212: a building cell passes no direct radiation) and of
 // alloc_coeff_diff2diff (:3579-3677: a stream leaving the cell through a building face receives only the Lambertian
@@ -3421,7 +3483,7 @@ __global__ void k_buildings_source(Grid g, int lsolar, int lthermal, int nb, con
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= nb) return;
   const BldFace f = bld_decode(g, iface[m]);
-  const long l = bld_face_loc(g, f);
+  const BldLoc ld = bld_face_loc<L::Nd>(g, f), lf = bld_face_loc<L::Nf>(g, f);
   const double ag = albedo[m];
   const bool top = f.face <= 2, xface = f.face == 3 || f.face == 4;
   const bool out_in = f.face == 2 || f.face == 4 || f.face == 6;
@@ -3432,8 +3494,8 @@ __global__ void k_buildings_source(Grid g, int lsolar, int lthermal, int nb, con
     for (int d = 0; d < nout; ++d) {
       if ((top ? L::top_in(d) : L::side_in(d)) != out_in) continue;
       double acc = 0.0;  // xsrc = 0, then += edir(src) * albedo / streams in ascending src order
-      for (int src = s0; src < s0 + ns; ++src) acc = acc + edir[(long)src * g.nlev + l] * ag / streams;
-      b[(long)(off + d) * g.nlev + l] = acc;
+      for (int src = s0; src < s0 + ns; ++src) acc = acc + edir[ld.base + src * ld.stride] * ag / streams;
+      b[lf.base + (off + d) * lf.stride] = acc;
     }
   }
   if (lthermal && planck != nullptr) {
@@ -3442,7 +3504,7 @@ __global__ void k_buildings_source(Grid g, int lsolar, int lthermal, int nb, con
     const double emis = M_PI * planck[m] * (1.0 - ag);
     for (int d = 0; d < nout; ++d) {
       if ((top ? L::top_in(d) : L::side_in(d)) != out_in) continue;
-      b[(long)(off + d) * g.nlev + l] = A * emis / streams;
+      b[lf.base + (off + d) * lf.stride] = A * emis / streams;
     }
   }
 }
@@ -3457,13 +3519,13 @@ __global__ void k_buildings_result(Grid g, int lsolar, double mu, int nb, const 
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= nb) return;
   const BldFace f = bld_decode(g, iface[m]);
-  const long l = bld_face_loc(g, f);
+  const BldLoc ld = bld_face_loc<L::Nd>(g, f), lf = bld_face_loc<L::Nf>(g, f);
   const bool top = f.face <= 2, xface = f.face == 3 || f.face == 4;
   const bool low = f.face == 1 || f.face == 3 || f.face == 5;  // inward streams ENTER the building through a low face
   double e = 0.0;
   if (lsolar) {
     const int s0 = top ? 0 : (xface ? Ndt : Ndt + Nds), ns = top ? Ndt : Nds;
-    for (int d = s0; d < s0 + ns; ++d) e += edir[(long)d * g.nlev + l] * mu;
+    for (int d = s0; d < s0 + ns; ++d) e += edir[ld.base + d * ld.stride] * mu;
     e = e / (double)(top ? L::dirtop_adiv : L::dirside_adiv);
   }
   out_edir[m] = e;
@@ -3471,7 +3533,7 @@ __global__ void k_buildings_result(Grid g, int lsolar, double mu, int nb, const 
   const int off = top ? 0 : (xface ? Nft : Nft + Nfs), n = top ? Nft : Nfs;
   double in = 0.0, out = 0.0;
   for (int d = 0; d < n; ++d) {
-    const double v = ediff[(long)(off + d) * g.nlev + l] * fmu;
+    const double v = ediff[lf.base + (off + d) * lf.stride] * fmu;
     if ((top ? L::top_in(d) : L::side_in(d)) == low) in += v; else out += v;
   }
   out_in[m] = in;

@@ -237,6 +237,8 @@ struct pprts_b200_solver {
   unsigned int *tile_class = nullptr;  // per coefficient tile: widening class of its diff2diff entries (common.cuh)
   int mm_variant = 2;  // 0: 2 stages + register prefetch, 1: 2 stages, 2: 1 stage x 4 CTAs/SM (fastest measured)
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
+  double *blur_buf[4] = {nullptr, nullptr, nullptr, nullptr};  // smooth_surface_fluxes on a decomposed solver: send lo/hi, halo lo/hi
+  size_t blur_cap = 0;
   double *bcx = nullptr, *bcy = nullptr;  // -pprts_open_bc: boundary inflow of the sunward edge columns [d][k][j] / [d][k][i]
   double *precR = nullptr, *precInv = nullptr;
   double *vh_atm = nullptr, *vh = nullptr;  // -pprts_geometric_coeffs: vertex heights on the atmosphere / solver levels
@@ -799,6 +801,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (double *p : ptrs) cudaFree(p);
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->bcx); cudaFree(s->bcy);
+  for (double *p : s->blur_buf) cudaFree(p);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->precPU); cudaFree(s->precPD); cudaFree(s->vh_atm);
   for (double *p : s->vh_ghost) cudaFree(p);
   for (auto &sp : s->spare) { cudaFree(sp[0]); cudaFree(sp[1]); cudaFree(sp[2]); }
@@ -2368,7 +2371,6 @@ extern "C" int pprts_b200_set_buildings(pprts_b200_solver *s, int nfaces, const 
                                         const double *planck) {
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));
-  if (nfaces > 0 && s->decomposed) return set_err(60, "buildings are not supported on an x/y-decomposed solver yet");
   if (nfaces > 0 && s->cfg.open_bc) return set_err(63, "buildings are not supported together with open_bc (the boundary columns read the stored dir2dir)");
   if (nfaces > 0 && (!iface || !albedo)) return set_err(2, "set_buildings: iface and albedo are required");
   const Grid &g = s->g;
@@ -2397,11 +2399,17 @@ extern "C" int pprts_b200_get_buildings_result(pprts_b200_solver *s, int uid, do
                                                double *outgoing) {
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));
-  if (s->nbld <= 0) return set_err(62, "no buildings attached to the solver");
+  if (s->nbld <= 0 && !s->decomposed) return set_err(62, "no buildings attached to the solver");
   Solution *sol;
   int rc = find_solution(s, uid, &sol);
   if (rc) return rc;
   const Grid &g = s->g;
+  if (s->decomposed) {  // collective: the right / front faces on the rank edge read the neighbour's low faces (in W/m2 by now)
+    if ((rc = need_comm(s))) return rc;
+    if (sol->lsolar_rad && (rc = halo_fill(s, sol->edir, s->Nd, dir_halo(s), true, true))) return rc;
+    if ((rc = halo_fill(s, sol->ediff, s->Nf, diff_halo(s), true, true))) return rc;
+    if (s->nbld <= 0) return 0;  // a rank without faces only takes part in the exchange
+  }
   const int n = s->nbld;
   DISPATCH_L(s, LAUNCH(s, FAM_ABSO, (k_buildings_result<L>), nblk(n, 128), 128, g, (int)sol->lsolar_rad, s->mu, n,
                         (const int *)s->bld_iface, (const double *)sol->edir, (const double *)sol->ediff, s->bld_out,
@@ -2489,15 +2497,72 @@ extern "C" int pprts_b200_find_iter_and_kernelwidth(double radius, double dx, do
   return 0;
 }
 // field: one level [Ny][Nx] on the device, smoothed in place; scratch: at least ncol doubles
+// One pass of the box blur on a decomposed solver: the kw edge columns (rows) travel to the two neighbours along that
+// direction (convolve_ediff_srfc's exchange, src/pprts_base.F90:1766-1795); a direction that is not split wraps locally.
+static int blur_pass_decomposed(pprts_b200_solver *s, int kw, int along_y, const double *in, double *out) {
+  const Grid &g = s->g;
+  const size_t n = (size_t)kw * (along_y ? g.Nx : g.Ny);
+  if (n > s->blur_cap) {
+    for (double *&p : s->blur_buf) { cudaFree(p); p = nullptr; }
+    for (double *&p : s->blur_buf) DA(p, n);
+    s->blur_cap = n;
+  }
+  double *snd_lo = s->blur_buf[0], *snd_hi = s->blur_buf[1], *halo_lo = s->blur_buf[2], *halo_hi = s->blur_buf[3];
+  LAUNCH(s, FAM_HALO, k_blur_pack, nblk((long)n, 256), 256, g.Nx, g.Ny, kw, along_y, in, snd_lo, snd_hi);
+  if (along_y ? g.gy : g.gx) {
+    const int lo_nb = along_y ? s->nb_south : s->nb_west, hi_nb = along_y ? s->nb_north : s->nb_east;
+    // my lowest columns are the halo ABOVE my low neighbour's range, my highest ones the halo BELOW my high neighbour's
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(snd_lo, n, NCCL_F64, lo_nb, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(halo_hi, n, NCCL_F64, hi_nb, s->nccl_comm, s->stream));
+    NC(g_nccl.Send(snd_hi, n, NCCL_F64, hi_nb, s->nccl_comm, s->stream));
+    NC(g_nccl.Recv(halo_lo, n, NCCL_F64, lo_nb, s->nccl_comm, s->stream));
+    NC(g_nccl.GroupEnd());
+    s->halo_exchanges++;
+  } else {  // periodic within the rank: my own opposite edge
+    halo_lo = snd_hi; halo_hi = snd_lo;
+  }
+  LAUNCH(s, FAM_ABSO, k_box_blur_halo, nblk(g.ncol, 256), 256, g.Nx, g.Ny, kw, along_y, in, (const double *)halo_lo,
+         (const double *)halo_hi, out);
+  return 0;
+}
 static int smooth_level_device(pprts_b200_solver *s, double radius, double *field, double *scratch) {
   const Grid &g = s->g;
-  if (s->decomposed) return set_err(71, "smooth_surface_fluxes is not supported on an x/y-decomposed solver yet");
+  int rc;
+  if (s->decomposed) {  // collective over the ranks of the decomposition
+    if ((rc = need_comm(s))) return rc;
+    if (radius < 0) {   // imp_allreduce_mean: sum over all ranks / global number of columns
+      LAUNCH(s, FAM_ABSO, k_field_sum, 1, 1024, (long)g.ncol, (const double *)field, s->sc + SC_TMP);
+      if ((rc = allreduce_scalars(s, s->sc + SC_TMP, 1))) return rc;
+      LAUNCH(s, FAM_ABSO, k_field_fill, nblk(g.ncol, 256), 256, (long)g.ncol, field, (const double *)(s->sc + SC_TMP), 1.0 / s->glob_ncol);
+      return 0;
+    }
+    // find_iter_and_kernelwidth works on the LOCAL domain size; Niter = max, kernel_width = min over the ranks
+    // (src/pprts_postprocess.F90:116-119).  A rank whose own search fails still takes part in the reduction.
+    int niter = 0, kw = 0;
+    char msg[sizeof(g_err)];
+    const int lrc = pprts_b200_find_iter_and_kernelwidth(radius, g.dx, g.dy, g.Nx, g.Ny, &niter, &kw);
+    if (lrc) snprintf(msg, sizeof(msg), "%s", g_err);
+    double h[3] = {(double)niter, -(double)kw, (double)lrc};
+    CU(cudaMemcpyAsync(s->sc + SC_TMP, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
+    NC(g_nccl.AllReduce(s->sc + SC_TMP, s->sc + SC_TMP, 3, NCCL_F64, NCCL_MAX, s->nccl_comm, s->stream));
+    CU(cudaMemcpyAsync(h, s->sc + SC_TMP, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (h[2] != 0.0) return lrc ? set_err(lrc, "%s", msg) : set_err(72, "smooth_surface_fluxes: find_iter_and_kernelwidth failed on another rank");
+    niter = (int)std::lround(h[0]); kw = (int)std::lround(-h[1]);
+    if (kw == 0) niter = 0;
+    for (int it = 0; it < niter; ++it) {
+      if ((rc = blur_pass_decomposed(s, kw, 0, field, scratch))) return rc;
+      if ((rc = blur_pass_decomposed(s, kw, 1, scratch, field))) return rc;
+    }
+    return 0;
+  }
   if (radius < 0) {
     LAUNCH(s, FAM_ABSO, k_fill_mean, 1, 1024, (long)g.ncol, field);
     return 0;
   }
   int niter = 0, kw = 0;
-  int rc = pprts_b200_find_iter_and_kernelwidth(radius, g.dx, g.dy, g.Nx, g.Ny, &niter, &kw);
+  rc = pprts_b200_find_iter_and_kernelwidth(radius, g.dx, g.dy, g.Nx, g.Ny, &niter, &kw);
   if (rc) return rc;
   for (int it = 0; it < niter; ++it) {
     LAUNCH(s, FAM_ABSO, k_box_blur, nblk(g.ncol, 256), 256, g.Nx, g.Ny, kw, 0, (const double *)field, scratch);

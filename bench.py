@@ -280,8 +280,10 @@ def run_ours(args):
             stage_async(0)
         for ib, b in enumerate(bands):
             s.set_optical_properties_staged(E2E_SLOT0 + (ib & 1))
-            if ib + 1 < len(bands):
-                stage_async(ib + 1)
+            # the band loop's software pipeline: the NEXT band -- of this step or, after the last one, of the next step --
+            # is uploaded while this one is solved (its slot was consumed by set_optical_properties_staged one band ago;
+            # the library orders the refill behind that ingest)
+            stage_async((ib + 1) % len(bands))
             P.solve_pprts(s, not b["lsolar"], b["lsolar"], b["edirTOA"], b["uid"])
             if ib == 0:
                 s.wait_results()     # the previous step's results are complete (they travelled during this solve)
@@ -289,7 +291,6 @@ def run_ours(args):
             s.accumulate_result(b["uid"], 1.0)
         if world > 1:
             s.allreduce_accumulated()
-        stage_async(0)
         staged_ahead[0] = True
         e2e_step[0] += 1
 

@@ -204,6 +204,7 @@ struct Staged {
   double *kabs = nullptr, *ksca = nullptr, *g = nullptr, *planck = nullptr, *Bsrfc = nullptr, *albedo2d = nullptr;
   bool have_planck = false, have_Bsrfc = false, have_albedo2d = false;
   cudaEvent_t ready = nullptr;  // stage_optical_properties_async: recorded on the copy stream behind the slot's uploads
+  cudaEvent_t consumed = nullptr;  // set_optical_properties_staged: recorded on the solver's stream behind the ingest kernels
 };
 
 struct pprts_b200_solver {
@@ -809,7 +810,10 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (int q = 0; q < 4; ++q) cudaFree(s->egress[q]);
   if (s->egress_ready) cudaEventDestroy(s->egress_ready);
   if (s->egress_done) cudaEventDestroy(s->egress_done);
-  for (auto &kv : s->staged) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+  for (auto &kv : s->staged) {
+    if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+    if (kv.second.consumed) cudaEventDestroy(kv.second.consumed);
+  }
   cudaFree(s->bld_iface); cudaFree(s->bld_albedo); cudaFree(s->bld_planck); cudaFree(s->bld_out);
   for (int q = 0; q < 4; ++q) { cudaFree(s->res[q]); cudaFree(s->acc[q]); cudaFree(s->d_ax[q]); }
   cudaFree(s->tile_class); cudaFree(s->d2d); cudaFree(s->d2f); cudaFree(s->f2f); cudaFree(s->d_Sdiff); cudaFree(s->counter); cudaFree(s->bad);
@@ -908,6 +912,7 @@ extern "C" int pprts_b200_stage_optical_properties(pprts_b200_solver *s, int slo
   const Grid &gr = s->g;
   Staged &st = s->staged[slot];
   st.albedo = albedo;
+  if (st.consumed) CU(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));  // the previous content is still being ingested
   auto up = [&](double **dst, const double *src, size_t n) -> int {
     if (!*dst) CU(cudaMalloc((void **)dst, n * sizeof(double)));
     CU(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -930,8 +935,13 @@ extern "C" int pprts_b200_set_optical_properties_staged(pprts_b200_solver *s, in
   Staged &st = it->second;
   CU(cudaSetDevice(s->device));
   if (st.ready) CU(cudaStreamWaitEvent(s->stream, st.ready, 0));  // uploaded by stage_optical_properties_async
-  return set_optprop_impl(s, st.albedo, st.kabs, st.ksca, st.g, st.have_planck ? st.planck : nullptr,
-                          st.have_Bsrfc ? st.Bsrfc : nullptr, st.have_albedo2d ? st.albedo2d : nullptr, ldelta, true);
+  const int rc = set_optprop_impl(s, st.albedo, st.kabs, st.ksca, st.g, st.have_planck ? st.planck : nullptr,
+                                  st.have_Bsrfc ? st.Bsrfc : nullptr, st.have_albedo2d ? st.albedo2d : nullptr, ldelta, true);
+  if (rc) return rc;
+  // the slot may be refilled (stage_optical_properties_async) as soon as the ingest kernels have read it
+  if (!st.consumed) CU(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming));
+  CU(cudaEventRecord(st.consumed, s->stream));
+  return 0;
 }
 static int ensure_copy_stream(pprts_b200_solver *s) {
   if (s->copy_stream) return 0;
@@ -953,6 +963,7 @@ extern "C" int pprts_b200_stage_optical_properties_async(pprts_b200_solver *s, i
   const Grid &gr = s->g;
   Staged &st = s->staged[slot];
   st.albedo = albedo;
+  if (st.consumed) CU(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));  // the previous content is still being ingested
   auto up = [&](double **dst, const double *src, size_t n) -> int {
     if (!*dst) CU(cudaMalloc((void **)dst, n * sizeof(double)));
     CU(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));

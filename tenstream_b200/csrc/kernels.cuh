@@ -2303,6 +2303,114 @@ k_cg_accumulate(Grid g, CgLevels lv, int n1d, const CT *__restrict__ T, const do
     }
   }
 }
+// The same sums with the fine coefficients read ONCE, through shared memory.  k_cg_accumulate walks the 64 cells of an
+// 8x8 aggregate per thread: the lanes of a warp sit 8 cells apart, every request touches 32 sectors for 128 useful bytes
+// and the rows of an aggregate come back through L1 / L2 -- 3.9 GB of DRAM reads for 2.1 GB of coefficients (ncu,
+// profiles/r2_hot_kernels.txt).  A register formulation with coalesced rows read exactly 2.1 GB but was latency-bound at
+// 12 warps per SM (1.1 ms against 0.82 ms; profiles/r2_cg_accumulate.txt).  Here a CTA owns, for ONE dst row, the
+// 128 fine columns of a coefficient tile over the AG rows of a coarsest-level aggregate row block: in the tile-blocked
+// layout the Nf source planes of that dst row are one contiguous run of Nf * 512 bytes per fine row, fetched by one
+// cp.async.bulk each (all rows in flight at once, one mbarrier); then thread = column reads its values from the stage,
+// the sums over the columns of an aggregate are xor-shuffles inside groups of AG lanes (aggregates start at multiples
+// of AG), and the lane on an aggregate's first column writes the finished row.
+// Needs fp32 coefficients, Nx a multiple of PB_TILE (a 128-column range is then exactly one tile), every AG a power of two,
+// the coarsest AG <= CG_ROWS_MAX; the host falls back to k_cg_accumulate otherwise.
+#define CG_ROWS_MAX 8
+template <class L>
+__global__ void __launch_bounds__(PB_TILE)
+k_cg_accumulate_tiles(Grid g, CgLevels lv, int n1d, const float *__restrict__ T, const double *__restrict__ a11,
+                      const double *__restrict__ a12) {
+  constexpr int Nf = L::Nf, Nft = L::Nft, Nfs = L::Nfs;
+  constexpr unsigned int FULL = 0xffffffffu;
+  constexpr unsigned int ROW_BYTES = Nf * PB_TILE * sizeof(float);
+  static_assert(Nft == 2, "coarse correction needs one up/down pair of top streams");
+  __shared__ __align__(128) float stage[CG_ROWS_MAX][Nf][PB_TILE];
+  __shared__ __align__(8) unsigned long long bar;
+  // per-level constants in registers (no dynamic indexing of the parameter struct); AG = 1 << sh
+  const int nl = lv.n;
+  const int sh0 = 31 - __clz(lv.c[0].AG), sh1 = nl > 1 ? 31 - __clz(lv.c[1].AG) : sh0;
+  const int sht = nl > 1 ? sh1 : sh0, NyCt = nl > 1 ? lv.c[1].NyC : lv.c[0].NyC;
+  const int ntx = g.Nx / PB_TILE;
+  const int tid = threadIdx.x, lane = tid & 31;
+  long r = blockIdx.x;
+  const int tx = (int)(r % ntx); r /= ntx;
+  const int J = (int)(r % NyCt); r /= NyCt;
+  const int k = (int)(r % g.Nz);
+  const int dst = (int)(r / g.Nz);
+  const int i = tx * PB_TILE + tid;
+  const bool l1d = is1d(g, n1d, k);
+  const int j0 = J << sht, j1 = min(g.Ny, j0 + (1 << sht)), nrows = j1 - j0;
+  if (!l1d) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&bar, ROW_BYTES * (unsigned int)nrows);
+      for (int q = 0; q < nrows; ++q) {
+        const long tile = (lidx(g, k, j0 + q, 0) >> PB_TILE_SHIFT) + tx;  // rows start on tile boundaries (Nx % PB_TILE == 0)
+        bulk_g2s(&stage[q][0][0], T + tile * (long)(Nf * Nf * PB_TILE) + (long)dst * Nf * PB_TILE, ROW_BYTES, &bar);
+      }
+    }
+    __syncthreads();
+  }
+  // does the stream of row dst leave through the high-x / high-y face (then that face has to lie inside the aggregate)?
+  const bool out_x = dst >= Nft && dst < Nft + Nfs && L::side_in(dst - Nft);
+  const bool out_y = dst >= Nft + Nfs && L::side_in(dst - Nft - Nfs);
+  // is the high-x face of my fine column inside level l's aggregate column?
+  auto xin_of = [&](int sh) { return (i + 1 < g.Nx) ? (((i + 1) >> sh) == (i >> sh)) : (!g.gx && (i >> sh) == 0); };
+  const bool xin0 = xin_of(sh0), xin1 = xin_of(sh1);
+  double acc0[Nf], acc1[Nf];
+#pragma unroll
+  for (int s2 = 0; s2 < Nf; ++s2) { acc0[s2] = 0.0; acc1[s2] = 0.0; }
+  // sum over the columns of the aggregates, scale, store the finished row of level l (AG = 1 << sh)
+  auto flush = [&](double (&row)[Nf], int sh, const CoarseGrid &cgl, float *coef, int j) {
+    for (int o = 1; o < (1 << sh); o <<= 1) {
+#pragma unroll
+      for (int s2 = 0; s2 < Nf; ++s2) row[s2] += __shfl_xor_sync(FULL, row[s2], o);
+    }
+    if ((lane & ((1 << sh) - 1)) == 0) {
+      const int Il = i >> sh, Jl = j >> sh;
+      const int ni = min(g.Nx, (Il + 1) << sh) - (Il << sh), nj = min(g.Ny, (Jl + 1) << sh) - (Jl << sh);
+      const double sc = 1.0 / (double)(ni * nj);
+      const long ccl = ((long)k * cgl.NyC + Jl) * cgl.NxC + Il;
+#pragma unroll
+      for (int s2 = 0; s2 < Nf; ++s2) coef[(long)(dst * Nf + s2) * cgl.ncc + ccl] = (float)(row[s2] * sc);
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < Nf; ++s2) row[s2] = 0.0;
+  };
+  if (!l1d) mbar_wait(&bar, 0);
+  for (int q = 0; q < nrows; ++q) {
+    const int j = j0 + q;
+    if (l1d) {
+      if (dst < Nft) {
+        const long c = lidx(g, k, j, i);
+        const double t11 = a11[c], t12 = a12[c];
+#pragma unroll
+        for (int s2 = 0; s2 < Nft; ++s2) { const double tv = (s2 == dst) ? t11 : t12; acc0[s2] += tv; acc1[s2] += tv; }
+      }
+    } else {
+      auto yin_of = [&](int sh) { return (j + 1 < g.Ny) ? (((j + 1) >> sh) == (j >> sh)) : (!g.gy && (j >> sh) == 0); };
+      const bool yin0 = yin_of(sh0), yin1 = yin_of(sh1);
+      // a coefficient counts when the faces of both its streams lie inside the aggregate column: predicates per level
+      // for sources without a high face (n), with the high-x face (x), with the high-y face (y)
+      const bool n0 = (!out_x || xin0) && (!out_y || yin0), n1 = (!out_x || xin1) && (!out_y || yin1);
+      const bool x0 = n0 && xin0, y0 = n0 && yin0, x1 = n1 && xin1, y1 = n1 && yin1;
+#pragma unroll
+      for (int s2 = 0; s2 < Nf; ++s2) {
+        const double dv = (double)stage[q][s2][tid];
+        const bool sx = s2 >= Nft && s2 < Nft + Nfs && !L::side_in(s2 - Nft);        // enters through the high-x face
+        const bool sy = s2 >= Nft + Nfs && !L::side_in(s2 - Nft - Nfs);               // enters through the high-y face
+        const bool p0 = sx ? x0 : (sy ? y0 : n0), p1 = sx ? x1 : (sy ? y1 : n1);
+        if (p0) acc0[s2] += dv;
+        if (p1) acc1[s2] += dv;
+      }
+    }
+    // rows of the aggregates that end with this fine row (CTA-uniform)
+    const bool last = j + 1 >= g.Ny;
+    if (last || ((j + 1) & ((1 << sh0) - 1)) == 0) flush(acc0, sh0, lv.c[0], lv.coef[0], j);
+    if (nl > 1 && (last || ((j + 1) & ((1 << sh1) - 1)) == 0)) flush(acc1, sh1, lv.c[1], lv.coef[1], j);
+  }
+}
 // raw Galerkin rows (scaled) -> condensed two-stream coefficients and back-substitution matrices, in place
 template <class L>
 __global__ void __launch_bounds__(64)

@@ -1324,7 +1324,21 @@ static void prec_setup_t(pprts_b200_solver *s) {
           lv.n = std::min(2, s->ncgl - l0);
           for (int l = 0; l < lv.n; ++l) { lv.c[l] = s->cgl[l0 + l].c; lv.coef[l] = s->cgl[l0 + l].coef; }
           const CoarseGrid &top = lv.c[lv.n - 1];
-          LAUNCH(s, FAM_PRECOND, (k_cg_accumulate<L, CT>), nblk(top.ncc * L::Nf, 128), 128, g, lv, s->n1d, (const CT *)s->f2f, s->a11, s->a12);
+          // tile-staged variant (k_cg_accumulate_tiles) where its layout conditions hold; PPRTS_B200_CG_ACC_WALK keeps the
+          // per-aggregate walk for comparison
+          const char *walk = getenv("PPRTS_B200_CG_ACC_WALK");
+          bool tiles = walk == nullptr && std::is_same<CT, float>::value && g.Nx % PB_TILE == 0 && top.AG <= CG_ROWS_MAX;
+          for (int l = 0; l < lv.n; ++l) tiles = tiles && (lv.c[l].AG & (lv.c[l].AG - 1)) == 0;
+          bool done = false;
+          if constexpr (sizeof(float) * CG_ROWS_MAX * L::Nf * PB_TILE <= 47 * 1024) {
+            if (tiles) {
+              const long nblocks = (long)(g.Nx / PB_TILE) * top.NyC * g.Nz * L::Nf;
+              LAUNCH(s, FAM_PRECOND, (k_cg_accumulate_tiles<L>), (unsigned int)nblocks, PB_TILE, g, lv, s->n1d, (const float *)s->f2f, s->a11, s->a12);
+              done = true;
+            }
+          }
+          if (!done)
+            LAUNCH(s, FAM_PRECOND, (k_cg_accumulate<L, CT>), nblk(top.ncc * L::Nf, 128), 128, g, lv, s->n1d, (const CT *)s->f2f, s->a11, s->a12);
         }
         for (int l = 0; l < s->ncgl; ++l) {
           const CoarseGrid &c = s->cgl[l].c;

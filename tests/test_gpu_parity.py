@@ -1214,3 +1214,35 @@ def test_geometric_vertex_variants_vs_oracle(P, gpu_lut, oracle_lut):
         T[planar, parallel] = s.coeffs(1).copy()
         P.destroy_pprts(s); o.destroy()
     assert np.abs(T[False, True] - T[True, True]).max() > 1e-4 and np.abs(T[True, False] - T[True, True]).max() > 1e-4
+
+
+@pytest.mark.parametrize("shape", [(8, 128, 11), (6, 256, 20), (5, 128, 8), (7, 37, 9)])
+@pytest.mark.parametrize("mixed", [False, True])
+def test_galerkin_accumulation_variants_agree(P, gpu_lut, shape, mixed):
+    """k_cg_accumulate_tiles (rows of a coefficient tile staged by bulk copies, shuffles over the columns of an aggregate;
+    taken when Nx is a multiple of the tile width) builds the same coarse operators as the per-aggregate walk
+    k_cg_accumulate (PPRTS_B200_CG_ACC_WALK): same Krylov iteration count, same converged fluxes -- with row counts that are
+    not multiples of the aggregate sizes and a 1-D layer on top; the last shape takes the walk either way."""
+    Nz, Nx, Ny = shape
+    rng = np.random.default_rng(21)
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny, cloudy=Nx > 6)
+    dz = np.full(Nz, 60.)
+    dz[0] = 300.                                                   # one 1-D layer on top
+    sd = P.sundir_from_angles(130., 45.)
+    res = {}
+    for walk in (False, True):
+        if walk:
+            os.environ["PPRTS_B200_CG_ACC_WALK"] = "1"
+        else:
+            os.environ.pop("PPRTS_B200_CG_ACC_WALK", None)
+        try:
+            s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, rtol=1e-9, atol=1e-30, precond=3, krylov_fp32=mixed)
+            P.set_optical_properties(s, 0.2, kabs, ksca, g)
+            P.solve_pprts(s, False, True, 1000.)
+            res[walk] = (P.pprts_get_result(s), s.info()["niter_diff"])
+            P.destroy_pprts(s)
+        finally:
+            os.environ.pop("PPRTS_B200_CG_ACC_WALK", None)
+    assert abs(res[False][1] - res[True][1]) <= 1, (res[False][1], res[True][1])
+    for a, b in zip(res[False][0], res[True][0]):
+        assert relerr(a, b) < 1e-7

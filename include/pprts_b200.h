@@ -137,7 +137,8 @@ typedef struct {
    * single_column_solve, src/pprts_base.F90:1189-1458) and leaves through the others without re-entering
    * (exchange_direct_boundary sends zeros across the edge, src/pprts_explicit.F90:262-306; the sweep takes the inflow,
    * :358-378).  As there, the stored solution keeps zeros on the inflow faces it owns, and the source term, absorption
-   * and the diffuse solve go on treating the stored beam periodically.  Not with geometric_coeffs or buildings. */
+   * and the diffuse solve go on treating the stored beam periodically.  The boundary columns always take the LUT's
+   * dir2dir, also with geometric_coeffs or buildings (get_coeff in single_column_solve, :1368-1382). */
   int open_bc;
 } pprts_b200_config;
 

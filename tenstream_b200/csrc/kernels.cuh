@@ -1244,11 +1244,14 @@ k_edir_tile_pass(Grid g, int xinc, int yinc, int n1d, double inc_top, const CT *
 // layer (I - M_ss) x_s = M_st top(k) by Gaussian elimination (2 Nds unknowns), then top(k+1); a 1-D layer carries
 // top(k+1) = exp(-kabs dz / cos theta) top(k) (:1355-1365 -- kabs alone, as written there) and no side flux.
 // One thread per edge column: the first Ny threads the x edge (-> bcx[d][k][j]), the next Nx the y edge (-> bcy[d][k][i]).
+// The coefficients are the stored dir2dir blocks of the edge column, which ARE the LUT's values unless geometric
+// coefficients or buildings replaced them (use_lut).
 template <class L, class CT>
 __global__ void __launch_bounds__(64)
 k_open_bc_columns(Grid g, int xinc, int yinc, int n1d, double fac, double costheta, int do_x, int do_y,
                   const CT *__restrict__ d2d, const double *__restrict__ kabs, const double *__restrict__ dz,
-                  double *__restrict__ bcx, double *__restrict__ bcy) {
+                  double *__restrict__ bcx, double *__restrict__ bcy, int use_lut, LutDev lut, SymMaps sym,
+                  const double *__restrict__ ksca, const double *__restrict__ gg) {
   constexpr int Nd = L::Nd, Ndt = L::Ndt, Nds = L::Nds, NS = 2 * L::Nds;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool isx = t < g.Ny;
@@ -1268,10 +1271,25 @@ k_open_bc_columns(Grid g, int xinc, int yinc, int n1d, double fac, double costhe
 #pragma unroll
       for (int d = Ndt; d < Nd; ++d) x[d] = 0.0;
     } else {
-      double cf[Nd * Nd], M[NS][NS + 1];
-      const long cb = cbase<Nd * Nd>(c);
+      double cf[Nd * Nd], M[NS][NS + 1];  // cf[dst * Nd + src]
+      if (use_lut) {
+        // the reference's boundary columns take the LUT's dir2dir whatever the interior uses (get_coeff in
+        // single_column_solve, :1368-1382): with geometric coefficients or buildings the stored blocks differ from it,
+        // so the block is interpolated here, with k_lookup's arithmetic (corner order, fma chain, rounding to CT)
+        float sample[4];
+        lut_sample(lut, kabs[c], ksca[c], gg[c], dz[c], g.dx, sample);
+        InterpPlan p;
+        make_plan(lut, sample, p);
+        for (int n = 0; n < Nd * Nd; ++n) {
+          double acc = 0.0;
+          for (int b = 0; b < p.ncorner; ++b) acc = fma(p.w[b], __ldg(lut.Tdir4 + p.ofs[b] * (long)(Nd * Nd) + sym.d2d[n]), acc);
+          cf[n] = (double)(CT)acc;
+        }
+      } else {
+        const long cb = cbase<Nd * Nd>(c);
 #pragma unroll
-      for (int n = 0; n < Nd * Nd; ++n) cf[n] = (double)d2d[cb + n * PB_TILE];  // cf[dst * Nd + src]
+        for (int n = 0; n < Nd * Nd; ++n) cf[n] = (double)d2d[cb + n * PB_TILE];
+      }
 #pragma unroll
       for (int p = 0; p < NS; ++p) {
         double rhs = 0.0;

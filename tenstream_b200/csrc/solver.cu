@@ -637,9 +637,6 @@ extern "C" int pprts_b200_create(const pprts_b200_config *cfg, const pprts_b200_
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return set_err(90, "no CUDA device: libpprts_b200 has no CPU fallback");
   if (cfg->geometric_coeffs && Nd != 3) return set_err(23, "geometric coeffs currently only implemented for 3 direct streams");
-  // the reference's boundary columns take LUT coefficients whatever the interior uses (src/pprts_base.F90:1368-1382);
-  // here they read the stored dir2dir of the edge columns, which is the same thing only without geometric coefficients
-  if (cfg->open_bc && cfg->geometric_coeffs) return set_err(25, "open_bc together with geometric_coeffs is not supported");
   if ((cfg->collapseindex > 1 ? cfg->collapseindex : 1) > cfg->Nz)
     return set_err(1, "collapseindex %d exceeds the %d atmosphere layers", cfg->collapseindex, cfg->Nz);
   auto *s = new pprts_b200_solver();
@@ -1138,7 +1135,8 @@ static int solve_edir(pprts_b200_solver *s, Solution &sol, double edirTOA) {
   if (edge_x || edge_y)
     DISPATCH_LC(s, LAUNCH(s, FAM_EDIR, (k_open_bc_columns<L, CT>), nblk(g.Nx + g.Ny, 64), 64, g, s->xinc, s->yinc, s->n1d, fac,
                            s->costheta, (int)edge_x, (int)edge_y, (const CT *)s->d2d, (const double *)s->kabs,
-                           (const double *)s->dz, s->bcx, s->bcy));
+                           (const double *)s->dz, s->bcx, s->bcy, (int)(s->cfg.geometric_coeffs != 0 || s->nbld > 0), s->lutdev,
+                           s->sym, (const double *)s->ksca, (const double *)s->gg));
   // The horizontal inputs of a pass are one pass old, so information needs one pass per column it crosses; the
   // norm is only read back every `check` passes to keep the host out of the loop.
   const int check = jacobi ? 4 : 2;
@@ -2396,7 +2394,6 @@ extern "C" int pprts_b200_set_buildings(pprts_b200_solver *s, int nfaces, const 
                                         const double *planck) {
   if (!s) return set_err(1, "null solver");
   CU(cudaSetDevice(s->device));
-  if (nfaces > 0 && s->cfg.open_bc) return set_err(63, "buildings are not supported together with open_bc (the boundary columns read the stored dir2dir)");
   if (nfaces > 0 && (!iface || !albedo)) return set_err(2, "set_buildings: iface and albedo are required");
   const Grid &g = s->g;
   for (int m = 0; m < nfaces; ++m)

@@ -120,15 +120,58 @@ def test_open_bc_8_streams(P, tmp_path_factory, phi0, theta0):
     P.destroy_pprts(s); o.destroy(); glut.close()
 
 
-def test_open_bc_errors(P, gpu_lut):
+@pytest.mark.parametrize("phi0,theta0", [(40., 35.), (220., 50.)])
+def test_open_bc_with_geometric_coeffs(P, gpu_lut, oracle_lut, phi0, theta0):
+    """-pprts_open_bc together with -pprts_geometric_coeffs: the boundary columns keep the LUT's dir2dir
+    (single_column_solve calls get_coeff, src/pprts_base.F90:1368-1382) while the interior sweeps with the analytic one"""
+    from oracle import binding as ob
+    rng = np.random.default_rng(5)
+    Nz, Nx, Ny = 6, 34, 9
+    j = np.arange(Ny)
+    dz3d = np.broadcast_to(60. * (1.0 - 0.3 / (1.0 + ((j - Ny / 2.0) / (Ny / 6.0)) ** 2))[None, None, :], (Nz, Nx, Ny)).copy()
+    kabs, ksca, g = atmosphere(rng, Nz, Nx, Ny)
+    sd = P.sundir_from_angles(phi0, theta0)
+    tol = dict(rtol=1e-10, atol=1e-30)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz3d=dz3d, lut=gpu_lut, coeff_fp32=False, geometric_coeffs=True,
+                     open_bc=True, **tol)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz3d, coeff_fp32=False, diff_solver=1, geometric_coeffs=True,
+                        open_bc=True, maxit_diff=5000, **tol)
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    o.set_optical_properties(0.2, kabs, ksca, g)
+    P.solve_pprts(s, False, True, 1000.)
+    assert o.solve(False, True, 1000.) == 0
+    assert relerr(s.state(1), o.state(1)) < 1e-9
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s), o.get_result()):
+        assert relerr(a, b, 1e-6) < 1e-7, (name, relerr(a, b, 1e-6))
+    P.destroy_pprts(s); o.destroy()
+
+
+@pytest.mark.parametrize("phi0,theta0", [(30., 40.), (210., 55.)])
+def test_open_bc_with_buildings(P, gpu_lut, oracle_lut, phi0, theta0):
+    """buildings in the sunward edge columns: their cells pass no direct radiation in the sweep (dir2dir = 0), the boundary
+    inflow is still that of the LUT's coefficients, as in the reference"""
+    from oracle import binding as ob
     from tenstream_b200 import buildings as B
-    sd = P.sundir_from_angles(10., 30.)
-    with pytest.raises(P.PprtsError, match="open_bc together with geometric_coeffs"):
-        P.init_pprts(0, 4, 3, 4, 100., 100., sd, dz3d=np.full((4, 3, 4), 60.), lut=gpu_lut, geometric_coeffs=True, open_bc=True)
-    s = P.init_pprts(0, 4, 3, 4, 100., 100., sd, dz1d=np.full(4, 60.), lut=gpu_lut, open_bc=True)
-    bld = B.box_buildings(4, 3, 4, [(4, 2, 2)], 0.3, None)
-    z = np.full((4, 3, 4), 1e-5)
-    P.set_optical_properties(s, 0.1, z, z, 0 * z)
-    with pytest.raises(P.PprtsError, match="open_bc"):
-        P.solve_pprts(s, False, True, 1000., opt_buildings=bld)
-    P.destroy_pprts(s)
+    rng = np.random.default_rng(6)
+    Nz, Nx, Ny = 7, 33, 9
+    kabs, ksca, g = atmosphere(rng, Nz, Nx, Ny)
+    sd = P.sundir_from_angles(phi0, theta0)
+    dz = np.full(Nz, 70.)
+    tol = dict(rtol=1e-10, atol=1e-30)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, dz1d=dz, lut=gpu_lut, coeff_fp32=False, open_bc=True, **tol)
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, 100., 100., sd, dz, coeff_fp32=False, diff_solver=1, open_bc=True,
+                        maxit_diff=20000, **tol)
+    cells = [(7, 1, 3), (6, 1, 3), (7, Nx, 5), (7, 12, 1), (7, 12, Ny), (5, 20, 4)]   # on all four domain edges + one inside
+    bld = B.box_buildings(Nz, Nx, Ny, cells, 0.3, None)
+    bld.albedo[:] = 0.3 * rng.uniform(0.5, 1.5, len(bld.albedo))
+    P.set_optical_properties(s, 0.2, kabs, ksca, g)
+    o.set_optical_properties(0.2, kabs, ksca, g)
+    o.set_buildings(bld.iface, bld.albedo, bld.planck)
+    P.solve_pprts(s, False, True, 1000., opt_buildings=bld)
+    assert o.solve(False, True, 1000.) == 0
+    assert relerr(s.state(1), o.state(1)) < 1e-9
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), P.pprts_get_result(s, opt_buildings=bld), o.get_result()):
+        assert relerr(a, b, 1e-6) < 1e-6, (name, relerr(a, b, 1e-6))
+    for name, a, b in zip(("edir", "incoming", "outgoing"), (bld.edir, bld.incoming, bld.outgoing), o.get_buildings_result()):
+        assert np.abs(a - b).max() <= 1e-6 * max(np.abs(b).max(), 1e-300), name
+    P.destroy_pprts(s); o.destroy()

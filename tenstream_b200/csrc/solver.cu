@@ -238,6 +238,11 @@ struct pprts_b200_solver {
   unsigned int *tile_class = nullptr;  // per coefficient tile: widening class of its diff2diff entries (common.cuh)
   int mm_variant = 2;  // 0: 2 stages + register prefetch, 1: 2 stages, 2: 1 stage x 4 CTAs/SM (fastest measured)
   double *b = nullptr, *kr[8] = {nullptr}, *edir_tmp = nullptr;
+  // CUDA graphs of one mixed-precision BiCGStab iteration (first / odd / even iteration of a cycle) for small domains,
+  // where the ~20 launches of an iteration cost more host time than GPU time
+  struct IterGraph { cudaGraphExec_t exec = nullptr; int key = -1; long launches = 0; long fam[FAM_COUNT] = {0}; };
+  IterGraph iter_graph[3];
+  bool iter_graph_off = false;
   double *blur_buf[4] = {nullptr, nullptr, nullptr, nullptr};  // smooth_surface_fluxes on a decomposed solver: send lo/hi, halo lo/hi
   size_t blur_cap = 0;
   double *bcx = nullptr, *bcy = nullptr;  // -pprts_open_bc: boundary inflow of the sunward edge columns [d][k][j] / [d][k][i]
@@ -800,6 +805,7 @@ extern "C" int pprts_b200_destroy(pprts_b200_solver *s) {
   for (int q = 0; q < 8; ++q) cudaFree(s->kr[q]);
   cudaFree(s->bcx); cudaFree(s->bcy);
   for (double *p : s->blur_buf) cudaFree(p);
+  for (auto &ig : s->iter_graph) if (ig.exec) cudaGraphExecDestroy(ig.exec);
   cudaFree(s->precRf); cudaFree(s->precInvf); cudaFree(s->precPU); cudaFree(s->precPD); cudaFree(s->vh_atm);
   for (double *p : s->vh_ghost) cudaFree(p);
   for (auto &sp : s->spare) { cudaFree(sp[0]); cudaFree(sp[1]); cudaFree(sp[2]); }
@@ -1509,6 +1515,14 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
   bool converged = false;
   sol.niter_diff = 0;
   bool have_ax = false;  // ax = A x of the current x is already there (a true-residual check that led to a new cycle)
+  // Small domains are launch-bound (configs[0]: ~20 launches of a few microseconds per iteration): their iterations are
+  // replayed as CUDA graphs.  Not while kernels are being timed, not on decomposed solvers (NCCL calls inside), not
+  // for large domains (the GPU is the limit there; PPRTS_B200_GRAPH_MAX_CELLS, default 2 M cells; 0 switches it off).
+  const char *gmc = getenv("PPRTS_B200_GRAPH_MAX_CELLS");  // read per solve: tests switch it
+  const long graph_max_cells = gmc ? strtol(gmc, nullptr, 10) : 2000000L;
+  const bool use_graph = !s->timing && !s->decomposed && !krylov_trace() && g.ncell <= graph_max_cells;
+  const int graph_key = (prec ? 1 : 0) | (fused ? 2 : 0) | (s->cg_off ? 4 : 0) | (s->cfg.precond << 3);
+  bool graphs_warm = false;
   for (int cycle = 0; !converged && cycle < 64; ++cycle) {
     if (cycle == 0 && sol.ediff_zero) {  // cold start: A x = 0 without looking (one fp64 MatMult per band)
       CU(cudaMemsetAsync(ax, 0, (size_t)n * sizeof(double), s->stream));
@@ -1531,22 +1545,62 @@ static int solve_ediff_mixed(pprts_b200_solver *s, Solution &sol, double rtol, d
     const double floor32 = 2e-6 * rc0;
     double inner = 0.9 * target;  // a little below: the recursive residual drifts from the true one by O(eps32)
     bool restart = false;
-    for (int it = 1; total < maxit && !restart && !converged; ++it) {
+    // the kernels of one iteration; they see `it` only as first / odd / even (which rho slot holds the new value)
+    auto iteration = [&](int it) -> int {
+      int irc;
       if (fused) {  // the update also leaves the restricted vector of the coarse-grid correction behind
         const CoarseGrid &c0 = s->cgl[0].c;
         DISPATCH_L(s, LAUNCH(s, FAM_VEC, (k_bicg32_update_restrict<L, 0>), nblk(c0.nclev, 128), 128, g, c0, it, (const float *)r, (const float *)v, p,
                               (const double *)s->sc, (const float *)s->cgl[0].coef, s->cgl[0].rbar, (float2 *)s->cgl[0].e));
       } else LAUNCH(s, FAM_VEC, k_bicg32_update_p, vec_grid(n), VEC_BLOCK, n, it, r, v, p, s->sc);
       if (prec) launch_prec32(s, p, ph, fused);
-      if ((rc = launch_matmult<1, float>(s, ph, v, rh, s->sc + SC_RHV))) return rc;
+      if ((irc = launch_matmult<1, float>(s, ph, v, rh, s->sc + SC_RHV))) return irc;
       if (fused) {
         const CoarseGrid &c0 = s->cgl[0].c;
         DISPATCH_L(s, LAUNCH(s, FAM_VEC, (k_bicg32_update_restrict<L, 1>), nblk(c0.nclev, 128), 128, g, c0, it, (const float *)r, (const float *)v, sv,
                               (const double *)s->sc, (const float *)s->cgl[0].coef, s->cgl[0].rbar, (float2 *)s->cgl[0].e));
       } else LAUNCH(s, FAM_VEC, k_bicg32_update_s, vec_grid(n), VEC_BLOCK, n, it, r, v, sv, s->sc);
       if (prec) launch_prec32(s, sv, sh, fused);
-      if ((rc = launch_matmult<2, float>(s, sh, t, sv, s->sc + SC_TS))) return rc;
+      if ((irc = launch_matmult<2, float>(s, sh, t, sv, s->sc + SC_TS))) return irc;
       LAUNCH(s, FAM_VEC, k_bicg32_update_xr, vec_grid(n), VEC_BLOCK, n, it, ph, sh, sv, t, rh, xc, r, s->partials, s->counter, s->sc);
+      return 0;
+    };
+    for (int it = 1; total < maxit && !restart && !converged; ++it) {
+      if (use_graph && !s->iter_graph_off && (it > 1 || graphs_warm)) {
+        // slot 0: first iteration of a cycle, 1: odd, 2: even; re-captured when the solver's preconditioner setting changed
+        auto &ig = s->iter_graph[it == 1 ? 0 : ((it & 1) ? 1 : 2)];
+        if (!ig.exec || ig.key != graph_key) {
+          if (ig.exec) { cudaGraphExecDestroy(ig.exec); ig.exec = nullptr; }
+          const long l0 = s->launches;
+          long f0[FAM_COUNT];
+          for (int q = 0; q < FAM_COUNT; ++q) f0[q] = s->fam_launch[q];
+          cudaGraph_t gr = nullptr;
+          bool ok = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+          if (ok) {
+            const int irc = iteration(it);
+            ok = cudaStreamEndCapture(s->stream, &gr) == cudaSuccess && irc == 0 && gr != nullptr;
+          }
+          if (ok) ok = cudaGraphInstantiate(&ig.exec, gr, 0) == cudaSuccess;
+          if (gr) cudaGraphDestroy(gr);
+          if (ok) {
+            ig.key = graph_key;
+            ig.launches = s->launches - l0;
+            for (int q = 0; q < FAM_COUNT; ++q) ig.fam[q] = s->fam_launch[q] - f0[q];
+          }
+          // the capture only recorded the launches: undo their count, the graph launch below adds it
+          s->launches = l0;
+          for (int q = 0; q < FAM_COUNT; ++q) s->fam_launch[q] = f0[q];
+          if (!ok) { cudaGetLastError(); ig.exec = nullptr; s->iter_graph_off = true; }
+        }
+        if (ig.exec) {
+          CU(cudaGraphLaunch(ig.exec, s->stream));
+          s->launches += ig.launches;
+          for (int q = 0; q < FAM_COUNT; ++q) s->fam_launch[q] += ig.fam[q];
+        } else if ((rc = iteration(it))) return rc;
+      } else {
+        if ((rc = iteration(it))) return rc;
+        graphs_warm = true;  // everything an iteration sets up lazily (function attributes, block sizes) exists now
+      }
       dirty = true;
       // The correction xc is an fp32 vector: left to grow over a whole cycle its rounding (6e-8 |x|) puts a floor of a few
       // 1e-5 r0 under the TRUE residual, right where the default tolerance sits (measured: recursive 1.3e-6, true 2.1e-5).

@@ -1246,3 +1246,44 @@ def test_galerkin_accumulation_variants_agree(P, gpu_lut, shape, mixed):
     assert abs(res[False][1] - res[True][1]) <= 1, (res[False][1], res[True][1])
     for a, b in zip(res[False][0], res[True][0]):
         assert relerr(a, b) < 1e-7
+
+
+@pytest.mark.parametrize("sid,shape", [(310, (10, 24, 20)), (310, (40, 32, 32)), (810, (8, 12, 10))])
+def test_iteration_graphs_replay_the_same_solve(P, gpu_lut, luts_810, sid, shape):
+    """Small domains replay the kernels of a mixed-precision BiCGStab iteration as CUDA graphs (first / odd / even
+    iteration): same iterates, same iteration and launch counts as the plain launches (PPRTS_B200_GRAPH_MAX_CELLS=0),
+    over several solves of one solver (solar, thermal, new optical properties, warm start)."""
+    Nz, Nx, Ny = shape
+    lut = gpu_lut if sid == 310 else luts_810[0]
+    rng = np.random.default_rng(31)
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny)
+    T = np.linspace(220, 290, Nz + 1)[:, None, None] + rng.uniform(-3, 3, (Nz + 1, Nx, Ny))
+    planck = 5.67e-8 * T ** 4 / np.pi
+    sd = P.sundir_from_angles(200., 50.)
+    res = {}
+    for graphs in (True, False):
+        if graphs:
+            os.environ.pop("PPRTS_B200_GRAPH_MAX_CELLS", None)
+        else:
+            os.environ["PPRTS_B200_GRAPH_MAX_CELLS"] = "0"
+        try:
+            s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., sd, solver=sid, dz1d=np.full(Nz, 60.), lut=lut, krylov_fp32=True,
+                             rtol=1e-8, atol=1e-30)
+            out = []
+            for rep in range(2):
+                P.set_optical_properties(s, 0.2, kabs * (1 + rep), ksca, g)
+                l0 = s.kernel_launches()
+                P.solve_pprts(s, False, True, 1000., 1)
+                out.append((P.pprts_get_result(s, 1), s.info(1)["niter_diff"], s.kernel_launches() - l0))
+                P.set_optical_properties(s, 0.1, kabs * 20, ksca * 0, g, planck=planck, planck_srfc=planck[-1])
+                l0 = s.kernel_launches()
+                P.solve_pprts(s, True, False, 0., 2)
+                out.append((P.pprts_get_result(s, 2), s.info(2)["niter_diff"], s.kernel_launches() - l0))
+            res[graphs] = out
+            P.destroy_pprts(s)
+        finally:
+            os.environ.pop("PPRTS_B200_GRAPH_MAX_CELLS", None)
+    for (fa, na, la), (fb, nb, lb) in zip(res[True], res[False]):
+        assert na == nb and la == lb, (na, nb, la, lb)
+        for a, b in zip(fa, fb):
+            assert np.array_equal(a, b)          # the same kernels in the same order: bitwise the same result

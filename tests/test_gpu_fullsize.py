@@ -217,3 +217,50 @@ def test_c5_hill_geometric_coeffs(P, bench_lut):
     # same absorbed fraction per cell and stream by construction -> domain absorption close; the beam is redistributed
     assert abs(res[True][2] / res[False][2] - 1) < 0.05
     assert abs(res[True][0] / res[False][0] - 1) < 0.10
+
+
+@pytest.mark.parametrize("phi0", [120., 300.])
+def test_c2_open_boundaries_properties(P, bench_lut, phi0):
+    """-pprts_open_bc at 256x256x80 (src/pprts_base.F90:1189-1458, src/pprts_explicit.F90:262-306, :358-378), through what
+    the construction guarantees at any size: (1) the boundary inflow is the side flux of a column that is its own
+    neighbour, so a horizontally homogeneous atmosphere reproduces its periodic beam in every cell; (2) nothing re-enters
+    the domain: with the cloud field the beam of the columns next to the sunward edges equals the homogeneous one down to
+    the level where their own clouds start, and the solve needs no more passes than the periodic one; (3) the owned
+    inflow faces hold zero, the TOA row the incoming flux; (4) the diffuse solve runs on top of it and closes the energy
+    budget of what entered through the top and the sides."""
+    from tenstream_b200 import scenarios
+    sc = scenarios.cloud_field(phi0=phi0)
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    assert (Nx, Ny, Nz) == (256, 256, 80)
+    sd = P.sundir_from_angles(sc["phi0"], sc["theta0"])
+    hom = {k: np.broadcast_to(sc[k][:, :1, :1], sc[k].shape).copy() for k in ("kabs", "ksca", "g")}   # the clear-sky profile
+    res = {}
+    for open_bc in (False, True):
+        s = P.init_pprts(0, Nz, Nx, Ny, sc["dx"], sc["dy"], sd, dz1d=sc["dz1d"], lut=bench_lut, coeff_fp32=True,
+                         krylov_fp32=True, open_bc=open_bc)
+        P.set_optical_properties(s, sc["albedo"], hom["kabs"], hom["ksca"], hom["g"])
+        P.solve_pprts(s, False, True, sc["edirTOA"], 1)
+        e_hom = s.state(1, 1)
+        P.set_optical_properties(s, sc["albedo"], sc["kabs"], sc["ksca"], sc["g"])
+        P.solve_pprts(s, False, True, sc["edirTOA"], 2)
+        res[open_bc] = dict(e_hom=e_hom, e=s.state(1, 2), info=s.info(2), flux=[a.copy() for a in P.pprts_get_result(s, 2)])
+        P.destroy_pprts(s)
+    per, opn = res[False], res[True]
+    xinc, yinc = int(np.sin(np.deg2rad(phi0)) <= 0), int(np.cos(np.deg2rad(phi0)) < 0)      # setup_suninfo (:1118-1183)
+    keep = np.ones_like(per["e_hom"], dtype=bool)
+    if xinc:
+        keep[1, :, 0, :] = False
+    if yinc:
+        keep[2, :, :, 0] = False
+    scale = np.abs(per["e_hom"]).max()
+    assert np.abs(opn["e_hom"] - per["e_hom"])[keep].max() < 1e-10 * scale                      # (1)
+    if xinc:
+        assert np.all(opn["e"][1, :, 0, :] == 0.0)                                              # (3)
+    if yinc:
+        assert np.all(opn["e"][2, :, :, 0] == 0.0)
+    assert np.allclose(opn["flux"][3][0], sc["edirTOA"] * np.cos(np.deg2rad(sc["theta0"])), rtol=1e-12)
+    assert opn["info"]["niter_dir"] <= per["info"]["niter_dir"]                                 # (2)
+    assert relmax(opn["flux"][3], per["flux"][3]) > 1e-3         # the beam that wrapped around the periodic domain is gone
+    edn, eup, abso, edir = opn["flux"]
+    assert all(np.isfinite(a).all() for a in opn["flux"])
+    assert abso.min() > -1e-6 * abso.max()

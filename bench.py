@@ -179,6 +179,29 @@ class Timer:
         return ms, s.kernel_launches() - l0
 
 
+def bind_near_gpu(torch, local):
+    """One process per GPU: run -- and first-touch the page-locked host buffers -- on the CPU cores next to this rank's
+    GPU (NVML's ideal CPU affinity of the device, intersected with what the process may use).  Multi-rank runs only: with
+    every rank on the default cores the transfers of the GPUs behind the other socket cross the inter-socket link.
+    Returns the cores the process was bound to, or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0")
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        near = cpus & allowed
+        if near and near != allowed:
+            os.sched_setaffinity(0, near)
+            return sorted(near)
+    except Exception:   # no NVML, restricted container, ...: keep the default placement
+        return None
+    return None
+
+
 def pinned_f(torch, shape):
     """page-locked float64 host array in Fortran order (what a host model's allocatable looks like to the C ABI)"""
     n = int(np.prod(shape))
@@ -197,6 +220,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the pprts path has no CPU fallback")
     torch.cuda.set_device(local)
+    near = bind_near_gpu(torch, local) if world > 1 and not os.environ.get("PPRTS_BENCH_NO_AFFINITY") else None
+    if near is not None:
+        print(f"[bench] rank {rank}: bound to the {len(near)} cores next to GPU {local} ({near[0]}..{near[-1]})", file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tenstream_b200 import pprts as P

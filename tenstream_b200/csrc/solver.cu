@@ -2582,6 +2582,7 @@ static int blur_pass_decomposed(pprts_b200_solver *s, int kw, int along_y, const
   const size_t n = (size_t)kw * (along_y ? g.Nx : g.Ny);
   if (n > s->blur_cap) {
     for (double *&p : s->blur_buf) { cudaFree(p); p = nullptr; }
+    s->blur_cap = 0;  // nothing usable until all four buffers exist again
     for (double *&p : s->blur_buf) DA(p, n);
     s->blur_cap = n;
   }

@@ -82,24 +82,57 @@ def reference_single_column(c, l1d, kabs, dz, costheta, Ndt, Nds):
     return np.linalg.solve(A, b).reshape(nz + 1, Nd).T     # (Nd, nz+1)
 
 
-def numpy_open_sweep(d2d, l1d, a33, bcx, bcy, xinc, yinc, fac):
-    """one sun-ordered pass with the boundary inflow on the sunward edge faces; faces are indexed 0..N (N = far edge)"""
-    top = np.zeros((Nz + 1, Nx, Ny)); X = np.zeros((Nz, Nx + 1, Ny)); Y = np.zeros((Nz, Nx, Ny + 1))
-    top[0] = fac
-    X[:, 0 if xinc else Nx, :] = bcx
-    Y[:, :, 0 if yinc else Ny] = bcy
+def numpy_open_sweep(d2d, l1d, a33, bcx, bcy, xinc, yinc, fac, Ndt=1, Nds=1):
+    """one sun-ordered pass with the boundary inflow on the sunward edge faces; faces are indexed 0..N (N = far edge);
+    top (Ndt, Nz+1, Nx, Ny), X (Nds, Nz, Nx+1, Ny), Y (Nds, Nz, Nx, Ny+1)"""
+    Nd = Ndt + 2 * Nds
+    top = np.zeros((Ndt, Nz + 1, Nx, Ny)); X = np.zeros((Nds, Nz, Nx + 1, Ny)); Y = np.zeros((Nds, Nz, Nx, Ny + 1))
+    top[:, 0] = fac
+    X[:, :, 0 if xinc else Nx, :] = bcx
+    Y[:, :, :, 0 if yinc else Ny] = bcy
     ii = range(Nx) if xinc else range(Nx - 1, -1, -1)
     jj = range(Ny) if yinc else range(Ny - 1, -1, -1)
     for k in range(Nz):
         for j in jj:
             for i in ii:
                 if l1d[k]:
-                    top[k + 1, i, j] = top[k, i, j] * a33[k, i, j]
+                    top[:, k + 1, i, j] = top[:, k, i, j] * a33[k, i, j]
                     continue
-                v = d2d[:, k, i, j].reshape(3, 3)
-                out = v @ np.array([top[k, i, j], X[k, i + 1 - xinc, j], Y[k, i, j + 1 - yinc]])
-                top[k + 1, i, j], X[k, i + xinc, j], Y[k, i, j + yinc] = out
+                v = d2d[:, k, i, j].reshape(Nd, Nd)
+                out = v @ np.concatenate([top[:, k, i, j], X[:, k, i + 1 - xinc, j], Y[:, k, i, j + 1 - yinc]])
+                top[:, k + 1, i, j], X[:, k, i + xinc, j], Y[:, k, i, j + yinc] = out[:Ndt], out[Ndt:Ndt + Nds], out[Ndt + Nds:]
     return top, X, Y
+
+
+def check_against_numpy(o, dz, Ndt, Nds, edirTOA=1000.):
+    """the oracle's open-boundary beam against the dense single-column solves + the numpy sweep"""
+    sun = o.suninfo()
+    xinc, yinc = sun["xinc"], sun["yinc"]
+    l1d = o.l1d
+    Nd = Ndt + 2 * Nds
+    E = np.asarray(o.scale_flx_arr(o.state(1), True, False))   # the stored W/m2 back to the energies [W] of the sweep
+    fac = edirTOA * DX * DX / (4 if Ndt == 4 else 1)           # dirtop%area_divider (src/pprts.F90:332-396)
+    assert np.allclose(E[:Ndt, 0], fac)
+    d2d = o.coeffs(1)                              # (Nd*Nd, Nz, Nx, Ny)
+    kabs = optprop(False)[0]
+    costheta = np.cos(np.deg2rad(40.))
+    a33 = np.where(l1d[:, None, None], E[0, 1:] / E[0, :-1], 0.0)
+    ib, jb = (0 if xinc else Nx - 1), (0 if yinc else Ny - 1)    # sunward edge columns
+    colx = [fac * reference_single_column(d2d[:, :, ib, j], l1d, kabs[:, ib, j], dz, costheta, Ndt, Nds) for j in range(Ny)]
+    coly = [fac * reference_single_column(d2d[:, :, i, jb], l1d, kabs[:, i, jb], dz, costheta, Ndt, Nds) for i in range(Nx)]
+    bcx = np.stack([c[Ndt:Ndt + Nds, :Nz] for c in colx], axis=2)          # (Nds, Nz, Ny)
+    bcy = np.stack([c[Ndt + Nds:Nd, :Nz] for c in coly], axis=2)           # (Nds, Nz, Nx)
+    top, X, Y = numpy_open_sweep(d2d, l1d, a33, bcx, bcy, xinc, yinc, fac, Ndt, Nds)
+    tol = dict(rtol=1e-11, atol=1e-9)
+    assert np.allclose(E[:Ndt], top, **tol)
+    Xs, Ys = X[:, :, :Nx].copy(), Y[:, :, :, :Ny].copy()  # the faces a rank owns
+    if xinc:
+        Xs[:, :, 0] = 0.0                          # the last exchange leaves zero on the owned inflow faces
+    if yinc:
+        Ys[:, :, :, 0] = 0.0
+    assert np.allclose(E[Ndt:Ndt + Nds, :Nz], Xs, **tol)
+    assert np.allclose(E[Ndt + Nds:, :Nz], Ys, **tol)
+    return bcx, bcy
 
 
 @pytest.mark.parametrize("phi0", [20., 110., 200., 290.])
@@ -109,34 +142,10 @@ def test_open_beam_vs_numpy_restatement(oracle_lut, phi0, thick_top):
     if thick_top:
         dz[:2] = 400.                              # dz/dx > twostr_ratio: two 1-D layers on top
     o = run(oracle_lut, phi0, True, False, dz=dz)
-    sun = o.suninfo()
-    xinc, yinc = sun["xinc"], sun["yinc"]
-    l1d = o.l1d
-    assert l1d.sum() == (2 if thick_top else 0)
-    E = np.asarray(o.scale_flx_arr(o.state(1), True, False))   # the stored W/m2 back to the energies [W] of the sweep
-    fac = 1000. * DX * DX
-    assert np.allclose(E[0, 0], fac)
-    d2d = o.coeffs(1)                              # (9, Nz, Nx, Ny)
-    kabs = optprop(False)[0]
-    costheta = np.cos(np.deg2rad(40.))
-    a33 = np.where(l1d[:, None, None], E[0, 1:] / E[0, :-1], 0.0)
-    ib, jb = (0 if xinc else Nx - 1), (0 if yinc else Ny - 1)    # sunward edge columns
-    bcx = np.stack([fac * reference_single_column(d2d[:, :, ib, j], l1d, kabs[:, ib, j], dz, costheta, 1, 1)[1, :Nz]
-                    for j in range(Ny)], axis=1)
-    bcy = np.stack([fac * reference_single_column(d2d[:, :, i, jb], l1d, kabs[:, i, jb], dz, costheta, 1, 1)[2, :Nz]
-                    for i in range(Nx)], axis=1)
+    assert o.l1d.sum() == (2 if thick_top else 0)
+    bcx, bcy = check_against_numpy(o, dz, 1, 1)
     if thick_top:                                  # 1-D layers: no side flux, exp(-kabs dz / cos theta) on top (:1355-1365)
-        assert np.all(bcx[:2] == 0.0) and np.all(bcy[:2] == 0.0) and np.all(bcx[2:] > 0.0)
-    top, X, Y = numpy_open_sweep(d2d, l1d, a33, bcx, bcy, xinc, yinc, fac)
-    tol = dict(rtol=1e-11, atol=1e-9)
-    assert np.allclose(E[0], top, **tol)
-    Xs, Ys = X[:, :Nx].copy(), Y[:, :, :Ny].copy()  # the faces a rank owns
-    if xinc:
-        Xs[:, 0] = 0.0                             # the last exchange leaves zero on the owned inflow faces
-    if yinc:
-        Ys[:, :, 0] = 0.0
-    assert np.allclose(E[1, :Nz], Xs, **tol)
-    assert np.allclose(E[2, :Nz], Ys, **tol)
+        assert np.all(bcx[:, :2] == 0.0) and np.all(bcy[:, :2] == 0.0) and np.all(bcx[:, 2:] > 0.0)
     o.destroy()
 
 
@@ -170,3 +179,13 @@ def test_open_bc_8_streams(oracle_lut_810, phi0=200.):
         keep[6:8, :, :, 0] = False
     assert np.allclose(eo[keep], ep[keep], rtol=1e-11, atol=1e-11 * np.abs(ep).max())
     p.destroy(); o.destroy()
+
+
+@pytest.mark.parametrize("phi0", [30., 250.])
+def test_open_beam_8_streams_vs_numpy_restatement(oracle_lut_810, phi0):
+    """8 direct streams: four top quadrants, two x-side and two y-side dofs -- 4 x 4 side systems per level"""
+    dz = np.full(Nz, 60.)
+    o = run(oracle_lut_810, phi0, True, False, dz=dz, solver_id=810)
+    check_against_numpy(o, dz, 4, 2)
+    o.destroy()
+

@@ -183,3 +183,84 @@ def test_solar_path_against_sparse_restatement(oracle_lut, phi0, theta0, thick_t
     ab = absorption(e, x, d2d, d2f, f2f, p, xinc, yinc)
     assert np.abs(ab - o.state(3)).max() < 1e-8 * np.abs(ab).max()
     o.destroy()
+
+
+def thermal_source(f2f, planck, Bsrfc, p):
+    """set_thermal_source (src/pprts.F90:4848-4987): Planck emission of every stream leaving a cell, weighted with the
+    emissivity 1 - sum_dst diff2diff(src, :) of that stream and B_eff of the layer seen from below / above"""
+    b = np.zeros(NF * (Nz + 1) * Nx * Ny)
+    a11, a12 = p["edd"][0], p["edd"][1]
+    Az = DX * DX
+    for i in range(Nx):
+        for j in range(Ny):
+            for k in range(Nz):
+                b0, b1 = planck[k, i, j], planck[k + 1, i, j]
+                tauz = p["kabs"][k, i, j] * p["dz"][k]
+                btop, bbot = ob.B_eff(b1, b0, tauz), ob.B_eff(b0, b1, tauz)
+                if p["l1d"][k]:
+                    emis = max(0.0, min(1.0, 1.0 - a11[k, i, j] - a12[k, i, j]))
+                    b[ix(NF, 1, k + 1, i, j)] += bbot * np.pi * Az * emis
+                    b[ix(NF, 0, k, i, j)] += btop * np.pi * Az * emis
+                    continue
+                _, ext = diff_locations(k, i, j)
+                D = f2f[:, k, i, j].reshape(NF, NF)
+                emis = np.clip(1.0 - D.sum(axis=0), 0.0, 1.0)
+                Ax = DX * p["dz"][k]
+                b[ext[0]] += btop * np.pi * Az * emis[0]      # E_up leaves through the top face
+                b[ext[1]] += bbot * np.pi * Az * emis[1]
+                for base in (2, 6):                           # x-side, y-side: streams = 2, the upper half is "up"
+                    for d in range(4):
+                        b[ext[base + d]] += (btop if d >= 2 else bbot) * emis[base + d] * np.pi * Ax / 2.0
+            b[ix(NF, 0, Nz, i, j)] += Bsrfc[i, j] * Az * max(0.0, min(1.0, 1.0 - p["albedo"])) * np.pi
+    return b
+
+
+@pytest.mark.parametrize("thick_top", [False, True])
+def test_thermal_path_against_sparse_restatement(oracle_lut, thick_top):
+    rng = np.random.default_rng(23)
+    kabs = 10 ** rng.uniform(-4.5, -3, (Nz, Nx, Ny))
+    ksca = 10 ** rng.uniform(-5, -3, (Nz, Nx, Ny))
+    g = rng.uniform(0, 0.9, (Nz, Nx, Ny))
+    dz = np.full(Nz, 60.)
+    if thick_top:
+        dz[:2] = 400.
+    T = np.linspace(220, 290, Nz + 1)[:, None, None] + rng.uniform(-3, 3, (Nz + 1, Nx, Ny))
+    planck = 5.67e-8 * T ** 4 / np.pi
+    Bsrfc = 5.67e-8 * rng.uniform(285, 295, (Nx, Ny)) ** 4 / np.pi
+    theta0 = 40.
+    o = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, DX, DX, ob.sundir_from_angles(10., theta0), dz, diff_solver=1, rtol=1e-13,
+                        atol=1e-30, maxit_diff=20000)
+    o.set_optical_properties(0.1, kabs, ksca, g, planck=planck, planck_srfc=Bsrfc)
+    assert o.solve(True, False, 0.0) == 0
+    l1d = o.l1d
+    edd = np.zeros((5, Nz, Nx, Ny))
+    for k in np.flatnonzero(l1d):
+        for i in range(Nx):
+            for j in range(Ny):
+                ka, ks, gg = ob.delta_scale(kabs[k, i, j], ksca[k, i, j], g[k, i, j])
+                ext = max(ka + ks, np.finfo(float).tiny)
+                edd[:, k, i, j] = ob.eddington_coeff_ec(dz[k] * ext, ks / ext, gg, np.cos(np.deg2rad(theta0)))
+    p = dict(kabs=kabs, dz=dz, l1d=l1d, edd=edd, albedo=0.1, theta0=theta0)
+    f2f = o.coeffs(3)
+    b = thermal_source(f2f, planck, Bsrfc, p)
+    b_or = o.state(4).reshape(-1)
+    assert np.abs(b - b_or).max() < 1e-10 * np.abs(b).max()
+    A = diffuse_matrix(f2f, edd[0], edd[1], l1d, p["albedo"])
+    x = spla.spsolve(A.tocsc(), b)
+    x_or = np.asarray(o.scale_flx_arr(o.state(2), False, False)).reshape(-1)
+    live = np.abs(x_or) > 0
+    assert np.abs(x - x_or)[live].max() < 1e-8 * np.abs(x).max()
+    # absorption: what the streams entering a cell lose, minus what the cell emits into the streams leaving it (:5372-5398)
+    ab = np.zeros((Nz, Nx, Ny))
+    for i in range(Nx):
+        for j in range(Ny):
+            for k in range(Nz):
+                ent, ext = diff_locations(k, i, j)
+                if l1d[k]:
+                    a = (x[ix(NF, 1, k, i, j)] + x[ix(NF, 0, k + 1, i, j)]) * max(0.0, 1 - edd[0, k, i, j] - edd[1, k, i, j])
+                else:
+                    a = x[ent] @ (1.0 - f2f[:, k, i, j].reshape(NF, NF).sum(axis=0))
+                a -= b[ext].sum()
+                ab[k, i, j] = a / (DX * DX * dz[k])
+    assert np.abs(ab - o.state(3)).max() < 1e-8 * np.abs(ab).max()
+    o.destroy()

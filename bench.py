@@ -18,6 +18,9 @@ reference's default solver tolerances (rtol 1e-5, atol 1e-4*Nx*Ny*(Nz+1); src/pp
   N > 1 : independent bands are sharded over the GPUs (weak scaling: every rank solves its own solar+thermal pair),
           the spectral sum of the fluxes is reduced with one NCCL all-reduce per step inside the timed region.
 
+`config` names the workload only and is the same object in both arms (the reference arm times a bounded sample of it,
+described in its cpu_baseline.sample); how this arm runs it (precisions, preconditioner, parallelism) is `implementation`.
+
 Legs appended to the same JSON line (each on the configuration BASELINE.json names, none of them the headline):
   roofline.step  whole-step HBM fraction with BASELINE.md's byte formula and the measured pass / MatMult / iteration counts
   parity         N = 1: deviation of the timed setting (default tolerances) from the committed converged oracle result
@@ -202,6 +205,16 @@ def bind_near_gpu(torch, local):
     return None
 
 
+def workload_config(nx, ny, nz, nbands):
+    """The `config` object of the JSON line: the workload, identical for both arms (the reference arm times a bounded
+    sample of it and says so in `cpu_baseline.sample`)."""
+    return {"workload": (f"pprts 3_10 solar+thermal, synthetic cloud field {nx}x{ny}x{nz}" +
+                         (" (BASELINE configs[1])" if (nx, ny, nz) == (256, 256, 80) else "")),
+            "bands_per_step_per_gpu": nbands, "cells": nx * ny * nz,
+            "tolerances": "reference defaults rtol=1e-5 atol=1e-4*Nx*Ny*(Nz+1)", "start": "cold (zero initial guess)",
+            "l2": "working set per step at this size (3.4 GB coefficients + 4 GB vectors at 256x256x80) is far larger than the 126 MB L2"}
+
+
 def pinned_f(torch, shape):
     """page-locked float64 host array in Fortran order (what a host model's allocatable looks like to the C ABI)"""
     n = int(np.prod(shape))
@@ -380,14 +393,15 @@ def run_ours(args):
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (solution, residual, fluxes) + f32 (Krylov work vectors, stored coefficients)" if mixed else "f64",
             "data": "synthetic",
-            "config": {"workload": (f"pprts 3_10 solar+thermal, synthetic cloud field {args.nx}x{args.ny}x{Nz} " +
-                                    ("(BASELINE configs[1])" if (args.nx, args.ny, Nz) == (256, 256, 80) else "")),
-                       "bands_per_step_per_gpu": len(bands), "cells": ncell, "coefficient_storage": "fp32",
-                       "state": ("fp64 solution + fp64 true residual (iterative refinement), fp32 Krylov work vectors"
-                                 if mixed else "fp64"), "tolerances": "reference defaults rtol=1e-5 atol=1e-4*Nx*Ny*(Nz+1)",
-                       "krylov": "BiCGStab, right-preconditioned: exact vertical-line (column) solve + additive coarse-grid correction on 4x4 and 8x8 column aggregates", "start": "cold (zero initial guess)",
-                       "l2": "working set per step (3.4 GB coefficients + 4 GB vectors) is far larger than the 126 MB L2",
-                       "parallelism": f"bands sharded over {world} GPU(s), one NCCL all-reduce of the flux sums per step"},
+            # `config` names the workload only -- the reference arm (--impl reference) prints the same object; how THIS arm
+            # runs it is under `implementation`
+            "config": workload_config(args.nx, args.ny, Nz, len(bands)),
+            "implementation": {
+                "coefficient_storage": "fp32",
+                "state": ("fp64 solution + fp64 true residual (iterative refinement), fp32 Krylov work vectors"
+                          if mixed else "fp64"),
+                "krylov": "BiCGStab, right-preconditioned: exact vertical-line (column) solve + additive coarse-grid correction on 4x4 and 8x8 column aggregates; the kernels of an iteration replayed as one CUDA graph",
+                "parallelism": f"bands sharded over {world} GPU(s), one NCCL all-reduce of the flux sums per step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "api": "stage_optical_properties_async -> set_optical_properties_staged -> solve -> get_result_async"},
@@ -841,8 +855,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"pprts 3_10 solar+thermal, synthetic cloud field {args.nx}x{args.ny}x{args.nz} "
-                                   f"(BASELINE configs[1]); timed on a bounded {a['sample']} sample of the same generator"},
+            "config": workload_config(args.nx, args.ny, args.nz, 2),   # the GPU arm's object; the sample is in cpu_baseline
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": a[best]["cores"], "kind": "port", "sample": sample, "rows": a},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

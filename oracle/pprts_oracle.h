@@ -10,7 +10,11 @@
  * its real LUT files are not available offline.  What pins this oracle is every LUT-free known-answer test of
  * the reference (tests/test_oracle_known_answers.py: interpolation, search, eddington, symmetry involutions,
  * mmap round trip, scale round trip) plus the reference's property tests run on synthetic tables
- * (absorption-by-divergence == absorption-by-coefficients, phi / phi+180 mirror symmetry, energy closure).
+ * (absorption-by-divergence == absorption-by-coefficients, phi / phi+180 mirror symmetry, energy closure), the
+ * reference's buildings / collapse / error-growth / geometric-coefficient / slope / convolution tests restated in
+ * tests/test_oracle_*.py, and a second, independent restatement of the path as sparse matrices in numpy / scipy
+ * (tests/test_oracle_independent_restatement.py: direct beam, sources, diffuse operator and solve, absorption for
+ * 3_10 / 8_10 / 3_24; tests/test_oracle_open_bc.py for the open-boundary beam) that agrees with this file to rounding.
  * End-to-end parity against reference-produced flux files is UNPINNED.
  *
  * Every function cites the reference file:line it follows (paths relative to the reference tree).

@@ -10,6 +10,7 @@ environment.
   thermal source   src/pprts.F90:4848-4987 (set_thermal_source)
   diffuse operator src/pprts_shell.F90:366-541 (op_mat_mult_ediff)
   absorption       src/pprts.F90:5300-5398, :5476-5503 (calc_flx_div by coefficient divergence)
+  results          src/pprts.F90:5840-5888 (pprts_get_result)
 
 The interpolated coefficients, the Eddington coefficients and B_eff are taken from the oracle (they are pinned separately
 on the reference's interpolation / Eddington / Schwarzschild known answers); everything that USES them is rebuilt here."""
@@ -237,6 +238,22 @@ def absorption(lay, e, x, b_th, d2d, d2f, f2f, p, xinc, yinc):
     return out
 
 
+def get_result(lay, e, x, ab, mu):
+    """pprts_get_result (src/pprts.F90:5840-5888) from the energies [W] of the solve: the direct flux is the mean over the
+    top streams, edn / eup the sums of the inward / outward top streams [W/m2]; solar results carry the factor mu"""
+    A = DX * DX
+    top = lambda v, nd, d: v.reshape(nd, Nz + 1, Nx, Ny)[d]   # noqa: E731
+    edir = sum(top(e, lay.ND, d) for d in range(lay.Ndt)) / A * mu if e is not None else np.zeros((Nz + 1, Nx, Ny))
+    edn = sum(top(x, lay.NF, d) for d, inw in enumerate(lay.top_in) if inw) / A * mu
+    eup = sum(top(x, lay.NF, d) for d, inw in enumerate(lay.top_in) if not inw) / A * mu
+    return edn, eup, ab * mu, edir
+
+
+def check_result(o, want):
+    for name, a, b in zip(("edn", "eup", "abso", "edir"), o.get_result(), want):
+        assert np.abs(a - b).max() <= 1e-8 * max(np.abs(b).max(), 1e-300), name
+
+
 def atmosphere(seed, thermal=False):
     rng = np.random.default_rng(seed)
     kabs = 10 ** rng.uniform(-4.5, -3, (Nz, Nx, Ny)) if thermal else 10 ** rng.uniform(-6, -4, (Nz, Nx, Ny))
@@ -284,6 +301,7 @@ def test_solar_path_against_sparse_restatement(luts, lay, phi0, theta0, thick_to
     # ---- absorption by coefficient divergence
     ab = absorption(lay, e, x, None, d2d, d2f, f2f, p, xinc, yinc)
     assert np.abs(ab - o.state(3)).max() < 1e-8 * np.abs(ab).max()
+    check_result(o, get_result(lay, e, x, ab, np.cos(np.deg2rad(theta0))))
     o.destroy()
 
 
@@ -315,4 +333,5 @@ def test_thermal_path_against_sparse_restatement(luts, lay, thick_top):
     # absorption: what the streams entering a cell lose, minus what the cell emits into the streams leaving it (:5372-5398)
     ab = absorption(lay, None, x, b, None, None, f2f, p, 0, 0)
     assert np.abs(ab - o.state(3)).max() < 1e-8 * np.abs(ab).max()
+    check_result(o, get_result(lay, None, x, ab, 1.0))
     o.destroy()

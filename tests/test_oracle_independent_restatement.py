@@ -335,3 +335,25 @@ def test_thermal_path_against_sparse_restatement(luts, lay, thick_top):
     assert np.abs(ab - o.state(3)).max() < 1e-8 * np.abs(ab).max()
     check_result(o, get_result(lay, None, x, ab, 1.0))
     o.destroy()
+
+
+@pytest.mark.parametrize("phi0", [110., 290.])
+def test_explicit_sor_path_reaches_the_same_solution(luts, phi0):
+    """explicit_ediff (alternating block Gauss-Seidel / SOR sweeps, src/pprts_explicit.F90:461-713, :849-1015) is the
+    reference's PETSc-free diffuse solver: iterated to its fixed point it has to give the direct solution of the same
+    sparse system"""
+    lay, theta0 = L310, 50.
+    _, kabs, ksca, g = atmosphere(29)
+    dz = np.full(Nz, 60.)
+    o = ob.OracleSolver(luts[310], Nz, Nx, Ny, DX, DX, ob.sundir_from_angles(phi0, theta0), dz, diff_solver=0, rtol=1e-14,
+                        atol=1e-30, maxit_diff=100000)
+    o.set_optical_properties(0.3, kabs, ksca, g)
+    assert o.solve(False, True, 1000.) == 0
+    l1d = o.l1d
+    p = dict(kabs=kabs, dz=dz, l1d=l1d, edd=np.zeros((5, Nz, Nx, Ny)), albedo=0.3, theta0=theta0)
+    A = diffuse_matrix(lay, o.coeffs(3), p["edd"][0], p["edd"][1], l1d, p["albedo"])
+    x = spla.spsolve(A.tocsc(), o.state(4).reshape(-1))
+    x_or = np.asarray(o.scale_flx_arr(o.state(2), False, False)).reshape(-1)
+    live = np.abs(x_or) > 0
+    assert np.abs(x - x_or)[live].max() < 1e-8 * np.abs(x).max()
+    o.destroy()

@@ -50,3 +50,54 @@ def test_oracle_reproduces_c1_golden(golden, tmp_path):
         assert a.shape == b.shape, k
         if a.dtype.kind == "f":
             assert np.abs(a - b).max() <= 1e-9 * max(1e-30, np.abs(b).max()), k
+
+
+def test_c1_golden_vs_independent_sparse_restatement(golden, tmp_path, monkeypatch):
+    """BASELINE configs[0] at its full size (32x32x40): the committed golden -- produced by the C oracle -- against the
+    independent sparse restatement of tests/test_oracle_independent_restatement.py, solved with scipy (direct solve for the
+    beam, scipy's own BiCGStab to 1e-12 for the diffuse system).  The fixture is thereby pinned by two restatements of the
+    reference that share nothing but the interpolated coefficients."""
+    import scipy.sparse.linalg as spla
+    import test_oracle_independent_restatement as R
+    from oracle import binding as ob
+    from tenstream_b200 import lut as L
+    sc, bands = mg.config_case("c1")
+    b0 = bands[0]
+    Nz, Nx, Ny = sc["Nz"], sc["Nx"], sc["Ny"]
+    assert (Nz, Nx, Ny) == (40, 32, 32) and sc["dx"] == sc["dy"]
+    for k, v in (("Nz", Nz), ("Nx", Nx), ("Ny", Ny), ("DX", sc["dx"])):
+        monkeypatch.setattr(R, k, v)
+    cfg = L.bench_config(310)
+    lut_dir = os.environ.get("PPRTS_B200_LUT_DIR", "/tmp/pprts_b200_luts")
+    os.makedirs(lut_dir, exist_ok=True)
+    base = os.path.join(lut_dir, "LUT")
+    paths = cfg.paths(base)
+    if not all(os.path.exists(p) for p in paths.values()):
+        L.write_synthetic_lut(cfg, base)
+    olut = ob.OracleLut(cfg, paths)
+    o = ob.OracleSolver(olut, Nz, Nx, Ny, sc["dx"], sc["dy"], ob.sundir_from_angles(sc["phi0"], sc["theta0"]), sc["dz1d"],
+                        coeff_fp32=True, diff_solver=1, maxit_diff=1)          # coefficients only: one Krylov iteration
+    o.set_optical_properties(b0["albedo"], b0["kabs"], b0["ksca"], b0["g"])
+    o.solve(False, True, b0["edirTOA"], b0["uid"])
+    l1d = o.l1d
+    assert not l1d.any()
+    sun = o.suninfo()
+    d2d, d2f, f2f = o.coeffs(1), o.coeffs(2), o.coeffs(3)
+    zeros = np.zeros((Nz, Nx, Ny))
+    lay = R.L310
+    p = dict(kabs=b0["kabs"], dz=sc["dz1d"], l1d=l1d, edd=np.zeros((5, Nz, Nx, Ny)), albedo=b0["albedo"], theta0=sc["theta0"])
+    A_dir, b_dir = R.direct_system(lay, d2d, zeros, l1d, sun["xinc"], sun["yinc"], b0["edirTOA"] * sc["dx"] * sc["dy"])
+    e = spla.spsolve(A_dir.tocsc(), b_dir)
+    b = R.solar_source(lay, e, d2f, zeros, zeros, l1d, sun["xinc"], sun["yinc"], b0["albedo"])
+    A = R.diffuse_matrix(lay, f2f, zeros, zeros, l1d, b0["albedo"]).tocsr()
+    x, info = spla.bicgstab(A, b, rtol=1e-12, atol=0.0, maxiter=5000)
+    assert info == 0
+    assert np.linalg.norm(A @ x - b) <= 1e-11 * np.linalg.norm(b)
+    ab = R.absorption(lay, e, x, None, d2d, d2f, f2f, p, sun["xinc"], sun["yinc"])
+    fields = R.get_result(lay, e, x, ab, np.cos(np.deg2rad(sc["theta0"])))
+    out = {}
+    mg.summarize("c1/solar", fields, golden["c1/cols"], golden["c1/levels"], out)
+    for k, a in out.items():
+        g = golden[k]
+        assert np.abs(a - g).max() <= 1e-7 * max(1e-30, np.abs(g).max()), (k, np.abs(a - g).max(), np.abs(g).max())
+    o.destroy(); olut.close()

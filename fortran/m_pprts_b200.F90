@@ -134,6 +134,12 @@ module m_pprts_b200
       type(c_ptr), value :: solver, edir, incoming, outgoing
       integer(c_int), value :: uid
     end function
+    integer(c_int) function c_set_abso_in_buildings(solver, uid, val) bind(c, name='pprts_b200_set_abso_in_buildings')
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: solver
+      integer(c_int), value :: uid
+      real(c_double), value :: val
+    end function
     ! overlapped host transfers for a caller's own band loop (INTEGRATION.md section 3)
     integer(c_int) function c_stage_optical_properties_async(solver, slot, albedo, kabs, ksca, g, planck, planck_srfc, albedo_2d) &
         & bind(c, name='pprts_b200_stage_optical_properties_async')
@@ -332,12 +338,14 @@ contains
   end function
 
   !> pprts_get_result (src/pprts.F90:5799): allocates the outputs if needed, like the reference
-  subroutine pprts_get_result(solver, redn, reup, rabso, redir, opt_solution_uid, opt_buildings)
+  !> set_abso_in_buildings: the value of -pprts_set_abso_in_buildings (src/pprts.F90:5986-6009), an argument here
+  subroutine pprts_get_result(solver, redn, reup, rabso, redir, opt_solution_uid, opt_buildings, set_abso_in_buildings)
     type(t_solver_b200), intent(inout) :: solver
     real(ireals), allocatable, target, intent(inout) :: redn(:, :, :), reup(:, :, :), rabso(:, :, :)
     real(ireals), allocatable, target, intent(inout), optional :: redir(:, :, :)
     integer(iintegers), intent(in), optional :: opt_solution_uid
     type(t_pprts_buildings_b200), intent(inout), target, optional :: opt_buildings
+    real(ireals), intent(in), optional :: set_abso_in_buildings
     integer(c_int) :: uid
     type(c_ptr) :: pdir
     uid = 0; if (present(opt_solution_uid)) uid = opt_solution_uid
@@ -356,6 +364,8 @@ contains
       if (.not. allocated(opt_buildings%outgoing)) allocate (opt_buildings%outgoing(size(opt_buildings%iface)))
       call chkerr(c_get_buildings_result(solver%h, uid, c_loc(opt_buildings%edir), c_loc(opt_buildings%incoming), &
         & c_loc(opt_buildings%outgoing)), 'pprts_get_result(opt_buildings)')
+      if (present(set_abso_in_buildings)) &
+        & call chkerr(c_set_abso_in_buildings(solver%h, uid, real(set_abso_in_buildings, c_double)), 'set_abso_in_buildings')
     end if
   end subroutine
 

@@ -274,6 +274,12 @@ int pprts_b200_set_buildings(pprts_b200_solver *solver, int nfaces, const int *i
 int pprts_b200_get_buildings_result(pprts_b200_solver *solver, int uid, double *edir, double *incoming,
                                     double *outgoing);
 
+/* -pprts_set_abso_in_buildings <val> (src/pprts.F90:5986-6009, the last step of pprts_get_result(opt_buildings)): the
+ * stored absorption of the cells that carry a building face becomes val; later pprts_b200_get_result calls for this uid
+ * return it (x mu for a solar solution), results already fetched are unaffected.  Call it after get_result, as the
+ * reference does. */
+int pprts_b200_set_abso_in_buildings(pprts_b200_solver *solver, int uid, double val);
+
 /* introspection (parity tests, profiling) */
 /* which: 1 dir2dir, 2 dir2diff, 3 diff2diff -> out (ncoef, Nz, Nx, Ny) column-major, zeros in 1-D layers */
 int pprts_b200_get_coeffs(pprts_b200_solver *solver, int which, double *out);

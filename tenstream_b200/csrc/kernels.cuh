@@ -3666,6 +3666,15 @@ __global__ void k_buildings_result(Grid g, int lsolar, double mu, int nb, const 
   out_out[m] = out;
 }
 
+// set_abso_in_buildings (-pprts_set_abso_in_buildings <val>, src/pprts.F90:5986-6009): the stored absorption of every
+// cell that carries a building face becomes val (as stored, i.e. before the mu scaling of a solar pprts_get_result)
+__global__ void k_buildings_set_abso(Grid g, int nb, const int *__restrict__ iface, double val, double *__restrict__ abso) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  const BldFace f = bld_decode(g, iface[m]);
+  abso[lidx(g, f.k, f.j, f.i)] = val;
+}
+
 // =================================================================================================================
 // HOT LOOP E: absorption (src/pprts.F90:5152-5504 calc_flx_div) -- fluxes in W, result in W/m3
 // =================================================================================================================

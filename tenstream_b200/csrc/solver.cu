@@ -2500,6 +2500,20 @@ extern "C" int pprts_b200_get_buildings_result(pprts_b200_solver *s, int uid, do
   if (outgoing) std::copy(h.begin() + 2 * n, h.end(), outgoing);
   return 0;
 }
+// set_abso_in_buildings (src/pprts.F90:5986-6009), what pprts_get_result(opt_buildings) does LAST under
+// -pprts_set_abso_in_buildings <val>: solution%abso of the cells with building faces is overwritten after the result has
+// been copied out, so the pprts_get_result calls that follow see val (x mu for a solar solution), the current one does not.
+extern "C" int pprts_b200_set_abso_in_buildings(pprts_b200_solver *s, int uid, double val) {
+  if (!s) return set_err(1, "null solver");
+  CU(cudaSetDevice(s->device));
+  if (s->nbld <= 0) return s->decomposed ? 0 : set_err(62, "no buildings attached to the solver");
+  Solution *sol;
+  int rc = find_solution(s, uid, &sol);
+  if (rc) return rc;
+  LAUNCH(s, FAM_ABSO, k_buildings_set_abso, nblk(s->nbld, 128), 128, s->g, s->nbld, (const int *)s->bld_iface, val, sol->abso);
+  s->res_valid = false;
+  return 0;
+}
 // slope_correction_fluxes(solver, edir) (src/pprts_postprocess.F90:130-196), the spectral callers' post-processing of
 // the direct flux on a terrain-following grid (rrtmg/rrtmg/pprts_rrtmg.F90 after the band sum).  edir: host array
 // (Nz+1,Nx,Ny) column-major, corrected in place.  Needs init with dz3d (atm%hgrad, src/pprts.F90:621) and one domain.

@@ -80,7 +80,7 @@ ABI_SYMBOLS = [
     "pprts_b200_slope_correction_fluxes", "pprts_b200_slope_correct_accumulated", "pprts_b200_polyfit",
     "pprts_b200_find_iter_and_kernelwidth", "pprts_b200_smooth_surface_fluxes", "pprts_b200_smooth_accumulated",
     "pprts_b200_krylov_retries", "pprts_b200_debug_fail_next_krylov", "pprts_b200_stage_optical_properties_async",
-    "pprts_b200_get_result_async", "pprts_b200_wait_results",
+    "pprts_b200_get_result_async", "pprts_b200_wait_results", "pprts_b200_set_abso_in_buildings",
 ]
 
 
@@ -131,6 +131,7 @@ def lib():
     L.pprts_b200_polyfit.argtypes = [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
     L.pprts_b200_set_buildings.argtypes = [C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_void_p]
     L.pprts_b200_get_buildings_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pprts_b200_set_abso_in_buildings.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.pprts_b200_kernel_launches.restype = C.c_long
     L.pprts_b200_kernel_launches.argtypes = [C.c_void_p]
     L.pprts_b200_stream.restype = C.c_void_p
@@ -528,10 +529,14 @@ def solution_times(solver: Solver, uid):
     return t, m
 
 
-def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None, opt_buildings=None):
+def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None, opt_buildings=None, set_abso_in_buildings=None):
     """``pprts_get_result`` (src/pprts.F90:5799-5917) -> (edn, eup, abso, edir) in W/m2 resp. W/m3,
     shapes (Nz+1,Nx,Ny) / (Nz,Nx,Ny).  ``out`` may carry preallocated Fortran-ordered arrays.  With ``opt_buildings``
-    (the object given to solve_pprts) its ``edir / incoming / outgoing`` per-face fluxes are filled (:5906-5910)."""
+    (the object given to solve_pprts) its ``edir / incoming / outgoing`` per-face fluxes are filled (:5906-5910).
+    ``set_abso_in_buildings`` is the value of the option ``-pprts_set_abso_in_buildings`` (:5986-6009): afterwards the
+    STORED absorption of the cells with building faces is that value, which the next pprts_get_result of this uid returns
+    (times mu for a solar solution) -- the arrays returned by this call still hold the computed absorption, as in the
+    reference."""
     edn, eup, abso, edir = out if out is not None else _alloc_results(solver)
     _chk(lib().pprts_b200_get_result(solver._h, int(opt_solution_uid), _vp(edn), _vp(eup), _vp(abso), _vp(edir)),
          "pprts_get_result")
@@ -541,6 +546,9 @@ def pprts_get_result(solver: Solver, opt_solution_uid=0, out=None, opt_buildings
         _chk(lib().pprts_b200_get_buildings_result(solver._h, int(opt_solution_uid), _vp(be), _vp(bi), _vp(bo)),
              "pprts_get_result(opt_buildings)")
         opt_buildings.edir, opt_buildings.incoming, opt_buildings.outgoing = be, bi, bo
+        if set_abso_in_buildings is not None:
+            _chk(lib().pprts_b200_set_abso_in_buildings(solver._h, int(opt_solution_uid), float(set_abso_in_buildings)),
+                 "pprts_get_result(set_abso_in_buildings)")
     return edn, eup, abso, edir
 
 

@@ -924,6 +924,40 @@ def test_buildings_removed_and_errors(P, gpu_lut):
     P.destroy_pprts(s)
 
 
+@pytest.mark.parametrize("solar", [True, False])
+def test_set_abso_in_buildings(P, gpu_lut, solar):
+    """-pprts_set_abso_in_buildings <val> (src/pprts.F90:5986-6009): pprts_get_result(opt_buildings) overwrites
+    solution%abso of the cells with building faces AFTER it has copied the result out (:5880 before :5909), so the
+    call that carries the option still returns the computed absorption, the next one returns val (x mu, :5882-5887, for a
+    solar solution) in exactly those cells and the same numbers everywhere else."""
+    from tenstream_b200 import buildings as B
+    rng = np.random.default_rng(11)
+    Nz, Nx, Ny = 5, 6, 7
+    theta0 = 35.
+    kabs, ksca, g = random_atm(rng, Nz, Nx, Ny, cloudy=False)
+    s = P.init_pprts(0, Nz, Nx, Ny, 100., 100., P.sundir_from_angles(200., theta0), dz1d=np.full(Nz, 80.), lut=gpu_lut,
+                     rtol=1e-10, atol=1e-30)
+    plck = None if solar else np.full((Nz + 1, Nx, Ny), 100. / np.pi)
+    P.set_optical_properties(s, 0.2, kabs, ksca * 20, g, planck=plck)
+    bld = B.box_buildings(Nz, Nx, Ny, [(4, 3, 3), (3, 5, 6)], 0.4, None if solar else 50.)
+    P.solve_pprts(s, not solar, solar, 100.0, 2, opt_buildings=bld)
+    first = [a.copy() for a in P.pprts_get_result(s, 2, opt_buildings=bld)]
+    val = -7.25
+    with_opt = [a.copy() for a in P.pprts_get_result(s, 2, opt_buildings=bld, set_abso_in_buildings=val)]
+    for a, b in zip(first, with_opt):
+        np.testing.assert_array_equal(a, b)
+    after = P.pprts_get_result(s, 2, opt_buildings=bld)
+    inside = np.zeros((Nz, Nx, Ny), dtype=bool)
+    for k, i, j in [(4, 3, 3), (3, 5, 6)]:
+        inside[k - 1, i - 1, j - 1] = True                    # box_buildings takes 1-based cells
+    mu = np.cos(np.deg2rad(theta0)) if solar else 1.0
+    np.testing.assert_allclose(after[2][inside], val * mu, rtol=1e-14)
+    np.testing.assert_array_equal(after[2][~inside], first[2][~inside])
+    for q in (0, 1, 3):
+        np.testing.assert_array_equal(after[q], first[q])
+    P.destroy_pprts(s)
+
+
 # ---- error-growth tracking of stored solutions (src/adaptive_spectral_integration.F90) ------------------------------------
 def test_error_growth_tracking(P, gpu_lut, oracle_lut):
     """tests/pprts_error_growth_tracking/pprts_error_growth_tracking.F90:66-125 through the CUDA path (options

@@ -22,7 +22,7 @@ def small_case(solar=True, seed=4):
     ksca = rng.uniform(1e-5, 5e-3, (Nz, Nx, Ny))
     g = rng.uniform(0.0, 0.8, (Nz, Nx, Ny))
     planck = None if solar else np.linspace(60., 120., Nz + 1)[:, None, None] * np.ones((1, Nx, Ny))
-    return dict(Nz=Nz, Nx=Nx, Ny=Ny, solver_id=310, dx=100., dy=120., sundir=P.sundir_from_angles(130., 35.),
+    return dict(Nz=Nz, Nx=Nx, Ny=Ny, solver_id=310, dx=100., dy=100., sundir=P.sundir_from_angles(130., 35.),
                 dz1d=np.linspace(60., 140., Nz), albedo=0.2, kabs=kabs, ksca=ksca, g=g, lsolar=solar, lthermal=not solar,
                 edirTOA=1000. if solar else 0., planck=planck, rtol=1e-9, atol=1e-30)
 

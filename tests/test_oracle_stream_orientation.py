@@ -1,0 +1,73 @@
+"""The chain sun azimuth -> xinc / yinc -> stream permutations -> table orientation, checked on its physics.
+
+The tables hold the beam in ONE orientation (towards +x / +y, pinned on the reference's boxmc known answers in
+tests/test_lut_stream_conventions.py); for any other sun azimuth pprts mirrors the stream indices
+(lswitch_east = xinc == 0, lswitch_north = yinc == 0, src/pprts.F90:1157-1167, :3161, src/optprop.F90:1009-1045).  A mirror
+applied the wrong way round keeps every symmetry test happy -- the solution is then the mirror image of the right one in the
+diffuse streams only -- but it sends the forward-scattered light of a cloud UPSTREAM.  One strongly forward-scattering cell in
+a vacuum domain, sun from the four cardinal directions: the diffuse energy that leaves the cell sideways must leave it on
+the side the beam leaves it, in the stream that travels that way, and land on the ground downstream of the cell.
+
+Stream numbering of 3_10 (src/pprts.F90:256-443, 0-based): 2 / 3 = downward through an x face travelling -x / +x, 6 / 7 the same
+in y; a stream travelling towards + leaves cell i through face i+1, one travelling towards - through face i.
+(Checked to discriminate: with the dir2diff permutation of the oracle applied the wrong way round -- `xinc != 0` in
+alloc_coeff_dir2diff -- all four cases fail.)
+sundir = the direction the photons travel (spherical_2_cartesian): phi0 = 0 sun in the north (towards -y), 90 in the east
+(towards -x)."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+
+Nz, Nx, Ny = 5, 9, 9
+K, I, J = 1, 4, 4
+DX = DZ = 100.0
+
+
+def solve(oracle_lut, phi0, theta0=60.0):
+    s = ob.OracleSolver(oracle_lut, Nz, Nx, Ny, DX, DX, ob.sundir_from_angles(phi0, theta0), np.full(Nz, DZ), diff_solver=0,
+                        rtol=1e-8)
+    kabs = np.zeros((Nz, Nx, Ny))
+    ksca = np.zeros((Nz, Nx, Ny))
+    g = np.zeros((Nz, Nx, Ny))
+    ksca[K, I, J] = 1.0 / DZ
+    g[K, I, J] = 0.85
+    s.set_optical_properties(0.0, kabs, ksca, g)
+    assert s.solve(False, True, 1000.0) == 0
+    ediff = s.state(2)
+    edn = s.get_result()[0]
+    s.destroy()
+    return ediff, edn
+
+
+# phi0 -> (axis the beam runs along, its sign)
+CASES = {90.0: ("x", -1), 270.0: ("x", +1), 0.0: ("y", -1), 180.0: ("y", +1)}
+
+
+@pytest.mark.parametrize("phi0", sorted(CASES))
+def test_forward_scattered_light_leaves_downstream(oracle_lut, phi0):
+    axis, sign = CASES[phi0]
+    ediff, edn = solve(oracle_lut, phi0)
+    minus, plus = (2, 3) if axis == "x" else (6, 7)
+
+    def face(dof, towards_plus):          # the cloud cell's face that a stream travelling that way leaves through
+        if axis == "x":
+            return ediff[dof, K, I + 1 if towards_plus else I, J]
+        return ediff[dof, K, I, J + 1 if towards_plus else J]
+    down = face(plus, True) if sign > 0 else face(minus, False)
+    up = face(minus, False) if sign > 0 else face(plus, True)
+    assert down > 0 and up > 0
+    assert down > 3.0 * up, (phi0, down, up)            # isotropic part both ways, the forward peak only downstream
+    # across the beam the two sides are mirror images
+    if axis == "x":
+        a, b = ediff[6, K, I, J], ediff[7, K, I, J + 1]
+    else:
+        a, b = ediff[2, K, I, J], ediff[3, K, I + 1, J]
+    assert a == pytest.approx(b, rel=1e-6)
+    # the diffuse light reaches the ground downstream of the cell, not upstream of it
+    srf = edn[Nz]
+    prof = srf.sum(axis=1) if axis == "x" else srf.sum(axis=0)
+    c = I if axis == "x" else J
+    ahead = sum(prof[(c + sign * d) % len(prof)] for d in (1, 2, 3))
+    behind = sum(prof[(c - sign * d) % len(prof)] for d in (1, 2, 3))
+    assert ahead > 1.2 * behind, (phi0, ahead, behind)

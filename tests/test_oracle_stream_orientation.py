@@ -71,3 +71,43 @@ def test_forward_scattered_light_leaves_downstream(oracle_lut, phi0):
     ahead = sum(prof[(c + sign * d) % len(prof)] for d in (1, 2, 3))
     behind = sum(prof[(c - sign * d) % len(prof)] for d in (1, 2, 3))
     assert ahead > 1.2 * behind, (phi0, ahead, behind)
+
+
+# ---- 8 direct streams: the sub-face permutations (dir2dir permutes sources AND destinations, src/optprop.F90:1268-1301) -------
+@pytest.fixture(scope="module")
+def lut810(tmp_path_factory):
+    from tenstream_b200 import lut as L
+    cfg = L.LutConfig(solver_id=810, tau=L.PRESET_TAU31[::3].copy(), w0=[0.0, 0.5, 0.99999], aspect=[0.25, 0.5, 1.0, 2.0],
+                      g=[0.0, 0.5], phi=[0., 45., 90.], theta=[0., 45., 90.])
+    paths = L.write_synthetic_lut(cfg, str(tmp_path_factory.mktemp("lut810o") / "LUT"))
+    return ob.OracleLut(cfg, paths)
+
+
+# phi0 -> (offset of the cell downstream of the cloud, top quadrants in its shadow, top quadrants in the light);
+# quadrants (src/boxmc_8_10.inc:27-35): 0 x-lo/y-lo, 1 x-hi/y-lo, 2 x-lo/y-hi, 3 x-hi/y-hi
+SHADOW = {270.0: ((1, 0), (0, 2), (1, 3)), 90.0: ((-1, 0), (1, 3), (0, 2)),
+          180.0: ((0, 1), (0, 1), (2, 3)), 0.0: ((0, -1), (2, 3), (0, 1))}
+
+
+@pytest.mark.parametrize("phi0", sorted(SHADOW))
+def test_half_cell_shadow_falls_on_the_downstream_quadrants(lut810, phi0):
+    """dz = dx / 2 and a 45 degree sun: the beam moves half a cell per layer, so one layer below an opaque cell the cell
+    downstream of it has the half next to the cloud in the shadow and the far half in the light.  (Fails in all four cases
+    when the oracle applies the dir2dir permutation the wrong way round.)"""
+    (di, dj), dark, lit = SHADOW[phi0]
+    s = ob.OracleSolver(lut810, Nz, Nx, Ny, DX, DX, ob.sundir_from_angles(phi0, 45.0), np.full(Nz, DX / 2), solver_id=810,
+                        diff_solver=0, rtol=1e-8)
+    kabs = np.zeros((Nz, Nx, Ny))
+    kabs[K, I, J] = 1.0                       # tau = 50: nothing gets through
+    s.set_optical_properties(0.0, kabs, np.zeros((Nz, Nx, Ny)), np.zeros((Nz, Nx, Ny)))
+    assert s.solve(False, True, 1000.0) == 0
+    edir = s.state(1)
+    s.destroy()
+    free = edir[:4, K + 1, 0, 0]              # far away from the cloud
+    assert free.min() > 0
+    here = edir[:4, K + 1, I + di, J + dj]
+    for q in dark:
+        assert here[q] < 0.1 * free[q], (phi0, q, here, free)      # rays that only clip the cloud's edge get through
+    for q in lit:
+        assert here[q] == pytest.approx(free[q], rel=1e-6), (phi0, q, here, free)
+    assert edir[:4, K + 1, I, J].max() < 0.1 * free.min()           # under the cloud itself: dark

@@ -111,3 +111,28 @@ def test_half_cell_shadow_falls_on_the_downstream_quadrants(lut810, phi0):
     for q in lit:
         assert here[q] == pytest.approx(free[q], rel=1e-6), (phi0, q, here, free)
     assert edir[:4, K + 1, I, J].max() < 0.1 * free.min()           # under the cloud itself: dark
+
+
+# ---- thermal emission: which level's Planck value an optically thick layer shows -------------------------------------------
+@pytest.mark.parametrize("dx", [100.0, 10.0])      # 3-D cells (dz / dx = 1) and 1-D layers (dz / dx = 10 > twostr_ratio)
+def test_thick_layers_emit_the_planck_value_of_the_near_level(oracle_lut, dx):
+    """set_thermal_source (src/pprts.F90:4848-4987): B_eff(far, near, tau) -- the upward stream leaving a layer through its
+    top carries the layer's emission weighted towards the TOP level, the downward one towards the BOTTOM level.  With
+    tau = 20 per layer the flux through a level is pi x its own Planck value plus a gradient term of order 1 / tau; mixing up
+    the two levels would show the neighbouring level's value (a factor 2 at the top of this profile)."""
+    nz = 4
+    s = ob.OracleSolver(oracle_lut, nz, 3, 3, dx, dx, ob.sundir_from_angles(0., 0.), np.full(nz, 100.0), diff_solver=0,
+                        rtol=1e-8)
+    assert s.l1d.all() == (dx < 50)
+    kabs = np.full((nz, 3, 3), 0.2)
+    z = np.zeros((nz, 3, 3))
+    planck = (np.array([10., 20., 30., 40., 50.]) / np.pi)[:, None, None] * np.ones((1, 3, 3))
+    s.set_optical_properties(0.0, kabs, z, z, planck=planck)
+    assert s.solve(True, False, 0.0) == 0
+    edn, eup, abso, _ = s.get_result()
+    s.destroy()
+    assert eup[0, 1, 1] == pytest.approx(10.0, rel=0.12) and eup[0, 1, 1] >= 10.0       # the level's own value, from below
+    assert edn[nz, 1, 1] == pytest.approx(50.0, rel=0.12) and edn[nz, 1, 1] <= 50.0
+    for k in (1, 2, 3):                                   # inside: up from the warmer side, down from the colder one
+        b = 10.0 * (k + 1)
+        assert b <= eup[k, 1, 1] < b * 1.12 and b * 0.88 < edn[k, 1, 1] <= b

@@ -136,3 +136,31 @@ def test_thick_layers_emit_the_planck_value_of_the_near_level(oracle_lut, dx):
     for k in (1, 2, 3):                                   # inside: up from the warmer side, down from the colder one
         b = 10.0 * (k + 1)
         assert b <= eup[k, 1, 1] < b * 1.12 and b * 0.88 < edn[k, 1, 1] <= b
+
+
+# ---- the direct beam's normalisation ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("phi0,theta0", [(0., 0.), (40., 30.), (200., 60.)])
+def test_direct_flux_through_horizontal_faces(oracle_lut, phi0, theta0):
+    """setup_incSolar puts edirTOA x dx x dy on the top faces (no cos, src/pprts_base.F90:1146-1181) and pprts_get_result
+    multiplies by mu (src/pprts.F90:5882-5887): the flux through a horizontal face at the top is S0 cos(theta); a vacuum
+    passes all of it down to the ground; absorbing 1-D layers follow Beer-Lambert along the slant path"""
+    mu = np.cos(np.deg2rad(theta0))
+    nz = 4
+    z = np.zeros((nz, 5, 5))
+    s = ob.OracleSolver(oracle_lut, nz, 5, 5, 100., 100., ob.sundir_from_angles(phi0, theta0), np.full(nz, 100.0),
+                        diff_solver=0, rtol=1e-8)
+    s.set_optical_properties(0.0, z, z, z)
+    assert s.solve(False, True, 1364.0) == 0
+    edir = s.get_result()[3]
+    s.destroy()
+    np.testing.assert_allclose(edir, 1364.0 * mu, rtol=1e-6)        # tau clamps to the table's 1e-10
+    s = ob.OracleSolver(oracle_lut, nz, 5, 5, 10., 10., ob.sundir_from_angles(phi0, theta0), np.full(nz, 100.0),
+                        diff_solver=0, rtol=1e-8)
+    assert s.l1d.all()
+    kabs = np.full((nz, 5, 5), 3e-3)
+    s.set_optical_properties(0.0, kabs, z, z)
+    assert s.solve(False, True, 1364.0) == 0
+    edir = s.get_result()[3]
+    s.destroy()
+    want = 1364.0 * mu * np.exp(-0.3 * np.arange(nz + 1) / mu)
+    np.testing.assert_allclose(edir, want[:, None, None] * np.ones((1, 5, 5)), rtol=1e-10)

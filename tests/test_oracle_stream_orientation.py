@@ -164,3 +164,30 @@ def test_direct_flux_through_horizontal_faces(oracle_lut, phi0, theta0):
     s.destroy()
     want = 1364.0 * mu * np.exp(-0.3 * np.arange(nz + 1) / mu)
     np.testing.assert_allclose(edir, want[:, None, None] * np.ones((1, 5, 5)), rtol=1e-10)
+
+
+def test_all_1d_layers_obey_the_twostream_statements(oracle_lut):
+    """tests/test_twostr/test_twostr.F90:54-59 for a pprts domain whose layers are all 1-D (dz / dx > twostr_ratio): the
+    beam at the ground is S0 exp(-tau / mu0) (x mu0 in pprts' flux through the horizontal face), nothing diffuse comes in at
+    the top, the ground reflects albedo x (direct + diffuse down); dtau = 1 / ke, w0 = g = 0.5, mu0 = 0.5, albedo = 0.1.
+    Delta scaling is switched off so that tau along the beam stays the optical depth of the test."""
+    ke, mu0, S0, albedo = 9, 0.5, 1e2, 0.1
+    dz = 100.0
+    s = ob.OracleSolver(oracle_lut, ke, 3, 3, 10., 10., ob.sundir_from_angles(0., 60.), np.full(ke, dz), diff_solver=0,
+                        rtol=1e-10)
+    assert s.l1d.all()
+    ext = (1.0 / ke) / dz
+    k = np.full((ke, 3, 3), 0.5 * ext)
+    s.set_optical_properties(albedo, k, k, np.full((ke, 3, 3), 0.5), ldelta_scaling=False)
+    assert s.solve(False, True, S0) == 0
+    edn, eup, abso, edir = s.get_result()
+    s.destroy()
+    assert edir[0, 1, 1] == pytest.approx(S0 * mu0, rel=1e-7)                            # float32-cast sun angle
+    assert edir[ke, 1, 1] == pytest.approx(S0 * mu0 * np.exp(-1.0 / mu0), rel=1e-6)
+    assert edn[0, 1, 1] == 0.0
+    assert eup[ke, 1, 1] == pytest.approx(albedo * (edir[ke, 1, 1] + edn[ke, 1, 1]), rel=1e-8)
+    # conservation: what enters at the top leaves at the top, is absorbed by the ground or by the layers.  Not to rounding:
+    # in 1-D layers calc_flx_div takes the beam's absorption as edir x (1 - exp(-kabs dz / mu0)) (src/pprts.F90:5305-5309)
+    # while the Eddington coefficients remove 1 - a33 - a13 - a23 from it; the two differ by a few 1e-4 here.
+    absorbed = (abso[:, 1, 1] * dz).sum() + (1 - albedo) * (edir[ke, 1, 1] + edn[ke, 1, 1])
+    assert edir[0, 1, 1] - eup[0, 1, 1] == pytest.approx(absorbed, rel=2e-3)

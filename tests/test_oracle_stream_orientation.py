@@ -191,3 +191,45 @@ def test_all_1d_layers_obey_the_twostream_statements(oracle_lut):
     # while the Eddington coefficients remove 1 - a33 - a13 - a23 from it; the two differ by a few 1e-4 here.
     absorbed = (abso[:, 1, 1] * dz).sum() + (1 - albedo) * (edir[ke, 1, 1] + edn[ke, 1, 1])
     assert edir[0, 1, 1] - eup[0, 1, 1] == pytest.approx(absorbed, rel=2e-3)
+
+
+# ---- 24 diffuse streams -----------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def lut324(tmp_path_factory):
+    from tenstream_b200 import lut as L
+    cfg = L.small_test_config(324)
+    paths = L.write_synthetic_lut(cfg, str(tmp_path_factory.mktemp("lut324o") / "LUT"))
+    return ob.OracleLut(cfg, paths)
+
+
+@pytest.mark.parametrize("phi0", sorted(CASES))
+def test_forward_scattered_light_leaves_downstream_24_streams(lut324, phi0):
+    """3_24 (src/boxmc_3_24.inc:36-120, src/pprts.F90:386-390): the side faces carry four angular quadrants each, [inward,
+    outward] per quadrant, sides start with an INWARD stream; 0-based 8 + 2 q + (0 towards +x | 1 towards -x) on x faces,
+    16 + ... on y faces, quadrants q = 2, 3 point downwards.  The 3_24 permutation (src/optprop.F90:1098-1124) has to send the
+    forward peak of the scattered beam into the downward streams that travel with the beam."""
+    axis, sign = CASES[phi0]
+    s = ob.OracleSolver(lut324, Nz, Nx, Ny, DX, DX, ob.sundir_from_angles(phi0, 60.0), np.full(Nz, DZ), solver_id=324,
+                        diff_solver=0, rtol=1e-8)
+    z = np.zeros((Nz, Nx, Ny))
+    ksca, g = z.copy(), z.copy()
+    ksca[K, I, J] = 1.0 / DZ
+    g[K, I, J] = 0.85
+    s.set_optical_properties(0.0, z, ksca, g)
+    assert s.solve(False, True, 1000.0) == 0
+    ediff = s.state(2)
+    s.destroy()
+    base = 8 if axis == "x" else 16
+    plus = [base + 4, base + 6]          # downward quadrants, travelling towards + (inward: leave through face index + 1)
+    minus = [base + 5, base + 7]         # ... towards - (leave through the cell's own low face)
+
+    def leaving(dofs, towards_plus):
+        if axis == "x":
+            return sum(ediff[d, K, I + 1 if towards_plus else I, J] for d in dofs)
+        return sum(ediff[d, K, I, J + 1 if towards_plus else J] for d in dofs)
+    down = leaving(plus, True) if sign > 0 else leaving(minus, False)
+    up = leaving(minus, False) if sign > 0 else leaving(plus, True)
+    assert down > 3.0 * up > 0, (phi0, down, up)
+    # upward quadrants (q = 0, 1) get the isotropic part only, the same on both sides
+    up_plus, up_minus = leaving([base + 0, base + 2], True), leaving([base + 1, base + 3], False)
+    assert up_plus == pytest.approx(up_minus, rel=1e-6) and up_plus < down

@@ -117,3 +117,59 @@ def test_header_is_c99_and_links_from_c(built_lib, tmp_path):
     subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(src), "-L", libdir, "-lpprts_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
+
+
+REF_C_WRAPPER = "/root/reference/c_wrapper"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_C_WRAPPER), reason="the reference checkout is not on this machine")
+@pytest.mark.parametrize("client", ["pprts.c", "opp.c"])
+def test_reference_c_clients_link_unchanged(built_lib, tmp_path, client):
+    """The drop-in claim of include/pprts_b200.h, layer 1: the reference's own C programs (c_wrapper/pprts.c, the host-model
+    example, and c_wrapper/opp.c, the coefficient probe) are compiled from where they lie, with the reference's own
+    headers (f2c_pprts.h, f2c_solver_ids.h), and linked against libpprts_b200.so instead of libf2c_pprts -- every symbol they
+    use must resolve.  MPI is not in this image: a four-function stub mpi.h stands in for it (the wrapper only passes the
+    communicator handle through).  Linked, not run (no device here)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    stub = tmp_path / "mpistub"
+    stub.mkdir()
+    (stub / "mpi.h").write_text(
+        "#ifndef MPI_STUB_H\n#define MPI_STUB_H\ntypedef int MPI_Comm;\n#define MPI_COMM_WORLD 0\n"
+        "static inline int MPI_Init(int *c, char ***v) { (void)c; (void)v; return 0; }\n"
+        "static inline int MPI_Finalize(void) { return 0; }\n"
+        "static inline int MPI_Comm_size(MPI_Comm c, int *n) { (void)c; *n = 1; return 0; }\n"
+        "static inline int MPI_Comm_rank(MPI_Comm c, int *r) { (void)c; *r = 0; return 0; }\n"
+        "static inline int MPI_Comm_c2f(MPI_Comm c) { return c; }\n#endif\n")
+    libdir = os.path.dirname(built_lib)
+    exe = tmp_path / client.replace(".c", "")
+    subprocess.check_call([cc, "-std=gnu99", "-I", str(stub), "-I", REF_C_WRAPPER, os.path.join(REF_C_WRAPPER, client),
+                           "-L", libdir, "-lpprts_b200", f"-Wl,-rpath,{libdir}", "-Wl,--no-undefined", "-lm", "-o", str(exe)])
+    undefined = subprocess.run(["nm", "-u", str(exe)], capture_output=True, text=True, check=True).stdout
+    used = sorted({ln.split()[-1] for ln in undefined.splitlines() if "pprts_f2c" in ln})
+    assert used, "the client calls no pprts_f2c_* symbol?"
+    exported = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    for sym in used:
+        assert f" T {sym}" in exported, sym
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_C_WRAPPER), reason="the reference checkout is not on this machine")
+def test_prototypes_agree_with_the_reference_header(tmp_path):
+    """One translation unit that sees the reference's c_wrapper/f2c_pprts.h AND include/pprts_b200.h: C rejects
+    incompatible redeclarations, so every pprts_f2c_* prototype has to agree in all argument types.  The one deliberate
+    difference is taken out: pprts_f2c_destroy takes its flag BY VALUE here, as the reference's implementation
+    (c_wrapper/f2c_pprts.F90:458-459) and its own caller (pprts.c:99, `pprts_f2c_destroy(0)`) do, while the reference's
+    header says int* (f2c_pprts.h:65)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "both.c"
+    src.write_text('#define pprts_f2c_destroy pprts_f2c_destroy_as_declared_by_the_reference\n'
+                   '#include <f2c_pprts.h>\n#undef pprts_f2c_destroy\n#include "pprts_b200.h"\nint main(void) { return 0; }\n')
+    subprocess.check_call([cc, "-std=gnu99", "-Werror", "-I", REF_C_WRAPPER, "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                           "-o", str(tmp_path / "both.o")])

@@ -123,7 +123,7 @@ REF_C_WRAPPER = "/root/reference/c_wrapper"
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_C_WRAPPER), reason="the reference checkout is not on this machine")
-@pytest.mark.parametrize("client", ["pprts.c", "opp.c"])
+@pytest.mark.parametrize("client", ["pprts.c", "opp.c", "set_global_optprop.c"])
 def test_reference_c_clients_link_unchanged(built_lib, tmp_path, client):
     """The drop-in claim of include/pprts_b200.h, layer 1: the reference's own C programs (c_wrapper/pprts.c, the host-model
     example, and c_wrapper/opp.c, the coefficient probe) are compiled from where they lie, with the reference's own

@@ -168,3 +168,93 @@ def pprts_get_result_toZero(api, solver, dec: CartDecomposition, opt_solution_ui
     global (Nz[+1], Nx, Ny) arrays -> (gedn, geup, gabso, gedir) there, four ``None`` elsewhere."""
     edn, eup, abso, edir = api.pprts_get_result(solver, opt_solution_uid)
     return tuple(gather_all_to_zero(a, dec) for a in (edn, eup, abso, edir))
+
+
+def gather_all_to_all(local, dec: CartDecomposition):
+    """``gather_all_to_all`` (src/pprts.F90:6361-6401): as ``gather_all_toZero`` but every rank ends up with the global
+    (nz, Nx, Ny) array (one allgather of the meta records, one of the blocks)."""
+    import torch
+    import torch.distributed as dist
+    a = np.ascontiguousarray(local, dtype=np.float64)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return a.copy()
+    meta = torch.tensor([dec.xs, dec.ys, dec.xm, dec.ym], dtype=torch.int64)
+    all_meta = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_meta, meta)
+    nz = a.shape[0]
+    nmax = max(int(m[2] * m[3]) for m in all_meta) * nz          # equal-sized slots (backends without allgatherv)
+    slot = torch.zeros(nmax, dtype=torch.float64)
+    slot[:a.size] = torch.from_numpy(a.reshape(-1))
+    slots = [torch.zeros(nmax, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(slots, slot)
+    Nx = max(int(m[0] + m[2]) for m in all_meta)
+    Ny = max(int(m[1] + m[3]) for m in all_meta)
+    out = np.zeros((nz, Nx, Ny))
+    for m, buf in zip(all_meta, slots):
+        xs, ys, xm, ym = (int(v) for v in m)
+        out[:, xs:xs + xm, ys:ys + ym] = buf[:nz * xm * ym].numpy().reshape(nz, xm, ym)
+    return out
+
+
+def extend_arr(arr, minimal_dimension: int = 3):
+    """``extend_arr`` of set_global_optical_properties (src/pprts.F90:2453-2483): a horizontal dimension of extent 1 is
+    replicated to the minimal 3 columns the periodic boundary conditions need; anything else below 3 is an error."""
+    a = np.asarray(arr)
+    if a.shape[1] == 1:
+        a = np.repeat(a, minimal_dimension, axis=1)
+    if a.shape[2] == 1:
+        a = np.repeat(a, minimal_dimension, axis=2)
+    if min(a.shape) < minimal_dimension:
+        raise ValueError("set_optprop -> extend_arr :: dimension is smaller than we support.. please think of something here")
+    return a
+
+
+def scatter_from_zero(global_arr, dec: CartDecomposition):
+    """``scatterZerotoPetscGlobal`` + ``petscVecToF90`` as set_global_optical_properties uses them
+    (src/pprts.F90:2397-2420): rank 0 holds the global (nz, Nx, Ny) array (``None`` elsewhere) and every rank receives
+    its (nz, xm, ym) block.  Host arrays over ``torch.distributed`` (any backend)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return np.array(dec.local(global_arr), dtype=np.float64, order="F")
+    rank = dist.get_rank()
+    meta = torch.tensor([dec.xs, dec.ys, dec.xm, dec.ym], dtype=torch.int64)
+    all_meta = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_meta, meta)
+    nz = torch.tensor([0 if global_arr is None else np.shape(global_arr)[0]], dtype=torch.int64)
+    dist.broadcast(nz, src=0)
+    nz = int(nz[0])
+    if rank == 0:
+        g = np.asarray(global_arr, dtype=np.float64)
+        for dst in range(1, world):
+            xs, ys, xm, ym = (int(v) for v in all_meta[dst])
+            dist.send(torch.from_numpy(np.ascontiguousarray(g[:, xs:xs + xm, ys:ys + ym])), dst=dst, tag=78)
+        return np.array(dec.local(g), dtype=np.float64, order="F")
+    buf = torch.empty((nz, dec.xm, dec.ym), dtype=torch.float64)
+    dist.recv(buf, src=0, tag=78)
+    return np.asfortranarray(buf.numpy())
+
+
+def set_global_optical_properties(api, solver, dec: CartDecomposition, global_albedo=None, global_kabs=None,
+                                  global_ksca=None, global_g=None, global_planck=None):
+    """``set_global_optical_properties`` (src/pprts.F90:2341-2451): rank 0 holds the optical properties of the whole
+    domain -- (Nz, Nx, Ny) resp. (Nz+1, Nx, Ny) for planck, ``None`` on the other ranks --, every rank receives its
+    block (which fields exist and the albedo are broadcast from rank 0, :2359-2362, :2393) and calls
+    ``set_optical_properties`` on it.  A horizontal dimension of extent 1 is replicated to 3 first (``extend_arr``)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    fields = [global_kabs, global_ksca, global_g, global_planck]
+    head = torch.tensor([float(f is not None) for f in fields] + [0.0 if global_albedo is None else float(global_albedo)],
+                        dtype=torch.float64)
+    if world > 1:
+        dist.broadcast(head, src=0)
+    have = [bool(v) for v in head[:4]]
+    if not all(have[:3]):
+        raise ValueError("set_global_optical_properties: kabs, ksca and g are required (set_optical_properties needs them)")
+    rank0 = world == 1 or dist.get_rank() == 0
+    local = [scatter_from_zero(extend_arr(f) if rank0 else None, dec) if h else None for f, h in zip(fields, have)]
+    api.set_optical_properties(solver, float(head[4]), local[0], local[1], local[2], planck=local[3])
+

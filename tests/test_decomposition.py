@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -90,3 +91,82 @@ def test_halo_fill_two_ranks_split_in_x():
 
 def test_halo_fill_two_ranks_split_in_y():
     _run(1, 2)
+
+
+# ---- set_global_optical_properties / gather_all_to_all (src/pprts.F90:2341-2451, :6361-6401) ----------------------------------
+class _RecordingApi:
+    """stands in for tenstream_b200.pprts: keeps what set_optical_properties was called with"""
+
+    def __init__(self):
+        self.calls = []
+
+    def set_optical_properties(self, solver, albedo, kabs, ksca, g, planck=None):
+        self.calls.append((solver, albedo, kabs, ksca, g, planck))
+
+
+def _worker_global_optprop(rank, world, port, nxp, nyp, q):
+    from tenstream_b200.parallel import gather_all_to_all, set_global_optical_properties
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Nz, Nx, Ny = 4, 7, 6
+    rng = np.random.default_rng(11)
+    gk, gs, gg = rng.random((Nz, Nx, Ny)), rng.random((Nz, Nx, Ny)), rng.random((Nz, Nx, Ny))
+    gp = rng.random((Nz + 1, Nx, Ny))
+    dec = CartDecomposition(Nx, Ny, nxp, nyp, rank)
+    api = _RecordingApi()
+    if rank == 0:      # only rank 0 holds the global fields (and the albedo), as in the reference
+        set_global_optical_properties(api, "solver", dec, 0.17, gk, gs, gg, gp)
+    else:
+        set_global_optical_properties(api, "solver", dec)
+    solver, albedo, k, s, g, p = api.calls[0]
+    ok = solver == "solver" and albedo == 0.17
+    for got, glob in ((k, gk), (s, gs), (g, gg), (p, gp)):
+        ok = ok and got.shape == (glob.shape[0], dec.xm, dec.ym) and bool(np.array_equal(got, dec.local(glob)))
+    api2 = _RecordingApi()   # without planck
+    if rank == 0:
+        set_global_optical_properties(api2, "solver", dec, 0.3, gk, gs, gg)
+    else:
+        set_global_optical_properties(api2, "solver", dec)
+    ok = ok and api2.calls[0][5] is None and api2.calls[0][1] == 0.3
+    full = gather_all_to_all(dec.local(gp), dec)           # every rank ends up with the global field
+    ok = ok and bool(np.array_equal(full, gp))
+    q.put((rank, ok, True))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nxp,nyp", [(2, 1), (1, 2)])
+def test_set_global_optical_properties_two_ranks(nxp, nyp):
+    world = nxp * nyp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_global_optprop, args=(r, world, port, nxp, nyp, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+
+
+def test_set_global_optical_properties_one_rank_and_extend_arr():
+    from tenstream_b200.parallel import extend_arr, gather_all_to_all, set_global_optical_properties
+    a = np.arange(4 * 1 * 5, dtype=float).reshape(4, 1, 5)
+    e = extend_arr(a)                                       # (Nz, 1, Ny) -> three identical columns (:2461-2468)
+    assert e.shape == (4, 3, 5) and all(np.array_equal(e[:, i], a[:, 0]) for i in range(3))
+    e = extend_arr(np.ones((4, 5, 1)))
+    assert e.shape == (4, 5, 3)
+    with pytest.raises(ValueError, match="smaller than we support"):
+        extend_arr(np.ones((4, 2, 5)))
+    api = _RecordingApi()
+    dec = CartDecomposition(3, 5, 1, 1, 0)
+    k = np.random.default_rng(0).random((4, 1, 5))
+    set_global_optical_properties(api, None, dec, 0.1, k, k, k)
+    assert api.calls[0][2].shape == (4, 3, 5) and api.calls[0][5] is None
+    assert np.array_equal(gather_all_to_all(k, dec), k)
+    with pytest.raises(ValueError, match="required"):
+        set_global_optical_properties(api, None, dec, 0.1, k, None, k)

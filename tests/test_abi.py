@@ -173,3 +173,94 @@ def test_prototypes_agree_with_the_reference_header(tmp_path):
                    '#include <f2c_pprts.h>\n#undef pprts_f2c_destroy\n#include "pprts_b200.h"\nint main(void) { return 0; }\n')
     subprocess.check_call([cc, "-std=gnu99", "-Werror", "-I", REF_C_WRAPPER, "-I", os.path.join(ROOT, "include"), "-c", str(src),
                            "-o", str(tmp_path / "both.o")])
+
+
+# ---- the three statements of the boundary's structs must stay in step ----------------------------------------------------------
+def _c_struct_fields(name):
+    """[(field, kind, count)] of a `typedef struct { ... } name;` in include/pprts_b200.h; kind in {int, double, ptr}"""
+    import re
+    txt = open(os.path.join(ROOT, "include", "pprts_b200.h")).read()
+    end = re.search(r"\}\s*" + name + r"\s*;", txt).start()
+    body = txt[txt.rfind("typedef struct {", 0, end) + len("typedef struct {"):end]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(const )?(int|double|float|long)\b(.*)", decl)
+        assert m, decl
+        base = m.group(2)
+        for item in m.group(3).split(","):
+            item = item.strip()
+            ptr = item.startswith("*")
+            item = item.lstrip("* ").replace("const ", "").strip()
+            am = re.match(r"(\w+)\[(\d+)\]", item)
+            fname, count = (am.group(1), int(am.group(2))) if am else (item, 1)
+            out.append((fname, "ptr" if ptr else base, count))
+    return out
+
+
+def _fortran_type_fields(name):
+    import re
+    txt = open(os.path.join(ROOT, "fortran", "m_pprts_b200.F90")).read()
+    body = re.search(r"type, bind\(c\) :: " + name + r"\n(.*?)\n\s*end type", txt, re.S | re.I).group(1)
+    body = re.sub(r"&\s*\n\s*&?", " ", body)
+    out = []
+    for line in body.splitlines():
+        line = line.split("!")[0].strip()
+        if not line:
+            continue
+        typ, names = line.split("::")
+        typ = typ.strip().lower().replace(" ", "")
+        kind = {"integer(c_int)": "int", "real(c_double)": "double", "type(c_ptr)": "ptr"}[typ]
+        for item in re.findall(r"\w+(?:\(\d+\))?", names):
+            am = re.match(r"(\w+)\((\d+)\)", item)
+            out.append((am.group(1), kind, int(am.group(2))) if am else (item, kind, 1))
+    return out
+
+
+def _ctypes_fields(struct):
+    import ctypes as C
+    out = []
+    for fname, typ in struct._fields_:
+        count = 1
+        if hasattr(typ, "_length_"):
+            count, typ = typ._length_, typ._type_
+        kind = {C.c_int: "int", C.c_double: "double", C.c_long: "long"}.get(typ, "ptr")
+        out.append((fname, kind, count))
+    return out
+
+
+def test_config_struct_is_the_same_in_c_fortran_and_python():
+    """pprts_b200_config crosses the boundary by reference: include/pprts_b200.h, the bind(C) type of the Fortran shim
+    and the ctypes mirror have to list the same fields, in the same order, with the same types -- a field added to one of
+    them only would shift everything behind it without any error"""
+    from tenstream_b200 import pprts as P
+    c = _c_struct_fields("pprts_b200_config")
+    low = lambda fields: [(n.lower(), k, cnt) for n, k, cnt in fields]      # noqa: E731  (Fortran is case-insensitive)
+    assert len(c) > 30
+    assert low(_fortran_type_fields("c_config")) == low(c)
+    assert _ctypes_fields(P._Config) == c
+    assert _ctypes_fields(P._Bands) == _c_struct_fields("pprts_b200_bands")
+
+
+def test_fortran_interfaces_match_the_header():
+    """every bind(C) interface of fortran/m_pprts_b200.F90 names a function include/pprts_b200.h declares and takes as many
+    arguments as its prototype (the shim cannot be compiled in this image, so at least its binding table is held to the
+    header)"""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "pprts_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(pprts_b200_\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.S):
+        args = " ".join(m.group(2).split())
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    f90 = open(os.path.join(ROOT, "fortran", "m_pprts_b200.F90")).read()
+    f90 = re.sub(r"&\s*\n\s*&?", " ", f90)
+    found = re.findall(r"function\s+\w+\s*\(([^)]*)\)\s*bind\(c,\s*name='(\w+)'\)", f90, re.I)
+    assert len(found) >= 20
+    for args, sym in found:
+        assert sym in protos, f"{sym} is bound in the Fortran shim but not declared in the header"
+        n = len([a for a in args.split(",") if a.strip()])
+        assert n == protos[sym], (sym, n, protos[sym])

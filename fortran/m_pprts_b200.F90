@@ -13,7 +13,7 @@ module m_pprts_b200
   private
   public :: t_solver_b200, t_lut_b200, lut_open, lut_close, init_pprts, set_angles, set_optical_properties, &
     & solve_pprts, pprts_get_result, destroy_pprts, t_pprts_buildings_b200, need_new_solution, slope_correction_fluxes, &
-    & smooth_surface_fluxes
+    & smooth_surface_fluxes, solve_bands, allreduce_accumulated, get_accumulated
 
   integer, parameter :: ireals = c_double, iintegers = c_int
 
@@ -47,6 +47,21 @@ module m_pprts_b200
     real(c_double) :: max_solution_err, max_solution_time
     integer(c_int) :: geometric_coeffs
     integer(c_int) :: accept_incomplete_solve, gmres_restart, max_cached_solutions, open_bc
+  end type
+
+  !> mirrors pprts_b200_bands (include/pprts_b200.h): the band loop of the spectral callers in one call
+  type, bind(c) :: c_bands
+    integer(c_int) :: nbands, lsolar, uid0, ldelta_scaling
+    real(c_double) :: albedo
+    type(c_ptr) :: albedo_2d
+    type(c_ptr) :: kabs, ksca, g
+    integer(c_long) :: stride_kabs, stride_ksca, stride_g
+    type(c_ptr) :: planck, planck_srfc
+    integer(c_long) :: stride_planck, stride_planck_srfc
+    type(c_ptr) :: edirTOA, weights
+    integer(c_int) :: accumulate_only
+    integer(c_int) :: have_time
+    real(c_double) :: time
   end type
 
   interface
@@ -164,6 +179,20 @@ module m_pprts_b200
     integer(c_int) function c_wait_results(solver) bind(c, name='pprts_b200_wait_results')
       import :: c_ptr, c_int
       type(c_ptr), value :: solver
+    end function
+    integer(c_int) function c_solve_bands(solver, bands, edn, eup, abso, edir, niter_diff) bind(c, name='pprts_b200_solve_bands')
+      import :: c_ptr, c_int, c_bands
+      type(c_ptr), value :: solver
+      type(c_bands), intent(in) :: bands
+      type(c_ptr), value :: edn, eup, abso, edir, niter_diff
+    end function
+    integer(c_int) function c_allreduce_accumulated(solver) bind(c, name='pprts_b200_allreduce_accumulated')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver
+    end function
+    integer(c_int) function c_get_accumulated(solver, edn, eup, abso, edir) bind(c, name='pprts_b200_get_accumulated')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: solver, edn, eup, abso, edir
     end function
     function c_last_error() bind(c, name='pprts_b200_last_error') result(msg)
       import; type(c_ptr) :: msg
@@ -387,6 +416,94 @@ contains
     real(ireals), intent(in), optional :: radius
     if (.not. present(radius)) return
     call chkerr(c_smooth_surface_fluxes(solver%h, real(radius, c_double), c_loc(edn), c_loc(eup)), 'smooth_surface_fluxes')
+  end subroutine
+
+  !> The band loop of the spectral callers (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053 solar, :621-708 thermal) in one call:
+  !> set_optical_properties -> solve_pprts -> pprts_get_result -> weighted sum for every band, the upload of band ib+1
+  !> overlapping the solve of band ib, the spectral sum kept on the device.  kabs / ksca / g: (Nz,Nx,Ny,nbands);
+  !> planck (Nz+1,Nx,Ny,nbands), planck_srfc (Nx,Ny,nbands) for thermal bands; edirTOA(nbands) for solar bands; weights
+  !> default to 1; uids are uid0 + ib - 1 (default: the reference's 1.. solar, 501.. thermal).  With opt_time, bands whose
+  !> stored solution is still good (need_new_solution) are not solved again (niter = -1).  The sums come back in
+  !> edn / eup / abso / edir if present; without them they stay in the device accumulator (bands sharded over several
+  !> processes: allreduce_accumulated, then get_accumulated).
+  subroutine solve_bands(solver, lsolar, albedo, kabs, ksca, g, planck, planck_srfc, edirTOA, weights, uid0, opt_time, &
+      & accumulate_only, edn, eup, abso, edir, niter)
+    type(t_solver_b200), intent(inout) :: solver
+    logical, intent(in) :: lsolar
+    real(ireals), intent(in) :: albedo
+    real(ireals), intent(in), contiguous, target :: kabs(:, :, :, :), ksca(:, :, :, :), g(:, :, :, :)
+    real(ireals), intent(in), contiguous, target, optional :: planck(:, :, :, :), planck_srfc(:, :, :)
+    real(ireals), intent(in), contiguous, target, optional :: edirTOA(:), weights(:)
+    integer(iintegers), intent(in), optional :: uid0
+    real(ireals), intent(in), optional :: opt_time
+    logical, intent(in), optional :: accumulate_only
+    real(ireals), allocatable, target, intent(inout), optional :: edn(:, :, :), eup(:, :, :), abso(:, :, :), edir(:, :, :)
+    integer(c_int), intent(out), contiguous, target, optional :: niter(:)
+    type(c_bands) :: b
+    type(c_ptr) :: pdn, pup, pab, pdi, pni
+
+    b%nbands = size(kabs, 4)
+    b%lsolar = merge(1, 0, lsolar)
+    b%uid0 = merge(1, 501, lsolar); if (present(uid0)) b%uid0 = uid0
+    b%ldelta_scaling = 1
+    b%albedo = albedo
+    b%albedo_2d = c_null_ptr
+    b%kabs = c_loc(kabs); b%ksca = c_loc(ksca); b%g = c_loc(g)
+    b%stride_kabs = size(kabs, kind=c_long) / b%nbands
+    b%stride_ksca = size(ksca, kind=c_long) / b%nbands
+    b%stride_g = size(g, kind=c_long) / b%nbands
+    b%planck = c_null_ptr; b%stride_planck = 0
+    if (present(planck)) then
+      b%planck = c_loc(planck); b%stride_planck = size(planck, kind=c_long) / b%nbands
+    end if
+    b%planck_srfc = c_null_ptr; b%stride_planck_srfc = 0
+    if (present(planck_srfc)) then
+      b%planck_srfc = c_loc(planck_srfc); b%stride_planck_srfc = size(planck_srfc, kind=c_long) / b%nbands
+    end if
+    b%edirTOA = c_null_ptr; if (present(edirTOA)) b%edirTOA = c_loc(edirTOA)
+    b%weights = c_null_ptr; if (present(weights)) b%weights = c_loc(weights)
+    b%accumulate_only = 0; if (present(accumulate_only)) b%accumulate_only = merge(1, 0, accumulate_only)
+    b%have_time = 0; b%time = 0
+    if (present(opt_time)) then
+      b%have_time = 1; b%time = opt_time
+    end if
+
+    pdn = c_null_ptr; pup = c_null_ptr; pab = c_null_ptr; pdi = c_null_ptr; pni = c_null_ptr
+    if (present(edn)) then
+      if (.not. allocated(edn)) allocate (edn(solver%Nz + 1, solver%Nx, solver%Ny))
+      pdn = c_loc(edn)
+    end if
+    if (present(eup)) then
+      if (.not. allocated(eup)) allocate (eup(solver%Nz + 1, solver%Nx, solver%Ny))
+      pup = c_loc(eup)
+    end if
+    if (present(abso)) then
+      if (.not. allocated(abso)) allocate (abso(solver%Nz, solver%Nx, solver%Ny))
+      pab = c_loc(abso)
+    end if
+    if (present(edir)) then
+      if (.not. allocated(edir)) allocate (edir(solver%Nz + 1, solver%Nx, solver%Ny))
+      pdi = c_loc(edir)
+    end if
+    if (present(niter)) pni = c_loc(niter)
+    call chkerr(c_solve_bands(solver%h, b, pdn, pup, pab, pdi, pni), 'solve_bands')
+  end subroutine
+
+  !> sum of the device accumulators over all processes (the final flux reduction of band sharding); needs comm_init
+  subroutine allreduce_accumulated(solver)
+    type(t_solver_b200), intent(inout) :: solver
+    call chkerr(c_allreduce_accumulated(solver%h), 'allreduce_accumulated')
+  end subroutine
+
+  !> the spectral sums held in the device accumulator -> host arrays (allocated if needed)
+  subroutine get_accumulated(solver, edn, eup, abso, edir)
+    type(t_solver_b200), intent(inout) :: solver
+    real(ireals), allocatable, target, intent(inout) :: edn(:, :, :), eup(:, :, :), abso(:, :, :), edir(:, :, :)
+    if (.not. allocated(edn)) allocate (edn(solver%Nz + 1, solver%Nx, solver%Ny))
+    if (.not. allocated(eup)) allocate (eup(solver%Nz + 1, solver%Nx, solver%Ny))
+    if (.not. allocated(abso)) allocate (abso(solver%Nz, solver%Nx, solver%Ny))
+    if (.not. allocated(edir)) allocate (edir(solver%Nz + 1, solver%Nx, solver%Ny))
+    call chkerr(c_get_accumulated(solver%h, c_loc(edn), c_loc(eup), c_loc(abso), c_loc(edir)), 'get_accumulated')
   end subroutine
 
   subroutine destroy_pprts(solver, lfinalizepetsc)

@@ -213,7 +213,7 @@ def _fortran_type_fields(name):
             continue
         typ, names = line.split("::")
         typ = typ.strip().lower().replace(" ", "")
-        kind = {"integer(c_int)": "int", "real(c_double)": "double", "type(c_ptr)": "ptr"}[typ]
+        kind = {"integer(c_int)": "int", "integer(c_long)": "long", "real(c_double)": "double", "type(c_ptr)": "ptr"}[typ]
         for item in re.findall(r"\w+(?:\(\d+\))?", names):
             am = re.match(r"(\w+)\((\d+)\)", item)
             out.append((am.group(1), kind, int(am.group(2))) if am else (item, kind, 1))
@@ -242,7 +242,9 @@ def test_config_struct_is_the_same_in_c_fortran_and_python():
     assert len(c) > 30
     assert low(_fortran_type_fields("c_config")) == low(c)
     assert _ctypes_fields(P._Config) == c
-    assert _ctypes_fields(P._Bands) == _c_struct_fields("pprts_b200_bands")
+    bands = _c_struct_fields("pprts_b200_bands")
+    assert _ctypes_fields(P._Bands) == bands
+    assert low(_fortran_type_fields("c_bands")) == low(bands)
 
 
 def test_fortran_interfaces_match_the_header():

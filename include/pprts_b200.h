@@ -59,7 +59,8 @@ void pprts_f2c_opp_get_info(void *opp, int *Ndir, int *Ndiff, float *diff_tauz_r
                             float *dir_phi_range, float *dir_theta_range, int *ierr);
 
 /* Not in the reference: register an already opened table set for the module-level solver of the pprts_f2c_* layer
- * (tests use reduced parameter spaces), and replace the "print + abort" of CHKERR by a callback. */
+ * (tests use reduced parameter spaces; the reference always loads `-lut_basename`, src/tenstream_options.F90:108-110),
+ * and replace the "print + abort" of CHKERR (src/helper_functions.fypp:888-906) by a callback. */
 struct pprts_b200_lut;
 void pprts_b200_f2c_set_lut(struct pprts_b200_lut *lut);
 void pprts_b200_f2c_set_abort_handler(void (*handler)(const char *message));
@@ -173,14 +174,16 @@ int pprts_b200_get_solution_times(pprts_b200_solver *solver, int uid, double tim
 int pprts_b200_get_result(pprts_b200_solver *solver, int uid, double *edn, double *eup, double *abso,
                           double *edir);
 
-/* Device-resident variants used for throughput measurement with inputs already in HBM: stage() uploads a set of
- * optical properties into slot (untimed), set_optical_properties_staged() consumes it on the device, and
- * compute_result_device() runs the result reduction without the device->host copy. */
+/* set_optical_properties (src/pprts.F90:1764-2076) split into its host->device copy and its device part, and
+ * pprts_get_result (src/pprts.F90:5799-5917) without the device->host copy -- used for throughput measurement with inputs
+ * already in HBM: stage() uploads a set of optical properties into slot (untimed), set_optical_properties_staged()
+ * consumes it on the device, and compute_result_device() runs the result reduction only. */
 int pprts_b200_stage_optical_properties(pprts_b200_solver *solver, int slot, double albedo, const double *kabs,
                                         const double *ksca, const double *g, const double *planck,
                                         const double *planck_srfc, const double *albedo_2d);
 int pprts_b200_set_optical_properties_staged(pprts_b200_solver *solver, int slot, int ldelta_scaling);
-/* Overlapped host transfers for a caller's own band loop (what pprts_b200_solve_bands does internally):
+/* Overlapped host transfers for a caller's own band loop (rrtmg/rrtmg/pprts_rrtmg.F90:999-1053; what
+ * pprts_b200_solve_bands does internally), the same two reference routines with their copies made asynchronous:
  * stage_optical_properties_async only ENQUEUES the upload of the next band on a copy stream (the host arrays must stay
  * valid, and should be page-locked, until set_optical_properties_staged(slot) has consumed them); get_result_async
  * returns once the result is on its way to the host arrays, which are complete after wait_results. */
@@ -193,7 +196,8 @@ int pprts_b200_wait_results(pprts_b200_solver *solver);
 int pprts_b200_compute_result_device(pprts_b200_solver *solver, int uid);
 int pprts_b200_synchronize(pprts_b200_solver *solver);
 
-/* spectral accumulation for band sharding: acc += weight * result(uid) on the device; read back once */
+/* spectral accumulation for band sharding: acc += weight * result(uid) on the device, read back once -- the sum the
+ * callers keep on the host after every pprts_get_result (rrtmg/rrtmg/pprts_rrtmg.F90:1048-1051, :702-706) */
 int pprts_b200_accumulate_result(pprts_b200_solver *solver, int uid, double weight);
 int pprts_b200_reset_accumulator(pprts_b200_solver *solver);
 int pprts_b200_get_accumulated(pprts_b200_solver *solver, double *edn, double *eup, double *abso, double *edir);
@@ -227,16 +231,19 @@ typedef struct {
   int have_time;
   double time;
 } pprts_b200_bands;
-/* edn/eup/edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny): spectral sums, any may be NULL (NULL for all four leaves the sums in the
- * device accumulator for pprts_b200_allreduce_accumulated / pprts_b200_get_accumulated); niter_diff (nbands) or NULL */
+/* the loop rrtmg/rrtmg/pprts_rrtmg.F90:999-1053 / :621-708 itself.  edn/eup/edir (Nz+1,Nx,Ny), abso (Nz,Nx,Ny): spectral
+ * sums, any may be NULL (NULL for all four leaves the sums in the device accumulator for
+ * pprts_b200_allreduce_accumulated / pprts_b200_get_accumulated); niter_diff (nbands) or NULL */
 int pprts_b200_solve_bands(pprts_b200_solver *solver, const pprts_b200_bands *bands, double *edn, double *eup,
                            double *abso, double *edir, int *niter_diff);
 
-/* NCCL plumbing (one process per GPU). The unique id is produced on rank 0 and distributed by the caller
- * (MPI_Bcast in a Fortran host, torch.distributed in the tests). */
+/* NCCL plumbing (one process per GPU), in place of the MPI communicator and the DMDA of init_pprts
+ * (setup_grid / setup_coord_native, src/pprts_base.F90:721-828): the unique id is produced on rank 0 and distributed
+ * by the caller (MPI_Bcast in a Fortran host, torch.distributed in the tests). */
 int pprts_b200_nccl_unique_id(char id[128]);
 int pprts_b200_comm_init(pprts_b200_solver *solver, int nranks, int rank, const char id[128]);
-/* sum of the accumulated spectral integrals over all ranks (final flux / heating-rate reduction) */
+/* sum of the accumulated spectral integrals over all ranks (final flux / heating-rate reduction): with the bands sharded
+ * over the processes this completes the callers' host-side sum (rrtmg/rrtmg/pprts_rrtmg.F90:1048-1051) */
 int pprts_b200_allreduce_accumulated(pprts_b200_solver *solver);
 
 /* slope_correction_fluxes(solver, edir) (src/pprts_postprocess.F90:130-196), the spectral callers' post-processing of
@@ -244,7 +251,8 @@ int pprts_b200_allreduce_accumulated(pprts_b200_solver *solver);
  * sundir.ez), n the surface normal from hgrad, src/pprts.F90:621-638), latm = -pprts_atm_correction (every level x
  * sundir.ez / sundir.n).  edir: host (Nz+1,Nx,Ny) column-major, in place.  Needs dz3d; single periodic domain. */
 int pprts_b200_slope_correction_fluxes(pprts_b200_solver *solver, int lslope, int latm, double *edir);
-/* the same applied to the direct flux of the device-side spectral sum (before pprts_b200_get_accumulated) */
+/* the same applied to the direct flux of the device-side spectral sum (before pprts_b200_get_accumulated), where the
+ * callers apply it: after the band sum (rrtmg/rrtmg/pprts_rrtmg.F90:320) */
 int pprts_b200_slope_correct_accumulated(pprts_b200_solver *solver, int lslope, int latm);
 
 /* smooth_surface_fluxes(solver, edn, eup) (src/pprts_postprocess.F90:44-84), the callers' post-processing of the diffuse
@@ -256,7 +264,8 @@ int pprts_b200_slope_correct_accumulated(pprts_b200_solver *solver, int lslope, 
 int pprts_b200_find_iter_and_kernelwidth(double radius, double dx, double dy, int xm, int ym, int *Niter,
                                          int *kernel_width);
 int pprts_b200_smooth_surface_fluxes(pprts_b200_solver *solver, double radius, double *edn, double *eup);
-/* the same applied to edn / eup of the device-side spectral sum (before pprts_b200_get_accumulated) */
+/* the same applied to edn / eup of the device-side spectral sum (before pprts_b200_get_accumulated), where the callers
+ * apply it: after the band sum (rrtmg/rrtmg/pprts_rrtmg.F90:319) */
 int pprts_b200_smooth_accumulated(pprts_b200_solver *solver, double radius);
 
 /* ---- buildings: the opt_buildings argument of solve_pprts / pprts_get_result ------------------------------------
@@ -269,8 +278,9 @@ int pprts_b200_smooth_accumulated(pprts_b200_solver *solver, double radius);
  * removes it.  Periodic single-GPU domains only (error 60 on a decomposed solver). */
 int pprts_b200_set_buildings(pprts_b200_solver *solver, int nfaces, const int *iface, const double *albedo,
                              const double *planck);
-/* per face, W/m2: direct flux on the face (0 for thermal solutions; may be NULL), diffuse flux entering the building
- * through it (incoming) and leaving it (outgoing) */
+/* fill_buildings_arr of pprts_get_result(opt_buildings) (src/pprts.F90:6011-6160).  Per face, W/m2: direct flux on the
+ * face (0 for thermal solutions; may be NULL), diffuse flux entering the building through it (incoming) and leaving it
+ * (outgoing) */
 int pprts_b200_get_buildings_result(pprts_b200_solver *solver, int uid, double *edir, double *incoming,
                                     double *outgoing);
 
@@ -280,7 +290,10 @@ int pprts_b200_get_buildings_result(pprts_b200_solver *solver, int uid, double *
  * reference does. */
 int pprts_b200_set_abso_in_buildings(pprts_b200_solver *solver, int uid, double val);
 
-/* introspection (parity tests, profiling) */
+/* introspection (parity tests, profiling): the members of t_solver the reference's own tests read -- solver%dir2dir /
+ * dir2diff / diff2diff (src/pprts_base.F90:92-268), solutions(uid)%edir / ediff / abso, solver%b, the iteration counts and
+ * residuals of the KSP history (src/pprts.F90:4206-4303) -- and the matrix-free operator op_mat_mult_ediff
+ * (src/pprts_shell.F90:366-541) applied to a host vector */
 /* which: 1 dir2dir, 2 dir2diff, 3 diff2diff -> out (ncoef, Nz, Nx, Ny) column-major, zeros in 1-D layers */
 int pprts_b200_get_coeffs(pprts_b200_solver *solver, int which, double *out);
 /* which: 1 edir (Nd,Nz+1,Nx,Ny), 2 ediff (Nf,Nz+1,Nx,Ny), 3 abso (Nz,Nx,Ny), 4 b (Nf,Nz+1,Nx,Ny); W/m2 resp. W */
@@ -293,7 +306,8 @@ int pprts_b200_mat_mult_ediff(pprts_b200_solver *solver, const double *x, double
  * out (ncoef, n) column-major */
 int pprts_b200_lookup_coeffs(pprts_b200_solver *solver, int mode, long n, const double *kabs, const double *ksca,
                              const double *g, const double *dz, double *out);
-/* counters: kernels launched by this library since creation, and the ids of the last timed kernels */
+/* counters: kernels launched by this library since creation, and the ids of the last timed kernels (the role of the
+ * reference's PETSc log stages, t_solver_log_events, src/pprts_base.F90:176-200) */
 long pprts_b200_kernel_launches(pprts_b200_solver *solver);
 /* the cudaStream_t every kernel of this solver is launched on (to record timing events on the launching stream) */
 void *pprts_b200_stream(pprts_b200_solver *solver);

@@ -233,3 +233,26 @@ def test_forward_scattered_light_leaves_downstream_24_streams(lut324, phi0):
     # upward quadrants (q = 0, 1) get the isotropic part only, the same on both sides
     up_plus, up_minus = leaving([base + 0, base + 2], True), leaving([base + 1, base + 3], False)
     assert up_plus == pytest.approx(up_minus, rel=1e-6) and up_plus < down
+
+
+# ---- the ground -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver_id", [310, 810, 324])
+def test_ground_reflects_albedo_times_what_arrives(oracle_lut, lut810, lut324, solver_id):
+    """the surface rows of the diffuse operator (src/pprts_shell.F90:500-505) and of the solar source (src/pprts.F90:4830-4842):
+    per column, what goes up at the ground is albedo x (direct + diffuse down), also with a 2-D albedo and whatever the
+    number of streams the upward flux is spread over"""
+    lut = {310: oracle_lut, 810: lut810, 324: lut324}[solver_id]
+    rng = np.random.default_rng(3)
+    nz, nx, ny = 4, 5, 6
+    s = ob.OracleSolver(lut, nz, nx, ny, 100., 100., ob.sundir_from_angles(150., 40.), np.full(nz, 100.0),
+                        solver_id=solver_id, diff_solver=0, rtol=1e-10)
+    kabs = rng.uniform(1e-4, 1e-3, (nz, nx, ny))
+    ksca = rng.uniform(1e-3, 1e-2, (nz, nx, ny))
+    g = rng.uniform(0.0, 0.5, (nz, nx, ny))
+    a2d = rng.uniform(0.05, 0.6, (nx, ny))
+    s.set_optical_properties(0.3, kabs, ksca, g, albedo_2d=a2d)
+    assert s.solve(False, True, 1000.0) == 0
+    edn, eup, abso, edir = s.get_result()
+    s.destroy()
+    np.testing.assert_allclose(eup[nz], a2d * (edir[nz] + edn[nz]), rtol=1e-7)
+    assert edn[0].max() == 0.0 and eup[0].min() > 0.0

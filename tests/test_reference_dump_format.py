@@ -87,3 +87,24 @@ def test_stand_in_producer(tmp_path, small_lut, solar):
         np.testing.assert_array_equal(a, b)
     assert got[0].shape == (c["Nz"] + 1, c["Nx"], c["Ny"]) and got[2].shape == (c["Nz"], c["Nx"], c["Ny"])
     assert np.abs(got[1]).max() > 0 and (np.abs(got[3]).max() > 0) == solar
+
+
+def test_make_cases_writes_what_it_promises(tmp_path, small_lut):
+    """tools/reference_dump/make_cases.py: the case files parse, cover the three stream layouts, a thermal band and 1-D
+    layers, and the stand-in producer solves the 3_10 ones (configs[0] at full size included)"""
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reference_dump", "make_cases.py"), str(tmp_path)], check=True)
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".case"))
+    assert len(files) == 6
+    cases = {f[:-5]: casefile.read_case(str(tmp_path / f)) for f in files}
+    assert {c["solver_id"] for c in cases.values()} == {310, 810, 324}
+    c1 = cases["c1_box_cloud"]
+    assert (c1["Nz"], c1["Nx"], c1["Ny"]) == (40, 32, 32) and c1["lsolar"] and c1["planck"] is None
+    assert cases["small_thermal"]["lthermal"] and cases["small_thermal"]["planck"] is not None
+    d1 = cases["small_solar_1d_layers"]
+    assert (d1["dz1d"][:4] / d1["dx"] > 2.0).all() and (d1["dz1d"][4:] / d1["dx"] <= 2.0).all()
+    cfg, paths = small_lut
+    for name, c in cases.items():
+        if c["solver_id"] != 310:
+            continue
+        edn, eup, abso, edir = oracle_dump.solve_case(c, cfg, paths)
+        assert np.isfinite(edn).all() and eup.max() > 0 and (edir.max() > 0) == c["lsolar"], name

@@ -1,5 +1,5 @@
-"""Case files for tools/reference_dump/ex_pprts_dump: BASELINE configs[0] (box cloud 32x32x40) and three small cases
-(sun in another quadrant, a thermal band, 1-D layers on top).
+"""Case files for tools/reference_dump/ex_pprts_dump: BASELINE configs[0] (box cloud 32x32x40) and five small cases
+(sun in another quadrant, a thermal band, the 8_10 and 3_24 stream layouts, 1-D layers on top).
 
     python tools/reference_dump/make_cases.py <output directory>"""
 import os
@@ -32,6 +32,9 @@ def cases():
     yield "small_solar_phi200", dict(base, sundir=sundir(200., 40.), dz1d=sm["dz1d"], lsolar=True, lthermal=False, edirTOA=1000.)
     planck = np.linspace(60., 130., sm["Nz"] + 1)[:, None, None] * np.ones((1, sm["Nx"], sm["Ny"]))
     yield "small_thermal", dict(base, sundir=sundir(0., 0.), dz1d=sm["dz1d"], lsolar=False, lthermal=True, edirTOA=0., planck=planck)
+    for sid in (810, 324):      # the other stream layouts (BASELINE configs[4]); 8_10 / 3_24 tables of the reference needed
+        yield f"small_solar_{sid}", dict(base, solver_id=sid, sundir=sundir(300., 35.), dz1d=sm["dz1d"], lsolar=True,
+                                         lthermal=False, edirTOA=1000.)
     dz = sm["dz1d"].copy()
     dz[:4] = 600.0        # dz / dx = 3 > twostr_ratio: the four top layers are 1-D (determine_1d_layers)
     yield "small_solar_1d_layers", dict(base, sundir=sundir(120., 55.), dz1d=dz, lsolar=True, lthermal=False, edirTOA=1364.)

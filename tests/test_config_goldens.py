@@ -42,6 +42,30 @@ def test_fixture_is_complete_and_physical(golden):
         assert abs((net[0] - net[-1]) - absorbed) < 1e-6 * net[0]
 
 
+def test_fixture_obeys_the_conservation_laws_layer_by_layer(golden):
+    """What the committed full-size results must obey whatever produced them (periodic domain, horizontal means): the flux
+    through the top is S0 cos(theta) and nothing diffuse comes in; the ground returns albedo x what arrives (uniform albedo);
+    in EVERY layer the divergence of the net flux is the absorbed (thermal: absorbed - emitted) power, solar and thermal --
+    the table conserves energy per source stream, so absorption by coefficient divergence and by flux divergence coincide at
+    convergence (src/pprts.F90:5286-5398 vs :5400-5503)."""
+    from tenstream_b200 import scenarios
+    for case, bands in (("c1", ["solar"]), ("c2", ["solar", "thermal"])):
+        sc, bdefs = scenarios.config_case(case)
+        dz = sc["dz1d"]
+        for band, bd in zip(bands, bdefs):
+            g = lambda nm: golden[f"{case}/{band}/{nm}_mean"]      # noqa: E731
+            edn, eup, abso = g("edn"), g("eup"), g("abso")
+            edir = g("edir") if band == "solar" else np.zeros_like(edn)
+            scale = max(edn.max(), eup.max(), edir.max())
+            assert edn[0] == 0.0
+            if band == "solar":
+                mu = np.cos(np.deg2rad(sc["theta0"]))
+                assert edir[0] == pytest.approx(bd["edirTOA"] * mu, rel=1e-7)
+                assert eup[-1] == pytest.approx(bd["albedo"] * (edir[-1] + edn[-1]), rel=1e-8)
+            net = edir + edn - eup
+            np.testing.assert_allclose(net[:-1] - net[1:], abso * dz, atol=1e-9 * scale, rtol=0)   # measured: 5e-11
+
+
 def test_oracle_reproduces_c1_golden(golden, tmp_path):
     out = {}
     mg.run_config("c1", str(tmp_path), out)

@@ -443,6 +443,7 @@ contains
     type(c_ptr) :: pdn, pup, pab, pdi, pni
 
     b%nbands = size(kabs, 4)
+    if (b%nbands .eq. 0) return  ! a process without bands of this kind (more processes than bands)
     b%lsolar = merge(1, 0, lsolar)
     b%uid0 = merge(1, 501, lsolar); if (present(uid0)) b%uid0 = uid0
     b%ldelta_scaling = 1

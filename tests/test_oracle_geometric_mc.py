@@ -110,3 +110,24 @@ def test_geometric_coeffs_vs_monte_carlo(case):
     assert np.abs(got - want).max() < 0.01, (got, want)               # 1 % of a unit coefficient; MC noise is ~1e-3
     for src in range(3):                                              # what does not leave is absorbed: never more than came in
         assert got[src::3].sum() <= 1.0 + 1e-12
+
+
+@pytest.mark.parametrize("case", CASES_NOT_PARALLEL)
+def test_deviation_grows_smoothly_with_the_angle_between_the_planes(case):
+    """The same boxes with the top plane turned from parallel to the bottom (eps = 0) to its full tilt (eps = 1): the
+    distance to the ray tracer starts below the Monte-Carlo noise and grows steadily, about linearly, with the angle between
+    the planes -- the signature of an approximation in the construction (one displaced vertex, one path length), not of a
+    wrong branch, which would show up as a jump."""
+    dx, dy, dz, sb, st, phi, theta, tau = case
+    sd = ob.sundir_from_angles(phi, theta) * FLIP
+    c_ext = max(tau / dz, np.finfo(np.float64).tiny)
+    errs = []
+    for eps in (0.0, 0.25, 0.5, 1.0):
+        top = (sb[0] + eps * (st[0] - sb[0]), sb[1] + eps * (st[1] - sb[1]))
+        verts = box(dx, dy, dz, sb, top)
+        got = ob.dir2dir3_geometric_coeffs(verts, sd, c_ext)
+        want = mc_coeffs(verts, sd / np.linalg.norm(sd), c_ext, n=300_000)
+        errs.append(np.abs(got - want).max())
+    assert errs[0] < 3e-3
+    assert errs[0] < errs[1] < errs[2] < errs[3]
+    assert 0.25 * errs[3] < errs[2] < 0.75 * errs[3] and 0.1 * errs[3] < errs[1] < 0.45 * errs[3]
